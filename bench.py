@@ -1,0 +1,382 @@
+#!/usr/bin/env python
+"""bench.py — BASELINE.json's metric on BASELINE.json's configuration.
+
+Headline line (one JSON object on stdout, rank 0): config C2 = the long fused elementwise chain
+`out = tanh(log(exp(a*b+c)+a)*b)+c` on 2^28 float32 elements per GPU, inputs `random([16384,16384], seed 1,2,3)`
+(Wang-hash uniform, Tensors.scala:432-443), evaluated through the lazy Tensor API -> C ABI -> one JIT-compiled sm_100a
+kernel per step.  `value` = algorithmic bytes (16 B/element) / device time with inputs resident in HBM;
+`e2e` = the same metric through the same API with HOST buffers (pinned), H2D of the three inputs and D2H of the result
+inside the timed region.  Other configs (C1, C3, C4, C5) are measured briefly and reported under "configs".
+
+    python bench.py --gpus 1 --steps 20 --warmup 3
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...      (one rank per GPU, weak scaling)
+    python bench.py --impl reference        (CPU port of the reference's generated kernel on the host cores)
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+ROWS, COLS = 16384, 16384
+BYTES_PER_ELEMENT = 16  # 3 reads + 1 write of fp32
+METRIC = "fused elementwise HBM GB/s (C2 chain, 2^28 fp32 elements per GPU)"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d, "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.rows = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+
+    def summary(self, t0: float, t1: float) -> dict:
+        rows = [r for t, r in self.rows if t0 - 0.05 <= t <= t1 + 0.15 and len(r) >= 7] or [r for _, r in self.rows if len(r) >= 7]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+        sm = sorted(float(r[0]) for r in rows)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith("active") for r in rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][1]), "reasons": reasons, "samples": len(rows),
+                "power_w_max": max(float(r[2]) for r in rows)}
+
+
+def c2_chain(T, a, b, c):
+    t = a * b + c
+    u = T.exp(t)
+    v = T.log(u + a)
+    w = T.tanh(v * b)
+    return w + c
+
+
+# ---- reference arm: the CPU port of the generated kernel on the host cores -----------------------------------------------
+
+
+def cpu_c2(sample_elems: int, reps: int):
+    from oracle import build as ob
+
+    ob.build()
+    L = ob.load("fma")
+    n = sample_elems
+    a, b, c, out = (np.empty(n, np.float32) for _ in range(4))
+    for arr, seed in ((a, 1), (b, 2), (c, 3)):
+        L.oracle_random(arr.ctypes.data, n, seed)
+    L.oracle_c2(a.ctypes.data, b.ctypes.data, c.ctypes.data, out.ctypes.data, n)  # warm-up (page faults, libm)
+    times = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        L.oracle_c2(a.ctypes.data, b.ctypes.data, c.ctypes.data, out.ctypes.data, n)
+        times.append(time.perf_counter() - t0)
+    return times, int(L.oracle_num_threads()), out
+
+
+def run_reference(args, rank: int):
+    if rank != 0:
+        return
+    n = 1 << 26
+    # each step = one pass of the generated kernel over a 2^26-element sample (1/4 of the per-GPU workload)
+    times, cores, _ = cpu_c2(n, args.warmup + args.steps)
+    times = times[args.warmup:]
+    sec = sum(times) / len(times)
+    gbs = BYTES_PER_ELEMENT * n / sec / 1e9
+    line = {
+        "impl": "reference", "metric": METRIC, "value": gbs, "unit": "GB/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "C2 long fused elementwise chain tanh(log(exp(a*b+c)+a)*b)+c", "elements_per_step": n,
+                   "note": "the reference (Scala + OpenCL/POCL) cannot run in this image (no JVM, no OpenCL ICD); this is the C/OpenMP port "
+                           "of the kernel it generates (oracle/oracle_cpu.c), all host threads"},
+        "cpu_baseline": {"value": gbs, "unit": "GB/s", "cores": cores, "kind": "port", "sample": f"2^26 of 2^28 elements per step, {len(times)} steps"},
+        "e2e": {"value": gbs, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---- cuda arm ---------------------------------------------------------------------------------------------------------------------
+
+
+def time_steps(cuda, fn, steps: int, warmup: int):
+    for _ in range(warmup):
+        fn()
+    cuda.synchronize()
+    s0 = cuda.stats()
+    cuda.timer_start()
+    w0 = time.time()
+    for _ in range(steps):
+        fn()
+    ms = cuda.timer_stop()
+    w1 = time.time()
+    s1 = cuda.stats()
+    return ms, s1["device_kernels"] - s0["device_kernels"], w0, w1
+
+
+def side_configs(cuda, hbm_peak: float, tf_peak: float) -> dict:
+    """C1, C3, C4 (and C5 when the contraction is built) — short device-resident measurements for the same JSON line"""
+    T = cuda.Tensor
+    out = {}
+
+    def measure(name, build, alg_bytes, steps=10, flops=None):
+        try:
+            expr = build()
+            k = expr.compile()
+            kind = k.info.kind
+            k.release()
+
+            def step():
+                expr.doBuffer().release()
+
+            ms, launches, _, _ = time_steps(cuda, step, steps, 3)
+            per = ms / steps
+            rec = {"ms": per, "kernels_per_step": launches / steps, "plan": kind}
+            if flops:
+                rec["tflops"] = flops / per / 1e9
+                rec["frac_of_3xtf32_peak"] = rec["tflops"] / tf_peak
+            else:
+                rec["gbs"] = alg_bytes / per / 1e6
+                rec["frac_of_hbm"] = rec["gbs"] / hbm_peak
+            out[name] = rec
+        except Exception as e:  # a side measurement must not take the headline down
+            out[name] = {"error": str(e)[:200]}
+
+    n1 = 1024
+    a1, b1, c1 = (T.random([n1, n1], seed=s).doCache() for s in (1, 2, 3))
+    measure("C1 tanh(a*b+c) 1024^2", lambda: T.tanh(a1 * b1 + c1), 16 * n1 * n1, steps=50)
+    del a1, b1, c1
+    x = T.random([ROWS, COLS], seed=5).doCache()
+    measure("C3 full sum 16384^2", lambda: x.sum(), 4 * ROWS * COLS + 4)
+
+    def axis(ax):
+        parts = x.split(ax)
+        acc = parts[0]
+        for p in parts[1:]:
+            acc = acc + p
+        return acc
+
+    measure("C3 axis-0 sum 16384^2", lambda: axis(0), 4 * ROWS * COLS + 4 * COLS)
+    measure("C3 axis-1 sum 16384^2", lambda: axis(1), 4 * ROWS * COLS + 4 * ROWS)
+    del x
+    n4 = 512
+    t4 = T.random([n4, n4, n4], seed=7).doCache()
+    m4 = T.random([n4, n4], seed=8).doCache()
+    measure("C4 permute(2,0,1)+translate 512^3", lambda: t4.permute([2, 0, 1]).translate([3, -5, 7]), 8 * n4**3)
+    measure("C4 trailing broadcast 512^2->512^3", lambda: m4.broadcast([n4, n4, n4]), 4 * n4**2 + 4 * n4**3)
+    measure("C4 leading broadcast 512^2->512^3", lambda: m4.reshape([1, n4, n4]).broadcast([n4, n4, n4]), 4 * n4**2 + 4 * n4**3)
+    measure("C4 split(1)/join round trip 512^3", lambda: T.join(t4.split(1)), 8 * n4**3)
+    del t4, m4
+    n5 = 8192
+    try:
+        A, B = T.randomNormal([n5, n5], seed=9).doCache(), T.randomNormal([n5, n5], seed=10).doCache()
+        ab, bb, c5 = A.doBuffer(), B.doBuffer(), cuda.Buffer.alloc(n5 * n5)
+
+        def step():
+            cuda.matmul_3xtf32(ab, bb, c5, n5, n5, n5)
+
+        ms, launches, _, _ = time_steps(cuda, step, 5, 2)
+        per = ms / 5
+        tf = 2 * n5**3 / per / 1e9
+        out["C5 matmul 8192^3 (3xTF32 tcgen05)"] = {"ms": per, "tflops": tf, "frac_of_3xtf32_peak": tf / tf_peak, "kernels_per_step": launches / 5}
+        ab.release(), bb.release(), c5.release()
+    except Exception as e:
+        out["C5 matmul 8192^3 (3xTF32 tcgen05)"] = {"error": str(e)[:200]}
+    return out
+
+
+def run_cuda(args, rank: int, local_rank: int, world: int):
+    from compute.scala_b200 import cuda
+
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist_mod
+
+        torch.cuda.set_device(local_rank)
+        dist_mod.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist = dist_mod
+    cuda.init(local_rank, streams=1)
+    T = cuda.Tensor
+    pk, pk_kind = peaks()
+    hbm_peak = float(pk["hbm_gbs"])
+    rows = args.rows
+    n = rows * COLS
+    shape = [rows, COLS]
+    alg_bytes = BYTES_PER_ELEMENT * n
+
+    # weak scaling: rank r owns rows [r*rows, (r+1)*rows) of a [world*rows, 16384] tensor; elementwise graphs need no exchange.
+    # random()'s stream is a function of the global element index, so shard r is seeded to continue it: i ^ seed with the
+    # global offset folded into distinct seeds keeps shards independent (synthetic data either way).
+    seeds = [1 + 16 * rank, 2 + 16 * rank, 3 + 16 * rank]
+    a, b, c = (T.random(shape, seed=s).doCache() for s in seeds)
+    expr = c2_chain(T, a, b, c)
+    kern = expr.compile()
+    kinfo = kern.info
+    assert kinfo.algorithmic_bytes == alg_bytes, (kinfo.algorithmic_bytes, alg_bytes)
+
+    def step():
+        expr.doBuffer().release()
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    if dist:
+        dist.barrier()
+    ms, launches, w0, w1 = time_steps(cuda, step, args.steps, args.warmup)
+    if dist:
+        import torch
+
+        t = torch.tensor([ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        dist.barrier()
+    clocks = sampler.summary(w0, w1)
+    ms_per_step = ms / args.steps
+    value = world * alg_bytes / ms_per_step / 1e6  # GB/s, whole job
+    kernel_gbs = alg_bytes / ms_per_step / 1e6
+
+    # ---- e2e: host buffers in, host buffer out, through the same public API -------------------------------------------------
+    chunks = args.e2e_chunks
+    crow = rows // chunks
+    cn = crow * COLS
+    ha, hb, hc, ho = (cuda.PinnedArray(n) for _ in range(4))
+    for h, src in ((ha, a), (hb, b), (hc, c)):
+        src.flatArrayInto(h.ptr, n)
+    da, db, dc = ([cuda.Buffer.alloc(cn) for _ in range(chunks)] for _ in range(3))
+    exprs = []
+    for i in range(chunks):
+        ta, tb, tc = (T.fromBuffer(d[i], [crow, COLS]) for d in (da, db, dc))
+        exprs.append(c2_chain(T, ta, tb, tc))
+
+    def e2e_step():
+        # leading-axis chunks: H2D of chunk i+1 overlaps the kernel of chunk i and the D2H of chunk i-1 (separate streams, event-ordered)
+        for i in range(chunks):
+            off = i * cn * 4
+            da[i].upload(ha.ptr + off, cn)
+            db[i].upload(hb.ptr + off, cn)
+            dc[i].upload(hc.ptr + off, cn)
+            out = exprs[i].doBuffer()
+            out.to_host_async(ho.ptr + off, cn)
+            out.release()
+        cuda.synchronize()  # the result is in host memory when the step ends
+
+    for _ in range(max(1, min(args.warmup, 2))):
+        e2e_step()
+    if dist:
+        dist.barrier()
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    e2e_sec = (time.perf_counter() - t0) / e2e_steps
+    if dist:
+        import torch
+
+        t = torch.tensor([e2e_sec], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_sec = float(t.item())
+    e2e_value = world * alg_bytes / e2e_sec / 1e9
+    e2e_ok = None
+    if rank == 0:
+        # the bytes that came back are the chain's result (spot check against the device-resident evaluation)
+        ref_out = expr.flatArray()
+        e2e_ok = bool(np.array_equal(ref_out[: 1 << 20].view(np.uint32), ho.array[: 1 << 20].view(np.uint32)))
+    sampler.stop()
+
+    line = None
+    if rank == 0:
+        tf_peak = float(pk.get("bf16_tflops", 1590.0)) / 2 / 3  # 3xTF32 fp32-equivalent peak = TF32 peak / 3 ~= bf16 / 2 / 3
+        line = {
+            "metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "C2 long fused elementwise chain tanh(log(exp(a*b+c)+a)*b)+c", "shape_per_gpu": shape, "elements_per_gpu": n,
+                       "inputs": "Tensor.random seeds 1,2,3 (Wang hash), cached in HBM", "l2": "inputs (3 GiB) and output (1 GiB) are far larger than the 126 MB L2",
+                       "sharding": "leading axis, no collective", "e2e_chunks": chunks},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "achieved": kernel_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": kernel_gbs / hbm_peak,
+                         "traffic": None, "peak_source": pk_kind, "kernel": "jit_kernel (fused elementwise template)",
+                         "algorithmic_bytes_per_launch": alg_bytes},
+            "e2e": {"value": e2e_value, "unit": "GB/s", "h2d_bytes_per_step": 3 * n * 4, "d2h_bytes_per_step": n * 4, "ms_per_step": e2e_sec * 1e3,
+                    "steps": e2e_steps, "result_matches_device_path": e2e_ok},
+        }
+        traffic_file = os.path.join(ROOT, "profiles", "c2_traffic_bytes.json")
+        if os.path.exists(traffic_file):
+            try:
+                line["roofline"]["traffic"] = json.load(open(traffic_file)).get("dram_bytes_per_launch")
+            except Exception:
+                pass
+    for h in (ha, hb, hc, ho):
+        h.free()
+    del exprs, da, db, dc
+    if rank == 0 and world == 1:
+        if not args.no_cpu_baseline:
+            times, cores, _ = cpu_c2(1 << 26, 3)
+            sec = min(times)
+            line["cpu_baseline"] = {"value": BYTES_PER_ELEMENT * (1 << 26) / sec / 1e9, "unit": "GB/s", "cores": cores, "kind": "port",
+                                    "sample": "2^26 of 2^28 elements, best of 3, C/OpenMP port of the generated kernel (oracle/oracle_cpu.c)"}
+        if not args.no_side_configs:
+            del a, b, c, expr
+            line["configs"] = side_configs(cuda, hbm_peak, tf_peak)
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if dist:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--rows", type=int, default=ROWS, help="rows of the [rows,16384] shard per GPU (default = the full config)")
+    ap.add_argument("--e2e-chunks", type=int, default=8)
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-side-configs", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+    else:
+        run_cuda(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

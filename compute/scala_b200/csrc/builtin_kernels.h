@@ -1,0 +1,37 @@
+// builtin_kernels.h — host launchers of the precompiled (nvcc, sm_100a) kernels: the hand-written programs that in the
+// reference are OpenCL C strings inside Tensors.scala (reduction T:313-392, random T:432-443, randomNormal T:398-429),
+// plus the tcgen05 contraction the matmul pattern lowers to.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime_api.h>
+
+#include <cstdint>
+
+namespace cc {
+
+// out[0] = sum(in[0..n)). scratch: >= reduce_sum_scratch_floats() floats; counter: one zero-initialised u32 that the
+// kernel resets itself. Deterministic (fixed grid, last-block-done second stage, no float atomics).
+uint64_t reduce_sum_scratch_floats();
+void launch_reduce_sum(const float* in, uint64_t n, float* out, float* scratch, unsigned* counter, int sm_count,
+                       cudaStream_t stream);
+
+void launch_random(float* out, uint64_t n, int32_t seed, cudaStream_t stream);
+void launch_random_normal(float* out, uint64_t n, int32_t seed, cudaStream_t stream);
+
+bool gemm_available();
+
+// ---- contraction ----------------------------------------------------------------------------------------------------
+struct GemmWorkspace {
+  float* a_lo;   // [M,K]  A - tf32_trunc(A)
+  float* bt_hi;  // [N,K]  B^T
+  float* bt_lo;  // [N,K]  (B - tf32_trunc(B))^T
+};
+typedef CUresult (*TensorMapEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                      const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                      CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+// C[M,N] = A[M,K] * B[K,N], fp32 row-major, 3xTF32 on tcgen05. M % 128 == 0, N % 128 == 0, K % 32 == 0.
+// Returns the number of device kernels launched; throws cc::Error on failure.
+int launch_gemm_3xtf32(const float* a, const float* b, float* c, int64_t m, int64_t n, int64_t k,
+                       const GemmWorkspace& ws, int sm_count, TensorMapEncodeFn encode, cudaStream_t stream);
+
+}  // namespace cc

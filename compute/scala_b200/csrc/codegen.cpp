@@ -1,0 +1,1017 @@
+// codegen.cpp — walks the Trees graph and instantiates the sm_100a kernel templates (jit_templates.cuh).
+//
+// What the reference does per tree (one scalar work-item per output element, global id 0 = slowest dimension,
+// OpenCLKernelBuilder.scala:135-221) is re-planned here for the GPU:
+//   * the index space is linearised with the LAST dimension fastest and processed as 128-bit vectors by a
+//     grid-stride loop over chunks (several independent vectors in flight per thread);
+//   * every affine view (OpenCLKernelBuilder.scala:348-411) with integer coefficients is folded on the host into
+//     `base + sum_x coef_x * g_x` over the flat source buffer, and bounds tests that interval analysis proves can
+//     never fail are dropped; the rest keep the reference's two-sided test -> padding semantics;
+//   * an unrolled chain `e_0 + e_1 + ... + e_{n-1}` (how users write per-axis sums and matmul, README.md:301-343,
+//     benchmarks.scala:174-193) whose terms differ only by an affine step in their views is RE-ROLLED into a real
+//     reduction over a new index t; `Tensor.join` of such terms is re-rolled into one more output dimension;
+//   * if the reduced operand is a not-yet-evaluated inline tensor (`definition_root`), its closure is composed into
+//     the reduction instead of being materialised (matmul2 would need an i*j*k intermediate, Tensors.scala:978-1003);
+//     `sum_t A[i,t] * B[t,k]` is lowered to the tcgen05 3xTF32 contraction.
+#include "codegen.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <unordered_map>
+
+namespace cc {
+
+double java_decimal_round(double v) {
+  if (!std::isfinite(v)) return v;
+  double s = v * 1000.0;
+  if (std::fabs(s) >= 9e15) return v;
+  double f = std::floor(s);
+  double res = std::fma(v, 1000.0, -f);  // exact residual in [0,1) up to one rounding
+  while (res < 0) {
+    f -= 1;
+    res = std::fma(v, 1000.0, -f);
+  }
+  while (res >= 1) {
+    f += 1;
+    res = std::fma(v, 1000.0, -f);
+  }
+  if (res > 0.5)
+    f += 1;
+  else if (res == 0.5 && std::fmod(f, 2.0) != 0.0)
+    f += 1;
+  return f / 1000.0;
+}
+
+namespace {
+
+struct Load {
+  int arg = -1;
+  std::vector<int64_t> src_shape;
+  float padding = 0.f;
+  std::vector<double> M;  // rows x (nd + 1), coefficients as the generated code uses them (DecimalFormat-rounded)
+  int rows = 0;
+  // analysis
+  bool integer = true;
+  std::vector<char> row_integer;
+  std::vector<int64_t> coef;  // per index dim, in floats of the flat source
+  int64_t base = 0;
+  std::vector<char> need_lo, need_hi;  // per source dim
+  int64_t max_abs_off = 0;
+  bool any_check() const {
+    for (size_t i = 0; i < need_lo.size(); ++i)
+      if (need_lo[i] || need_hi[i]) return true;
+    return false;
+  }
+};
+
+struct Op {
+  uint32_t kind = 0;
+  int a = -1, b = -1;
+  float lit = 0.f;
+  int load = -1;
+};
+
+struct Program {
+  std::vector<int64_t> dims;  // index space (output dims, then the re-rolled index t if any)
+  std::vector<Op> ops;
+  std::vector<Load> loads;
+  std::vector<int> results;
+};
+
+int64_t product(const std::vector<int64_t>& v) {
+  int64_t p = 1;
+  for (int64_t x : v) p *= x;
+  return p;
+}
+
+void analyze_load(Load& L, const std::vector<int64_t>& dims) {
+  const int nd = (int)dims.size();
+  const int cols = nd + 1;
+  L.rows = (int)L.src_shape.size();
+  L.row_integer.assign(L.rows, 1);
+  L.need_lo.assign(L.rows, 0);
+  L.need_hi.assign(L.rows, 0);
+  L.coef.assign(nd, 0);
+  L.base = 0;
+  L.integer = true;
+  for (double& m : L.M) m = java_decimal_round(m);
+  std::vector<int64_t> stride(L.rows, 1);
+  for (int y = L.rows - 2; y >= 0; --y) stride[y] = stride[y + 1] * L.src_shape[y + 1];
+  for (int y = 0; y < L.rows; ++y) {
+    bool any = false;
+    for (int x = 0; x < cols; ++x) {
+      double m = L.M[(size_t)y * cols + x];
+      if (m != 0.0) any = true;
+      if (m != std::floor(m) || std::fabs(m) > 4e15) L.row_integer[y] = 0;
+    }
+    if (!L.row_integer[y]) {
+      L.integer = false;
+      L.need_lo[y] = L.need_hi[y] = 1;
+      continue;
+    }
+    if (!any) continue;  // index 0, no test (K:383-385)
+    int64_t lo = (int64_t)L.M[(size_t)y * cols + nd], hi = lo;
+    for (int x = 0; x < nd; ++x) {
+      int64_t m = (int64_t)L.M[(size_t)y * cols + x];
+      int64_t ext = m * (dims[x] - 1);
+      if (dims[x] == 0) ext = 0;
+      lo += std::min<int64_t>(0, ext);
+      hi += std::max<int64_t>(0, ext);
+    }
+    L.need_lo[y] = lo < 0;
+    L.need_hi[y] = hi >= L.src_shape[y];
+  }
+  if (L.integer) {
+    int64_t mx = 0;
+    for (int y = 0; y < L.rows; ++y) L.base += (int64_t)L.M[(size_t)y * cols + nd] * stride[y];
+    mx = std::llabs(L.base);
+    for (int x = 0; x < nd; ++x) {
+      for (int y = 0; y < L.rows; ++y) L.coef[x] += (int64_t)L.M[(size_t)y * cols + x] * stride[y];
+      mx += std::llabs(L.coef[x]) * std::max<int64_t>(0, dims[x] - 1);
+    }
+    // row indices themselves are bounded by the same expression with stride 1
+    L.max_abs_off = mx;
+  }
+}
+
+// ---- program construction ---------------------------------------------------------------------------------------
+
+struct Builder {
+  const Tree& t;
+  Program prog;
+  int nd_base;                                                  // rank of the closure being exported
+  const std::unordered_map<uint32_t, std::vector<double>>* ext;  // Transform node -> extra column (re-rolled index)
+  std::unordered_map<uint32_t, int> memo;                       // node -> op index (ExportContext, R:220)
+  std::map<uint32_t, int>* arg_of_param;                        // param node -> plan arg (shared across programs)
+  std::vector<uint32_t>* arg_nodes;
+
+  int arg_for(uint32_t param_node) {
+    auto it = arg_of_param->find(param_node);
+    if (it != arg_of_param->end()) return it->second;
+    int a = (int)arg_nodes->size();
+    arg_nodes->push_back(param_node);
+    (*arg_of_param)[param_node] = a;
+    return a;
+  }
+
+  int make_load(uint32_t extract_node) {
+    const Node& ex = t.nodes[extract_node];
+    const Node& arr = t.nodes[ex.kids[0]];
+    const int nd = (int)prog.dims.size();
+    Load L;
+    if (arr.kind == K_PARAM) {
+      // ArrayParameter.extract (K:435-455): indexed by the kernel's own ids, same rank as the kernel
+      CC_REQUIRE((int)arr.shape.size() == nd_base, CC_ERR_BAD_TREE,
+                 "direct Extract of a rank-%d array inside a rank-%d kernel", (int)arr.shape.size(), nd_base);
+      L.arg = arg_for(ex.kids[0]);
+      L.padding = arr.value;
+      for (int32_t s : arr.shape) L.src_shape.push_back(s);
+      L.M.assign((size_t)nd_base * (nd + 1), 0.0);
+      for (int y = 0; y < nd_base; ++y) L.M[(size_t)y * (nd + 1) + y] = 1.0;
+    } else {
+      const Node& p = t.nodes[arr.kids[0]];
+      CC_REQUIRE((int)arr.cols == nd_base + 1, CC_ERR_BAD_TREE, "transform has %u columns inside a rank-%d kernel",
+                 arr.cols, nd_base);
+      L.arg = arg_for(arr.kids[0]);
+      L.padding = p.value;
+      for (int32_t s : p.shape) L.src_shape.push_back(s);
+      const std::vector<double>* e = nullptr;
+      if (ext) {
+        auto it = ext->find(ex.kids[0]);
+        if (it != ext->end()) e = &it->second;
+      }
+      L.M.assign((size_t)arr.rows * (nd + 1), 0.0);
+      for (uint32_t y = 0; y < arr.rows; ++y) {
+        for (int x = 0; x < nd_base; ++x) L.M[(size_t)y * (nd + 1) + x] = arr.matrix[(size_t)y * arr.cols + x];
+        if (nd > nd_base) L.M[(size_t)y * (nd + 1) + nd_base] = e ? (*e)[y] : 0.0;
+        L.M[(size_t)y * (nd + 1) + nd] = arr.matrix[(size_t)y * arr.cols + nd_base];
+      }
+    }
+    analyze_load(L, prog.dims);
+    prog.loads.push_back(std::move(L));
+    return (int)prog.loads.size() - 1;
+  }
+
+  // iterative post-order export with identity memo
+  int export_node(uint32_t root) {
+    std::vector<std::pair<uint32_t, bool>> stack{{root, false}};
+    while (!stack.empty()) {
+      auto [i, ready] = stack.back();
+      stack.pop_back();
+      if (memo.count(i)) continue;
+      const Node& nd = t.nodes[i];
+      if (nd.kind == K_LITERAL) {
+        Op op;
+        op.kind = K_LITERAL;
+        op.lit = nd.value;
+        prog.ops.push_back(op);
+        memo[i] = (int)prog.ops.size() - 1;
+      } else if (nd.kind == K_EXTRACT) {
+        Op op;
+        op.kind = K_EXTRACT;
+        op.load = make_load(i);
+        prog.ops.push_back(op);
+        memo[i] = (int)prog.ops.size() - 1;
+      } else if (is_unary(nd.kind) || is_binary(nd.kind)) {
+        if (!ready) {
+          stack.push_back({i, true});
+          for (size_t k = nd.kids.size(); k-- > 0;)
+            if (!memo.count(nd.kids[k])) stack.push_back({nd.kids[k], false});
+        } else {
+          Op op;
+          op.kind = nd.kind;
+          op.a = memo.at(nd.kids[0]);
+          if (nd.kids.size() > 1) op.b = memo.at(nd.kids[1]);
+          prog.ops.push_back(op);
+          memo[i] = (int)prog.ops.size() - 1;
+        }
+      } else {
+        fail(CC_ERR_BAD_TREE, strprintf("%s is only allowed at the root of a tree", kind_name(nd.kind)));
+      }
+    }
+    return memo.at(root);
+  }
+};
+
+// ---- congruence (re-rolling) --------------------------------------------------------------------------------------
+
+// Are subtrees a and b the same expression up to the constant column of their Transforms? Records const(b) - const(a)
+// per Transform node of a.
+bool congruent(const Tree& t, uint32_t a0, uint32_t b0, std::unordered_map<uint32_t, std::vector<double>>& delta) {
+  std::unordered_map<uint32_t, uint32_t> seen;
+  std::vector<std::pair<uint32_t, uint32_t>> stack{{a0, b0}};
+  while (!stack.empty()) {
+    auto [a, b] = stack.back();
+    stack.pop_back();
+    auto it = seen.find(a);
+    if (it != seen.end()) {
+      if (it->second != b) return false;
+      continue;
+    }
+    seen[a] = b;
+    const Node& na = t.nodes[a];
+    const Node& nb = t.nodes[b];
+    if (na.kind != nb.kind) return false;
+    switch (na.kind) {
+      case K_LITERAL:
+        if (memcmp(&na.value, &nb.value, 4) != 0) return false;
+        break;
+      case K_PARAM:
+        if (a != b) return false;
+        break;
+      case K_TRANSFORM: {
+        if (na.kids[0] != nb.kids[0] || na.rows != nb.rows || na.cols != nb.cols) return false;
+        std::vector<double> d(na.rows, 0.0);
+        for (uint32_t y = 0; y < na.rows; ++y) {
+          for (uint32_t x = 0; x + 1 < na.cols; ++x)
+            if (na.matrix[(size_t)y * na.cols + x] != nb.matrix[(size_t)y * na.cols + x]) return false;
+          d[y] = nb.matrix[(size_t)y * na.cols + na.cols - 1] - na.matrix[(size_t)y * na.cols + na.cols - 1];
+        }
+        delta[a] = std::move(d);
+        break;
+      }
+      default:
+        if (na.kids.size() != nb.kids.size()) return false;
+        for (size_t k = 0; k < na.kids.size(); ++k) stack.push_back({na.kids[k], nb.kids[k]});
+    }
+  }
+  return true;
+}
+
+// elements e_0..e_{n-1} -> per-Transform step such that const(e_i) = const(e_0) + i * step. Empty result = not congruent.
+bool reroll(const Tree& t, const std::vector<uint32_t>& elems, std::unordered_map<uint32_t, std::vector<double>>& step) {
+  if (elems.size() < 2) return false;
+  if (!congruent(t, elems[0], elems[1], step)) return false;
+  bool any = false;
+  for (auto& kv : step)
+    for (double d : kv.second)
+      if (d != 0.0) any = true;
+  if (!any) return false;
+  for (size_t i = 2; i < elems.size(); ++i) {
+    std::unordered_map<uint32_t, std::vector<double>> di;
+    if (!congruent(t, elems[0], elems[i], di)) return false;
+    if (di.size() != step.size()) return false;
+    for (auto& kv : di) {
+      auto it = step.find(kv.first);
+      if (it == step.end()) return false;
+      for (size_t y = 0; y < kv.second.size(); ++y)
+        if (kv.second[y] != (double)i * it->second[y]) return false;
+    }
+  }
+  return true;
+}
+
+// ---- text helpers ---------------------------------------------------------------------------------------------------
+
+std::string flit(float v) {
+  if (std::isnan(v)) return "__int_as_float(0x7fc00000)";
+  if (std::isinf(v)) return v > 0 ? "__int_as_float(0x7f800000)" : "__int_as_float(0xff800000)";
+  uint32_t u;
+  memcpy(&u, &v, 4);
+  // bit-exact literal; the decimal form is kept in a comment for readability
+  return strprintf("__uint_as_float(0x%08xu) /*%.9g*/", u, (double)v);
+}
+
+std::string dlit(double v) {
+  return strprintf("%.17g", v);
+}
+
+struct Emit {
+  std::string s;
+  void operator()(const char* fmt, ...) __attribute__((format(printf, 2, 3))) {
+    va_list ap;
+    va_start(ap, fmt);
+    va_list ap2;
+    va_copy(ap2, ap);
+    int n = vsnprintf(nullptr, 0, fmt, ap);
+    va_end(ap);
+    size_t old = s.size();
+    s.resize(old + (size_t)n);
+    vsnprintf(&s[old], (size_t)n + 1, fmt, ap2);
+    va_end(ap2);
+  }
+};
+
+const char* op_expr(uint32_t kind) {
+  switch (kind) {
+    case K_EXP: return "cc_exp(%s)";
+    case K_LOG: return "cc_log(%s)";
+    case K_ABS: return "fabsf(%s)";
+    case K_TANH: return "cc_tanh(%s)";
+    case K_SQRT: return "sqrtf(%s)";
+    case K_NEG: return "(-%s)";
+    case K_MIN: return "fminf(%s, %s)";
+    case K_MAX: return "fmaxf(%s, %s)";
+    case K_PLUS: return "(%s + %s)";
+    case K_MINUS: return "(%s - %s)";
+    case K_TIMES: return "(%s * %s)";
+    case K_DIV: return "(%s / %s)";
+    case K_PERCENT: return "fmodf(%s, %s)";
+  }
+  return "?";
+}
+
+// Emits the SSA body of the program for one lane; value names are _<op>; loads read `ldname(j)` .
+void emit_ops(Emit& e, const Program& p, const char* indent, const std::string& lane) {
+  for (size_t i = 0; i < p.ops.size(); ++i) {
+    const Op& op = p.ops[i];
+    if (op.kind == K_LITERAL) {
+      e("%sconst float _%zu = %s;\n", indent, i, flit(op.lit).c_str());
+    } else if (op.kind == K_EXTRACT) {
+      e("%sconst float _%zu = L%d[%s];\n", indent, i, op.load, lane.c_str());
+    } else {
+      std::string a = strprintf("_%d", op.a), b = strprintf("_%d", op.b);
+      std::string fmt = op_expr(op.kind);
+      std::string ex = is_unary(op.kind) ? strprintf(fmt.c_str(), a.c_str()) : strprintf(fmt.c_str(), a.c_str(), b.c_str());
+      e("%sconst float _%zu = %s;\n", indent, i, ex.c_str());
+    }
+  }
+}
+
+struct LoadCtx {
+  int V;                 // lanes
+  int vdim;              // index dim the lanes run along (-1: none)
+  const char* idx_type;  // "int" or "long long"
+};
+
+// index expression of source row y for lane `lane` ("" = lane 0 / no lane term)
+std::string row_index_expr(const Load& L, int y, int nd, int vdim, const std::string& lane) {
+  const int cols = nd + 1;
+  std::string s;
+  if (L.row_integer[y]) {
+    int64_t c = (int64_t)L.M[(size_t)y * cols + nd];
+    s = strprintf("%lld", (long long)c);
+    for (int x = 0; x < nd; ++x) {
+      int64_t m = (int64_t)L.M[(size_t)y * cols + x];
+      if (m == 0) continue;
+      if (x == vdim && !lane.empty())
+        s += strprintf(" + %lld * (g%d + %s)", (long long)m, x, lane.c_str());
+      else
+        s += strprintf(" + %lld * g%d", (long long)m, x);
+    }
+    return s;
+  }
+  // non-integer row: the reference evaluates `(int)(g_x * a + ... + c)` in double, left to right (K:363-386)
+  bool first = true;
+  for (int x = 0; x <= nd; ++x) {
+    double m = L.M[(size_t)y * cols + x];
+    if (m == 0.0) continue;
+    std::string term;
+    if (x == nd)
+      term = dlit(m);
+    else {
+      std::string g = (x == vdim && !lane.empty()) ? strprintf("(double)(g%d + %s)", x, lane.c_str()) : strprintf("(double)g%d", x);
+      term = (m == 1.0) ? g : g + " * " + dlit(m);
+    }
+    s += first ? term : " + " + term;
+    first = false;
+  }
+  if (first) s = "0.0";
+  return "(int)(" + s + ")";
+}
+
+// Emits code filling `float L<j>[V]` for load j. g<x> index variables are in scope.
+void emit_load(Emit& e, const Program& p, int j, const LoadCtx& c, const char* indent) {
+  const Load& L = p.loads[j];
+  const int nd = (int)p.dims.size();
+  const int V = c.V;
+  std::string pad = flit(L.padding);
+  e("%sfloat L%d[%d];\n", indent, j, V);
+  if (!L.integer) {
+    // general path: per lane, per row index in the reference's arithmetic
+    e("%s#pragma unroll\n%sfor (int l = 0; l < %d; ++l) {\n", indent, indent, V);
+    std::string cond, off = "0";
+    int64_t stride = 1;
+    std::vector<int64_t> strides(L.rows, 1);
+    for (int y = L.rows - 2; y >= 0; --y) strides[y] = strides[y + 1] * L.src_shape[y + 1];
+    (void)stride;
+    for (int y = 0; y < L.rows; ++y) {
+      e("%s  const long long i%d = %s;\n", indent, y, row_index_expr(L, y, nd, c.vdim, "l").c_str());
+      if (L.need_lo[y]) cond += strprintf("%si%d >= 0", cond.empty() ? "" : " && ", y);
+      if (L.need_hi[y]) cond += strprintf("%si%d < %lld", cond.empty() ? "" : " && ", y, (long long)L.src_shape[y]);
+      off += strprintf(" + i%d * %lldLL", y, (long long)strides[y]);
+    }
+    if (cond.empty())
+      e("%s  L%d[l] = cc_ldg(p%d + (%s));\n", indent, j, L.arg, off.c_str());
+    else
+      e("%s  L%d[l] = (%s) ? cc_ldg(p%d + (%s)) : %s;\n", indent, j, cond.c_str(), L.arg, off.c_str(), pad.c_str());
+    e("%s}\n", indent);
+    return;
+  }
+  const int64_t coefV = (c.vdim >= 0 && V > 1) ? L.coef[c.vdim] : 0;
+  // offset of lane 0
+  std::string off = strprintf("(%s)%lld", c.idx_type, (long long)L.base);
+  for (int x = 0; x < nd; ++x)
+    if (L.coef[x] != 0) off += strprintf(" + (%s)%lld * g%d", c.idx_type, (long long)L.coef[x], x);
+  e("%sconst %s o%d = %s;\n", indent, c.idx_type, j, off.c_str());
+  // bounds tests: uniform rows vs lane-dependent rows
+  std::string ucond;
+  bool lane_checks = false;
+  const int cols = nd + 1;
+  for (int y = 0; y < L.rows; ++y) {
+    if (!L.need_lo[y] && !L.need_hi[y]) continue;
+    bool lane_dep = V > 1 && c.vdim >= 0 && L.M[(size_t)y * cols + c.vdim] != 0.0;
+    if (lane_dep) {
+      lane_checks = true;
+      continue;
+    }
+    e("%sconst %s i%d_%d = %s;\n", indent, c.idx_type, j, y, row_index_expr(L, y, nd, c.vdim, "").c_str());
+    if (L.need_lo[y]) ucond += strprintf("%si%d_%d >= 0", ucond.empty() ? "" : " && ", j, y);
+    if (L.need_hi[y]) ucond += strprintf("%si%d_%d < %lld", ucond.empty() ? "" : " && ", j, y, (long long)L.src_shape[y]);
+  }
+  bool aligned = V == 4 && coefV == 1 && (L.base % 4 == 0);
+  if (aligned)
+    for (int x = 0; x < nd; ++x)
+      if (x != c.vdim && L.coef[x] % 4 != 0) aligned = false;
+  if (V == 1) {
+    if (ucond.empty())
+      e("%sL%d[0] = cc_ldg(p%d + o%d);\n", indent, j, L.arg, j);
+    else
+      e("%sL%d[0] = (%s) ? cc_ldg(p%d + o%d) : %s;\n", indent, j, ucond.c_str(), L.arg, j, pad.c_str());
+    return;
+  }
+  if (!lane_checks && aligned) {
+    if (ucond.empty())
+      e("%scc_ldg4(p%d + o%d, L%d);\n", indent, L.arg, j, j);
+    else
+      e("%sif (%s) cc_ldg4(p%d + o%d, L%d); else { L%d[0] = L%d[1] = L%d[2] = L%d[3] = %s; }\n", indent, ucond.c_str(),
+        L.arg, j, j, j, j, j, j, pad.c_str());
+    return;
+  }
+  if (!lane_checks && coefV == 0) {
+    if (ucond.empty())
+      e("%sL%d[0] = cc_ldg(p%d + o%d);\n", indent, j, L.arg, j);
+    else
+      e("%sL%d[0] = (%s) ? cc_ldg(p%d + o%d) : %s;\n", indent, j, ucond.c_str(), L.arg, j, pad.c_str());
+    e("%sL%d[1] = L%d[2] = L%d[3] = L%d[0];\n", indent, j, j, j, j);
+    return;
+  }
+  // per-lane scalar loads (strided / misaligned / lane-dependent bounds)
+  e("%s#pragma unroll\n%sfor (int l = 0; l < %d; ++l) {\n", indent, indent, V);
+  std::string cond = ucond;
+  for (int y = 0; y < L.rows; ++y) {
+    if (!L.need_lo[y] && !L.need_hi[y]) continue;
+    bool lane_dep = L.M[(size_t)y * cols + c.vdim] != 0.0;
+    if (!lane_dep) continue;
+    e("%s  const %s k%d = %s;\n", indent, c.idx_type, y, row_index_expr(L, y, nd, c.vdim, "l").c_str());
+    if (L.need_lo[y]) cond += strprintf("%sk%d >= 0", cond.empty() ? "" : " && ", y);
+    if (L.need_hi[y]) cond += strprintf("%sk%d < %lld", cond.empty() ? "" : " && ", y, (long long)L.src_shape[y]);
+  }
+  if (cond.empty())
+    e("%s  L%d[l] = cc_ldg(p%d + o%d + (%s)%lld * l);\n", indent, j, L.arg, j, c.idx_type, (long long)coefV);
+  else
+    e("%s  L%d[l] = (%s) ? cc_ldg(p%d + o%d + (%s)%lld * l) : %s;\n", indent, j, cond.c_str(), L.arg, j, c.idx_type,
+      (long long)coefV, pad.c_str());
+  e("%s}\n", indent);
+}
+
+std::string param_list(int n_args, bool with_out, const char* out_name = "out") {
+  std::string s;
+  for (int i = 0; i < n_args; ++i) s += strprintf("%sconst float* __restrict__ p%d", i ? ", " : "", i);
+  if (with_out) s += strprintf("%sfloat* __restrict__ %s", n_args ? ", " : "", out_name);
+  return s;
+}
+std::string arg_pass(int n_args) {
+  std::string s;
+  for (int i = 0; i < n_args; ++i) s += strprintf("%sp%d", i ? ", " : "", i);
+  return s;
+}
+
+// decode `e` (element index over dims[0..n)) into g0..g{n-1}; dims beyond `n` are not touched
+void emit_decode(Emit& e, const std::vector<int64_t>& dims, int n, const char* idx_type, const char* src, const char* indent) {
+  if (n == 0) return;
+  e("%s%s rem_ = %s;\n", indent, idx_type, src);
+  for (int x = n - 1; x >= 1; --x) {
+    e("%sconst %s g%d = rem_ %% (%s)%lld; rem_ /= (%s)%lld;\n", indent, idx_type, x, idx_type, (long long)dims[x], idx_type,
+      (long long)dims[x]);
+  }
+  e("%sconst %s g0 = rem_;\n", indent, idx_type);
+}
+
+bool program_is_flat(const Program& p) {
+  // every load reads src[linear output index] with no test
+  const int nd = (int)p.dims.size();
+  std::vector<int64_t> stride(nd, 1);
+  for (int x = nd - 2; x >= 0; --x) stride[x] = stride[x + 1] * p.dims[x + 1];
+  for (const Load& L : p.loads) {
+    if (!L.integer || L.any_check() || L.base != 0) return false;
+    for (int x = 0; x < nd; ++x)
+      if (p.dims[x] > 1 && L.coef[x] != stride[x]) return false;
+  }
+  return true;
+}
+
+const char* pick_idx_type(const Program& p, int64_t total) {
+  int64_t mx = total;
+  for (const Load& L : p.loads) {
+    if (!L.integer) return "long long";
+    mx = std::max(mx, L.max_abs_off);
+    mx = std::max<int64_t>(mx, product(L.src_shape));
+  }
+  return mx >= (int64_t)1 << 30 ? "long long" : "int";
+}
+
+uint64_t count_flops(const Program& p) {
+  uint64_t f = 0;
+  for (const Op& op : p.ops)
+    if (op.kind != K_LITERAL && op.kind != K_EXTRACT) ++f;
+  return f;
+}
+
+// ---- elementwise kernel ------------------------------------------------------------------------------------------
+
+void emit_elementwise(Plan& plan, const Program& p, int n_args, const DeviceProps& dev, int concat_fallback_n) {
+  const int nd = (int)p.dims.size();
+  const int64_t total = product(p.dims);
+  const int nres = (int)p.results.size();
+  int V = (nd >= 1 && p.dims[nd - 1] % 4 == 0 && nres == 1) ? 4 : 1;
+  const int64_t NV = total / V;
+  const bool flat = program_is_flat(p);
+  const char* IDX = pick_idx_type(p, total * std::max(1, nres));
+  const int nloads = (int)p.loads.size();
+  int U = 4;
+  if (nloads > 4) U = 2;
+  if (nloads > 8) U = 1;
+  while (U > 1 && NV < (int64_t)256 * U * dev.sm_count * 2) U /= 2;
+  const int64_t chunk = (int64_t)256 * U;
+  const int64_t nchunks = (NV + chunk - 1) / chunk;
+  int64_t grid = std::min<int64_t>(nchunks, (int64_t)dev.sm_count * 8);
+  if (grid < 1) grid = 1;
+
+  Emit e;
+  e("// elementwise: dims=[");
+  for (int x = 0; x < nd; ++x) e("%s%lld", x ? "," : "", (long long)p.dims[x]);
+  e("] V=%d U=%d flat=%d idx=%s loads=%d ops=%zu grid=%lld\n", V, U, (int)flat, IDX, nloads, p.ops.size(), (long long)grid);
+  e("struct Regs {");
+  for (int j = 0; j < nloads; ++j) e(" float L%d[%d];", j, V);
+  if (nloads == 0) e(" int unused_;");
+  e(" };\n");
+  // ld
+  e("__device__ __forceinline__ void ld(const %s v%s%s, Regs& r) {\n", IDX, n_args ? ", " : "", param_list(n_args, false).c_str());
+  if (nloads) {
+    LoadCtx c{V, nd - 1, IDX};
+    if (flat) {
+      for (int j = 0; j < nloads; ++j) {
+        if (V == 4)
+          e("  cc_ldg4(p%d + v * 4, r.L%d);\n", p.loads[j].arg, j);
+        else
+          e("  r.L%d[0] = cc_ldg(p%d + v);\n", j, p.loads[j].arg);
+      }
+    } else {
+      emit_decode(e, p.dims, nd, IDX, strprintf("v * %d", V).c_str(), "  ");
+      for (int j = 0; j < nloads; ++j) {
+        e("  {\n");
+        emit_load(e, p, j, c, "    ");
+        e("    #pragma unroll\n    for (int l = 0; l < %d; ++l) r.L%d[l] = L%d[l];\n  }\n", V, j, j);
+      }
+    }
+  }
+  e("}\n");
+  // st
+  e("__device__ __forceinline__ void st(const %s v, const Regs& r, float* __restrict__ out) {\n", IDX);
+  e("  float o[%d][%d];\n", nres, V);
+  e("  #pragma unroll\n  for (int l = 0; l < %d; ++l) {\n", V);
+  for (int j = 0; j < nloads; ++j) e("    const float* L%d = r.L%d;\n", j, j);
+  emit_ops(e, p, "    ", "l");
+  for (int r = 0; r < nres; ++r) e("    o[%d][l] = _%d;\n", r, p.results[r]);
+  e("  }\n");
+  if (nres == 1) {
+    if (V == 4)
+      e("  cc_stg4(out + v * 4, o[0]);\n");
+    else
+      e("  out[v] = o[0][0];\n");
+  } else {
+    for (int r = 0; r < nres; ++r) e("  out[v * %d + %d] = o[%d][0];\n", nres, r, r);
+  }
+  e("}\n");
+  e("extern \"C\" __global__ void __launch_bounds__(256) jit_kernel(%s) {\n", param_list(n_args, true).c_str());
+  e("  const %s NV = %lld;\n  const %s nchunks = %lld;\n", IDX, (long long)NV, IDX, (long long)nchunks);
+  e("  for (%s c = blockIdx.x; c < nchunks; c += gridDim.x) {\n", IDX);
+  e("    const %s v0 = c * %lld + threadIdx.x;\n", IDX, (long long)chunk);
+  e("    if ((c + 1) * %lld <= NV) {\n", (long long)chunk);
+  e("      Regs r[%d];\n", U);
+  e("      #pragma unroll\n      for (int u = 0; u < %d; ++u) ld(v0 + u * 256%s%s, r[u]);\n", U, n_args ? ", " : "", arg_pass(n_args).c_str());
+  e("      #pragma unroll\n      for (int u = 0; u < %d; ++u) st(v0 + u * 256, r[u], out);\n", U);
+  e("    } else {\n");
+  e("      for (int u = 0; u < %d; ++u) {\n        const %s v = v0 + u * 256;\n        if (v < NV) { Regs r; ld(v%s%s, r); st(v, r, out); }\n      }\n", U, IDX,
+    n_args ? ", " : "", arg_pass(n_args).c_str());
+  e("    }\n  }\n}\n");
+  plan.source += e.s;
+  LaunchSpec ls;
+  ls.entry = "jit_kernel";
+  ls.grid[0] = (uint32_t)grid;
+  ls.block[0] = 256;
+  for (int i = 0; i < n_args; ++i) ls.args.push_back(i);
+  ls.args.push_back(ARG_OUT);
+  if (total > 0) plan.launches.push_back(ls);
+  (void)concat_fallback_n;
+}
+
+// ---- reductions over the re-rolled index --------------------------------------------------------------------------
+
+// out[g] = sum_t E(g, t).  dims = out dims + [T].
+void emit_reduce(Plan& plan, const Program& p, int n_args, const DeviceProps& dev) {
+  const int nd = (int)p.dims.size();
+  const int no = nd - 1;
+  const int64_t T = p.dims[nd - 1];
+  std::vector<int64_t> odims(p.dims.begin(), p.dims.end() - 1);
+  const int64_t NOUT = product(odims);
+  const char* IDX = pick_idx_type(p, NOUT * T);
+  const int nloads = (int)p.loads.size();
+  // choose the orientation: which index do neighbouring threads walk?
+  bool any_t_contig = false, any_o_contig = false;
+  for (const Load& L : p.loads) {
+    if (!L.integer) continue;
+    if (std::llabs(L.coef[nd - 1]) == 1) any_t_contig = true;
+    if (no >= 1 && std::llabs(L.coef[no - 1]) == 1) any_o_contig = true;
+  }
+  const bool rows = (any_t_contig && !any_o_contig) || no == 0 || NOUT < 64;
+  Emit e;
+  if (!rows) {
+    // --- column owner: a thread owns V adjacent outputs and walks t; T is split over blockIdx.y ----------------------
+    const int V = (odims[no - 1] % 4 == 0) ? 4 : 1;
+    const int64_t NV = NOUT / V;
+    int64_t want = ((int64_t)dev.sm_count * 2048 * 2 + NV - 1) / NV;
+    int64_t S = std::max<int64_t>(1, std::min<int64_t>(want, T / 32));
+    S = std::min<int64_t>(S, 1024);
+    const int64_t TCH = (T + S - 1) / S;
+    S = (T + TCH - 1) / TCH;
+    e("// axis reduction (column owner): out dims=[");
+    for (int x = 0; x < no; ++x) e("%s%lld", x ? "," : "", (long long)odims[x]);
+    e("] T=%lld V=%d splits=%lld chunk=%lld idx=%s\n", (long long)T, V, (long long)S, (long long)TCH, IDX);
+    e("__device__ __forceinline__ void ev(const %s g%d", IDX, nd - 1);
+    for (int x = 0; x < no; ++x) e(", const %s g%d", IDX, x);
+    e("%s%s, float (&o)[%d]) {\n", n_args ? ", " : "", param_list(n_args, false).c_str(), V);
+    LoadCtx c{V, no - 1, IDX};
+    for (int j = 0; j < nloads; ++j) emit_load(e, p, j, c, "  ");
+    e("  #pragma unroll\n  for (int l = 0; l < %d; ++l) {\n", V);
+    emit_ops(e, p, "    ", "l");
+    e("    o[l] = _%d;\n  }\n}\n", p.results[0]);
+    e("extern \"C\" __global__ void __launch_bounds__(256) reduce_cols(%s) {\n", param_list(n_args, true, "dst").c_str());
+    e("  const %s v = (%s)blockIdx.x * 256 + threadIdx.x;\n  if (v >= %lld) return;\n", IDX, IDX, (long long)NV);
+    emit_decode(e, odims, no, IDX, strprintf("v * %d", V).c_str(), "  ");
+    std::string gs;
+    for (int x = 0; x < no; ++x) gs += strprintf(", g%d", x);
+    e("  const int t0 = blockIdx.y * %lld;\n  const int t1 = min(%lld, t0 + %lld);\n", (long long)TCH, (long long)T, (long long)TCH);
+    e("  float acc[%d];\n  ev(t0%s%s%s, acc);\n", V, gs.c_str(), n_args ? ", " : "", arg_pass(n_args).c_str());
+    e("  #pragma unroll 4\n  for (int t = t0 + 1; t < t1; ++t) {\n    float x[%d];\n    ev(t%s%s%s, x);\n", V, gs.c_str(), n_args ? ", " : "",
+      arg_pass(n_args).c_str());
+    e("    #pragma unroll\n    for (int l = 0; l < %d; ++l) acc[l] = acc[l] + x[l];\n  }\n", V);
+    e("  float* d = dst + (%s)blockIdx.y * %lld + v * %d;\n", "long long", (long long)NOUT, V);
+    if (V == 4)
+      e("  cc_stg4(d, acc);\n");
+    else
+      e("  d[0] = acc[0];\n");
+    e("}\n");
+    LaunchSpec ls;
+    ls.entry = "reduce_cols";
+    ls.grid[0] = (uint32_t)((NV + 255) / 256);
+    ls.grid[1] = (uint32_t)S;
+    ls.block[0] = 256;
+    for (int i = 0; i < n_args; ++i) ls.args.push_back(i);
+    ls.args.push_back(S == 1 ? ARG_OUT : ARG_SCRATCH0);
+    plan.launches.push_back(ls);
+    if (S > 1) {
+      plan.scratch_floats.push_back((uint64_t)(S * NOUT));
+      e("extern \"C\" __global__ void __launch_bounds__(256) reduce_partials(const float* __restrict__ part, float* __restrict__ out) {\n");
+      e("  const long long v = (long long)blockIdx.x * 256 + threadIdx.x;\n  if (v >= %lld) return;\n", (long long)NV);
+      e("  float acc[%d];\n", V);
+      if (V == 4) {
+        e("  cc_ldg4(part + v * 4, acc);\n  for (int s = 1; s < %lld; ++s) {\n    float x[4];\n    cc_ldg4(part + (long long)s * %lld + v * 4, x);\n", (long long)S,
+          (long long)NOUT);
+        e("    #pragma unroll\n    for (int l = 0; l < 4; ++l) acc[l] = acc[l] + x[l];\n  }\n  cc_stg4(out + v * 4, acc);\n}\n");
+      } else {
+        e("  acc[0] = part[v];\n  for (int s = 1; s < %lld; ++s) acc[0] = acc[0] + part[(long long)s * %lld + v];\n  out[v] = acc[0];\n}\n", (long long)S,
+          (long long)NOUT);
+      }
+      LaunchSpec l2;
+      l2.entry = "reduce_partials";
+      l2.grid[0] = (uint32_t)((NV + 255) / 256);
+      l2.block[0] = 256;
+      l2.args = {ARG_SCRATCH0, ARG_OUT};
+      plan.launches.push_back(l2);
+    }
+  } else {
+    // --- row owner: G threads share one output and stride over t in 128-bit vectors -----------------------------------
+    const int V = (T % 4 == 0) ? 4 : 1;
+    const int64_t TV = T / V;
+    const int G = TV <= 64 ? 32 : 256;
+    const int OPB = 256 / G;  // outputs per block
+    e("// axis reduction (row owner): out dims=[");
+    for (int x = 0; x < no; ++x) e("%s%lld", x ? "," : "", (long long)odims[x]);
+    e("] T=%lld V=%d threads/output=%d idx=%s\n", (long long)T, V, G, IDX);
+    e("__device__ __forceinline__ float ev(const %s g%d", IDX, nd - 1);
+    for (int x = 0; x < no; ++x) e(", const %s g%d", IDX, x);
+    e("%s%s) {\n", n_args ? ", " : "", param_list(n_args, false).c_str());
+    LoadCtx c{V, nd - 1, IDX};
+    for (int j = 0; j < nloads; ++j) emit_load(e, p, j, c, "  ");
+    e("  float o[%d];\n  #pragma unroll\n  for (int l = 0; l < %d; ++l) {\n", V, V);
+    emit_ops(e, p, "    ", "l");
+    e("    o[l] = _%d;\n  }\n", p.results[0]);
+    if (V == 4)
+      e("  return (o[0] + o[1]) + (o[2] + o[3]);\n}\n");
+    else
+      e("  return o[0];\n}\n");
+    e("extern \"C\" __global__ void __launch_bounds__(256) reduce_rows(%s) {\n", param_list(n_args, true).c_str());
+    e("  const int lane = threadIdx.x %% %d;\n", G);
+    e("  const %s oidx = (%s)blockIdx.x * %d + threadIdx.x / %d;\n", IDX, IDX, OPB, G);
+    e("  const bool live = oidx < %lld;\n  const %s oc = live ? oidx : 0;\n", (long long)NOUT, IDX);
+    emit_decode(e, odims, no, IDX, "oc", "  ");
+    std::string gs;
+    for (int x = 0; x < no; ++x) gs += strprintf(", g%d", x);
+    e("  float acc = 0.f;\n  #pragma unroll 4\n  for (int tv = lane; tv < %lld; tv += %d) acc += ev((%s)tv * %d%s%s%s);\n", (long long)TV, G, IDX, V, gs.c_str(),
+      n_args ? ", " : "", arg_pass(n_args).c_str());
+    if (G == 32)
+      e("  acc = cc_warp_sum(acc);\n");
+    else
+      e("  acc = cc_block_sum_256(acc);\n");
+    e("  if (lane == 0 && live) out[oidx] = acc;\n}\n");
+    LaunchSpec ls;
+    ls.entry = "reduce_rows";
+    ls.grid[0] = (uint32_t)((NOUT + OPB - 1) / OPB);
+    ls.block[0] = 256;
+    for (int i = 0; i < n_args; ++i) ls.args.push_back(i);
+    ls.args.push_back(ARG_OUT);
+    plan.launches.push_back(ls);
+  }
+  plan.source += e.s;
+}
+
+// ---- definition inlining -----------------------------------------------------------------------------------------
+
+// M_outer: rows_p x (nd+1) maps the reduction's index space onto P's index space; M_def: rows_s x (rows_p+1) maps P's
+// index space onto a source. Returns rows_s x (nd+1). (Same accumulation order as NDimensionalAffineTransform.scala:48-95.)
+std::vector<double> compose(const std::vector<double>& M_def, int rows_s, const std::vector<double>& M_outer, int rows_p, int nd) {
+  std::vector<double> out((size_t)rows_s * (nd + 1), 0.0);
+  for (int y = 0; y < rows_s; ++y) {
+    for (int x = 0; x < nd; ++x) {
+      double acc = 0.0;
+      for (int k = 0; k < rows_p; ++k) acc = acc + M_def[(size_t)y * (rows_p + 1) + k] * M_outer[(size_t)k * (nd + 1) + x];
+      out[(size_t)y * (nd + 1) + x] = acc;
+    }
+    double acc = M_def[(size_t)y * (rows_p + 1) + rows_p];
+    for (int k = 0; k < rows_p; ++k) acc = acc + M_def[(size_t)y * (rows_p + 1) + k] * M_outer[(size_t)k * (nd + 1) + nd];
+    out[(size_t)y * (nd + 1) + nd] = acc;
+  }
+  return out;
+}
+
+}  // namespace
+
+Plan make_plan(const Tree& t, const DeviceProps& dev) {
+  Plan plan;
+  const Node& root = t.nodes[t.root];
+  std::vector<int64_t> odims(t.out_shape.begin(), t.out_shape.end());
+  std::map<uint32_t, int> arg_of_param;
+  std::vector<uint32_t> arg_nodes;
+  std::vector<int32_t> ordinal_of_node(t.nodes.size(), -1);
+  for (size_t p = 0; p < t.params.size(); ++p) ordinal_of_node[t.params[p]] = (int32_t)p;
+
+  Program prog;
+  bool is_reduce = false;
+  int nd_base = (int)odims.size();
+
+  if (root.kind == K_CONCAT) {
+    // Tensor.join (Tensors.scala:577-598): elements are evaluated over the head shape = out_shape minus the last dim
+    CC_REQUIRE(!odims.empty() && odims.back() == (int64_t)root.kids.size(), CC_ERR_BAD_TREE,
+               "Concatenate of %zu elements needs an output shape ending in %zu", root.kids.size(), root.kids.size());
+    nd_base = (int)odims.size() - 1;
+    std::vector<int64_t> head(odims.begin(), odims.end() - 1);
+    std::unordered_map<uint32_t, std::vector<double>> step;
+    if (root.kids.size() >= 2 && reroll(t, root.kids, step)) {
+      Builder b{t, {}, nd_base, &step, {}, &arg_of_param, &arg_nodes};
+      b.prog.dims = odims;  // head dims + the re-rolled element index as the fastest dimension
+      b.prog.results.push_back(b.export_node(root.kids[0]));
+      prog = std::move(b.prog);
+      plan.note = "join re-rolled into an output dimension";
+    } else {
+      Builder b{t, {}, nd_base, nullptr, {}, &arg_of_param, &arg_nodes};
+      b.prog.dims = head;
+      for (uint32_t k : root.kids) b.prog.results.push_back(b.export_node(k));
+      prog = std::move(b.prog);
+      plan.note = "join as per-index tuple stores";
+    }
+  } else {
+    // left-leaning Plus chain?  (((e0 + e1) + e2) + ... )
+    std::vector<uint32_t> elems;
+    {
+      uint32_t cur = t.root;
+      while (t.nodes[cur].kind == K_PLUS) {
+        elems.push_back(t.nodes[cur].kids[1]);
+        cur = t.nodes[cur].kids[0];
+      }
+      elems.push_back(cur);
+      std::reverse(elems.begin(), elems.end());
+    }
+    std::unordered_map<uint32_t, std::vector<double>> step;
+    if (elems.size() >= 8 && reroll(t, elems, step)) {
+      Builder b{t, {}, nd_base, &step, {}, &arg_of_param, &arg_nodes};
+      b.prog.dims = odims;
+      b.prog.dims.push_back((int64_t)elems.size());
+      b.prog.results.push_back(b.export_node(elems[0]));
+      prog = std::move(b.prog);
+      is_reduce = true;
+      plan.note = strprintf("Plus chain of %zu congruent terms re-rolled into a reduction", elems.size());
+    } else {
+      Builder b{t, {}, nd_base, nullptr, {}, &arg_of_param, &arg_nodes};
+      b.prog.dims = odims;
+      b.prog.results.push_back(b.export_node(t.root));
+      prog = std::move(b.prog);
+    }
+  }
+
+  if (is_reduce) {
+    // compose the closure of an unevaluated inline operand into the reduction (looks through the fusion barrier,
+    // SURVEY finding 2) when the view of it is integer and provably in range
+    const int nd = (int)prog.dims.size();
+    bool changed = false;
+    Program np;
+    np.dims = prog.dims;
+    std::map<uint32_t, int> arg2;
+    std::vector<uint32_t> nodes2;
+    std::vector<int> remap(prog.ops.size(), -1);
+    for (size_t i = 0; i < prog.ops.size(); ++i) {
+      const Op& op = prog.ops[i];
+      if (op.kind == K_EXTRACT) {
+        const Load& L = prog.loads[op.load];
+        uint32_t pnode = arg_nodes[L.arg];
+        const Node& pn = t.nodes[pnode];
+        if (pn.def_root >= 0 && L.integer && !L.any_check()) {
+          // export the definition over P's own index space, then re-map every load through L.M
+          std::map<uint32_t, int> a3;
+          std::vector<uint32_t> n3;
+          Builder db{t, {}, (int)pn.shape.size(), nullptr, {}, &a3, &n3};
+          for (int32_t s : pn.shape) db.prog.dims.push_back(s);
+          int res = db.export_node((uint32_t)pn.def_root);
+          std::vector<int> dmap(db.prog.ops.size(), -1);
+          for (size_t k = 0; k < db.prog.ops.size(); ++k) {
+            Op o = db.prog.ops[k];
+            if (o.kind == K_EXTRACT) {
+              Load dl = db.prog.loads[o.load];
+              uint32_t srcnode = n3[dl.arg];
+              auto it = arg2.find(srcnode);
+              if (it == arg2.end()) {
+                arg2[srcnode] = (int)nodes2.size();
+                nodes2.push_back(srcnode);
+                it = arg2.find(srcnode);
+              }
+              Load nl;
+              nl.arg = it->second;
+              nl.src_shape = dl.src_shape;
+              nl.padding = dl.padding;
+              nl.M = compose(dl.M, (int)dl.src_shape.size(), L.M, (int)pn.shape.size(), nd);
+              analyze_load(nl, np.dims);
+              np.loads.push_back(std::move(nl));
+              o.load = (int)np.loads.size() - 1;
+            } else {
+              if (o.a >= 0) o.a = dmap[o.a];
+              if (o.b >= 0) o.b = dmap[o.b];
+            }
+            np.ops.push_back(o);
+            dmap[k] = (int)np.ops.size() - 1;
+          }
+          remap[i] = dmap[res];
+          changed = true;
+          continue;
+        }
+        Load nl = L;
+        auto it = arg2.find(pnode);
+        if (it == arg2.end()) {
+          arg2[pnode] = (int)nodes2.size();
+          nodes2.push_back(pnode);
+          it = arg2.find(pnode);
+        }
+        nl.arg = it->second;
+        np.loads.push_back(std::move(nl));
+        Op o = op;
+        o.load = (int)np.loads.size() - 1;
+        np.ops.push_back(o);
+        remap[i] = (int)np.ops.size() - 1;
+      } else {
+        Op o = op;
+        if (o.a >= 0) o.a = remap[o.a];
+        if (o.b >= 0) o.b = remap[o.b];
+        np.ops.push_back(o);
+        remap[i] = (int)np.ops.size() - 1;
+      }
+    }
+    if (changed) {
+      np.results.push_back(remap[prog.results[0]]);
+      prog = std::move(np);
+      arg_nodes = nodes2;
+      plan.note += "; inline operand composed into the reduction (never materialised)";
+    }
+  }
+
+  const int n_args = (int)arg_nodes.size();
+  for (uint32_t pn : arg_nodes) {
+    CC_REQUIRE(ordinal_of_node[pn] >= 0, CC_ERR_BAD_TREE, "parameter node %u unreachable", pn);
+    plan.arg_params.push_back((uint32_t)ordinal_of_node[pn]);
+    int64_t n = 1;
+    for (int32_t s : t.nodes[pn].shape) n *= s;
+    plan.arg_min_floats.push_back((uint64_t)n);
+  }
+  plan.out_floats = (uint64_t)product(odims);
+  const int64_t space = product(prog.dims);
+  // algorithmic traffic: every distinct source once (or as much of it as the index space can touch) + the output once
+  {
+    std::vector<uint64_t> touched(n_args, 0);
+    for (const Load& L : prog.loads) touched[L.arg] += (uint64_t)space;
+    uint64_t bytes = plan.out_floats * 4;
+    for (int a = 0; a < n_args; ++a) bytes += 4 * std::min<uint64_t>(touched[a], plan.arg_min_floats[a]);
+    plan.algorithmic_bytes = bytes;
+    plan.flops = count_flops(prog) * (uint64_t)space + (is_reduce ? (uint64_t)space : 0);
+  }
+
+  if (is_reduce) {
+    plan.kind = PLAN_AXIS_REDUCE;
+    // contraction: sum_t A[i,t] * B[t,k] with A [M,K] and B [K,N] row-major
+    const int nd = (int)prog.dims.size();
+    if (dev.contraction && nd == 3 && prog.ops.size() == 3 && prog.loads.size() == 2 && prog.ops[prog.results[0]].kind == K_TIMES) {
+      const Op& mul = prog.ops[prog.results[0]];
+      if (prog.ops[mul.a].kind == K_EXTRACT && prog.ops[mul.b].kind == K_EXTRACT && mul.a != mul.b) {
+        const int64_t M = prog.dims[0], N = prog.dims[1], K = prog.dims[2];
+        auto is_A = [&](const Load& L) {
+          return L.integer && !L.any_check() && L.base == 0 && L.coef[0] == K && L.coef[1] == 0 && L.coef[2] == 1 &&
+                 product(L.src_shape) == M * K;
+        };
+        auto is_B = [&](const Load& L) {
+          return L.integer && !L.any_check() && L.base == 0 && L.coef[0] == 0 && L.coef[1] == 1 && L.coef[2] == N &&
+                 product(L.src_shape) == K * N;
+        };
+        const Load& La = prog.loads[prog.ops[mul.a].load];
+        const Load& Lb = prog.loads[prog.ops[mul.b].load];
+        int a_arg = -1, b_arg = -1;
+        if (is_A(La) && is_B(Lb)) a_arg = La.arg, b_arg = Lb.arg;
+        if (is_A(Lb) && is_B(La)) a_arg = Lb.arg, b_arg = La.arg;
+        if (a_arg >= 0 && a_arg != b_arg && M % 128 == 0 && N % 128 == 0 && K % 32 == 0 && M * K < ((int64_t)1 << 31) &&
+            N * K < ((int64_t)1 << 31)) {
+          plan.kind = PLAN_CONTRACTION;
+          plan.M = M;
+          plan.N = N;
+          plan.K = K;
+          // canonical argument order: A then B
+          std::vector<uint32_t> ap{plan.arg_params[a_arg], plan.arg_params[b_arg]};
+          std::vector<uint64_t> am{plan.arg_min_floats[a_arg], plan.arg_min_floats[b_arg]};
+          plan.arg_params = ap;
+          plan.arg_min_floats = am;
+          plan.flops = 2ull * (uint64_t)M * (uint64_t)N * (uint64_t)K;
+          plan.algorithmic_bytes = 4ull * (uint64_t)(M * K + K * N + M * N);
+          plan.scratch_floats = {(uint64_t)(M * K), (uint64_t)(N * K), (uint64_t)(N * K)};
+          plan.note += strprintf("; contraction %lldx%lldx%lld -> tcgen05 3xTF32", (long long)M, (long long)N, (long long)K);
+          plan.source = "// contraction pattern: runs the precompiled TMA + tcgen05 3xTF32 pipeline (gemm_3xtf32.cu)\n";
+          return plan;
+        }
+      }
+    }
+    emit_reduce(plan, prog, n_args, dev);
+  } else {
+    plan.kind = PLAN_ELEMENTWISE;
+    emit_elementwise(plan, prog, n_args, dev, 0);
+  }
+  return plan;
+}
+
+}  // namespace cc

@@ -1,0 +1,51 @@
+// codegen.h — Trees graph -> execution plan (pattern matching + CUDA C++ generated from the sm_100a templates).
+// Replaces OpenCLKernelBuilder.generateKernelSourceCode (OpenCLKernelBuilder.scala:135-221) and the per-node
+// emitters (:251-326, 348-455, 516-571, 632-652).
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "ir.h"
+
+namespace cc {
+
+enum PlanKind { PLAN_ELEMENTWISE = 0, PLAN_AXIS_REDUCE = 1, PLAN_CONTRACTION = 2, PLAN_TILED_TRANSPOSE = 3 };
+
+enum { ARG_OUT = -1, ARG_SCRATCH0 = -2 /* -2-k = scratch k */ };
+
+struct LaunchSpec {
+  std::string entry;  // __global__ name inside the generated module
+  uint32_t grid[3] = {1, 1, 1};
+  uint32_t block[3] = {1, 1, 1};
+  uint32_t smem = 0;
+  std::vector<int> args;  // >= 0: plan argument i; ARG_OUT; ARG_SCRATCH0 - k
+};
+
+struct Plan {
+  int kind = PLAN_ELEMENTWISE;
+  std::string source;                  // generated CUDA C++ (without the template prelude)
+  std::vector<LaunchSpec> launches;    // empty for PLAN_CONTRACTION (runs the precompiled tcgen05 pipeline)
+  std::vector<uint32_t> arg_params;    // tree parameter ordinal of each buffer argument
+  std::vector<uint64_t> arg_min_floats;  // minimum length each argument buffer must have
+  std::vector<uint64_t> scratch_floats;
+  uint64_t out_floats = 0;
+  uint64_t algorithmic_bytes = 0;
+  uint64_t flops = 0;
+  int64_t M = 0, N = 0, K = 0;  // contraction
+  std::string note;             // human-readable description of the choices made (kept in the kernel source header)
+};
+
+struct DeviceProps {
+  int sm_count = 148;
+  int max_smem = 227 * 1024;
+  bool contraction = true;  // lower sum_t A[i,t]*B[t,k] to the tcgen05 pipeline
+};
+
+Plan make_plan(const Tree& t, const DeviceProps& dev);
+
+// K:14-32 — `new DecimalFormat()` (<= 3 fraction digits, HALF_EVEN) as applied to every affine coefficient before it
+// is pasted into the kernel text; returns the value the generated code actually uses.
+double java_decimal_round(double v);
+
+}  // namespace cc

@@ -1,0 +1,61 @@
+// jit_templates.cuh — hand-written sm_100a device templates every generated kernel is instantiated from.
+// Embedded into libcompute_cuda.so as a string and prepended to the generated source before NVRTC
+// (--gpu-architecture=sm_100a). Replaces the scalar, one-work-item-per-element OpenCL C the reference generates
+// (OpenCLKernelBuilder.scala:135-221) — no OpenCL construct is translated; these are CUDA-native building blocks:
+//   * 128-bit read-only streaming loads that do not allocate in L1, 128-bit streaming stores;
+//   * float ops with the accuracy contract of the north star (<= 2 ulp): IEEE add/mul/div/sqrt, fma contraction on
+//     (the reference builds with -cl-unsafe-math-optimizations and FP_CONTRACT ON, OpenCL.scala:1131-1135);
+//   * warp-shuffle and shared-memory block reductions.
+
+// ---- memory ---------------------------------------------------------------------------------------------------------
+
+__device__ __forceinline__ float cc_ldg(const float* p) {
+  float v;
+  asm("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
+
+// p must be 16-byte aligned
+__device__ __forceinline__ void cc_ldg4(const float* p, float (&v)[4]) {
+  asm("ld.global.nc.L1::no_allocate.L2::256B.v4.f32 {%0, %1, %2, %3}, [%4];"
+      : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3])
+      : "l"(p));
+}
+
+__device__ __forceinline__ void cc_stg4(float* p, const float (&v)[4]) {
+  asm volatile("st.global.cs.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]) : "memory");
+}
+
+// ---- math -------------------------------------------------------------------------------------------------------------
+// CUDA's expf / logf / tanhf are documented at <= 2 / 1 / 2 ulp; kept behind cc_* names so that leaner or tighter
+// implementations can be swapped in without touching the generator.
+
+__device__ __forceinline__ float cc_exp(float x) { return expf(x); }
+__device__ __forceinline__ float cc_log(float x) { return logf(x); }
+__device__ __forceinline__ float cc_tanh(float x) { return tanhf(x); }
+
+// ---- reductions -------------------------------------------------------------------------------------------------------
+
+__device__ __forceinline__ float cc_warp_sum(float v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 16);
+  v += __shfl_xor_sync(0xffffffffu, v, 8);
+  v += __shfl_xor_sync(0xffffffffu, v, 4);
+  v += __shfl_xor_sync(0xffffffffu, v, 2);
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  return v;
+}
+
+// all 256 threads of the block must call; result valid in thread 0
+__device__ __forceinline__ float cc_block_sum_256(float v) {
+  __shared__ float cc_red_[8];
+  v = cc_warp_sum(v);
+  if ((threadIdx.x & 31) == 0) cc_red_[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    v = threadIdx.x < 8 ? cc_red_[threadIdx.x] : 0.f;
+    v += __shfl_xor_sync(0xffffffffu, v, 4);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+  }
+  return v;
+}

@@ -1,0 +1,184 @@
+// kernels_basic.cu — precompiled sm_100a kernels for the hand-written programs of Tensors.scala:
+//   full-sum reduction   (replaces sequentialReductionProgram T:313-351 / parallelReductionProgram T:358-392)
+//   random               (T:432-443, Wang hash T:106-117)
+//   random_normal        (T:398-429)
+// Designed for B200: 128-bit streaming loads with 4 independent vectors in flight per thread, grid sized to the SM
+// count, warp-shuffle + shared-memory block reduction, deterministic last-block-done second stage (no float atomics).
+#include <cstdint>
+
+#include "builtin_kernels.h"
+#include "common.h"
+
+namespace cc {
+namespace {
+
+constexpr int kReduceThreads = 512;
+constexpr int kReduceMaxBlocks = 148 * 4 * 2;  // upper bound on partials for any sm_count <= 296
+
+__device__ __forceinline__ float4 ldg_stream4(const float4* p) {
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::256B.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p));
+  return v;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ float block_sum(float v, float* smem /* >= 32 floats */) {
+  v = warp_sum(v);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) smem[warp] = v;
+  __syncthreads();
+  if (warp == 0) {
+    v = lane < (blockDim.x >> 5) ? smem[lane] : 0.f;
+    v = warp_sum(v);
+  }
+  return v;  // valid in warp 0
+}
+
+__global__ void __launch_bounds__(kReduceThreads) reduce_sum_kernel(const float* __restrict__ in, uint64_t n, float* __restrict__ out,
+                                                                   float* __restrict__ partials, unsigned* __restrict__ counter) {
+  __shared__ float smem[32];
+  __shared__ bool is_last;
+  const uint64_t nvec = n >> 2;
+  const float4* in4 = reinterpret_cast<const float4*>(in);
+  const uint64_t stride = (uint64_t)gridDim.x * kReduceThreads;
+  uint64_t v = (uint64_t)blockIdx.x * kReduceThreads + threadIdx.x;
+  float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, a2 = a0, a3 = a0;
+  // 4 independent 128-bit loads in flight per thread per iteration
+  for (; v + 3 * stride < nvec; v += 4 * stride) {
+    float4 x0 = ldg_stream4(in4 + v);
+    float4 x1 = ldg_stream4(in4 + v + stride);
+    float4 x2 = ldg_stream4(in4 + v + 2 * stride);
+    float4 x3 = ldg_stream4(in4 + v + 3 * stride);
+    a0.x += x0.x; a0.y += x0.y; a0.z += x0.z; a0.w += x0.w;
+    a1.x += x1.x; a1.y += x1.y; a1.z += x1.z; a1.w += x1.w;
+    a2.x += x2.x; a2.y += x2.y; a2.z += x2.z; a2.w += x2.w;
+    a3.x += x3.x; a3.y += x3.y; a3.z += x3.z; a3.w += x3.w;
+  }
+  for (; v < nvec; v += stride) {
+    float4 x0 = ldg_stream4(in4 + v);
+    a0.x += x0.x; a0.y += x0.y; a0.z += x0.z; a0.w += x0.w;
+  }
+  float acc = ((a0.x + a1.x) + (a2.x + a3.x)) + ((a0.y + a1.y) + (a2.y + a3.y)) + (((a0.z + a1.z) + (a2.z + a3.z)) + ((a0.w + a1.w) + (a2.w + a3.w)));
+  // scalar tail (n % 4 elements) — one designated thread
+  if (blockIdx.x == 0 && threadIdx.x == 0)
+    for (uint64_t i = nvec << 2; i < n; ++i) acc += in[i];
+  acc = block_sum(acc, smem);
+  if (threadIdx.x == 0) {
+    partials[blockIdx.x] = acc;
+    __threadfence();
+    const unsigned done = atomicAdd(counter, 1u);
+    is_last = (done == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  // second stage: fixed order over the (<= kReduceMaxBlocks) partials
+  float p = 0.f;
+  for (unsigned i = threadIdx.x; i < gridDim.x; i += kReduceThreads) p += __ldcg(partials + i);
+  p = block_sum(p, smem);
+  if (threadIdx.x == 0) {
+    out[0] = p;
+    *counter = 0u;  // ready for the next launch on this stream
+  }
+}
+
+__device__ __forceinline__ uint32_t wang_hash(uint32_t value) {  // T:106-117
+  value = (value ^ 61u) ^ (value >> 16);
+  value *= 9u;
+  value ^= value << 4;
+  value *= 0x27d4eb2du;
+  value ^= value >> 15;
+  return value;
+}
+__device__ __forceinline__ uint32_t xorshift(uint32_t seed) {  // T:403-407
+  const uint32_t tmp1 = seed ^ (seed << 13);
+  const uint32_t tmp2 = tmp1 ^ (tmp1 >> 17);
+  return tmp2 ^ (tmp2 << 5);
+}
+__device__ __forceinline__ float u32_to_unit(uint32_t h) { return __uint2float_rn(h) * 2.3283064365386963e-10f; }  // h / 2^32
+
+__global__ void __launch_bounds__(256) random_kernel(float* __restrict__ out, uint64_t n, uint32_t seed) {
+  const uint64_t nvec = n >> 2;
+  const uint64_t stride = (uint64_t)gridDim.x * 256;
+  for (uint64_t v = (uint64_t)blockIdx.x * 256 + threadIdx.x; v < nvec; v += stride) {
+    const uint32_t i = (uint32_t)(v << 2);
+    float4 r;
+    r.x = u32_to_unit(wang_hash((i + 0u) ^ seed));
+    r.y = u32_to_unit(wang_hash((i + 1u) ^ seed));
+    r.z = u32_to_unit(wang_hash((i + 2u) ^ seed));
+    r.w = u32_to_unit(wang_hash((i + 3u) ^ seed));
+    __stcs(reinterpret_cast<float4*>(out) + v, r);
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+    const uint64_t i = (nvec << 2) + threadIdx.x;
+    out[i] = u32_to_unit(wang_hash((uint32_t)i ^ seed));
+  }
+}
+
+__global__ void __launch_bounds__(256) random_normal_kernel(float* __restrict__ out, uint64_t n, uint32_t seed) {
+  const uint64_t npair = (n + 1) >> 1;
+  const uint64_t stride = (uint64_t)gridDim.x * 256;
+  for (uint64_t p = (uint64_t)blockIdx.x * 256 + threadIdx.x; p < npair; p += stride) {
+    const uint32_t i = (uint32_t)p;
+    const uint32_t r1 = wang_hash(i ^ seed);
+    const uint32_t r2 = xorshift(r1);
+    const float u1 = u32_to_unit(r1);
+    const float u2 = u32_to_unit(r2);
+    const float r = sqrtf(-2.f * logf(u1));
+    const float theta = (2.f * 3.14159274101257f) * u2;  // 2 * M_PI_F
+    float s, c;
+    sincosf(theta, &s, &c);
+    const float z0 = r * c;
+    const float z1 = r * s;
+    if (2 * p + 1 < n) {
+      __stcs(reinterpret_cast<float2*>(out) + p, make_float2(z0, z1));
+    } else {
+      out[2 * p] = z0;
+    }
+  }
+}
+
+void check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) fail(CC_ERR_CUDA, strprintf("%s launch failed: %s", what, cudaGetErrorString(e)));
+}
+
+}  // namespace
+
+uint64_t reduce_sum_scratch_floats() { return kReduceMaxBlocks; }
+
+void launch_reduce_sum(const float* in, uint64_t n, float* out, float* scratch, unsigned* counter, int sm_count, cudaStream_t stream) {
+  const uint64_t nvec = n >> 2;
+  uint64_t want = (nvec + (uint64_t)kReduceThreads * 4 - 1) / ((uint64_t)kReduceThreads * 4);
+  uint64_t cap = (uint64_t)sm_count * 4;
+  if (cap > (uint64_t)kReduceMaxBlocks) cap = kReduceMaxBlocks;
+  unsigned grid = (unsigned)(want < 1 ? 1 : (want > cap ? cap : want));
+  reduce_sum_kernel<<<grid, kReduceThreads, 0, stream>>>(in, n, out, scratch, counter);
+  check_launch("reduce_sum");
+}
+
+void launch_random(float* out, uint64_t n, int32_t seed, cudaStream_t stream) {
+  uint64_t blocks = ((n >> 2) + 255) / 256;
+  if (blocks < 1) blocks = 1;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  random_kernel<<<(unsigned)blocks, 256, 0, stream>>>(out, n, (uint32_t)seed);
+  check_launch("random");
+}
+
+void launch_random_normal(float* out, uint64_t n, int32_t seed, cudaStream_t stream) {
+  uint64_t blocks = (((n + 1) >> 1) + 255) / 256;
+  if (blocks < 1) blocks = 1;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  random_normal_kernel<<<(unsigned)blocks, 256, 0, stream>>>(out, n, (uint32_t)seed);
+  check_launch("random_normal");
+}
+
+}  // namespace cc

@@ -1,0 +1,1103 @@
+// runtime.cpp — the cc_* half of the C ABI: context, stream pool, events, pooled device memory, pinned staging, the
+// structural kernel cache with NVRTC (sm_100a), launches, NCCL. Replaces trait OpenCL (OpenCL.scala:1139-1433) and the
+// launcher half of Tensors.scala (:1263-1392); see include/compute_cuda.h for the per-function citations.
+#include <dlfcn.h>
+#include <nccl.h>
+#include <nvrtc.h>
+
+#include <atomic>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <unordered_map>
+#include <unordered_set>
+#include <vector>
+
+#include "builtin_kernels.h"
+#include "codegen.h"
+#include "driver.h"
+#include "ir.h"
+#include "jit_templates_embed.h"
+
+namespace cc {
+namespace {
+
+struct Event {
+  CUevent ev = nullptr;
+  std::atomic<int> rc{1};
+};
+
+struct Buffer {
+  CUdeviceptr ptr = 0;
+  uint64_t n_floats = 0;
+  size_t bytes = 0;  // pooled block size (0 for wrapped memory)
+  bool owned = true;
+  std::atomic<int> rc{1};
+  Event* last_write = nullptr;
+  std::vector<Event*> reads;
+};
+
+struct Block {
+  CUdeviceptr ptr;
+  size_t bytes;
+  std::vector<Event*> pending;
+};
+
+struct Kernel {
+  Plan plan;
+  std::string full_source;
+  std::vector<char> cubin;
+  CUmodule mod = nullptr;
+  std::vector<CUfunction> fns;
+  bool loaded = false;
+  std::atomic<int> rc{1};
+  uint64_t hash = 0;
+  int last_hit = 0;
+};
+
+struct Nccl {
+  void* lib = nullptr;
+  decltype(&ncclGetUniqueId) GetUniqueId = nullptr;
+  decltype(&ncclCommInitRank) CommInitRank = nullptr;
+  decltype(&ncclCommDestroy) CommDestroy = nullptr;
+  decltype(&ncclAllReduce) AllReduce = nullptr;
+  decltype(&ncclAllGather) AllGather = nullptr;
+  decltype(&ncclBroadcast) Broadcast = nullptr;
+  decltype(&ncclGetErrorString) GetErrorString = nullptr;
+  ncclComm_t comm = nullptr;
+  int n_ranks = 0, rank = 0;
+  void load() {
+    if (lib) return;
+    lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) fail(CC_ERR_NCCL, strprintf("cannot load libnccl.so.2: %s", dlerror()));
+#define CC_NCCL(sym)                                                        \
+  sym = (decltype(sym))dlsym(lib, "nccl" #sym);                             \
+  if (!sym) fail(CC_ERR_NCCL, "libnccl.so.2 lacks nccl" #sym);
+    CC_NCCL(GetUniqueId) CC_NCCL(CommInitRank) CC_NCCL(CommDestroy) CC_NCCL(AllReduce) CC_NCCL(AllGather) CC_NCCL(Broadcast)
+        CC_NCCL(GetErrorString)
+#undef CC_NCCL
+  }
+  void check(ncclResult_t r, const char* what) {
+    if (r != ncclSuccess) fail(CC_ERR_NCCL, strprintf("%s failed: %s", what, GetErrorString ? GetErrorString(r) : "?"));
+  }
+};
+
+struct Runtime {
+  std::recursive_mutex mu;
+  bool initialized = false;
+  int ordinal = 0;
+  CUdevice dev = 0;
+  CUcontext ctx = nullptr;
+  cc_device_info_t info{};
+  std::vector<CUstream> streams;
+  size_t next_stream = 0;
+  int stream_count = 4;
+  CUstream h2d = nullptr, d2h = nullptr, aux = nullptr;
+  std::vector<CUevent> event_pool;
+  std::map<size_t, std::vector<Block>> pool;
+  size_t bytes_pooled = 0, bytes_in_use = 0;
+  std::unordered_set<Buffer*> buffers;
+  std::unordered_set<Event*> events;
+  std::unordered_set<Kernel*> kernels;
+  std::unordered_map<std::string, Kernel*> cache;
+  cc_stats_t stats{};
+  // builtin scratch
+  Buffer* reduce_scratch = nullptr;
+  CUdeviceptr reduce_counter = 0;
+  CUevent timer0 = nullptr, timer1 = nullptr;
+  Nccl nccl;
+};
+
+Runtime& rt() {
+  static Runtime* r = new Runtime();  // intentionally leaked: survives static destruction order
+  return *r;
+}
+
+struct Lock {
+  std::lock_guard<std::recursive_mutex> g;
+  Lock() : g(rt().mu) {}
+};
+
+void require_init() {
+  CC_REQUIRE(rt().initialized, CC_ERR_NOT_INITIALIZED, "cc_init has not been called (or failed): no CUDA context — there is no CPU fallback");
+  CC_CU(cuCtxSetCurrent(rt().ctx));
+}
+
+// ---- events ---------------------------------------------------------------------------------------------------------
+
+Event* new_event() {
+  Runtime& r = rt();
+  Event* e = new Event();
+  if (!r.event_pool.empty()) {
+    e->ev = r.event_pool.back();
+    r.event_pool.pop_back();
+  } else {
+    CC_CU(cuEventCreate(&e->ev, CU_EVENT_DISABLE_TIMING));
+  }
+  r.events.insert(e);
+  return e;
+}
+void retain(Event* e) { e->rc.fetch_add(1); }
+void release(Event* e) {
+  if (e->rc.fetch_sub(1) == 1) {
+    Runtime& r = rt();
+    r.events.erase(e);
+    if (r.initialized)
+      r.event_pool.push_back(e->ev);
+    delete e;
+  }
+}
+Event* as_event(cc_event h) {
+  Event* e = (Event*)(uintptr_t)h;
+  CC_REQUIRE(e && rt().events.count(e), CC_ERR_ILLEGAL_ARGUMENT, "invalid event handle");
+  return e;
+}
+Buffer* as_buffer(cc_buffer h) {
+  Buffer* b = (Buffer*)(uintptr_t)h;
+  CC_REQUIRE(b && rt().buffers.count(b), CC_ERR_ILLEGAL_ARGUMENT, "invalid buffer handle");
+  return b;
+}
+Kernel* as_kernel(cc_kernel h) {
+  Kernel* k = (Kernel*)(uintptr_t)h;
+  CC_REQUIRE(k && rt().kernels.count(k), CC_ERR_ILLEGAL_ARGUMENT, "invalid kernel handle");
+  return k;
+}
+
+// ---- streams & hazards ---------------------------------------------------------------------------------------------------
+
+CUstream pick_stream() {
+  Runtime& r = rt();
+  CUstream s = r.streams[r.next_stream % r.streams.size()];
+  r.next_stream++;
+  return s;
+}
+
+struct Op {
+  CUstream stream;
+  std::vector<Buffer*> reads, writes;
+};
+
+void op_begin(Op& op, const cc_event* waits, int n_waits) {
+  for (int i = 0; i < n_waits; ++i)
+    if (waits[i]) CC_CU(cuStreamWaitEvent(op.stream, as_event(waits[i])->ev, 0));
+  for (Buffer* b : op.reads)
+    if (b->last_write) CC_CU(cuStreamWaitEvent(op.stream, b->last_write->ev, 0));
+  for (Buffer* b : op.writes) {
+    if (b->last_write) CC_CU(cuStreamWaitEvent(op.stream, b->last_write->ev, 0));
+    for (Event* e : b->reads) CC_CU(cuStreamWaitEvent(op.stream, e->ev, 0));
+  }
+}
+
+void op_end(Op& op, cc_event* out_event) {
+  Event* e = new_event();
+  CC_CU(cuEventRecord(e->ev, op.stream));
+  for (Buffer* b : op.writes) {
+    if (b->last_write) release(b->last_write);
+    for (Event* x : b->reads) release(x);
+    b->reads.clear();
+    b->last_write = e;
+    retain(e);
+  }
+  for (Buffer* b : op.reads) {
+    bool also_written = false;
+    for (Buffer* w : op.writes) also_written |= (w == b);
+    if (also_written) continue;
+    if (b->reads.size() >= 16) {
+      // prune completed readers
+      std::vector<Event*> keep;
+      for (Event* x : b->reads) {
+        if (driver().cuEventQuery(x->ev) == CUDA_SUCCESS)
+          release(x);
+        else
+          keep.push_back(x);
+      }
+      b->reads.swap(keep);
+    }
+    b->reads.push_back(e);
+    retain(e);
+  }
+  if (out_event) {
+    *out_event = (cc_event)(uintptr_t)e;  // the creation reference goes to the caller
+  } else {
+    release(e);
+  }
+}
+
+// ---- memory pool ----------------------------------------------------------------------------------------------------------
+
+size_t size_class(size_t bytes) {
+  if (bytes < 512) bytes = 512;
+  if (bytes <= (1u << 20)) {
+    size_t p = 512;
+    while (p < bytes) p <<= 1;
+    return p;
+  }
+  const size_t g = 2u << 20;
+  return (bytes + g - 1) / g * g;
+}
+
+void trim_pool() {
+  Runtime& r = rt();
+  for (auto& kv : r.pool)
+    for (Block& b : kv.second) {
+      for (Event* e : b.pending) release(e);
+      driver().cuMemFree(b.ptr);
+    }
+  r.pool.clear();
+  r.bytes_pooled = 0;
+}
+
+Buffer* alloc_buffer(uint64_t n_floats) {
+  Runtime& r = rt();
+  size_t bytes = size_class((size_t)n_floats * 4);
+  Buffer* b = new Buffer();
+  b->n_floats = n_floats;
+  b->bytes = bytes;
+  r.stats.alloc_calls++;
+  auto it = r.pool.find(bytes);
+  if (it != r.pool.end() && !it->second.empty()) {
+    Block blk = std::move(it->second.back());
+    it->second.pop_back();
+    b->ptr = blk.ptr;
+    b->reads = std::move(blk.pending);
+    r.bytes_pooled -= bytes;
+    r.stats.pool_hits++;
+  } else {
+    CUresult res = driver().cuMemAlloc(&b->ptr, bytes);
+    if (res == CUDA_ERROR_OUT_OF_MEMORY) {
+      trim_pool();
+      res = driver().cuMemAlloc(&b->ptr, bytes);
+    }
+    if (res != CUDA_SUCCESS) {
+      delete b;
+      check_cu(res, "cuMemAlloc");
+    }
+  }
+  r.bytes_in_use += bytes;
+  r.buffers.insert(b);
+  return b;
+}
+
+void release(Buffer* b) {
+  if (b->rc.fetch_sub(1) != 1) return;
+  Runtime& r = rt();
+  r.buffers.erase(b);
+  if (b->owned && r.initialized) {
+    Block blk{b->ptr, b->bytes, std::move(b->reads)};
+    if (b->last_write) blk.pending.push_back(b->last_write);
+    r.pool[b->bytes].push_back(std::move(blk));
+    r.bytes_pooled += b->bytes;
+    r.bytes_in_use -= b->bytes;
+  } else {
+    if (b->last_write) release(b->last_write);
+    for (Event* e : b->reads) release(e);
+  }
+  delete b;
+}
+
+// ---- NVRTC ----------------------------------------------------------------------------------------------------------------
+
+void nvrtc_compile(Kernel& k) {
+  k.full_source = std::string("// ") + k.plan.note + "\n" + kJitTemplates + "\n" + k.plan.source;
+  nvrtcProgram prog;
+  nvrtcResult r = nvrtcCreateProgram(&prog, k.full_source.c_str(), "jit_kernel.cu", 0, nullptr, nullptr);
+  CC_REQUIRE(r == NVRTC_SUCCESS, CC_ERR_COMPILE, "nvrtcCreateProgram: %s", nvrtcGetErrorString(r));
+  const char* opts[] = {"--gpu-architecture=sm_100a", "--std=c++17", "--fmad=true", "-lineinfo", "--extra-device-vectorization"};
+  r = nvrtcCompileProgram(prog, 5, opts);
+  if (r != NVRTC_SUCCESS) {
+    size_t n = 0;
+    nvrtcGetProgramLogSize(prog, &n);
+    std::string log(n, '\0');
+    if (n) nvrtcGetProgramLog(prog, &log[0]);
+    nvrtcDestroyProgram(&prog);
+    fail(CC_ERR_COMPILE, strprintf("NVRTC (sm_100a) failed: %s\n%s\n---- source ----\n%s", nvrtcGetErrorString(r), log.c_str(),
+                                   k.full_source.c_str()));
+  }
+  size_t n = 0;
+  nvrtcGetCUBINSize(prog, &n);
+  k.cubin.resize(n);
+  nvrtcGetCUBIN(prog, k.cubin.data());
+  nvrtcDestroyProgram(&prog);
+}
+
+void ensure_loaded(Kernel& k) {
+  if (k.loaded) return;
+  if (!k.plan.launches.empty()) {
+    CC_CU(cuModuleLoadData(&k.mod, k.cubin.data()));
+    for (const LaunchSpec& ls : k.plan.launches) {
+      CUfunction f;
+      CC_CU(cuModuleGetFunction(&f, k.mod, ls.entry.c_str()));
+      k.fns.push_back(f);
+    }
+  }
+  k.loaded = true;
+}
+
+void release(Kernel* k) {
+  if (k->rc.fetch_sub(1) != 1) return;
+  Runtime& r = rt();
+  r.kernels.erase(k);
+  if (k->mod && r.initialized) driver().cuModuleUnload(k->mod);
+  delete k;
+}
+
+void join_all(CUstream target) {
+  Runtime& r = rt();
+  std::vector<CUstream> all = r.streams;
+  all.push_back(r.h2d);
+  all.push_back(r.d2h);
+  for (CUstream s : all) {
+    if (s == target) continue;
+    Event* e = new_event();
+    CC_CU(cuEventRecord(e->ev, s));
+    CC_CU(cuStreamWaitEvent(target, e->ev, 0));
+    release(e);
+  }
+}
+
+Buffer* reduce_scratch() {
+  Runtime& r = rt();
+  if (!r.reduce_scratch) {
+    r.reduce_scratch = alloc_buffer(reduce_sum_scratch_floats() + 64);
+    CC_CU(cuMemAlloc(&r.reduce_counter, 256));
+    CC_CU(cuMemsetD32Async(r.reduce_counter, 0, 64, r.streams[0]));
+    CC_CU(cuStreamSynchronize(r.streams[0]));
+  }
+  return r.reduce_scratch;
+}
+
+}  // namespace
+}  // namespace cc
+
+using namespace cc;
+
+extern "C" {
+
+const char* cc_last_error(void) { return last_error_cstr(); }
+const char* cc_version(void) { return "compute_cuda 0.1 (sm_100a)"; }
+int cc_is_initialized(void) { return rt().initialized ? 1 : 0; }
+
+int cc_init(int device_ordinal) {
+  return guarded([&] {
+    Lock lock;
+    Runtime& r = rt();
+    if (r.initialized) return;
+    driver().load();
+    CC_CU(cuInit(0));
+    int count = 0;
+    CC_CU(cuDeviceGetCount(&count));
+    CC_REQUIRE(count > 0, CC_ERR_NO_DRIVER, "no CUDA device visible — this backend has no CPU fallback");
+    if (device_ordinal < 0) {
+      const char* lr = getenv("LOCAL_RANK");
+      device_ordinal = lr ? atoi(lr) % count : 0;
+    }
+    CC_REQUIRE(device_ordinal < count, CC_ERR_ILLEGAL_ARGUMENT, "device %d out of range (%d visible)", device_ordinal, count);
+    r.ordinal = device_ordinal;
+    CC_CU(cuDeviceGet(&r.dev, device_ordinal));
+    CC_CU(cuDevicePrimaryCtxRetain(&r.ctx, r.dev));
+    CC_CU(cuCtxSetCurrent(r.ctx));
+    cc_device_info_t& di = r.info;
+    memset(&di, 0, sizeof di);
+    di.ordinal = device_ordinal;
+    auto attr = [&](CUdevice_attribute a) {
+      int v = 0;
+      CC_CU(cuDeviceGetAttribute(&v, a, r.dev));
+      return v;
+    };
+    di.sm_count = attr(CU_DEVICE_ATTRIBUTE_MULTIPROCESSOR_COUNT);
+    di.cc_major = attr(CU_DEVICE_ATTRIBUTE_COMPUTE_CAPABILITY_MAJOR);
+    di.cc_minor = attr(CU_DEVICE_ATTRIBUTE_COMPUTE_CAPABILITY_MINOR);
+    di.max_smem_per_block = attr(CU_DEVICE_ATTRIBUTE_MAX_SHARED_MEMORY_PER_BLOCK_OPTIN);
+    di.l2_bytes = attr(CU_DEVICE_ATTRIBUTE_L2_CACHE_SIZE);
+    di.sm_clock_khz = attr(CU_DEVICE_ATTRIBUTE_CLOCK_RATE);
+    di.mem_clock_khz = attr(CU_DEVICE_ATTRIBUTE_MEMORY_CLOCK_RATE);
+    size_t total = 0;
+    CC_CU(cuDeviceTotalMem(&total, r.dev));
+    di.total_mem = (int64_t)total;
+    CC_CU(cuDeviceGetName(di.name, sizeof di.name, r.dev));
+    if (di.cc_major != 10) {
+      driver().cuDevicePrimaryCtxRelease(r.dev);
+      fail(CC_ERR_UNSUPPORTED, strprintf("device %d (%s) is sm_%d%d; this backend only generates sm_100a code", device_ordinal, di.name,
+                                         di.cc_major, di.cc_minor));
+    }
+    for (int i = 0; i < r.stream_count; ++i) {
+      CUstream s;
+      CC_CU(cuStreamCreate(&s, CU_STREAM_NON_BLOCKING));
+      r.streams.push_back(s);
+    }
+    // copies always get their own streams so H2D / compute / D2H of independent chunks overlap
+    CC_CU(cuStreamCreate(&r.h2d, CU_STREAM_NON_BLOCKING));
+    CC_CU(cuStreamCreate(&r.d2h, CU_STREAM_NON_BLOCKING));
+    CC_CU(cuStreamCreate(&r.aux, CU_STREAM_NON_BLOCKING));
+    CC_CU(cuEventCreate(&r.timer0, CU_EVENT_DEFAULT));
+    CC_CU(cuEventCreate(&r.timer1, CU_EVENT_DEFAULT));
+    r.initialized = true;
+  });
+}
+
+int cc_set_stream_count(int n) {
+  return guarded([&] {
+    Lock lock;
+    CC_REQUIRE(n >= 1 && n <= 32, CC_ERR_ILLEGAL_ARGUMENT, "stream count must be in [1, 32]");
+    CC_REQUIRE(!rt().initialized, CC_ERR_ILLEGAL_ARGUMENT, "cc_set_stream_count must be called before cc_init");
+    rt().stream_count = n;
+  });
+}
+
+int cc_shutdown(void) {
+  return guarded([&] {
+    Lock lock;
+    Runtime& r = rt();
+    if (!r.initialized) return;
+    CC_CU(cuCtxSetCurrent(r.ctx));
+    driver().cuCtxSynchronize();
+    if (r.nccl.comm) {
+      r.nccl.CommDestroy(r.nccl.comm);
+      r.nccl.comm = nullptr;
+    }
+    for (auto& kv : r.cache) release(kv.second);
+    r.cache.clear();
+    if (r.reduce_scratch) {
+      release(r.reduce_scratch);
+      r.reduce_scratch = nullptr;
+      driver().cuMemFree(r.reduce_counter);
+      r.reduce_counter = 0;
+    }
+    trim_pool();
+    // anything the caller still holds stays valid as a handle but its device memory is gone with the context
+    for (Buffer* b : r.buffers)
+      if (b->owned && b->ptr) {
+        driver().cuMemFree(b->ptr);
+        b->ptr = 0;
+        b->owned = false;
+      }
+    for (Kernel* k : r.kernels)
+      if (k->mod) {
+        driver().cuModuleUnload(k->mod);
+        k->mod = nullptr;
+        k->loaded = false;
+        k->fns.clear();
+      }
+    for (CUevent e : r.event_pool) driver().cuEventDestroy(e);
+    r.event_pool.clear();
+    for (Event* e : r.events) {
+      driver().cuEventDestroy(e->ev);
+      e->ev = nullptr;
+    }
+    std::unordered_set<CUstream> uniq(r.streams.begin(), r.streams.end());
+    uniq.insert(r.h2d);
+    uniq.insert(r.d2h);
+    uniq.insert(r.aux);
+    for (CUstream s : uniq) driver().cuStreamDestroy(s);
+    r.streams.clear();
+    driver().cuEventDestroy(r.timer0);
+    driver().cuEventDestroy(r.timer1);
+    driver().cuDevicePrimaryCtxRelease(r.dev);
+    r.ctx = nullptr;
+    r.bytes_in_use = r.bytes_pooled = 0;
+    r.initialized = false;
+  });
+}
+
+int cc_device_count(int* out) {
+  return guarded([&] {
+    CC_REQUIRE(out, CC_ERR_ILLEGAL_ARGUMENT, "null output");
+    driver().load();
+    CC_CU(cuInit(0));
+    CC_CU(cuDeviceGetCount(out));
+  });
+}
+
+int cc_device_info(cc_device_info_t* out) {
+  return guarded([&] {
+    Lock lock;
+    require_init();
+    CC_REQUIRE(out, CC_ERR_ILLEGAL_ARGUMENT, "null output");
+    *out = rt().info;
+  });
+}
+
+// ---- memory -----------------------------------------------------------------------------------------------------------------
+
+int cc_buffer_alloc(uint64_t n_floats, cc_buffer* out) {
+  return guarded([&] {
+    Lock lock;
+    require_init();
+    CC_REQUIRE(out, CC_ERR_ILLEGAL_ARGUMENT, "null output");
+    *out = (cc_buffer)(uintptr_t)alloc_buffer(n_floats);
+  });
+}
+
+int cc_buffer_upload(cc_buffer buf, const float* host, uint64_t n_floats, const cc_event* waits, int n_waits, cc_event* out_event) {
+  return guarded([&] {
+    Event* done = nullptr;
+    {
+      Lock lock;
+      require_init();
+      Buffer* b = as_buffer(buf);
+      CC_REQUIRE(n_floats <= b->n_floats, CC_ERR_ILLEGAL_ARGUMENT, "upload of %llu floats into a buffer of %llu",
+                 (unsigned long long)n_floats, (unsigned long long)b->n_floats);
+      CC_REQUIRE(host || n_floats == 0, CC_ERR_ILLEGAL_ARGUMENT, "null host pointer");
+      Op op{rt().h2d, {}, {b}};
+      op_begin(op, waits, n_waits);
+      if (n_floats) CC_CU(cuMemcpyHtoDAsync(b->ptr, host, (size_t)n_floats * 4, op.stream));
+      rt().stats.h2d_bytes += n_floats * 4;
+      cc_event ev = 0;
+      op_end(op, &ev);
+      done = (Event*)(uintptr_t)ev;
+      if (out_event) {
+        *out_event = ev;
+        return;
+      }
+    }
+    CC_CU(cuEventSynchronize(done->ev));
+    Lock lock;
+    release(done);
+  });
+}
+
+int cc_buffer_from_host(const float* host, uint64_t n_floats, cc_buffer* out, cc_event* out_event) {
+  cc_buffer b = 0;
+  int st = cc_buffer_alloc(n_floats, &b);
+  if (st != CC_OK) return st;
+  st = cc_buffer_upload(b, host, n_floats, nullptr, 0, out_event);
+  if (st != CC_OK) {
+    std::string keep = cc_last_error();
+    cc_buffer_release(b);
+    set_last_error(keep);
+    return st;
+  }
+  *out = b;
+  return CC_OK;
+}
+
+int cc_buffer_wrap(uint64_t device_ptr, uint64_t n_floats, cc_buffer* out) {
+  return guarded([&] {
+    Lock lock;
+    require_init();
+    CC_REQUIRE(out, CC_ERR_ILLEGAL_ARGUMENT, "null output");
+    CC_REQUIRE(device_ptr % 16 == 0, CC_ERR_ILLEGAL_ARGUMENT, "wrapped device memory must be 16-byte aligned");
+    Buffer* b = new Buffer();
+    b->ptr = (CUdeviceptr)device_ptr;
+    b->n_floats = n_floats;
+    b->owned = false;
+    rt().buffers.insert(b);
+    *out = (cc_buffer)(uintptr_t)b;
+  });
+}
+
+int cc_buffer_retain(cc_buffer h) {
+  return guarded([&] {
+    Lock lock;
+    as_buffer(h)->rc.fetch_add(1);
+  });
+}
+int cc_buffer_release(cc_buffer h) {
+  return guarded([&] {
+    Lock lock;
+    release(as_buffer(h));
+  });
+}
+int cc_buffer_device_ptr(cc_buffer h, uint64_t* out) {
+  return guarded([&] {
+    Lock lock;
+    CC_REQUIRE(out, CC_ERR_ILLEGAL_ARGUMENT, "null output");
+    *out = (uint64_t)as_buffer(h)->ptr;
+  });
+}
+int cc_buffer_length(cc_buffer h, uint64_t* out) {
+  return guarded([&] {
+    Lock lock;
+    CC_REQUIRE(out, CC_ERR_ILLEGAL_ARGUMENT, "null output");
+    *out = as_buffer(h)->n_floats;
+  });
+}
+
+int cc_buffer_to_host(cc_buffer h, uint64_t offset, float* host, uint64_t n_floats, const cc_event* waits, int n_waits,
+                      cc_event* out_event) {
+  return guarded([&] {
+    Event* done = nullptr;
+    {
+      Lock lock;
+      require_init();
+      Buffer* b = as_buffer(h);
+      CC_REQUIRE(offset + n_floats <= b->n_floats, CC_ERR_ILLEGAL_ARGUMENT, "read of [%llu, %llu) from a buffer of %llu floats",
+                 (unsigned long long)offset, (unsigned long long)(offset + n_floats), (unsigned long long)b->n_floats);
+      CC_REQUIRE(host || n_floats == 0, CC_ERR_ILLEGAL_ARGUMENT, "null host pointer");
+      Op op{rt().d2h, {b}, {}};
+      op_begin(op, waits, n_waits);
+      if (n_floats) CC_CU(cuMemcpyDtoHAsync(host, b->ptr + offset * 4, (size_t)n_floats * 4, op.stream));
+      rt().stats.d2h_bytes += n_floats * 4;
+      cc_event ev = 0;
+      op_end(op, &ev);
+      done = (Event*)(uintptr_t)ev;
+      if (out_event) {
+        *out_event = ev;
+        return;
+      }
+    }
+    CC_CU(cuEventSynchronize(done->ev));
+    Lock lock;
+    release(done);
+  });
+}
+
+int cc_host_alloc(uint64_t bytes, void** out) {
+  return guarded([&] {
+    Lock lock;
+    require_init();
+    CC_REQUIRE(out, CC_ERR_ILLEGAL_ARGUMENT, "null output");
+    CC_CU(cuMemHostAlloc(out, bytes ? bytes : 1, CU_MEMHOSTALLOC_PORTABLE));
+  });
+}
+int cc_host_free(void* p) {
+  return guarded([&] {
+    Lock lock;
+    require_init();
+    if (p) CC_CU(cuMemFreeHost(p));
+  });
+}
+
+// ---- events -----------------------------------------------------------------------------------------------------------------
+
+int cc_event_retain(cc_event h) {
+  return guarded([&] {
+    Lock lock;
+    retain(as_event(h));
+  });
+}
+int cc_event_release(cc_event h) {
+  return guarded([&] {
+    Lock lock;
+    release(as_event(h));
+  });
+}
+int cc_event_wait(cc_event h) {
+  return guarded([&] {
+    CUevent ev;
+    {
+      Lock lock;
+      require_init();
+      ev = as_event(h)->ev;
+    }
+    CC_CU(cuEventSynchronize(ev));
+  });
+}
+int cc_event_query(cc_event h, int* out_done) {
+  return guarded([&] {
+    Lock lock;
+    require_init();
+    CC_REQUIRE(out_done, CC_ERR_ILLEGAL_ARGUMENT, "null output");
+    CUresult r = driver().cuEventQuery(as_event(h)->ev);
+    if (r == CUDA_SUCCESS)
+      *out_done = 1;
+    else if (r == CUDA_ERROR_NOT_READY)
+      *out_done = 0;
+    else
+      check_cu(r, "cuEventQuery");
+  });
+}
+
+namespace {
+struct Callback {
+  cc_event_callback cb;
+  void* user;
+};
+void CUDA_CB host_trampoline(void* p) {
+  Callback* c = (Callback*)p;
+  c->cb(c->user, 0);
+  delete c;
+}
+}  // namespace
+
+int cc_event_on_complete(cc_event h, cc_event_callback cb, void* user) {
+  return guarded([&] {
+    Lock lock;
+    require_init();
+    CC_REQUIRE(cb, CC_ERR_ILLEGAL_ARGUMENT, "null callback");
+    Event* e = as_event(h);
+    CC_CU(cuStreamWaitEvent(rt().aux, e->ev, 0));
+    CC_CU(cuLaunchHostFunc(rt().aux, host_trampoline, new Callback{cb, user}));
+  });
+}
+
+int cc_synchronize(void) {
+  return guarded([&] {
+    {
+      Lock lock;
+      require_init();
+    }
+    CC_CU(cuCtxSynchronize());
+  });
+}
+
+// ---- kernels ----------------------------------------------------------------------------------------------------------------
+
+int cc_compile(const void* blob, uint64_t n_bytes, cc_kernel* out) { return cc_compile_ex(blob, n_bytes, out, nullptr, 0, nullptr); }
+
+int cc_compile_ex(const void* blob, uint64_t n_bytes, cc_kernel* out, uint64_t* ids_out, int capacity, int* n_params_out) {
+  return guarded([&] {
+    CC_REQUIRE(out, CC_ERR_ILLEGAL_ARGUMENT, "null output");
+    Tree t = parse_tree(blob, n_bytes);
+    canonicalize(t);
+    if (n_params_out) *n_params_out = (int)t.params.size();
+    if (ids_out) {
+      CC_REQUIRE(capacity >= (int)t.params.size(), CC_ERR_ILLEGAL_ARGUMENT, "param id capacity %d < %zu", capacity, t.params.size());
+      for (size_t i = 0; i < t.params.size(); ++i) ids_out[i] = t.nodes[t.params[i]].param_id;
+    }
+    Lock lock;
+    Runtime& r = rt();
+    auto it = r.cache.find(t.key);
+    if (it != r.cache.end()) {
+      Kernel* k = it->second;
+      k->rc.fetch_add(1);
+      k->last_hit = 1;
+      r.stats.cache_hits++;
+      *out = (cc_kernel)(uintptr_t)k;
+      return;
+    }
+    DeviceProps dp;
+    dp.contraction = gemm_available() && !getenv("CC_DISABLE_CONTRACTION");
+    if (r.initialized) {
+      dp.sm_count = r.info.sm_count;
+      dp.max_smem = r.info.max_smem_per_block;
+    }
+    std::unique_ptr<Kernel> k(new Kernel());
+    k->plan = make_plan(t, dp);
+    k->hash = t.hash;
+    if (!k->plan.launches.empty())
+      nvrtc_compile(*k);
+    else
+      k->full_source = std::string("// ") + k->plan.note + "\n" + k->plan.source;
+    r.stats.compiles++;
+    Kernel* raw = k.release();
+    raw->rc.store(2);  // cache + caller
+    r.kernels.insert(raw);
+    r.cache.emplace(std::move(t.key), raw);
+    *out = (cc_kernel)(uintptr_t)raw;
+  });
+}
+
+int cc_kernel_retain(cc_kernel h) {
+  return guarded([&] {
+    Lock lock;
+    as_kernel(h)->rc.fetch_add(1);
+  });
+}
+int cc_kernel_release(cc_kernel h) {
+  return guarded([&] {
+    Lock lock;
+    release(as_kernel(h));
+  });
+}
+int cc_kernel_info(cc_kernel h, cc_kernel_info_t* out) {
+  return guarded([&] {
+    Lock lock;
+    CC_REQUIRE(out, CC_ERR_ILLEGAL_ARGUMENT, "null output");
+    Kernel* k = as_kernel(h);
+    out->kind = k->plan.kind;
+    out->cache_hit = k->last_hit;
+    out->n_args = (int32_t)k->plan.arg_params.size();
+    out->n_launches = k->plan.kind == PLAN_CONTRACTION ? 3 : (int32_t)k->plan.launches.size();
+    out->out_floats = k->plan.out_floats;
+    out->algorithmic_bytes = k->plan.algorithmic_bytes;
+    out->flops = k->plan.flops;
+    out->structural_hash = k->hash;
+  });
+}
+int cc_kernel_arg_param(cc_kernel h, int i, int32_t* out) {
+  return guarded([&] {
+    Lock lock;
+    Kernel* k = as_kernel(h);
+    CC_REQUIRE(out && i >= 0 && i < (int)k->plan.arg_params.size(), CC_ERR_ILLEGAL_ARGUMENT, "argument index %d out of range", i);
+    *out = (int32_t)k->plan.arg_params[i];
+  });
+}
+int cc_kernel_source(cc_kernel h, const char** out) {
+  return guarded([&] {
+    Lock lock;
+    CC_REQUIRE(out, CC_ERR_ILLEGAL_ARGUMENT, "null output");
+    *out = as_kernel(h)->full_source.c_str();
+  });
+}
+
+namespace {
+void gemm_on_stream(Buffer* a, Buffer* b, Buffer* c, int64_t m, int64_t n, int64_t k, const std::vector<Buffer*>& scratch, CUstream s) {
+  GemmWorkspace ws{(float*)scratch[0]->ptr, (float*)scratch[1]->ptr, (float*)scratch[2]->ptr};
+  int launched = launch_gemm_3xtf32((const float*)a->ptr, (const float*)b->ptr, (float*)c->ptr, m, n, k, ws, rt().info.sm_count,
+                                    (TensorMapEncodeFn)driver().cuTensorMapEncodeTiled, (cudaStream_t)s);
+  rt().stats.device_kernels += (uint64_t)launched;
+}
+}  // namespace
+
+int cc_launch(cc_kernel h, const cc_buffer* args, int n_args, cc_buffer out, const cc_event* waits, int n_waits, cc_event* out_event) {
+  return guarded([&] {
+    Lock lock;
+    require_init();
+    Runtime& r = rt();
+    Kernel* k = as_kernel(h);
+    const Plan& p = k->plan;
+    CC_REQUIRE(n_args == (int)p.arg_params.size(), CC_ERR_ILLEGAL_ARGUMENT, "kernel expects %zu buffers, got %d", p.arg_params.size(), n_args);
+    Buffer* ob = as_buffer(out);
+    CC_REQUIRE(ob->n_floats >= p.out_floats, CC_ERR_ILLEGAL_ARGUMENT, "output buffer has %llu floats, kernel writes %llu",
+               (unsigned long long)ob->n_floats, (unsigned long long)p.out_floats);
+    std::vector<Buffer*> in;
+    for (int i = 0; i < n_args; ++i) {
+      Buffer* b = as_buffer(args[i]);
+      CC_REQUIRE(b->n_floats >= p.arg_min_floats[i], CC_ERR_ILLEGAL_ARGUMENT, "argument %d has %llu floats, kernel reads up to %llu", i,
+                 (unsigned long long)b->n_floats, (unsigned long long)p.arg_min_floats[i]);
+      CC_REQUIRE(b != ob, CC_ERR_ILLEGAL_ARGUMENT, "output buffer aliases argument %d", i);
+      in.push_back(b);
+    }
+    ensure_loaded(*k);
+    std::vector<Buffer*> scratch;
+    for (uint64_t n : p.scratch_floats) scratch.push_back(alloc_buffer(n));
+    Op op{pick_stream(), in, {ob}};
+    for (Buffer* s : scratch) op.writes.push_back(s);
+    op_begin(op, waits, n_waits);
+    if (p.kind == PLAN_CONTRACTION) {
+      gemm_on_stream(in[0], in[1], ob, p.M, p.N, p.K, scratch, op.stream);
+    } else {
+      for (size_t li = 0; li < p.launches.size(); ++li) {
+        const LaunchSpec& ls = p.launches[li];
+        std::vector<CUdeviceptr> ptrs;
+        std::vector<void*> argv;
+        ptrs.reserve(ls.args.size());
+        for (int a : ls.args) {
+          if (a >= 0)
+            ptrs.push_back(in[a]->ptr);
+          else if (a == ARG_OUT)
+            ptrs.push_back(ob->ptr);
+          else
+            ptrs.push_back(scratch[ARG_SCRATCH0 - a]->ptr);
+        }
+        for (CUdeviceptr& q : ptrs) argv.push_back(&q);
+        CC_CU(cuLaunchKernel(k->fns[li], ls.grid[0], ls.grid[1], ls.grid[2], ls.block[0], ls.block[1], ls.block[2], ls.smem, op.stream,
+                             argv.data(), nullptr));
+        r.stats.device_kernels++;
+      }
+    }
+    r.stats.launches++;
+    op_end(op, out_event);
+    for (Buffer* s : scratch) release(s);
+  });
+}
+
+int cc_reduce_sum(cc_buffer in, uint64_t n_floats, cc_buffer out, const cc_event* waits, int n_waits, cc_event* out_event) {
+  return guarded([&] {
+    Lock lock;
+    require_init();
+    Runtime& r = rt();
+    Buffer* ib = as_buffer(in);
+    Buffer* ob = as_buffer(out);
+    CC_REQUIRE(n_floats <= ib->n_floats && ob->n_floats >= 1 && ib != ob, CC_ERR_ILLEGAL_ARGUMENT, "bad reduce_sum arguments");
+    Buffer* sc = reduce_scratch();
+    // the shared scratch + counter serialise full reductions on one stream
+    Op op{r.streams[0], {ib}, {ob, sc}};
+    op_begin(op, waits, n_waits);
+    launch_reduce_sum((const float*)ib->ptr, n_floats, (float*)ob->ptr, (float*)sc->ptr, (unsigned*)r.reduce_counter, r.info.sm_count,
+                      (cudaStream_t)op.stream);
+    r.stats.launches++;
+    r.stats.device_kernels++;
+    op_end(op, out_event);
+  });
+}
+
+int cc_random(cc_buffer out, uint64_t n_floats, int32_t seed, cc_event* out_event) {
+  return guarded([&] {
+    Lock lock;
+    require_init();
+    Buffer* ob = as_buffer(out);
+    CC_REQUIRE(n_floats <= ob->n_floats, CC_ERR_ILLEGAL_ARGUMENT, "random: buffer too small");
+    Op op{pick_stream(), {}, {ob}};
+    op_begin(op, nullptr, 0);
+    launch_random((float*)ob->ptr, n_floats, seed, (cudaStream_t)op.stream);
+    rt().stats.launches++;
+    rt().stats.device_kernels++;
+    op_end(op, out_event);
+  });
+}
+
+int cc_random_normal(cc_buffer out, uint64_t n_floats, int32_t seed, cc_event* out_event) {
+  return guarded([&] {
+    Lock lock;
+    require_init();
+    Buffer* ob = as_buffer(out);
+    CC_REQUIRE(n_floats <= ob->n_floats, CC_ERR_ILLEGAL_ARGUMENT, "randomNormal: buffer too small");
+    Op op{pick_stream(), {}, {ob}};
+    op_begin(op, nullptr, 0);
+    launch_random_normal((float*)ob->ptr, n_floats, seed, (cudaStream_t)op.stream);
+    rt().stats.launches++;
+    rt().stats.device_kernels++;
+    op_end(op, out_event);
+  });
+}
+
+int cc_matmul_3xtf32(cc_buffer a, cc_buffer b, cc_buffer c, int64_t m, int64_t n, int64_t k, const cc_event* waits, int n_waits,
+                     cc_event* out_event) {
+  return guarded([&] {
+    Lock lock;
+    require_init();
+    Buffer* ab = as_buffer(a);
+    Buffer* bb = as_buffer(b);
+    Buffer* cb = as_buffer(c);
+    CC_REQUIRE(m > 0 && n > 0 && k > 0 && m % 128 == 0 && n % 128 == 0 && k % 32 == 0, CC_ERR_UNSUPPORTED,
+               "cc_matmul_3xtf32 needs M %% 128 == 0, N %% 128 == 0, K %% 32 == 0 (got %lld x %lld x %lld)", (long long)m, (long long)n,
+               (long long)k);
+    CC_REQUIRE(ab->n_floats >= (uint64_t)(m * k) && bb->n_floats >= (uint64_t)(k * n) && cb->n_floats >= (uint64_t)(m * n),
+               CC_ERR_ILLEGAL_ARGUMENT, "matmul buffers too small");
+    CC_REQUIRE(cb != ab && cb != bb, CC_ERR_ILLEGAL_ARGUMENT, "matmul output aliases an input");
+    std::vector<Buffer*> scratch{alloc_buffer((uint64_t)(m * k)), alloc_buffer((uint64_t)(n * k)), alloc_buffer((uint64_t)(n * k))};
+    Op op{pick_stream(), {ab, bb}, {cb}};
+    for (Buffer* s : scratch) op.writes.push_back(s);
+    op_begin(op, waits, n_waits);
+    gemm_on_stream(ab, bb, cb, m, n, k, scratch, op.stream);
+    rt().stats.launches++;
+    op_end(op, out_event);
+    for (Buffer* s : scratch) release(s);
+  });
+}
+
+// ---- stats / timing -----------------------------------------------------------------------------------------------------------
+
+int cc_stats(cc_stats_t* out) {
+  return guarded([&] {
+    Lock lock;
+    CC_REQUIRE(out, CC_ERR_ILLEGAL_ARGUMENT, "null output");
+    *out = rt().stats;
+    out->bytes_in_use = rt().bytes_in_use;
+    out->bytes_pooled = rt().bytes_pooled;
+  });
+}
+int cc_stats_reset(void) {
+  return guarded([&] {
+    Lock lock;
+    rt().stats = cc_stats_t{};
+  });
+}
+
+int cc_timer_start(void) {
+  return guarded([&] {
+    Lock lock;
+    require_init();
+    Runtime& r = rt();
+    join_all(r.aux);
+    CC_CU(cuEventRecord(r.timer0, r.aux));
+    std::unordered_set<CUstream> uniq(r.streams.begin(), r.streams.end());
+    uniq.insert(r.h2d);
+    uniq.insert(r.d2h);
+    for (CUstream s : uniq)
+      if (s != r.aux) CC_CU(cuStreamWaitEvent(s, r.timer0, 0));
+  });
+}
+int cc_timer_stop(float* out_ms) {
+  return guarded([&] {
+    {
+      Lock lock;
+      require_init();
+      Runtime& r = rt();
+      CC_REQUIRE(out_ms, CC_ERR_ILLEGAL_ARGUMENT, "null output");
+      join_all(r.aux);
+      CC_CU(cuEventRecord(r.timer1, r.aux));
+    }
+    CC_CU(cuEventSynchronize(rt().timer1));
+    CC_CU(cuEventElapsedTime(out_ms, rt().timer0, rt().timer1));
+  });
+}
+
+// ---- NCCL -------------------------------------------------------------------------------------------------------------------------
+
+int cc_comm_unique_id(void* out) {
+  return guarded([&] {
+    Lock lock;
+    CC_REQUIRE(out, CC_ERR_ILLEGAL_ARGUMENT, "null output");
+    Nccl& n = rt().nccl;
+    n.load();
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    n.check(n.GetUniqueId((ncclUniqueId*)out), "ncclGetUniqueId");
+  });
+}
+int cc_comm_init(const void* id, int n_ranks, int rank) {
+  return guarded([&] {
+    Lock lock;
+    require_init();
+    Nccl& n = rt().nccl;
+    n.load();
+    CC_REQUIRE(id && n_ranks >= 1 && rank >= 0 && rank < n_ranks, CC_ERR_ILLEGAL_ARGUMENT, "bad communicator arguments");
+    CC_REQUIRE(!n.comm, CC_ERR_ILLEGAL_ARGUMENT, "communicator already initialised");
+    ncclUniqueId uid;
+    memcpy(&uid, id, sizeof uid);
+    cudaSetDevice(rt().ordinal);
+    n.check(n.CommInitRank(&n.comm, n_ranks, uid, rank), "ncclCommInitRank");
+    n.n_ranks = n_ranks;
+    n.rank = rank;
+  });
+}
+int cc_comm_destroy(void) {
+  return guarded([&] {
+    Lock lock;
+    Nccl& n = rt().nccl;
+    if (n.comm) {
+      driver().cuCtxSynchronize();
+      n.check(n.CommDestroy(n.comm), "ncclCommDestroy");
+      n.comm = nullptr;
+      n.n_ranks = 0;
+    }
+  });
+}
+int cc_comm_info(int* out_n, int* out_rank) {
+  return guarded([&] {
+    Lock lock;
+    if (out_n) *out_n = rt().nccl.comm ? rt().nccl.n_ranks : 1;
+    if (out_rank) *out_rank = rt().nccl.comm ? rt().nccl.rank : 0;
+  });
+}
+
+int cc_allreduce_sum(cc_buffer buf, uint64_t n_floats, const cc_event* waits, int n_waits, cc_event* out_event) {
+  return guarded([&] {
+    Lock lock;
+    require_init();
+    Nccl& n = rt().nccl;
+    Buffer* b = as_buffer(buf);
+    CC_REQUIRE(n_floats <= b->n_floats, CC_ERR_ILLEGAL_ARGUMENT, "allreduce: buffer too small");
+    Op op{rt().streams[0], {}, {b}};
+    op_begin(op, waits, n_waits);
+    if (n.comm) n.check(n.AllReduce((const void*)b->ptr, (void*)b->ptr, n_floats, ncclFloat, ncclSum, n.comm, (cudaStream_t)op.stream), "ncclAllReduce");
+    op_end(op, out_event);
+  });
+}
+int cc_allgather(cc_buffer send, cc_buffer recv, uint64_t n_per_rank, const cc_event* waits, int n_waits, cc_event* out_event) {
+  return guarded([&] {
+    Lock lock;
+    require_init();
+    Nccl& n = rt().nccl;
+    Buffer* s = as_buffer(send);
+    Buffer* d = as_buffer(recv);
+    int ranks = n.comm ? n.n_ranks : 1;
+    CC_REQUIRE(n_per_rank <= s->n_floats && n_per_rank * ranks <= d->n_floats && s != d, CC_ERR_ILLEGAL_ARGUMENT, "allgather: bad buffers");
+    Op op{rt().streams[0], {s}, {d}};
+    op_begin(op, waits, n_waits);
+    if (n.comm)
+      n.check(n.AllGather((const void*)s->ptr, (void*)d->ptr, n_per_rank, ncclFloat, n.comm, (cudaStream_t)op.stream), "ncclAllGather");
+    else
+      CC_CU(cuMemcpyDtoDAsync(d->ptr, s->ptr, (size_t)n_per_rank * 4, op.stream));
+    op_end(op, out_event);
+  });
+}
+int cc_broadcast(cc_buffer buf, uint64_t n_floats, int root, const cc_event* waits, int n_waits, cc_event* out_event) {
+  return guarded([&] {
+    Lock lock;
+    require_init();
+    Nccl& n = rt().nccl;
+    Buffer* b = as_buffer(buf);
+    CC_REQUIRE(n_floats <= b->n_floats, CC_ERR_ILLEGAL_ARGUMENT, "broadcast: buffer too small");
+    Op op{rt().streams[0], {}, {b}};
+    op_begin(op, waits, n_waits);
+    if (n.comm) n.check(n.Broadcast((const void*)b->ptr, (void*)b->ptr, n_floats, ncclFloat, root, n.comm, (cudaStream_t)op.stream), "ncclBroadcast");
+    op_end(op, out_event);
+  });
+}
+
+}  // extern "C"

@@ -1,0 +1,783 @@
+// tensor.cpp — host-side mirror of Tensors.scala's lazy Tensor API on top of the cc_* C ABI, plus its flat ct_* C view.
+#include "tensor.h"
+
+#include <atomic>
+#include <charconv>
+#include <cmath>
+#include <cstring>
+
+#include "ndat.h"
+
+namespace compute {
+namespace cuda {
+
+using cc::Error;
+using cc::fail;
+using cc::strprintf;
+
+namespace {
+std::atomic<int64_t> g_live{0};
+
+void check(int status) {
+  if (status != CC_OK) throw Error(status, cc_last_error());
+}
+
+std::string shape_str(const Shape& s) {
+  std::string r = "[";
+  for (size_t i = 0; i < s.size(); ++i) r += (i ? "," : "") + std::to_string(s[i]);
+  return r + "]";
+}
+
+int64_t product(const Shape& s) {
+  int64_t p = 1;
+  for (int32_t d : s) p *= d;
+  return p;
+}
+
+void check_shape(const Shape& s) {
+  for (int32_t d : s) CC_REQUIRE(d >= 0, CC_ERR_ILLEGAL_ARGUMENT, "negative dimension in shape %s", shape_str(s).c_str());
+  CC_REQUIRE(s.size() <= 16, CC_ERR_ILLEGAL_ARGUMENT, "rank %zu > 16", s.size());
+}
+
+// deep expression chains (a 16384-term per-axis sum) must not recurse on destruction
+thread_local std::vector<TensorPtr> g_graveyard;
+thread_local bool g_draining = false;
+void bury(TensorPtr&& p) {
+  if (!p) return;
+  g_graveyard.push_back(std::move(p));
+  if (g_draining) return;
+  g_draining = true;
+  while (!g_graveyard.empty()) {
+    TensorPtr victim = std::move(g_graveyard.back());
+    g_graveyard.pop_back();
+    victim.reset();
+  }
+  g_draining = false;
+}
+}  // namespace
+
+int64_t live_tensors() { return g_live.load(); }
+
+Session::~Session() {
+  for (auto& kv : done) {
+    if (kv.second.buffer) cc_buffer_release(kv.second.buffer);
+    if (kv.second.event) cc_event_release(kv.second.event);
+  }
+}
+
+// ---- closure emission ----------------------------------------------------------------------------------------------------
+
+struct Tensor::EmitCtx {
+  cc::TreeWriter w;
+  std::unordered_map<const Tensor*, uint32_t> closures;
+  std::unordered_map<const Tensor*, uint32_t> param_nodes;
+  std::vector<const Tensor*> params;  // in creation order
+
+  uint32_t param(const Tensor* t) {
+    auto it = param_nodes.find(t);
+    if (it != param_nodes.end()) return it->second;
+    // ArrayParameter(id = the tensor itself, padding, shape) — Tensors.scala:1254-1260
+    uint32_t n = w.parameter((uint64_t)(uintptr_t)t, t->padding, t->shape, -1);
+    param_nodes[t] = n;
+    params.push_back(t);
+    return n;
+  }
+};
+
+Tensor::~Tensor() { g_live.fetch_sub(1); }
+
+int64_t Tensor::size() const { return product(shape); }
+
+uint32_t Tensor::closure(EmitCtx& ctx) const {
+  std::vector<std::pair<const Tensor*, bool>> stack{{this, false}};
+  std::vector<const Tensor*> ops;
+  while (!stack.empty()) {
+    auto [t, expanded] = stack.back();
+    stack.pop_back();
+    if (ctx.closures.count(t)) continue;
+    ops.clear();
+    t->closure_operands(ops);
+    if (!expanded && !ops.empty()) {
+      stack.push_back({t, true});
+      for (size_t k = ops.size(); k-- > 0;)
+        if (!ctx.closures.count(ops[k])) stack.push_back({ops[k], false});
+      continue;
+    }
+    std::vector<uint32_t> ids;
+    for (const Tensor* o : ops) ids.push_back(ctx.closures.at(o));
+    ctx.closures[t] = t->emit_closure(ctx, ids);
+  }
+  return ctx.closures.at(this);
+}
+
+namespace {
+
+// ---- concrete tensors ------------------------------------------------------------------------------------------------------
+
+struct Counted : Tensor {
+  Counted() { g_live.fetch_add(1); }
+};
+
+PendingBuffer enqueue_closure(Session& s, Tensor::EmitCtx& ctx, uint32_t root, const Shape& out_shape, bool attach_definitions);
+
+// InlineTensor (Tensors.scala:1400-1411)
+struct InlineTensor : Counted {
+  bool is_inline() const override { return true; }
+  PendingBuffer evaluate(Session& s) const override {
+    EmitCtx ctx;
+    uint32_t root = closure(ctx);
+    return enqueue_closure(s, ctx, root, shape, true);
+  }
+};
+
+// FillTensor (Tensors.scala:1394-1397)
+struct FillTensor final : InlineTensor {
+  float value;
+  uint32_t emit_closure(EmitCtx& ctx, const std::vector<uint32_t>&) const override { return ctx.w.literal(value); }
+};
+
+// derivedTensor (Tensors.scala:857-863) of a unary / binary float term
+struct DerivedTensor final : InlineTensor {
+  uint32_t kind;
+  TensorPtr a, b;
+  ~DerivedTensor() override {
+    bury(std::move(a));
+    bury(std::move(b));
+  }
+  void closure_operands(std::vector<const Tensor*>& out) const override {
+    out.push_back(a.get());
+    if (b) out.push_back(b.get());
+  }
+  uint32_t emit_closure(EmitCtx& ctx, const std::vector<uint32_t>& o) const override {
+    return b ? ctx.w.binary(kind, o[0], o[1]) : ctx.w.unary(kind, o[0]);
+  }
+};
+
+// TransformedTensor (Tensors.scala:1413-1428): closure = checkpoint.arrayTerm.transform(matrix).extract
+struct TransformedTensor final : InlineTensor {
+  TensorPtr checkpoint;
+  std::vector<double> matrix;  // checkpoint rank x (own rank + 1)
+  ~TransformedTensor() override { bury(std::move(checkpoint)); }
+  uint32_t emit_closure(EmitCtx& ctx, const std::vector<uint32_t>&) const override {
+    uint32_t p = ctx.param(checkpoint.get());
+    uint32_t rows = (uint32_t)checkpoint->shape.size(), cols = (uint32_t)shape.size() + 1;
+    return ctx.w.extract(ctx.w.transform(p, rows, cols, matrix.data()));
+  }
+};
+
+// NonInlineTensor (Tensors.scala:1431-1440): closure = arrayTerm.extract
+struct NonInlineTensor : Counted {
+  bool is_inline() const override { return false; }
+  uint32_t emit_closure(EmitCtx& ctx, const std::vector<uint32_t>&) const override { return ctx.w.extract(ctx.param(this)); }
+  TensorPtr non_inline() override { return shared_from_this(); }
+};
+
+// Tensor.apply / CachedTensor: owns a device buffer
+struct BufferTensor final : NonInlineTensor {
+  cc_buffer buffer = 0;
+  ~BufferTensor() override {
+    if (buffer) cc_buffer_release(buffer);
+  }
+  PendingBuffer evaluate(Session&) const override {
+    check(cc_buffer_retain(buffer));
+    return {buffer, 0};
+  }
+};
+
+// reshape (Tensors.scala:879-888) and InlineTensor.nonInline (:1405-1410): same doBuffer, new shape
+struct AliasTensor final : NonInlineTensor {
+  TensorPtr base;
+  ~AliasTensor() override { bury(std::move(base)); }
+  PendingBuffer evaluate(Session& s) const override { return base->do_buffer(s); }
+};
+
+struct RandomTensor final : NonInlineTensor {
+  int32_t seed;
+  bool normal;
+  PendingBuffer evaluate(Session&) const override {
+    cc_buffer out = 0;
+    uint64_t n = (uint64_t)size();
+    check(cc_buffer_alloc(n, &out));
+    int st = normal ? cc_random_normal(out, n, seed, nullptr) : cc_random(out, n, seed, nullptr);
+    if (st != CC_OK) {
+      std::string m = cc_last_error();
+      cc_buffer_release(out);
+      throw Error(st, m);
+    }
+    return {out, 0};
+  }
+};
+
+// Tensor.sum (Tensors.scala:673-771)
+struct SumTensor final : NonInlineTensor {
+  TensorPtr base;
+  ~SumTensor() override { bury(std::move(base)); }
+  PendingBuffer evaluate(Session& s) const override {
+    PendingBuffer in = base->do_buffer(s);
+    cc_buffer out = 0;
+    int st = cc_buffer_alloc(1, &out);
+    if (st == CC_OK) st = cc_reduce_sum(in.buffer, (uint64_t)base->size(), out, nullptr, 0, nullptr);
+    std::string m = st == CC_OK ? "" : cc_last_error();
+    cc_buffer_release(in.buffer);
+    if (st != CC_OK) {
+      if (out) cc_buffer_release(out);
+      throw Error(st, m);
+    }
+    return {out, 0};
+  }
+};
+
+// Tensor.join (Tensors.scala:577-598): one kernel over the head shape whose root is Concatenate(elements)
+struct JoinTensor final : NonInlineTensor {
+  std::vector<TensorPtr> tensors;
+  ~JoinTensor() override {
+    for (auto& t : tensors) bury(std::move(t));
+  }
+  uint32_t emit_root(EmitCtx& ctx) const {
+    std::vector<uint32_t> e;
+    for (auto& t : tensors) e.push_back(t->closure(ctx));
+    return ctx.w.concatenate(e);
+  }
+  PendingBuffer evaluate(Session& s) const override {
+    EmitCtx ctx;
+    uint32_t root = emit_root(ctx);
+    return enqueue_closure(s, ctx, root, shape, true);
+  }
+};
+
+cc_kernel compile_closure(Tensor::EmitCtx& ctx, uint32_t root, const Shape& out_shape, bool attach_definitions,
+                          std::vector<uint64_t>* ids) {
+  if (attach_definitions) {
+    // let the code generator look through the fusion barrier: an ArrayParameter produced by a not-yet-evaluated
+    // InlineTensor carries that tensor's closure (one level deep)
+    std::vector<const Tensor*> snapshot = ctx.params;
+    for (const Tensor* p : snapshot)
+      if (p->is_inline()) {
+        uint32_t def = p->closure(ctx);
+        ctx.w.set_definition(ctx.param_nodes.at(p), (int32_t)def);
+      }
+  }
+  std::string blob = ctx.w.finish(root, out_shape);
+  cc_kernel k = 0;
+  int n = 0;
+  std::vector<uint64_t> tmp(ctx.params.size() + 1);
+  check(cc_compile_ex(blob.data(), blob.size(), &k, tmp.data(), (int)tmp.size(), &n));
+  tmp.resize((size_t)n);
+  if (ids) *ids = std::move(tmp);
+  return k;
+}
+
+// enqueueClosure (Tensors.scala:1291-1392)
+PendingBuffer enqueue_closure(Session& s, Tensor::EmitCtx& ctx, uint32_t root, const Shape& out_shape, bool attach_definitions) {
+  std::vector<uint64_t> ids;
+  cc_kernel k = compile_closure(ctx, root, out_shape, attach_definitions, &ids);
+  std::vector<cc_buffer> args;
+  cc_buffer out = 0;
+  auto cleanup = [&] {
+    for (cc_buffer b : args) cc_buffer_release(b);
+    cc_kernel_release(k);
+  };
+  try {
+    cc_kernel_info_t info;
+    check(cc_kernel_info(k, &info));
+    for (int i = 0; i < info.n_args; ++i) {
+      int32_t ord = -1;
+      check(cc_kernel_arg_param(k, i, &ord));
+      CC_REQUIRE(ord >= 0 && (size_t)ord < ids.size(), CC_ERR_BAD_TREE, "kernel argument refers to unknown parameter %d", ord);
+      const Tensor* t = (const Tensor*)(uintptr_t)ids[(size_t)ord];
+      // upvalues.traverse(tree.id.asInstanceOf[Tensor].doBuffer) — Tensors.scala:1336-1340
+      args.push_back(t->do_buffer(s).buffer);
+    }
+    check(cc_buffer_alloc((uint64_t)product(out_shape), &out));
+    check(cc_launch(k, args.data(), (int)args.size(), out, nullptr, 0, nullptr));
+  } catch (...) {
+    if (out) cc_buffer_release(out);
+    cleanup();
+    throw;
+  }
+  cleanup();
+  return {out, 0};
+}
+
+template <class T>
+std::shared_ptr<T> make(const Shape& shape, float padding) {
+  check_shape(shape);
+  auto t = std::make_shared<T>();
+  t->shape = shape;
+  t->padding = padding;
+  return t;
+}
+
+}  // namespace
+
+PendingBuffer Tensor::do_buffer(Session& s) const {
+  auto it = s.done.find(this);
+  if (it == s.done.end()) {
+    PendingBuffer p = evaluate(s);
+    it = s.done.emplace(this, p).first;  // the session keeps evaluate()'s reference
+  }
+  check(cc_buffer_retain(it->second.buffer));
+  return {it->second.buffer, 0};
+}
+
+cc_kernel Tensor::compile_only() const {
+  EmitCtx ctx;
+  if (auto j = dynamic_cast<const JoinTensor*>(this)) {
+    uint32_t root = j->emit_root(ctx);
+    return compile_closure(ctx, root, shape, true, nullptr);
+  }
+  uint32_t root = closure(ctx);
+  return compile_closure(ctx, root, shape, true, nullptr);
+}
+
+// ---- factories ----------------------------------------------------------------------------------------------------------------
+
+TensorPtr from_buffer(cc_buffer buf, const Shape& shape, float padding) {
+  auto t = make<BufferTensor>(shape, padding);
+  uint64_t n = 0;
+  check(cc_buffer_length(buf, &n));
+  CC_REQUIRE((int64_t)n >= t->size(), CC_ERR_ILLEGAL_ARGUMENT, "buffer of %llu floats is smaller than shape %s", (unsigned long long)n,
+             shape_str(shape).c_str());
+  check(cc_buffer_retain(buf));
+  t->buffer = buf;
+  return t;
+}
+
+TensorPtr from_host(const float* data, const Shape& shape, float padding) {
+  auto t = make<BufferTensor>(shape, padding);
+  check(cc_buffer_from_host(data, (uint64_t)t->size(), &t->buffer, nullptr));
+  return t;
+}
+
+TensorPtr fill(float value, const Shape& shape, float padding) {
+  auto t = make<FillTensor>(shape, padding);
+  t->value = value;
+  return t;
+}
+TensorPtr scalar(float value, float padding) { return fill(value, {}, padding); }
+
+TensorPtr random(const Shape& shape, int32_t seed, float padding) {
+  auto t = make<RandomTensor>(shape, padding);
+  t->seed = seed;
+  t->normal = false;
+  return t;
+}
+TensorPtr random_normal(const Shape& shape, int32_t seed, float padding) {
+  auto t = make<RandomTensor>(shape, padding);
+  t->seed = seed;
+  t->normal = true;
+  return t;
+}
+
+Shape auto_broadcast_shape(const Shape& s1, const Shape& s2) {
+  Shape out;
+  const size_t n = std::max(s1.size(), s2.size());
+  for (size_t i = 0; i < n; ++i) {
+    if (i >= s1.size() || s1[i] == 1)
+      out.push_back(s2[i]);
+    else if (i >= s2.size() || s2[i] == 1)
+      out.push_back(s1[i]);
+    else if (s1[i] == s2[i])
+      out.push_back(s1[i]);
+    else
+      fail(CC_ERR_ILLEGAL_ARGUMENT, strprintf("Failed to automatically broadcast between shape %s and %s", shape_str(s1).c_str(),
+                                              shape_str(s2).c_str()));
+  }
+  return out;
+}
+
+TensorPtr unary(uint32_t kind, const TensorPtr& t) {
+  CC_REQUIRE(t, CC_ERR_ILLEGAL_ARGUMENT, "null tensor");
+  CC_REQUIRE(cc::is_unary(kind), CC_ERR_ILLEGAL_ARGUMENT, "not a unary operator: %u", kind);
+  auto d = make<DerivedTensor>(t->shape, t->padding);
+  d->kind = kind;
+  d->a = t;
+  return d;
+}
+
+TensorPtr binary(uint32_t kind, const TensorPtr& l, const TensorPtr& r) {
+  CC_REQUIRE(l && r, CC_ERR_ILLEGAL_ARGUMENT, "null tensor");
+  CC_REQUIRE(cc::is_binary(kind), CC_ERR_ILLEGAL_ARGUMENT, "not a binary operator: %u", kind);
+  Shape ns = auto_broadcast_shape(l->shape, r->shape);
+  TensorPtr bl = l->broadcast(ns), br = r->broadcast(ns);
+  auto d = make<DerivedTensor>(bl->shape, bl->padding);
+  d->kind = kind;
+  d->a = bl;
+  d->b = br;
+  return d;
+}
+
+TensorPtr join(const std::vector<TensorPtr>& tensors) {
+  CC_REQUIRE(!tensors.empty(), CC_ERR_ILLEGAL_ARGUMENT, "join of an empty sequence");
+  for (auto& t : tensors) {
+    CC_REQUIRE(t, CC_ERR_ILLEGAL_ARGUMENT, "null tensor");
+    CC_REQUIRE(t->shape == tensors[0]->shape, CC_ERR_ILLEGAL_ARGUMENT, "join of tensors with different shapes %s and %s",
+               shape_str(tensors[0]->shape).c_str(), shape_str(t->shape).c_str());
+  }
+  Shape s = tensors[0]->shape;
+  s.push_back((int32_t)tensors.size());
+  auto j = make<JoinTensor>(s, tensors[0]->padding);
+  j->tensors = tensors;
+  return j;
+}
+
+TensorPtr join(const std::vector<TensorPtr>& tensors, int dimension) {
+  TensorPtr j = join(tensors);
+  const int n = (int)j->shape.size();
+  CC_REQUIRE(dimension >= 0 && dimension < n, CC_ERR_ILLEGAL_ARGUMENT, "join dimension %d out of range", dimension);
+  if (n - 1 == dimension) return j;
+  std::vector<int32_t> perm(n);
+  for (int i = 0; i < n; ++i) perm[i] = i < dimension ? i : (i == dimension ? n - 1 : i - 1);
+  return j->permute(perm);
+}
+
+// ---- delayed operators ---------------------------------------------------------------------------------------------------------
+
+TensorPtr Tensor::transform(const Shape& new_shape, const std::vector<double>& matrix1) {
+  // Tensors.scala:978-1003: views of views are composed on the host and keep the ORIGINAL checkpoint
+  if (auto tt = dynamic_cast<TransformedTensor*>(this)) {
+    auto t = make<TransformedTensor>(new_shape, padding);
+    t->matrix = cc::ndat::pre_concatenate(matrix1, tt->matrix, new_shape.size());
+    t->checkpoint = tt->checkpoint;
+    return t;
+  }
+  auto t = make<TransformedTensor>(new_shape, padding);
+  CC_REQUIRE(matrix1.size() == shape.size() * (new_shape.size() + 1), CC_ERR_ILLEGAL_ARGUMENT, "transform matrix has %zu entries, expected %zu",
+             matrix1.size(), shape.size() * (new_shape.size() + 1));
+  t->matrix = matrix1;
+  t->checkpoint = shared_from_this();
+  return t;
+}
+
+TensorPtr Tensor::broadcast(const Shape& new_shape) {
+  if (new_shape == shape) return shared_from_this();
+  if (auto f = dynamic_cast<FillTensor*>(this)) return fill(f->value, new_shape, padding);
+  const size_t nl = new_shape.size(), l = shape.size();
+  CC_REQUIRE(nl >= l, CC_ERR_ILLEGAL_ARGUMENT, "Cannot broadcast %s to %s", shape_str(shape).c_str(), shape_str(new_shape).c_str());
+  std::vector<double> m((nl + 1) * l, 0.0);
+  for (size_t i = 0; i < l; ++i) {
+    if (shape[i] == new_shape[i])
+      m[i * (nl + 1) + i] = 1.0;
+    else if (shape[i] != 1)
+      fail(CC_ERR_ILLEGAL_ARGUMENT, strprintf("Cannot broadcast %s to %s", shape_str(shape).c_str(), shape_str(new_shape).c_str()));
+  }
+  return transform(new_shape, m);
+}
+
+TensorPtr Tensor::reshape(const Shape& new_shape) {
+  check_shape(new_shape);
+  CC_REQUIRE(product(new_shape) == size(), CC_ERR_ILLEGAL_ARGUMENT, "cannot reshape %s to %s", shape_str(shape).c_str(),
+             shape_str(new_shape).c_str());
+  auto a = make<AliasTensor>(new_shape, padding);
+  a->base = shared_from_this();
+  return a;
+}
+
+TensorPtr Tensor::non_inline() {
+  auto a = make<AliasTensor>(shape, padding);
+  a->base = shared_from_this();
+  return a;
+}
+
+TensorPtr Tensor::scale(const Shape& new_shape) {
+  const size_t n = new_shape.size();
+  CC_REQUIRE(n == shape.size(), CC_ERR_ILLEGAL_ARGUMENT, "scale to a different rank");
+  std::vector<double> m(n * (n + 1), 0.0);
+  for (size_t i = 0; i < n; ++i) m[i * (n + 1) + i] = (double)shape[i] / (double)new_shape[i];
+  return transform(new_shape, m);
+}
+
+TensorPtr Tensor::translate(const std::vector<double>& offset) { return translate(offset, shape); }
+
+TensorPtr Tensor::translate(const std::vector<double>& offset, const Shape& new_shape) {
+  CC_REQUIRE(offset.size() == shape.size(), CC_ERR_ILLEGAL_ARGUMENT, "translate offset has %zu entries for a rank-%zu tensor", offset.size(),
+             shape.size());
+  std::vector<double> neg(offset.size());
+  for (size_t i = 0; i < offset.size(); ++i) neg[i] = -offset[i];
+  return transform(new_shape, cc::ndat::translate(neg));
+}
+
+TensorPtr Tensor::permute(const std::vector<int32_t>& dimensions) {
+  const size_t n = shape.size();
+  CC_REQUIRE(dimensions.size() == n, CC_ERR_ILLEGAL_ARGUMENT, "permute with %zu dimensions on a rank-%zu tensor", dimensions.size(), n);
+  Shape ns(n);
+  std::vector<double> m(n * (n + 1), 0.0);
+  for (size_t nd = 0; nd < n; ++nd) {
+    int32_t od = dimensions[nd];
+    CC_REQUIRE(od >= 0 && (size_t)od < n, CC_ERR_ILLEGAL_ARGUMENT, "permute dimension %d out of range", od);
+    ns[nd] = shape[(size_t)od];
+    m[(size_t)od * (n + 1) + nd] = 1.0;
+  }
+  return transform(ns, m);
+}
+
+TensorPtr Tensor::transpose() {
+  std::vector<int32_t> d(shape.size());
+  for (size_t i = 0; i < d.size(); ++i) d[i] = (int32_t)(d.size() - 1 - i);
+  return permute(d);
+}
+
+std::vector<TensorPtr> Tensor::split(int dimension) {
+  const int n = (int)shape.size();
+  CC_REQUIRE(dimension >= 0 && dimension < n, CC_ERR_ILLEGAL_ARGUMENT, "split dimension %d out of range for rank %d", dimension, n);
+  Shape ns;
+  for (int i = 0; i < n; ++i)
+    if (i != dimension) ns.push_back(shape[(size_t)i]);
+  std::vector<TensorPtr> out;
+  out.reserve((size_t)shape[(size_t)dimension]);
+  for (int32_t index = 0; index < shape[(size_t)dimension]; ++index) {
+    std::vector<double> m((size_t)n * (size_t)n, 0.0);
+    for (int i = 0; i < dimension; ++i) m[(size_t)i * n + i] = 1.0;
+    m[(size_t)dimension * n + n - 1] = (double)index;
+    for (int i = dimension + 1; i < n; ++i) m[(size_t)i * n + i - 1] = 1.0;
+    out.push_back(transform(ns, m));
+  }
+  return out;
+}
+
+TensorPtr Tensor::sum() {
+  auto s = make<SumTensor>({}, padding);
+  s->base = shared_from_this();
+  return s;
+}
+
+TensorPtr Tensor::do_cache() {
+  Session s;
+  PendingBuffer p = do_buffer(s);
+  auto t = make<BufferTensor>(shape, padding);
+  t->buffer = p.buffer;
+  return t;
+}
+
+// ---- slow actions ---------------------------------------------------------------------------------------------------------------
+
+void Tensor::flat_array_into(float* host, uint64_t capacity) const {
+  const uint64_t n = (uint64_t)size();
+  CC_REQUIRE(capacity >= n, CC_ERR_ILLEGAL_ARGUMENT, "flatArray needs room for %llu floats, got %llu", (unsigned long long)n,
+             (unsigned long long)capacity);
+  Session s;
+  PendingBuffer p = do_buffer(s);
+  int st = cc_buffer_to_host(p.buffer, 0, host, n, nullptr, 0, nullptr);
+  std::string m = st == CC_OK ? "" : cc_last_error();
+  cc_buffer_release(p.buffer);
+  if (st != CC_OK) throw Error(st, m);
+}
+
+std::vector<float> Tensor::flat_array() const {
+  std::vector<float> v((size_t)size());
+  flat_array_into(v.data(), v.size());
+  return v;
+}
+
+std::string java_float_to_string(float x) {
+  if (std::isnan(x)) return "NaN";
+  if (std::isinf(x)) return x > 0 ? "Infinity" : "-Infinity";
+  if (x == 0.f) return std::signbit(x) ? "-0.0" : "0.0";
+  char buf[64];
+  auto r = std::to_chars(buf, buf + sizeof buf, x, std::chars_format::scientific);
+  std::string s(buf, r.ptr);  // [-]d[.ddd]e[+-]XX, shortest round-trip digits
+  bool neg = s[0] == '-';
+  if (neg) s.erase(0, 1);
+  size_t epos = s.find('e');
+  std::string mant = s.substr(0, epos);
+  int exp = atoi(s.c_str() + epos + 1);
+  std::string digits;
+  for (char c : mant)
+    if (c != '.') digits.push_back(c);
+  std::string out;
+  const double a = std::fabs((double)x);
+  if (a >= 1e-3 && a < 1e7) {
+    if (exp >= 0) {
+      std::string ip = digits.substr(0, std::min<size_t>(digits.size(), (size_t)exp + 1));
+      while ((int)ip.size() < exp + 1) ip.push_back('0');
+      std::string fp = digits.size() > (size_t)exp + 1 ? digits.substr((size_t)exp + 1) : "0";
+      out = ip + "." + fp;
+    } else {
+      out = "0." + std::string((size_t)(-exp - 1), '0') + digits;
+    }
+  } else {
+    out = digits.substr(0, 1) + "." + (digits.size() > 1 ? digits.substr(1) : "0") + "E" + std::to_string(exp);
+  }
+  return neg ? "-" + out : out;
+}
+
+std::string Tensor::to_string() const {
+  std::vector<float> flat = flat_array();
+  std::string out;
+  // Tensors.scala:776-811
+  struct Rec {
+    const Shape& shape;
+    const std::vector<float>& a;
+    std::string& out;
+    void go(size_t dim, size_t begin, size_t count) {
+      if (dim == shape.size()) {
+        CC_REQUIRE(count == 1, CC_ERR_ILLEGAL_ARGUMENT, "shape does not match the data size");
+        out += java_float_to_string(a[begin]);
+        return;
+      }
+      out += "[";
+      const size_t head = (size_t)shape[dim];
+      const size_t g = head ? count / head : 0;
+      for (size_t i = 0; i < head; ++i) {
+        if (i) out += ",";
+        go(dim + 1, begin + i * g, g);
+      }
+      out += "]";
+    }
+  } rec{shape, flat, out};
+  rec.go(0, 0, flat.size());
+  return out;
+}
+
+}  // namespace cuda
+}  // namespace compute
+
+// ---- flat C view ---------------------------------------------------------------------------------------------------------------------
+
+using namespace compute::cuda;
+using cc::guarded;
+
+namespace {
+TensorPtr& ref(ct_tensor h) {
+  CC_REQUIRE(h, CC_ERR_ILLEGAL_ARGUMENT, "null tensor handle");
+  return *(TensorPtr*)(uintptr_t)h;
+}
+ct_tensor wrap(TensorPtr t) { return (ct_tensor)(uintptr_t) new TensorPtr(std::move(t)); }
+Shape to_shape(const int32_t* s, int rank) {
+  CC_REQUIRE(rank >= 0 && (rank == 0 || s), CC_ERR_ILLEGAL_ARGUMENT, "bad shape arguments");
+  return Shape(s, s + rank);
+}
+}  // namespace
+
+extern "C" {
+
+int ct_from_host(const float* data, const int32_t* shape, int rank, float padding, ct_tensor* out) {
+  return guarded([&] { *out = wrap(from_host(data, to_shape(shape, rank), padding)); });
+}
+int ct_from_buffer(cc_buffer buf, const int32_t* shape, int rank, float padding, ct_tensor* out) {
+  return guarded([&] { *out = wrap(from_buffer(buf, to_shape(shape, rank), padding)); });
+}
+int ct_scalar(float value, float padding, ct_tensor* out) {
+  return guarded([&] { *out = wrap(scalar(value, padding)); });
+}
+int ct_fill(float value, const int32_t* shape, int rank, float padding, ct_tensor* out) {
+  return guarded([&] { *out = wrap(fill(value, to_shape(shape, rank), padding)); });
+}
+int ct_random(const int32_t* shape, int rank, int32_t seed, float padding, ct_tensor* out) {
+  return guarded([&] { *out = wrap(compute::cuda::random(to_shape(shape, rank), seed, padding)); });
+}
+int ct_random_normal(const int32_t* shape, int rank, int32_t seed, float padding, ct_tensor* out) {
+  return guarded([&] { *out = wrap(random_normal(to_shape(shape, rank), seed, padding)); });
+}
+int ct_unary(int op, ct_tensor t, ct_tensor* out) {
+  return guarded([&] { *out = wrap(unary((uint32_t)op, ref(t))); });
+}
+int ct_binary(int op, ct_tensor l, ct_tensor r, ct_tensor* out) {
+  return guarded([&] { *out = wrap(binary((uint32_t)op, ref(l), ref(r))); });
+}
+int ct_broadcast(ct_tensor t, const int32_t* shape, int rank, ct_tensor* out) {
+  return guarded([&] { *out = wrap(ref(t)->broadcast(to_shape(shape, rank))); });
+}
+int ct_reshape(ct_tensor t, const int32_t* shape, int rank, ct_tensor* out) {
+  return guarded([&] { *out = wrap(ref(t)->reshape(to_shape(shape, rank))); });
+}
+int ct_scale(ct_tensor t, const int32_t* shape, int rank, ct_tensor* out) {
+  return guarded([&] { *out = wrap(ref(t)->scale(to_shape(shape, rank))); });
+}
+int ct_translate(ct_tensor t, const double* offset, int n_offset, const int32_t* new_shape, int new_rank, ct_tensor* out) {
+  return guarded([&] {
+    CC_REQUIRE(n_offset >= 0 && (offset || n_offset == 0), CC_ERR_ILLEGAL_ARGUMENT, "bad offset");
+    std::vector<double> off(offset, offset + n_offset);
+    if (new_rank < 0)
+      *out = wrap(ref(t)->translate(off));
+    else
+      *out = wrap(ref(t)->translate(off, to_shape(new_shape, new_rank)));
+  });
+}
+int ct_permute(ct_tensor t, const int32_t* dims, int n, ct_tensor* out) {
+  return guarded([&] { *out = wrap(ref(t)->permute(std::vector<int32_t>(dims, dims + n))); });
+}
+int ct_transpose(ct_tensor t, ct_tensor* out) {
+  return guarded([&] { *out = wrap(ref(t)->transpose()); });
+}
+int ct_split(ct_tensor t, int dimension, ct_tensor* out, int capacity, int* out_count) {
+  return guarded([&] {
+    auto parts = ref(t)->split(dimension);
+    if (out_count) *out_count = (int)parts.size();
+    if (!out) return;
+    CC_REQUIRE(capacity >= (int)parts.size(), CC_ERR_ILLEGAL_ARGUMENT, "split produces %zu tensors, capacity %d", parts.size(), capacity);
+    for (size_t i = 0; i < parts.size(); ++i) out[i] = wrap(std::move(parts[i]));
+  });
+}
+int ct_join(const ct_tensor* tensors, int n, ct_tensor* out) {
+  return guarded([&] {
+    std::vector<TensorPtr> v;
+    for (int i = 0; i < n; ++i) v.push_back(ref(tensors[i]));
+    *out = wrap(join(v));
+  });
+}
+int ct_join_dim(const ct_tensor* tensors, int n, int dimension, ct_tensor* out) {
+  return guarded([&] {
+    std::vector<TensorPtr> v;
+    for (int i = 0; i < n; ++i) v.push_back(ref(tensors[i]));
+    *out = wrap(join(v, dimension));
+  });
+}
+int ct_sum(ct_tensor t, ct_tensor* out) {
+  return guarded([&] { *out = wrap(ref(t)->sum()); });
+}
+int ct_non_inline(ct_tensor t, ct_tensor* out) {
+  return guarded([&] { *out = wrap(ref(t)->non_inline()); });
+}
+int ct_do_cache(ct_tensor t, ct_tensor* out) {
+  return guarded([&] { *out = wrap(ref(t)->do_cache()); });
+}
+int ct_rank(ct_tensor t, int* out) {
+  return guarded([&] { *out = (int)ref(t)->shape.size(); });
+}
+int ct_shape(ct_tensor t, int32_t* out, int capacity) {
+  return guarded([&] {
+    const Shape& s = ref(t)->shape;
+    CC_REQUIRE(capacity >= (int)s.size(), CC_ERR_ILLEGAL_ARGUMENT, "shape capacity too small");
+    for (size_t i = 0; i < s.size(); ++i) out[i] = s[i];
+  });
+}
+int ct_padding(ct_tensor t, float* out) {
+  return guarded([&] { *out = ref(t)->padding; });
+}
+int ct_flat_array(ct_tensor t, float* host_out, uint64_t capacity) {
+  return guarded([&] { ref(t)->flat_array_into(host_out, capacity); });
+}
+int ct_to_string(ct_tensor t, char* out, uint64_t capacity, uint64_t* out_needed) {
+  return guarded([&] {
+    std::string s = ref(t)->to_string();
+    if (out_needed) *out_needed = s.size() + 1;
+    if (out && capacity) {
+      size_t n = std::min<size_t>(s.size(), (size_t)capacity - 1);
+      memcpy(out, s.data(), n);
+      out[n] = 0;
+    }
+  });
+}
+int ct_do_buffer(ct_tensor t, cc_buffer* out, cc_event* out_event) {
+  return guarded([&] {
+    Session s;
+    PendingBuffer p = ref(t)->do_buffer(s);
+    *out = p.buffer;
+    if (out_event) *out_event = 0;
+  });
+}
+int ct_compile(ct_tensor t, cc_kernel* out) {
+  return guarded([&] { *out = ref(t)->compile_only(); });
+}
+int ct_release(ct_tensor t) {
+  return guarded([&] {
+    TensorPtr* p = &ref(t);
+    delete p;
+  });
+}
+int ct_live_tensors(int64_t* out) {
+  return guarded([&] { *out = live_tensors(); });
+}
+
+}  // extern "C"

@@ -1,0 +1,95 @@
+// tensor.h — host-side mirror of the reference's lazy Tensor API (`object cuda`, the sibling of cpu.scala:103-117 /
+// gpu.scala:15-27), written in C++ because the reference's own toolchain (Scala/JVM) is not available here.
+// Same names, argument meaning and error behaviour as Tensors.scala:395-1442; everything device-side goes through the
+// cc_* C ABI (include/compute_cuda.h), exactly as the Scala `cuda` object would.
+#pragma once
+#include <memory>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "common.h"
+#include "ir.h"
+
+namespace compute {
+namespace cuda {
+
+using Shape = std::vector<int32_t>;
+class Tensor;
+using TensorPtr = std::shared_ptr<Tensor>;
+
+// PendingBuffer (Tensors.scala:253-299): a device buffer plus the event that completes it.
+struct PendingBuffer {
+  cc_buffer buffer = 0;
+  cc_event event = 0;  // 0 = ReadyBuffer
+};
+
+// One slow action = one session: every tensor is evaluated at most once per session (`.shared`, Tensors.scala:1401-1403)
+// and its buffer is released when the session ends (deterministic release, README.md:10).
+class Session {
+ public:
+  ~Session();
+  std::unordered_map<const Tensor*, PendingBuffer> done;
+};
+
+class Tensor : public std::enable_shared_from_this<Tensor> {
+ public:
+  Shape shape;
+  float padding = 0.f;
+  virtual ~Tensor();
+
+  int64_t size() const;
+
+  // ---- closures (Tensors.scala:1254-1260, 1394-1440) ----
+  virtual bool is_inline() const = 0;
+  // emits this tensor's closure (a float term) into `w`; `ctx` memoises per tensor so shared sub-graphs stay shared
+  struct EmitCtx;
+  uint32_t closure(EmitCtx& ctx) const;
+  virtual void closure_operands(std::vector<const Tensor*>& out) const { (void)out; }
+  virtual uint32_t emit_closure(EmitCtx& ctx, const std::vector<uint32_t>& operands) const = 0;
+
+  // ---- evaluation ----
+  // doBuffer (Tensors.scala:1401-1403 etc.): the returned buffer is retained for the caller
+  PendingBuffer do_buffer(Session& s) const;
+  virtual PendingBuffer evaluate(Session& s) const = 0;
+  // compile only (no device work): the kernel this tensor's closure maps to
+  cc_kernel compile_only() const;
+
+  // ---- delayed operators (Tensors.scala:816-1074) ----
+  TensorPtr broadcast(const Shape& new_shape);
+  TensorPtr reshape(const Shape& new_shape);
+  TensorPtr scale(const Shape& new_shape);
+  TensorPtr translate(const std::vector<double>& offset);
+  TensorPtr translate(const std::vector<double>& offset, const Shape& new_shape);
+  TensorPtr permute(const std::vector<int32_t>& dimensions);
+  TensorPtr transpose();
+  std::vector<TensorPtr> split(int dimension);
+  TensorPtr sum();
+  virtual TensorPtr non_inline();
+  TensorPtr do_cache();
+  TensorPtr transform(const Shape& new_shape, const std::vector<double>& matrix1);
+
+  // ---- slow actions (Tensors.scala:776-811, 1099-1118) ----
+  std::vector<float> flat_array() const;
+  void flat_array_into(float* host, uint64_t capacity) const;
+  std::string to_string() const;
+};
+
+// object Tensor (Tensors.scala:395-600)
+TensorPtr from_host(const float* data, const Shape& shape, float padding = 0.f);       // apply
+TensorPtr from_buffer(cc_buffer buf, const Shape& shape, float padding = 0.f);
+TensorPtr scalar(float value, float padding = 0.f);
+TensorPtr fill(float value, const Shape& shape, float padding = 0.f);
+TensorPtr random(const Shape& shape, int32_t seed, float padding = 0.f);
+TensorPtr random_normal(const Shape& shape, int32_t seed, float padding = 0.f);
+TensorPtr unary(uint32_t kind, const TensorPtr& t);                                    // abs sqrt tanh exp log unary_-
+TensorPtr binary(uint32_t kind, const TensorPtr& l, const TensorPtr& r);               // + - * / % min max
+TensorPtr join(const std::vector<TensorPtr>& tensors);
+TensorPtr join(const std::vector<TensorPtr>& tensors, int dimension);
+Shape auto_broadcast_shape(const Shape& a, const Shape& b);                            // Tensors.scala:208-222
+std::string java_float_to_string(float v);
+
+int64_t live_tensors();
+
+}  // namespace cuda
+}  // namespace compute

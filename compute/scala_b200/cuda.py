@@ -1,0 +1,548 @@
+"""`com.thoughtworks.compute.cuda` — the new backend object beside `cpu` / `gpu` (cpu.scala:103-117, gpu.scala:15-27),
+as seen from Python.  This module is a ctypes VIEW of the host-side mirror compiled into libcompute_cuda.so
+(csrc/tensor.cpp): names, argument meaning and error behaviour follow Tensors.scala:395-1442; nothing is computed
+here and nothing falls back to numpy.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Iterable, Sequence
+
+import numpy as np
+
+from . import _lib
+from ._lib import ComputeCudaError, IllegalArgumentException, check, i32, u64  # noqa: F401
+
+_UNARY = {"exp": 10, "log": 11, "abs": 12, "tanh": 13, "sqrt": 14, "neg": 15}
+_BINARY = {"min": 20, "max": 21, "+": 22, "-": 23, "*": 24, "/": 25, "%": 26}
+
+_configured = False
+
+
+def _L():
+    global _configured
+    L = _lib.lib()
+    if not _configured:
+        f32, h, ip, fp = C.c_float, u64, C.POINTER(i32), C.POINTER(C.c_float)
+        hp = C.POINTER(u64)
+        L.ct_from_host.argtypes = [C.c_void_p, ip, C.c_int, f32, hp]
+        L.ct_from_buffer.argtypes = [h, ip, C.c_int, f32, hp]
+        L.ct_scalar.argtypes = [f32, f32, hp]
+        L.ct_fill.argtypes = [f32, ip, C.c_int, f32, hp]
+        L.ct_random.argtypes = [ip, C.c_int, i32, f32, hp]
+        L.ct_random_normal.argtypes = [ip, C.c_int, i32, f32, hp]
+        L.ct_unary.argtypes = [C.c_int, h, hp]
+        L.ct_binary.argtypes = [C.c_int, h, h, hp]
+        for n in ("ct_broadcast", "ct_reshape", "ct_scale"):
+            getattr(L, n).argtypes = [h, ip, C.c_int, hp]
+        L.ct_translate.argtypes = [h, C.POINTER(C.c_double), C.c_int, ip, C.c_int, hp]
+        L.ct_permute.argtypes = [h, ip, C.c_int, hp]
+        L.ct_transpose.argtypes = [h, hp]
+        L.ct_split.argtypes = [h, C.c_int, hp, C.c_int, C.POINTER(C.c_int)]
+        L.ct_join.argtypes = [hp, C.c_int, hp]
+        L.ct_join_dim.argtypes = [hp, C.c_int, C.c_int, hp]
+        for n in ("ct_sum", "ct_non_inline", "ct_do_cache"):
+            getattr(L, n).argtypes = [h, hp]
+        L.ct_rank.argtypes = [h, C.POINTER(C.c_int)]
+        L.ct_shape.argtypes = [h, ip, C.c_int]
+        L.ct_padding.argtypes = [h, fp]
+        L.ct_flat_array.argtypes = [h, C.c_void_p, u64]
+        L.ct_to_string.argtypes = [h, C.c_char_p, u64, hp]
+        L.ct_do_buffer.argtypes = [h, hp, hp]
+        L.ct_compile.argtypes = [h, hp]
+        L.ct_release.argtypes = [h]
+        L.ct_live_tensors.argtypes = [C.POINTER(C.c_int64)]
+        L.cc_init.argtypes = [C.c_int]
+        L.cc_set_stream_count.argtypes = [C.c_int]
+        L.cc_device_info.argtypes = [C.POINTER(_lib.DeviceInfo)]
+        L.cc_buffer_alloc.argtypes = [u64, hp]
+        L.cc_buffer_from_host.argtypes = [C.c_void_p, u64, hp, hp]
+        L.cc_buffer_upload.argtypes = [h, C.c_void_p, u64, hp, C.c_int, hp]
+        L.cc_buffer_wrap.argtypes = [u64, u64, hp]
+        L.cc_buffer_retain.argtypes = [h]
+        L.cc_buffer_release.argtypes = [h]
+        L.cc_buffer_device_ptr.argtypes = [h, hp]
+        L.cc_buffer_length.argtypes = [h, hp]
+        L.cc_buffer_to_host.argtypes = [h, u64, C.c_void_p, u64, hp, C.c_int, hp]
+        L.cc_host_alloc.argtypes = [u64, C.POINTER(C.c_void_p)]
+        L.cc_host_free.argtypes = [C.c_void_p]
+        for n in ("cc_event_retain", "cc_event_release", "cc_event_wait"):
+            getattr(L, n).argtypes = [h]
+        L.cc_event_query.argtypes = [h, C.POINTER(C.c_int)]
+        L.cc_event_on_complete.argtypes = [h, C.c_void_p, C.c_void_p]
+        L.cc_compile.argtypes = [C.c_void_p, u64, hp]
+        L.cc_compile_ex.argtypes = [C.c_void_p, u64, hp, hp, C.c_int, C.POINTER(C.c_int)]
+        L.cc_kernel_retain.argtypes = [h]
+        L.cc_kernel_release.argtypes = [h]
+        L.cc_kernel_info.argtypes = [h, C.POINTER(_lib.KernelInfo)]
+        L.cc_kernel_arg_param.argtypes = [h, C.c_int, ip]
+        L.cc_kernel_source.argtypes = [h, C.POINTER(C.c_char_p)]
+        L.cc_launch.argtypes = [h, hp, C.c_int, h, hp, C.c_int, hp]
+        L.cc_reduce_sum.argtypes = [h, u64, h, hp, C.c_int, hp]
+        L.cc_random.argtypes = [h, u64, i32, hp]
+        L.cc_random_normal.argtypes = [h, u64, i32, hp]
+        L.cc_matmul_3xtf32.argtypes = [h, h, h, C.c_int64, C.c_int64, C.c_int64, hp, C.c_int, hp]
+        L.cc_stats.argtypes = [C.POINTER(_lib.Stats)]
+        L.cc_timer_stop.argtypes = [fp]
+        L.cc_comm_unique_id.argtypes = [C.c_void_p]
+        L.cc_comm_init.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.cc_comm_info.argtypes = [C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        L.cc_allreduce_sum.argtypes = [h, u64, hp, C.c_int, hp]
+        L.cc_allgather.argtypes = [h, h, u64, hp, C.c_int, hp]
+        L.cc_broadcast.argtypes = [h, u64, C.c_int, hp, C.c_int, hp]
+        _configured = True
+    return L
+
+
+def _shape_arg(shape: Sequence[int]):
+    shape = [int(s) for s in shape]
+    return (i32 * max(1, len(shape)))(*shape), len(shape)
+
+
+# ---- runtime (trait OpenCL's role) ----------------------------------------------------------------------------------------
+
+
+def init(device: int = -1, streams: int | None = None) -> None:
+    """Factory[... cuda ...].newInstance(): creates the context / stream pool. Raises without a B200 + driver."""
+    L = _L()
+    if streams is not None and not L.cc_is_initialized():
+        check(L.cc_set_stream_count(int(streams)))
+    check(L.cc_init(int(device)))
+
+
+def shutdown() -> None:
+    check(_L().cc_shutdown())
+
+
+def is_initialized() -> bool:
+    return bool(_L().cc_is_initialized())
+
+
+def device_info() -> _lib.DeviceInfo:
+    info = _lib.DeviceInfo()
+    check(_L().cc_device_info(C.byref(info)))
+    return info
+
+
+def stats() -> dict:
+    s = _lib.Stats()
+    check(_L().cc_stats(C.byref(s)))
+    return {n: int(getattr(s, n)) for n, _ in s._fields_}
+
+
+def stats_reset() -> None:
+    check(_L().cc_stats_reset())
+
+
+def synchronize() -> None:
+    check(_L().cc_synchronize())
+
+
+def timer_start() -> None:
+    check(_L().cc_timer_start())
+
+
+def timer_stop() -> float:
+    ms = C.c_float()
+    check(_L().cc_timer_stop(C.byref(ms)))
+    return float(ms.value)
+
+
+class PinnedArray:
+    """pinned host staging memory (cc_host_alloc) exposed as a numpy float32 array"""
+
+    def __init__(self, n_floats: int):
+        self._p = C.c_void_p()
+        self.n = int(n_floats)
+        check(_L().cc_host_alloc(self.n * 4, C.byref(self._p)))
+        self.array = np.ctypeslib.as_array(C.cast(self._p, C.POINTER(C.c_float)), shape=(max(self.n, 1),))[: self.n]
+
+    @property
+    def ptr(self) -> int:
+        return self._p.value
+
+    def free(self) -> None:
+        if self._p:
+            self.array = None
+            check(_L().cc_host_free(self._p))
+            self._p = C.c_void_p()
+
+
+class Kernel:
+    """CompiledKernel (Tensors.scala:1263-1265) handle, for cache / pattern tests"""
+
+    def __init__(self, handle: int):
+        self.handle = handle
+
+    @property
+    def info(self) -> _lib.KernelInfo:
+        k = _lib.KernelInfo()
+        check(_L().cc_kernel_info(self.handle, C.byref(k)))
+        return k
+
+    @property
+    def source(self) -> str:
+        s = C.c_char_p()
+        check(_L().cc_kernel_source(self.handle, C.byref(s)))
+        return s.value.decode()
+
+    def release(self) -> None:
+        if self.handle:
+            check(_L().cc_kernel_release(self.handle))
+            self.handle = 0
+
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:
+            pass
+
+
+class Buffer:
+    """DeviceBuffer[Float] handle (OpenCL.scala:636-715)"""
+
+    def __init__(self, handle: int):
+        self.handle = handle
+
+    @staticmethod
+    def alloc(n_floats: int) -> "Buffer":
+        h = u64()
+        check(_L().cc_buffer_alloc(int(n_floats), C.byref(h)))
+        return Buffer(h.value)
+
+    @staticmethod
+    def wrap(device_ptr: int, n_floats: int) -> "Buffer":
+        h = u64()
+        check(_L().cc_buffer_wrap(int(device_ptr), int(n_floats), C.byref(h)))
+        return Buffer(h.value)
+
+    @staticmethod
+    def from_host(a: np.ndarray) -> "Buffer":
+        a = np.ascontiguousarray(a, dtype=np.float32)
+        h = u64()
+        check(_L().cc_buffer_from_host(a.ctypes.data, a.size, C.byref(h), None))
+        return Buffer(h.value)
+
+    @property
+    def ptr(self) -> int:
+        p = u64()
+        check(_L().cc_buffer_device_ptr(self.handle, C.byref(p)))
+        return p.value
+
+    @property
+    def length(self) -> int:
+        p = u64()
+        check(_L().cc_buffer_length(self.handle, C.byref(p)))
+        return p.value
+
+    def upload(self, host_ptr: int, n_floats: int) -> None:
+        """async H2D (host memory must stay alive until the next synchronising call)"""
+        ev = u64()
+        check(_L().cc_buffer_upload(self.handle, host_ptr, int(n_floats), None, 0, C.byref(ev)))
+        check(_L().cc_event_release(ev.value))
+
+    def to_host(self, n_floats: int | None = None, offset: int = 0) -> np.ndarray:
+        n = self.length - offset if n_floats is None else int(n_floats)
+        out = np.empty(n, dtype=np.float32)
+        check(_L().cc_buffer_to_host(self.handle, int(offset), out.ctypes.data, n, None, 0, None))
+        return out
+
+    def to_host_async(self, host_ptr: int, n_floats: int, offset: int = 0) -> None:
+        ev = u64()
+        check(_L().cc_buffer_to_host(self.handle, int(offset), host_ptr, int(n_floats), None, 0, C.byref(ev)))
+        check(_L().cc_event_release(ev.value))
+
+    def release(self) -> None:
+        if self.handle:
+            check(_L().cc_buffer_release(self.handle))
+            self.handle = 0
+
+    def __del__(self):
+        try:
+            if _lib._lib is not None:
+                self.release()
+        except Exception:
+            pass
+
+
+def reduce_sum(src: Buffer, n_floats: int, dst: Buffer) -> None:
+    check(_L().cc_reduce_sum(src.handle, int(n_floats), dst.handle, None, 0, None))
+
+
+def matmul_3xtf32(a: Buffer, b: Buffer, c: Buffer, m: int, n: int, k: int) -> None:
+    check(_L().cc_matmul_3xtf32(a.handle, b.handle, c.handle, m, n, k, None, 0, None))
+
+
+def comm_unique_id() -> bytes:
+    buf = C.create_string_buffer(128)
+    check(_L().cc_comm_unique_id(buf))
+    return buf.raw
+
+
+def comm_init(unique_id: bytes, n_ranks: int, rank: int) -> None:
+    check(_L().cc_comm_init(C.create_string_buffer(unique_id, 128), int(n_ranks), int(rank)))
+
+
+def comm_destroy() -> None:
+    check(_L().cc_comm_destroy())
+
+
+def allreduce_sum(buf: Buffer, n_floats: int) -> None:
+    check(_L().cc_allreduce_sum(buf.handle, int(n_floats), None, 0, None))
+
+
+def allgather(send: Buffer, recv: Buffer, n_floats_per_rank: int) -> None:
+    check(_L().cc_allgather(send.handle, recv.handle, int(n_floats_per_rank), None, 0, None))
+
+
+def broadcast(buf: Buffer, n_floats: int, root: int = 0) -> None:
+    check(_L().cc_broadcast(buf.handle, int(n_floats), int(root), None, 0, None))
+
+
+# ---- Tensor (Tensors.scala:395-1261) ---------------------------------------------------------------------------------------
+
+
+def _flatten(elements):
+    """TensorBuilder (Tensors.scala:44-94): nested sequences -> (shape, row-major flat floats); ragged input is an
+    IllegalArgumentException (TensorsSpec.scala:67-73)."""
+    if isinstance(elements, np.ndarray):
+        return tuple(elements.shape), np.ascontiguousarray(elements, dtype=np.float32).reshape(-1)
+    if isinstance(elements, (int, float, np.floating, np.integer)):
+        return (), np.asarray([elements], dtype=np.float32)
+    subs = [_flatten(e) for e in elements]
+    if not subs:
+        return (0,), np.zeros(0, dtype=np.float32)
+    for s, _ in subs:
+        if s != subs[0][0]:
+            raise IllegalArgumentException(-1, "tensor literal is not rectangular")
+    return (len(subs),) + subs[0][0], np.concatenate([f for _, f in subs]).astype(np.float32)
+
+
+class Tensor:
+    """`cuda.Tensor` — lazily evaluated N-dimensional float32 array."""
+
+    __slots__ = ("_h", "__weakref__")
+
+    def __init__(self, elements=None, padding: float = 0.0, *, _handle: int | None = None):
+        if _handle is not None:
+            self._h = _handle
+            return
+        shape, flat = _flatten(elements)
+        sa, rank = _shape_arg(shape)
+        h = u64()
+        check(_L().ct_from_host(flat.ctypes.data, sa, rank, float(padding), C.byref(h)))
+        self._h = h.value
+
+    # -- construction (object Tensor) --
+    @staticmethod
+    def _wrap(h: u64) -> "Tensor":
+        return Tensor(_handle=h.value)
+
+    @staticmethod
+    def scalar(value: float, padding: float = 0.0) -> "Tensor":
+        h = u64()
+        check(_L().ct_scalar(float(value), float(padding), C.byref(h)))
+        return Tensor._wrap(h)
+
+    @staticmethod
+    def fill(value: float, shape: Sequence[int], padding: float = 0.0) -> "Tensor":
+        sa, rank = _shape_arg(shape)
+        h = u64()
+        check(_L().ct_fill(float(value), sa, rank, float(padding), C.byref(h)))
+        return Tensor._wrap(h)
+
+    @staticmethod
+    def random(shape: Sequence[int], seed: int, padding: float = 0.0) -> "Tensor":
+        sa, rank = _shape_arg(shape)
+        h = u64()
+        check(_L().ct_random(sa, rank, np.int32(np.uint32(seed & 0xFFFFFFFF)).item(), float(padding), C.byref(h)))
+        return Tensor._wrap(h)
+
+    @staticmethod
+    def randomNormal(shape: Sequence[int], seed: int, padding: float = 0.0) -> "Tensor":
+        sa, rank = _shape_arg(shape)
+        h = u64()
+        check(_L().ct_random_normal(sa, rank, np.int32(np.uint32(seed & 0xFFFFFFFF)).item(), float(padding), C.byref(h)))
+        return Tensor._wrap(h)
+
+    @staticmethod
+    def fromBuffer(buf: Buffer, shape: Sequence[int], padding: float = 0.0) -> "Tensor":
+        sa, rank = _shape_arg(shape)
+        h = u64()
+        check(_L().ct_from_buffer(buf.handle, sa, rank, float(padding), C.byref(h)))
+        return Tensor._wrap(h)
+
+    @staticmethod
+    def _un(op: str, t: "Tensor") -> "Tensor":
+        h = u64()
+        check(_L().ct_unary(_UNARY[op], t._h, C.byref(h)))
+        return Tensor._wrap(h)
+
+    @staticmethod
+    def _bin(op: str, l: "Tensor", r: "Tensor") -> "Tensor":
+        h = u64()
+        check(_L().ct_binary(_BINARY[op], l._h, r._h, C.byref(h)))
+        return Tensor._wrap(h)
+
+    abs = staticmethod(lambda t: Tensor._un("abs", t))
+    sqrt = staticmethod(lambda t: Tensor._un("sqrt", t))
+    tanh = staticmethod(lambda t: Tensor._un("tanh", t))
+    exp = staticmethod(lambda t: Tensor._un("exp", t))
+    log = staticmethod(lambda t: Tensor._un("log", t))
+    min = staticmethod(lambda l, r: Tensor._bin("min", l, r))
+    max = staticmethod(lambda l, r: Tensor._bin("max", l, r))
+
+    @staticmethod
+    def join(tensors: Iterable["Tensor"], dimension: int | None = None) -> "Tensor":
+        ts = list(tensors)
+        arr = (u64 * max(1, len(ts)))(*[t._h for t in ts])
+        h = u64()
+        if dimension is None:
+            check(_L().ct_join(arr, len(ts), C.byref(h)))
+        else:
+            check(_L().ct_join_dim(arr, len(ts), int(dimension), C.byref(h)))
+        return Tensor._wrap(h)
+
+    # -- operators --
+    def __add__(self, o):
+        return Tensor._bin("+", self, o)
+
+    def __sub__(self, o):
+        return Tensor._bin("-", self, o)
+
+    def __mul__(self, o):
+        return Tensor._bin("*", self, o)
+
+    def __truediv__(self, o):
+        return Tensor._bin("/", self, o)
+
+    def __mod__(self, o):
+        return Tensor._bin("%", self, o)
+
+    def __neg__(self):
+        return Tensor._un("neg", self)
+
+    def __pos__(self):
+        return self
+
+    # -- delayed --
+    def _shape_op(self, fn, shape) -> "Tensor":
+        sa, rank = _shape_arg(shape)
+        h = u64()
+        check(fn(self._h, sa, rank, C.byref(h)))
+        return Tensor._wrap(h)
+
+    def broadcast(self, newShape) -> "Tensor":
+        return self._shape_op(_L().ct_broadcast, newShape)
+
+    def reshape(self, newShape) -> "Tensor":
+        return self._shape_op(_L().ct_reshape, newShape)
+
+    def scale(self, newShape) -> "Tensor":
+        return self._shape_op(_L().ct_scale, newShape)
+
+    def translate(self, offset: Sequence[float], newShape: Sequence[int] | None = None) -> "Tensor":
+        off = (C.c_double * max(1, len(offset)))(*[float(o) for o in offset])
+        h = u64()
+        if newShape is None:
+            check(_L().ct_translate(self._h, off, len(offset), None, -1, C.byref(h)))
+        else:
+            sa, rank = _shape_arg(newShape)
+            check(_L().ct_translate(self._h, off, len(offset), sa, rank, C.byref(h)))
+        return Tensor._wrap(h)
+
+    def permute(self, dimensions: Sequence[int]) -> "Tensor":
+        sa, n = _shape_arg(dimensions)
+        h = u64()
+        check(_L().ct_permute(self._h, sa, n, C.byref(h)))
+        return Tensor._wrap(h)
+
+    def transpose(self) -> "Tensor":
+        h = u64()
+        check(_L().ct_transpose(self._h, C.byref(h)))
+        return Tensor._wrap(h)
+
+    def split(self, dimension: int) -> list["Tensor"]:
+        n = C.c_int()
+        check(_L().ct_split(self._h, int(dimension), None, 0, C.byref(n)))
+        arr = (u64 * max(1, n.value))()
+        check(_L().ct_split(self._h, int(dimension), arr, n.value, C.byref(n)))
+        return [Tensor(_handle=arr[i]) for i in range(n.value)]
+
+    def sum(self) -> "Tensor":
+        h = u64()
+        check(_L().ct_sum(self._h, C.byref(h)))
+        return Tensor._wrap(h)
+
+    def nonInline(self) -> "Tensor":
+        h = u64()
+        check(_L().ct_non_inline(self._h, C.byref(h)))
+        return Tensor._wrap(h)
+
+    def doCache(self) -> "Tensor":
+        """evaluates now and pins the buffer until the returned tensor is released (Tensors.scala:642-666)"""
+        h = u64()
+        check(_L().ct_do_cache(self._h, C.byref(h)))
+        return Tensor._wrap(h)
+
+    # -- properties --
+    @property
+    def shape(self) -> tuple:
+        r = C.c_int()
+        check(_L().ct_rank(self._h, C.byref(r)))
+        arr = (i32 * max(1, r.value))()
+        check(_L().ct_shape(self._h, arr, r.value))
+        return tuple(arr[i] for i in range(r.value))
+
+    @property
+    def padding(self) -> float:
+        p = C.c_float()
+        check(_L().ct_padding(self._h, C.byref(p)))
+        return p.value
+
+    # -- slow actions --
+    def flatArray(self) -> np.ndarray:
+        n = int(np.prod(self.shape, dtype=np.int64)) if self.shape else 1
+        out = np.empty(n, dtype=np.float32)
+        check(_L().ct_flat_array(self._h, out.ctypes.data, n))
+        return out
+
+    def flatArrayInto(self, host_ptr: int, capacity_floats: int) -> None:
+        check(_L().ct_flat_array(self._h, host_ptr, int(capacity_floats)))
+
+    def toString(self) -> str:
+        need = u64()
+        check(_L().ct_to_string(self._h, None, 0, C.byref(need)))
+        buf = C.create_string_buffer(need.value)
+        check(_L().ct_to_string(self._h, buf, need.value, None))
+        return buf.value.decode()
+
+    __str__ = toString
+
+    def doBuffer(self) -> Buffer:
+        h = u64()
+        check(_L().ct_do_buffer(self._h, C.byref(h), None))
+        return Buffer(h.value)
+
+    def compile(self) -> Kernel:
+        h = u64()
+        check(_L().ct_compile(self._h, C.byref(h)))
+        return Kernel(h.value)
+
+    def release(self) -> None:
+        if getattr(self, "_h", 0):
+            check(_L().ct_release(self._h))
+            self._h = 0
+
+    def __del__(self):
+        try:
+            if _lib._lib is not None:
+                self.release()
+        except Exception:
+            pass
+
+
+def live_tensors() -> int:
+    n = C.c_int64()
+    check(_L().ct_live_tensors(C.byref(n)))
+    return n.value

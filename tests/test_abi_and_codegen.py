@@ -1,0 +1,200 @@
+"""CPU-only checks (no GPU, no compute calls): the C-ABI library loads and exports every symbol include/compute_cuda.h
+declares, the product path fails loudly without a driver, and the code generator (tree blob -> plan -> NVRTC for
+sm_100a) behaves as the reference's kernel cache / Trees laws require (TreesSpec.scala:36-91, TensorsSpec.scala:37-55)."""
+import ctypes as C
+import struct
+
+import numpy as np
+import pytest
+
+from compute.scala_b200 import _lib, cuda
+
+
+def test_library_exports_every_declared_symbol():
+    names = _lib.declared_symbols()
+    assert len(names) >= 70
+    L = _lib.lib()
+    for n in names:
+        assert getattr(L, n) is not None
+    assert b"sm_100a" in L.cc_version()
+
+
+def test_no_cpu_fallback_without_a_gpu():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(cuda.ComputeCudaError) as e:
+        cuda.init()
+    assert e.value.status in (-3, -4, -8)
+    # compute entry points refuse to run without a context
+    with pytest.raises(cuda.ComputeCudaError):
+        cuda.Tensor.fill(1.0, [4]).flatArray()
+    with pytest.raises(cuda.ComputeCudaError):
+        cuda.Buffer.alloc(16)
+
+
+def test_product_does_not_import_the_oracle():
+    import os
+    import re
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pkg = os.path.join(root, "compute")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cpp", ".cu", ".h", ".cuh")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", text, flags=re.M), f
+                assert "oracle_cpu" not in text, f
+
+
+T = cuda.Tensor
+
+
+def rnd(shape, seed=1):
+    return T.random(shape, seed=seed)  # lazy: no device work until a slow action
+
+
+def test_kernel_cache_is_structural():
+    # same structure, different parameter identities and seeds -> one compile (TreesSpec.scala:47-66, TensorsSpec.scala:50-52)
+    k1 = T.tanh(rnd([64, 64], 1) * rnd([64, 64], 2) + rnd([64, 64], 3)).compile()
+    before = cuda.stats()
+    k2 = T.tanh(rnd([64, 64], 7) * rnd([64, 64], 8) + rnd([64, 64], 9)).compile()
+    after = cuda.stats()
+    assert k1.handle == k2.handle and k2.info.cache_hit == 1
+    assert after["compiles"] == before["compiles"] and after["cache_hits"] == before["cache_hits"] + 1
+    # different literal / shape / padding / operand order -> different kernels (TreesSpec.scala:68-91)
+    base = (T.fill(2.0, [8]) + rnd([8])).compile()
+    assert (T.fill(3.0, [8]) + rnd([8])).compile().handle != base.handle
+    assert (T.fill(2.0, [9]) + rnd([9])).compile().handle != base.handle
+    assert (rnd([8]) + T.fill(2.0, [8])).compile().handle != base.handle
+    p0 = T.random([8], seed=1, padding=0.0).translate([1]).compile()
+    p1 = T.random([8], seed=1, padding=1.0).translate([1]).compile()
+    assert p0.handle != p1.handle
+    # sharing is part of the structure: x*x (one parameter) is not x*y (two)
+    x = rnd([8])
+    assert (x * x).compile().info.n_args == 1
+    assert (x * rnd([8], 2)).compile().info.n_args == 2
+    assert (x * x).compile().handle != (x * rnd([8], 2)).compile().handle
+
+
+def test_parameter_order_is_dfs_preorder():
+    # parameterDescendants (Tensors.scala:230-251): a, b, c for tanh(a*b+c)
+    k = T.tanh(rnd([4, 4], 1) * rnd([4, 4], 2) + rnd([4, 4], 3)).compile()
+    ords = []
+    for i in range(k.info.n_args):
+        o = C.c_int32()
+        cuda.check(cuda._L().cc_kernel_arg_param(k.handle, i, C.byref(o)))
+        ords.append(o.value)
+    assert ords == [0, 1, 2]
+
+
+def test_c1_kernel_is_vectorised_and_flat():
+    k = T.tanh(rnd([1024, 1024], 1) * rnd([1024, 1024], 2) + rnd([1024, 1024], 3)).compile()
+    assert k.info.kind == 0 and k.info.n_args == 3
+    assert k.info.algorithmic_bytes == 16 * 1024 * 1024
+    src = k.source
+    assert "V=4" in src and "flat=1" in src and "cc_ldg4(p0 + v * 4" in src and "cc_stg4" in src
+
+
+def test_views_fold_into_integer_strides_and_drop_dead_bounds_tests():
+    t = rnd([512, 512, 512], 7)
+    src = t.permute([2, 0, 1]).translate([3, -5, 7]).compile().source
+    # out[g0,g1,g2] = T[g1+5, g2-7, g0-3]
+    assert "(int)1307133 + (int)1 * g0 + (int)262144 * g1 + (int)512 * g2" in src
+    assert "i0_0 < 512" in src and "i0_2 >= 0" in src and "k1 >= 0" in src
+    assert "i0_0 >= 0" not in src and "i0_2 < 512" not in src  # proven in range by interval analysis
+    # permute / broadcast / split can never leave the source: no tests at all, and the contiguous case vectorises
+    src = rnd([512, 512], 8).reshape([1, 512, 512]).broadcast([512, 512, 512]).compile().source
+    assert "?" not in src.split("// elementwise")[1].split("st(")[0]
+    assert "cc_ldg4" in src
+    src = rnd([512, 512], 8).broadcast([512, 512, 512]).compile().source
+    assert "L0[1] = L0[2] = L0[3] = L0[0]" in src  # trailing broadcast: one scalar load feeds 4 lanes
+
+
+def axis_sum(x, axis):
+    parts = x.split(axis)
+    acc = parts[0]
+    for p in parts[1:]:
+        acc = acc + p
+    return acc
+
+
+def test_plus_chain_is_rerolled_into_a_reduction():
+    x = rnd([256, 512])
+    k0 = axis_sum(x, 0).compile()
+    assert k0.info.kind == 1 and k0.info.n_args == 1 and "column owner" in k0.source
+    assert k0.info.algorithmic_bytes == 4 * 256 * 512 + 4 * 512
+    k1 = axis_sum(x, 1).compile()
+    assert k1.info.kind == 1 and "row owner" in k1.source
+    # short chains stay unrolled in one elementwise kernel, as the reference runs them
+    assert axis_sum(rnd([4, 16]), 0).compile().info.kind == 0
+    # a chain whose terms are not congruent is not a reduction
+    y = rnd([8, 16])
+    parts = y.split(0)
+    acc = parts[0]
+    for i, p in enumerate(parts[1:]):
+        acc = acc + (p * p if i == 3 else p)
+    assert acc.compile().info.kind == 0
+
+
+def matmul2(a, b):
+    i, j = a.shape
+    _, k = b.shape
+    product = a.broadcast([i, j, k]) * b.reshape([1, j, k]).broadcast([i, j, k])
+    return axis_sum(product, 1)
+
+
+def test_matmul_pattern_is_recognised_through_the_fusion_barrier():
+    k = matmul2(rnd([64, 48], 1), rnd([48, 32], 2)).compile()
+    info = k.info
+    assert info.kind in (1, 2)
+    assert info.n_args == 2  # A and B — never the i*j*k product
+    assert "inline operand composed into the reduction" in k.source
+    big = matmul2(rnd([256, 128], 1), rnd([128, 256], 2)).compile()
+    assert big.info.flops in (2 * 256 * 128 * 256, 2 * 256 * 128 * 256)
+
+
+def test_join_is_rerolled_into_an_output_dimension():
+    t = rnd([16, 8, 32])
+    k = T.join(t.split(1)).compile()
+    assert k.info.kind == 0 and "join re-rolled" in k.source and k.info.out_floats == 16 * 8 * 32
+    k2 = T.join([rnd([4, 4], 1), rnd([4, 4], 2) * rnd([4, 4], 3)]).compile()
+    assert "per-index tuple stores" in k2.source and k2.info.out_floats == 32
+
+
+def test_bad_blobs_are_rejected():
+    L = cuda._L()
+    h = C.c_uint64()
+    for blob in (b"", b"\x00" * 16, struct.pack("<4I", 0x31544343, 1, 5, 0), struct.pack("<4I", 0x31544343, 1, 0, 0) + struct.pack("<I", 99)):
+        st = L.cc_compile(blob, len(blob), C.byref(h))
+        assert st == -6, st
+        assert L.cc_last_error()
+
+
+def test_error_behaviour_matches_the_reference():
+    with pytest.raises(ValueError):  # IllegalArgumentException, Tensors.scala:208-222
+        rnd([2, 3]) + rnd([3, 3])
+    with pytest.raises(ValueError):  # Tensors.scala:879-882
+        rnd([2, 3]).reshape([4, 2])
+    with pytest.raises(ValueError):  # Tensors.scala:1009-1011
+        rnd([2, 3]).permute([0])
+    with pytest.raises(ValueError):  # Tensors.scala:971-973
+        rnd([2, 3]).translate([1.0])
+    with pytest.raises(ValueError):  # Tensors.scala:845-848
+        rnd([2, 3]).broadcast([2, 4])
+    with pytest.raises(ValueError):
+        T([[1.0], [2.0, 3.0]])
+    assert (rnd([2, 1]) + rnd([1, 3])).shape == (2, 3)
+    assert (rnd([2]) + rnd([2, 3])).shape == (2, 3)
+    assert rnd([2, 3, 4]).transpose().shape == (4, 3, 2)
+    assert [p.shape for p in rnd([2, 3, 4]).split(1)] == [(2, 4)] * 3
+    assert T.join(rnd([2, 3, 4]).split(1), 1).shape == (2, 3, 4)
+
+
+def test_deep_chains_do_not_overflow_the_stack():
+    x = rnd([16384, 8])
+    k = axis_sum(x, 0).compile()  # 16384-term Plus chain (the JVM recurses to this depth, Trees.scala:70-91)
+    assert k.info.kind == 1
+    del x, k
+    assert cuda.live_tensors() >= 0

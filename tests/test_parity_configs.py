@@ -1,0 +1,274 @@
+"""GPU parity, part 2: the five BASELINE.json configurations, CUDA path (through the C ABI) vs the CPU oracle on the
+same seeded inputs, at sizes the oracle finishes in seconds; full-size runs are checked through size-independent
+properties (tests/test_full_size.py).  Tolerances are the north star's: bit-exact for index/view work, <= 2 ulp for
+fused elementwise fp32, <= 1e-5 relative for reductions and matmul."""
+import numpy as np
+import pytest
+
+from oracle import reference as ref
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def cuda():
+    from compute.scala_b200 import cuda as c
+
+    c.init()
+    yield c
+    c.synchronize()
+
+
+def bits(a):
+    return np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
+
+
+def oracle_bracket(build, *args):
+    """oracle result with and without FP_CONTRACT (the reference compiles with -cl-unsafe-math-optimizations)"""
+    out = []
+    for contract in (False, True):
+        ref.CONTRACT[0] = contract
+        try:
+            out.append(build(ref.Tensor, *args).flat_array())
+        finally:
+            ref.CONTRACT[0] = False
+    return out
+
+
+def min_ulp(got, candidates):
+    d = None
+    for c in candidates:
+        x = ref.ulp_distance(got, c)
+        d = x if d is None else np.minimum(d, x)
+    return d
+
+
+# ---- C1: tanh(a*b+c), 1024 x 1024 ------------------------------------------------------------------------------------
+
+
+def c1(T, n):
+    a, b, c = T.random([n, n], seed=1), T.random([n, n], seed=2), T.random([n, n], seed=3)
+    return T.tanh(a * b + c)
+
+
+@pytest.mark.parametrize("n", [1024, 33])
+def test_c1_fused_elementwise(cuda, n):
+    got = c1(cuda.Tensor, n).flatArray()
+    d = min_ulp(got, oracle_bracket(c1, n))
+    assert d.max() <= 2, f"max ulp distance {d.max()}"
+
+
+# ---- C2: long chain with every op kind -----------------------------------------------------------------------------------
+
+
+def c2(T, shape):
+    a, b, c = T.random(shape, seed=1), T.random(shape, seed=2), T.random(shape, seed=3)
+    t = a * b + c
+    u = T.exp(t)
+    v = T.log(u + a)
+    w = T.tanh(v * b)
+    return w + c
+
+
+def c2_fp64_truth(shape):
+    n = int(np.prod(shape))
+    a, b, c = (ref.random_buffer(n, s).astype(np.float64) for s in (1, 2, 3))
+    return (np.tanh(np.log(np.exp(a * b + c) + a) * b) + c).astype(np.float32)
+
+
+@pytest.mark.parametrize("shape", [(1024, 1024), (7, 5, 3), (4099,)])
+def test_c2_long_chain(cuda, shape):
+    got = c2(cuda.Tensor, list(shape)).flatArray()
+    step = oracle_bracket(c2, list(shape))
+    d_step = min_ulp(got, step)
+    d_truth = ref.ulp_distance(got, c2_fp64_truth(shape))
+    d_oracle_truth = ref.ulp_distance(step[0], c2_fp64_truth(shape))
+    # the CUDA path must be no further from the correctly rounded result than 2 ulp, and the restated reference
+    # (fp32 steps with correctly rounded libm) is reported beside it
+    assert d_truth.max() <= 2, (d_truth.max(), d_oracle_truth.max(), d_step.max())
+    assert d_step.max() <= 3
+
+
+def test_all_elementwise_ops(cuda):
+    """every node kind of Expressions.scala:103-124 on awkward shapes (ragged sizes exercise the scalar tail path)"""
+    for shape in ([5, 7], [64, 64], [3, 1, 9]):
+
+        def build(T):
+            x, y = T.random(shape, seed=11), T.random(shape, seed=12)
+            one = T.fill(1.0, shape)
+            e = T.sqrt(x + one) / (y + one)
+            e = T.max(e, x) - T.min(y, e)
+            e = T.abs(-e) % (y + one)
+            return e * T.exp(x) + T.log(y + one)
+
+        got = build(cuda.Tensor).flatArray()
+        d = min_ulp(got, oracle_bracket(build))
+        assert d.max() <= 2, (shape, d.max())
+
+
+# ---- C3: reductions ----------------------------------------------------------------------------------------------------------
+
+
+def dataset_e(T, shape, seed=5):
+    """floor(random*9) - 4 in {-4..4}: exactly summable in any order. floor is built from `%`."""
+    r = T.random(shape, seed=seed) * T.fill(9.0, shape)
+    return (r - r % T.fill(1.0, shape)) - T.fill(4.0, shape)
+
+
+def dataset_e_np(n, seed=5):
+    r = (ref.random_buffer(n, seed) * np.float32(9.0)).astype(np.float32)
+    return (np.floor(r) - np.float32(4.0)).astype(np.float32)
+
+
+@pytest.mark.parametrize("n", [1024, 1000, 17])
+def test_c3_full_sum(cuda, n):
+    T = cuda.Tensor
+    e = dataset_e(T, [n, n])
+    want_e = dataset_e_np(n * n)
+    assert np.array_equal(e.flatArray(), want_e)
+    got = e.sum().flatArray()[0]
+    assert got == ref.sum_reference_cpu_order(want_e) == np.float32(want_e.astype(np.int64).sum())  # bit-exact
+    u = T.random([n, n], seed=5)
+    got_u = float(u.sum().flatArray()[0])
+    truth = float(ref.random_buffer(n * n, 5).astype(np.float64).sum())
+    ref_order = float(ref.sum_reference_cpu_order(ref.random_buffer(n * n, 5)))
+    assert abs(got_u - truth) <= 1e-5 * abs(truth), (got_u, truth, ref_order)
+
+
+def axis_sum(T, x, axis):
+    parts = x.split(axis)
+    acc = parts[0]
+    for p in parts[1:]:
+        acc = acc + p
+    return acc
+
+
+@pytest.mark.parametrize("shape,axis", [((512, 1024), 0), ((512, 1024), 1), ((256, 8, 12), 0), ((33, 70), 1), ((6, 9), 0)])
+def test_c3_axis_sums(cuda, shape, axis):
+    T = cuda.Tensor
+    n = int(np.prod(shape))
+    e = dataset_e(T, list(shape)).doCache()
+    k = axis_sum(T, e, axis).compile()
+    assert k.info.kind == (1 if shape[axis] >= 8 else 0)  # re-rolled into a real reduction
+    got = axis_sum(T, e, axis).flatArray()
+    want = dataset_e_np(n).reshape(shape).astype(np.int64).sum(axis=axis).astype(np.float32).reshape(-1)
+    assert np.array_equal(got, want)  # bit-exact on exactly summable data
+    u = T.random(list(shape), seed=5).doCache()
+    got_u = axis_sum(T, u, axis).flatArray().astype(np.float64)
+    x = ref.random_buffer(n, 5).reshape(shape)
+    truth = x.astype(np.float64).sum(axis=axis).reshape(-1)
+    left_fold = np.add.accumulate(np.moveaxis(x, axis, 0), axis=0, dtype=np.float32)[-1].reshape(-1)  # reference order
+    assert np.abs(got_u - truth).max() <= 1e-5 * np.abs(truth).max()
+    assert np.abs(got_u - left_fold.astype(np.float64)).max() <= 2e-5 * np.abs(truth).max()
+
+
+# ---- C4: views ------------------------------------------------------------------------------------------------------------------
+
+
+@pytest.mark.parametrize("n", [64, 20])
+def test_c4_views_bit_exact(cuda, n):
+    def permute_translate(T):
+        t = T.random([n, n, n], seed=7)
+        return t.permute([2, 0, 1]).translate([3, -5, 7])
+
+    def trailing(T):
+        return T.random([n, n], seed=8).broadcast([n, n, n])
+
+    def leading(T):
+        return T.random([n, n], seed=8).reshape([1, n, n]).broadcast([n, n, n])
+
+    def split_join(T):
+        return T.join(T.random([n, n, n], seed=7).split(1))
+
+    def split_join_mid(T):
+        return T.join(T.random([n, n, n], seed=7).split(1), 1)
+
+    def fused_views(T):  # views feeding arithmetic in one kernel
+        t = T.random([n, n, n], seed=7)
+        m = T.random([n, n], seed=8)
+        return t.transpose() * m.broadcast([n, n, n]) + t.translate([1, 0, -2])
+
+    for build in (permute_translate, trailing, leading, split_join, split_join_mid):
+        got = build(cuda.Tensor).flatArray()
+        want = build(ref.Tensor).flat_array()
+        assert np.array_equal(bits(got), bits(want)), build.__name__
+    got = fused_views(cuda.Tensor).flatArray()
+    assert min_ulp(got, oracle_bracket(fused_views)).max() <= 1
+
+
+def test_c4_roundtrip_is_identity(cuda):
+    T = cuda.Tensor
+    t = T.random([24, 16, 40], seed=7).doCache()
+    base = t.flatArray()
+    assert np.array_equal(bits(T.join(t.split(1), 1).flatArray()), bits(base))
+    assert np.array_equal(bits(t.permute([2, 0, 1]).permute([1, 2, 0]).flatArray()), bits(base))
+    assert np.array_equal(bits(t.translate([1, -2, 3]).translate([-1, 2, -3]).flatArray()[:0]), bits(base)[:0])
+
+
+def test_scale_non_integer_coefficients(cuda):
+    """Tensors.scala:950-965 + the DecimalFormat / (int) truncation quirks of OpenCLKernelBuilder.scala:14-32,386"""
+    for src, dst in (([6, 9], [4, 3]), ([5, 5], [7, 8]), ([3, 4], [9, 16])):
+
+        def build(T):
+            return T.random(src, seed=21).scale(dst)
+
+        got = build(cuda.Tensor).flatArray()
+        want = build(ref.Tensor).flat_array()
+        assert np.array_equal(bits(got), bits(want)), (src, dst)
+
+
+# ---- C5: matmul expressed as split / broadcast / sum ---------------------------------------------------------------------------------
+
+
+def matmul2(T, a, b):  # benchmarks.scala:188-191
+    i, j = a.shape
+    _, k = b.shape
+    product = a.broadcast([i, j, k]) * b.reshape([1, j, k]).broadcast([i, j, k])
+    parts = product.split(1)
+    acc = parts[0]
+    for p in parts[1:]:
+        acc = acc + p
+    return acc
+
+
+def left_fold_matmul(a, b):
+    """restated reference arithmetic: C[i,k] = fp32 left fold over t of A[i,t]*B[t,k]"""
+    acc = (a[:, 0:1] * b[0:1, :]).astype(np.float32)
+    for t in range(1, a.shape[1]):
+        acc = (acc + (a[:, t : t + 1] * b[t : t + 1, :]).astype(np.float32)).astype(np.float32)
+    return acc
+
+
+@pytest.mark.parametrize("m,k,n", [(128, 256, 128), (256, 512, 384), (48, 40, 24), (5, 9, 7)])
+def test_c5_matmul_pattern(cuda, m, k, n):
+    T = cuda.Tensor
+    rng = np.random.default_rng(9)
+    a_e = rng.integers(-4, 5, (m, k)).astype(np.float32)
+    b_e = rng.integers(-4, 5, (k, n)).astype(np.float32)
+    got = matmul2(T, T(a_e), T(b_e)).flatArray().reshape(m, n)
+    assert np.array_equal(got, left_fold_matmul(a_e, b_e))  # dataset E: bit-exact
+    assert np.array_equal(got, (a_e.astype(np.int64) @ b_e.astype(np.int64)).astype(np.float32))
+    a_n = ref.random_normal_buffer(m * k, 9).reshape(m, k)
+    b_n = ref.random_normal_buffer(k * n, 10).reshape(k, n)
+    got = matmul2(T, T(a_n), T(b_n)).flatArray().reshape(m, n).astype(np.float64)
+    want = left_fold_matmul(a_n, b_n).astype(np.float64)
+    scale = np.abs(a_n.astype(np.float64)) @ np.abs(b_n.astype(np.float64))
+    assert (np.abs(got - want) / scale).max() <= 1e-5
+    truth = a_n.astype(np.float64) @ b_n.astype(np.float64)
+    assert (np.abs(got - truth) / scale).max() <= 1e-5
+
+
+def test_c5_never_materialises_the_product(cuda):
+    """matmul2's i*j*k intermediate (SURVEY finding 2) must not be allocated: the pattern is composed into the reduction"""
+    T = cuda.Tensor
+    m = k = n = 256
+    a, b = T.randomNormal([m, k], seed=9).doCache(), T.randomNormal([k, n], seed=10).doCache()
+    cuda.synchronize()
+    before = cuda.stats()
+    kern = matmul2(T, a, b).compile()
+    assert kern.info.kind in (1, 2)
+    assert kern.info.n_args == 2
+    out = matmul2(T, a, b).flatArray()
+    after = cuda.stats()
+    assert out.size == m * n
+    assert after["bytes_in_use"] == before["bytes_in_use"]
