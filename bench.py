@@ -52,7 +52,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -67,7 +67,11 @@ class ClockSampler:
             self.proc.terminate()
 
     def summary(self, t0: float, t1: float) -> dict:
-        rows = [r for t, r in self.rows if t0 - 0.05 <= t <= t1 + 0.15 and len(r) >= 7] or [r for _, r in self.rows if len(r) >= 7]
+        good = [(t, r) for t, r in self.rows if len(r) >= 7]
+        rows = [r for t, r in good if t0 <= t <= t1 + 0.03]
+        if len(rows) < 3 and good:  # timed region shorter than a few sampling periods: take the samples nearest to it
+            mid = 0.5 * (t0 + t1)
+            rows = [r for _, r in sorted(good, key=lambda tr: abs(tr[0] - mid))[:5]]
         if not rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
         sm = sorted(float(r[0]) for r in rows)
@@ -228,6 +232,8 @@ def run_cuda(args, rank: int, local_rank: int, world: int):
         dist_mod.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
         dist = dist_mod
     cuda.init(local_rank, streams=1)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     T = cuda.Tensor
     pk, pk_kind = peaks()
     hbm_peak = float(pk["hbm_gbs"])
@@ -249,8 +255,6 @@ def run_cuda(args, rank: int, local_rank: int, world: int):
     def step():
         expr.doBuffer().release()
 
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     if dist:
         dist.barrier()
     ms, launches, w0, w1 = time_steps(cuda, step, args.steps, args.warmup)
@@ -261,7 +265,6 @@ def run_cuda(args, rank: int, local_rank: int, world: int):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
         dist.barrier()
-    clocks = sampler.summary(w0, w1)
     ms_per_step = ms / args.steps
     value = world * alg_bytes / ms_per_step / 1e6  # GB/s, whole job
     kernel_gbs = alg_bytes / ms_per_step / 1e6
@@ -312,6 +315,8 @@ def run_cuda(args, rank: int, local_rank: int, world: int):
         # the bytes that came back are the chain's result (spot check against the device-resident evaluation)
         ref_out = expr.flatArray()
         e2e_ok = bool(np.array_equal(ref_out[: 1 << 20].view(np.uint32), ho.array[: 1 << 20].view(np.uint32)))
+    time.sleep(0.1)
+    clocks = sampler.summary(w0, w1)
     sampler.stop()
 
     line = None
@@ -359,7 +364,7 @@ def run_cuda(args, rank: int, local_rank: int, world: int):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--rows", type=int, default=ROWS, help="rows of the [rows,16384] shard per GPU (default = the full config)")

@@ -5,6 +5,7 @@
 #include <charconv>
 #include <cmath>
 #include <cstring>
+#include <mutex>
 
 #include "ndat.h"
 
@@ -118,15 +119,31 @@ struct Counted : Tensor {
   Counted() { g_live.fetch_add(1); }
 };
 
-PendingBuffer enqueue_closure(Session& s, Tensor::EmitCtx& ctx, uint32_t root, const Shape& out_shape, bool attach_definitions);
+struct PlanCache {
+  std::mutex mu;
+  cc_kernel kernel = 0;
+  std::vector<const Tensor*> args;  // kept alive by the owning tensor's own sub-graph
+  ~PlanCache() {
+    if (kernel) cc_kernel_release(kernel);
+  }
+};
+void resolve_plan(PlanCache& pc, Tensor::EmitCtx& ctx, uint32_t root, const Shape& out_shape);
+PendingBuffer enqueue_plan(Session& s, const PlanCache& pc, const Shape& out_shape);
 
 // InlineTensor (Tensors.scala:1400-1411)
 struct InlineTensor : Counted {
+  mutable PlanCache plan;
   bool is_inline() const override { return true; }
   PendingBuffer evaluate(Session& s) const override {
-    EmitCtx ctx;
-    uint32_t root = closure(ctx);
-    return enqueue_closure(s, ctx, root, shape, true);
+    {
+      std::lock_guard<std::mutex> lock(plan.mu);
+      if (!plan.kernel) {
+        EmitCtx ctx;
+        uint32_t root = closure(ctx);
+        resolve_plan(plan, ctx, root, shape);
+      }
+    }
+    return enqueue_plan(s, plan, shape);
   }
 };
 
@@ -238,10 +255,17 @@ struct JoinTensor final : NonInlineTensor {
     for (auto& t : tensors) e.push_back(t->closure(ctx));
     return ctx.w.concatenate(e);
   }
+  mutable PlanCache plan;
   PendingBuffer evaluate(Session& s) const override {
-    EmitCtx ctx;
-    uint32_t root = emit_root(ctx);
-    return enqueue_closure(s, ctx, root, shape, true);
+    {
+      std::lock_guard<std::mutex> lock(plan.mu);
+      if (!plan.kernel) {
+        EmitCtx ctx;
+        uint32_t root = emit_root(ctx);
+        resolve_plan(plan, ctx, root, shape);
+      }
+    }
+    return enqueue_plan(s, plan, shape);
   }
 };
 
@@ -267,35 +291,45 @@ cc_kernel compile_closure(Tensor::EmitCtx& ctx, uint32_t root, const Shape& out_
   return k;
 }
 
-// enqueueClosure (Tensors.scala:1291-1392)
-PendingBuffer enqueue_closure(Session& s, Tensor::EmitCtx& ctx, uint32_t root, const Shape& out_shape, bool attach_definitions) {
+// The graph under a tensor is immutable, so the kernel its closure compiles to and the tensors that kernel takes as
+// arguments never change: resolve them once per tensor. (The reference re-hashes the whole tree on every evaluation,
+// Tensors.scala:1293 — O(nodes) per slow action, which for a 16384-term per-axis sum is ~10 ms of host time.)
+void resolve_plan(PlanCache& pc, Tensor::EmitCtx& ctx, uint32_t root, const Shape& out_shape) {
   std::vector<uint64_t> ids;
-  cc_kernel k = compile_closure(ctx, root, out_shape, attach_definitions, &ids);
-  std::vector<cc_buffer> args;
-  cc_buffer out = 0;
-  auto cleanup = [&] {
-    for (cc_buffer b : args) cc_buffer_release(b);
-    cc_kernel_release(k);
-  };
+  cc_kernel k = compile_closure(ctx, root, out_shape, true, &ids);
   try {
     cc_kernel_info_t info;
     check(cc_kernel_info(k, &info));
+    std::vector<const Tensor*> args;
     for (int i = 0; i < info.n_args; ++i) {
       int32_t ord = -1;
       check(cc_kernel_arg_param(k, i, &ord));
       CC_REQUIRE(ord >= 0 && (size_t)ord < ids.size(), CC_ERR_BAD_TREE, "kernel argument refers to unknown parameter %d", ord);
-      const Tensor* t = (const Tensor*)(uintptr_t)ids[(size_t)ord];
-      // upvalues.traverse(tree.id.asInstanceOf[Tensor].doBuffer) — Tensors.scala:1336-1340
-      args.push_back(t->do_buffer(s).buffer);
+      args.push_back((const Tensor*)(uintptr_t)ids[(size_t)ord]);
     }
-    check(cc_buffer_alloc((uint64_t)product(out_shape), &out));
-    check(cc_launch(k, args.data(), (int)args.size(), out, nullptr, 0, nullptr));
+    pc.args = std::move(args);
+    pc.kernel = k;
   } catch (...) {
-    if (out) cc_buffer_release(out);
-    cleanup();
+    cc_kernel_release(k);
     throw;
   }
-  cleanup();
+}
+
+// enqueueClosure (Tensors.scala:1291-1392)
+PendingBuffer enqueue_plan(Session& s, const PlanCache& pc, const Shape& out_shape) {
+  std::vector<cc_buffer> args;
+  cc_buffer out = 0;
+  try {
+    // upvalues.traverse(tree.id.asInstanceOf[Tensor].doBuffer) — Tensors.scala:1336-1340
+    for (const Tensor* t : pc.args) args.push_back(t->do_buffer(s).buffer);
+    check(cc_buffer_alloc((uint64_t)product(out_shape), &out));
+    check(cc_launch(pc.kernel, args.data(), (int)args.size(), out, nullptr, 0, nullptr));
+  } catch (...) {
+    if (out) cc_buffer_release(out);
+    for (cc_buffer b : args) cc_buffer_release(b);
+    throw;
+  }
+  for (cc_buffer b : args) cc_buffer_release(b);
   return {out, 0};
 }
 

@@ -70,23 +70,61 @@ def c2(T, shape):
     return w + c
 
 
-def c2_fp64_truth(shape):
+def c2_truth_and_bound(shape, func_ulps=2.0):
+    """fp64 evaluation of the chain plus the first-order forward error bound of an fp32 evaluation in which every
+    + and * is correctly rounded (relative error <= 2^-24) and exp / log / tanh are within `func_ulps` ulp — i.e. what
+    "each fused op within 2 ulp" means for a chain whose intermediate roundings are amplified at ill-conditioned
+    points (log(u + a) near u + a = 1)."""
     n = int(np.prod(shape))
     a, b, c = (ref.random_buffer(n, s).astype(np.float64) for s in (1, 2, 3))
-    return (np.tanh(np.log(np.exp(a * b + c) + a) * b) + c).astype(np.float32)
+    u24, F = 2.0**-24, func_ulps * 2.0**-23
+    ab = a * b
+    t = ab + c
+    e_t = (np.abs(ab) + np.abs(t)) * u24
+    u = np.exp(t)
+    e_u = u * e_t + u * F
+    s_ = u + a
+    e_s = e_u + np.abs(s_) * u24
+    v = np.log(s_)
+    e_v = e_s / s_ + np.abs(v) * F
+    p = v * b
+    e_p = np.abs(b) * e_v + np.abs(p) * u24
+    w = np.tanh(p)
+    e_w = (1.0 - w * w) * e_p + np.abs(w) * F
+    out = w + c
+    e_out = e_w + np.abs(out) * u24
+    return out, 1.05 * e_out + 1e-30
 
 
 @pytest.mark.parametrize("shape", [(1024, 1024), (7, 5, 3), (4099,)])
 def test_c2_long_chain(cuda, shape):
-    got = c2(cuda.Tensor, list(shape)).flatArray()
-    step = oracle_bracket(c2, list(shape))
-    d_step = min_ulp(got, step)
-    d_truth = ref.ulp_distance(got, c2_fp64_truth(shape))
-    d_oracle_truth = ref.ulp_distance(step[0], c2_fp64_truth(shape))
-    # the CUDA path must be no further from the correctly rounded result than 2 ulp, and the restated reference
-    # (fp32 steps with correctly rounded libm) is reported beside it
-    assert d_truth.max() <= 2, (d_truth.max(), d_oracle_truth.max(), d_step.max())
-    assert d_step.max() <= 3
+    got = c2(cuda.Tensor, list(shape)).flatArray().astype(np.float64)
+    truth, bound = c2_truth_and_bound(shape, func_ulps=2.0)
+    ratio = np.abs(got - truth) / bound
+    assert ratio.max() <= 1.0, f"error is {ratio.max():.2f}x the 2-ulp-per-op bound"
+    # the restated reference (fp32 steps, correctly rounded libm) sits inside the same envelope; the two agree to within
+    # the sum of their envelopes
+    for step in oracle_bracket(c2, list(shape)):
+        assert (np.abs(step.astype(np.float64) - truth) <= bound).all()
+        assert (np.abs(step.astype(np.float64) - got) <= 2 * bound).all()
+    # where the chain is well conditioned (bound below 2 ulp of the result) the plain 2-ulp statement holds
+    well = bound <= 2 * np.spacing(np.abs(truth).astype(np.float32)).astype(np.float64)
+    if well.any():
+        d = ref.ulp_distance(got.astype(np.float32)[well], truth.astype(np.float32)[well])
+        assert d.max() <= 2
+
+
+@pytest.mark.parametrize("op", ["exp", "log", "tanh", "sqrt", "abs"])
+def test_single_op_within_2_ulp(cuda, op):
+    """each math function alone, fused with the affine map that spreads random() over its interesting domain"""
+    T = cuda.Tensor
+    n = 1 << 20
+    lo, hi = {"exp": (-20.0, 20.0), "log": (1e-6, 30.0), "tanh": (-9.0, 9.0), "sqrt": (0.0, 1e6), "abs": (-1.0, 1.0)}[op]
+    x_np = (ref.random_buffer(n, 31) * np.float32(hi - lo) + np.float32(lo)).astype(np.float32)
+    x = T(x_np)
+    got = getattr(T, op)(x).flatArray()
+    want = getattr(np, op if op != "abs" else "abs")(x_np.astype(np.float64)).astype(np.float32)
+    assert ref.ulp_distance(got, want).max() <= 2
 
 
 def test_all_elementwise_ops(cuda):
