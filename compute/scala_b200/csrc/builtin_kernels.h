@@ -22,14 +22,16 @@ bool gemm_available();
 
 // ---- contraction ----------------------------------------------------------------------------------------------------
 struct GemmWorkspace {
-  float* a_lo;   // [M,K]  A - tf32_trunc(A)
-  float* bt_hi;  // [N,K]  B^T
-  float* bt_lo;  // [N,K]  (B - tf32_trunc(B))^T
+  float* a_hi;   // [M,K]  tf32_trunc(A)
+  float* a_lo;   // [M,K]  tf32(A - a_hi)
+  float* bt_hi;  // [N,K]  tf32_trunc(B)^T
+  float* bt_lo;  // [N,K]  tf32(B - b_hi)^T
 };
+constexpr int kGemmTileM = 128, kGemmTileN = 256, kGemmTileK = 32;
 typedef CUresult (*TensorMapEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                       const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                       CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-// C[M,N] = A[M,K] * B[K,N], fp32 row-major, 3xTF32 on tcgen05. M % 128 == 0, N % 128 == 0, K % 32 == 0.
+// C[M,N] = A[M,K] * B[K,N], fp32 row-major, 3xTF32 on tcgen05. M % 128 == 0, N % 256 == 0, K % 32 == 0.
 // Returns the number of device kernels launched; throws cc::Error on failure.
 int launch_gemm_3xtf32(const float* a, const float* b, float* c, int64_t m, int64_t n, int64_t k,
                        const GemmWorkspace& ws, int sm_count, TensorMapEncodeFn encode, cudaStream_t stream);

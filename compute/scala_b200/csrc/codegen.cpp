@@ -986,7 +986,7 @@ Plan make_plan(const Tree& t, const DeviceProps& dev) {
         int a_arg = -1, b_arg = -1;
         if (is_A(La) && is_B(Lb)) a_arg = La.arg, b_arg = Lb.arg;
         if (is_A(Lb) && is_B(La)) a_arg = Lb.arg, b_arg = La.arg;
-        if (a_arg >= 0 && a_arg != b_arg && M % 128 == 0 && N % 128 == 0 && K % 32 == 0 && M * K < ((int64_t)1 << 31) &&
+        if (a_arg >= 0 && a_arg != b_arg && M % 128 == 0 && N % 256 == 0 && K % 32 == 0 && M * K < ((int64_t)1 << 31) &&
             N * K < ((int64_t)1 << 31)) {
           plan.kind = PLAN_CONTRACTION;
           plan.M = M;
@@ -999,7 +999,7 @@ Plan make_plan(const Tree& t, const DeviceProps& dev) {
           plan.arg_min_floats = am;
           plan.flops = 2ull * (uint64_t)M * (uint64_t)N * (uint64_t)K;
           plan.algorithmic_bytes = 4ull * (uint64_t)(M * K + K * N + M * N);
-          plan.scratch_floats = {(uint64_t)(M * K), (uint64_t)(N * K), (uint64_t)(N * K)};
+          plan.scratch_floats = {(uint64_t)(M * K), (uint64_t)(M * K), (uint64_t)(N * K), (uint64_t)(N * K)};
           plan.note += strprintf("; contraction %lldx%lldx%lld -> tcgen05 3xTF32", (long long)M, (long long)N, (long long)K);
           plan.source = "// contraction pattern: runs the precompiled TMA + tcgen05 3xTF32 pipeline (gemm_3xtf32.cu)\n";
           return plan;

@@ -1,9 +1,385 @@
-// gemm_3xtf32.cu — placeholder until the tcgen05 pipeline lands (next commit).
+// gemm_3xtf32.cu — the contraction the matmul pattern (split / broadcast / sum, benchmarks.scala:174-193,
+// README.md:312-343) lowers to:  C[M,N] = A[M,K] * B[K,N], fp32 in / fp32 out, computed on the 5th-generation tensor
+// cores as 3xTF32 so fp32 accuracy is kept (north star): with x = hi + lo, hi = the TF32-representable top of x,
+//     A*B ~= A_lo*B_hi + A_hi*B_lo + A_hi*B_hi        (lo*lo ~ 2^-22 relative is dropped)
+// all three products accumulated into the same fp32 TMEM accumulator, small terms first.
+//
+// Pipeline (sm_100a only — TMA, mbarrier, tcgen05, TMEM):
+//   prologue kernels   split A into A_hi / A_lo [M,K] and B into B^T_hi / B^T_lo [N,K]  (both operands K-major)
+//   gemm kernel        persistent, one CTA per SM, 128 x 256 output tile, BLOCK_K = 32 floats (one 128-byte swizzle row)
+//     warp 0  TMA producer: 4 tiles per stage (A_hi, A_lo, B_hi, B_lo), SWIZZLE_128B, mbarrier expect_tx
+//     warp 1  MMA issuer: one elected thread issues 12 tcgen05.mma.kind::tf32 (M128 N256 K8) per stage,
+//             tcgen05.commit releases the smem stage / publishes the accumulator
+//     warp 2  TMEM allocator (512 columns = two 128x256 fp32 accumulators, so the epilogue of tile i overlaps tile i+1)
+//     warps 4-7  epilogue: tcgen05.ld 32 lanes x 32 columns -> registers -> 128-bit global stores
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
 #include "builtin_kernels.h"
 #include "common.h"
+
 namespace cc {
-bool gemm_available() { return false; }
-int launch_gemm_3xtf32(const float*, const float*, float*, int64_t, int64_t, int64_t, const GemmWorkspace&, int, TensorMapEncodeFn, cudaStream_t) {
-  fail(CC_ERR_UNSUPPORTED, "tcgen05 contraction not built");
+namespace {
+
+constexpr int BM = 128, BN = 256, BK = 32;  // BK floats = 128 bytes = one swizzle row
+constexpr int STAGES = 2;
+constexpr int A_TILE_BYTES = BM * BK * 4;                          // 16 KiB
+constexpr int B_TILE_BYTES = BN * BK * 4;                          // 32 KiB
+constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;   // 96 KiB
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int GEMM_THREADS = 256;
+constexpr int TMEM_COLS = 512;
+constexpr int GROUP_M = 16;  // tile rasterisation: 16 m-tiles share each sweep over n (L2 reuse of the A panels)
+
+// ---- PTX wrappers ------------------------------------------------------------------------------------------------------
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  uint32_t spins = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) return;
+    if (++spins > (1u << 26)) __trap();  // a pipeline bug must abort the launch, not hang the GPU
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int x, int y) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+               "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(x), "r"(y)
+               : "memory");
+}
+__device__ __forceinline__ void prefetch_tensormap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+
+// K-major operand, SWIZZLE_128B, rows of 128 bytes, 8-row groups 1024 bytes apart (cute::UMMA::SmemDescriptor)
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);  // start address
+  d |= (uint64_t)1 << 16;                      // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;            // stride byte offset between 8-row groups
+  d |= (uint64_t)1 << 46;                      // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                      // SWIZZLE_128B
+  return d;
+}
+
+// cute::UMMA::InstrDescriptor for kind::tf32, fp32 accumulate, both operands K-major, M = 128, N = 256
+constexpr uint32_t kInstrDesc = (1u << 4) /*D = f32*/ | (2u << 7) /*A = tf32*/ | (2u << 10) /*B = tf32*/ | ((uint32_t)(BN >> 3) << 17) |
+                                ((uint32_t)(BM >> 4) << 24);
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      :
+      : "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(kInstrDesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+        "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+        "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]),
+        "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ void tile_coords(int tile, int tiles_m, int tiles_n, int& m_blk, int& n_blk) {
+  const int per_group = GROUP_M * tiles_n;
+  const int group = tile / per_group;
+  const int first_m = group * GROUP_M;
+  const int rows = min(GROUP_M, tiles_m - first_m);
+  const int in_group = tile - group * per_group;
+  m_blk = first_m + in_group % rows;
+  n_blk = in_group / rows;
+}
+
+// ---- the GEMM ------------------------------------------------------------------------------------------------------------
+
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
+                   const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo, float* __restrict__ C, int N, int K,
+                   int tiles_m, int tiles_n) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024-byte alignment
+  const uint32_t bars = smem_base + STAGES * STAGE_BYTES;
+  // barrier layout (8 bytes each): full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], then the TMEM base address
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (STAGES + s); };
+  auto tmem_full_bar = [&](int a) { return bars + 8u * (2 * STAGES + a); };
+  auto tmem_empty_bar = [&](int a) { return bars + 8u * (2 * STAGES + 2 + a); };
+  const uint32_t tmem_slot = bars + 8u * (2 * STAGES + 4);
+  uint8_t* smem_generic = smem_raw + (smem_base - smem_u32(smem_raw));
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_generic + STAGES * STAGE_BYTES + 8 * (2 * STAGES + 4));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_tiles = tiles_m * tiles_n;
+  const int num_kb = K / BK;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tensormap(&tm_a_hi);
+    prefetch_tensormap(&tm_a_lo);
+    prefetch_tensormap(&tm_b_hi);
+    prefetch_tensormap(&tm_b_lo);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tmem_full_bar(a), 1);
+      mbar_init(tmem_empty_bar(a), 128);  // every epilogue thread arrives
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        int m_blk, n_blk;
+        tile_coords(tile, tiles_m, tiles_n, m_blk, n_blk);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1);
+          const uint32_t st = smem_base + stage * STAGE_BYTES;
+          mbar_arrive_expect_tx(full_bar(stage), STAGE_BYTES);
+          tma_load_2d(st, &tm_a_hi, full_bar(stage), kb * BK, m_blk * BM);
+          tma_load_2d(st + A_TILE_BYTES, &tm_a_lo, full_bar(stage), kb * BK, m_blk * BM);
+          tma_load_2d(st + 2 * A_TILE_BYTES, &tm_b_hi, full_bar(stage), kb * BK, n_blk * BN);
+          tma_load_2d(st + 2 * A_TILE_BYTES + B_TILE_BYTES, &tm_b_lo, full_bar(stage), kb * BK, n_blk * BN);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(tmem_empty_bar(acc), acc_phase ^ 1);  // the epilogue has drained this accumulator
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(full_bar(stage), phase);  // TMA has landed this stage
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t st = smem_base + stage * STAGE_BYTES;
+          const uint64_t a_hi = umma_desc_sw128(st);
+          const uint64_t a_lo = umma_desc_sw128(st + A_TILE_BYTES);
+          const uint64_t b_hi = umma_desc_sw128(st + 2 * A_TILE_BYTES);
+          const uint64_t b_lo = umma_desc_sw128(st + 2 * A_TILE_BYTES + B_TILE_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / 8; ++k) {
+            const uint64_t adv = (uint64_t)((k * 8 * 4) >> 4);  // +32 bytes along K inside the 128-byte swizzle row
+            umma_tf32(tmem_d, a_lo + adv, b_hi + adv, (kb | k) != 0);
+            umma_tf32(tmem_d, a_hi + adv, b_lo + adv, 1);
+            umma_tf32(tmem_d, a_hi + adv, b_hi + adv, 1);
+          }
+          umma_commit(empty_bar(stage));                          // frees the smem stage when these MMAs retire
+          if (kb == num_kb - 1) umma_commit(tmem_full_bar(acc));  // accumulator complete -> epilogue
+        }
+        __syncwarp();
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===== epilogue: TMEM -> registers -> global =====
+    const int ew = warp - 4;  // TMEM lanes [32*ew, 32*ew + 32)
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      int m_blk, n_blk;
+      tile_coords(tile, tiles_m, tiles_n, m_blk, n_blk);
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(tmem_full_bar(acc), acc_phase);
+      tc_fence_after();
+      const size_t row = (size_t)m_blk * BM + (size_t)ew * 32 + lane;
+      float* out = C + row * (size_t)N + (size_t)n_blk * BN;
+      const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * BN);
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32(taddr + (uint32_t)(c * 32), r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          float4 v = make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]), __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
+          __stcs(reinterpret_cast<float4*>(out + c * 32) + q, v);
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(tmem_empty_bar(acc));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
+  }
+}
+
+// ---- prologue: hi / lo split -------------------------------------------------------------------------------------------------
+
+__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
+  hi = __uint_as_float(__float_as_uint(x) & 0xffffe000u);  // exactly TF32-representable (the tensor core then has nothing to drop)
+  const float r = x - hi;                                  // exact in fp32
+  uint32_t t;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(r));
+  lo = __uint_as_float(t);
+}
+
+__global__ void __launch_bounds__(256) split_a_kernel(const float4* __restrict__ a, float4* __restrict__ hi, float4* __restrict__ lo, size_t nvec) {
+  const size_t stride = (size_t)gridDim.x * 256;
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < nvec; i += stride) {
+    const float4 x = __ldcs(a + i);
+    float4 h, l;
+    split_tf32(x.x, h.x, l.x);
+    split_tf32(x.y, h.y, l.y);
+    split_tf32(x.z, h.z, l.z);
+    split_tf32(x.w, h.w, l.w);
+    hi[i] = h;
+    lo[i] = l;
+  }
+}
+
+// B [K,N] row-major -> B^T hi / lo [N,K] row-major, 32x32 tiles through padded shared memory
+__global__ void __launch_bounds__(256) split_transpose_b_kernel(const float* __restrict__ b, float* __restrict__ bt_hi, float* __restrict__ bt_lo, int K,
+                                                                int N) {
+  __shared__ float th[32][33];
+  __shared__ float tl[32][33];
+  const int n0 = blockIdx.x * 32, k0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+#pragma unroll
+  for (int r = 0; r < 32; r += 8) {
+    const float x = b[(size_t)(k0 + ty + r) * N + n0 + tx];
+    float h, l;
+    split_tf32(x, h, l);
+    th[ty + r][tx] = h;
+    tl[ty + r][tx] = l;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < 32; r += 8) {
+    const size_t o = (size_t)(n0 + ty + r) * K + k0 + tx;
+    bt_hi[o] = th[tx][ty + r];
+    bt_lo[o] = tl[tx][ty + r];
+  }
+}
+
+void make_map(TensorMapEncodeFn encode, CUtensorMap* map, const float* base, int64_t rows, int64_t k, int box_rows) {
+  cuuint64_t dims[2] = {(cuuint64_t)k, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)k * 4};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) fail(CC_ERR_CUDA, strprintf("cuTensorMapEncodeTiled failed (%d)", (int)r));
+}
+
+void check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) fail(CC_ERR_CUDA, strprintf("%s launch failed: %s", what, cudaGetErrorString(e)));
+}
+
+}  // namespace
+
+bool gemm_available() { return true; }
+
+int launch_gemm_3xtf32(const float* a, const float* b, float* c, int64_t m, int64_t n, int64_t k, const GemmWorkspace& ws, int sm_count,
+                       TensorMapEncodeFn encode, cudaStream_t stream) {
+  CC_REQUIRE(m % BM == 0 && n % BN == 0 && k % BK == 0, CC_ERR_UNSUPPORTED, "gemm_3xtf32 needs M %% %d == 0, N %% %d == 0, K %% %d == 0", BM, BN,
+             BK);
+  CC_REQUIRE(encode, CC_ERR_NO_DRIVER, "cuTensorMapEncodeTiled unavailable");
+  // A_hi shares the B^T_hi workspace layout: ws.a_lo holds A_lo, A_hi is written into the first M*K floats of a second buffer
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_3xtf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e != cudaSuccess) fail(CC_ERR_CUDA, strprintf("cudaFuncSetAttribute(smem=%d): %s", SMEM_BYTES, cudaGetErrorString(e)));
+    attr_set = true;
+  }
+  const size_t nvec = (size_t)(m * k) / 4;
+  int blocks = (int)((nvec + 255) / 256);
+  if (blocks > sm_count * 8) blocks = sm_count * 8;
+  split_a_kernel<<<blocks, 256, 0, stream>>>(reinterpret_cast<const float4*>(a), reinterpret_cast<float4*>(ws.a_hi), reinterpret_cast<float4*>(ws.a_lo),
+                                             nvec);
+  check_launch("split_a");
+  split_transpose_b_kernel<<<dim3((unsigned)(n / 32), (unsigned)(k / 32)), 256, 0, stream>>>(b, ws.bt_hi, ws.bt_lo, (int)k, (int)n);
+  check_launch("split_transpose_b");
+  CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
+  make_map(encode, &ma_hi, ws.a_hi, m, k, BM);
+  make_map(encode, &ma_lo, ws.a_lo, m, k, BM);
+  make_map(encode, &mb_hi, ws.bt_hi, n, k, BN);
+  make_map(encode, &mb_lo, ws.bt_lo, n, k, BN);
+  const int tiles_m = (int)(m / BM), tiles_n = (int)(n / BN);
+  int grid = tiles_m * tiles_n;
+  if (grid > sm_count) grid = sm_count;
+  gemm_3xtf32_kernel<<<grid, GEMM_THREADS, SMEM_BYTES, stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, c, (int)n, (int)k, tiles_m, tiles_n);
+  check_launch("gemm_3xtf32");
+  return 3;
+}
+
 }  // namespace cc

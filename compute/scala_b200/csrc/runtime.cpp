@@ -825,7 +825,7 @@ int cc_kernel_source(cc_kernel h, const char** out) {
 
 namespace {
 void gemm_on_stream(Buffer* a, Buffer* b, Buffer* c, int64_t m, int64_t n, int64_t k, const std::vector<Buffer*>& scratch, CUstream s) {
-  GemmWorkspace ws{(float*)scratch[0]->ptr, (float*)scratch[1]->ptr, (float*)scratch[2]->ptr};
+  GemmWorkspace ws{(float*)scratch[0]->ptr, (float*)scratch[1]->ptr, (float*)scratch[2]->ptr, (float*)scratch[3]->ptr};
   int launched = launch_gemm_3xtf32((const float*)a->ptr, (const float*)b->ptr, (float*)c->ptr, m, n, k, ws, rt().info.sm_count,
                                     (TensorMapEncodeFn)driver().cuTensorMapEncodeTiled, (cudaStream_t)s);
   rt().stats.device_kernels += (uint64_t)launched;
@@ -943,13 +943,14 @@ int cc_matmul_3xtf32(cc_buffer a, cc_buffer b, cc_buffer c, int64_t m, int64_t n
     Buffer* ab = as_buffer(a);
     Buffer* bb = as_buffer(b);
     Buffer* cb = as_buffer(c);
-    CC_REQUIRE(m > 0 && n > 0 && k > 0 && m % 128 == 0 && n % 128 == 0 && k % 32 == 0, CC_ERR_UNSUPPORTED,
-               "cc_matmul_3xtf32 needs M %% 128 == 0, N %% 128 == 0, K %% 32 == 0 (got %lld x %lld x %lld)", (long long)m, (long long)n,
+    CC_REQUIRE(m > 0 && n > 0 && k > 0 && m % kGemmTileM == 0 && n % kGemmTileN == 0 && k % kGemmTileK == 0, CC_ERR_UNSUPPORTED,
+               "cc_matmul_3xtf32 needs M %% 128 == 0, N %% 256 == 0, K %% 32 == 0 (got %lld x %lld x %lld)", (long long)m, (long long)n,
                (long long)k);
     CC_REQUIRE(ab->n_floats >= (uint64_t)(m * k) && bb->n_floats >= (uint64_t)(k * n) && cb->n_floats >= (uint64_t)(m * n),
                CC_ERR_ILLEGAL_ARGUMENT, "matmul buffers too small");
     CC_REQUIRE(cb != ab && cb != bb, CC_ERR_ILLEGAL_ARGUMENT, "matmul output aliases an input");
-    std::vector<Buffer*> scratch{alloc_buffer((uint64_t)(m * k)), alloc_buffer((uint64_t)(n * k)), alloc_buffer((uint64_t)(n * k))};
+    std::vector<Buffer*> scratch{alloc_buffer((uint64_t)(m * k)), alloc_buffer((uint64_t)(m * k)), alloc_buffer((uint64_t)(n * k)),
+                                 alloc_buffer((uint64_t)(n * k))};
     Op op{pick_stream(), {ab, bb}, {cb}};
     for (Buffer* s : scratch) op.writes.push_back(s);
     op_begin(op, waits, n_waits);

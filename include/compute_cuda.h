@@ -172,7 +172,8 @@ int cc_random(cc_buffer out, uint64_t n_floats, int32_t seed, cc_event* out_even
 int cc_random_normal(cc_buffer out, uint64_t n_floats, int32_t seed, cc_event* out_event);
 
 /* C[M,N] = A[M,K] * B[K,N] (row-major fp32) with 3xTF32 tcgen05 MMAs; what the contraction pattern lowers to.
- * Exposed for direct measurement; `c` may alias neither input. */
+ * Exposed for direct measurement; `c` may alias neither input. Needs M % 128 == 0, N % 256 == 0, K % 32 == 0 (other
+ * shapes of the pattern run through the generic JIT reduction). */
 int cc_matmul_3xtf32(cc_buffer a, cc_buffer b, cc_buffer c, int64_t m, int64_t n, int64_t k, const cc_event* waits,
                      int n_waits, cc_event* out_event);
 
