@@ -649,6 +649,107 @@ void emit_elementwise(Plan& plan, const Program& p, int n_args, const DeviceProp
   (void)concat_fallback_n;
 }
 
+// ---- tiled-transpose elementwise kernel ---------------------------------------------------------------------------
+//
+// When a load is contiguous in the source along an output dimension d that is NOT the output's fastest dimension L
+// (permute / transpose views, `join` of a split), a plain gather reads 4 bytes per 128-byte line. This template walks
+// 32 x 32 tiles over (d, L): such loads are read with threads running along d (coalesced), staged through padded
+// shared memory, and consumed with threads running along L, where every other load and the store are coalesced.
+int transpose_dim(const Program& p) {
+  const int nd = (int)p.dims.size();
+  if (nd < 2 || p.results.size() != 1) return -1;
+  const int L = nd - 1;
+  int d = -1;
+  for (const Load& ld : p.loads) {
+    if (!ld.integer) return -1;
+    if (ld.coef[L] == 0 || ld.coef[L] == 1 || ld.coef[L] == -1) continue;
+    for (int x = 0; x < L; ++x)
+      if (ld.coef[x] == 1 && p.dims[x] >= 32) {
+        if (d < 0) d = x;
+        break;
+      }
+  }
+  if (d < 0 || p.dims[L] < 32) return -1;
+  return d;
+}
+
+void emit_tiled_transpose(Plan& plan, const Program& p, int n_args, const DeviceProps& dev, int d) {
+  const int nd = (int)p.dims.size();
+  const int L = nd - 1;
+  const int64_t total = product(p.dims);
+  const char* IDX = pick_idx_type(p, total);
+  const int nloads = (int)p.loads.size();
+  std::vector<int> slot(nloads, -1);
+  int nt = 0;
+  for (int j = 0; j < nloads; ++j) {
+    const Load& ld = p.loads[j];
+    if (ld.coef[L] != 0 && ld.coef[L] != 1 && ld.coef[L] != -1 && ld.coef[d] == 1) slot[j] = nt++;
+  }
+  // 64 x 64 tiles (256-byte row segments on both sides, 16 independent loads in flight per thread) when the extents allow
+  const int TS = (p.dims[d] >= 64 && p.dims[L] >= 64 && nt <= 3) ? 64 : 32;
+  const int RY = 256 / TS;       // rows covered per pass
+  const int NR = TS / RY;        // passes
+  const int64_t tilesL = (p.dims[L] + TS - 1) / TS, tilesD = (p.dims[d] + TS - 1) / TS;
+  int64_t outer = 1;
+  for (int x = 0; x < nd; ++x)
+    if (x != d && x != L) outer *= p.dims[x];
+  const int64_t ntiles = tilesL * tilesD * outer;
+  int64_t grid = std::min<int64_t>(ntiles, (int64_t)dev.sm_count * (TS == 64 ? 6 : 8));
+  if (grid < 1) grid = 1;
+  std::vector<int64_t> ostride(nd, 1);
+  for (int x = nd - 2; x >= 0; --x) ostride[x] = ostride[x + 1] * p.dims[x + 1];
+
+  Emit e;
+  e("// tiled transpose: dims=[");
+  for (int x = 0; x < nd; ++x) e("%s%lld", x ? "," : "", (long long)p.dims[x]);
+  e("] tile %dx%d over (g%d, g%d), %d staged load(s) of %d, idx=%s grid=%lld\n", TS, TS, d, L, nt, nloads, IDX, (long long)grid);
+  e("extern \"C\" __global__ void __launch_bounds__(256) jit_kernel(%s) {\n", param_list(n_args, true).c_str());
+  e("  __shared__ float tile[%d][%d][%d];\n", nt, TS, TS + 1);
+  e("  const int tx = threadIdx.x %% %d, ty = threadIdx.x / %d;\n", TS, TS);
+  e("  for (%s t_ = blockIdx.x; t_ < (%s)%lld; t_ += gridDim.x) {\n", IDX, IDX, (long long)ntiles);
+  e("    %s r_ = t_;\n    const %s tl = r_ %% (%s)%lld; r_ /= (%s)%lld;\n    const %s td = r_ %% (%s)%lld; r_ /= (%s)%lld;\n", IDX, IDX, IDX, (long long)tilesL, IDX,
+    (long long)tilesL, IDX, IDX, (long long)tilesD, IDX, (long long)tilesD);
+  for (int x = nd - 1; x >= 0; --x) {
+    if (x == d || x == L) continue;
+    e("    const %s g%d = r_ %% (%s)%lld; r_ /= (%s)%lld;\n", IDX, x, IDX, (long long)p.dims[x], IDX, (long long)p.dims[x]);
+  }
+  LoadCtx c{1, -1, IDX};
+  // phase 1: threads run along d (the source-contiguous index of the staged loads)
+  e("    #pragma unroll\n    for (int r = 0; r < %d; ++r) {\n", NR);
+  e("      const %s g%d = td * %d + tx;\n      const %s g%d = tl * %d + ty + %d * r;\n", IDX, d, TS, IDX, L, TS, RY);
+  e("      if (g%d < (%s)%lld && g%d < (%s)%lld) {\n", d, IDX, (long long)p.dims[d], L, IDX, (long long)p.dims[L]);
+  for (int j = 0; j < nloads; ++j) {
+    if (slot[j] < 0) continue;
+    e("        {\n");
+    emit_load(e, p, j, c, "          ");
+    e("          tile[%d][ty + %d * r][tx] = L%d[0];\n        }\n", slot[j], RY, j);
+  }
+  e("      }\n    }\n    __syncthreads();\n");
+  // phase 2: threads run along L (the output-contiguous index)
+  e("    #pragma unroll\n    for (int r = 0; r < %d; ++r) {\n", NR);
+  e("      const %s g%d = td * %d + ty + %d * r;\n      const %s g%d = tl * %d + tx;\n", IDX, d, TS, RY, IDX, L, TS);
+  e("      if (g%d < (%s)%lld && g%d < (%s)%lld) {\n", d, IDX, (long long)p.dims[d], L, IDX, (long long)p.dims[L]);
+  for (int j = 0; j < nloads; ++j) {
+    if (slot[j] >= 0)
+      e("        const float L%d[1] = {tile[%d][tx][ty + %d * r]};\n", j, slot[j], RY);
+    else
+      emit_load(e, p, j, c, "        ");
+  }
+  emit_ops(e, p, "        ", "0");
+  std::string lin = "(long long)0";
+  for (int x = 0; x < nd; ++x) lin += strprintf(" + (long long)g%d * %lldLL", x, (long long)ostride[x]);
+  e("        __stcs(out + (%s), _%d);\n", lin.c_str(), p.results[0]);
+  e("      }\n    }\n    __syncthreads();\n  }\n}\n");
+  plan.source += e.s;
+  LaunchSpec ls;
+  ls.entry = "jit_kernel";
+  ls.grid[0] = (uint32_t)grid;
+  ls.block[0] = 256;
+  for (int i = 0; i < n_args; ++i) ls.args.push_back(i);
+  ls.args.push_back(ARG_OUT);
+  if (total > 0) plan.launches.push_back(ls);
+}
+
 // ---- reductions over the re-rolled index --------------------------------------------------------------------------
 
 // out[g] = sum_t E(g, t).  dims = out dims + [T].
@@ -1008,8 +1109,14 @@ Plan make_plan(const Tree& t, const DeviceProps& dev) {
     }
     emit_reduce(plan, prog, n_args, dev);
   } else {
-    plan.kind = PLAN_ELEMENTWISE;
-    emit_elementwise(plan, prog, n_args, dev, 0);
+    const int td = transpose_dim(prog);
+    if (td >= 0) {
+      plan.kind = PLAN_TILED_TRANSPOSE;
+      emit_tiled_transpose(plan, prog, n_args, dev, td);
+    } else {
+      plan.kind = PLAN_ELEMENTWISE;
+      emit_elementwise(plan, prog, n_args, dev, 0);
+    }
   }
   return plan;
 }

@@ -29,20 +29,29 @@ struct Event {
   std::atomic<int> rc{1};
 };
 
+// A point on a stream's timeline: "the first `seq` commands submitted to stream `stream`". Hazards between commands
+// on different streams are resolved lazily: only when a consumer on another stream shows up is an event recorded on
+// the producer's stream (which then covers the producer command and everything before it). Commands on the same
+// stream need nothing, so the common single-stream launch path makes no event / wait driver calls at all.
+struct Mark {
+  int stream = -1;
+  uint64_t seq = 0;
+};
+
 struct Buffer {
   CUdeviceptr ptr = 0;
   uint64_t n_floats = 0;
   size_t bytes = 0;  // pooled block size (0 for wrapped memory)
   bool owned = true;
   std::atomic<int> rc{1};
-  Event* last_write = nullptr;
-  std::vector<Event*> reads;
+  Mark last_write;
+  std::vector<Mark> reads;  // at most one per stream
 };
 
 struct Block {
   CUdeviceptr ptr;
   size_t bytes;
-  std::vector<Event*> pending;
+  std::vector<Mark> pending;
 };
 
 struct Kernel {
@@ -91,10 +100,12 @@ struct Runtime {
   CUdevice dev = 0;
   CUcontext ctx = nullptr;
   cc_device_info_t info{};
-  std::vector<CUstream> streams;
+  std::vector<CUstream> streams;       // compute streams [0, stream_count), then h2d, d2h, aux
+  std::vector<uint64_t> seq;           // commands submitted per stream
+  std::vector<std::vector<uint64_t>> synced;  // synced[s][a]: stream s already waits for the first synced[s][a] commands of a
   size_t next_stream = 0;
   int stream_count = 4;
-  CUstream h2d = nullptr, d2h = nullptr, aux = nullptr;
+  int h2d = 0, d2h = 0, aux = 0;       // indices into `streams`
   std::vector<CUevent> event_pool;
   std::map<size_t, std::vector<Block>> pool;
   size_t bytes_pooled = 0, bytes_in_use = 0;
@@ -167,61 +178,68 @@ Kernel* as_kernel(cc_kernel h) {
 
 // ---- streams & hazards ---------------------------------------------------------------------------------------------------
 
-CUstream pick_stream() {
+int pick_stream() {
   Runtime& r = rt();
-  CUstream s = r.streams[r.next_stream % r.streams.size()];
+  int s = (int)(r.next_stream % (size_t)r.stream_count);
   r.next_stream++;
   return s;
 }
 
 struct Op {
-  CUstream stream;
+  int stream;
   std::vector<Buffer*> reads, writes;
+  CUstream cu() const { return rt().streams[(size_t)stream]; }
 };
+
+void need(int s, const Mark& m) {
+  Runtime& r = rt();
+  if (m.stream < 0 || m.stream == s || r.synced[(size_t)s][(size_t)m.stream] >= m.seq) return;
+  CUevent ev;
+  if (!r.event_pool.empty()) {
+    ev = r.event_pool.back();
+    r.event_pool.pop_back();
+  } else {
+    CC_CU(cuEventCreate(&ev, CU_EVENT_DISABLE_TIMING));
+  }
+  CC_CU(cuEventRecord(ev, r.streams[(size_t)m.stream]));
+  CC_CU(cuStreamWaitEvent(r.streams[(size_t)s], ev, 0));
+  r.synced[(size_t)s][(size_t)m.stream] = r.seq[(size_t)m.stream];
+  r.event_pool.push_back(ev);  // the wait has captured this record; the CUevent can be re-recorded
+}
 
 void op_begin(Op& op, const cc_event* waits, int n_waits) {
   for (int i = 0; i < n_waits; ++i)
-    if (waits[i]) CC_CU(cuStreamWaitEvent(op.stream, as_event(waits[i])->ev, 0));
-  for (Buffer* b : op.reads)
-    if (b->last_write) CC_CU(cuStreamWaitEvent(op.stream, b->last_write->ev, 0));
+    if (waits[i]) CC_CU(cuStreamWaitEvent(op.cu(), as_event(waits[i])->ev, 0));
+  for (Buffer* b : op.reads) need(op.stream, b->last_write);  // read after write
   for (Buffer* b : op.writes) {
-    if (b->last_write) CC_CU(cuStreamWaitEvent(op.stream, b->last_write->ev, 0));
-    for (Event* e : b->reads) CC_CU(cuStreamWaitEvent(op.stream, e->ev, 0));
+    need(op.stream, b->last_write);                       // write after write
+    for (const Mark& m : b->reads) need(op.stream, m);    // write after read (also covers pooled-memory reuse)
   }
 }
 
 void op_end(Op& op, cc_event* out_event) {
-  Event* e = new_event();
-  CC_CU(cuEventRecord(e->ev, op.stream));
+  Runtime& r = rt();
+  const uint64_t q = ++r.seq[(size_t)op.stream];
   for (Buffer* b : op.writes) {
-    if (b->last_write) release(b->last_write);
-    for (Event* x : b->reads) release(x);
     b->reads.clear();
-    b->last_write = e;
-    retain(e);
+    b->last_write = Mark{op.stream, q};
   }
   for (Buffer* b : op.reads) {
     bool also_written = false;
     for (Buffer* w : op.writes) also_written |= (w == b);
     if (also_written) continue;
-    if (b->reads.size() >= 16) {
-      // prune completed readers
-      std::vector<Event*> keep;
-      for (Event* x : b->reads) {
-        if (driver().cuEventQuery(x->ev) == CUDA_SUCCESS)
-          release(x);
-        else
-          keep.push_back(x);
+    bool found = false;
+    for (Mark& m : b->reads)
+      if (m.stream == op.stream) {
+        m.seq = q;
+        found = true;
       }
-      b->reads.swap(keep);
-    }
-    b->reads.push_back(e);
-    retain(e);
+    if (!found) b->reads.push_back(Mark{op.stream, q});
   }
   if (out_event) {
+    Event* e = new_event();
+    CC_CU(cuEventRecord(e->ev, op.cu()));
     *out_event = (cc_event)(uintptr_t)e;  // the creation reference goes to the caller
-  } else {
-    release(e);
   }
 }
 
@@ -241,10 +259,7 @@ size_t size_class(size_t bytes) {
 void trim_pool() {
   Runtime& r = rt();
   for (auto& kv : r.pool)
-    for (Block& b : kv.second) {
-      for (Event* e : b.pending) release(e);
-      driver().cuMemFree(b.ptr);
-    }
+    for (Block& b : kv.second) driver().cuMemFree(b.ptr);
   r.pool.clear();
   r.bytes_pooled = 0;
 }
@@ -286,13 +301,10 @@ void release(Buffer* b) {
   r.buffers.erase(b);
   if (b->owned && r.initialized) {
     Block blk{b->ptr, b->bytes, std::move(b->reads)};
-    if (b->last_write) blk.pending.push_back(b->last_write);
+    if (b->last_write.stream >= 0) blk.pending.push_back(b->last_write);
     r.pool[b->bytes].push_back(std::move(blk));
     r.bytes_pooled += b->bytes;
     r.bytes_in_use -= b->bytes;
-  } else {
-    if (b->last_write) release(b->last_write);
-    for (Event* e : b->reads) release(e);
   }
   delete b;
 }
@@ -343,18 +355,9 @@ void release(Kernel* k) {
   delete k;
 }
 
-void join_all(CUstream target) {
+void join_all(int target) {
   Runtime& r = rt();
-  std::vector<CUstream> all = r.streams;
-  all.push_back(r.h2d);
-  all.push_back(r.d2h);
-  for (CUstream s : all) {
-    if (s == target) continue;
-    Event* e = new_event();
-    CC_CU(cuEventRecord(e->ev, s));
-    CC_CU(cuStreamWaitEvent(target, e->ev, 0));
-    release(e);
-  }
+  for (int a = 0; a < (int)r.streams.size(); ++a) need(target, Mark{a, r.seq[(size_t)a] + 1});
 }
 
 Buffer* reduce_scratch() {
@@ -422,15 +425,17 @@ int cc_init(int device_ordinal) {
       fail(CC_ERR_UNSUPPORTED, strprintf("device %d (%s) is sm_%d%d; this backend only generates sm_100a code", device_ordinal, di.name,
                                          di.cc_major, di.cc_minor));
     }
-    for (int i = 0; i < r.stream_count; ++i) {
+    // copies always get their own streams so H2D / compute / D2H of independent chunks overlap
+    for (int i = 0; i < r.stream_count + 3; ++i) {
       CUstream s;
       CC_CU(cuStreamCreate(&s, CU_STREAM_NON_BLOCKING));
       r.streams.push_back(s);
     }
-    // copies always get their own streams so H2D / compute / D2H of independent chunks overlap
-    CC_CU(cuStreamCreate(&r.h2d, CU_STREAM_NON_BLOCKING));
-    CC_CU(cuStreamCreate(&r.d2h, CU_STREAM_NON_BLOCKING));
-    CC_CU(cuStreamCreate(&r.aux, CU_STREAM_NON_BLOCKING));
+    r.h2d = r.stream_count;
+    r.d2h = r.stream_count + 1;
+    r.aux = r.stream_count + 2;
+    r.seq.assign(r.streams.size(), 0);
+    r.synced.assign(r.streams.size(), std::vector<uint64_t>(r.streams.size(), 0));
     CC_CU(cuEventCreate(&r.timer0, CU_EVENT_DEFAULT));
     CC_CU(cuEventCreate(&r.timer1, CU_EVENT_DEFAULT));
     r.initialized = true;
@@ -486,11 +491,7 @@ int cc_shutdown(void) {
       driver().cuEventDestroy(e->ev);
       e->ev = nullptr;
     }
-    std::unordered_set<CUstream> uniq(r.streams.begin(), r.streams.end());
-    uniq.insert(r.h2d);
-    uniq.insert(r.d2h);
-    uniq.insert(r.aux);
-    for (CUstream s : uniq) driver().cuStreamDestroy(s);
+    for (CUstream s : r.streams) driver().cuStreamDestroy(s);
     r.streams.clear();
     driver().cuEventDestroy(r.timer0);
     driver().cuEventDestroy(r.timer1);
@@ -542,7 +543,7 @@ int cc_buffer_upload(cc_buffer buf, const float* host, uint64_t n_floats, const 
       CC_REQUIRE(host || n_floats == 0, CC_ERR_ILLEGAL_ARGUMENT, "null host pointer");
       Op op{rt().h2d, {}, {b}};
       op_begin(op, waits, n_waits);
-      if (n_floats) CC_CU(cuMemcpyHtoDAsync(b->ptr, host, (size_t)n_floats * 4, op.stream));
+      if (n_floats) CC_CU(cuMemcpyHtoDAsync(b->ptr, host, (size_t)n_floats * 4, op.cu()));
       rt().stats.h2d_bytes += n_floats * 4;
       cc_event ev = 0;
       op_end(op, &ev);
@@ -628,7 +629,7 @@ int cc_buffer_to_host(cc_buffer h, uint64_t offset, float* host, uint64_t n_floa
       CC_REQUIRE(host || n_floats == 0, CC_ERR_ILLEGAL_ARGUMENT, "null host pointer");
       Op op{rt().d2h, {b}, {}};
       op_begin(op, waits, n_waits);
-      if (n_floats) CC_CU(cuMemcpyDtoHAsync(host, b->ptr + offset * 4, (size_t)n_floats * 4, op.stream));
+      if (n_floats) CC_CU(cuMemcpyDtoHAsync(host, b->ptr + offset * 4, (size_t)n_floats * 4, op.cu()));
       rt().stats.d2h_bytes += n_floats * 4;
       cc_event ev = 0;
       op_end(op, &ev);
@@ -718,8 +719,10 @@ int cc_event_on_complete(cc_event h, cc_event_callback cb, void* user) {
     require_init();
     CC_REQUIRE(cb, CC_ERR_ILLEGAL_ARGUMENT, "null callback");
     Event* e = as_event(h);
-    CC_CU(cuStreamWaitEvent(rt().aux, e->ev, 0));
-    CC_CU(cuLaunchHostFunc(rt().aux, host_trampoline, new Callback{cb, user}));
+    CUstream aux = rt().streams[(size_t)rt().aux];
+    CC_CU(cuStreamWaitEvent(aux, e->ev, 0));
+    CC_CU(cuLaunchHostFunc(aux, host_trampoline, new Callback{cb, user}));
+    rt().seq[(size_t)rt().aux]++;
   });
 }
 
@@ -858,7 +861,7 @@ int cc_launch(cc_kernel h, const cc_buffer* args, int n_args, cc_buffer out, con
     for (Buffer* s : scratch) op.writes.push_back(s);
     op_begin(op, waits, n_waits);
     if (p.kind == PLAN_CONTRACTION) {
-      gemm_on_stream(in[0], in[1], ob, p.M, p.N, p.K, scratch, op.stream);
+      gemm_on_stream(in[0], in[1], ob, p.M, p.N, p.K, scratch, op.cu());
     } else {
       for (size_t li = 0; li < p.launches.size(); ++li) {
         const LaunchSpec& ls = p.launches[li];
@@ -874,7 +877,7 @@ int cc_launch(cc_kernel h, const cc_buffer* args, int n_args, cc_buffer out, con
             ptrs.push_back(scratch[ARG_SCRATCH0 - a]->ptr);
         }
         for (CUdeviceptr& q : ptrs) argv.push_back(&q);
-        CC_CU(cuLaunchKernel(k->fns[li], ls.grid[0], ls.grid[1], ls.grid[2], ls.block[0], ls.block[1], ls.block[2], ls.smem, op.stream,
+        CC_CU(cuLaunchKernel(k->fns[li], ls.grid[0], ls.grid[1], ls.grid[2], ls.block[0], ls.block[1], ls.block[2], ls.smem, op.cu(),
                              argv.data(), nullptr));
         r.stats.device_kernels++;
       }
@@ -895,10 +898,10 @@ int cc_reduce_sum(cc_buffer in, uint64_t n_floats, cc_buffer out, const cc_event
     CC_REQUIRE(n_floats <= ib->n_floats && ob->n_floats >= 1 && ib != ob, CC_ERR_ILLEGAL_ARGUMENT, "bad reduce_sum arguments");
     Buffer* sc = reduce_scratch();
     // the shared scratch + counter serialise full reductions on one stream
-    Op op{r.streams[0], {ib}, {ob, sc}};
+    Op op{0, {ib}, {ob, sc}};
     op_begin(op, waits, n_waits);
     launch_reduce_sum((const float*)ib->ptr, n_floats, (float*)ob->ptr, (float*)sc->ptr, (unsigned*)r.reduce_counter, r.info.sm_count,
-                      (cudaStream_t)op.stream);
+                      (cudaStream_t)op.cu());
     r.stats.launches++;
     r.stats.device_kernels++;
     op_end(op, out_event);
@@ -913,7 +916,7 @@ int cc_random(cc_buffer out, uint64_t n_floats, int32_t seed, cc_event* out_even
     CC_REQUIRE(n_floats <= ob->n_floats, CC_ERR_ILLEGAL_ARGUMENT, "random: buffer too small");
     Op op{pick_stream(), {}, {ob}};
     op_begin(op, nullptr, 0);
-    launch_random((float*)ob->ptr, n_floats, seed, (cudaStream_t)op.stream);
+    launch_random((float*)ob->ptr, n_floats, seed, (cudaStream_t)op.cu());
     rt().stats.launches++;
     rt().stats.device_kernels++;
     op_end(op, out_event);
@@ -928,7 +931,7 @@ int cc_random_normal(cc_buffer out, uint64_t n_floats, int32_t seed, cc_event* o
     CC_REQUIRE(n_floats <= ob->n_floats, CC_ERR_ILLEGAL_ARGUMENT, "randomNormal: buffer too small");
     Op op{pick_stream(), {}, {ob}};
     op_begin(op, nullptr, 0);
-    launch_random_normal((float*)ob->ptr, n_floats, seed, (cudaStream_t)op.stream);
+    launch_random_normal((float*)ob->ptr, n_floats, seed, (cudaStream_t)op.cu());
     rt().stats.launches++;
     rt().stats.device_kernels++;
     op_end(op, out_event);
@@ -954,7 +957,7 @@ int cc_matmul_3xtf32(cc_buffer a, cc_buffer b, cc_buffer c, int64_t m, int64_t n
     Op op{pick_stream(), {ab, bb}, {cb}};
     for (Buffer* s : scratch) op.writes.push_back(s);
     op_begin(op, waits, n_waits);
-    gemm_on_stream(ab, bb, cb, m, n, k, scratch, op.stream);
+    gemm_on_stream(ab, bb, cb, m, n, k, scratch, op.cu());
     rt().stats.launches++;
     op_end(op, out_event);
     for (Buffer* s : scratch) release(s);
@@ -984,13 +987,11 @@ int cc_timer_start(void) {
     Lock lock;
     require_init();
     Runtime& r = rt();
-    join_all(r.aux);
-    CC_CU(cuEventRecord(r.timer0, r.aux));
-    std::unordered_set<CUstream> uniq(r.streams.begin(), r.streams.end());
-    uniq.insert(r.h2d);
-    uniq.insert(r.d2h);
-    for (CUstream s : uniq)
-      if (s != r.aux) CC_CU(cuStreamWaitEvent(s, r.timer0, 0));
+    join_all(r.aux);  // the stopwatch stream waits for everything submitted so far ...
+    CC_CU(cuEventRecord(r.timer0, r.streams[(size_t)r.aux]));
+    r.seq[(size_t)r.aux]++;
+    for (int s = 0; s < (int)r.streams.size(); ++s)  // ... and nothing submitted from now on starts before the timestamp
+      if (s != r.aux) CC_CU(cuStreamWaitEvent(r.streams[(size_t)s], r.timer0, 0));
   });
 }
 int cc_timer_stop(float* out_ms) {
@@ -1001,7 +1002,8 @@ int cc_timer_stop(float* out_ms) {
       Runtime& r = rt();
       CC_REQUIRE(out_ms, CC_ERR_ILLEGAL_ARGUMENT, "null output");
       join_all(r.aux);
-      CC_CU(cuEventRecord(r.timer1, r.aux));
+      CC_CU(cuEventRecord(r.timer1, r.streams[(size_t)r.aux]));
+      r.seq[(size_t)r.aux]++;
     }
     CC_CU(cuEventSynchronize(rt().timer1));
     CC_CU(cuEventElapsedTime(out_ms, rt().timer0, rt().timer1));
@@ -1063,9 +1065,9 @@ int cc_allreduce_sum(cc_buffer buf, uint64_t n_floats, const cc_event* waits, in
     Nccl& n = rt().nccl;
     Buffer* b = as_buffer(buf);
     CC_REQUIRE(n_floats <= b->n_floats, CC_ERR_ILLEGAL_ARGUMENT, "allreduce: buffer too small");
-    Op op{rt().streams[0], {}, {b}};
+    Op op{0, {}, {b}};
     op_begin(op, waits, n_waits);
-    if (n.comm) n.check(n.AllReduce((const void*)b->ptr, (void*)b->ptr, n_floats, ncclFloat, ncclSum, n.comm, (cudaStream_t)op.stream), "ncclAllReduce");
+    if (n.comm) n.check(n.AllReduce((const void*)b->ptr, (void*)b->ptr, n_floats, ncclFloat, ncclSum, n.comm, (cudaStream_t)op.cu()), "ncclAllReduce");
     op_end(op, out_event);
   });
 }
@@ -1078,12 +1080,12 @@ int cc_allgather(cc_buffer send, cc_buffer recv, uint64_t n_per_rank, const cc_e
     Buffer* d = as_buffer(recv);
     int ranks = n.comm ? n.n_ranks : 1;
     CC_REQUIRE(n_per_rank <= s->n_floats && n_per_rank * ranks <= d->n_floats && s != d, CC_ERR_ILLEGAL_ARGUMENT, "allgather: bad buffers");
-    Op op{rt().streams[0], {s}, {d}};
+    Op op{0, {s}, {d}};
     op_begin(op, waits, n_waits);
     if (n.comm)
-      n.check(n.AllGather((const void*)s->ptr, (void*)d->ptr, n_per_rank, ncclFloat, n.comm, (cudaStream_t)op.stream), "ncclAllGather");
+      n.check(n.AllGather((const void*)s->ptr, (void*)d->ptr, n_per_rank, ncclFloat, n.comm, (cudaStream_t)op.cu()), "ncclAllGather");
     else
-      CC_CU(cuMemcpyDtoDAsync(d->ptr, s->ptr, (size_t)n_per_rank * 4, op.stream));
+      CC_CU(cuMemcpyDtoDAsync(d->ptr, s->ptr, (size_t)n_per_rank * 4, op.cu()));
     op_end(op, out_event);
   });
 }
@@ -1094,9 +1096,9 @@ int cc_broadcast(cc_buffer buf, uint64_t n_floats, int root, const cc_event* wai
     Nccl& n = rt().nccl;
     Buffer* b = as_buffer(buf);
     CC_REQUIRE(n_floats <= b->n_floats, CC_ERR_ILLEGAL_ARGUMENT, "broadcast: buffer too small");
-    Op op{rt().streams[0], {}, {b}};
+    Op op{0, {}, {b}};
     op_begin(op, waits, n_waits);
-    if (n.comm) n.check(n.Broadcast((const void*)b->ptr, (void*)b->ptr, n_floats, ncclFloat, root, n.comm, (cudaStream_t)op.stream), "ncclBroadcast");
+    if (n.comm) n.check(n.Broadcast((const void*)b->ptr, (void*)b->ptr, n_floats, ncclFloat, root, n.comm, (cudaStream_t)op.cu()), "ncclBroadcast");
     op_end(op, out_event);
   });
 }

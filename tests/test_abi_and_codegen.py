@@ -102,8 +102,9 @@ def test_views_fold_into_integer_strides_and_drop_dead_bounds_tests():
     src = t.permute([2, 0, 1]).translate([3, -5, 7]).compile().source
     # out[g0,g1,g2] = T[g1+5, g2-7, g0-3]
     assert "(int)1307133 + (int)1 * g0 + (int)262144 * g1 + (int)512 * g2" in src
-    assert "i0_0 < 512" in src and "i0_2 >= 0" in src and "k1 >= 0" in src
-    assert "i0_0 >= 0" not in src and "i0_2 < 512" not in src  # proven in range by interval analysis
+    assert "i0_0 < 512" in src and "i0_2 >= 0" in src and "i0_1 >= 0" in src
+    assert "i0_0 >= 0" not in src and "i0_2 < 512" not in src and "i0_1 < 512" not in src  # proven in range by interval analysis
+    assert "tiled transpose" in src and "tile[0][ty + 4 * r][tx]" in src  # source-contiguous along g0, output along g2
     # permute / broadcast / split can never leave the source: no tests at all, and the contiguous case vectorises
     src = rnd([512, 512], 8).reshape([1, 512, 512]).broadcast([512, 512, 512]).compile().source
     assert "?" not in src.split("// elementwise")[1].split("st(")[0]
