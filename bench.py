@@ -220,6 +220,68 @@ def side_configs(cuda, hbm_peak: float, tf_peak: float) -> dict:
     return out
 
 
+def sharded_configs(cuda, dist, rank: int, world: int, hbm_peak: float, tf_peak: float) -> dict:
+    """C3 (16384^2, rows/N per GPU, NCCL combine of the partials) and C5 (8192^3, A and C row-sharded, B replicated) at N GPUs.
+    Strong scaling of the fixed BASELINE sizes; every time is the max over ranks of the device time including the collective."""
+    import torch
+
+    from compute.scala_b200 import sharding
+
+    T = cuda.Tensor
+    comm = sharding.Communicator(cuda, dist)
+    out = {}
+
+    def axis_sum(x, axis):
+        parts = x.split(axis)
+        acc = parts[0]
+        for p in parts[1:]:
+            acc = acc + p
+        return acc
+
+    def measure(name, step, alg_bytes=None, flops=None, steps=10):
+        for _ in range(3):
+            step()
+        cuda.synchronize()
+        dist.barrier()
+        cuda.timer_start()
+        for _ in range(steps):
+            step()
+        ms = cuda.timer_stop() / steps
+        t = torch.tensor([ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        rec = {"ms": ms, "n_gpus": world}
+        if flops:
+            rec["tflops"] = flops / ms / 1e9
+            rec["frac_of_3xtf32_peak_all_gpus"] = rec["tflops"] / (tf_peak * world)
+        else:
+            rec["gbs"] = alg_bytes / ms / 1e6
+            rec["frac_of_hbm_all_gpus"] = rec["gbs"] / (hbm_peak * world)
+        out[name] = rec
+
+    rows = sharding.shard_rows(ROWS, world, rank)[1]
+    x = T.random([rows, COLS], seed=5 + 16 * rank).doCache()
+    measure("C3 full sum 16384^2 sharded + allreduce(1 float)", lambda: comm.full_sum(x).release(), alg_bytes=4 * ROWS * COLS)
+    col_sums, row_sums = axis_sum(x, 0), axis_sum(x, 1)  # lazy graphs, built once
+    measure("C3 axis-0 sum 16384^2 sharded + allreduce(16384 floats)", lambda: comm.axis0_sum(col_sums).release(), alg_bytes=4 * ROWS * COLS)
+    measure("C3 axis-1 sum 16384^2 sharded + allgather", lambda: comm.axis1_sum(row_sums).release(), alg_bytes=4 * ROWS * COLS)
+    del x, col_sums, row_sums
+    n5 = 8192
+    m5 = sharding.shard_rows(n5, world, rank)[1]
+    if m5 % 128 == 0:
+        A = T.randomNormal([m5, n5], seed=9 + 16 * rank).doCache()
+        B = T.randomNormal([n5, n5], seed=10).doCache()
+        ab, bb = A.doBuffer(), B.doBuffer()
+        measure("C5 matmul 8192^3 row-sharded (B replicated, C left sharded)", lambda: comm.matmul_rows(ab, bb, m5, n5, n5).release(),
+                flops=2 * n5**3, steps=5)
+        measure("C5 matmul 8192^3 row-sharded + allgather(C)", lambda: comm.matmul_rows(ab, bb, m5, n5, n5, gather=True).release(),
+                flops=2 * n5**3, steps=5)
+        ab.release(), bb.release()
+    cuda.synchronize()
+    comm.close()
+    return out
+
+
 def run_cuda(args, rank: int, local_rank: int, world: int):
     from compute.scala_b200 import cuda
 
@@ -354,6 +416,11 @@ def run_cuda(args, rank: int, local_rank: int, world: int):
         if not args.no_side_configs:
             del a, b, c, expr
             line["configs"] = side_configs(cuda, hbm_peak, tf_peak)
+    if world > 1 and not args.no_side_configs:
+        pk2, _ = peaks()
+        sc = sharded_configs(cuda, dist, rank, world, float(pk2["hbm_gbs"]), float(pk2.get("bf16_tflops", 1590.0)) / 6)
+        if rank == 0:
+            line["configs"] = sc
     if rank == 0:
         print(json.dumps(line), flush=True)
     if dist:

@@ -1,0 +1,110 @@
+"""Leading-axis sharding across the GPUs of one box, one process per GPU.
+
+Row-major tensors shard into contiguous row blocks, so elementwise graphs and views that do not mix the leading axis
+need no exchange at all.  Only two things cross NVLink: partial reductions (a scalar, or one vector of column sums)
+and, on request, the row blocks of a sharded result.  The collectives are the library's own (cc_comm_* over NCCL,
+include/compute_cuda.h); `torch.distributed` — any backend — is used for nothing but handing rank 0's NCCL unique id to
+the other ranks.
+
+Host-side logic only: nothing here computes on the CPU.
+"""
+from __future__ import annotations
+
+from typing import Sequence
+
+
+def shard_rows(rows: int, world: int, rank: int) -> tuple[int, int]:
+    """(first row, row count) of `rank`'s block: the first `rows % world` ranks get one extra row"""
+    if not (0 <= rank < world) or rows < 0:
+        raise ValueError("bad shard request")
+    base, extra = divmod(rows, world)
+    start = rank * base + min(rank, extra)
+    return start, base + (1 if rank < extra else 0)
+
+
+def shard_shape(shape: Sequence[int], world: int, rank: int) -> list[int]:
+    _, n = shard_rows(int(shape[0]), world, rank)
+    return [n] + [int(s) for s in shape[1:]]
+
+
+def shard_offsets(shape: Sequence[int], world: int) -> list[int]:
+    """flat element offset of every rank's block (+ the total), for gathering"""
+    inner = 1
+    for s in shape[1:]:
+        inner *= int(s)
+    return [shard_rows(int(shape[0]), world, r)[0] * inner for r in range(world)] + [int(shape[0]) * inner]
+
+
+def exchange_unique_id(dist, make_id) -> bytes:
+    """rank 0 creates the NCCL unique id (make_id()), everybody receives it through torch.distributed"""
+    box = [make_id() if dist.get_rank() == 0 else None]
+    dist.broadcast_object_list(box, src=0)
+    uid = box[0]
+    if not isinstance(uid, (bytes, bytearray)) or len(uid) != 128:
+        raise RuntimeError("bad NCCL unique id")
+    return bytes(uid)
+
+
+class Communicator:
+    """the process' NCCL communicator inside libcompute_cuda.so"""
+
+    def __init__(self, cuda, dist=None):
+        self.cuda = cuda
+        self.dist = dist
+        self.world = dist.get_world_size() if dist is not None else 1
+        self.rank = dist.get_rank() if dist is not None else 0
+        if self.world > 1:
+            uid = exchange_unique_id(dist, cuda.comm_unique_id)
+            cuda.comm_init(uid, self.world, self.rank)
+
+    def close(self) -> None:
+        if self.world > 1:
+            self.cuda.comm_destroy()
+
+    # ---- the three exchange patterns of the path -------------------------------------------------------------------------
+
+    def full_sum(self, shard_tensor):
+        """Tensor.sum over a row-sharded tensor: local deterministic reduction, then all-reduce of ONE float"""
+        cuda = self.cuda
+        part = shard_tensor.sum().doBuffer()
+        if self.world > 1:
+            cuda.allreduce_sum(part, 1)
+        return part
+
+    def axis0_sum(self, local_column_sums):
+        """column sums when the sharded axis is the reduced one. `local_column_sums` is the lazy tensor
+        `shard.split(0).reduce(_ + _)` built once by the caller: local partial sums, then all-reduce of one row"""
+        cuda = self.cuda
+        part = local_column_sums.doBuffer()
+        if self.world > 1:
+            n = 1
+            for s in local_column_sums.shape:
+                n *= s
+            cuda.allreduce_sum(part, n)
+        return part
+
+    def axis1_sum(self, local_row_sums, gather: bool = True):
+        """row sums (`shard.split(1).reduce(_ + _)`): purely local; all-gather only if every rank wants the whole vector"""
+        cuda = self.cuda
+        part = local_row_sums.doBuffer()
+        if self.world == 1 or not gather:
+            return part
+        n = 1
+        for s in local_row_sums.shape:
+            n *= s
+        whole = cuda.Buffer.alloc(n * self.world)
+        cuda.allgather(part, whole, n)
+        part.release()
+        return whole
+
+    def matmul_rows(self, a_shard, b_full, m_shard: int, n: int, k: int, gather: bool = False):
+        """C[rows of this rank, :] = A[rows of this rank, :] @ B — A and C row-sharded, B replicated; no exchange unless gathered"""
+        cuda = self.cuda
+        c = cuda.Buffer.alloc(m_shard * n)
+        cuda.matmul_3xtf32(a_shard, b_full, c, m_shard, n, k)
+        if self.world == 1 or not gather:
+            return c
+        whole = cuda.Buffer.alloc(m_shard * n * self.world)
+        cuda.allgather(c, whole, m_shard * n)
+        c.release()
+        return whole
