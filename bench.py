@@ -261,10 +261,16 @@ def sharded_configs(cuda, dist, rank: int, world: int, hbm_peak: float, tf_peak:
 
     rows = sharding.shard_rows(ROWS, world, rank)[1]
     x = T.random([rows, COLS], seed=5 + 16 * rank).doCache()
-    measure("C3 full sum 16384^2 sharded + allreduce(1 float)", lambda: comm.full_sum(x).release(), alg_bytes=4 * ROWS * COLS)
     col_sums, row_sums = axis_sum(x, 0), axis_sum(x, 1)  # lazy graphs, built once
-    measure("C3 axis-0 sum 16384^2 sharded + allreduce(16384 floats)", lambda: comm.axis0_sum(col_sums).release(), alg_bytes=4 * ROWS * COLS)
-    measure("C3 axis-1 sum 16384^2 sharded + allgather", lambda: comm.axis1_sum(row_sums).release(), alg_bytes=4 * ROWS * COLS)
+    for route, tag in ((True, "fused / one-shot over NVLink peer memory"), (False, "NCCL")):
+        if route and not comm.peer:
+            continue
+        comm.route_peer(route)
+        measure(f"C3 full sum 16384^2 sharded + allreduce(1 float) [{tag}]", lambda: comm.full_sum(x).release(), alg_bytes=4 * ROWS * COLS, steps=50)
+        measure(f"C3 axis-0 sum 16384^2 sharded + allreduce(16384 floats) [{tag}]", lambda: comm.axis0_sum(col_sums).release(),
+                alg_bytes=4 * ROWS * COLS, steps=50)
+    comm.route_peer(comm.cuda.comm_peer_enabled() or False) if False else None
+    measure("C3 axis-1 sum 16384^2 sharded + allgather [NCCL]", lambda: comm.axis1_sum(row_sums).release(), alg_bytes=4 * ROWS * COLS, steps=50)
     del x, col_sums, row_sums
     n5 = 8192
     m5 = sharding.shard_rows(n5, world, rank)[1]

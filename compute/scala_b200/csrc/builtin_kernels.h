@@ -18,6 +18,28 @@ void launch_reduce_sum(const float* in, uint64_t n, float* out, float* scratch, 
 void launch_random(float* out, uint64_t n, int32_t seed, cudaStream_t stream);
 void launch_random_normal(float* out, uint64_t n, int32_t seed, cudaStream_t stream);
 
+// ---- one-shot all-reduce over NVLink peer memory (one process per GPU, CUDA IPC mailboxes) ---------------------------------
+// Every rank owns a mailbox in its own HBM; peers store their contribution straight into it over NVLink / NVSwitch and
+// raise a per-block epoch flag; each rank then sums the contributions in rank order (deterministic, identical everywhere).
+constexpr int kPeerMaxRanks = 8;
+constexpr int kPeerCapFloats = 65536;  // largest vector the mailbox carries (the 16384-float column sums of C3 use a quarter)
+constexpr int kPeerChunk = 1024;       // floats per block
+constexpr int kPeerMaxBlocks = kPeerCapFloats / kPeerChunk;
+struct PeerMailboxes {
+  float* data[kPeerMaxRanks];      // data[r]: rank r's mailbox payload [2][world][kPeerCapFloats]
+  unsigned* flags[kPeerMaxRanks];  // flags[r]: rank r's mailbox flags  [2][world][kPeerMaxBlocks]
+  int world;
+  int rank;
+};
+size_t peer_mailbox_bytes(int world);
+size_t peer_mailbox_flag_offset(int world);  // byte offset of the flags inside one mailbox allocation
+// in-place all-reduce(sum) of v[0..n), n <= kPeerCapFloats; `epoch` must increase by one per collective call on every rank
+void launch_peer_allreduce(float* v, uint64_t n, const PeerMailboxes& mb, unsigned epoch, cudaStream_t stream);
+// Tensor.sum over a sharded tensor as ONE kernel: local two-stage reduction whose last block pushes the partial into every
+// peer's mailbox and completes the all-reduce itself
+void launch_reduce_sum_allreduce(const float* in, uint64_t n, float* out, float* scratch, unsigned* counter, int sm_count,
+                                 const PeerMailboxes& mb, unsigned epoch, cudaStream_t stream);
+
 bool gemm_available();
 
 // ---- contraction ----------------------------------------------------------------------------------------------------

@@ -47,7 +47,12 @@ namespace cc {
   X(cuLaunchHostFunc)               \
   X(cuGetErrorString)               \
   X(cuGetErrorName)                 \
-  X(cuTensorMapEncodeTiled)
+  X(cuTensorMapEncodeTiled)         \
+  X(cuIpcGetMemHandle)              \
+  X(cuIpcOpenMemHandle)             \
+  X(cuIpcCloseMemHandle)            \
+  X(cuMemcpyHtoD)                   \
+  X(cuMemcpyDtoH)
 
 struct Driver {
 #define CC_DECL(name) decltype(&::name) name = nullptr;

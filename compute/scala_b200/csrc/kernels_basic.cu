@@ -42,8 +42,31 @@ __device__ __forceinline__ float block_sum(float v, float* smem /* >= 32 floats 
   return v;  // valid in warp 0
 }
 
+// ---- peer mailbox helpers ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void wait_flag(const unsigned* p, unsigned epoch) {
+  unsigned spins = 0;
+  while (ld_acquire_sys(p) != epoch)
+    if (++spins > (1u << 27)) __trap();  // a peer that never shows up must abort this launch, not hang the GPU
+}
+__device__ __forceinline__ size_t mb_data_index(int parity, int world, int src_rank, size_t i) {
+  return ((size_t)parity * world + src_rank) * kPeerCapFloats + i;
+}
+__device__ __forceinline__ size_t mb_flag_index(int parity, int world, int src_rank, int block) {
+  return ((size_t)parity * world + src_rank) * kPeerMaxBlocks + block;
+}
+
+template <bool kFused>
 __global__ void __launch_bounds__(kReduceThreads) reduce_sum_kernel(const float* __restrict__ in, uint64_t n, float* __restrict__ out,
-                                                                   float* __restrict__ partials, unsigned* __restrict__ counter) {
+                                                                   float* __restrict__ partials, unsigned* __restrict__ counter, PeerMailboxes mb,
+                                                                   unsigned epoch) {
   __shared__ float smem[32];
   __shared__ bool is_last;
   const uint64_t nvec = n >> 2;
@@ -84,9 +107,69 @@ __global__ void __launch_bounds__(kReduceThreads) reduce_sum_kernel(const float*
   float p = 0.f;
   for (unsigned i = threadIdx.x; i < gridDim.x; i += kReduceThreads) p += __ldcg(partials + i);
   p = block_sum(p, smem);
+  if (!kFused) {
+    if (threadIdx.x == 0) {
+      out[0] = p;
+      *counter = 0u;  // ready for the next launch on this stream
+    }
+    return;
+  }
+  // fused all-reduce: push this GPU's total into slot [rank] of every peer's mailbox over NVLink, raise the epoch flag, wait
+  // for every peer's flag in our own mailbox, then add the totals in rank order (same order, same bits on every rank)
+  const int parity = (int)(epoch & 1u);
+  if (threadIdx.x == 0) smem[0] = p;
+  __syncthreads();
+  if ((int)threadIdx.x < mb.world) {
+    const int peer = threadIdx.x;
+    mb.data[peer][mb_data_index(parity, mb.world, mb.rank, 0)] = smem[0];
+    __threadfence_system();
+    st_release_sys(mb.flags[peer] + mb_flag_index(parity, mb.world, mb.rank, 0), epoch);
+    wait_flag(mb.flags[mb.rank] + mb_flag_index(parity, mb.world, peer, 0), epoch);
+  }
+  __syncthreads();
   if (threadIdx.x == 0) {
-    out[0] = p;
-    *counter = 0u;  // ready for the next launch on this stream
+    float total = 0.f;
+    for (int r = 0; r < mb.world; ++r) total += __ldcv(mb.data[mb.rank] + mb_data_index(parity, mb.world, r, 0));
+    out[0] = total;
+    *counter = 0u;
+  }
+}
+
+// one-shot in-place all-reduce of a vector: block b owns floats [b*1024, (b+1)*1024)
+__global__ void __launch_bounds__(256) peer_allreduce_kernel(float* __restrict__ v, uint64_t n, PeerMailboxes mb, unsigned epoch) {
+  const int parity = (int)(epoch & 1u);
+  const int b = blockIdx.x;
+  const size_t i = (size_t)b * kPeerChunk + (size_t)threadIdx.x * 4;
+  float4 mine = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (i + 3 < n) {
+    mine = *reinterpret_cast<const float4*>(v + i);
+  } else {
+    float t[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int j = 0; j < 4; ++j)
+      if (i + j < n) t[j] = v[i + j];
+    mine = make_float4(t[0], t[1], t[2], t[3]);
+  }
+  for (int peer = 0; peer < mb.world; ++peer)
+    *reinterpret_cast<float4*>(mb.data[peer] + mb_data_index(parity, mb.world, mb.rank, i)) = mine;  // NVLink store (local for peer == rank)
+  __threadfence_system();
+  __syncthreads();
+  if ((int)threadIdx.x < mb.world) {
+    const int peer = threadIdx.x;
+    st_release_sys(mb.flags[peer] + mb_flag_index(parity, mb.world, mb.rank, b), epoch);
+    wait_flag(mb.flags[mb.rank] + mb_flag_index(parity, mb.world, peer, b), epoch);
+  }
+  __syncthreads();
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int r = 0; r < mb.world; ++r) {
+    const float4 x = __ldcv(reinterpret_cast<const float4*>(mb.data[mb.rank] + mb_data_index(parity, mb.world, r, i)));
+    acc.x += x.x; acc.y += x.y; acc.z += x.z; acc.w += x.w;
+  }
+  if (i + 3 < n) {
+    *reinterpret_cast<float4*>(v + i) = acc;
+  } else {
+    const float t[4] = {acc.x, acc.y, acc.z, acc.w};
+    for (int j = 0; j < 4; ++j)
+      if (i + j < n) v[i + j] = t[j];
   }
 }
 
@@ -161,8 +244,30 @@ void launch_reduce_sum(const float* in, uint64_t n, float* out, float* scratch, 
   uint64_t cap = (uint64_t)sm_count * 4;
   if (cap > (uint64_t)kReduceMaxBlocks) cap = kReduceMaxBlocks;
   unsigned grid = (unsigned)(want < 1 ? 1 : (want > cap ? cap : want));
-  reduce_sum_kernel<<<grid, kReduceThreads, 0, stream>>>(in, n, out, scratch, counter);
+  reduce_sum_kernel<false><<<grid, kReduceThreads, 0, stream>>>(in, n, out, scratch, counter, PeerMailboxes{}, 0u);
   check_launch("reduce_sum");
+}
+
+size_t peer_mailbox_flag_offset(int world) { return (size_t)2 * world * kPeerCapFloats * sizeof(float); }
+size_t peer_mailbox_bytes(int world) { return peer_mailbox_flag_offset(world) + (size_t)2 * world * kPeerMaxBlocks * sizeof(unsigned); }
+
+void launch_peer_allreduce(float* v, uint64_t n, const PeerMailboxes& mb, unsigned epoch, cudaStream_t stream) {
+  CC_REQUIRE(n <= (uint64_t)kPeerCapFloats, CC_ERR_UNSUPPORTED, "peer all-reduce carries at most %d floats", kPeerCapFloats);
+  if (n == 0) return;
+  const unsigned blocks = (unsigned)((n + kPeerChunk - 1) / kPeerChunk);
+  peer_allreduce_kernel<<<blocks, 256, 0, stream>>>(v, n, mb, epoch);
+  check_launch("peer_allreduce");
+}
+
+void launch_reduce_sum_allreduce(const float* in, uint64_t n, float* out, float* scratch, unsigned* counter, int sm_count,
+                                 const PeerMailboxes& mb, unsigned epoch, cudaStream_t stream) {
+  const uint64_t nvec = n >> 2;
+  uint64_t want = (nvec + (uint64_t)kReduceThreads * 4 - 1) / ((uint64_t)kReduceThreads * 4);
+  uint64_t cap = (uint64_t)sm_count * 4;
+  if (cap > (uint64_t)kReduceMaxBlocks) cap = kReduceMaxBlocks;
+  unsigned grid = (unsigned)(want < 1 ? 1 : (want > cap ? cap : want));
+  reduce_sum_kernel<true><<<grid, kReduceThreads, 0, stream>>>(in, n, out, scratch, counter, mb, epoch);
+  check_launch("reduce_sum_allreduce");
 }
 
 void launch_random(float* out, uint64_t n, int32_t seed, cudaStream_t stream) {

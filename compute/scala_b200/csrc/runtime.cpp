@@ -77,6 +77,13 @@ struct Nccl {
   decltype(&ncclGetErrorString) GetErrorString = nullptr;
   ncclComm_t comm = nullptr;
   int n_ranks = 0, rank = 0;
+  // NVLink peer mailboxes (CUDA IPC)
+  bool peer_enabled = false;
+  bool peer_mapped = false;
+  CUdeviceptr mailbox = 0;
+  CUdeviceptr peer_base[kPeerMaxRanks] = {0};
+  PeerMailboxes mb{};
+  unsigned epoch = 0;
   void load() {
     if (lib) return;
     lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
@@ -376,6 +383,19 @@ Buffer* reduce_scratch() {
 
 using namespace cc;
 
+namespace {
+void close_peers(Nccl& n) {
+  if (!n.peer_mapped) return;
+  driver().cuCtxSynchronize();
+  for (int r = 0; r < n.n_ranks; ++r)
+    if (r != n.rank && n.peer_base[r]) driver().cuIpcCloseMemHandle(n.peer_base[r]);
+  if (n.mailbox) driver().cuMemFree(n.mailbox);
+  n.mailbox = 0;
+  n.peer_enabled = false;
+  n.peer_mapped = false;
+}
+}  // namespace
+
 extern "C" {
 
 const char* cc_last_error(void) { return last_error_cstr(); }
@@ -458,6 +478,7 @@ int cc_shutdown(void) {
     if (!r.initialized) return;
     CC_CU(cuCtxSetCurrent(r.ctx));
     driver().cuCtxSynchronize();
+    close_peers(r.nccl);
     if (r.nccl.comm) {
       r.nccl.CommDestroy(r.nccl.comm);
       r.nccl.comm = nullptr;
@@ -1038,10 +1059,120 @@ int cc_comm_init(const void* id, int n_ranks, int rank) {
     n.rank = rank;
   });
 }
+int cc_comm_enable_peer(void) {
+  return guarded([&] {
+    Lock lock;
+    require_init();
+    Nccl& n = rt().nccl;
+    CC_REQUIRE(n.comm, CC_ERR_ILLEGAL_ARGUMENT, "cc_comm_enable_peer needs an initialised communicator");
+    if (n.peer_mapped) {
+      n.peer_enabled = true;
+      return;
+    }
+    CC_REQUIRE(n.n_ranks <= kPeerMaxRanks, CC_ERR_UNSUPPORTED, "peer mailboxes support at most %d ranks", kPeerMaxRanks);
+    const size_t bytes = peer_mailbox_bytes(n.n_ranks);
+    CC_CU(cuMemAlloc(&n.mailbox, bytes));
+    CUstream s0 = rt().streams[0];
+    CC_CU(cuMemsetD32Async(n.mailbox, 0, bytes / 4, s0));
+    // exchange the IPC handles through the communicator itself (64 bytes per rank)
+    CUipcMemHandle mine;
+    CC_CU(cuIpcGetMemHandle(&mine, n.mailbox));
+    static_assert(sizeof(CUipcMemHandle) == 64, "CUipcMemHandle is 64 bytes");
+    CUdeviceptr send = 0, recv = 0;
+    CC_CU(cuMemAlloc(&send, 64));
+    CC_CU(cuMemAlloc(&recv, 64 * (size_t)n.n_ranks));
+    CC_CU(cuMemcpyHtoD(send, &mine, 64));
+    n.check(n.AllGather((const void*)send, (void*)recv, 64, ncclChar, n.comm, (cudaStream_t)s0), "ncclAllGather(ipc handles)");
+    CC_CU(cuStreamSynchronize(s0));
+    std::vector<CUipcMemHandle> all((size_t)n.n_ranks);
+    CC_CU(cuMemcpyDtoH(all.data(), recv, 64 * (size_t)n.n_ranks));
+    driver().cuMemFree(send);
+    driver().cuMemFree(recv);
+    const size_t flag_off = peer_mailbox_flag_offset(n.n_ranks);
+    n.mb = PeerMailboxes{};
+    n.mb.world = n.n_ranks;
+    n.mb.rank = n.rank;
+    for (int r = 0; r < n.n_ranks; ++r) {
+      CUdeviceptr base = n.mailbox;
+      if (r != n.rank) {
+        CUresult res = driver().cuIpcOpenMemHandle(&base, all[(size_t)r], CU_IPC_MEM_LAZY_ENABLE_PEER_ACCESS);
+        if (res != CUDA_SUCCESS) {
+          for (int q = 0; q < r; ++q)
+            if (q != n.rank && n.peer_base[q]) driver().cuIpcCloseMemHandle(n.peer_base[q]);
+          driver().cuMemFree(n.mailbox);
+          n.mailbox = 0;
+          fail(CC_ERR_UNSUPPORTED, strprintf("cuIpcOpenMemHandle(rank %d) failed (%d): no peer access between these GPUs", r, (int)res));
+        }
+      }
+      n.peer_base[r] = base;
+      n.mb.data[r] = (float*)base;
+      n.mb.flags[r] = (unsigned*)(base + flag_off);
+    }
+    // nobody may push into a mailbox before its owner has zeroed it: one barrier through the communicator
+    CUdeviceptr token = 0;
+    CC_CU(cuMemAlloc(&token, 256));
+    CC_CU(cuMemsetD32Async(token, 0, 64, s0));
+    n.check(n.AllReduce((const void*)token, (void*)token, 1, ncclFloat, ncclSum, n.comm, (cudaStream_t)s0), "ncclAllReduce(barrier)");
+    CC_CU(cuStreamSynchronize(s0));
+    driver().cuMemFree(token);
+    rt().seq[0]++;
+    n.epoch = 0;
+    n.peer_enabled = true;
+    n.peer_mapped = true;
+  });
+}
+
+int cc_comm_route_peer(int on) {
+  return guarded([&] {
+    Lock lock;
+    Nccl& n = rt().nccl;
+    CC_REQUIRE(!on || n.peer_mapped, CC_ERR_ILLEGAL_ARGUMENT, "peer mailboxes are not mapped: call cc_comm_enable_peer first");
+    n.peer_enabled = on != 0;
+  });
+}
+
+int cc_comm_peer_enabled(int* out) {
+  return guarded([&] {
+    Lock lock;
+    CC_REQUIRE(out, CC_ERR_ILLEGAL_ARGUMENT, "null output");
+    *out = rt().nccl.peer_enabled ? 1 : 0;
+  });
+}
+
+int cc_reduce_sum_allreduce(cc_buffer in, uint64_t n_floats, cc_buffer out, const cc_event* waits, int n_waits, cc_event* out_event) {
+  return guarded([&] {
+    Lock lock;
+    require_init();
+    Runtime& r = rt();
+    Nccl& n = r.nccl;
+    Buffer* ib = as_buffer(in);
+    Buffer* ob = as_buffer(out);
+    CC_REQUIRE(n_floats <= ib->n_floats && ob->n_floats >= 1 && ib != ob, CC_ERR_ILLEGAL_ARGUMENT, "bad reduce_sum arguments");
+    Buffer* sc = reduce_scratch();
+    Op op{0, {ib}, {ob, sc}};
+    op_begin(op, waits, n_waits);
+    if (n.comm && n.peer_enabled) {
+      // ONE kernel: local reduction + all-reduce of its result over NVLink peer memory
+      launch_reduce_sum_allreduce((const float*)ib->ptr, n_floats, (float*)ob->ptr, (float*)sc->ptr, (unsigned*)r.reduce_counter, r.info.sm_count,
+                                  n.mb, ++n.epoch, (cudaStream_t)op.cu());
+      r.stats.device_kernels++;
+    } else {
+      launch_reduce_sum((const float*)ib->ptr, n_floats, (float*)ob->ptr, (float*)sc->ptr, (unsigned*)r.reduce_counter, r.info.sm_count,
+                        (cudaStream_t)op.cu());
+      r.stats.device_kernels++;
+      if (n.comm)
+        n.check(n.AllReduce((const void*)ob->ptr, (void*)ob->ptr, 1, ncclFloat, ncclSum, n.comm, (cudaStream_t)op.cu()), "ncclAllReduce");
+    }
+    r.stats.launches++;
+    op_end(op, out_event);
+  });
+}
+
 int cc_comm_destroy(void) {
   return guarded([&] {
     Lock lock;
     Nccl& n = rt().nccl;
+    close_peers(n);
     if (n.comm) {
       driver().cuCtxSynchronize();
       n.check(n.CommDestroy(n.comm), "ncclCommDestroy");
@@ -1067,7 +1198,12 @@ int cc_allreduce_sum(cc_buffer buf, uint64_t n_floats, const cc_event* waits, in
     CC_REQUIRE(n_floats <= b->n_floats, CC_ERR_ILLEGAL_ARGUMENT, "allreduce: buffer too small");
     Op op{0, {}, {b}};
     op_begin(op, waits, n_waits);
-    if (n.comm) n.check(n.AllReduce((const void*)b->ptr, (void*)b->ptr, n_floats, ncclFloat, ncclSum, n.comm, (cudaStream_t)op.cu()), "ncclAllReduce");
+    if (n.comm && n.peer_enabled && n_floats <= (uint64_t)kPeerCapFloats) {
+      launch_peer_allreduce((float*)b->ptr, n_floats, n.mb, ++n.epoch, (cudaStream_t)op.cu());
+      rt().stats.device_kernels++;
+    } else if (n.comm) {
+      n.check(n.AllReduce((const void*)b->ptr, (void*)b->ptr, n_floats, ncclFloat, ncclSum, n.comm, (cudaStream_t)op.cu()), "ncclAllReduce");
+    }
     op_end(op, out_event);
   });
 }

@@ -88,6 +88,9 @@ def _L():
         L.cc_comm_init.argtypes = [C.c_void_p, C.c_int, C.c_int]
         L.cc_comm_info.argtypes = [C.POINTER(C.c_int), C.POINTER(C.c_int)]
         L.cc_allreduce_sum.argtypes = [h, u64, hp, C.c_int, hp]
+        L.cc_reduce_sum_allreduce.argtypes = [h, u64, h, hp, C.c_int, hp]
+        L.cc_comm_peer_enabled.argtypes = [C.POINTER(C.c_int)]
+        L.cc_comm_route_peer.argtypes = [C.c_int]
         L.cc_allgather.argtypes = [h, h, u64, hp, C.c_int, hp]
         L.cc_broadcast.argtypes = [h, u64, C.c_int, hp, C.c_int, hp]
         _configured = True
@@ -281,6 +284,25 @@ def comm_unique_id() -> bytes:
 
 def comm_init(unique_id: bytes, n_ranks: int, rank: int) -> None:
     check(_L().cc_comm_init(C.create_string_buffer(unique_id, 128), int(n_ranks), int(rank)))
+
+
+def comm_enable_peer() -> None:
+    """map the NVLink peer mailboxes; afterwards small all-reduces and the sharded Tensor.sum bypass NCCL"""
+    check(_L().cc_comm_enable_peer())
+
+
+def comm_route_peer(on: bool) -> None:
+    check(_L().cc_comm_route_peer(1 if on else 0))
+
+
+def comm_peer_enabled() -> bool:
+    v = C.c_int()
+    check(_L().cc_comm_peer_enabled(C.byref(v)))
+    return bool(v.value)
+
+
+def reduce_sum_allreduce(src: Buffer, n_floats: int, dst: Buffer) -> None:
+    check(_L().cc_reduce_sum_allreduce(src.handle, int(n_floats), dst.handle, None, 0, None))
 
 
 def comm_destroy() -> None:

@@ -48,14 +48,25 @@ def exchange_unique_id(dist, make_id) -> bytes:
 class Communicator:
     """the process' NCCL communicator inside libcompute_cuda.so"""
 
-    def __init__(self, cuda, dist=None):
+    def __init__(self, cuda, dist=None, peer: bool = True):
         self.cuda = cuda
         self.dist = dist
         self.world = dist.get_world_size() if dist is not None else 1
         self.rank = dist.get_rank() if dist is not None else 0
+        self.peer = False
         if self.world > 1:
             uid = exchange_unique_id(dist, cuda.comm_unique_id)
             cuda.comm_init(uid, self.world, self.rank)
+            if peer:
+                # NVLink peer mailboxes: our own one-shot / fused collectives for the small combines (NCCL stays for the rest)
+                cuda.comm_enable_peer()
+                self.peer = cuda.comm_peer_enabled()
+
+    def route_peer(self, on: bool) -> None:
+        """A/B switch: small combines over the NVLink peer mailboxes (True) or over NCCL (False)"""
+        if self.world > 1:
+            self.cuda.comm_route_peer(on)
+            self.peer = on
 
     def close(self) -> None:
         if self.world > 1:
@@ -66,6 +77,16 @@ class Communicator:
     def full_sum(self, shard_tensor):
         """Tensor.sum over a row-sharded tensor: local deterministic reduction, then all-reduce of ONE float"""
         cuda = self.cuda
+        if self.world > 1 and self.peer:
+            # fused: the reduction kernel's last block completes the all-reduce over peer memory itself (one launch)
+            src = shard_tensor.doBuffer()
+            n = 1
+            for s in shard_tensor.shape:
+                n *= s
+            out = cuda.Buffer.alloc(1)
+            cuda.reduce_sum_allreduce(src, n, out)
+            src.release()
+            return out
         part = shard_tensor.sum().doBuffer()
         if self.world > 1:
             cuda.allreduce_sum(part, 1)

@@ -195,6 +195,18 @@ int cc_comm_unique_id(void* out_128_bytes);                       /* rank 0; shi
 int cc_comm_init(const void* id_128_bytes, int n_ranks, int rank); /* ncclCommInitRank on this process' device */
 int cc_comm_destroy(void);
 int cc_comm_info(int* out_n_ranks, int* out_rank);
+/* Our own collective over NVLink peer memory (B200 HGX: every peer at full bandwidth through NVSwitch): maps one small
+ * CUDA-IPC mailbox per rank into every other rank (handles exchanged once through the communicator). Afterwards
+ * cc_allreduce_sum routes vectors of <= 65536 floats through a one-shot kernel (peers store straight into each other's
+ * HBM, flags, rank-ordered sum: deterministic, one launch, no NCCL call) and cc_reduce_sum_allreduce fuses Tensor.sum's
+ * reduction with the all-reduce of its result in ONE kernel. Returns CC_ERR_UNSUPPORTED if peer access is impossible. */
+int cc_comm_enable_peer(void);
+int cc_comm_peer_enabled(int* out);
+/* route small all-reduces through the peer mailboxes (1, default after cc_comm_enable_peer) or through NCCL (0) — for A/B timing */
+int cc_comm_route_peer(int on);
+/* out[0] = sum over all ranks of sum(in[0..n)) — collective: every rank of the communicator must call it in the same order */
+int cc_reduce_sum_allreduce(cc_buffer in, uint64_t n_floats, cc_buffer out, const cc_event* waits, int n_waits,
+                            cc_event* out_event);
 int cc_allreduce_sum(cc_buffer buf, uint64_t n_floats, const cc_event* waits, int n_waits, cc_event* out_event);
 /* recv[rank*n .. (rank+1)*n) = send[0..n) of every rank */
 int cc_allgather(cc_buffer send, cc_buffer recv, uint64_t n_floats_per_rank, const cc_event* waits, int n_waits,

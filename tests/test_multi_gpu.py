@@ -43,10 +43,28 @@ def _worker(rank, world, port):
         full = (np.floor(ref.random_buffer(rows * cols, 5) * np.float32(9.0)) - np.float32(4.0)).astype(np.float32).reshape(rows, cols)
         start, n = sharding.shard_rows(rows, world, rank)
         shard = T(full[start : start + n])
+        assert comm.peer, "NVLink peer mailboxes should map on an HGX box"
+        col_sums = _axis_sum(shard, 0)
+        for route in (True, False, True, True):  # fused / one-shot kernels over peer memory, NCCL, and back (epoch parity)
+            comm.route_peer(route)
+            s = comm.full_sum(shard)
+            assert s.to_host(1)[0] == np.float32(full.astype(np.int64).sum())
+            c0 = comm.axis0_sum(col_sums)
+            assert np.array_equal(c0.to_host(cols), full.astype(np.int64).sum(axis=0).astype(np.float32))
+            s.release(), c0.release()
+        # ragged one-shot all-reduces, back to back (mailbox double buffering)
+        for length in (1, 3, 1000, 1025, 65536):
+            v = np.arange(length, dtype=np.float32) % 17 + rank
+            buf = cuda.Buffer.from_host(v)
+            for rep in range(3):
+                cuda.allreduce_sum(buf, length)
+            got = buf.to_host(length)
+            base = np.arange(length, dtype=np.float32) % 17
+            expect = ((base * world + sum(range(world))) * world) * world
+            assert np.array_equal(got, expect), (length, got[:4], expect[:4])
+            buf.release()
         s = comm.full_sum(shard)
-        assert s.to_host(1)[0] == np.float32(full.astype(np.int64).sum())
-        c0 = comm.axis0_sum(_axis_sum(shard, 0))
-        assert np.array_equal(c0.to_host(cols), full.astype(np.int64).sum(axis=0).astype(np.float32))
+        c0 = comm.axis0_sum(col_sums)
         c1 = comm.axis1_sum(_axis_sum(shard, 1), gather=True)
         assert np.array_equal(c1.to_host(rows), full.astype(np.int64).sum(axis=1).astype(np.float32))
         m, k, nn = 512, 256, 512
