@@ -17,6 +17,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <unordered_map>
@@ -571,13 +572,19 @@ void emit_elementwise(Plan& plan, const Program& p, int n_args, const DeviceProp
   const bool flat = program_is_flat(p);
   const char* IDX = pick_idx_type(p, total * std::max(1, nres));
   const int nloads = (int)p.loads.size();
-  int U = 4;
-  if (nloads > 4) U = 2;
+  // Measured on B200 (scripts/gpu_sweep_c2.sh, profiles/r01_sweep_c2.log): one CTA per chunk (no persistence), 2 vectors in
+  // flight per thread and a register cap that keeps 8 CTAs/SM resident beats a persistent grid by ~15 % (7.0 vs 6.1 TB/s on C2).
+  int U = 2;
   if (nloads > 8) U = 1;
-  while (U > 1 && NV < (int64_t)256 * U * dev.sm_count * 2) U /= 2;
+  while (U > 1 && NV < (int64_t)256 * U * dev.sm_count * 8) U /= 2;  // small tensors: more CTAs beats more vectors per thread
+  int64_t grid_mult = (int64_t)1 << 40;
+  int min_blocks = nloads * V * U <= 24 ? 8 : (nloads * V * U <= 40 ? 6 : 0);
+  if (const char* e = getenv("CC_TUNE_U")) U = std::max(1, atoi(e));          // tuning knobs (scripts/gpu_sweep_c2.sh)
+  if (const char* e = getenv("CC_TUNE_GRID_MULT")) grid_mult = std::max(1, atoi(e));
+  if (const char* e = getenv("CC_TUNE_MIN_BLOCKS")) min_blocks = std::max(0, atoi(e));
   const int64_t chunk = (int64_t)256 * U;
   const int64_t nchunks = (NV + chunk - 1) / chunk;
-  int64_t grid = std::min<int64_t>(nchunks, (int64_t)dev.sm_count * 8);
+  int64_t grid = std::min<int64_t>(nchunks, std::min<int64_t>((int64_t)dev.sm_count * grid_mult, 0x7fffffff));
   if (grid < 1) grid = 1;
 
   Emit e;
@@ -626,7 +633,10 @@ void emit_elementwise(Plan& plan, const Program& p, int n_args, const DeviceProp
     for (int r = 0; r < nres; ++r) e("  out[v * %d + %d] = o[%d][0];\n", nres, r, r);
   }
   e("}\n");
-  e("extern \"C\" __global__ void __launch_bounds__(256) jit_kernel(%s) {\n", param_list(n_args, true).c_str());
+  if (min_blocks > 0)
+    e("extern \"C\" __global__ void __launch_bounds__(256, %d) jit_kernel(%s) {\n", min_blocks, param_list(n_args, true).c_str());
+  else
+    e("extern \"C\" __global__ void __launch_bounds__(256) jit_kernel(%s) {\n", param_list(n_args, true).c_str());
   e("  const %s NV = %lld;\n  const %s nchunks = %lld;\n", IDX, (long long)NV, IDX, (long long)nchunks);
   e("  for (%s c = blockIdx.x; c < nchunks; c += gridDim.x) {\n", IDX);
   e("    const %s v0 = c * %lld + threadIdx.x;\n", IDX, (long long)chunk);
@@ -694,7 +704,9 @@ void emit_tiled_transpose(Plan& plan, const Program& p, int n_args, const Device
   for (int x = 0; x < nd; ++x)
     if (x != d && x != L) outer *= p.dims[x];
   const int64_t ntiles = tilesL * tilesD * outer;
-  int64_t grid = std::min<int64_t>(ntiles, (int64_t)dev.sm_count * (TS == 64 ? 6 : 8));
+  int64_t tgm = (int64_t)1 << 30;
+  if (const char* ev = getenv("CC_TUNE_T_GRID_MULT")) tgm = std::max(1, atoi(ev));
+  int64_t grid = std::min<int64_t>(ntiles, std::min<int64_t>((int64_t)dev.sm_count * tgm, 0x7fffffff));
   if (grid < 1) grid = 1;
   std::vector<int64_t> ostride(nd, 1);
   for (int x = nd - 2; x >= 0; --x) ostride[x] = ostride[x + 1] * p.dims[x + 1];
@@ -820,11 +832,11 @@ void emit_reduce(Plan& plan, const Program& p, int n_args, const DeviceProps& de
       e("  const long long v = (long long)blockIdx.x * 256 + threadIdx.x;\n  if (v >= %lld) return;\n", (long long)NV);
       e("  float acc[%d];\n", V);
       if (V == 4) {
-        e("  cc_ldg4(part + v * 4, acc);\n  for (int s = 1; s < %lld; ++s) {\n    float x[4];\n    cc_ldg4(part + (long long)s * %lld + v * 4, x);\n", (long long)S,
+        e("  cc_ldg4(part + v * 4, acc);\n  #pragma unroll 8\n  for (int s = 1; s < %lld; ++s) {\n    float x[4];\n    cc_ldg4(part + (long long)s * %lld + v * 4, x);\n", (long long)S,
           (long long)NOUT);
         e("    #pragma unroll\n    for (int l = 0; l < 4; ++l) acc[l] = acc[l] + x[l];\n  }\n  cc_stg4(out + v * 4, acc);\n}\n");
       } else {
-        e("  acc[0] = part[v];\n  for (int s = 1; s < %lld; ++s) acc[0] = acc[0] + part[(long long)s * %lld + v];\n  out[v] = acc[0];\n}\n", (long long)S,
+        e("  acc[0] = part[v];\n  #pragma unroll 8\n  for (int s = 1; s < %lld; ++s) acc[0] = acc[0] + part[(long long)s * %lld + v];\n  out[v] = acc[0];\n}\n", (long long)S,
           (long long)NOUT);
       }
       LaunchSpec l2;
