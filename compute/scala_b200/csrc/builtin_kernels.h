@@ -44,17 +44,20 @@ bool gemm_available();
 
 // ---- contraction ----------------------------------------------------------------------------------------------------
 struct GemmWorkspace {
-  float* a_hi;   // [M,K]  tf32_trunc(A)
-  float* a_lo;   // [M,K]  tf32(A - a_hi)
-  float* bt_hi;  // [N,K]  tf32_trunc(B)^T
-  float* bt_lo;  // [N,K]  tf32(B - b_hi)^T
+  float* a_hi;   // [M,Kp]  tf32_trunc(A), columns >= K zero
+  float* a_lo;   // [M,Kp]  tf32(A - a_hi)
+  float* bt_hi;  // [N,Kp]  tf32_trunc(B)^T
+  float* bt_lo;  // [N,Kp]  tf32(B - b_hi)^T
 };
-constexpr int kGemmTileM = 128, kGemmTileN = 256, kGemmTileK = 32;
+// K rounded up to the pipeline's K step (32 floats): the row length of the four workspace panels
+int64_t gemm_padded_k(int64_t k);
+// output tile width (256 / 128 / 64) the launcher picks for an M x N problem on `sm_count` SMs
+int gemm_pick_bn(int64_t m, int64_t n, int sm_count);
 typedef CUresult (*TensorMapEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                       const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                       CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-// C[M,N] = A[M,K] * B[K,N], fp32 row-major, 3xTF32 on tcgen05. M % 128 == 0, N % 256 == 0, K % 32 == 0.
-// Returns the number of device kernels launched; throws cc::Error on failure.
+// C[M,N] = A[M,K] * B[K,N], fp32 row-major, 3xTF32 on tcgen05, any M, N, K >= 1 (ragged edges: TMA zero fill in, predicated
+// stores out; K is zero-padded inside the workspace). Returns the number of device kernels launched; throws cc::Error.
 int launch_gemm_3xtf32(const float* a, const float* b, float* c, int64_t m, int64_t n, int64_t k,
                        const GemmWorkspace& ws, int sm_count, TensorMapEncodeFn encode, cudaStream_t stream);
 

@@ -139,11 +139,13 @@ void analyze_load(Load& L, const std::vector<int64_t>& dims) {
 
 // ---- program construction ---------------------------------------------------------------------------------------
 
+typedef std::unordered_map<uint32_t, std::vector<double>> StepMap;
+
 struct Builder {
   const Tree& t;
   Program prog;
   int nd_base;                                                  // rank of the closure being exported
-  const std::unordered_map<uint32_t, std::vector<double>>* ext;  // Transform node -> extra column (re-rolled index)
+  std::vector<const StepMap*> exts;                             // per re-rolled index: Transform node -> extra matrix column
   std::unordered_map<uint32_t, int> memo;                       // node -> op index (ExportContext, R:220)
   std::map<uint32_t, int>* arg_of_param;                        // param node -> plan arg (shared across programs)
   std::vector<uint32_t>* arg_nodes;
@@ -178,15 +180,15 @@ struct Builder {
       L.arg = arg_for(arr.kids[0]);
       L.padding = p.value;
       for (int32_t s : p.shape) L.src_shape.push_back(s);
-      const std::vector<double>* e = nullptr;
-      if (ext) {
-        auto it = ext->find(ex.kids[0]);
-        if (it != ext->end()) e = &it->second;
-      }
+      CC_REQUIRE(nd == nd_base + (int)exts.size(), CC_ERR_BAD_TREE, "index space rank %d != closure rank %d + %zu re-rolled indices", nd, nd_base,
+                 exts.size());
       L.M.assign((size_t)arr.rows * (nd + 1), 0.0);
       for (uint32_t y = 0; y < arr.rows; ++y) {
         for (int x = 0; x < nd_base; ++x) L.M[(size_t)y * (nd + 1) + x] = arr.matrix[(size_t)y * arr.cols + x];
-        if (nd > nd_base) L.M[(size_t)y * (nd + 1) + nd_base] = e ? (*e)[y] : 0.0;
+        for (size_t k = 0; k < exts.size(); ++k) {
+          auto it = exts[k]->find(ex.kids[0]);
+          if (it != exts[k]->end()) L.M[(size_t)y * (nd + 1) + nd_base + k] = it->second[y];
+        }
         L.M[(size_t)y * (nd + 1) + nd] = arr.matrix[(size_t)y * arr.cols + nd_base];
       }
     }
@@ -301,6 +303,56 @@ bool reroll(const Tree& t, const std::vector<uint32_t>& elems, std::unordered_ma
         if (kv.second[y] != (double)i * it->second[y]) return false;
     }
   }
+  return true;
+}
+
+// left-leaning Plus chain (((e0 + e1) + e2) + ...) -> [e0, e1, ...]
+std::vector<uint32_t> plus_chain(const Tree& t, uint32_t root) {
+  std::vector<uint32_t> elems;
+  uint32_t cur = root;
+  while (t.nodes[cur].kind == K_PLUS) {
+    elems.push_back(t.nodes[cur].kids[1]);
+    cur = t.nodes[cur].kids[0];
+  }
+  elems.push_back(cur);
+  std::reverse(elems.begin(), elems.end());
+  return elems;
+}
+
+constexpr size_t kMinRerollTerms = 8;  // shorter chains stay unrolled in one elementwise kernel, as the reference runs them
+
+// Concatenate of C left folds of T terms each, term(c, t) congruent to term(0, 0) with Transform constants
+// const(0,0) + c * step_c + t * step_t. Fills the steps (keyed by the Transform nodes of term(0,0)) and the terms of chain 0.
+bool reroll_join_of_folds(const Tree& t, const std::vector<uint32_t>& kids, StepMap& step_c, StepMap& step_t, std::vector<uint32_t>& terms0) {
+  if (kids.size() < 2) return false;
+  std::vector<std::vector<uint32_t>> terms;
+  for (uint32_t k : kids) {
+    if (t.nodes[k].kind != K_PLUS) return false;
+    terms.push_back(plus_chain(t, k));
+    if (terms.back().size() != terms[0].size()) return false;
+  }
+  const size_t T = terms[0].size();
+  if (T < kMinRerollTerms) return false;
+  if (!reroll(t, terms[0], step_t)) return false;
+  std::vector<uint32_t> heads;
+  for (auto& ch : terms) heads.push_back(ch[0]);
+  {
+    // the step over c may be all-zero for some transforms but must exist; reroll() insists on a non-zero step somewhere
+    if (!reroll(t, heads, step_c)) return false;
+  }
+  if (step_c.size() != step_t.size()) return false;
+  for (size_t c = 1; c < terms.size(); ++c)
+    for (size_t i = 1; i < T; ++i) {
+      StepMap d;
+      if (!congruent(t, terms[0][0], terms[c][i], d) || d.size() != step_t.size()) return false;
+      for (auto& kv : d) {
+        auto ic = step_c.find(kv.first), it = step_t.find(kv.first);
+        if (ic == step_c.end() || it == step_t.end()) return false;
+        for (size_t y = 0; y < kv.second.size(); ++y)
+          if (kv.second[y] != (double)c * ic->second[y] + (double)i * it->second[y]) return false;
+      }
+    }
+  terms0 = terms[0];
   return true;
 }
 
@@ -892,6 +944,96 @@ void emit_reduce(Plan& plan, const Program& p, int n_args, const DeviceProps& de
   plan.source += e.s;
 }
 
+// ---- whole-tensor fold (Tensor.sum and the other monoids) with the operand's closure fused in -----------------------------
+//
+// Same schedule as the precompiled reduce_sum_kernel (kernels_basic.cu): 512 threads, grid <= 4 CTAs per SM, U independent
+// 128-bit vectors in flight per thread folded into U accumulators, warp-shuffle + shared-memory block fold, deterministic
+// last-block-done second stage. With U == 4 and a 4-divisible element count the fold order is identical to reduce_sum_kernel,
+// so `expr.sum` fused and `expr.doCache.sum` give the same bits.
+const char* monoid_type(uint32_t m) {
+  switch (m) {
+    case K_PLUS: return "cc_plus";
+    case K_TIMES: return "cc_times";
+    case K_MIN: return "cc_min";
+    case K_MAX: return "cc_max";
+  }
+  return "?";
+}
+
+void emit_full_reduce(Plan& plan, const Program& p, int n_args, const DeviceProps& dev, uint32_t monoid) {
+  const int nd = (int)p.dims.size();
+  const int64_t total = product(p.dims);
+  const int V = (nd >= 1 && p.dims[nd - 1] % 4 == 0) ? 4 : 1;
+  const int64_t NV = total / V;
+  const bool flat = program_is_flat(p);
+  const char* IDX = pick_idx_type(p, total + (int64_t)4 * kFullReduceMaxBlocks * kFullReduceThreads);
+  const int nloads = (int)p.loads.size();
+  const int U = nloads * V <= 16 ? 4 : (nloads * V <= 32 ? 2 : 1);
+  int64_t want = (NV + (int64_t)kFullReduceThreads * 4 - 1) / ((int64_t)kFullReduceThreads * 4);
+  int64_t cap = std::min<int64_t>((int64_t)dev.sm_count * 4, kFullReduceMaxBlocks);
+  const int64_t grid = std::max<int64_t>(1, std::min(want, cap));
+  const char* M = monoid_type(monoid);
+
+  Emit e;
+  e("// whole-tensor fold: dims=[");
+  for (int x = 0; x < nd; ++x) e("%s%lld", x ? "," : "", (long long)p.dims[x]);
+  e("] monoid=%s V=%d U=%d flat=%d idx=%s loads=%d ops=%zu grid=%lld\n", M, V, U, (int)flat, IDX, nloads, p.ops.size(), (long long)grid);
+  e("__device__ __forceinline__ void ev(const %s v%s%s, float (&o)[%d]) {\n", IDX, n_args ? ", " : "", param_list(n_args, false).c_str(), V);
+  if (flat) {
+    for (int j = 0; j < nloads; ++j) {
+      e("  float L%d[%d];\n", j, V);
+      if (V == 4)
+        e("  cc_ldg4(p%d + v * 4, L%d);\n", p.loads[j].arg, j);
+      else
+        e("  L%d[0] = cc_ldg(p%d + v);\n", j, p.loads[j].arg);
+    }
+  } else {
+    LoadCtx c{V, nd - 1, IDX};
+    emit_decode(e, p.dims, nd, IDX, strprintf("v * %d", V).c_str(), "  ");
+    for (int j = 0; j < nloads; ++j) emit_load(e, p, j, c, "  ");
+  }
+  e("  #pragma unroll\n  for (int l = 0; l < %d; ++l) {\n", V);
+  emit_ops(e, p, "    ", "l");
+  e("    o[l] = _%d;\n  }\n}\n", p.results[0]);
+  e("extern \"C\" __global__ void __launch_bounds__(%d) reduce_all(%s%sfloat* __restrict__ out, float* __restrict__ partials, unsigned* __restrict__ counter) {\n",
+    kFullReduceThreads, param_list(n_args, false).c_str(), n_args ? ", " : "");
+  e("  typedef %s M;\n  __shared__ float smem[32];\n", M);
+  e("  const %s NV = %lld;\n  const %s stride = (%s)gridDim.x * %d;\n  %s v = (%s)blockIdx.x * %d + threadIdx.x;\n", IDX, (long long)NV, IDX, IDX,
+    kFullReduceThreads, IDX, IDX, kFullReduceThreads);
+  e("  float a[%d][%d];\n  #pragma unroll\n  for (int u = 0; u < %d; ++u)\n    #pragma unroll\n    for (int l = 0; l < %d; ++l) a[u][l] = M::zero();\n", U, V, U, V);
+  const std::string pass = (n_args ? ", " : "") + arg_pass(n_args);
+  if (U > 1) {
+    e("  for (; v + %d * stride < NV; v += %d * stride) {\n    float x[%d][%d];\n", U - 1, U, U, V);
+    e("    #pragma unroll\n    for (int u = 0; u < %d; ++u) ev(v + u * stride%s, x[u]);\n", U, pass.c_str());
+    e("    #pragma unroll\n    for (int u = 0; u < %d; ++u)\n      #pragma unroll\n      for (int l = 0; l < %d; ++l) a[u][l] = M::ap(a[u][l], x[u][l]);\n  }\n", U, V);
+  }
+  e("  for (; v < NV; v += stride) {\n    float x[%d];\n    ev(v%s, x);\n", V, pass.c_str());
+  e("    #pragma unroll\n    for (int l = 0; l < %d; ++l) a[0][l] = M::ap(a[0][l], x[l]);\n  }\n", V);
+  // fold the U accumulators per lane, then the lanes: ((x + y) + (z + w))
+  e("  float q[%d];\n  #pragma unroll\n  for (int l = 0; l < %d; ++l) ", V, V);
+  if (U == 4)
+    e("q[l] = M::ap(M::ap(a[0][l], a[1][l]), M::ap(a[2][l], a[3][l]));\n");
+  else if (U == 2)
+    e("q[l] = M::ap(a[0][l], a[1][l]);\n");
+  else
+    e("q[l] = a[0][l];\n");
+  if (V == 4)
+    e("  float acc = M::ap(M::ap(q[0], q[1]), M::ap(q[2], q[3]));\n");
+  else
+    e("  float acc = q[0];\n");
+  e("  acc = cc_block_fold<M>(acc, smem);\n  cc_fold_finish<M>(acc, out, partials, counter, smem);\n}\n");
+  plan.source += e.s;
+  LaunchSpec ls;
+  ls.entry = "reduce_all";
+  ls.grid[0] = (uint32_t)grid;
+  ls.block[0] = kFullReduceThreads;
+  for (int i = 0; i < n_args; ++i) ls.args.push_back(i);
+  ls.args.push_back(ARG_OUT);
+  ls.args.push_back(ARG_REDUCE_PARTIALS);
+  ls.args.push_back(ARG_REDUCE_COUNTER);
+  plan.launches.push_back(ls);
+}
+
 // ---- definition inlining -----------------------------------------------------------------------------------------
 
 // M_outer: rows_p x (nd+1) maps the reduction's index space onto P's index space; M_def: rows_s x (rows_p+1) maps P's
@@ -926,21 +1068,41 @@ Plan make_plan(const Tree& t, const DeviceProps& dev) {
   bool is_reduce = false;
   int nd_base = (int)odims.size();
 
-  if (root.kind == K_CONCAT) {
+  if (root.kind == K_REDUCE) {
+    CC_REQUIRE(product(odims) == 1, CC_ERR_BAD_TREE, "Reduce produces one float; output shape has %lld elements", (long long)product(odims));
+    nd_base = (int)root.shape.size();
+    Builder b{t, {}, nd_base, {}, {}, &arg_of_param, &arg_nodes};
+    for (int32_t s : root.shape) b.prog.dims.push_back(s);
+    b.prog.results.push_back(b.export_node(root.kids[0]));
+    prog = std::move(b.prog);
+    plan.note = strprintf("whole-tensor %s fold with the operand's closure fused in", kind_name(root.monoid));
+  } else if (root.kind == K_CONCAT) {
     // Tensor.join (Tensors.scala:577-598): elements are evaluated over the head shape = out_shape minus the last dim
     CC_REQUIRE(!odims.empty() && odims.back() == (int64_t)root.kids.size(), CC_ERR_BAD_TREE,
                "Concatenate of %zu elements needs an output shape ending in %zu", root.kids.size(), root.kids.size());
     nd_base = (int)odims.size() - 1;
     std::vector<int64_t> head(odims.begin(), odims.end() - 1);
     std::unordered_map<uint32_t, std::vector<double>> step;
-    if (root.kids.size() >= 2 && reroll(t, root.kids, step)) {
-      Builder b{t, {}, nd_base, &step, {}, &arg_of_param, &arg_nodes};
+    StepMap step_c, step_t;
+    std::vector<uint32_t> terms0;
+    if (reroll_join_of_folds(t, root.kids, step_c, step_t, terms0)) {
+      // matmul1 (benchmarks.scala:176-187, README.md:312-329): join over c of left folds over t -> dims = head + [C] + [T]
+      Builder b{t, {}, nd_base, {&step_c, &step_t}, {}, &arg_of_param, &arg_nodes};
+      b.prog.dims = odims;
+      b.prog.dims.push_back((int64_t)terms0.size());
+      b.prog.results.push_back(b.export_node(terms0[0]));
+      prog = std::move(b.prog);
+      is_reduce = true;
+      plan.note = strprintf("join of %zu Plus chains of %zu congruent terms re-rolled into an output dimension and a reduction", root.kids.size(),
+                            terms0.size());
+    } else if (root.kids.size() >= 2 && reroll(t, root.kids, step)) {
+      Builder b{t, {}, nd_base, {&step}, {}, &arg_of_param, &arg_nodes};
       b.prog.dims = odims;  // head dims + the re-rolled element index as the fastest dimension
       b.prog.results.push_back(b.export_node(root.kids[0]));
       prog = std::move(b.prog);
       plan.note = "join re-rolled into an output dimension";
     } else {
-      Builder b{t, {}, nd_base, nullptr, {}, &arg_of_param, &arg_nodes};
+      Builder b{t, {}, nd_base, {}, {}, &arg_of_param, &arg_nodes};
       b.prog.dims = head;
       for (uint32_t k : root.kids) b.prog.results.push_back(b.export_node(k));
       prog = std::move(b.prog);
@@ -948,19 +1110,10 @@ Plan make_plan(const Tree& t, const DeviceProps& dev) {
     }
   } else {
     // left-leaning Plus chain?  (((e0 + e1) + e2) + ... )
-    std::vector<uint32_t> elems;
-    {
-      uint32_t cur = t.root;
-      while (t.nodes[cur].kind == K_PLUS) {
-        elems.push_back(t.nodes[cur].kids[1]);
-        cur = t.nodes[cur].kids[0];
-      }
-      elems.push_back(cur);
-      std::reverse(elems.begin(), elems.end());
-    }
+    std::vector<uint32_t> elems = plus_chain(t, t.root);
     std::unordered_map<uint32_t, std::vector<double>> step;
-    if (elems.size() >= 8 && reroll(t, elems, step)) {
-      Builder b{t, {}, nd_base, &step, {}, &arg_of_param, &arg_nodes};
+    if (elems.size() >= kMinRerollTerms && reroll(t, elems, step)) {
+      Builder b{t, {}, nd_base, {&step}, {}, &arg_of_param, &arg_nodes};
       b.prog.dims = odims;
       b.prog.dims.push_back((int64_t)elems.size());
       b.prog.results.push_back(b.export_node(elems[0]));
@@ -968,7 +1121,7 @@ Plan make_plan(const Tree& t, const DeviceProps& dev) {
       is_reduce = true;
       plan.note = strprintf("Plus chain of %zu congruent terms re-rolled into a reduction", elems.size());
     } else {
-      Builder b{t, {}, nd_base, nullptr, {}, &arg_of_param, &arg_nodes};
+      Builder b{t, {}, nd_base, {}, {}, &arg_of_param, &arg_nodes};
       b.prog.dims = odims;
       b.prog.results.push_back(b.export_node(t.root));
       prog = std::move(b.prog);
@@ -995,7 +1148,7 @@ Plan make_plan(const Tree& t, const DeviceProps& dev) {
           // export the definition over P's own index space, then re-map every load through L.M
           std::map<uint32_t, int> a3;
           std::vector<uint32_t> n3;
-          Builder db{t, {}, (int)pn.shape.size(), nullptr, {}, &a3, &n3};
+          Builder db{t, {}, (int)pn.shape.size(), {}, {}, &a3, &n3};
           for (int32_t s : pn.shape) db.prog.dims.push_back(s);
           int res = db.export_node((uint32_t)pn.def_root);
           std::vector<int> dmap(db.prog.ops.size(), -1);
@@ -1075,7 +1228,13 @@ Plan make_plan(const Tree& t, const DeviceProps& dev) {
     uint64_t bytes = plan.out_floats * 4;
     for (int a = 0; a < n_args; ++a) bytes += 4 * std::min<uint64_t>(touched[a], plan.arg_min_floats[a]);
     plan.algorithmic_bytes = bytes;
-    plan.flops = count_flops(prog) * (uint64_t)space + (is_reduce ? (uint64_t)space : 0);
+    plan.flops = count_flops(prog) * (uint64_t)space + ((is_reduce || root.kind == K_REDUCE) ? (uint64_t)space : 0);
+  }
+
+  if (root.kind == K_REDUCE) {
+    plan.kind = PLAN_FULL_REDUCE;
+    emit_full_reduce(plan, prog, n_args, dev, root.monoid);
+    return plan;
   }
 
   if (is_reduce) {
@@ -1099,8 +1258,16 @@ Plan make_plan(const Tree& t, const DeviceProps& dev) {
         int a_arg = -1, b_arg = -1;
         if (is_A(La) && is_B(Lb)) a_arg = La.arg, b_arg = Lb.arg;
         if (is_A(Lb) && is_B(La)) a_arg = Lb.arg, b_arg = La.arg;
-        if (a_arg >= 0 && a_arg != b_arg && M % 128 == 0 && N % 256 == 0 && K % 32 == 0 && M * K < ((int64_t)1 << 31) &&
-            N * K < ((int64_t)1 << 31)) {
+        // Any shape runs on the tensor cores (ragged edges are handled by the pipeline); tiny or very skinny products stay on
+        // the generic reduction, which needs one launch and no hi/lo workspace traffic. Measured on B200
+        // (scripts/gpu_gemm_shapes.py, profiles/r01_gemm_shapes.json): the three-launch pipeline costs ~15 us at least, the
+        // generic kernel ~8-13 us; they cross near 2^24..2^25 multiply-adds (256^3: 15.5 vs 13.1 us, 8192x64x64: 15.3 vs
+        // 16.7 us, 65536x32x32: 16.9 vs 29.1 us, 512^3: 20.9 vs 33.4 us).
+        int64_t min_macs = (int64_t)1 << 25;
+        if (const char* ev = getenv("CC_TUNE_CONTRACTION_MIN_MACS")) min_macs = atoll(ev);
+        const bool worth = M * N * K >= min_macs && N >= 32 && K >= 32;
+        if (a_arg >= 0 && a_arg != b_arg && worth && M < ((int64_t)1 << 31) && N < ((int64_t)1 << 31) && K < ((int64_t)1 << 31) - 32) {
+          const int64_t Kp = (K + 31) / 32 * 32;  // gemm_padded_k
           plan.kind = PLAN_CONTRACTION;
           plan.M = M;
           plan.N = N;
@@ -1112,7 +1279,7 @@ Plan make_plan(const Tree& t, const DeviceProps& dev) {
           plan.arg_min_floats = am;
           plan.flops = 2ull * (uint64_t)M * (uint64_t)N * (uint64_t)K;
           plan.algorithmic_bytes = 4ull * (uint64_t)(M * K + K * N + M * N);
-          plan.scratch_floats = {(uint64_t)(M * K), (uint64_t)(M * K), (uint64_t)(N * K), (uint64_t)(N * K)};
+          plan.scratch_floats = {(uint64_t)(M * Kp), (uint64_t)(M * Kp), (uint64_t)(N * Kp), (uint64_t)(N * Kp)};
           plan.note += strprintf("; contraction %lldx%lldx%lld -> tcgen05 3xTF32", (long long)M, (long long)N, (long long)K);
           plan.source = "// contraction pattern: runs the precompiled TMA + tcgen05 3xTF32 pipeline (gemm_3xtf32.cu)\n";
           return plan;

@@ -10,9 +10,17 @@
 
 namespace cc {
 
-enum PlanKind { PLAN_ELEMENTWISE = 0, PLAN_AXIS_REDUCE = 1, PLAN_CONTRACTION = 2, PLAN_TILED_TRANSPOSE = 3 };
+enum PlanKind { PLAN_ELEMENTWISE = 0, PLAN_AXIS_REDUCE = 1, PLAN_CONTRACTION = 2, PLAN_TILED_TRANSPOSE = 3, PLAN_FULL_REDUCE = 4 };
 
-enum { ARG_OUT = -1, ARG_SCRATCH0 = -2 /* -2-k = scratch k */ };
+enum {
+  ARG_OUT = -1,
+  ARG_SCRATCH0 = -2 /* -2-k = scratch k */,
+  // PLAN_FULL_REDUCE: the runtime's shared partials buffer and its self-resetting block counter (serialised on stream 0)
+  ARG_REDUCE_PARTIALS = -100,
+  ARG_REDUCE_COUNTER = -101
+};
+constexpr int kFullReduceThreads = 512;
+constexpr int kFullReduceMaxBlocks = 148 * 4 * 2;  // = kReduceMaxBlocks of kernels_basic.cu: the partials buffer holds this many floats
 
 struct LaunchSpec {
   std::string entry;  // __global__ name inside the generated module

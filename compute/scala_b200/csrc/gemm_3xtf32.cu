@@ -5,8 +5,11 @@
 // all three products accumulated into the same fp32 TMEM accumulator, small terms first.
 //
 // Pipeline (sm_100a only — TMA, mbarrier, tcgen05, TMEM):
-//   prologue kernels   split A into A_hi / A_lo [M,K] and B into B^T_hi / B^T_lo [N,K]  (both operands K-major)
-//   gemm kernel        persistent, one CTA per SM, 128 x 256 output tile, BLOCK_K = 32 floats (one 128-byte swizzle row)
+//   prologue kernels   split A into A_hi / A_lo [M,Kp] and B into B^T_hi / B^T_lo [N,Kp]  (both operands K-major, K zero-padded
+//                      to Kp = a multiple of 32 so any K works; ragged M / N edges are TMA out-of-bounds zero fill on the way
+//                      in and predicated stores on the way out)
+//   gemm kernel        persistent, one CTA per SM, 128 x BN output tile (BN = 256 / 128 / 64 picked per problem so that small
+//                      problems still fill the SMs), BLOCK_K = 32 floats (one 128-byte swizzle row)
 //     warp 0  TMA producer: 4 tiles per stage (A_hi, A_lo, B_hi, B_lo), SWIZZLE_128B, mbarrier expect_tx
 //     warp 1  MMA issuer: one elected thread issues 12 tcgen05.mma.kind::tf32 (M128 N256 K8) per stage,
 //             tcgen05.commit releases the smem stage / publishes the accumulator
@@ -23,15 +26,23 @@
 namespace cc {
 namespace {
 
-constexpr int BM = 128, BN = 256, BK = 32;  // BK floats = 128 bytes = one swizzle row
-constexpr int STAGES = 2;
-constexpr int A_TILE_BYTES = BM * BK * 4;                          // 16 KiB
-constexpr int B_TILE_BYTES = BN * BK * 4;                          // 32 KiB
-constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;   // 96 KiB
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int BM = 128, BK = 32;  // BK floats = 128 bytes = one swizzle row
+constexpr int A_TILE_BYTES = BM * BK * 4;  // 16 KiB
 constexpr int GEMM_THREADS = 256;
-constexpr int TMEM_COLS = 512;
 constexpr int GROUP_M = 16;  // tile rasterisation: 16 m-tiles share each sweep over n (L2 reuse of the A panels)
+
+template <int BN>
+struct Cfg {
+  static_assert(BN == 256 || BN == 128 || BN == 64, "BN must be 256, 128 or 64");
+  static constexpr int B_TILE_BYTES = BN * BK * 4;                         // 32 / 16 / 8 KiB
+  static constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;  // 96 / 64 / 48 KiB
+  static constexpr int STAGES = BN == 256 ? 2 : (BN == 128 ? 3 : 4);       // 192 KiB of operands in flight
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int TMEM_COLS = 2 * BN;  // two accumulators: the epilogue of tile i overlaps the MMAs of tile i+1
+  // cute::UMMA::InstrDescriptor for kind::tf32, fp32 accumulate, both operands K-major, M = 128, N = BN
+  static constexpr uint32_t kInstrDesc = (1u << 4) /*D = f32*/ | (2u << 7) /*A = tf32*/ | (2u << 10) /*B = tf32*/ | ((uint32_t)(BN >> 3) << 17) |
+                                         ((uint32_t)(BM >> 4) << 24);
+};
 
 // ---- PTX wrappers ------------------------------------------------------------------------------------------------------
 
@@ -95,17 +106,13 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
   return d;
 }
 
-// cute::UMMA::InstrDescriptor for kind::tf32, fp32 accumulate, both operands K-major, M = 128, N = 256
-constexpr uint32_t kInstrDesc = (1u << 4) /*D = f32*/ | (2u << 7) /*A = tf32*/ | (2u << 10) /*B = tf32*/ | ((uint32_t)(BN >> 3) << 17) |
-                                ((uint32_t)(BM >> 4) << 24);
-
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
       :
-      : "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(kInstrDesc), "r"(accumulate)
+      : "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
@@ -138,10 +145,16 @@ __device__ __forceinline__ void tile_coords(int tile, int tiles_m, int tiles_n, 
 
 // ---- the GEMM ------------------------------------------------------------------------------------------------------------
 
+template <int BN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
-                   const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo, float* __restrict__ C, int N, int K,
+                   const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo, float* __restrict__ C, int M, int N, int Kp,
                    int tiles_m, int tiles_n) {
+  constexpr int STAGES = Cfg<BN>::STAGES;
+  constexpr int STAGE_BYTES = Cfg<BN>::STAGE_BYTES;
+  constexpr int B_TILE_BYTES = Cfg<BN>::B_TILE_BYTES;
+  constexpr int TMEM_COLS = Cfg<BN>::TMEM_COLS;
+  constexpr uint32_t kInstrDesc = Cfg<BN>::kInstrDesc;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024-byte alignment
   const uint32_t bars = smem_base + STAGES * STAGE_BYTES;
@@ -157,7 +170,7 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int num_tiles = tiles_m * tiles_n;
-  const int num_kb = K / BK;
+  const int num_kb = Kp / BK;
 
   if (warp == 0 && lane == 0) {
     prefetch_tensormap(&tm_a_hi);
@@ -231,9 +244,9 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
 #pragma unroll
           for (int k = 0; k < BK / 8; ++k) {
             const uint64_t adv = (uint64_t)((k * 8 * 4) >> 4);  // +32 bytes along K inside the 128-byte swizzle row
-            umma_tf32(tmem_d, a_lo + adv, b_hi + adv, (kb | k) != 0);
-            umma_tf32(tmem_d, a_hi + adv, b_lo + adv, 1);
-            umma_tf32(tmem_d, a_hi + adv, b_hi + adv, 1);
+            umma_tf32(tmem_d, a_lo + adv, b_hi + adv, kInstrDesc, (kb | k) != 0);
+            umma_tf32(tmem_d, a_hi + adv, b_lo + adv, kInstrDesc, 1);
+            umma_tf32(tmem_d, a_hi + adv, b_hi + adv, kInstrDesc, 1);
           }
           umma_commit(empty_bar(stage));                          // frees the smem stage when these MMAs retire
           if (kb == num_kb - 1) umma_commit(tmem_full_bar(acc));  // accumulator complete -> epilogue
@@ -256,19 +269,32 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
       const uint32_t acc_phase = (it >> 1) & 1;
       mbar_wait(tmem_full_bar(acc), acc_phase);
       tc_fence_after();
-      const size_t row = (size_t)m_blk * BM + (size_t)ew * 32 + lane;
-      float* out = C + row * (size_t)N + (size_t)n_blk * BN;
+      const int row = m_blk * BM + ew * 32 + lane;
+      const int col0 = n_blk * BN;
+      float* out = C + (size_t)row * (size_t)N + (size_t)col0;
       const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * BN);
+      const bool row_ok = row < M;
+      const bool vec_ok = (N & 3) == 0;  // 16-byte aligned row starts
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
+        if (col0 + c * 32 >= N) break;  // warp-uniform: the whole 32-column slab is outside the matrix
         uint32_t r[32];
         tmem_ld_32x32(taddr + (uint32_t)(c * 32), r);
         tmem_ld_wait();
+        if (!row_ok) {
+          // rows past M (TMA zero fill): nothing to store, but stay converged for the next warp-collective tcgen05.ld
+        } else if (vec_ok && col0 + c * 32 + 32 <= N) {
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          float4 v = make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]), __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
-          __stcs(reinterpret_cast<float4*>(out + c * 32) + q, v);
+          for (int q = 0; q < 8; ++q) {
+            float4 v = make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]), __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
+            __stcs(reinterpret_cast<float4*>(out + c * 32) + q, v);
+          }
+        } else {
+#pragma unroll
+          for (int q = 0; q < 32; ++q)
+            if (col0 + c * 32 + q < N) __stcs(out + c * 32 + q, __uint_as_float(r[q]));
         }
+        __syncwarp();
       }
       tc_fence_before();
       mbar_arrive(tmem_empty_bar(acc));
@@ -292,30 +318,46 @@ __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
   lo = __uint_as_float(t);
 }
 
-__global__ void __launch_bounds__(256) split_a_kernel(const float4* __restrict__ a, float4* __restrict__ hi, float4* __restrict__ lo, size_t nvec) {
+// A [M,K] row-major -> A_hi / A_lo [M,Kp] (Kp % 32 == 0, columns >= K zero). One thread per 4 output floats.
+__global__ void __launch_bounds__(256) split_a_kernel(const float* __restrict__ a, float* __restrict__ hi, float* __restrict__ lo, int M, int K, int Kp) {
+  const size_t vec_per_row = (size_t)Kp / 4;
+  const size_t nvec = (size_t)M * vec_per_row;
   const size_t stride = (size_t)gridDim.x * 256;
+  const bool aligned = (K & 3) == 0;
   for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < nvec; i += stride) {
-    const float4 x = __ldcs(a + i);
+    const size_t row = i / vec_per_row;
+    const int k = (int)(i - row * vec_per_row) * 4;
+    float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float* src = a + row * (size_t)K + k;
+    if (aligned && k + 3 < K) {
+      x = __ldcs(reinterpret_cast<const float4*>(src));
+    } else {
+      if (k < K) x.x = __ldcs(src);
+      if (k + 1 < K) x.y = __ldcs(src + 1);
+      if (k + 2 < K) x.z = __ldcs(src + 2);
+      if (k + 3 < K) x.w = __ldcs(src + 3);
+    }
     float4 h, l;
     split_tf32(x.x, h.x, l.x);
     split_tf32(x.y, h.y, l.y);
     split_tf32(x.z, h.z, l.z);
     split_tf32(x.w, h.w, l.w);
-    hi[i] = h;
-    lo[i] = l;
+    reinterpret_cast<float4*>(hi)[i] = h;
+    reinterpret_cast<float4*>(lo)[i] = l;
   }
 }
 
-// B [K,N] row-major -> B^T hi / lo [N,K] row-major, 32x32 tiles through padded shared memory
+// B [K,N] row-major -> B^T hi / lo [N,Kp] row-major (columns >= K zero), 32x32 tiles through padded shared memory
 __global__ void __launch_bounds__(256) split_transpose_b_kernel(const float* __restrict__ b, float* __restrict__ bt_hi, float* __restrict__ bt_lo, int K,
-                                                                int N) {
+                                                                int N, int Kp) {
   __shared__ float th[32][33];
   __shared__ float tl[32][33];
   const int n0 = blockIdx.x * 32, k0 = blockIdx.y * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
 #pragma unroll
   for (int r = 0; r < 32; r += 8) {
-    const float x = b[(size_t)(k0 + ty + r) * N + n0 + tx];
+    const int k = k0 + ty + r, n = n0 + tx;
+    const float x = (k < K && n < N) ? b[(size_t)k * N + n] : 0.f;
     float h, l;
     split_tf32(x, h, l);
     th[ty + r][tx] = h;
@@ -324,9 +366,12 @@ __global__ void __launch_bounds__(256) split_transpose_b_kernel(const float* __r
   __syncthreads();
 #pragma unroll
   for (int r = 0; r < 32; r += 8) {
-    const size_t o = (size_t)(n0 + ty + r) * K + k0 + tx;
-    bt_hi[o] = th[tx][ty + r];
-    bt_lo[o] = tl[tx][ty + r];
+    const int n = n0 + ty + r;
+    if (n < N) {  // k0 + tx < Kp always: Kp is a multiple of 32
+      const size_t o = (size_t)n * Kp + k0 + tx;
+      bt_hi[o] = th[tx][ty + r];
+      bt_lo[o] = tl[tx][ty + r];
+    }
   }
 }
 
@@ -349,36 +394,58 @@ void check_launch(const char* what) {
 
 bool gemm_available() { return true; }
 
-int launch_gemm_3xtf32(const float* a, const float* b, float* c, int64_t m, int64_t n, int64_t k, const GemmWorkspace& ws, int sm_count,
-                       TensorMapEncodeFn encode, cudaStream_t stream) {
-  CC_REQUIRE(m % BM == 0 && n % BN == 0 && k % BK == 0, CC_ERR_UNSUPPORTED, "gemm_3xtf32 needs M %% %d == 0, N %% %d == 0, K %% %d == 0", BM, BN,
-             BK);
-  CC_REQUIRE(encode, CC_ERR_NO_DRIVER, "cuTensorMapEncodeTiled unavailable");
-  // A_hi shares the B^T_hi workspace layout: ws.a_lo holds A_lo, A_hi is written into the first M*K floats of a second buffer
+int64_t gemm_padded_k(int64_t k) { return (k + BK - 1) / BK * BK; }
+
+int gemm_pick_bn(int64_t m, int64_t n, int sm_count) {
+  // the widest tile that still gives every SM a tile; problems too small for that take the narrowest tile (most CTAs)
+  const int64_t tiles_m = (m + BM - 1) / BM;
+  for (int bn : {256, 128, 64}) {
+    if (bn > 64 && n <= bn / 2) continue;  // a tile that would be more than half empty
+    if (tiles_m * ((n + bn - 1) / bn) >= sm_count) return bn;
+  }
+  return 64;
+}
+
+namespace {
+template <int BN>
+void launch_main(const GemmWorkspace& ws, float* c, int64_t m, int64_t n, int64_t kp, int sm_count, TensorMapEncodeFn encode, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_3xtf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-    if (e != cudaSuccess) fail(CC_ERR_CUDA, strprintf("cudaFuncSetAttribute(smem=%d): %s", SMEM_BYTES, cudaGetErrorString(e)));
+    cudaError_t e = cudaFuncSetAttribute(gemm_3xtf32_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM_BYTES);
+    if (e != cudaSuccess) fail(CC_ERR_CUDA, strprintf("cudaFuncSetAttribute(smem=%d): %s", Cfg<BN>::SMEM_BYTES, cudaGetErrorString(e)));
     attr_set = true;
   }
-  const size_t nvec = (size_t)(m * k) / 4;
-  int blocks = (int)((nvec + 255) / 256);
-  if (blocks > sm_count * 8) blocks = sm_count * 8;
-  split_a_kernel<<<blocks, 256, 0, stream>>>(reinterpret_cast<const float4*>(a), reinterpret_cast<float4*>(ws.a_hi), reinterpret_cast<float4*>(ws.a_lo),
-                                             nvec);
-  check_launch("split_a");
-  split_transpose_b_kernel<<<dim3((unsigned)(n / 32), (unsigned)(k / 32)), 256, 0, stream>>>(b, ws.bt_hi, ws.bt_lo, (int)k, (int)n);
-  check_launch("split_transpose_b");
   CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
-  make_map(encode, &ma_hi, ws.a_hi, m, k, BM);
-  make_map(encode, &ma_lo, ws.a_lo, m, k, BM);
-  make_map(encode, &mb_hi, ws.bt_hi, n, k, BN);
-  make_map(encode, &mb_lo, ws.bt_lo, n, k, BN);
-  const int tiles_m = (int)(m / BM), tiles_n = (int)(n / BN);
+  make_map(encode, &ma_hi, ws.a_hi, m, kp, BM);
+  make_map(encode, &ma_lo, ws.a_lo, m, kp, BM);
+  make_map(encode, &mb_hi, ws.bt_hi, n, kp, BN);
+  make_map(encode, &mb_lo, ws.bt_lo, n, kp, BN);
+  const int tiles_m = (int)((m + BM - 1) / BM), tiles_n = (int)((n + BN - 1) / BN);
   int grid = tiles_m * tiles_n;
   if (grid > sm_count) grid = sm_count;
-  gemm_3xtf32_kernel<<<grid, GEMM_THREADS, SMEM_BYTES, stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, c, (int)n, (int)k, tiles_m, tiles_n);
+  gemm_3xtf32_kernel<BN><<<grid, GEMM_THREADS, Cfg<BN>::SMEM_BYTES, stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, c, (int)m, (int)n, (int)kp, tiles_m, tiles_n);
   check_launch("gemm_3xtf32");
+}
+}  // namespace
+
+int launch_gemm_3xtf32(const float* a, const float* b, float* c, int64_t m, int64_t n, int64_t k, const GemmWorkspace& ws, int sm_count,
+                       TensorMapEncodeFn encode, cudaStream_t stream) {
+  CC_REQUIRE(m >= 1 && n >= 1 && k >= 1 && m < (1ll << 31) && n < (1ll << 31) && k < (1ll << 31) - BK, CC_ERR_UNSUPPORTED,
+             "gemm_3xtf32: bad shape %lld x %lld x %lld", (long long)m, (long long)n, (long long)k);
+  CC_REQUIRE(encode, CC_ERR_NO_DRIVER, "cuTensorMapEncodeTiled unavailable");
+  const int64_t kp = gemm_padded_k(k);
+  const size_t nvec = (size_t)(m * kp) / 4;
+  size_t blocks = (nvec + 255) / 256;
+  if (blocks > (size_t)sm_count * 8) blocks = (size_t)sm_count * 8;
+  split_a_kernel<<<(unsigned)blocks, 256, 0, stream>>>(a, ws.a_hi, ws.a_lo, (int)m, (int)k, (int)kp);
+  check_launch("split_a");
+  split_transpose_b_kernel<<<dim3((unsigned)((n + 31) / 32), (unsigned)(kp / 32)), 256, 0, stream>>>(b, ws.bt_hi, ws.bt_lo, (int)k, (int)n, (int)kp);
+  check_launch("split_transpose_b");
+  switch (gemm_pick_bn(m, n, sm_count)) {
+    case 256: launch_main<256>(ws, c, m, n, kp, sm_count, encode, stream); break;
+    case 128: launch_main<128>(ws, c, m, n, kp, sm_count, encode, stream); break;
+    default: launch_main<64>(ws, c, m, n, kp, sm_count, encode, stream); break;
+  }
   return 3;
 }
 

@@ -42,6 +42,7 @@ const char* kind_name(uint32_t k) {
     case K_TIMES: return "Times";
     case K_DIV: return "Div";
     case K_PERCENT: return "Percent";
+    case K_REDUCE: return "Reduce";
   }
   return "?";
 }
@@ -143,6 +144,19 @@ Tree parse_tree(const void* blob, uint64_t n_bytes) {
       uint32_t m = r.u32();
       CC_REQUIRE(m >= 1 && m <= (1u << 24), CC_ERR_BAD_TREE, "bad Concatenate length");
       for (uint32_t j = 0; j < m; ++j) nd.kids.push_back(kid());
+    } else if (nd.kind == K_REDUCE) {
+      nd.monoid = r.u32();
+      CC_REQUIRE(nd.monoid == K_PLUS || nd.monoid == K_MIN || nd.monoid == K_MAX || nd.monoid == K_TIMES, CC_ERR_BAD_TREE,
+                 "Reduce monoid must be Plus, Min, Max or Times (got %u)", nd.monoid);
+      nd.kids.push_back(kid());
+      uint32_t rank = r.u32();
+      CC_REQUIRE(rank <= 16, CC_ERR_BAD_TREE, "Reduce rank %u too large", rank);
+      for (uint32_t d = 0; d < rank; ++d) {
+        int32_t s = r.i32();
+        CC_REQUIRE(s >= 0, CC_ERR_BAD_TREE, "negative Reduce dimension");
+        nd.shape.push_back(s);
+      }
+      CC_REQUIRE(i == t.root, CC_ERR_BAD_TREE, "Reduce is only allowed at the root of a tree");
     } else if (is_unary(nd.kind)) {
       nd.kids.push_back(kid());
     } else if (is_binary(nd.kind)) {
@@ -151,10 +165,10 @@ Tree parse_tree(const void* blob, uint64_t n_bytes) {
     } else {
       fail(CC_ERR_BAD_TREE, strprintf("unknown node kind %u", nd.kind));
     }
-    if (nd.kind == K_CONCAT || is_unary(nd.kind) || is_binary(nd.kind)) {
+    if (nd.kind == K_CONCAT || nd.kind == K_REDUCE || is_unary(nd.kind) || is_binary(nd.kind)) {
       for (uint32_t k : nd.kids) {
         uint32_t kk = t.nodes[k].kind;
-        CC_REQUIRE(kk != K_PARAM && kk != K_TRANSFORM && kk != K_CONCAT, CC_ERR_BAD_TREE,
+        CC_REQUIRE(kk != K_PARAM && kk != K_TRANSFORM && kk != K_CONCAT && kk != K_REDUCE, CC_ERR_BAD_TREE,
                    "%s operand must be a float term", kind_name(nd.kind));
       }
     }
@@ -165,7 +179,7 @@ Tree parse_tree(const void* blob, uint64_t n_bytes) {
   for (const Node& nd : t.nodes)
     if (nd.kind == K_PARAM && nd.def_root >= 0) {
       uint32_t dk = t.nodes[nd.def_root].kind;
-      CC_REQUIRE(dk != K_PARAM && dk != K_TRANSFORM && dk != K_CONCAT, CC_ERR_BAD_TREE, "definition must be a float term");
+      CC_REQUIRE(dk != K_PARAM && dk != K_TRANSFORM && dk != K_CONCAT && dk != K_REDUCE, CC_ERR_BAD_TREE, "definition must be a float term");
     }
   return t;
 }
@@ -234,6 +248,12 @@ void canonicalize(Tree& t) {
         put32(nd.rows);
         put32(nd.cols);
         key.append((const char*)nd.matrix.data(), nd.matrix.size() * sizeof(double));
+        break;
+      case K_REDUCE:
+        put32(nd.monoid);
+        put32((uint32_t)canon[nd.kids[0]]);
+        put32((uint32_t)nd.shape.size());
+        for (int32_t s : nd.shape) put32((uint32_t)s);
         break;
       default:
         put32((uint32_t)nd.kids.size());
@@ -311,6 +331,14 @@ uint32_t TreeWriter::binary(uint32_t kind, uint32_t a, uint32_t b) {
   uint32_t i = begin(kind);
   u32(a);
   u32(b);
+  return i;
+}
+uint32_t TreeWriter::reduce(uint32_t monoid, uint32_t operand, const std::vector<int32_t>& operand_shape) {
+  uint32_t i = begin(K_REDUCE);
+  u32(monoid);
+  u32(operand);
+  u32((uint32_t)operand_shape.size());
+  for (int32_t s : operand_shape) i32(s);
   return i;
 }
 std::string TreeWriter::finish(uint32_t root, const std::vector<int32_t>& out_shape) const {

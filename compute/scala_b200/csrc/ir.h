@@ -31,6 +31,11 @@ enum Kind : uint32_t {
   K_TIMES = 24,
   K_DIV = 25,
   K_PERCENT = 26,
+  // Root-only: fold the operand over its whole index space with a monoid (K_PLUS / K_MIN / K_MAX / K_TIMES). The reference
+  // has no such tree node — Tensor.sum materialises its operand and runs a hand-written program over the buffer
+  // (Tensors.scala:303-393, 673-771); MonoidPrograms is generic over append / zero, and this node lets the backend fuse the
+  // operand's closure into the reduction.
+  K_REDUCE = 30,
 };
 
 inline bool is_unary(uint32_t k) { return k >= K_EXP && k <= K_NEG; }
@@ -46,6 +51,7 @@ struct Node {
   uint32_t rows = 0, cols = 0; // transform matrix, row-major rows x cols (cols = view rank + 1)
   std::vector<double> matrix;
   std::vector<uint32_t> kids;  // operands / array / concatenate elements
+  uint32_t monoid = 0;         // K_REDUCE: K_PLUS / K_MIN / K_MAX / K_TIMES (shape = index space of the operand)
 };
 
 struct Tree {
@@ -75,6 +81,7 @@ class TreeWriter {
   uint32_t concatenate(const std::vector<uint32_t>& elements);
   uint32_t unary(uint32_t kind, uint32_t a);
   uint32_t binary(uint32_t kind, uint32_t a, uint32_t b);
+  uint32_t reduce(uint32_t monoid, uint32_t operand, const std::vector<int32_t>& operand_shape);
   void set_definition(uint32_t param_node, int32_t def_root);
   std::string finish(uint32_t root, const std::vector<int32_t>& out_shape) const;
   uint32_t size() const { return (uint32_t)offsets_.size(); }

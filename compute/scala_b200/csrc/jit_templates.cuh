@@ -59,3 +59,61 @@ __device__ __forceinline__ float cc_block_sum_256(float v) {
   }
   return v;
 }
+
+// ---- monoids (MonoidPrograms, Tensors.scala:308-311: append / zero) ------------------------------------------------------
+// ap() never contracts with the producer of its operands (__fadd_rn / __fmul_rn), so a reduction fused with an elementwise
+// closure folds exactly the values the unfused "materialise, then reduce" sequence of the reference would fold.
+
+struct cc_plus { static __device__ __forceinline__ float zero() { return 0.f; } static __device__ __forceinline__ float ap(float a, float b) { return __fadd_rn(a, b); } };
+struct cc_times { static __device__ __forceinline__ float zero() { return 1.f; } static __device__ __forceinline__ float ap(float a, float b) { return __fmul_rn(a, b); } };
+struct cc_min { static __device__ __forceinline__ float zero() { return __int_as_float(0x7f800000); } static __device__ __forceinline__ float ap(float a, float b) { return fminf(a, b); } };
+struct cc_max { static __device__ __forceinline__ float zero() { return __int_as_float(0xff800000); } static __device__ __forceinline__ float ap(float a, float b) { return fmaxf(a, b); } };
+
+template <class M>
+__device__ __forceinline__ float cc_warp_fold(float v) {
+  v = M::ap(v, __shfl_xor_sync(0xffffffffu, v, 16));
+  v = M::ap(v, __shfl_xor_sync(0xffffffffu, v, 8));
+  v = M::ap(v, __shfl_xor_sync(0xffffffffu, v, 4));
+  v = M::ap(v, __shfl_xor_sync(0xffffffffu, v, 2));
+  v = M::ap(v, __shfl_xor_sync(0xffffffffu, v, 1));
+  return v;
+}
+
+// every thread of the (multiple-of-32, <= 1024 thread) block must call; result valid in warp 0
+template <class M>
+__device__ __forceinline__ float cc_block_fold(float v, float* smem /* >= 32 floats */) {
+  v = cc_warp_fold<M>(v);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) smem[warp] = v;
+  __syncthreads();
+  if (warp == 0) {
+    v = lane < (int)(blockDim.x >> 5) ? smem[lane] : M::zero();
+    v = cc_warp_fold<M>(v);
+  }
+  return v;
+}
+
+// Second stage of a whole-tensor fold: block `blockIdx.x` publishes its partial; the last block to arrive folds all partials
+// in index order (deterministic: no float atomics) and resets the counter for the next launch on this stream.
+template <class M>
+__device__ __forceinline__ void cc_fold_finish(float block_value /* valid in thread 0 */, float* __restrict__ out, float* __restrict__ partials,
+                                               unsigned* __restrict__ counter, float* smem) {
+  __shared__ bool cc_is_last_;
+  if (threadIdx.x == 0) {
+    partials[blockIdx.x] = block_value;
+    __threadfence();
+    const unsigned done = atomicAdd(counter, 1u);
+    cc_is_last_ = (done == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!cc_is_last_) return;
+  __threadfence();
+  float p = M::zero();
+  for (unsigned i = threadIdx.x; i < gridDim.x; i += blockDim.x) p = M::ap(p, __ldcg(partials + i));
+  p = cc_block_fold<M>(p, smem);
+  if (threadIdx.x == 0) {
+    out[0] = p;
+    *counter = 0u;
+  }
+}

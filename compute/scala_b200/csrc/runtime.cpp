@@ -878,8 +878,11 @@ int cc_launch(cc_kernel h, const cc_buffer* args, int n_args, cc_buffer out, con
     ensure_loaded(*k);
     std::vector<Buffer*> scratch;
     for (uint64_t n : p.scratch_floats) scratch.push_back(alloc_buffer(n));
-    Op op{pick_stream(), in, {ob}};
+    // whole-tensor folds share the runtime's partials buffer and block counter: serialised on stream 0 like cc_reduce_sum
+    Buffer* shared_partials = p.kind == PLAN_FULL_REDUCE ? reduce_scratch() : nullptr;
+    Op op{shared_partials ? 0 : pick_stream(), in, {ob}};
     for (Buffer* s : scratch) op.writes.push_back(s);
+    if (shared_partials) op.writes.push_back(shared_partials);
     op_begin(op, waits, n_waits);
     if (p.kind == PLAN_CONTRACTION) {
       gemm_on_stream(in[0], in[1], ob, p.M, p.N, p.K, scratch, op.cu());
@@ -894,6 +897,10 @@ int cc_launch(cc_kernel h, const cc_buffer* args, int n_args, cc_buffer out, con
             ptrs.push_back(in[a]->ptr);
           else if (a == ARG_OUT)
             ptrs.push_back(ob->ptr);
+          else if (a == ARG_REDUCE_PARTIALS)
+            ptrs.push_back(shared_partials->ptr);
+          else if (a == ARG_REDUCE_COUNTER)
+            ptrs.push_back(r.reduce_counter);
           else
             ptrs.push_back(scratch[ARG_SCRATCH0 - a]->ptr);
         }
@@ -967,14 +974,14 @@ int cc_matmul_3xtf32(cc_buffer a, cc_buffer b, cc_buffer c, int64_t m, int64_t n
     Buffer* ab = as_buffer(a);
     Buffer* bb = as_buffer(b);
     Buffer* cb = as_buffer(c);
-    CC_REQUIRE(m > 0 && n > 0 && k > 0 && m % kGemmTileM == 0 && n % kGemmTileN == 0 && k % kGemmTileK == 0, CC_ERR_UNSUPPORTED,
-               "cc_matmul_3xtf32 needs M %% 128 == 0, N %% 256 == 0, K %% 32 == 0 (got %lld x %lld x %lld)", (long long)m, (long long)n,
-               (long long)k);
+    CC_REQUIRE(m > 0 && n > 0 && k > 0 && m < (1ll << 31) && n < (1ll << 31) && k < (1ll << 31) - 32, CC_ERR_ILLEGAL_ARGUMENT,
+               "cc_matmul_3xtf32: bad shape %lld x %lld x %lld", (long long)m, (long long)n, (long long)k);
     CC_REQUIRE(ab->n_floats >= (uint64_t)(m * k) && bb->n_floats >= (uint64_t)(k * n) && cb->n_floats >= (uint64_t)(m * n),
                CC_ERR_ILLEGAL_ARGUMENT, "matmul buffers too small");
     CC_REQUIRE(cb != ab && cb != bb, CC_ERR_ILLEGAL_ARGUMENT, "matmul output aliases an input");
-    std::vector<Buffer*> scratch{alloc_buffer((uint64_t)(m * k)), alloc_buffer((uint64_t)(m * k)), alloc_buffer((uint64_t)(n * k)),
-                                 alloc_buffer((uint64_t)(n * k))};
+    const int64_t kp = gemm_padded_k(k);
+    std::vector<Buffer*> scratch{alloc_buffer((uint64_t)(m * kp)), alloc_buffer((uint64_t)(m * kp)), alloc_buffer((uint64_t)(n * kp)),
+                                 alloc_buffer((uint64_t)(n * kp))};
     Op op{pick_stream(), {ab, bb}, {cb}};
     for (Buffer* s : scratch) op.writes.push_back(s);
     op_begin(op, waits, n_waits);

@@ -225,23 +225,38 @@ struct RandomTensor final : NonInlineTensor {
   }
 };
 
-// Tensor.sum (Tensors.scala:673-771)
-struct SumTensor final : NonInlineTensor {
+// Tensor.sum / reduce(MonoidPrograms) (Tensors.scala:303-393, 673-771). The reference always materialises the operand and
+// folds the buffer; here an inline operand's closure is fused into the fold kernel (one pass over the inputs, no intermediate),
+// and a materialised operand summed with Plus runs the precompiled reduce_sum_kernel — both fold in the same order.
+struct ReduceTensor final : NonInlineTensor {
   TensorPtr base;
-  ~SumTensor() override { bury(std::move(base)); }
+  uint32_t monoid = cc::K_PLUS;
+  mutable PlanCache plan;
+  ~ReduceTensor() override { bury(std::move(base)); }
   PendingBuffer evaluate(Session& s) const override {
-    PendingBuffer in = base->do_buffer(s);
-    cc_buffer out = 0;
-    int st = cc_buffer_alloc(1, &out);
-    if (st == CC_OK) st = cc_reduce_sum(in.buffer, (uint64_t)base->size(), out, nullptr, 0, nullptr);
-    std::string m = st == CC_OK ? "" : cc_last_error();
-    cc_buffer_release(in.buffer);
-    if (st != CC_OK) {
-      if (out) cc_buffer_release(out);
-      throw Error(st, m);
+    if (monoid == cc::K_PLUS && !base->is_inline()) {
+      PendingBuffer in = base->do_buffer(s);
+      cc_buffer out = 0;
+      int st = cc_buffer_alloc(1, &out);
+      if (st == CC_OK) st = cc_reduce_sum(in.buffer, (uint64_t)base->size(), out, nullptr, 0, nullptr);
+      std::string m = st == CC_OK ? "" : cc_last_error();
+      cc_buffer_release(in.buffer);
+      if (st != CC_OK) {
+        if (out) cc_buffer_release(out);
+        throw Error(st, m);
+      }
+      return {out, 0};
     }
-    return {out, 0};
+    {
+      std::lock_guard<std::mutex> lock(plan.mu);
+      if (!plan.kernel) {
+        EmitCtx ctx;
+        resolve_plan(plan, ctx, emit_root(ctx), shape);
+      }
+    }
+    return enqueue_plan(s, plan, shape);
   }
+  uint32_t emit_root(EmitCtx& ctx) const { return ctx.w.reduce(monoid, base->closure(ctx), base->shape); }
 };
 
 // Tensor.join (Tensors.scala:577-598): one kernel over the head shape whose root is Concatenate(elements)
@@ -358,6 +373,10 @@ cc_kernel Tensor::compile_only() const {
   EmitCtx ctx;
   if (auto j = dynamic_cast<const JoinTensor*>(this)) {
     uint32_t root = j->emit_root(ctx);
+    return compile_closure(ctx, root, shape, true, nullptr);
+  }
+  if (auto r = dynamic_cast<const ReduceTensor*>(this)) {
+    uint32_t root = r->emit_root(ctx);
     return compile_closure(ctx, root, shape, true, nullptr);
   }
   uint32_t root = closure(ctx);
@@ -569,11 +588,16 @@ std::vector<TensorPtr> Tensor::split(int dimension) {
   return out;
 }
 
-TensorPtr Tensor::sum() {
-  auto s = make<SumTensor>({}, padding);
+TensorPtr Tensor::reduce(uint32_t monoid) {
+  CC_REQUIRE(monoid == cc::K_PLUS || monoid == cc::K_MIN || monoid == cc::K_MAX || monoid == cc::K_TIMES, CC_ERR_ILLEGAL_ARGUMENT,
+             "reduce needs a monoid: Plus, Min, Max or Times (got %u)", monoid);
+  auto s = make<ReduceTensor>({}, padding);
   s->base = shared_from_this();
+  s->monoid = monoid;
   return s;
 }
+
+TensorPtr Tensor::sum() { return reduce(cc::K_PLUS); }
 
 TensorPtr Tensor::do_cache() {
   Session s;
@@ -759,6 +783,9 @@ int ct_join_dim(const ct_tensor* tensors, int n, int dimension, ct_tensor* out) 
 }
 int ct_sum(ct_tensor t, ct_tensor* out) {
   return guarded([&] { *out = wrap(ref(t)->sum()); });
+}
+int ct_reduce(ct_tensor t, int monoid, ct_tensor* out) {
+  return guarded([&] { *out = wrap(ref(t)->reduce((uint32_t)monoid)); });
 }
 int ct_non_inline(ct_tensor t, ct_tensor* out) {
   return guarded([&] { *out = wrap(ref(t)->non_inline()); });

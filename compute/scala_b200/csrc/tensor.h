@@ -65,6 +65,8 @@ class Tensor : public std::enable_shared_from_this<Tensor> {
   TensorPtr transpose();
   std::vector<TensorPtr> split(int dimension);
   TensorPtr sum();
+  // reduce(MonoidPrograms) (Tensors.scala:308-311, 673-766) for Plus / Min / Max / Times
+  TensorPtr reduce(uint32_t monoid);
   virtual TensorPtr non_inline();
   TensorPtr do_cache();
   TensorPtr transform(const Shape& new_shape, const std::vector<double>& matrix1);

@@ -43,6 +43,7 @@ def _L():
         L.ct_join_dim.argtypes = [hp, C.c_int, C.c_int, hp]
         for n in ("ct_sum", "ct_non_inline", "ct_do_cache"):
             getattr(L, n).argtypes = [h, hp]
+        L.ct_reduce.argtypes = [h, C.c_int, hp]
         L.ct_rank.argtypes = [h, C.POINTER(C.c_int)]
         L.ct_shape.argtypes = [h, ip, C.c_int]
         L.ct_padding.argtypes = [h, fp]
@@ -495,6 +496,18 @@ class Tensor:
         h = u64()
         check(_L().ct_sum(self._h, C.byref(h)))
         return Tensor._wrap(h)
+
+    def reduce(self, monoid: str) -> "Tensor":
+        """reduce(MonoidPrograms) (Tensors.scala:308-311, 673-766): fold the whole tensor with "+", "*", "min" or "max";
+        an inline operand is fused into the fold kernel"""
+        if monoid not in ("+", "*", "min", "max"):
+            raise IllegalArgumentException(-1, f"not a monoid: {monoid!r}")
+        h = u64()
+        check(_L().ct_reduce(self._h, _BINARY[monoid], C.byref(h)))
+        return Tensor._wrap(h)
+
+    def product(self) -> "Tensor":
+        return self.reduce("*")
 
     def nonInline(self) -> "Tensor":
         h = u64()

@@ -129,6 +129,9 @@ int cc_synchronize(void);
  *     5 Concatenate     u32 n, u32 element[n]                                 R:953-973
  *     10 Exp 11 Log 12 Abs 13 Tanh 14 Sqrt 15 UnaryMinus     u32 operand       R:384-470,620-658
  *     20 Min 21 Max 22 Plus 23 Minus 24 Times 25 Div 26 Percent   u32 lhs, u32 rhs   R:472-618
+ *     30 Reduce         u32 monoid (22 Plus | 20 Min | 21 Max | 24 Times), u32 operand, u32 rank, i32 shape[rank]
+ *                       root only, out_shape = []: folds the operand over the index space `shape` (T:303-393, 673-771;
+ *                       lets the backend fuse the operand's closure into the reduction instead of materialising it)
  *
  * cc_compile = cache probe by structure (parameters numbered by first visit, literals / shapes / paddings / matrices
  * part of the key — R:70-91,152-177,336-369) and on a miss: pattern matching (axis reduction / contraction),
@@ -143,7 +146,7 @@ int cc_kernel_retain(cc_kernel k);
 int cc_kernel_release(cc_kernel k);
 
 typedef struct cc_kernel_info_t {
-  int32_t kind;       /* 0 elementwise, 1 axis reduction, 2 contraction (tcgen05), 3 tiled-transpose elementwise */
+  int32_t kind;       /* 0 elementwise, 1 axis reduction, 2 contraction (tcgen05), 3 tiled-transpose elementwise, 4 whole-tensor fold */
   int32_t cache_hit;  /* 1 if this cc_compile call was served from the structural cache */
   int32_t n_args;     /* number of buffers cc_launch expects */
   int32_t n_launches; /* device kernels per cc_launch */
@@ -239,6 +242,9 @@ int ct_split(ct_tensor t, int dimension, ct_tensor* out, int capacity, int* out_
 int ct_join(const ct_tensor* tensors, int n, ct_tensor* out);                                      /* T:577-598 */
 int ct_join_dim(const ct_tensor* tensors, int n, int dimension, ct_tensor* out);                   /* T:560-575 */
 int ct_sum(ct_tensor t, ct_tensor* out);                                                           /* T:771 */
+/* reduce(MonoidPrograms) (T:308-311, 673-766) with monoid = CT_PLUS / CT_MIN / CT_MAX / CT_TIMES. An inline operand's closure
+ * is fused into the fold (one pass, nothing materialised); ct_sum(t) == ct_reduce(t, CT_PLUS). */
+int ct_reduce(ct_tensor t, int monoid, ct_tensor* out);
 int ct_non_inline(ct_tensor t, ct_tensor* out);                                                    /* T:671, 1405-1410 */
 int ct_do_cache(ct_tensor t, ct_tensor* out);                                                      /* T:642-666 */
 int ct_rank(ct_tensor t, int* out);

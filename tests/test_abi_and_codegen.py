@@ -156,6 +156,59 @@ def test_matmul_pattern_is_recognised_through_the_fusion_barrier():
     assert big.info.flops in (2 * 256 * 128 * 256, 2 * 256 * 128 * 256)
 
 
+def matmul1(m1, m2):
+    cols1 = m1.split(1)
+    outs = []
+    for col2 in m2.split(1):
+        terms = [l * r.broadcast(l.shape) for l, r in zip(cols1, col2.split(0))]
+        acc = terms[0]
+        for x in terms[1:]:
+            acc = acc + x
+        outs.append(acc)
+    return T.join(outs)
+
+
+def test_matmul1_join_of_folds_is_rerolled_twice():
+    # benchmarks.scala:176-187: Concatenate over c of left folds over t -> one output dimension + one reduction index
+    k = matmul1(rnd([4096, 32], 1), rnd([32, 32], 2)).compile()
+    assert k.info.kind == 1 and k.info.n_args == 2 and "join of 32 Plus chains of 32 congruent terms" in k.source
+    assert k.info.algorithmic_bytes == 4 * (4096 * 32 + 32 * 32 + 4096 * 32)
+    big = matmul1(rnd([1024, 128], 1), rnd([128, 256], 2)).compile()
+    assert big.info.kind == 2 and big.info.flops == 2 * 1024 * 128 * 256
+    # a join whose chains differ in more than the affine step stays a tuple store of unrolled chains
+    a, b = rnd([64, 8], 1), rnd([8, 2], 2)
+    cols = a.split(1)
+    c0 = [l * r.broadcast(l.shape) for l, r in zip(cols, b.split(1)[0].split(0))]
+    c1 = [l + r.broadcast(l.shape) for l, r in zip(cols, b.split(1)[1].split(0))]
+    f = lambda ts: __import__("functools").reduce(lambda x, y: x + y, ts)
+    assert T.join([f(c0), f(c1)]).compile().info.kind == 0
+
+
+def test_contraction_accepts_any_shape_and_skips_tiny_products():
+    assert matmul2(rnd([1000, 300], 1), rnd([300, 700], 2)).compile().info.kind == 2
+    assert matmul2(rnd([1029, 33], 1), rnd([33, 2000], 2)).compile().info.kind == 2
+    assert matmul2(rnd([48, 40], 1), rnd([40, 24], 2)).compile().info.kind == 1      # tiny: one generic launch beats three
+    assert matmul2(rnd([65536, 32], 1), rnd([32, 16], 2)).compile().info.kind == 1   # skinny N: HBM-bound, no workspace traffic
+
+
+def test_whole_tensor_fold_fuses_the_operand():
+    a, b, c = rnd([1024, 1024], 1), rnd([1024, 1024], 2), rnd([1024, 1024], 3)
+    k = T.tanh(a * b + c).sum().compile()
+    assert k.info.kind == 4 and k.info.n_args == 3 and k.info.n_launches == 1
+    assert k.info.algorithmic_bytes == 12 * 1024 * 1024 + 4
+    src = k.source
+    assert "monoid=cc_plus V=4 U=4 flat=1" in src and "cc_fold_finish<M>" in src and "cc_tanh" in src
+    assert "monoid=cc_max" in rnd([5, 7, 3]).translate([1, 0, -1]).reduce("max").compile().source
+    assert "monoid=cc_times" in rnd([8]).product().compile().source
+    with pytest.raises(ValueError):
+        rnd([8]).reduce("/")
+    # Reduce is a root-only node
+    L = cuda._L()
+    h = C.c_uint64()
+    blob = struct.pack("<4I", 0x31544343, 3, 2, 0) + struct.pack("<If", 1, 1.0) + struct.pack("<4I", 30, 22, 0, 0) + struct.pack("<2I", 15, 1)
+    assert L.cc_compile(blob, len(blob), C.byref(h)) == -6
+
+
 def test_join_is_rerolled_into_an_output_dimension():
     t = rnd([16, 8, 32])
     k = T.join(t.split(1)).compile()

@@ -42,6 +42,35 @@ def test_exact_on_small_integers(cuda, m, n, k):
     assert np.array_equal(got, want)
 
 
+# ragged shapes: M / N edges are TMA out-of-bounds zero fill in + predicated stores out, K is zero-padded in the workspace;
+# the tile width (256 / 128 / 64) is picked per problem, so these also cover every instantiation of the pipeline
+@pytest.mark.parametrize("m,n,k", [(1, 1, 1), (5, 7, 9), (127, 255, 31), (129, 257, 33), (200, 100, 50), (1000, 1000, 1000), (333, 64, 70),
+                                   (2048, 96, 40), (77, 1030, 129), (4096, 32, 32), (130, 66, 2051), (19000, 130, 64)])
+def test_exact_on_small_integers_any_shape(cuda, m, n, k):
+    rng = np.random.default_rng(m * 7 + n * 3 + k)
+    a = rng.integers(-4, 5, (m, k)).astype(np.float32)
+    b = rng.integers(-4, 5, (k, n)).astype(np.float32)
+    got = run_matmul(cuda, a, b)
+    want = (a.astype(np.float64) @ b.astype(np.float64)).astype(np.float32)
+    assert np.array_equal(got, want)
+
+
+def test_ragged_edges_do_not_write_outside_the_result(cuda):
+    m, n, k = 130, 70, 33
+    rng = np.random.default_rng(1)
+    a = rng.integers(-4, 5, (m, k)).astype(np.float32)
+    b = rng.integers(-4, 5, (k, n)).astype(np.float32)
+    guard = 4096
+    A, B = cuda.Buffer.from_host(a), cuda.Buffer.from_host(b)
+    C = cuda.Buffer.from_host(np.full(m * n + guard, -777.0, np.float32))
+    cuda.matmul_3xtf32(A, B, C, m, n, k)
+    out = C.to_host(m * n + guard)
+    assert np.array_equal(out[: m * n].reshape(m, n), (a.astype(np.float64) @ b.astype(np.float64)).astype(np.float32))
+    assert (out[m * n:] == -777.0).all()
+    for x in (A, B, C):
+        x.release()
+
+
 def test_layout_is_not_symmetric(cuda):
     """catches transposed / swizzle-permuted operands that a random-sign test could hide"""
     m, n, k = 128, 256, 64
@@ -90,6 +119,49 @@ def test_pattern_lowers_to_tcgen05(cuda):
     assert kern.info.kind == 2 and kern.info.n_args == 2 and kern.info.flops == 2 * m * n * k
     got = acc.flatArray().reshape(m, n)
     assert np.array_equal(got, (a.astype(np.float64) @ b.astype(np.float64)).astype(np.float32))
+
+
+def matmul1(T, m1, m2):
+    """benchmarks.scala:176-187 / README.md:312-329: join over the columns of m2 of left folds over the inner dimension"""
+    cols1 = m1.split(1)
+    outs = []
+    for col2 in m2.split(1):
+        terms = [l * r.broadcast(l.shape) for l, r in zip(cols1, col2.split(0))]
+        acc = terms[0]
+        for x in terms[1:]:
+            acc = acc + x
+        outs.append(acc)
+    return T.join(outs)
+
+
+@pytest.mark.parametrize("m,k,n,kind", [(1024, 128, 256, 2), (4096, 32, 32, 1), (300, 40, 36, 1), (64, 4, 8, 0)])
+def test_matmul1_join_of_folds_is_rerolled(cuda, m, k, n, kind):
+    T = cuda.Tensor
+    rng = np.random.default_rng(m + k + n)
+    a = rng.integers(-4, 5, (m, k)).astype(np.float32)
+    b = rng.integers(-4, 5, (k, n)).astype(np.float32)
+    e = matmul1(T, T(a), T(b))
+    kern = e.compile()
+    assert kern.info.kind == kind, kern.source[:300]
+    assert kern.info.n_args == 2
+    got = e.flatArray().reshape(m, n)
+    assert np.array_equal(got, (a.astype(np.float64) @ b.astype(np.float64)).astype(np.float32))
+
+
+def test_pattern_with_ragged_shape_runs_on_the_tensor_cores(cuda):
+    T = cuda.Tensor
+    m, k, n = 1000, 300, 700
+    a = finite_normal(m * k, 9).reshape(m, k)
+    b = finite_normal(k * n, 10).reshape(k, n)
+    product = T(a).broadcast([m, k, n]) * T(b).reshape([1, k, n]).broadcast([m, k, n])
+    parts = product.split(1)
+    acc = parts[0]
+    for p in parts[1:]:
+        acc = acc + p
+    assert acc.compile().info.kind == 2
+    got = acc.flatArray().reshape(m, n).astype(np.float64)
+    scale = np.abs(a.astype(np.float64)) @ np.abs(b.astype(np.float64))
+    assert (np.abs(got - a.astype(np.float64) @ b.astype(np.float64)) / scale).max() <= 5e-6
 
 
 def test_full_size_8192_rows_sampled(cuda):

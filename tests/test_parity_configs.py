@@ -173,6 +173,60 @@ def test_c3_full_sum(cuda, n):
     assert abs(got_u - truth) <= 1e-5 * abs(truth), (got_u, truth, ref_order)
 
 
+@pytest.mark.parametrize("shape", [(512, 1024), (1000, 36), (7, 9, 5), (3,), ()])
+def test_fused_sum_equals_materialise_then_sum(cuda, shape):
+    """SURVEY 8f-4: `expr.sum` folds the closure of an inline operand inside the reduction kernel (one pass, no intermediate);
+    the reference materialises first (Tensors.scala:678). Same fold order => same bits as the two-step sequence."""
+    T = cuda.Tensor
+    shape = list(shape)
+    a, b, c = (T.random(shape, seed=s).doCache() for s in (1, 2, 3))
+    expr = T.tanh(a * b + c)
+    k = expr.sum().compile()
+    assert k.info.kind == 4 and k.info.n_args == 3 and k.info.n_launches == 1
+    n = int(np.prod(shape)) if shape else 1
+    assert k.info.algorithmic_bytes == 12 * n + 4
+    s0 = cuda.stats()
+    fused = expr.sum().flatArray()[0]
+    s1 = cuda.stats()
+    assert s1["device_kernels"] - s0["device_kernels"] == 1  # one kernel: loads, chain and fold
+    two_step = expr.doCache().sum().flatArray()[0]
+    if n % 4 == 0 and shape and shape[-1] % 4 == 0:
+        assert fused.view(np.uint32) == two_step.view(np.uint32)
+    want = ref.Tensor.tanh(ref.Tensor.random(shape, seed=1) * ref.Tensor.random(shape, seed=2) + ref.Tensor.random(shape, seed=3)).flat_array()
+    truth = float(want.astype(np.float64).sum())
+    assert abs(float(fused) - truth) <= 1e-5 * abs(truth)
+    assert abs(float(two_step) - truth) <= 1e-5 * abs(truth)
+    # exactly summable data: bit-exact in any order
+    e = dataset_e(T, shape)
+    assert e.sum().flatArray()[0] == np.float32(dataset_e_np(n).astype(np.int64).sum())
+
+
+def test_other_monoids_and_views_inside_the_fold(cuda):
+    """MonoidPrograms is generic over append / zero (Tensors.scala:308-311); only Plus is instantiated by the reference"""
+    T = cuda.Tensor
+    shape = [37, 50]
+    x = ref.random_buffer(37 * 50, 11).reshape(shape)
+    t = T.random(shape, seed=11).doCache()
+    assert t.reduce("min").flatArray()[0] == x.min()
+    assert t.reduce("max").flatArray()[0] == x.max()
+    assert (t * T.fill(2.0, shape)).reduce("max").flatArray()[0] == (x * np.float32(2.0)).max()
+    small = T.random([10, 12], seed=4) + T.fill(0.5, [10, 12])
+    want = np.prod((ref.random_buffer(120, 4) + np.float32(0.5)).astype(np.float64))
+    assert abs(float(small.product().flatArray()[0]) - want) <= 1e-5 * abs(want)
+    # a view with padding inside the fold: translate pulls in the padding value (here 2.0) on the shifted border
+    p = T.random([16, 24], seed=6, padding=2.0).doCache()
+    v = p.translate([3, -5])
+    want_v = ref.Tensor.random([16, 24], seed=6, padding=2.0).translate([3, -5]).flat_array()
+    got = v.sum().flatArray()[0]
+    assert abs(float(got) - float(want_v.astype(np.float64).sum())) <= 1e-5 * float(want_v.astype(np.float64).sum())
+    assert v.reduce("max").flatArray()[0] == 2.0 and v.reduce("min").flatArray()[0] == want_v.min()
+    # permuted operand (non-flat index decode) on exactly summable data
+    e = dataset_e(T, [24, 32, 8]).doCache()
+    assert e.permute([2, 0, 1]).sum().flatArray()[0] == np.float32(dataset_e_np(24 * 32 * 8).astype(np.int64).sum())
+    with pytest.raises(ValueError):
+        t.reduce("-")
+
+
 def axis_sum(T, x, axis):
     parts = x.split(axis)
     acc = parts[0]
