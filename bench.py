@@ -128,7 +128,7 @@ def run_reference(args, rank: int):
         "cpu_baseline": {"value": gbs, "unit": "GB/s", "cores": cores, "kind": "port", "sample": f"2^26 of 2^28 elements per step, {len(times)} steps"},
         "e2e": {"value": gbs, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ---- cuda arm ---------------------------------------------------------------------------------------------------------------------
@@ -210,10 +210,19 @@ def side_configs(cuda, hbm_peak: float, tf_peak: float) -> dict:
         def step():
             cuda.matmul_3xtf32(ab, bb, c5, n5, n5, n5)
 
+        # both operands fresh every step (hi/lo split of A and of B inside the timed region) ...
+        cuda.set_operand_cache(False)
         ms, launches, _, _ = time_steps(cuda, step, 5, 2)
         per = ms / 5
         tf = 2 * n5**3 / per / 1e9
         out["C5 matmul 8192^3 (3xTF32 tcgen05)"] = {"ms": per, "tflops": tf, "frac_of_3xtf32_peak": tf / tf_peak, "kernels_per_step": launches / 5}
+        # ... and with B unchanged between steps (weights): its panels are split once and kept by the runtime
+        cuda.set_operand_cache(True)
+        ms, launches, _, _ = time_steps(cuda, step, 5, 2)
+        per = ms / 5
+        tf = 2 * n5**3 / per / 1e9
+        out["C5 matmul 8192^3, B unchanged between steps (panels cached)"] = {"ms": per, "tflops": tf, "frac_of_3xtf32_peak": tf / tf_peak,
+                                                                             "kernels_per_step": launches / 5}
         ab.release(), bb.release(), c5.release()
     except Exception as e:
         out["C5 matmul 8192^3 (3xTF32 tcgen05)"] = {"error": str(e)[:200]}
@@ -274,7 +283,7 @@ def sharded_configs(cuda, dist, rank: int, world: int, hbm_peak: float, tf_peak:
     del x, col_sums, row_sums
     n5 = 8192
     m5 = sharding.shard_rows(n5, world, rank)[1]
-    if m5 % 128 == 0:
+    if m5 > 0:
         A = T.randomNormal([m5, n5], seed=9 + 16 * rank).doCache()
         B = T.randomNormal([n5, n5], seed=10).doCache()
         ab, bb = A.doBuffer(), B.doBuffer()
@@ -428,13 +437,29 @@ def run_cuda(args, rank: int, local_rank: int, world: int):
         if rank == 0:
             line["configs"] = sc
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
     if dist:
         dist.barrier()
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def emit(line: dict) -> None:
+    """the ONE JSON line of the contract, on the process' real stdout"""
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    # Libraries underneath (NCCL prints its version banner on stdout when the box sets NCCL_DEBUG) must not add lines to stdout:
+    # everything written to fd 1 from here on goes to stderr, and only emit() writes to the real stdout.
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)

@@ -57,8 +57,10 @@ typedef CUresult (*TensorMapEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint3
                                       const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                       CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 // C[M,N] = A[M,K] * B[K,N], fp32 row-major, 3xTF32 on tcgen05, any M, N, K >= 1 (ragged edges: TMA zero fill in, predicated
-// stores out; K is zero-padded inside the workspace). Returns the number of device kernels launched; throws cc::Error.
+// stores out; K is zero-padded inside the workspace). `b_panels_ready`: ws.bt_hi / ws.bt_lo already hold the split of this B
+// (the runtime keeps them while B is unchanged), so only A is split. Returns the number of device kernels launched; throws.
 int launch_gemm_3xtf32(const float* a, const float* b, float* c, int64_t m, int64_t n, int64_t k,
-                       const GemmWorkspace& ws, int sm_count, TensorMapEncodeFn encode, cudaStream_t stream);
+                       const GemmWorkspace& ws, int sm_count, TensorMapEncodeFn encode, cudaStream_t stream,
+                       bool b_panels_ready = false);
 
 }  // namespace cc

@@ -60,6 +60,7 @@ struct Load {
   int64_t base = 0;
   std::vector<char> need_lo, need_hi;  // per source dim
   int64_t max_abs_off = 0;
+  bool reuse = false;  // some index dimension does not move the address: the same element is read from many index points
   bool any_check() const {
     for (size_t i = 0; i < need_lo.size(); ++i)
       if (need_lo[i] || need_hi[i]) return true;
@@ -74,11 +75,19 @@ struct Op {
   int load = -1;
 };
 
+constexpr uint32_t K_ACC = 0xACC;  // pseudo-op of the epilogue: the value the reduction produced for this output element
+
 struct Program {
-  std::vector<int64_t> dims;  // index space (output dims, then the re-rolled index t if any)
-  std::vector<Op> ops;
+  std::vector<int64_t> dims;  // index space: output dims, then the re-rolled reduction indices (outermost first) if any
+  std::vector<Op> ops;        // the term (evaluated for every point of the index space)
   std::vector<Load> loads;
   std::vector<int> results;
+  // reductions only
+  int n_red = 0;              // number of trailing reduction dims
+  std::vector<Op> post_ops;   // epilogue applied once per output element to the folded value (K_ACC); may use loads
+  int post_result = -1;
+  std::vector<char> load_in_post;  // per load: referenced by the epilogue (1) or by the term (0)
+  bool trivial_post() const { return post_ops.size() == 1 && post_ops[0].kind == K_ACC; }
 };
 
 int64_t product(const std::vector<int64_t>& v) {
@@ -134,6 +143,8 @@ void analyze_load(Load& L, const std::vector<int64_t>& dims) {
     }
     // row indices themselves are bounded by the same expression with stride 1
     L.max_abs_off = mx;
+    for (int x = 0; x < nd; ++x)
+      if (dims[x] > 1 && L.coef[x] == 0) L.reuse = true;
   }
 }
 
@@ -149,6 +160,21 @@ struct Builder {
   std::unordered_map<uint32_t, int> memo;                       // node -> op index (ExportContext, R:220)
   std::map<uint32_t, int>* arg_of_param;                        // param node -> plan arg (shared across programs)
   std::vector<uint32_t>* arg_nodes;
+  bool in_post = false;                                         // exporting the epilogue of a reduction (prog.post_ops)
+
+  std::vector<Op>& target() { return in_post ? prog.post_ops : prog.ops; }
+  int push(const Op& op) {
+    target().push_back(op);
+    return (int)target().size() - 1;
+  }
+  // switch to the epilogue: `acc_node` (the top of the re-rolled chain) becomes the folded value
+  void begin_post(uint32_t acc_node) {
+    in_post = true;
+    memo.clear();
+    Op op;
+    op.kind = K_ACC;
+    memo[acc_node] = push(op);
+  }
 
   int arg_for(uint32_t param_node) {
     auto it = arg_of_param->find(param_node);
@@ -194,6 +220,7 @@ struct Builder {
     }
     analyze_load(L, prog.dims);
     prog.loads.push_back(std::move(L));
+    prog.load_in_post.push_back(in_post ? 1 : 0);
     return (int)prog.loads.size() - 1;
   }
 
@@ -209,14 +236,12 @@ struct Builder {
         Op op;
         op.kind = K_LITERAL;
         op.lit = nd.value;
-        prog.ops.push_back(op);
-        memo[i] = (int)prog.ops.size() - 1;
+        memo[i] = push(op);
       } else if (nd.kind == K_EXTRACT) {
         Op op;
         op.kind = K_EXTRACT;
         op.load = make_load(i);
-        prog.ops.push_back(op);
-        memo[i] = (int)prog.ops.size() - 1;
+        memo[i] = push(op);
       } else if (is_unary(nd.kind) || is_binary(nd.kind)) {
         if (!ready) {
           stack.push_back({i, true});
@@ -227,8 +252,7 @@ struct Builder {
           op.kind = nd.kind;
           op.a = memo.at(nd.kids[0]);
           if (nd.kids.size() > 1) op.b = memo.at(nd.kids[1]);
-          prog.ops.push_back(op);
-          memo[i] = (int)prog.ops.size() - 1;
+          memo[i] = push(op);
         }
       } else {
         fail(CC_ERR_BAD_TREE, strprintf("%s is only allowed at the root of a tree", kind_name(nd.kind)));
@@ -242,8 +266,10 @@ struct Builder {
 
 // Are subtrees a and b the same expression up to the constant column of their Transforms? Records const(b) - const(a)
 // per Transform node of a.
-bool congruent(const Tree& t, uint32_t a0, uint32_t b0, std::unordered_map<uint32_t, std::vector<double>>& delta) {
-  std::unordered_map<uint32_t, uint32_t> seen;
+bool congruent(const Tree& t, uint32_t a0, uint32_t b0, std::unordered_map<uint32_t, std::vector<double>>& delta,
+               std::unordered_map<uint32_t, uint32_t>* node_map = nullptr) {
+  std::unordered_map<uint32_t, uint32_t> local_seen;
+  std::unordered_map<uint32_t, uint32_t>& seen = node_map ? *node_map : local_seen;
   std::vector<std::pair<uint32_t, uint32_t>> stack{{a0, b0}};
   while (!stack.empty()) {
     auto [a, b] = stack.back();
@@ -321,38 +347,159 @@ std::vector<uint32_t> plus_chain(const Tree& t, uint32_t root) {
 
 constexpr size_t kMinRerollTerms = 8;  // shorter chains stay unrolled in one elementwise kernel, as the reference runs them
 
-// Concatenate of C left folds of T terms each, term(c, t) congruent to term(0, 0) with Transform constants
-// const(0,0) + c * step_c + t * step_t. Fills the steps (keyed by the Transform nodes of term(0,0)) and the terms of chain 0.
-bool reroll_join_of_folds(const Tree& t, const std::vector<uint32_t>& kids, StepMap& step_c, StepMap& step_t, std::vector<uint32_t>& terms0) {
-  if (kids.size() < 2) return false;
-  std::vector<std::vector<uint32_t>> terms;
-  for (uint32_t k : kids) {
-    if (t.nodes[k].kind != K_PLUS) return false;
-    terms.push_back(plus_chain(t, k));
-    if (terms.back().size() != terms[0].size()) return false;
+// A re-rolled reduction found inside an expression: `top` is the root of a left-leaning Plus chain whose terms are all
+// congruent to terms[0], with Transform constants affine in a multi-index over `levels` (outermost first):
+//   const(term i) = const(term 0) + sum_j digit_j(i) * steps[j]      (i = ((d_0 * n_1 + d_1) * n_2 + d_2) ...)
+// One level is the plain per-axis sum / matmul pattern (README.md:301-343); three levels is the convolution of
+// benchmarks.scala:526-545 (kernel row, kernel column, input channel).
+struct Chain {
+  uint32_t top = 0;
+  std::vector<uint32_t> terms;
+  std::vector<int64_t> levels;
+  std::vector<StepMap> steps;  // keyed by the Transform nodes of terms[0]
+};
+
+bool nested_reroll(const Tree& t, Chain& ch) {
+  const size_t n = ch.terms.size();
+  if (n < 2) return false;
+  std::vector<StepMap> D(n);
+  std::vector<uint32_t> keys;
+  for (size_t i = 1; i < n; ++i) {
+    if (!congruent(t, ch.terms[0], ch.terms[i], D[i])) return false;
+    if (i == 1)
+      for (auto& kv : D[1]) keys.push_back(kv.first);
+    else if (D[i].size() != keys.size())
+      return false;
   }
-  const size_t T = terms[0].size();
-  if (T < kMinRerollTerms) return false;
-  if (!reroll(t, terms[0], step_t)) return false;
-  std::vector<uint32_t> heads;
-  for (auto& ch : terms) heads.push_back(ch[0]);
-  {
-    // the step over c may be all-zero for some transforms but must exist; reroll() insists on a non-zero step somewhere
-    if (!reroll(t, heads, step_c)) return false;
+  std::sort(keys.begin(), keys.end());
+  size_t width = 0;
+  for (uint32_t k : keys) width += D[1].at(k).size();
+  std::vector<std::vector<double>> F(n, std::vector<double>(width, 0.0));  // flattened deltas, F[0] = 0
+  for (size_t i = 1; i < n; ++i) {
+    size_t o = 0;
+    for (uint32_t k : keys) {
+      auto it = D[i].find(k);
+      if (it == D[i].end()) return false;
+      for (double v : it->second) F[i][o++] = v;
+    }
   }
-  if (step_c.size() != step_t.size()) return false;
-  for (size_t c = 1; c < terms.size(); ++c)
-    for (size_t i = 1; i < T; ++i) {
-      StepMap d;
-      if (!congruent(t, terms[0][0], terms[c][i], d) || d.size() != step_t.size()) return false;
-      for (auto& kv : d) {
-        auto ic = step_c.find(kv.first), it = step_t.find(kv.first);
-        if (ic == step_c.end() || it == step_t.end()) return false;
-        for (size_t y = 0; y < kv.second.size(); ++y)
-          if (kv.second[y] != (double)c * ic->second[y] + (double)i * it->second[y]) return false;
+  auto is_multiple = [&](const std::vector<double>& x, const std::vector<double>& step, double q) {
+    for (size_t j = 0; j < width; ++j)
+      if (x[j] != q * step[j]) return false;
+    return true;
+  };
+  std::vector<int64_t> levels;               // innermost first while building
+  std::vector<std::vector<double>> fsteps;
+  size_t stride = 1;
+  while (stride < n) {
+    const size_t count = n / stride;
+    const std::vector<double>& step = F[stride];
+    size_t m = count;
+    for (size_t q = 1; q < count; ++q)
+      if (!is_multiple(F[q * stride], step, (double)q)) {
+        m = q;
+        break;
+      }
+    if (m < 2 || count % m != 0) return false;
+    levels.push_back((int64_t)m);
+    fsteps.push_back(step);
+    stride *= m;
+    if (levels.size() > 6) return false;
+  }
+  bool any = false;
+  for (auto& st : fsteps)
+    for (double v : st)
+      if (v != 0.0) any = true;
+  if (!any) return false;
+  // every term must satisfy the digit formula
+  for (size_t i = 1; i < n; ++i) {
+    size_t rem = i;
+    std::vector<double> want(width, 0.0);
+    for (size_t j = 0; j < levels.size(); ++j) {
+      const double digit = (double)(rem % (size_t)levels[j]);
+      rem /= (size_t)levels[j];
+      for (size_t x = 0; x < width; ++x) want[x] += digit * fsteps[j][x];
+    }
+    if (want != F[i]) return false;
+  }
+  ch.levels.assign(levels.rbegin(), levels.rend());
+  ch.steps.clear();
+  for (size_t j = levels.size(); j-- > 0;) {
+    StepMap sm;
+    size_t o = 0;
+    for (uint32_t k : keys) {
+      const size_t rows = D[1].at(k).size();
+      sm[k] = std::vector<double>(fsteps[j].begin() + (long)o, fsteps[j].begin() + (long)(o + rows));
+      o += rows;
+    }
+    ch.steps.push_back(std::move(sm));
+  }
+  return true;
+}
+
+// Finds the longest re-rollable Plus chain inside the float term `root` (searching through unary / binary nodes only).
+bool find_chain(const Tree& t, uint32_t root, Chain& best) {
+  std::vector<uint32_t> tops;
+  std::unordered_map<uint32_t, char> seen;
+  std::vector<uint32_t> stack{root};
+  while (!stack.empty()) {
+    uint32_t i = stack.back();
+    stack.pop_back();
+    if (seen.count(i)) continue;
+    seen[i] = 1;
+    const Node& nd = t.nodes[i];
+    if (nd.kind == K_PLUS) {
+      std::vector<uint32_t> terms = plus_chain(t, i);
+      if (terms.size() >= kMinRerollTerms) tops.push_back(i);
+      for (uint32_t term : terms) stack.push_back(term);  // the chain's own Plus nodes are not candidates
+    } else if (is_unary(nd.kind) || is_binary(nd.kind)) {
+      for (uint32_t k : nd.kids) stack.push_back(k);
+    }
+  }
+  size_t best_len = 0;
+  for (uint32_t top : tops) {
+    Chain c;
+    c.top = top;
+    c.terms = plus_chain(t, top);
+    if (c.terms.size() <= best_len) continue;
+    if (!nested_reroll(t, c)) continue;
+    best_len = c.terms.size();
+    best = std::move(c);
+  }
+  if (best_len == 0) return false;
+  // the epilogue (root with the chain replaced by its folded value) must not reach the Transforms the reduction steps apply to
+  if (root != best.top) {
+    std::unordered_map<uint32_t, char> s2;
+    std::vector<uint32_t> st{root};
+    while (!st.empty()) {
+      uint32_t i = st.back();
+      st.pop_back();
+      if (i == best.top || s2.count(i)) continue;
+      s2[i] = 1;
+      const Node& nd = t.nodes[i];
+      if (nd.kind == K_EXTRACT) {
+        if (best.steps[0].count(nd.kids[0])) return false;
+      } else {
+        for (uint32_t k : nd.kids) st.push_back(k);
       }
     }
-  terms0 = terms[0];
+  }
+  return true;
+}
+
+// When a join (Concatenate) has been re-rolled over its element index c, the reduction found in element 0 is also the
+// reduction of every other element only if the step over c is the same for corresponding Transforms of every term.
+bool join_step_uniform_over_terms(const Tree& t, const Chain& ch, const StepMap& step_c) {
+  for (size_t i = 1; i < ch.terms.size(); ++i) {
+    StepMap d;
+    std::unordered_map<uint32_t, uint32_t> node_map;
+    if (!congruent(t, ch.terms[0], ch.terms[i], d, &node_map)) return false;
+    for (auto& kv : d) {
+      auto a = step_c.find(kv.first);
+      auto b = step_c.find(node_map.at(kv.first));
+      if (a == step_c.end() || b == step_c.end() || a->second != b->second) return false;
+    }
+  }
   return true;
 }
 
@@ -407,6 +554,25 @@ const char* op_expr(uint32_t kind) {
 }
 
 // Emits the SSA body of the program for one lane; value names are _<op>; loads read `ldname(j)` .
+void emit_op_list(Emit& e, const std::vector<Op>& ops, const char* indent, const std::string& lane, const char* prefix = "_",
+                  const char* acc = nullptr) {
+  for (size_t i = 0; i < ops.size(); ++i) {
+    const Op& op = ops[i];
+    if (op.kind == K_ACC) {
+      e("%sconst float %s%zu = %s;\n", indent, prefix, i, acc);
+    } else if (op.kind == K_LITERAL) {
+      e("%sconst float %s%zu = %s;\n", indent, prefix, i, flit(op.lit).c_str());
+    } else if (op.kind == K_EXTRACT) {
+      e("%sconst float %s%zu = L%d[%s];\n", indent, prefix, i, op.load, lane.c_str());
+    } else {
+      std::string a = strprintf("%s%d", prefix, op.a), b = strprintf("%s%d", prefix, op.b);
+      std::string fmt = op_expr(op.kind);
+      std::string ex = is_unary(op.kind) ? strprintf(fmt.c_str(), a.c_str()) : strprintf(fmt.c_str(), a.c_str(), b.c_str());
+      e("%sconst float %s%zu = %s;\n", indent, prefix, i, ex.c_str());
+    }
+  }
+}
+
 void emit_ops(Emit& e, const Program& p, const char* indent, const std::string& lane) {
   for (size_t i = 0; i < p.ops.size(); ++i) {
     const Op& op = p.ops[i];
@@ -471,6 +637,9 @@ void emit_load(Emit& e, const Program& p, int j, const LoadCtx& c, const char* i
   const int nd = (int)p.dims.size();
   const int V = c.V;
   std::string pad = flit(L.padding);
+  // streaming (no L1 allocation) for data read once; cached for data reused across the index space (broadcasts, reductions)
+  const char* LD1 = L.reuse ? "cc_ldc" : "cc_ldg";
+  const char* LD4 = L.reuse ? "cc_ldc4" : "cc_ldg4";
   e("%sfloat L%d[%d];\n", indent, j, V);
   if (!L.integer) {
     // general path: per lane, per row index in the reference's arithmetic
@@ -487,9 +656,9 @@ void emit_load(Emit& e, const Program& p, int j, const LoadCtx& c, const char* i
       off += strprintf(" + i%d * %lldLL", y, (long long)strides[y]);
     }
     if (cond.empty())
-      e("%s  L%d[l] = cc_ldg(p%d + (%s));\n", indent, j, L.arg, off.c_str());
+      e("%s  L%d[l] = %s(p%d + (%s));\n", indent, j, LD1, L.arg, off.c_str());
     else
-      e("%s  L%d[l] = (%s) ? cc_ldg(p%d + (%s)) : %s;\n", indent, j, cond.c_str(), L.arg, off.c_str(), pad.c_str());
+      e("%s  L%d[l] = (%s) ? %s(p%d + (%s)) : %s;\n", indent, j, cond.c_str(), LD1, L.arg, off.c_str(), pad.c_str());
     e("%s}\n", indent);
     return;
   }
@@ -520,24 +689,24 @@ void emit_load(Emit& e, const Program& p, int j, const LoadCtx& c, const char* i
       if (x != c.vdim && L.coef[x] % 4 != 0) aligned = false;
   if (V == 1) {
     if (ucond.empty())
-      e("%sL%d[0] = cc_ldg(p%d + o%d);\n", indent, j, L.arg, j);
+      e("%sL%d[0] = %s(p%d + o%d);\n", indent, j, LD1, L.arg, j);
     else
-      e("%sL%d[0] = (%s) ? cc_ldg(p%d + o%d) : %s;\n", indent, j, ucond.c_str(), L.arg, j, pad.c_str());
+      e("%sL%d[0] = (%s) ? %s(p%d + o%d) : %s;\n", indent, j, ucond.c_str(), LD1, L.arg, j, pad.c_str());
     return;
   }
   if (!lane_checks && aligned) {
     if (ucond.empty())
-      e("%scc_ldg4(p%d + o%d, L%d);\n", indent, L.arg, j, j);
+      e("%s%s(p%d + o%d, L%d);\n", indent, LD4, L.arg, j, j);
     else
-      e("%sif (%s) cc_ldg4(p%d + o%d, L%d); else { L%d[0] = L%d[1] = L%d[2] = L%d[3] = %s; }\n", indent, ucond.c_str(),
+      e("%sif (%s) %s(p%d + o%d, L%d); else { L%d[0] = L%d[1] = L%d[2] = L%d[3] = %s; }\n", indent, ucond.c_str(), LD4,
         L.arg, j, j, j, j, j, j, pad.c_str());
     return;
   }
   if (!lane_checks && coefV == 0) {
     if (ucond.empty())
-      e("%sL%d[0] = cc_ldg(p%d + o%d);\n", indent, j, L.arg, j);
+      e("%sL%d[0] = %s(p%d + o%d);\n", indent, j, LD1, L.arg, j);
     else
-      e("%sL%d[0] = (%s) ? cc_ldg(p%d + o%d) : %s;\n", indent, j, ucond.c_str(), L.arg, j, pad.c_str());
+      e("%sL%d[0] = (%s) ? %s(p%d + o%d) : %s;\n", indent, j, ucond.c_str(), LD1, L.arg, j, pad.c_str());
     e("%sL%d[1] = L%d[2] = L%d[3] = L%d[0];\n", indent, j, j, j, j);
     return;
   }
@@ -553,9 +722,9 @@ void emit_load(Emit& e, const Program& p, int j, const LoadCtx& c, const char* i
     if (L.need_hi[y]) cond += strprintf("%sk%d < %lld", cond.empty() ? "" : " && ", y, (long long)L.src_shape[y]);
   }
   if (cond.empty())
-    e("%s  L%d[l] = cc_ldg(p%d + o%d + (%s)%lld * l);\n", indent, j, L.arg, j, c.idx_type, (long long)coefV);
+    e("%s  L%d[l] = %s(p%d + o%d + (%s)%lld * l);\n", indent, j, LD1, L.arg, j, c.idx_type, (long long)coefV);
   else
-    e("%s  L%d[l] = (%s) ? cc_ldg(p%d + o%d + (%s)%lld * l) : %s;\n", indent, j, cond.c_str(), L.arg, j, c.idx_type,
+    e("%s  L%d[l] = (%s) ? %s(p%d + o%d + (%s)%lld * l) : %s;\n", indent, j, cond.c_str(), LD1, L.arg, j, c.idx_type,
       (long long)coefV, pad.c_str());
   e("%s}\n", indent);
 }
@@ -817,23 +986,60 @@ void emit_tiled_transpose(Plan& plan, const Program& p, int n_args, const Device
 // ---- reductions over the re-rolled index --------------------------------------------------------------------------
 
 // out[g] = sum_t E(g, t).  dims = out dims + [T].
+// out[g] = post(sum_t E(g, t)).  dims = out dims + the reduction dims (n_red of them, outermost first; t runs over their
+// product in row-major order, which is the reference's left-to-right order of the chain).
 void emit_reduce(Plan& plan, const Program& p, int n_args, const DeviceProps& dev) {
   const int nd = (int)p.dims.size();
-  const int no = nd - 1;
-  const int64_t T = p.dims[nd - 1];
-  std::vector<int64_t> odims(p.dims.begin(), p.dims.end() - 1);
+  const int R = std::max(1, p.n_red);
+  const int no = nd - R;
+  std::vector<int64_t> odims(p.dims.begin(), p.dims.begin() + no);
+  std::vector<int64_t> rdims(p.dims.begin() + no, p.dims.end());
+  const int64_t T = product(rdims);
   const int64_t NOUT = product(odims);
-  const char* IDX = pick_idx_type(p, NOUT * T);
+  const char* IDX = pick_idx_type(p, std::max(NOUT, T));  // indices are output positions, reduction positions and source offsets
   const int nloads = (int)p.loads.size();
+  const bool has_post = !p.post_ops.empty() && !p.trivial_post();
+  auto in_post = [&](int j) { return j < (int)p.load_in_post.size() && p.load_in_post[j]; };
   // choose the orientation: which index do neighbouring threads walk?
   bool any_t_contig = false, any_o_contig = false;
-  for (const Load& L : p.loads) {
-    if (!L.integer) continue;
+  for (int j = 0; j < nloads; ++j) {
+    const Load& L = p.loads[j];
+    if (!L.integer || in_post(j)) continue;
     if (std::llabs(L.coef[nd - 1]) == 1) any_t_contig = true;
     if (no >= 1 && std::llabs(L.coef[no - 1]) == 1) any_o_contig = true;
   }
   const bool rows = (any_t_contig && !any_o_contig) || no == 0 || NOUT < 64;
+  std::string gs;  // ", g0, g1, ..." over the output dims
+  for (int x = 0; x < no; ++x) gs += strprintf(", g%d", x);
+  const std::string pass = (n_args ? ", " : "") + arg_pass(n_args);
+  const std::string params = (n_args ? ", " : "") + param_list(n_args, false);
   Emit e;
+  // decode of the flat reduction index into its digits g{no}..g{nd-1}
+  auto emit_t_decode = [&](const char* src) {
+    if (R == 1) {
+      e("  const %s g%d = %s;\n", IDX, no, src);
+      return;
+    }
+    e("  %s tr_ = %s;\n", IDX, src);
+    for (int x = nd - 1; x > no; --x)
+      e("  const %s g%d = tr_ %% (%s)%lld; tr_ /= (%s)%lld;\n", IDX, x, IDX, (long long)p.dims[x], IDX, (long long)p.dims[x]);
+    e("  const %s g%d = tr_;\n", IDX, no);
+  };
+  // epilogue: acc[V] -> final values, in place
+  auto emit_post_fn = [&](int V, int vdim) {
+    if (!has_post) return;
+    e("__device__ __forceinline__ void post(float (&acc)[%d]", V);
+    for (int x = 0; x < no; ++x) e(", const %s g%d", IDX, x);
+    e("%s) {\n", params.c_str());
+    LoadCtx c{V, vdim, IDX};
+    for (int j = 0; j < nloads; ++j)
+      if (in_post(j)) emit_load(e, p, j, c, "  ");
+    e("  #pragma unroll\n  for (int l = 0; l < %d; ++l) {\n", V);
+    emit_op_list(e, p.post_ops, "    ", "l", "q", "acc[l]");
+    e("    acc[l] = q%d;\n  }\n}\n", p.post_result);
+  };
+  std::string rd;
+  for (int x = 0; x < R; ++x) rd += strprintf("%s%lld", x ? "x" : "", (long long)rdims[x]);
   if (!rows) {
     // --- column owner: a thread owns V adjacent outputs and walks t; T is split over blockIdx.y ----------------------
     const int V = (odims[no - 1] % 4 == 0) ? 4 : 1;
@@ -841,29 +1047,64 @@ void emit_reduce(Plan& plan, const Program& p, int n_args, const DeviceProps& de
     int64_t want = ((int64_t)dev.sm_count * 2048 * 2 + NV - 1) / NV;
     int64_t S = std::max<int64_t>(1, std::min<int64_t>(want, T / 32));
     S = std::min<int64_t>(S, 1024);
+    if (NV * 2 >= (int64_t)dev.sm_count * 2048) S = 1;  // the outputs alone fill the machine: no partials round trip
     const int64_t TCH = (T + S - 1) / S;
     S = (T + TCH - 1) / TCH;
     e("// axis reduction (column owner): out dims=[");
     for (int x = 0; x < no; ++x) e("%s%lld", x ? "," : "", (long long)odims[x]);
-    e("] T=%lld V=%d splits=%lld chunk=%lld idx=%s\n", (long long)T, V, (long long)S, (long long)TCH, IDX);
-    e("__device__ __forceinline__ void ev(const %s g%d", IDX, nd - 1);
+    e("] T=%s V=%d splits=%lld chunk=%lld idx=%s epilogue=%d\n", rd.c_str(), V, (long long)S, (long long)TCH, IDX, (int)has_post);
+    // evd: the term at explicit reduction digits; ev: the same from the flat reduction index (used when T is split)
+    std::string rgs, rgdecl;
+    for (int x = no; x < nd; ++x) {
+      rgs += strprintf("%sg%d", x > no ? ", " : "", x);
+      rgdecl += strprintf("%sconst %s g%d", x > no ? ", " : "", IDX, x);
+    }
+    e("__device__ __forceinline__ void evd(%s", rgdecl.c_str());
     for (int x = 0; x < no; ++x) e(", const %s g%d", IDX, x);
-    e("%s%s, float (&o)[%d]) {\n", n_args ? ", " : "", param_list(n_args, false).c_str(), V);
+    e("%s, float (&o)[%d]) {\n", params.c_str(), V);
     LoadCtx c{V, no - 1, IDX};
-    for (int j = 0; j < nloads; ++j) emit_load(e, p, j, c, "  ");
+    for (int j = 0; j < nloads; ++j)
+      if (!in_post(j)) emit_load(e, p, j, c, "  ");
     e("  #pragma unroll\n  for (int l = 0; l < %d; ++l) {\n", V);
-    emit_ops(e, p, "    ", "l");
+    emit_op_list(e, p.ops, "    ", "l");
     e("    o[l] = _%d;\n  }\n}\n", p.results[0]);
+    e("__device__ __forceinline__ void ev(const %s t", IDX);
+    for (int x = 0; x < no; ++x) e(", const %s g%d", IDX, x);
+    e("%s, float (&o)[%d]) {\n", params.c_str(), V);
+    emit_t_decode("t");
+    e("  evd(%s%s%s, o);\n}\n", rgs.c_str(), gs.c_str(), pass.c_str());
+    emit_post_fn(V, no - 1);
     e("extern \"C\" __global__ void __launch_bounds__(256) reduce_cols(%s) {\n", param_list(n_args, true, "dst").c_str());
     e("  const %s v = (%s)blockIdx.x * 256 + threadIdx.x;\n  if (v >= %lld) return;\n", IDX, IDX, (long long)NV);
     emit_decode(e, odims, no, IDX, strprintf("v * %d", V).c_str(), "  ");
-    std::string gs;
-    for (int x = 0; x < no; ++x) gs += strprintf(", g%d", x);
-    e("  const int t0 = blockIdx.y * %lld;\n  const int t1 = min(%lld, t0 + %lld);\n", (long long)TCH, (long long)T, (long long)TCH);
-    e("  float acc[%d];\n  ev(t0%s%s%s, acc);\n", V, gs.c_str(), n_args ? ", " : "", arg_pass(n_args).c_str());
-    e("  #pragma unroll 4\n  for (int t = t0 + 1; t < t1; ++t) {\n    float x[%d];\n    ev(t%s%s%s, x);\n", V, gs.c_str(), n_args ? ", " : "",
-      arg_pass(n_args).c_str());
-    e("    #pragma unroll\n    for (int l = 0; l < %d; ++l) acc[l] = acc[l] + x[l];\n  }\n", V);
+    if (S == 1) {
+      // one thread folds the whole chain: nested loops over the reduction digits (bounds tests and address terms of the outer
+      // digits hoist out of the inner loop), left to right = the reference's order; `0 + e_0` is exact
+      e("  float acc[%d];\n  #pragma unroll\n  for (int l = 0; l < %d; ++l) acc[l] = 0.f;\n", V, V);
+      std::string ind = "  ";
+      for (int x = no; x < nd; ++x) {
+        if (T <= 96)
+          e("%s#pragma unroll\n", ind.c_str());
+        else if (x == nd - 1)
+          e("%s#pragma unroll %d\n", ind.c_str(), (int)std::min<int64_t>(8, p.dims[x]));
+        else
+          e("%s#pragma unroll 1\n", ind.c_str());
+        e("%sfor (%s g%d = 0; g%d < %lld; ++g%d) {\n", ind.c_str(), IDX, x, x, (long long)p.dims[x], x);
+        ind += "  ";
+      }
+      e("%sfloat x[%d];\n%sevd(%s%s%s, x);\n", ind.c_str(), V, ind.c_str(), rgs.c_str(), gs.c_str(), pass.c_str());
+      e("%s#pragma unroll\n%sfor (int l = 0; l < %d; ++l) acc[l] = acc[l] + x[l];\n", ind.c_str(), ind.c_str(), V);
+      for (int x = no; x < nd; ++x) {
+        ind.resize(ind.size() - 2);
+        e("%s}\n", ind.c_str());
+      }
+    } else {
+      e("  const int t0 = blockIdx.y * %lld;\n  const int t1 = min(%lld, t0 + %lld);\n", (long long)TCH, (long long)T, (long long)TCH);
+      e("  float acc[%d];\n  ev(t0%s%s, acc);\n", V, gs.c_str(), pass.c_str());
+      e("  #pragma unroll 4\n  for (int t = t0 + 1; t < t1; ++t) {\n    float x[%d];\n    ev(t%s%s, x);\n", V, gs.c_str(), pass.c_str());
+      e("    #pragma unroll\n    for (int l = 0; l < %d; ++l) acc[l] = acc[l] + x[l];\n  }\n", V);
+    }
+    if (has_post && S == 1) e("  post(acc%s%s);\n", gs.c_str(), pass.c_str());
     e("  float* d = dst + (%s)blockIdx.y * %lld + v * %d;\n", "long long", (long long)NOUT, V);
     if (V == 4)
       e("  cc_stg4(d, acc);\n");
@@ -880,59 +1121,73 @@ void emit_reduce(Plan& plan, const Program& p, int n_args, const DeviceProps& de
     plan.launches.push_back(ls);
     if (S > 1) {
       plan.scratch_floats.push_back((uint64_t)(S * NOUT));
-      e("extern \"C\" __global__ void __launch_bounds__(256) reduce_partials(const float* __restrict__ part, float* __restrict__ out) {\n");
+      e("extern \"C\" __global__ void __launch_bounds__(256) reduce_partials(const float* __restrict__ part, float* __restrict__ out%s) {\n",
+        has_post ? params.c_str() : "");
       e("  const long long v = (long long)blockIdx.x * 256 + threadIdx.x;\n  if (v >= %lld) return;\n", (long long)NV);
       e("  float acc[%d];\n", V);
       if (V == 4) {
         e("  cc_ldg4(part + v * 4, acc);\n  #pragma unroll 8\n  for (int s = 1; s < %lld; ++s) {\n    float x[4];\n    cc_ldg4(part + (long long)s * %lld + v * 4, x);\n", (long long)S,
           (long long)NOUT);
-        e("    #pragma unroll\n    for (int l = 0; l < 4; ++l) acc[l] = acc[l] + x[l];\n  }\n  cc_stg4(out + v * 4, acc);\n}\n");
+        e("    #pragma unroll\n    for (int l = 0; l < 4; ++l) acc[l] = acc[l] + x[l];\n  }\n");
       } else {
-        e("  acc[0] = part[v];\n  #pragma unroll 8\n  for (int s = 1; s < %lld; ++s) acc[0] = acc[0] + part[(long long)s * %lld + v];\n  out[v] = acc[0];\n}\n", (long long)S,
-          (long long)NOUT);
+        e("  acc[0] = part[v];\n  #pragma unroll 8\n  for (int s = 1; s < %lld; ++s) acc[0] = acc[0] + part[(long long)s * %lld + v];\n", (long long)S, (long long)NOUT);
       }
+      if (has_post) {
+        emit_decode(e, odims, no, IDX, strprintf("(%s)v * %d", IDX, V).c_str(), "  ");
+        e("  post(acc%s%s);\n", gs.c_str(), pass.c_str());
+      }
+      if (V == 4)
+        e("  cc_stg4(out + v * 4, acc);\n}\n");
+      else
+        e("  out[v] = acc[0];\n}\n");
       LaunchSpec l2;
       l2.entry = "reduce_partials";
       l2.grid[0] = (uint32_t)((NV + 255) / 256);
       l2.block[0] = 256;
       l2.args = {ARG_SCRATCH0, ARG_OUT};
+      if (has_post)
+        for (int i = 0; i < n_args; ++i) l2.args.push_back(i);
       plan.launches.push_back(l2);
     }
   } else {
     // --- row owner: G threads share one output and stride over t in 128-bit vectors -----------------------------------
-    const int V = (T % 4 == 0) ? 4 : 1;
+    const int V = (p.dims[nd - 1] % 4 == 0) ? 4 : 1;
     const int64_t TV = T / V;
     const int G = TV <= 64 ? 32 : 256;
     const int OPB = 256 / G;  // outputs per block
     e("// axis reduction (row owner): out dims=[");
     for (int x = 0; x < no; ++x) e("%s%lld", x ? "," : "", (long long)odims[x]);
-    e("] T=%lld V=%d threads/output=%d idx=%s\n", (long long)T, V, G, IDX);
-    e("__device__ __forceinline__ float ev(const %s g%d", IDX, nd - 1);
+    e("] T=%s V=%d threads/output=%d idx=%s epilogue=%d\n", rd.c_str(), V, G, IDX, (int)has_post);
+    e("__device__ __forceinline__ float ev(const %s t", IDX);
     for (int x = 0; x < no; ++x) e(", const %s g%d", IDX, x);
-    e("%s%s) {\n", n_args ? ", " : "", param_list(n_args, false).c_str());
+    e("%s) {\n", params.c_str());
+    emit_t_decode("t");
     LoadCtx c{V, nd - 1, IDX};
-    for (int j = 0; j < nloads; ++j) emit_load(e, p, j, c, "  ");
+    for (int j = 0; j < nloads; ++j)
+      if (!in_post(j)) emit_load(e, p, j, c, "  ");
     e("  float o[%d];\n  #pragma unroll\n  for (int l = 0; l < %d; ++l) {\n", V, V);
-    emit_ops(e, p, "    ", "l");
+    emit_op_list(e, p.ops, "    ", "l");
     e("    o[l] = _%d;\n  }\n", p.results[0]);
     if (V == 4)
       e("  return (o[0] + o[1]) + (o[2] + o[3]);\n}\n");
     else
       e("  return o[0];\n}\n");
+    emit_post_fn(1, -1);
     e("extern \"C\" __global__ void __launch_bounds__(256) reduce_rows(%s) {\n", param_list(n_args, true).c_str());
     e("  const int lane = threadIdx.x %% %d;\n", G);
     e("  const %s oidx = (%s)blockIdx.x * %d + threadIdx.x / %d;\n", IDX, IDX, OPB, G);
     e("  const bool live = oidx < %lld;\n  const %s oc = live ? oidx : 0;\n", (long long)NOUT, IDX);
     emit_decode(e, odims, no, IDX, "oc", "  ");
-    std::string gs;
-    for (int x = 0; x < no; ++x) gs += strprintf(", g%d", x);
-    e("  float acc = 0.f;\n  #pragma unroll 4\n  for (int tv = lane; tv < %lld; tv += %d) acc += ev((%s)tv * %d%s%s%s);\n", (long long)TV, G, IDX, V, gs.c_str(),
-      n_args ? ", " : "", arg_pass(n_args).c_str());
+    e("  float acc = 0.f;\n  #pragma unroll 4\n  for (int tv = lane; tv < %lld; tv += %d) acc += ev((%s)tv * %d%s%s);\n", (long long)TV, G, IDX, V, gs.c_str(),
+      pass.c_str());
     if (G == 32)
       e("  acc = cc_warp_sum(acc);\n");
     else
       e("  acc = cc_block_sum_256(acc);\n");
-    e("  if (lane == 0 && live) out[oidx] = acc;\n}\n");
+    if (has_post)
+      e("  if (lane == 0 && live) {\n    float a1[1] = {acc};\n    post(a1%s%s);\n    out[oidx] = a1[0];\n  }\n}\n", gs.c_str(), pass.c_str());
+    else
+      e("  if (lane == 0 && live) out[oidx] = acc;\n}\n");
     LaunchSpec ls;
     ls.entry = "reduce_rows";
     ls.grid[0] = (uint32_t)((NOUT + OPB - 1) / OPB);
@@ -1076,59 +1331,58 @@ Plan make_plan(const Tree& t, const DeviceProps& dev) {
     b.prog.results.push_back(b.export_node(root.kids[0]));
     prog = std::move(b.prog);
     plan.note = strprintf("whole-tensor %s fold with the operand's closure fused in", kind_name(root.monoid));
-  } else if (root.kind == K_CONCAT) {
-    // Tensor.join (Tensors.scala:577-598): elements are evaluated over the head shape = out_shape minus the last dim
-    CC_REQUIRE(!odims.empty() && odims.back() == (int64_t)root.kids.size(), CC_ERR_BAD_TREE,
-               "Concatenate of %zu elements needs an output shape ending in %zu", root.kids.size(), root.kids.size());
-    nd_base = (int)odims.size() - 1;
-    std::vector<int64_t> head(odims.begin(), odims.end() - 1);
-    std::unordered_map<uint32_t, std::vector<double>> step;
-    StepMap step_c, step_t;
-    std::vector<uint32_t> terms0;
-    if (reroll_join_of_folds(t, root.kids, step_c, step_t, terms0)) {
-      // matmul1 (benchmarks.scala:176-187, README.md:312-329): join over c of left folds over t -> dims = head + [C] + [T]
-      Builder b{t, {}, nd_base, {&step_c, &step_t}, {}, &arg_of_param, &arg_nodes};
-      b.prog.dims = odims;
-      b.prog.dims.push_back((int64_t)terms0.size());
-      b.prog.results.push_back(b.export_node(terms0[0]));
-      prog = std::move(b.prog);
-      is_reduce = true;
-      plan.note = strprintf("join of %zu Plus chains of %zu congruent terms re-rolled into an output dimension and a reduction", root.kids.size(),
-                            terms0.size());
-    } else if (root.kids.size() >= 2 && reroll(t, root.kids, step)) {
-      Builder b{t, {}, nd_base, {&step}, {}, &arg_of_param, &arg_nodes};
-      b.prog.dims = odims;  // head dims + the re-rolled element index as the fastest dimension
-      b.prog.results.push_back(b.export_node(root.kids[0]));
-      prog = std::move(b.prog);
-      plan.note = "join re-rolled into an output dimension";
-    } else {
+  } else {
+    // Tensor.join (Tensors.scala:577-598): a Concatenate root; its elements are evaluated over the head shape = out_shape minus
+    // the last dim. Congruent elements are re-rolled into that last output dimension (index c).
+    const bool joined = root.kind == K_CONCAT;
+    StepMap step_c;
+    bool rolled_c = false;
+    uint32_t base = t.root;
+    if (joined) {
+      CC_REQUIRE(!odims.empty() && odims.back() == (int64_t)root.kids.size(), CC_ERR_BAD_TREE,
+                 "Concatenate of %zu elements needs an output shape ending in %zu", root.kids.size(), root.kids.size());
+      nd_base = (int)odims.size() - 1;
+      rolled_c = root.kids.size() >= 2 && reroll(t, root.kids, step_c);
+      base = root.kids[0];
+    }
+    if (joined && !rolled_c) {
       Builder b{t, {}, nd_base, {}, {}, &arg_of_param, &arg_nodes};
-      b.prog.dims = head;
+      b.prog.dims.assign(odims.begin(), odims.end() - 1);
       for (uint32_t k : root.kids) b.prog.results.push_back(b.export_node(k));
       prog = std::move(b.prog);
       plan.note = "join as per-index tuple stores";
-    }
-  } else {
-    // left-leaning Plus chain?  (((e0 + e1) + e2) + ... )
-    std::vector<uint32_t> elems = plus_chain(t, t.root);
-    std::unordered_map<uint32_t, std::vector<double>> step;
-    if (elems.size() >= kMinRerollTerms && reroll(t, elems, step)) {
-      Builder b{t, {}, nd_base, {&step}, {}, &arg_of_param, &arg_nodes};
-      b.prog.dims = odims;
-      b.prog.dims.push_back((int64_t)elems.size());
-      b.prog.results.push_back(b.export_node(elems[0]));
-      prog = std::move(b.prog);
-      is_reduce = true;
-      plan.note = strprintf("Plus chain of %zu congruent terms re-rolled into a reduction", elems.size());
     } else {
-      Builder b{t, {}, nd_base, {}, {}, &arg_of_param, &arg_nodes};
-      b.prog.dims = odims;
-      b.prog.results.push_back(b.export_node(t.root));
+      // A long left-leaning Plus chain of congruent terms inside the expression (`t.split(axis).reduce(_ + _)`, both matmul
+      // formulations, the convolution of benchmarks.scala:526-545) is re-rolled into a reduction over 1..n nested indices; what
+      // surrounds the chain (e.g. `bias + chain`) becomes the epilogue applied once per output element.
+      Chain ch;
+      const bool found = find_chain(t, base, ch) && (!rolled_c || join_step_uniform_over_terms(t, ch, step_c));
+      std::vector<const StepMap*> exts;
+      if (rolled_c) exts.push_back(&step_c);
+      if (found)
+        for (const StepMap& sm : ch.steps) exts.push_back(&sm);
+      Builder b{t, {}, nd_base, exts, {}, &arg_of_param, &arg_nodes};
+      b.prog.dims = odims;  // (head dims + the re-rolled element index c as the fastest output dimension when joined)
+      if (found) {
+        for (int64_t n : ch.levels) b.prog.dims.push_back(n);
+        b.prog.n_red = (int)ch.levels.size();
+        b.prog.results.push_back(b.export_node(ch.terms[0]));
+        b.begin_post(ch.top);
+        b.prog.post_result = b.export_node(base);
+        is_reduce = true;
+        std::string lv;
+        for (size_t j = 0; j < ch.levels.size(); ++j) lv += strprintf("%s%lld", j ? " x " : "", (long long)ch.levels[j]);
+        plan.note = strprintf("%sPlus chain of %zu congruent terms re-rolled into a reduction over %s%s", rolled_c ? "join re-rolled into an output dimension; " : "",
+                              ch.terms.size(), lv.c_str(), b.prog.trivial_post() ? "" : " with an elementwise epilogue");
+      } else {
+        b.prog.results.push_back(b.export_node(base));
+        if (rolled_c) plan.note = "join re-rolled into an output dimension";
+      }
       prog = std::move(b.prog);
     }
   }
 
-  if (is_reduce) {
+  if (is_reduce && prog.trivial_post() && prog.n_red == 1) {
     // compose the closure of an unevaluated inline operand into the reduction (looks through the fusion barrier,
     // SURVEY finding 2) when the view of it is integer and provably in range
     const int nd = (int)prog.dims.size();
@@ -1205,6 +1459,10 @@ Plan make_plan(const Tree& t, const DeviceProps& dev) {
     }
     if (changed) {
       np.results.push_back(remap[prog.results[0]]);
+      np.n_red = prog.n_red;
+      np.post_ops = prog.post_ops;
+      np.post_result = prog.post_result;
+      np.load_in_post.assign(np.loads.size(), 0);
       prog = std::move(np);
       arg_nodes = nodes2;
       plan.note += "; inline operand composed into the reduction (never materialised)";
@@ -1241,7 +1499,8 @@ Plan make_plan(const Tree& t, const DeviceProps& dev) {
     plan.kind = PLAN_AXIS_REDUCE;
     // contraction: sum_t A[i,t] * B[t,k] with A [M,K] and B [K,N] row-major
     const int nd = (int)prog.dims.size();
-    if (dev.contraction && nd == 3 && prog.ops.size() == 3 && prog.loads.size() == 2 && prog.ops[prog.results[0]].kind == K_TIMES) {
+    if (dev.contraction && nd == 3 && prog.n_red == 1 && prog.trivial_post() && prog.ops.size() == 3 && prog.loads.size() == 2 &&
+        prog.ops[prog.results[0]].kind == K_TIMES) {
       const Op& mul = prog.ops[prog.results[0]];
       if (prog.ops[mul.a].kind == K_EXTRACT && prog.ops[mul.b].kind == K_EXTRACT && mul.a != mul.b) {
         const int64_t M = prog.dims[0], N = prog.dims[1], K = prog.dims[2];

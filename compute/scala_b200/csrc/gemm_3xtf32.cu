@@ -429,7 +429,7 @@ void launch_main(const GemmWorkspace& ws, float* c, int64_t m, int64_t n, int64_
 }  // namespace
 
 int launch_gemm_3xtf32(const float* a, const float* b, float* c, int64_t m, int64_t n, int64_t k, const GemmWorkspace& ws, int sm_count,
-                       TensorMapEncodeFn encode, cudaStream_t stream) {
+                       TensorMapEncodeFn encode, cudaStream_t stream, bool b_panels_ready) {
   CC_REQUIRE(m >= 1 && n >= 1 && k >= 1 && m < (1ll << 31) && n < (1ll << 31) && k < (1ll << 31) - BK, CC_ERR_UNSUPPORTED,
              "gemm_3xtf32: bad shape %lld x %lld x %lld", (long long)m, (long long)n, (long long)k);
   CC_REQUIRE(encode, CC_ERR_NO_DRIVER, "cuTensorMapEncodeTiled unavailable");
@@ -439,14 +439,16 @@ int launch_gemm_3xtf32(const float* a, const float* b, float* c, int64_t m, int6
   if (blocks > (size_t)sm_count * 8) blocks = (size_t)sm_count * 8;
   split_a_kernel<<<(unsigned)blocks, 256, 0, stream>>>(a, ws.a_hi, ws.a_lo, (int)m, (int)k, (int)kp);
   check_launch("split_a");
-  split_transpose_b_kernel<<<dim3((unsigned)((n + 31) / 32), (unsigned)(kp / 32)), 256, 0, stream>>>(b, ws.bt_hi, ws.bt_lo, (int)k, (int)n, (int)kp);
-  check_launch("split_transpose_b");
+  if (!b_panels_ready) {
+    split_transpose_b_kernel<<<dim3((unsigned)((n + 31) / 32), (unsigned)(kp / 32)), 256, 0, stream>>>(b, ws.bt_hi, ws.bt_lo, (int)k, (int)n, (int)kp);
+    check_launch("split_transpose_b");
+  }
   switch (gemm_pick_bn(m, n, sm_count)) {
     case 256: launch_main<256>(ws, c, m, n, kp, sm_count, encode, stream); break;
     case 128: launch_main<128>(ws, c, m, n, kp, sm_count, encode, stream); break;
     default: launch_main<64>(ws, c, m, n, kp, sm_count, encode, stream); break;
   }
-  return 3;
+  return b_panels_ready ? 2 : 3;
 }
 
 }  // namespace cc

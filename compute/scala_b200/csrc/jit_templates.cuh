@@ -22,6 +22,17 @@ __device__ __forceinline__ void cc_ldg4(const float* p, float (&v)[4]) {
       : "l"(p));
 }
 
+// cached flavours (allocate in L1) for data that is reused across the index space: broadcast operands, the operands of a
+// re-rolled reduction whose address does not depend on every output index (matmul / convolution patterns)
+__device__ __forceinline__ float cc_ldc(const float* p) { return __ldg(p); }
+__device__ __forceinline__ void cc_ldc4(const float* p, float (&v)[4]) {
+  const float4 x = __ldg(reinterpret_cast<const float4*>(p));
+  v[0] = x.x;
+  v[1] = x.y;
+  v[2] = x.z;
+  v[3] = x.w;
+}
+
 __device__ __forceinline__ void cc_stg4(float* p, const float (&v)[4]) {
   asm volatile("st.global.cs.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]) : "memory");
 }

@@ -46,6 +46,8 @@ struct Buffer {
   std::atomic<int> rc{1};
   Mark last_write;
   std::vector<Mark> reads;  // at most one per stream
+  uint64_t uid = 0;         // never reused: identity for the operand-panel cache
+  uint64_t version = 0;     // bumped by every command that writes the buffer
 };
 
 struct Block {
@@ -121,6 +123,17 @@ struct Runtime {
   std::unordered_set<Kernel*> kernels;
   std::unordered_map<std::string, Kernel*> cache;
   cc_stats_t stats{};
+  // B^T hi / lo panels of recent contractions, kept while the B buffer is unchanged (same uid and write version)
+  struct Panels {
+    uint64_t uid, version;
+    int64_t k, n;
+    Buffer* hi;
+    Buffer* lo;
+    uint64_t last_use;
+  };
+  std::vector<Panels> panel_cache;
+  bool panel_cache_on = true;
+  uint64_t panel_clock = 0, next_uid = 1;
   // builtin scratch
   Buffer* reduce_scratch = nullptr;
   CUdeviceptr reduce_counter = 0;
@@ -230,6 +243,7 @@ void op_end(Op& op, cc_event* out_event) {
   for (Buffer* b : op.writes) {
     b->reads.clear();
     b->last_write = Mark{op.stream, q};
+    b->version++;
   }
   for (Buffer* b : op.reads) {
     bool also_written = false;
@@ -277,6 +291,7 @@ Buffer* alloc_buffer(uint64_t n_floats) {
   Buffer* b = new Buffer();
   b->n_floats = n_floats;
   b->bytes = bytes;
+  b->uid = r.next_uid++;
   r.stats.alloc_calls++;
   auto it = r.pool.find(bytes);
   if (it != r.pool.end() && !it->second.empty()) {
@@ -302,10 +317,26 @@ Buffer* alloc_buffer(uint64_t n_floats) {
   return b;
 }
 
+void release(Buffer* b);
+void drop_panels_of(uint64_t uid) {
+  Runtime& r = rt();
+  for (size_t i = 0; i < r.panel_cache.size();) {
+    if (uid == 0 || r.panel_cache[i].uid == uid) {
+      Runtime::Panels p = r.panel_cache[i];
+      r.panel_cache.erase(r.panel_cache.begin() + (long)i);
+      release(p.hi);
+      release(p.lo);
+    } else {
+      ++i;
+    }
+  }
+}
+
 void release(Buffer* b) {
   if (b->rc.fetch_sub(1) != 1) return;
   Runtime& r = rt();
   r.buffers.erase(b);
+  if (b->owned && !r.panel_cache.empty()) drop_panels_of(b->uid);
   if (b->owned && r.initialized) {
     Block blk{b->ptr, b->bytes, std::move(b->reads)};
     if (b->last_write.stream >= 0) blk.pending.push_back(b->last_write);
@@ -483,6 +514,7 @@ int cc_shutdown(void) {
       r.nccl.CommDestroy(r.nccl.comm);
       r.nccl.comm = nullptr;
     }
+    drop_panels_of(0);
     for (auto& kv : r.cache) release(kv.second);
     r.cache.clear();
     if (r.reduce_scratch) {
@@ -824,7 +856,7 @@ int cc_kernel_info(cc_kernel h, cc_kernel_info_t* out) {
     out->kind = k->plan.kind;
     out->cache_hit = k->last_hit;
     out->n_args = (int32_t)k->plan.arg_params.size();
-    out->n_launches = k->plan.kind == PLAN_CONTRACTION ? 3 : (int32_t)k->plan.launches.size();
+    out->n_launches = k->plan.kind == PLAN_CONTRACTION ? 3 : (int32_t)k->plan.launches.size();  // 2 when B's panels are cached
     out->out_floats = k->plan.out_floats;
     out->algorithmic_bytes = k->plan.algorithmic_bytes;
     out->flops = k->plan.flops;
@@ -848,10 +880,74 @@ int cc_kernel_source(cc_kernel h, const char** out) {
 }
 
 namespace {
-void gemm_on_stream(Buffer* a, Buffer* b, Buffer* c, int64_t m, int64_t n, int64_t k, const std::vector<Buffer*>& scratch, CUstream s) {
-  GemmWorkspace ws{(float*)scratch[0]->ptr, (float*)scratch[1]->ptr, (float*)scratch[2]->ptr, (float*)scratch[3]->ptr};
+// Workspace of one contraction: A panels are per call; the B^T panels are looked up in / added to the panel cache so that a B that
+// has not been written since its last contraction (weights, the replicated operand of the row-sharded matmul) is split once.
+struct GemmRun {
+  Buffer *a_hi = nullptr, *a_lo = nullptr, *bt_hi = nullptr, *bt_lo = nullptr;
+  bool b_ready = false;
+  void declare(Op& op) const {
+    op.writes.push_back(a_hi);
+    op.writes.push_back(a_lo);
+    (b_ready ? op.reads : op.writes).push_back(bt_hi);
+    (b_ready ? op.reads : op.writes).push_back(bt_lo);
+  }
+};
+
+GemmRun gemm_prepare(Buffer* b, int64_t m, int64_t n, int64_t k) {
+  Runtime& r = rt();
+  GemmRun g;
+  const int64_t kp = gemm_padded_k(k);
+  if (r.panel_cache_on && b->owned)
+    for (Runtime::Panels& p : r.panel_cache)
+      if (p.uid == b->uid && p.version == b->version && p.k == k && p.n == n) {
+        g.bt_hi = p.hi;
+        g.bt_lo = p.lo;
+        g.bt_hi->rc.fetch_add(1);
+        g.bt_lo->rc.fetch_add(1);
+        g.b_ready = true;
+        p.last_use = ++r.panel_clock;
+        break;
+      }
+  try {
+    g.a_hi = alloc_buffer((uint64_t)(m * kp));
+    g.a_lo = alloc_buffer((uint64_t)(m * kp));
+    if (!g.b_ready) {
+      g.bt_hi = alloc_buffer((uint64_t)(n * kp));
+      g.bt_lo = alloc_buffer((uint64_t)(n * kp));
+    }
+  } catch (...) {
+    for (Buffer* x : {g.a_hi, g.a_lo, g.bt_hi, g.bt_lo})
+      if (x) release(x);
+    throw;
+  }
+  return g;
+}
+
+void gemm_finish(GemmRun& g, Buffer* b, int64_t n, int64_t k, bool launched) {
+  Runtime& r = rt();
+  if (launched && !g.b_ready && r.panel_cache_on && b->owned) {
+    constexpr size_t kMaxPanels = 4;
+    while (r.panel_cache.size() >= kMaxPanels) {
+      size_t lru = 0;
+      for (size_t i = 1; i < r.panel_cache.size(); ++i)
+        if (r.panel_cache[i].last_use < r.panel_cache[lru].last_use) lru = i;
+      Runtime::Panels old = r.panel_cache[lru];
+      r.panel_cache.erase(r.panel_cache.begin() + (long)lru);
+      release(old.hi);
+      release(old.lo);
+    }
+    g.bt_hi->rc.fetch_add(1);
+    g.bt_lo->rc.fetch_add(1);
+    r.panel_cache.push_back(Runtime::Panels{b->uid, b->version, k, n, g.bt_hi, g.bt_lo, ++r.panel_clock});
+  }
+  for (Buffer* x : {g.a_hi, g.a_lo, g.bt_hi, g.bt_lo})
+    if (x) release(x);
+}
+
+void gemm_on_stream(Buffer* a, Buffer* b, Buffer* c, int64_t m, int64_t n, int64_t k, const GemmRun& g, CUstream s) {
+  GemmWorkspace ws{(float*)g.a_hi->ptr, (float*)g.a_lo->ptr, (float*)g.bt_hi->ptr, (float*)g.bt_lo->ptr};
   int launched = launch_gemm_3xtf32((const float*)a->ptr, (const float*)b->ptr, (float*)c->ptr, m, n, k, ws, rt().info.sm_count,
-                                    (TensorMapEncodeFn)driver().cuTensorMapEncodeTiled, (cudaStream_t)s);
+                                    (TensorMapEncodeFn)driver().cuTensorMapEncodeTiled, (cudaStream_t)s, g.b_ready);
   rt().stats.device_kernels += (uint64_t)launched;
 }
 }  // namespace
@@ -876,6 +972,24 @@ int cc_launch(cc_kernel h, const cc_buffer* args, int n_args, cc_buffer out, con
       in.push_back(b);
     }
     ensure_loaded(*k);
+    if (p.kind == PLAN_CONTRACTION) {
+      GemmRun g = gemm_prepare(in[1], p.M, p.N, p.K);
+      bool launched = false;
+      try {
+        Op op{pick_stream(), in, {ob}};
+        g.declare(op);
+        op_begin(op, waits, n_waits);
+        gemm_on_stream(in[0], in[1], ob, p.M, p.N, p.K, g, op.cu());
+        launched = true;
+        r.stats.launches++;
+        op_end(op, out_event);
+      } catch (...) {
+        gemm_finish(g, in[1], p.N, p.K, launched);
+        throw;
+      }
+      gemm_finish(g, in[1], p.N, p.K, true);
+      return;
+    }
     std::vector<Buffer*> scratch;
     for (uint64_t n : p.scratch_floats) scratch.push_back(alloc_buffer(n));
     // whole-tensor folds share the runtime's partials buffer and block counter: serialised on stream 0 like cc_reduce_sum
@@ -884,9 +998,7 @@ int cc_launch(cc_kernel h, const cc_buffer* args, int n_args, cc_buffer out, con
     for (Buffer* s : scratch) op.writes.push_back(s);
     if (shared_partials) op.writes.push_back(shared_partials);
     op_begin(op, waits, n_waits);
-    if (p.kind == PLAN_CONTRACTION) {
-      gemm_on_stream(in[0], in[1], ob, p.M, p.N, p.K, scratch, op.cu());
-    } else {
+    {
       for (size_t li = 0; li < p.launches.size(); ++li) {
         const LaunchSpec& ls = p.launches[li];
         std::vector<CUdeviceptr> ptrs;
@@ -979,16 +1091,32 @@ int cc_matmul_3xtf32(cc_buffer a, cc_buffer b, cc_buffer c, int64_t m, int64_t n
     CC_REQUIRE(ab->n_floats >= (uint64_t)(m * k) && bb->n_floats >= (uint64_t)(k * n) && cb->n_floats >= (uint64_t)(m * n),
                CC_ERR_ILLEGAL_ARGUMENT, "matmul buffers too small");
     CC_REQUIRE(cb != ab && cb != bb, CC_ERR_ILLEGAL_ARGUMENT, "matmul output aliases an input");
-    const int64_t kp = gemm_padded_k(k);
-    std::vector<Buffer*> scratch{alloc_buffer((uint64_t)(m * kp)), alloc_buffer((uint64_t)(m * kp)), alloc_buffer((uint64_t)(n * kp)),
-                                 alloc_buffer((uint64_t)(n * kp))};
-    Op op{pick_stream(), {ab, bb}, {cb}};
-    for (Buffer* s : scratch) op.writes.push_back(s);
-    op_begin(op, waits, n_waits);
-    gemm_on_stream(ab, bb, cb, m, n, k, scratch, op.cu());
-    rt().stats.launches++;
-    op_end(op, out_event);
-    for (Buffer* s : scratch) release(s);
+    GemmRun g = gemm_prepare(bb, m, n, k);
+    bool launched = false;
+    try {
+      Op op{pick_stream(), {ab, bb}, {cb}};
+      g.declare(op);
+      op_begin(op, waits, n_waits);
+      gemm_on_stream(ab, bb, cb, m, n, k, g, op.cu());
+      launched = true;
+      rt().stats.launches++;
+      op_end(op, out_event);
+    } catch (...) {
+      gemm_finish(g, bb, n, k, launched);
+      throw;
+    }
+    gemm_finish(g, bb, n, k, true);
+  });
+}
+
+int cc_set_operand_cache(int on) {
+  return guarded([&] {
+    Lock lock;
+    rt().panel_cache_on = on != 0;
+    if (!on && rt().initialized) {
+      CC_CU(cuCtxSetCurrent(rt().ctx));
+      drop_panels_of(0);
+    }
   });
 }
 

@@ -83,6 +83,7 @@ def _L():
         L.cc_random.argtypes = [h, u64, i32, hp]
         L.cc_random_normal.argtypes = [h, u64, i32, hp]
         L.cc_matmul_3xtf32.argtypes = [h, h, h, C.c_int64, C.c_int64, C.c_int64, hp, C.c_int, hp]
+        L.cc_set_operand_cache.argtypes = [C.c_int]
         L.cc_stats.argtypes = [C.POINTER(_lib.Stats)]
         L.cc_timer_stop.argtypes = [fp]
         L.cc_comm_unique_id.argtypes = [C.c_void_p]
@@ -275,6 +276,11 @@ def reduce_sum(src: Buffer, n_floats: int, dst: Buffer) -> None:
 
 def matmul_3xtf32(a: Buffer, b: Buffer, c: Buffer, m: int, n: int, k: int) -> None:
     check(_L().cc_matmul_3xtf32(a.handle, b.handle, c.handle, m, n, k, None, 0, None))
+
+
+def set_operand_cache(on: bool) -> None:
+    """keep (True, default) or drop (False) the TF32 hi / lo panels of recently used, unchanged B operands"""
+    check(_L().cc_set_operand_cache(1 if on else 0))
 
 
 def comm_unique_id() -> bytes:

@@ -175,10 +175,15 @@ int cc_random(cc_buffer out, uint64_t n_floats, int32_t seed, cc_event* out_even
 int cc_random_normal(cc_buffer out, uint64_t n_floats, int32_t seed, cc_event* out_event);
 
 /* C[M,N] = A[M,K] * B[K,N] (row-major fp32) with 3xTF32 tcgen05 MMAs; what the contraction pattern lowers to.
- * Exposed for direct measurement; `c` may alias neither input. Needs M % 128 == 0, N % 256 == 0, K % 32 == 0 (other
- * shapes of the pattern run through the generic JIT reduction). */
+ * Exposed for direct measurement; `c` may alias neither input. Any M, N, K >= 1 (ragged edges: TMA zero fill on the way in,
+ * predicated stores on the way out; K is zero-padded inside the hi/lo workspace). */
 int cc_matmul_3xtf32(cc_buffer a, cc_buffer b, cc_buffer c, int64_t m, int64_t n, int64_t k, const cc_event* waits,
                      int n_waits, cc_event* out_event);
+
+/* The contraction splits B into two K-major TF32 panels (hi / lo) before the tensor-core pipeline runs. The panels of the
+ * last few B operands are kept while the B buffer has not been written since (tracked per buffer by the runtime; wrapped
+ * memory is never cached), so a replicated / weight operand is split once. 1 = on (default), 0 = off and drop the panels. */
+int cc_set_operand_cache(int on);
 
 /* ---- counters / timing -------------------------------------------------------------------------------------- */
 

@@ -71,6 +71,40 @@ def test_ragged_edges_do_not_write_outside_the_result(cuda):
         x.release()
 
 
+def test_b_panels_are_cached_while_b_is_unchanged(cuda):
+    """the hi / lo split of an unchanged B (weights, the replicated operand of the sharded matmul) runs once; any write to B
+    (here an upload into the same buffer) invalidates it"""
+    m, n, k = 256, 192, 100
+    rng = np.random.default_rng(5)
+    a = rng.integers(-4, 5, (m, k)).astype(np.float32)
+    b1 = rng.integers(-4, 5, (k, n)).astype(np.float32)
+    b2 = rng.integers(-4, 5, (k, n)).astype(np.float32)
+    A, B, C = cuda.Buffer.from_host(a), cuda.Buffer.from_host(b1), cuda.Buffer.alloc(m * n)
+
+    def run():
+        s0 = cuda.stats()["device_kernels"]
+        cuda.matmul_3xtf32(A, B, C, m, n, k)
+        return cuda.stats()["device_kernels"] - s0, C.to_host(m * n).reshape(m, n)
+
+    want1 = (a.astype(np.float64) @ b1.astype(np.float64)).astype(np.float32)
+    want2 = (a.astype(np.float64) @ b2.astype(np.float64)).astype(np.float32)
+    cuda.set_operand_cache(True)
+    k1, c1 = run()
+    k2, c2 = run()
+    assert (k1, k2) == (3, 2) and np.array_equal(c1, want1) and np.array_equal(c2, want1)
+    B.upload(b2.ctypes.data, k * n)  # same buffer, new contents
+    k3, c3 = run()
+    k4, c4 = run()
+    assert (k3, k4) == (3, 2) and np.array_equal(c3, want2) and np.array_equal(c4, want2)
+    cuda.set_operand_cache(False)
+    k5, c5 = run()
+    k6, c6 = run()
+    assert (k5, k6) == (3, 3) and np.array_equal(c6, want2)
+    cuda.set_operand_cache(True)
+    for x in (A, B, C):
+        x.release()
+
+
 def test_layout_is_not_symmetric(cuda):
     """catches transposed / swizzle-permuted operands that a random-sign test could hide"""
     m, n, k = 128, 256, 64
