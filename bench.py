@@ -271,6 +271,7 @@ def sharded_configs(cuda, dist, rank: int, world: int, hbm_peak: float, tf_peak:
     rows = sharding.shard_rows(ROWS, world, rank)[1]
     x = T.random([rows, COLS], seed=5 + 16 * rank).doCache()
     col_sums, row_sums = axis_sum(x, 0), axis_sum(x, 1)  # lazy graphs, built once
+    had_peer = comm.peer
     for route, tag in ((True, "fused / one-shot over NVLink peer memory"), (False, "NCCL")):
         if route and not comm.peer:
             continue
@@ -278,7 +279,8 @@ def sharded_configs(cuda, dist, rank: int, world: int, hbm_peak: float, tf_peak:
         measure(f"C3 full sum 16384^2 sharded + allreduce(1 float) [{tag}]", lambda: comm.full_sum(x).release(), alg_bytes=4 * ROWS * COLS, steps=50)
         measure(f"C3 axis-0 sum 16384^2 sharded + allreduce(16384 floats) [{tag}]", lambda: comm.axis0_sum(col_sums).release(),
                 alg_bytes=4 * ROWS * COLS, steps=50)
-    comm.route_peer(comm.cuda.comm_peer_enabled() or False) if False else None
+    if had_peer:
+        comm.route_peer(True)
     measure("C3 axis-1 sum 16384^2 sharded + allgather [NCCL]", lambda: comm.axis1_sum(row_sums).release(), alg_bytes=4 * ROWS * COLS, steps=50)
     del x, col_sums, row_sums
     n5 = 8192
@@ -289,8 +291,11 @@ def sharded_configs(cuda, dist, rank: int, world: int, hbm_peak: float, tf_peak:
         ab, bb = A.doBuffer(), B.doBuffer()
         measure("C5 matmul 8192^3 row-sharded (B replicated, C left sharded)", lambda: comm.matmul_rows(ab, bb, m5, n5, n5).release(),
                 flops=2 * n5**3, steps=5)
-        measure("C5 matmul 8192^3 row-sharded + allgather(C)", lambda: comm.matmul_rows(ab, bb, m5, n5, n5, gather=True).release(),
-                flops=2 * n5**3, steps=5)
+        if comm.peer and n5 % world == 0:
+            measure("C5 matmul 8192^3 row-sharded + allgather(C) [fused into the contraction's epilogue: TMA stores over NVLink peer memory]",
+                    lambda: comm.matmul_rows(ab, bb, m5, n5, n5, gather=True, fused=True).release(), flops=2 * n5**3, steps=5)
+        measure("C5 matmul 8192^3 row-sharded + allgather(C) [contraction, then ncclAllGather]",
+                lambda: comm.matmul_rows(ab, bb, m5, n5, n5, gather=True, fused=False).release(), flops=2 * n5**3, steps=5)
         ab.release(), bb.release()
     cuda.synchronize()
     comm.close()

@@ -35,6 +35,8 @@ size_t peer_mailbox_bytes(int world);
 size_t peer_mailbox_flag_offset(int world);  // byte offset of the flags inside one mailbox allocation
 // in-place all-reduce(sum) of v[0..n), n <= kPeerCapFloats; `epoch` must increase by one per collective call on every rank
 void launch_peer_allreduce(float* v, uint64_t n, const PeerMailboxes& mb, unsigned epoch, cudaStream_t stream);
+// cross-rank barrier over the mailbox flags (one tiny kernel): returns on the stream once every rank has reached it
+void launch_peer_barrier(const PeerMailboxes& mb, unsigned epoch, cudaStream_t stream);
 // Tensor.sum over a sharded tensor as ONE kernel: local two-stage reduction whose last block pushes the partial into every
 // peer's mailbox and completes the all-reduce itself
 void launch_reduce_sum_allreduce(const float* in, uint64_t n, float* out, float* scratch, unsigned* counter, int sm_count,
@@ -62,5 +64,12 @@ typedef CUresult (*TensorMapEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint3
 int launch_gemm_3xtf32(const float* a, const float* b, float* c, int64_t m, int64_t n, int64_t k,
                        const GemmWorkspace& ws, int sm_count, TensorMapEncodeFn encode, cudaStream_t stream,
                        bool b_panels_ready = false);
+// The row-sharded matmul fused with the all-gather of its result: this rank computes C[rank*m_shard .. +m_shard, :] = A_shard * B
+// and the epilogue TMA-stores every 32x32 block of it straight into gathered_c[d] (rank d's [world*m_shard, N] result; own HBM for
+// d == rank, peer HBM over NVLink otherwise), so the transfer overlaps the MMAs tile by tile. Needs N % 4 == 0. The caller runs a
+// cross-rank barrier (launch_peer_barrier) afterwards: when it completes every block of every rank has landed.
+int launch_gemm_3xtf32_allgather(const float* a, const float* b, float* const* gathered_c, int world, int rank, int64_t m_shard,
+                                 int64_t n, int64_t k, const GemmWorkspace& ws, int sm_count, TensorMapEncodeFn encode,
+                                 cudaStream_t stream, bool b_panels_ready = false);
 
 }  // namespace cc

@@ -462,7 +462,23 @@ bool find_chain(const Tree& t, uint32_t root, Chain& best) {
     c.top = top;
     c.terms = plus_chain(t, top);
     if (c.terms.size() <= best_len) continue;
-    if (!nested_reroll(t, c)) continue;
+    if (!nested_reroll(t, c)) {
+      // `chain + other` parses as one longer left-leaning chain: keep the leading terms that are congruent to the first one
+      // (their Plus node sits further down the left spine); the rest becomes part of the epilogue
+      size_t m = 1;
+      for (; m < c.terms.size(); ++m) {
+        StepMap d;
+        if (!congruent(t, c.terms[0], c.terms[m], d)) break;
+      }
+      if (m == c.terms.size() || m < kMinRerollTerms || m <= best_len) continue;
+      uint32_t spine = top;
+      for (size_t k = c.terms.size(); k > m; --k) spine = t.nodes[spine].kids[0];
+      c.top = spine;
+      c.terms.resize(m);
+      c.levels.clear();
+      c.steps.clear();
+      if (!nested_reroll(t, c)) continue;
+    }
     best_len = c.terms.size();
     best = std::move(c);
   }

@@ -38,6 +38,9 @@ struct Cfg {
   static constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;  // 96 / 64 / 48 KiB
   static constexpr int STAGES = BN == 256 ? 2 : (BN == 128 ? 3 : 4);       // 192 KiB of operands in flight
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  // all-gather epilogue: 4 epilogue warps x 2 staging buffers x (32 rows x 128 bytes) for the TMA stores to every rank
+  static constexpr int GATHER_STAGING_BYTES = 4 * 2 * 4096;
+  static constexpr int SMEM_BYTES_GATHER = STAGES * STAGE_BYTES + GATHER_STAGING_BYTES + 1024 + 256;
   static constexpr int TMEM_COLS = 2 * BN;  // two accumulators: the epilogue of tile i overlaps the MMAs of tile i+1
   // cute::UMMA::InstrDescriptor for kind::tf32, fp32 accumulate, both operands K-major, M = 128, N = BN
   static constexpr uint32_t kInstrDesc = (1u << 4) /*D = f32*/ | (2u << 7) /*A = tf32*/ | (2u << 10) /*B = tf32*/ | ((uint32_t)(BN >> 3) << 17) |
@@ -91,6 +94,19 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
                "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(x), "r"(y)
                : "memory");
 }
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int x, int y) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(x),
+               "r"(y)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 __device__ __forceinline__ void prefetch_tensormap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
@@ -145,11 +161,18 @@ __device__ __forceinline__ void tile_coords(int tile, int tiles_m, int tiles_n, 
 
 // ---- the GEMM ------------------------------------------------------------------------------------------------------------
 
-template <int BN>
+// Destinations of the fused all-gather epilogue: one tensor map per rank, each describing THIS rank's row block [m_shard, N]
+// inside that rank's gathered C (so rows past the shard and columns past N are clipped by the TMA unit).
+struct GatherMaps {
+  CUtensorMap dst[kPeerMaxRanks];
+  int world;
+};
+
+template <int BN, bool kGather>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                    const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo, float* __restrict__ C, int M, int N, int Kp,
-                   int tiles_m, int tiles_n) {
+                   int tiles_m, int tiles_n, const __grid_constant__ GatherMaps gather) {
   constexpr int STAGES = Cfg<BN>::STAGES;
   constexpr int STAGE_BYTES = Cfg<BN>::STAGE_BYTES;
   constexpr int B_TILE_BYTES = Cfg<BN>::B_TILE_BYTES;
@@ -157,7 +180,9 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
   constexpr uint32_t kInstrDesc = Cfg<BN>::kInstrDesc;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024-byte alignment
-  const uint32_t bars = smem_base + STAGES * STAGE_BYTES;
+  constexpr int STAGING_BYTES = kGather ? Cfg<BN>::GATHER_STAGING_BYTES : 0;
+  const uint32_t staging = smem_base + STAGES * STAGE_BYTES;  // 1024-byte aligned (SWIZZLE_128B boxes)
+  const uint32_t bars = staging + STAGING_BYTES;
   // barrier layout (8 bytes each): full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], then the TMEM base address
   auto full_bar = [&](int s) { return bars + 8u * s; };
   auto empty_bar = [&](int s) { return bars + 8u * (STAGES + s); };
@@ -165,7 +190,7 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
   auto tmem_empty_bar = [&](int a) { return bars + 8u * (2 * STAGES + 2 + a); };
   const uint32_t tmem_slot = bars + 8u * (2 * STAGES + 4);
   uint8_t* smem_generic = smem_raw + (smem_base - smem_u32(smem_raw));
-  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_generic + STAGES * STAGE_BYTES + 8 * (2 * STAGES + 4));
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_generic + STAGES * STAGE_BYTES + STAGING_BYTES + 8 * (2 * STAGES + 4));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -177,6 +202,8 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
     prefetch_tensormap(&tm_a_lo);
     prefetch_tensormap(&tm_b_hi);
     prefetch_tensormap(&tm_b_lo);
+    if (kGather)
+      for (int d = 0; d < gather.world; ++d) prefetch_tensormap(&gather.dst[d]);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -262,6 +289,7 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
     // ===== epilogue: TMEM -> registers -> global =====
     const int ew = warp - 4;  // TMEM lanes [32*ew, 32*ew + 32)
     int it = 0;
+    int gchunk = 0;  // staging buffer parity (kGather)
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       int m_blk, n_blk;
       tile_coords(tile, tiles_m, tiles_n, m_blk, n_blk);
@@ -271,8 +299,34 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
       tc_fence_after();
       const int row = m_blk * BM + ew * 32 + lane;
       const int col0 = n_blk * BN;
-      float* out = C + (size_t)row * (size_t)N + (size_t)col0;
       const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * BN);
+      if constexpr (kGather) {
+        // TMEM -> registers -> swizzled smem staging -> one TMA store per rank (own HBM and every peer's over NVLink)
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          if (col0 + c * 32 >= N) break;
+          const uint32_t buf = staging + (uint32_t)((ew * 2 + (gchunk & 1)) * 4096);
+          if (lane == 0) bulk_wait_read<1>();  // the stores issued from this buffer two chunks ago have read it
+          __syncwarp();
+          uint32_t r[32];
+          tmem_ld_32x32(taddr + (uint32_t)(c * 32), r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const uint32_t dst = buf + (uint32_t)(lane * 128 + ((q ^ (lane & 7)) << 4));
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(r[4 * q]), "r"(r[4 * q + 1]), "r"(r[4 * q + 2]), "r"(r[4 * q + 3])
+                         : "memory");
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            for (int d = 0; d < gather.world; ++d) tma_store_2d(&gather.dst[d], buf, col0 + c * 32, m_blk * BM + ew * 32);
+            bulk_commit();
+          }
+          ++gchunk;
+        }
+      } else {
+      float* out = C + (size_t)row * (size_t)N + (size_t)col0;
       const bool row_ok = row < M;
       const bool vec_ok = (N & 3) == 0;  // 16-byte aligned row starts
 #pragma unroll 1
@@ -296,9 +350,12 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
         }
         __syncwarp();
       }
+      }
       tc_fence_before();
       mbar_arrive(tmem_empty_bar(acc));
     }
+    if (kGather && lane == 0) bulk_wait_all();  // every store (local and remote) has completed before this CTA retires
+    (void)gchunk;
   }
   tc_fence_before();
   __syncthreads();
@@ -407,12 +464,14 @@ int gemm_pick_bn(int64_t m, int64_t n, int sm_count) {
 }
 
 namespace {
-template <int BN>
-void launch_main(const GemmWorkspace& ws, float* c, int64_t m, int64_t n, int64_t kp, int sm_count, TensorMapEncodeFn encode, cudaStream_t stream) {
+template <int BN, bool kGather>
+void launch_main(const GemmWorkspace& ws, float* c, int64_t m, int64_t n, int64_t kp, int sm_count, TensorMapEncodeFn encode, cudaStream_t stream,
+                 const GatherMaps& gather) {
+  constexpr int SMEM = kGather ? Cfg<BN>::SMEM_BYTES_GATHER : Cfg<BN>::SMEM_BYTES;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_3xtf32_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM_BYTES);
-    if (e != cudaSuccess) fail(CC_ERR_CUDA, strprintf("cudaFuncSetAttribute(smem=%d): %s", Cfg<BN>::SMEM_BYTES, cudaGetErrorString(e)));
+    cudaError_t e = cudaFuncSetAttribute(gemm_3xtf32_kernel<BN, kGather>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    if (e != cudaSuccess) fail(CC_ERR_CUDA, strprintf("cudaFuncSetAttribute(smem=%d): %s", SMEM, cudaGetErrorString(e)));
     attr_set = true;
   }
   CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
@@ -423,13 +482,13 @@ void launch_main(const GemmWorkspace& ws, float* c, int64_t m, int64_t n, int64_
   const int tiles_m = (int)((m + BM - 1) / BM), tiles_n = (int)((n + BN - 1) / BN);
   int grid = tiles_m * tiles_n;
   if (grid > sm_count) grid = sm_count;
-  gemm_3xtf32_kernel<BN><<<grid, GEMM_THREADS, Cfg<BN>::SMEM_BYTES, stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, c, (int)m, (int)n, (int)kp, tiles_m, tiles_n);
-  check_launch("gemm_3xtf32");
+  gemm_3xtf32_kernel<BN, kGather><<<grid, GEMM_THREADS, SMEM, stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, c, (int)m, (int)n, (int)kp, tiles_m, tiles_n, gather);
+  check_launch(kGather ? "gemm_3xtf32 (all-gather epilogue)" : "gemm_3xtf32");
 }
-}  // namespace
 
-int launch_gemm_3xtf32(const float* a, const float* b, float* c, int64_t m, int64_t n, int64_t k, const GemmWorkspace& ws, int sm_count,
-                       TensorMapEncodeFn encode, cudaStream_t stream, bool b_panels_ready) {
+template <bool kGather>
+int launch_pipeline(const float* a, const float* b, float* c, int64_t m, int64_t n, int64_t k, const GemmWorkspace& ws, int sm_count,
+                    TensorMapEncodeFn encode, cudaStream_t stream, bool b_panels_ready, const GatherMaps& gather) {
   CC_REQUIRE(m >= 1 && n >= 1 && k >= 1 && m < (1ll << 31) && n < (1ll << 31) && k < (1ll << 31) - BK, CC_ERR_UNSUPPORTED,
              "gemm_3xtf32: bad shape %lld x %lld x %lld", (long long)m, (long long)n, (long long)k);
   CC_REQUIRE(encode, CC_ERR_NO_DRIVER, "cuTensorMapEncodeTiled unavailable");
@@ -444,11 +503,39 @@ int launch_gemm_3xtf32(const float* a, const float* b, float* c, int64_t m, int6
     check_launch("split_transpose_b");
   }
   switch (gemm_pick_bn(m, n, sm_count)) {
-    case 256: launch_main<256>(ws, c, m, n, kp, sm_count, encode, stream); break;
-    case 128: launch_main<128>(ws, c, m, n, kp, sm_count, encode, stream); break;
-    default: launch_main<64>(ws, c, m, n, kp, sm_count, encode, stream); break;
+    case 256: launch_main<256, kGather>(ws, c, m, n, kp, sm_count, encode, stream, gather); break;
+    case 128: launch_main<128, kGather>(ws, c, m, n, kp, sm_count, encode, stream, gather); break;
+    default: launch_main<64, kGather>(ws, c, m, n, kp, sm_count, encode, stream, gather); break;
   }
   return b_panels_ready ? 2 : 3;
+}
+}  // namespace
+
+int launch_gemm_3xtf32(const float* a, const float* b, float* c, int64_t m, int64_t n, int64_t k, const GemmWorkspace& ws, int sm_count,
+                       TensorMapEncodeFn encode, cudaStream_t stream, bool b_panels_ready) {
+  GatherMaps none{};
+  return launch_pipeline<false>(a, b, c, m, n, k, ws, sm_count, encode, stream, b_panels_ready, none);
+}
+
+int launch_gemm_3xtf32_allgather(const float* a, const float* b, float* const* gathered_c, int world, int rank, int64_t m_shard, int64_t n, int64_t k,
+                                 const GemmWorkspace& ws, int sm_count, TensorMapEncodeFn encode, cudaStream_t stream, bool b_panels_ready) {
+  CC_REQUIRE(world >= 1 && world <= kPeerMaxRanks && rank >= 0 && rank < world, CC_ERR_ILLEGAL_ARGUMENT, "bad world / rank");
+  CC_REQUIRE(n % 4 == 0, CC_ERR_UNSUPPORTED, "the all-gather epilogue needs N %% 4 == 0 (16-byte row pitch for the TMA stores)");
+  CC_REQUIRE(encode, CC_ERR_NO_DRIVER, "cuTensorMapEncodeTiled unavailable");
+  GatherMaps g{};
+  g.world = world;
+  for (int d = 0; d < world; ++d) {
+    // rank `rank`'s row block inside rank d's gathered C: [m_shard, N] at row offset rank * m_shard
+    float* base = gathered_c[d] + (size_t)rank * (size_t)m_shard * (size_t)n;
+    cuuint64_t dims[2] = {(cuuint64_t)n, (cuuint64_t)m_shard};
+    cuuint64_t strides[1] = {(cuuint64_t)n * 4};
+    cuuint32_t box[2] = {32, 32};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = encode(&g.dst[d], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) fail(CC_ERR_CUDA, strprintf("cuTensorMapEncodeTiled(gather destination %d) failed (%d)", d, (int)r));
+  }
+  return launch_pipeline<true>(a, b, nullptr, m_shard, n, k, ws, sm_count, encode, stream, b_panels_ready, g);
 }
 
 }  // namespace cc

@@ -173,6 +173,18 @@ __global__ void __launch_bounds__(256) peer_allreduce_kernel(float* __restrict__
   }
 }
 
+// every rank raises its epoch flag in every peer's mailbox (after a system-scope fence, so everything this GPU wrote before —
+// including the previous kernel's stores into peer memory — is visible first) and waits for all peers' flags in its own
+__global__ void __launch_bounds__(32) peer_barrier_kernel(PeerMailboxes mb, unsigned epoch) {
+  const int parity = (int)(epoch & 1u);
+  if ((int)threadIdx.x < mb.world) {
+    const int peer = threadIdx.x;
+    __threadfence_system();
+    st_release_sys(mb.flags[peer] + mb_flag_index(parity, mb.world, mb.rank, 0), epoch);
+    wait_flag(mb.flags[mb.rank] + mb_flag_index(parity, mb.world, peer, 0), epoch);
+  }
+}
+
 __device__ __forceinline__ uint32_t wang_hash(uint32_t value) {  // T:106-117
   value = (value ^ 61u) ^ (value >> 16);
   value *= 9u;
@@ -257,6 +269,11 @@ void launch_peer_allreduce(float* v, uint64_t n, const PeerMailboxes& mb, unsign
   const unsigned blocks = (unsigned)((n + kPeerChunk - 1) / kPeerChunk);
   peer_allreduce_kernel<<<blocks, 256, 0, stream>>>(v, n, mb, epoch);
   check_launch("peer_allreduce");
+}
+
+void launch_peer_barrier(const PeerMailboxes& mb, unsigned epoch, cudaStream_t stream) {
+  peer_barrier_kernel<<<1, 32, 0, stream>>>(mb, epoch);
+  check_launch("peer_barrier");
 }
 
 void launch_reduce_sum_allreduce(const float* in, uint64_t n, float* out, float* scratch, unsigned* counter, int sm_count,

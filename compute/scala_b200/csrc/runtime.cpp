@@ -46,6 +46,7 @@ struct Buffer {
   std::atomic<int> rc{1};
   Mark last_write;
   std::vector<Mark> reads;  // at most one per stream
+  std::vector<CUdeviceptr> peers;  // symmetric buffers only: the same allocation on every rank (own pointer at own rank)
   uint64_t uid = 0;         // never reused: identity for the operand-panel cache
   uint64_t version = 0;     // bumped by every command that writes the buffer
 };
@@ -86,6 +87,7 @@ struct Nccl {
   CUdeviceptr peer_base[kPeerMaxRanks] = {0};
   PeerMailboxes mb{};
   unsigned epoch = 0;
+  std::vector<Buffer*> symmetric;  // cc_comm_symmetric_alloc results, freed when the communicator goes
   void load() {
     if (lib) return;
     lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
@@ -418,6 +420,15 @@ namespace {
 void close_peers(Nccl& n) {
   if (!n.peer_mapped) return;
   driver().cuCtxSynchronize();
+  for (Buffer* b : n.symmetric) {
+    for (int r = 0; r < (int)b->peers.size(); ++r)
+      if (r != n.rank && b->peers[(size_t)r]) driver().cuIpcCloseMemHandle(b->peers[(size_t)r]);
+    if (b->ptr) driver().cuMemFree(b->ptr);
+    b->ptr = 0;
+    b->peers.clear();
+    release(b);
+  }
+  n.symmetric.clear();
   for (int r = 0; r < n.n_ranks; ++r)
     if (r != n.rank && n.peer_base[r]) driver().cuIpcCloseMemHandle(n.peer_base[r]);
   if (n.mailbox) driver().cuMemFree(n.mailbox);
@@ -1300,6 +1311,102 @@ int cc_reduce_sum_allreduce(cc_buffer in, uint64_t n_floats, cc_buffer out, cons
     }
     r.stats.launches++;
     op_end(op, out_event);
+  });
+}
+
+int cc_comm_symmetric_alloc(uint64_t n_floats, cc_buffer* out) {
+  return guarded([&] {
+    Lock lock;
+    require_init();
+    Runtime& r = rt();
+    Nccl& n = r.nccl;
+    CC_REQUIRE(out && n_floats > 0, CC_ERR_ILLEGAL_ARGUMENT, "bad symmetric allocation request");
+    CC_REQUIRE(n.comm && n.peer_mapped, CC_ERR_ILLEGAL_ARGUMENT, "cc_comm_symmetric_alloc needs cc_comm_enable_peer first");
+    CUstream s0 = r.streams[0];
+    const size_t bytes = ((size_t)n_floats * 4 + 1023) / 1024 * 1024;
+    CUdeviceptr mine = 0;
+    CC_CU(cuMemAlloc(&mine, bytes));
+    CUipcMemHandle h;
+    CC_CU(cuIpcGetMemHandle(&h, mine));
+    CUdeviceptr send = 0, recv = 0;
+    CC_CU(cuMemAlloc(&send, 64));
+    CC_CU(cuMemAlloc(&recv, 64 * (size_t)n.n_ranks));
+    CC_CU(cuMemcpyHtoD(send, &h, 64));
+    n.check(n.AllGather((const void*)send, (void*)recv, 64, ncclChar, n.comm, (cudaStream_t)s0), "ncclAllGather(ipc handles)");
+    CC_CU(cuStreamSynchronize(s0));
+    std::vector<CUipcMemHandle> all((size_t)n.n_ranks);
+    CC_CU(cuMemcpyDtoH(all.data(), recv, 64 * (size_t)n.n_ranks));
+    driver().cuMemFree(send);
+    driver().cuMemFree(recv);
+    r.seq[0]++;
+    Buffer* b = new Buffer();
+    b->ptr = mine;
+    b->n_floats = n_floats;
+    b->owned = false;  // not pool memory: freed with the communicator
+    b->uid = r.next_uid++;
+    b->peers.assign((size_t)n.n_ranks, 0);
+    for (int q = 0; q < n.n_ranks; ++q) {
+      CUdeviceptr base = mine;
+      if (q != n.rank) {
+        CUresult res = driver().cuIpcOpenMemHandle(&base, all[(size_t)q], CU_IPC_MEM_LAZY_ENABLE_PEER_ACCESS);
+        if (res != CUDA_SUCCESS) {
+          for (int z = 0; z < q; ++z)
+            if (z != n.rank && b->peers[(size_t)z]) driver().cuIpcCloseMemHandle(b->peers[(size_t)z]);
+          driver().cuMemFree(mine);
+          delete b;
+          fail(CC_ERR_UNSUPPORTED, strprintf("cuIpcOpenMemHandle(rank %d) failed (%d)", q, (int)res));
+        }
+      }
+      b->peers[(size_t)q] = base;
+    }
+    b->rc.store(2);  // the caller's handle + the communicator's list
+    r.buffers.insert(b);
+    n.symmetric.push_back(b);
+    *out = (cc_buffer)(uintptr_t)b;
+  });
+}
+
+int cc_matmul_3xtf32_allgather(cc_buffer a, cc_buffer b, cc_buffer gathered, int64_t m_shard, int64_t n, int64_t k, const cc_event* waits, int n_waits,
+                               cc_event* out_event) {
+  return guarded([&] {
+    Lock lock;
+    require_init();
+    Runtime& r = rt();
+    Nccl& nc = r.nccl;
+    Buffer* ab = as_buffer(a);
+    Buffer* bb = as_buffer(b);
+    Buffer* gb = as_buffer(gathered);
+    CC_REQUIRE(nc.comm && nc.peer_mapped, CC_ERR_ILLEGAL_ARGUMENT, "cc_matmul_3xtf32_allgather needs cc_comm_enable_peer");
+    CC_REQUIRE((int)gb->peers.size() == nc.n_ranks, CC_ERR_ILLEGAL_ARGUMENT, "`gathered` must come from cc_comm_symmetric_alloc");
+    CC_REQUIRE(m_shard > 0 && n > 0 && k > 0 && n % 4 == 0, CC_ERR_UNSUPPORTED, "fused all-gather needs N %% 4 == 0 (got %lld x %lld x %lld)",
+               (long long)m_shard, (long long)n, (long long)k);
+    CC_REQUIRE(ab->n_floats >= (uint64_t)(m_shard * k) && bb->n_floats >= (uint64_t)(k * n) &&
+                   gb->n_floats >= (uint64_t)(m_shard * n) * (uint64_t)nc.n_ranks,
+               CC_ERR_ILLEGAL_ARGUMENT, "matmul buffers too small");
+    GemmRun g = gemm_prepare(bb, m_shard, n, k);
+    bool launched = false;
+    try {
+      Op op{0, {ab, bb}, {gb}};  // collectives stay on stream 0, in call order
+      g.declare(op);
+      op_begin(op, waits, n_waits);
+      // entry barrier: every rank has finished whatever still read its copy of `gathered` (stream order on each rank) ...
+      launch_peer_barrier(nc.mb, ++nc.epoch, (cudaStream_t)op.cu());
+      GemmWorkspace ws{(float*)g.a_hi->ptr, (float*)g.a_lo->ptr, (float*)g.bt_hi->ptr, (float*)g.bt_lo->ptr};
+      float* dst[kPeerMaxRanks] = {nullptr};
+      for (int q = 0; q < nc.n_ranks; ++q) dst[q] = (float*)gb->peers[(size_t)q];
+      int kernels = launch_gemm_3xtf32_allgather((const float*)ab->ptr, (const float*)bb->ptr, dst, nc.n_ranks, nc.rank, m_shard, n, k, ws,
+                                                 r.info.sm_count, (TensorMapEncodeFn)driver().cuTensorMapEncodeTiled, (cudaStream_t)op.cu(), g.b_ready);
+      // ... exit barrier: every rank's blocks have landed in every copy
+      launch_peer_barrier(nc.mb, ++nc.epoch, (cudaStream_t)op.cu());
+      launched = true;
+      r.stats.device_kernels += (uint64_t)kernels + 2;
+      r.stats.launches++;
+      op_end(op, out_event);
+    } catch (...) {
+      gemm_finish(g, bb, n, k, launched);
+      throw;
+    }
+    gemm_finish(g, bb, n, k, true);
   });
 }
 

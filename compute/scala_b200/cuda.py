@@ -84,6 +84,8 @@ def _L():
         L.cc_random_normal.argtypes = [h, u64, i32, hp]
         L.cc_matmul_3xtf32.argtypes = [h, h, h, C.c_int64, C.c_int64, C.c_int64, hp, C.c_int, hp]
         L.cc_set_operand_cache.argtypes = [C.c_int]
+        L.cc_comm_symmetric_alloc.argtypes = [u64, hp]
+        L.cc_matmul_3xtf32_allgather.argtypes = [h, h, h, C.c_int64, C.c_int64, C.c_int64, hp, C.c_int, hp]
         L.cc_stats.argtypes = [C.POINTER(_lib.Stats)]
         L.cc_timer_stop.argtypes = [fp]
         L.cc_comm_unique_id.argtypes = [C.c_void_p]
@@ -240,6 +242,11 @@ class Buffer:
         check(_L().cc_buffer_length(self.handle, C.byref(p)))
         return p.value
 
+    def share(self) -> "Buffer":
+        """another handle object on the same device buffer (DeviceBuffer.retain, OpenCL.scala:644)"""
+        check(_L().cc_buffer_retain(self.handle))
+        return Buffer(self.handle)
+
     def upload(self, host_ptr: int, n_floats: int) -> None:
         """async H2D (host memory must stay alive until the next synchronising call)"""
         ev = u64()
@@ -276,6 +283,18 @@ def reduce_sum(src: Buffer, n_floats: int, dst: Buffer) -> None:
 
 def matmul_3xtf32(a: Buffer, b: Buffer, c: Buffer, m: int, n: int, k: int) -> None:
     check(_L().cc_matmul_3xtf32(a.handle, b.handle, c.handle, m, n, k, None, 0, None))
+
+
+def comm_symmetric_alloc(n_floats: int) -> "Buffer":
+    """collective: the same allocation on every rank, mapped into every other rank over NVLink (CUDA IPC)"""
+    h = u64()
+    check(_L().cc_comm_symmetric_alloc(int(n_floats), C.byref(h)))
+    return Buffer(h.value)
+
+
+def matmul_3xtf32_allgather(a: "Buffer", b: "Buffer", gathered: "Buffer", m_shard: int, n: int, k: int) -> None:
+    """collective: row-sharded matmul whose epilogue stores the result blocks into `gathered` on every rank"""
+    check(_L().cc_matmul_3xtf32_allgather(a.handle, b.handle, gathered.handle, m_shard, n, k, None, 0, None))
 
 
 def set_operand_cache(on: bool) -> None:

@@ -70,6 +70,8 @@ class Communicator:
 
     def close(self) -> None:
         if self.world > 1:
+            for arena in self.__dict__.pop("_arenas", {}).values():
+                arena.release()
             self.cuda.comm_destroy()
 
     # ---- the three exchange patterns of the path -------------------------------------------------------------------------
@@ -118,9 +120,25 @@ class Communicator:
         part.release()
         return whole
 
-    def matmul_rows(self, a_shard, b_full, m_shard: int, n: int, k: int, gather: bool = False):
-        """C[rows of this rank, :] = A[rows of this rank, :] @ B — A and C row-sharded, B replicated; no exchange unless gathered"""
+    def gather_arena(self, n_floats: int):
+        """a symmetric (peer-mapped) buffer of at least n_floats, kept for reuse; collective on first use of a size"""
+        arenas = self.__dict__.setdefault("_arenas", {})
+        if n_floats not in arenas:
+            arenas[n_floats] = self.cuda.comm_symmetric_alloc(n_floats)
+        return arenas[n_floats]
+
+    def matmul_rows(self, a_shard, b_full, m_shard: int, n: int, k: int, gather: bool = False, fused: bool | None = None):
+        """C[rows of this rank, :] = A[rows of this rank, :] @ B — A and C row-sharded, B replicated; no exchange unless gathered.
+        With gather=True and the peer mailboxes mapped (equal shards, N % 4 == 0) the all-gather is fused into the contraction's
+        epilogue (TMA stores into every rank's copy over NVLink); the result is then a view of the communicator's arena, valid
+        until the next fused call of the same size. fused=False forces contraction + ncclAllGather."""
         cuda = self.cuda
+        if fused is None:
+            fused = self.peer
+        if gather and self.world > 1 and fused and self.peer and n % 4 == 0:
+            whole = self.gather_arena(m_shard * n * self.world)
+            cuda.matmul_3xtf32_allgather(a_shard, b_full, whole, m_shard, n, k)
+            return whole.share()
         c = cuda.Buffer.alloc(m_shard * n)
         cuda.matmul_3xtf32(a_shard, b_full, c, m_shard, n, k)
         if self.world == 1 or not gather:

@@ -216,6 +216,16 @@ int cc_comm_route_peer(int on);
 int cc_reduce_sum_allreduce(cc_buffer in, uint64_t n_floats, cc_buffer out, const cc_event* waits, int n_waits,
                             cc_event* out_event);
 int cc_allreduce_sum(cc_buffer buf, uint64_t n_floats, const cc_event* waits, int n_waits, cc_event* out_event);
+/* Symmetric memory: every rank allocates `n_floats` and maps every other rank's allocation (CUDA IPC over NVLink). Collective;
+ * needs cc_comm_enable_peer. The handle behaves like any cc_buffer; the memory itself lives until cc_comm_destroy. */
+int cc_comm_symmetric_alloc(uint64_t n_floats, cc_buffer* out);
+/* The row-sharded matmul (A and C row-sharded, B replicated) fused with the all-gather of its result in ONE tensor-core
+ * kernel: rank r computes C[r*m_shard .. (r+1)*m_shard, :] = A_shard * B and the epilogue TMA-stores every 32x32 block straight into
+ * `gathered` ([n_ranks * m_shard, N], from cc_comm_symmetric_alloc) on EVERY rank — its own HBM and the peers' over NVLink — so the
+ * exchange overlaps the MMAs tile by tile instead of following them as an ncclAllGather. Collective (same m_shard on every rank),
+ * bracketed by two flag barriers over the peer mailboxes. Needs N % 4 == 0. */
+int cc_matmul_3xtf32_allgather(cc_buffer a_shard, cc_buffer b, cc_buffer gathered, int64_t m_shard, int64_t n, int64_t k,
+                               const cc_event* waits, int n_waits, cc_event* out_event);
 /* recv[rank*n .. (rank+1)*n) = send[0..n) of every rank */
 int cc_allgather(cc_buffer send, cc_buffer recv, uint64_t n_floats_per_rank, const cc_event* waits, int n_waits,
                  cc_event* out_event);

@@ -209,6 +209,43 @@ def test_whole_tensor_fold_fuses_the_operand():
     assert L.cc_compile(blob, len(blob), C.byref(h)) == -6
 
 
+def convolute(inp, weight, bias):
+    """benchmarks.scala:463-556"""
+    batch, height, width, depth = inp.shape
+    kh, kw, _, filters = weight.shape
+    input_seq = inp.split(3)
+    bias_seq = bias.split(0)
+    outs = []
+    for f, khkwd in enumerate(weight.split(3)):
+        summands = []
+        for oy, kwd in zip(range(-(kh // 2), kh // 2 + 1), khkwd.split(0)):
+            for ox, d in zip(range(-(kw // 2), kw // 2 + 1), kwd.split(0)):
+                for in_c, w_c in zip(input_seq, d.split(0)):
+                    summands.append(in_c.translate([0, oy, ox]) * w_c.broadcast([batch, height, width]))
+        acc = summands[0]
+        for x in summands[1:]:
+            acc = acc + x
+        outs.append(bias_seq[f].broadcast([batch, height, width]) + acc)
+    return T.join(outs)
+
+
+def test_convolution_is_a_nested_reduction_with_an_epilogue():
+    # 3 x 3 x depth terms per output channel, affine in (kernel row, kernel column, channel); `bias + chain` is the epilogue
+    k = convolute(rnd([16, 32, 32, 8], 1), rnd([3, 3, 8, 8], 2), rnd([8], 3)).compile()
+    assert k.info.kind == 1 and k.info.n_args == 3
+    src = k.source
+    assert "Plus chain of 72 congruent terms re-rolled into a reduction over 3 x 3 x 8 with an elementwise epilogue" in src
+    assert "T=3x3x8" in src and "epilogue=1" in src and "post(acc" in src
+    assert "cc_ldc4(p1" in src  # the weights are reused by every output pixel: L1-cached loads
+    # padding tests survive only where the 3x3 window can leave the image (rows / columns), never on batch or channel
+    assert "i0_1 >= 0 && i0_1 < 32 && i0_2 >= 0 && i0_2 < 32" in src and "i0_0" not in src and "i0_3" not in src
+    # an epilogue around a plain per-axis sum
+    x, b = rnd([64, 512], 1), rnd([512], 2)
+    e = T.tanh(axis_sum(x, 0) + b)
+    ke = e.compile()
+    assert ke.info.kind == 1 and "with an elementwise epilogue" in ke.source and "cc_tanh" in ke.source
+
+
 def test_join_is_rerolled_into_an_output_dimension():
     t = rnd([16, 8, 32])
     k = T.join(t.split(1)).compile()

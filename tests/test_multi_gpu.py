@@ -74,6 +74,24 @@ def _worker(rank, world, port):
         A, B = cuda.Buffer.from_host(a[ms : ms + mn]), cuda.Buffer.from_host(b)
         Cw = comm.matmul_rows(A, B, mn, nn, k, gather=True)
         assert np.array_equal(Cw.to_host(m * nn).reshape(m, nn), (a.astype(np.float64) @ b.astype(np.float64)).astype(np.float32))
+        # the same exchange fused into the contraction's epilogue (TMA stores into every rank's copy over NVLink), vs NCCL
+        for (m, k, nn) in ((512, 256, 512), (2 * 200, 96, 132), (2 * 1000, 300, 1000)):
+            a = (np.floor(ref.random_buffer(m * k, 9) * 9) - 4).astype(np.float32).reshape(m, k)
+            b = (np.floor(ref.random_buffer(k * nn, 10) * 9) - 4).astype(np.float32).reshape(k, nn)
+            ms, mn = sharding.shard_rows(m, world, rank)
+            A2, B2 = cuda.Buffer.from_host(a[ms : ms + mn]), cuda.Buffer.from_host(b)
+            want = (a.astype(np.float64) @ b.astype(np.float64)).astype(np.float32)
+            for rep in range(3):  # back to back: the entry barrier protects the arena of the previous round
+                s0 = cuda.stats()["device_kernels"]
+                Cf = comm.matmul_rows(A2, B2, mn, nn, k, gather=True, fused=True)
+                used = cuda.stats()["device_kernels"] - s0
+                assert used == (5 if rep == 0 else 4), used  # barrier, split A, (split B once), contraction + gather, barrier
+                assert np.array_equal(Cf.to_host(m * nn).reshape(m, nn), want), (m, k, nn, rep)
+                Cf.release()
+            Cn = comm.matmul_rows(A2, B2, mn, nn, k, gather=True, fused=False)
+            assert np.array_equal(Cn.to_host(m * nn).reshape(m, nn), want)
+            for x in (A2, B2, Cn):
+                x.release()
         for x in (s, c0, c1, A, B, Cw):
             x.release()
         cuda.synchronize()

@@ -365,3 +365,64 @@ def test_c5_never_materialises_the_product(cuda):
     after = cuda.stats()
     assert out.size == m * n
     assert after["bytes_in_use"] == before["bytes_in_use"]
+
+
+def _convolute(T, inp, weight, bias):
+    """benchmarks.scala:463-556 (the 8f-2 workload): split + translate + broadcast + join with padding"""
+    batch, height, width, depth = inp.shape
+    kh, kw, _, filters = weight.shape
+    input_seq = inp.split(3)
+    bias_seq = bias.split(0)
+    outs = []
+    for f, khkwd in enumerate(weight.split(3)):
+        summands = []
+        for oy, kwd in zip(range(-(kh // 2), kh // 2 + 1), khkwd.split(0)):
+            for ox, d in zip(range(-(kw // 2), kw // 2 + 1), kwd.split(0)):
+                for in_c, w_c in zip(input_seq, d.split(0)):
+                    summands.append(in_c.translate([0, oy, ox]) * w_c.broadcast([batch, height, width]))
+        acc = summands[0]
+        for x in summands[1:]:
+            acc = acc + x
+        outs.append(bias_seq[f].broadcast([batch, height, width]) + acc)
+    return T.join(outs)
+
+
+@pytest.mark.parametrize("batch,size,depth,filters,ks", [(4, 16, 8, 8, 3), (3, 9, 5, 6, 3), (2, 8, 16, 4, 1), (2, 12, 3, 7, 5)])
+def test_convolution_nested_reduction(cuda, batch, size, depth, filters, ks):
+    """the re-rolled (kernel row x kernel column x channel) reduction with its bias epilogue against a direct numpy convolution
+    on exactly representable data (bit-exact in any order) and against the oracle's literal evaluation of the same graph"""
+    T = cuda.Tensor
+    rng = np.random.default_rng(batch + size + depth)
+    inp = rng.integers(-3, 4, (batch, size, size, depth)).astype(np.float32)
+    w = rng.integers(-3, 4, (ks, ks, depth, filters)).astype(np.float32)
+    b = rng.integers(-8, 9, (filters,)).astype(np.float32) / np.float32(2.0)
+    e = _convolute(T, T(inp), T(w), T(b))
+    assert e.compile().info.kind == (1 if ks * ks * depth >= 8 else 0)
+    got = e.flatArray().reshape(batch, size, size, filters)
+    r = ks // 2
+    padded = np.zeros((batch, size + 2 * r, size + 2 * r, depth), np.float64)
+    padded[:, r : r + size, r : r + size, :] = inp
+    want = np.zeros((batch, size, size, filters), np.float64) + b
+    for ky in range(ks):
+        for kx in range(ks):
+            # out[y, x] += in[y - oy, x - ox] * w[ky, kx] with oy = ky - r (translate semantics, Tensors.scala:970-976)
+            oy, ox = ky - r, kx - r
+            window = padded[:, r - oy : r - oy + size, r - ox : r - ox + size, :]
+            want += np.einsum("bhwd,df->bhwf", window, w[ky, kx].astype(np.float64))
+    assert np.array_equal(got.astype(np.float64), want)
+    if batch * size * size * filters * ks * ks * depth <= 200000:
+        R = ref.Tensor
+        lit = _convolute(R, R(inp), R(w), R(b)).flat_array()
+        assert np.array_equal(got.reshape(-1).view(np.uint32), lit.view(np.uint32))
+
+
+def test_epilogue_around_an_axis_sum(cuda):
+    T = cuda.Tensor
+    x = dataset_e(T, [64, 512]).doCache()
+    b = T.random([512], seed=2).doCache()
+    e = T.tanh(axis_sum(T, x, 0) + b)
+    assert e.compile().info.kind == 1
+    got = e.flatArray()
+    cols = dataset_e_np(64 * 512).reshape(64, 512).astype(np.int64).sum(axis=0).astype(np.float32)
+    want = np.tanh((cols + ref.random_buffer(512, 2)).astype(np.float64))
+    assert np.abs(got - want).max() <= 4e-7  # tanh within 2 ulp of values in [-1, 1]
