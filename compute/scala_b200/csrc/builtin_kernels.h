@@ -53,7 +53,9 @@ struct GemmWorkspace {
 };
 // K rounded up to the pipeline's K step (32 floats): the row length of the four workspace panels
 int64_t gemm_padded_k(int64_t k);
-// output tile width (256 / 128 / 64) the launcher picks for an M x N problem on `sm_count` SMs
+// tile configuration the launcher picks for an M x N problem on `sm_count` SMs: 512 = 256 x 256 tiles on CTA pairs
+// (tcgen05 cta_group::2), 256 / 128 / 64 = 128 x that many columns on single CTAs
+int gemm_pick_config(int64_t m, int64_t n, int sm_count, bool allow_pair);
 int gemm_pick_bn(int64_t m, int64_t n, int sm_count);
 typedef CUresult (*TensorMapEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                       const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,

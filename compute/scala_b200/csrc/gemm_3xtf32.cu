@@ -18,7 +18,9 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstdint>
+#include <cstdlib>
 
 #include "builtin_kernels.h"
 #include "common.h"
@@ -365,6 +367,220 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
   }
 }
 
+// ---- the same GEMM on CTA pairs (cta_group::2) ----------------------------------------------------------------------------------
+//
+// ncu on the one-CTA kernel (profiles/r01b_gemm, 4096^3): tensor pipe 80 % active with each CTA pulling 96 KiB of operand panels per
+// 1536 MMA cycles (~64 B/clk/SM) through L2 -> shared memory. Two CTAs of one TPC cooperate on a 256 x 256 tile instead: each loads
+// its own 128 rows of A_hi / A_lo and only HALF of the B_hi / B_lo tile (128 of the 256 columns); the tensor cores of both SMs read
+// both halves (tcgen05.mma.cta_group::2, M = 256). 64 KiB per stage per CTA instead of 96 (a third less L2 / shared-memory traffic
+// for the same MMAs) and room for a third stage.
+//   CTA 0 (leader): issues every MMA and commit; its `full` barriers collect the TMA bytes of BOTH CTAs (2 x 64 KiB per stage);
+//   both CTAs: TMA producer for their own panels, epilogue for their own 128 accumulator rows (own TMEM);
+//   commits are multicast to both CTAs (stage free / accumulator ready); epilogue warps of both CTAs arrive on the leader's
+//   tmem_empty barriers (remote mbarrier arrive for CTA 1).
+constexpr int PAIR_BN = 256;
+constexpr int PAIR_STAGES = 3;
+constexpr int PAIR_B_HALF_BYTES = (PAIR_BN / 2) * BK * 4;                      // 16 KiB
+constexpr int PAIR_STAGE_BYTES = 2 * A_TILE_BYTES + 2 * PAIR_B_HALF_BYTES;     // 64 KiB per CTA
+constexpr int PAIR_SMEM_BYTES = PAIR_STAGES * PAIR_STAGE_BYTES + 1024 + 256;
+constexpr uint32_t kPairInstrDesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(PAIR_BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t smem_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t leader_bar, int x, int y) {
+  asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+               "l"(reinterpret_cast<uint64_t>(map)), "r"(leader_bar), "r"(x), "r"(y)
+               : "memory");
+}
+__device__ __forceinline__ void umma_tf32_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      :
+      : "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(kPairInstrDesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"((uint16_t)3)
+               : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+gemm_3xtf32_pair_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
+                        const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo, float* __restrict__ C, int M, int N,
+                        int Kp, int tiles_pm, int tiles_n) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bars = smem_base + PAIR_STAGES * PAIR_STAGE_BYTES;
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (PAIR_STAGES + s); };
+  auto tmem_full_bar = [&](int a) { return bars + 8u * (2 * PAIR_STAGES + a); };
+  auto tmem_empty_bar = [&](int a) { return bars + 8u * (2 * PAIR_STAGES + 2 + a); };
+  const uint32_t tmem_slot = bars + 8u * (2 * PAIR_STAGES + 4);
+  uint8_t* smem_generic = smem_raw + (smem_base - smem_u32(smem_raw));
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_generic + PAIR_STAGES * PAIR_STAGE_BYTES + 8 * (2 * PAIR_STAGES + 4));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();  // 0 = leader
+  const int pair = blockIdx.x >> 1;
+  const int num_pairs = gridDim.x >> 1;
+  const int num_tiles = tiles_pm * tiles_n;
+  const int num_kb = Kp / BK;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tensormap(&tm_a_hi);
+    prefetch_tensormap(&tm_a_lo);
+    prefetch_tensormap(&tm_b_hi);
+    prefetch_tensormap(&tm_b_lo);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < PAIR_STAGES; ++s) {
+      mbar_init(full_bar(s), 1);   // leader only: its own arrive.expect_tx; the bytes come from both CTAs' TMA loads
+      mbar_init(empty_bar(s), 1);  // one multicast commit
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tmem_full_bar(a), 1);     // one multicast commit
+      mbar_init(tmem_empty_bar(a), 256);  // leader only: the 128 epilogue threads of each CTA
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  cluster_sync_all();  // both CTAs' barriers are initialised before anybody signals across
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ===== TMA producer (both CTAs): own 128 rows of A_hi / A_lo, own 128 columns of B_hi / B_lo =====
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+        int m_blk, n_blk;
+        tile_coords(tile, tiles_pm, tiles_n, m_blk, n_blk);
+        const int row_a = m_blk * 256 + (int)rank * 128;
+        const int row_b = n_blk * PAIR_BN + (int)rank * (PAIR_BN / 2);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1);
+          const uint32_t st = smem_base + stage * PAIR_STAGE_BYTES;
+          const uint32_t leader_full = map_to_cta(full_bar(stage), 0);
+          if (rank == 0) mbar_arrive_expect_tx(full_bar(stage), 2 * PAIR_STAGE_BYTES);
+          tma_load_2d_pair(st, &tm_a_hi, leader_full, kb * BK, row_a);
+          tma_load_2d_pair(st + A_TILE_BYTES, &tm_a_lo, leader_full, kb * BK, row_a);
+          tma_load_2d_pair(st + 2 * A_TILE_BYTES, &tm_b_hi, leader_full, kb * BK, row_b);
+          tma_load_2d_pair(st + 2 * A_TILE_BYTES + PAIR_B_HALF_BYTES, &tm_b_lo, leader_full, kb * BK, row_b);
+          if (++stage == PAIR_STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1 && rank == 0) {
+    // ===== MMA issuer (leader CTA only) =====
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(tmem_empty_bar(acc), acc_phase ^ 1);  // both CTAs' epilogues have drained this accumulator
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + (uint32_t)(acc * PAIR_BN);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(full_bar(stage), phase);  // both CTAs' panels have landed
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t st = smem_base + stage * PAIR_STAGE_BYTES;
+          const uint64_t a_hi = umma_desc_sw128(st);
+          const uint64_t a_lo = umma_desc_sw128(st + A_TILE_BYTES);
+          const uint64_t b_hi = umma_desc_sw128(st + 2 * A_TILE_BYTES);
+          const uint64_t b_lo = umma_desc_sw128(st + 2 * A_TILE_BYTES + PAIR_B_HALF_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / 8; ++k) {
+            const uint64_t adv = (uint64_t)((k * 8 * 4) >> 4);
+            umma_tf32_pair(tmem_d, a_lo + adv, b_hi + adv, (kb | k) != 0);
+            umma_tf32_pair(tmem_d, a_hi + adv, b_lo + adv, 1);
+            umma_tf32_pair(tmem_d, a_hi + adv, b_hi + adv, 1);
+          }
+          umma_commit_pair(empty_bar(stage));                          // frees this stage in BOTH CTAs
+          if (kb == num_kb - 1) umma_commit_pair(tmem_full_bar(acc));  // accumulator complete in BOTH CTAs
+        }
+        __syncwarp();
+        if (++stage == PAIR_STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===== epilogue (both CTAs): own TMEM (128 rows of the pair's 256) -> registers -> global =====
+    const int ew = warp - 4;
+    int it = 0;
+    for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
+      int m_blk, n_blk;
+      tile_coords(tile, tiles_pm, tiles_n, m_blk, n_blk);
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(tmem_full_bar(acc), acc_phase);
+      tc_fence_after();
+      const int row = m_blk * 256 + (int)rank * 128 + ew * 32 + lane;
+      const int col0 = n_blk * PAIR_BN;
+      const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * PAIR_BN);
+      float* out = C + (size_t)row * (size_t)N + (size_t)col0;
+      const bool row_ok = row < M;
+      const bool vec_ok = (N & 3) == 0;
+#pragma unroll 1
+      for (int c = 0; c < PAIR_BN / 32; ++c) {
+        if (col0 + c * 32 >= N) break;
+        uint32_t r[32];
+        tmem_ld_32x32(taddr + (uint32_t)(c * 32), r);
+        tmem_ld_wait();
+        if (!row_ok) {
+        } else if (vec_ok && col0 + c * 32 + 32 <= N) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            float4 v = make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]), __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
+            __stcs(reinterpret_cast<float4*>(out + c * 32) + q, v);
+          }
+        } else {
+#pragma unroll
+          for (int q = 0; q < 32; ++q)
+            if (col0 + c * 32 + q < N) __stcs(out + c * 32 + q, __uint_as_float(r[q]));
+        }
+        __syncwarp();
+      }
+      tc_fence_before();
+      mbar_arrive_cluster(map_to_cta(tmem_empty_bar(acc), 0));  // the leader's barrier (a remote arrive from CTA 1)
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();  // nobody frees TMEM / exits while the peer may still read it or signal into it
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
 // ---- prologue: hi / lo split -------------------------------------------------------------------------------------------------
 
 __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
@@ -453,14 +669,34 @@ bool gemm_available() { return true; }
 
 int64_t gemm_padded_k(int64_t k) { return (k + BK - 1) / BK * BK; }
 
-int gemm_pick_bn(int64_t m, int64_t n, int sm_count) {
-  // the widest tile that still gives every SM a tile; problems too small for that take the narrowest tile (most CTAs)
-  const int64_t tiles_m = (m + BM - 1) / BM;
-  for (int bn : {256, 128, 64}) {
-    if (bn > 64 && n <= bn / 2) continue;  // a tile that would be more than half empty
-    if (tiles_m * ((n + bn - 1) / bn) >= sm_count) return bn;
+// Tile configuration for an M x N problem: 256 x 256 on CTA pairs, or 128 x {256, 128, 64} on single CTAs. Cost model = waves x
+// (tile time per SM) with the tensor-pipe efficiencies ncu measured for each variant (profiles/README.md): the wide tiles are the
+// most efficient per flop, the narrow ones fill the SMs on small problems.
+int gemm_pick_config(int64_t m, int64_t n, int sm_count, bool allow_pair) {
+  struct Cand {
+    int code, bm, bn, units_div;
+    double eff;
+  };
+  const Cand cands[4] = {{512, 256, 256, 2, 0.92}, {256, 128, 256, 1, 0.80}, {128, 128, 128, 1, 0.75}, {64, 128, 64, 1, 0.35}};
+  int best = 64;
+  double best_cost = 1e300;
+  for (const Cand& c : cands) {
+    if (c.code == 512 && (!allow_pair || m <= BM)) continue;
+    const int64_t tiles = ((m + c.bm - 1) / c.bm) * ((n + c.bn - 1) / c.bn);
+    const int64_t units = std::max(1, sm_count / c.units_div);
+    const int64_t waves = (tiles + units - 1) / units;
+    const double cost = (double)waves * (double)c.bn / c.eff;  // per-SM work of one tile is 128 x bn in every variant
+    if (cost < best_cost) {
+      best_cost = cost;
+      best = c.code;
+    }
   }
-  return 64;
+  return best;
+}
+
+int gemm_pick_bn(int64_t m, int64_t n, int sm_count) {
+  const int c = gemm_pick_config(m, n, sm_count, false);
+  return c;
 }
 
 namespace {
@@ -486,6 +722,25 @@ void launch_main(const GemmWorkspace& ws, float* c, int64_t m, int64_t n, int64_
   check_launch(kGather ? "gemm_3xtf32 (all-gather epilogue)" : "gemm_3xtf32");
 }
 
+void launch_pair(const GemmWorkspace& ws, float* c, int64_t m, int64_t n, int64_t kp, int sm_count, TensorMapEncodeFn encode, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_3xtf32_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM_BYTES);
+    if (e != cudaSuccess) fail(CC_ERR_CUDA, strprintf("cudaFuncSetAttribute(pair, smem=%d): %s", PAIR_SMEM_BYTES, cudaGetErrorString(e)));
+    attr_set = true;
+  }
+  CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
+  make_map(encode, &ma_hi, ws.a_hi, m, kp, BM);
+  make_map(encode, &ma_lo, ws.a_lo, m, kp, BM);
+  make_map(encode, &mb_hi, ws.bt_hi, n, kp, PAIR_BN / 2);
+  make_map(encode, &mb_lo, ws.bt_lo, n, kp, PAIR_BN / 2);
+  const int tiles_pm = (int)((m + 255) / 256), tiles_n = (int)((n + PAIR_BN - 1) / PAIR_BN);
+  int pairs = tiles_pm * tiles_n;
+  if (pairs > sm_count / 2) pairs = sm_count / 2;
+  gemm_3xtf32_pair_kernel<<<2 * pairs, GEMM_THREADS, PAIR_SMEM_BYTES, stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, c, (int)m, (int)n, (int)kp, tiles_pm, tiles_n);
+  check_launch("gemm_3xtf32 (CTA pairs)");
+}
+
 template <bool kGather>
 int launch_pipeline(const float* a, const float* b, float* c, int64_t m, int64_t n, int64_t k, const GemmWorkspace& ws, int sm_count,
                     TensorMapEncodeFn encode, cudaStream_t stream, bool b_panels_ready, const GatherMaps& gather) {
@@ -502,7 +757,14 @@ int launch_pipeline(const float* a, const float* b, float* c, int64_t m, int64_t
     split_transpose_b_kernel<<<dim3((unsigned)((n + 31) / 32), (unsigned)(kp / 32)), 256, 0, stream>>>(b, ws.bt_hi, ws.bt_lo, (int)k, (int)n, (int)kp);
     check_launch("split_transpose_b");
   }
-  switch (gemm_pick_bn(m, n, sm_count)) {
+  // CC_GEMM_FORCE_CONFIG = 512 | 256 | 128 | 64 pins the tile configuration (tests run every variant on the same shapes)
+  int config = gemm_pick_config(m, n, sm_count, !kGather);
+  if (const char* force = getenv("CC_GEMM_FORCE_CONFIG")) {
+    const int f = atoi(force);
+    if (f == 256 || f == 128 || f == 64 || (f == 512 && !kGather && m > BM)) config = f;
+  }
+  switch (config) {
+    case 512: launch_pair(ws, c, m, n, kp, sm_count, encode, stream); break;
     case 256: launch_main<256, kGather>(ws, c, m, n, kp, sm_count, encode, stream, gather); break;
     case 128: launch_main<128, kGather>(ws, c, m, n, kp, sm_count, encode, stream, gather); break;
     default: launch_main<64, kGather>(ws, c, m, n, kp, sm_count, encode, stream, gather); break;

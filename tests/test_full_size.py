@@ -71,6 +71,13 @@ def test_c3_sums_16384_squared(cuda):
     hi = he.astype(np.int64).reshape(rows, cols)
     assert np.abs(np.cumsum(he[: 1 << 20].astype(np.int64))).max() < 2**24  # partial sums stay exactly representable
     assert e.sum().flatArray()[0] == np.float32(hi.sum())  # bit-exact, any order
+    # the same sum with the dataset's closure fused into the fold kernel (nothing materialised), and the other monoids
+    r2 = T.random([rows, cols], seed=5)
+    inline_e = (r2 * T.fill(9.0, [rows, cols])) - (r2 * T.fill(9.0, [rows, cols])) % T.fill(1.0, [rows, cols]) - T.fill(4.0, [rows, cols])
+    fused = inline_e.sum()
+    assert fused.compile().info.kind == 4
+    assert fused.flatArray()[0] == np.float32(hi.sum())
+    assert e.reduce("max").flatArray()[0] == he.max() and e.reduce("min").flatArray()[0] == he.min()  # (r * 9 can round up to 9.0)
 
     def axis_sum(x, axis):
         parts = x.split(axis)

@@ -43,9 +43,11 @@ def test_exact_on_small_integers(cuda, m, n, k):
 
 
 # ragged shapes: M / N edges are TMA out-of-bounds zero fill in + predicated stores out, K is zero-padded in the workspace;
-# the tile width (256 / 128 / 64) is picked per problem, so these also cover every instantiation of the pipeline
+# the tile width (256 / 128 / 64) is picked per problem, so these also cover every instantiation of the pipeline; the last four
+# are large enough for 256-wide tiles and run on CTA pairs (tcgen05.mma.cta_group::2), with ragged M / N / K and an odd tile count
 @pytest.mark.parametrize("m,n,k", [(1, 1, 1), (5, 7, 9), (127, 255, 31), (129, 257, 33), (200, 100, 50), (1000, 1000, 1000), (333, 64, 70),
-                                   (2048, 96, 40), (77, 1030, 129), (4096, 32, 32), (130, 66, 2051), (19000, 130, 64)])
+                                   (2048, 96, 40), (77, 1030, 129), (4096, 32, 32), (130, 66, 2051), (19000, 130, 64), (20000, 520, 40), (19072, 256, 32),
+                                   (37888, 512, 256)])
 def test_exact_on_small_integers_any_shape(cuda, m, n, k):
     rng = np.random.default_rng(m * 7 + n * 3 + k)
     a = rng.integers(-4, 5, (m, k)).astype(np.float32)
@@ -53,6 +55,18 @@ def test_exact_on_small_integers_any_shape(cuda, m, n, k):
     got = run_matmul(cuda, a, b)
     want = (a.astype(np.float64) @ b.astype(np.float64)).astype(np.float32)
     assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("config", [512, 256, 128, 64])
+@pytest.mark.parametrize("m,n,k", [(300, 260, 40), (129, 1, 1), (1000, 513, 200), (2048, 2048, 96)])
+def test_every_tile_configuration_on_the_same_shapes(cuda, monkeypatch, config, m, n, k):
+    """512 = 256x256 tiles on CTA pairs (tcgen05.mma.cta_group::2, 3 stages), 256 / 128 / 64 = one CTA per 128 x that many columns"""
+    monkeypatch.setenv("CC_GEMM_FORCE_CONFIG", str(config))
+    rng = np.random.default_rng(m + n + k + config)
+    a = rng.integers(-4, 5, (m, k)).astype(np.float32)
+    b = rng.integers(-4, 5, (k, n)).astype(np.float32)
+    got = run_matmul(cuda, a, b)
+    assert np.array_equal(got, (a.astype(np.float64) @ b.astype(np.float64)).astype(np.float32))
 
 
 def test_ragged_edges_do_not_write_outside_the_result(cuda):
