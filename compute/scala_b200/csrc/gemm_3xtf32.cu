@@ -383,6 +383,8 @@ constexpr int PAIR_STAGES = 3;
 constexpr int PAIR_B_HALF_BYTES = (PAIR_BN / 2) * BK * 4;                      // 16 KiB
 constexpr int PAIR_STAGE_BYTES = 2 * A_TILE_BYTES + 2 * PAIR_B_HALF_BYTES;     // 64 KiB per CTA
 constexpr int PAIR_SMEM_BYTES = PAIR_STAGES * PAIR_STAGE_BYTES + 1024 + 256;
+constexpr int PAIR_STAGING_BYTES = 4 * 2 * 4096;  // all-gather epilogue: per epilogue warp two 32 x 128-byte staging buffers
+constexpr int PAIR_SMEM_BYTES_GATHER = PAIR_SMEM_BYTES + PAIR_STAGING_BYTES;
 constexpr uint32_t kPairInstrDesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(PAIR_BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -420,20 +422,24 @@ __device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
                : "memory");
 }
 
+template <bool kGather>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm_3xtf32_pair_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                         const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo, float* __restrict__ C, int M, int N,
-                        int Kp, int tiles_pm, int tiles_n) {
+                        int Kp, int tiles_pm, int tiles_n, const __grid_constant__ GatherMaps gather) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bars = smem_base + PAIR_STAGES * PAIR_STAGE_BYTES;
+  constexpr int STAGING_BYTES = kGather ? PAIR_STAGING_BYTES : 0;
+  const uint32_t staging = smem_base + PAIR_STAGES * PAIR_STAGE_BYTES;
+  const uint32_t bars = staging + STAGING_BYTES;
   auto full_bar = [&](int s) { return bars + 8u * s; };
   auto empty_bar = [&](int s) { return bars + 8u * (PAIR_STAGES + s); };
   auto tmem_full_bar = [&](int a) { return bars + 8u * (2 * PAIR_STAGES + a); };
   auto tmem_empty_bar = [&](int a) { return bars + 8u * (2 * PAIR_STAGES + 2 + a); };
   const uint32_t tmem_slot = bars + 8u * (2 * PAIR_STAGES + 4);
   uint8_t* smem_generic = smem_raw + (smem_base - smem_u32(smem_raw));
-  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_generic + PAIR_STAGES * PAIR_STAGE_BYTES + 8 * (2 * PAIR_STAGES + 4));
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(smem_generic + PAIR_STAGES * PAIR_STAGE_BYTES + STAGING_BYTES + 8 * (2 * PAIR_STAGES + 4));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -448,6 +454,8 @@ gemm_3xtf32_pair_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __gri
     prefetch_tensormap(&tm_a_lo);
     prefetch_tensormap(&tm_b_hi);
     prefetch_tensormap(&tm_b_lo);
+    if (kGather)
+      for (int d = 0; d < gather.world; ++d) prefetch_tensormap(&gather.dst[d]);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < PAIR_STAGES; ++s) {
@@ -536,6 +544,7 @@ gemm_3xtf32_pair_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __gri
     // ===== epilogue (both CTAs): own TMEM (128 rows of the pair's 256) -> registers -> global =====
     const int ew = warp - 4;
     int it = 0;
+    int gchunk = 0;
     for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
       int m_blk, n_blk;
       tile_coords(tile, tiles_pm, tiles_n, m_blk, n_blk);
@@ -546,6 +555,31 @@ gemm_3xtf32_pair_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __gri
       const int row = m_blk * 256 + (int)rank * 128 + ew * 32 + lane;
       const int col0 = n_blk * PAIR_BN;
       const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * PAIR_BN);
+      if constexpr (kGather) {
+#pragma unroll 1
+        for (int c = 0; c < PAIR_BN / 32; ++c) {
+          if (col0 + c * 32 >= N) break;
+          const uint32_t buf = staging + (uint32_t)((ew * 2 + (gchunk & 1)) * 4096);
+          if (lane == 0) bulk_wait_read<1>();
+          __syncwarp();
+          uint32_t r[32];
+          tmem_ld_32x32(taddr + (uint32_t)(c * 32), r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const uint32_t dst = buf + (uint32_t)(lane * 128 + ((q ^ (lane & 7)) << 4));
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(r[4 * q]), "r"(r[4 * q + 1]), "r"(r[4 * q + 2]), "r"(r[4 * q + 3])
+                         : "memory");
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            for (int d = 0; d < gather.world; ++d) tma_store_2d(&gather.dst[d], buf, col0 + c * 32, m_blk * 256 + (int)rank * 128 + ew * 32);
+            bulk_commit();
+          }
+          ++gchunk;
+        }
+      } else {
       float* out = C + (size_t)row * (size_t)N + (size_t)col0;
       const bool row_ok = row < M;
       const bool vec_ok = (N & 3) == 0;
@@ -569,9 +603,12 @@ gemm_3xtf32_pair_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __gri
         }
         __syncwarp();
       }
+      }
       tc_fence_before();
       mbar_arrive_cluster(map_to_cta(tmem_empty_bar(acc), 0));  // the leader's barrier (a remote arrive from CTA 1)
     }
+    if (kGather && lane == 0) bulk_wait_all();
+    (void)gchunk;
   }
   tc_fence_before();
   cluster_sync_all();  // nobody frees TMEM / exits while the peer may still read it or signal into it
@@ -722,11 +759,14 @@ void launch_main(const GemmWorkspace& ws, float* c, int64_t m, int64_t n, int64_
   check_launch(kGather ? "gemm_3xtf32 (all-gather epilogue)" : "gemm_3xtf32");
 }
 
-void launch_pair(const GemmWorkspace& ws, float* c, int64_t m, int64_t n, int64_t kp, int sm_count, TensorMapEncodeFn encode, cudaStream_t stream) {
+template <bool kGather>
+void launch_pair(const GemmWorkspace& ws, float* c, int64_t m, int64_t n, int64_t kp, int sm_count, TensorMapEncodeFn encode, cudaStream_t stream,
+                 const GatherMaps& gather) {
+  constexpr int SMEM = kGather ? PAIR_SMEM_BYTES_GATHER : PAIR_SMEM_BYTES;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_3xtf32_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM_BYTES);
-    if (e != cudaSuccess) fail(CC_ERR_CUDA, strprintf("cudaFuncSetAttribute(pair, smem=%d): %s", PAIR_SMEM_BYTES, cudaGetErrorString(e)));
+    cudaError_t e = cudaFuncSetAttribute(gemm_3xtf32_pair_kernel<kGather>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    if (e != cudaSuccess) fail(CC_ERR_CUDA, strprintf("cudaFuncSetAttribute(pair, smem=%d): %s", SMEM, cudaGetErrorString(e)));
     attr_set = true;
   }
   CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
@@ -737,8 +777,8 @@ void launch_pair(const GemmWorkspace& ws, float* c, int64_t m, int64_t n, int64_
   const int tiles_pm = (int)((m + 255) / 256), tiles_n = (int)((n + PAIR_BN - 1) / PAIR_BN);
   int pairs = tiles_pm * tiles_n;
   if (pairs > sm_count / 2) pairs = sm_count / 2;
-  gemm_3xtf32_pair_kernel<<<2 * pairs, GEMM_THREADS, PAIR_SMEM_BYTES, stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, c, (int)m, (int)n, (int)kp, tiles_pm, tiles_n);
-  check_launch("gemm_3xtf32 (CTA pairs)");
+  gemm_3xtf32_pair_kernel<kGather><<<2 * pairs, GEMM_THREADS, SMEM, stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, c, (int)m, (int)n, (int)kp, tiles_pm, tiles_n, gather);
+  check_launch(kGather ? "gemm_3xtf32 (CTA pairs, all-gather epilogue)" : "gemm_3xtf32 (CTA pairs)");
 }
 
 template <bool kGather>
@@ -758,13 +798,13 @@ int launch_pipeline(const float* a, const float* b, float* c, int64_t m, int64_t
     check_launch("split_transpose_b");
   }
   // CC_GEMM_FORCE_CONFIG = 512 | 256 | 128 | 64 pins the tile configuration (tests run every variant on the same shapes)
-  int config = gemm_pick_config(m, n, sm_count, !kGather);
+  int config = gemm_pick_config(m, n, sm_count, true);
   if (const char* force = getenv("CC_GEMM_FORCE_CONFIG")) {
     const int f = atoi(force);
-    if (f == 256 || f == 128 || f == 64 || (f == 512 && !kGather && m > BM)) config = f;
+    if (f == 256 || f == 128 || f == 64 || (f == 512 && m > BM)) config = f;
   }
   switch (config) {
-    case 512: launch_pair(ws, c, m, n, kp, sm_count, encode, stream); break;
+    case 512: launch_pair<kGather>(ws, c, m, n, kp, sm_count, encode, stream, gather); break;
     case 256: launch_main<256, kGather>(ws, c, m, n, kp, sm_count, encode, stream, gather); break;
     case 128: launch_main<128, kGather>(ws, c, m, n, kp, sm_count, encode, stream, gather); break;
     default: launch_main<64, kGather>(ws, c, m, n, kp, sm_count, encode, stream, gather); break;

@@ -81,12 +81,16 @@ def _worker(rank, world, port):
             ms, mn = sharding.shard_rows(m, world, rank)
             A2, B2 = cuda.Buffer.from_host(a[ms : ms + mn]), cuda.Buffer.from_host(b)
             want = (a.astype(np.float64) @ b.astype(np.float64)).astype(np.float32)
-            for rep in range(3):  # back to back: the entry barrier protects the arena of the previous round
+            for rep, config in enumerate((None, None, "512", "256", "64")):  # back to back: the entry barrier protects the arena
+                # every tile configuration of the gather epilogue: CTA pairs (cta_group::2) and single CTAs
+                if config:
+                    os.environ["CC_GEMM_FORCE_CONFIG"] = config
                 s0 = cuda.stats()["device_kernels"]
                 Cf = comm.matmul_rows(A2, B2, mn, nn, k, gather=True, fused=True)
                 used = cuda.stats()["device_kernels"] - s0
+                os.environ.pop("CC_GEMM_FORCE_CONFIG", None)
                 assert used == (5 if rep == 0 else 4), used  # barrier, split A, (split B once), contraction + gather, barrier
-                assert np.array_equal(Cf.to_host(m * nn).reshape(m, nn), want), (m, k, nn, rep)
+                assert np.array_equal(Cf.to_host(m * nn).reshape(m, nn), want), (m, k, nn, rep, config)
                 Cf.release()
             Cn = comm.matmul_rows(A2, B2, mn, nn, k, gather=True, fused=False)
             assert np.array_equal(Cn.to_host(m * nn).reshape(m, nn), want)
