@@ -168,6 +168,7 @@ __device__ __forceinline__ void tile_coords(int tile, int tiles_m, int tiles_n, 
 struct GatherMaps {
   CUtensorMap dst[kPeerMaxRanks];
   int world;
+  int rank;
 };
 
 template <int BN, bool kGather>
@@ -322,7 +323,12 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) {
-            for (int d = 0; d < gather.world; ++d) tma_store_2d(&gather.dst[d], buf, col0 + c * 32, m_blk * BM + ew * 32);
+            // staggered: at any moment every rank targets a different peer (no inbound hot spot), own HBM first
+            for (int i = 0; i < gather.world; ++i) {
+              int d = gather.rank + i;
+              if (d >= gather.world) d -= gather.world;
+              tma_store_2d(&gather.dst[d], buf, col0 + c * 32, m_blk * BM + ew * 32);
+            }
             bulk_commit();
           }
           ++gchunk;
@@ -574,7 +580,11 @@ gemm_3xtf32_pair_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __gri
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) {
-            for (int d = 0; d < gather.world; ++d) tma_store_2d(&gather.dst[d], buf, col0 + c * 32, m_blk * 256 + (int)rank * 128 + ew * 32);
+            for (int i = 0; i < gather.world; ++i) {  // staggered destinations, see the one-CTA kernel
+              int d = gather.rank + i;
+              if (d >= gather.world) d -= gather.world;
+              tma_store_2d(&gather.dst[d], buf, col0 + c * 32, m_blk * 256 + (int)rank * 128 + ew * 32);
+            }
             bulk_commit();
           }
           ++gchunk;
@@ -826,6 +836,7 @@ int launch_gemm_3xtf32_allgather(const float* a, const float* b, float* const* g
   CC_REQUIRE(encode, CC_ERR_NO_DRIVER, "cuTensorMapEncodeTiled unavailable");
   GatherMaps g{};
   g.world = world;
+  g.rank = rank;
   for (int d = 0; d < world; ++d) {
     // rank `rank`'s row block inside rank d's gathered C: [m_shard, N] at row offset rank * m_shard
     float* base = gathered_c[d] + (size_t)rank * (size_t)m_shard * (size_t)n;
