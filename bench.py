@@ -89,6 +89,26 @@ def c2_chain(T, a, b, c):
     return w + c
 
 
+def convolute(T, inp, weight, bias):
+    """benchmarks.scala:463-556, written the way the reference writes it: split / translate / broadcast / join"""
+    batch, height, width, depth = inp.shape
+    kh, kw, _, filters = weight.shape
+    input_seq = inp.split(3)
+    bias_seq = bias.split(0)
+    outs = []
+    for f, khkwd in enumerate(weight.split(3)):
+        summands = []
+        for oy, kwd in zip(range(-(kh // 2), kh // 2 + 1), khkwd.split(0)):
+            for ox, d in zip(range(-(kw // 2), kw // 2 + 1), kwd.split(0)):
+                for in_c, w_c in zip(input_seq, d.split(0)):
+                    summands.append(in_c.translate([0, oy, ox]) * w_c.broadcast([batch, height, width]))
+        acc = summands[0]
+        for x in summands[1:]:
+            acc = acc + x
+        outs.append(bias_seq[f].broadcast([batch, height, width]) + acc)
+    return T.join(outs)
+
+
 # ---- reference arm: the CPU port of the generated kernel on the host cores -----------------------------------------------
 
 
@@ -191,6 +211,10 @@ def side_configs(cuda, hbm_peak: float, tf_peak: float) -> dict:
             acc = acc + p
         return acc
 
+    # Tensor.sum of an inline expression folds its closure inside the reduction kernel (12 B/element, nothing materialised)
+    a3, b3, c3 = (T.random([ROWS, COLS], seed=s).doCache() for s in (1, 2, 3))
+    measure("sum of the C2 chain 16384^2, fused into one fold kernel", lambda: c2_chain(T, a3, b3, c3).sum(), 12 * ROWS * COLS + 4)
+    del a3, b3, c3
     measure("C3 axis-0 sum 16384^2", lambda: axis(0), 4 * ROWS * COLS + 4 * COLS)
     measure("C3 axis-1 sum 16384^2", lambda: axis(1), 4 * ROWS * COLS + 4 * ROWS)
     del x
@@ -202,6 +226,22 @@ def side_configs(cuda, hbm_peak: float, tf_peak: float) -> dict:
     measure("C4 leading broadcast 512^2->512^3", lambda: m4.reshape([1, n4, n4]).broadcast([n4, n4, n4]), 4 * n4**2 + 4 * n4**3)
     measure("C4 split(1)/join round trip 512^3", lambda: T.join(t4.split(1)), 8 * n4**3)
     del t4, m4
+    # the reference's convolution benchmark (benchmarks.scala:412-622) at its own size and at a realistic one
+    for (cb, ch, cd) in ((128, 32, 8), (64, 56, 64)):
+        try:
+            ci, cw, cbias = (T.randomNormal(sh, seed=s).doCache() for sh, s in (([cb, ch, ch, cd], 1), ([3, 3, cd, cd], 2), ([cd], 3)))
+            e = convolute(T, ci, cw, cbias)
+            k = e.compile()
+            kind = k.info.kind
+            k.release()
+            ms, launches, _, _ = time_steps(cuda, lambda: e.doBuffer().release(), 10, 3)
+            per = ms / 10
+            flops = 2 * cb * ch * ch * cd * cd * 9
+            out[f"convolution 3x3 batch {cb} {ch}x{ch} depth {cd} (benchmarks.scala:463-556)"] = {
+                "ms": per, "tflops_fp32_fma": flops / per / 1e9, "plan": kind, "kernels_per_step": launches / 10}
+            del ci, cw, cbias, e
+        except Exception as ex:
+            out[f"convolution 3x3 batch {cb} {ch}x{ch} depth {cd} (benchmarks.scala:463-556)"] = {"error": str(ex)[:200]}
     n5 = 8192
     try:
         A, B = T.randomNormal([n5, n5], seed=9).doCache(), T.randomNormal([n5, n5], seed=10).doCache()
