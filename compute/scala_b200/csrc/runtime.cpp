@@ -67,6 +67,7 @@ struct Kernel {
   std::atomic<int> rc{1};
   uint64_t hash = 0;
   int last_hit = 0;
+  uint64_t last_use = 0;  // kernel-cache clock (LRU eviction when a limit is set)
 };
 
 struct Nccl {
@@ -124,6 +125,8 @@ struct Runtime {
   std::unordered_set<Event*> events;
   std::unordered_set<Kernel*> kernels;
   std::unordered_map<std::string, Kernel*> cache;
+  uint64_t cache_clock = 0;
+  uint64_t cache_limit = 0;  // 0 = unbounded (the reference's default kernelCacheBuilder, Tensors.scala:1267-1277)
   cc_stats_t stats{};
   // B^T hi / lo panels of recent contractions, kept while the B buffer is unchanged (same uid and write version)
   struct Panels {
@@ -393,6 +396,20 @@ void release(Kernel* k) {
   r.kernels.erase(k);
   if (k->mod && r.initialized) driver().cuModuleUnload(k->mod);
   delete k;
+}
+
+// drop least-recently-used kernels beyond the limit (RemovalListener -> monadicClose, Tensors.scala:1267-1277); handles held by
+// callers stay valid until released
+void evict_kernels() {
+  Runtime& r = rt();
+  while (r.cache_limit && r.cache.size() > r.cache_limit) {
+    auto victim = r.cache.begin();
+    for (auto it = r.cache.begin(); it != r.cache.end(); ++it)
+      if (it->second->last_use < victim->second->last_use) victim = it;
+    Kernel* k = victim->second;
+    r.cache.erase(victim);
+    release(k);
+  }
 }
 
 void join_all(int target) {
@@ -821,6 +838,7 @@ int cc_compile_ex(const void* blob, uint64_t n_bytes, cc_kernel* out, uint64_t* 
       Kernel* k = it->second;
       k->rc.fetch_add(1);
       k->last_hit = 1;
+      k->last_use = ++r.cache_clock;
       r.stats.cache_hits++;
       *out = (cc_kernel)(uintptr_t)k;
       return;
@@ -841,9 +859,38 @@ int cc_compile_ex(const void* blob, uint64_t n_bytes, cc_kernel* out, uint64_t* 
     r.stats.compiles++;
     Kernel* raw = k.release();
     raw->rc.store(2);  // cache + caller
+    raw->last_use = ++r.cache_clock;
     r.kernels.insert(raw);
     r.cache.emplace(std::move(t.key), raw);
+    evict_kernels();
     *out = (cc_kernel)(uintptr_t)raw;
+  });
+}
+
+int cc_kernel_cache_limit(uint64_t max_kernels) {
+  return guarded([&] {
+    Lock lock;
+    rt().cache_limit = max_kernels;
+    if (rt().initialized) CC_CU(cuCtxSetCurrent(rt().ctx));
+    evict_kernels();
+  });
+}
+
+int cc_kernel_cache_clear(void) {
+  return guarded([&] {
+    Lock lock;
+    Runtime& r = rt();
+    if (r.initialized) CC_CU(cuCtxSetCurrent(r.ctx));
+    for (auto& kv : r.cache) release(kv.second);
+    r.cache.clear();
+  });
+}
+
+int cc_kernel_cache_size(uint64_t* out) {
+  return guarded([&] {
+    Lock lock;
+    CC_REQUIRE(out, CC_ERR_ILLEGAL_ARGUMENT, "null output");
+    *out = rt().cache.size();
   });
 }
 

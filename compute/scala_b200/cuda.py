@@ -84,6 +84,8 @@ def _L():
         L.cc_random_normal.argtypes = [h, u64, i32, hp]
         L.cc_matmul_3xtf32.argtypes = [h, h, h, C.c_int64, C.c_int64, C.c_int64, hp, C.c_int, hp]
         L.cc_set_operand_cache.argtypes = [C.c_int]
+        L.cc_kernel_cache_limit.argtypes = [u64]
+        L.cc_kernel_cache_size.argtypes = [hp]
         L.cc_comm_symmetric_alloc.argtypes = [u64, hp]
         L.cc_matmul_3xtf32_allgather.argtypes = [h, h, h, C.c_int64, C.c_int64, C.c_int64, hp, C.c_int, hp]
         L.cc_stats.argtypes = [C.POINTER(_lib.Stats)]
@@ -295,6 +297,21 @@ def comm_symmetric_alloc(n_floats: int) -> "Buffer":
 def matmul_3xtf32_allgather(a: "Buffer", b: "Buffer", gathered: "Buffer", m_shard: int, n: int, k: int) -> None:
     """collective: row-sharded matmul whose epilogue stores the result blocks into `gathered` on every rank"""
     check(_L().cc_matmul_3xtf32_allgather(a.handle, b.handle, gathered.handle, m_shard, n, k, None, 0, None))
+
+
+def kernel_cache_limit(max_kernels: int) -> None:
+    """0 = unbounded (reference default); otherwise LRU eviction (kernelCacheBuilder.maximumSize, Tensors.scala:1267-1277)"""
+    check(_L().cc_kernel_cache_limit(int(max_kernels)))
+
+
+def kernel_cache_clear() -> None:
+    check(_L().cc_kernel_cache_clear())
+
+
+def kernel_cache_size() -> int:
+    n = u64()
+    check(_L().cc_kernel_cache_size(C.byref(n)))
+    return n.value
 
 
 def set_operand_cache(on: bool) -> None:

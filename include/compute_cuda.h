@@ -142,6 +142,11 @@ int cc_compile(const void* tree_blob, uint64_t n_bytes, cc_kernel* out);
  * map cc_kernel_arg_param ordinals back to its own tensors. `param_ids_out` may be NULL. */
 int cc_compile_ex(const void* tree_blob, uint64_t n_bytes, cc_kernel* out, uint64_t* param_ids_out, int capacity,
                   int* n_params_out);
+/* kernelCache policy (T:1267-1289): the reference's cache is an overridable Guava CacheBuilder, unbounded by default. A non-zero
+ * limit evicts least-recently-used kernels (their modules unload once no caller holds them); clear = clearCache (T:1282-1285). */
+int cc_kernel_cache_limit(uint64_t max_kernels);
+int cc_kernel_cache_clear(void);
+int cc_kernel_cache_size(uint64_t* out);
 int cc_kernel_retain(cc_kernel k);
 int cc_kernel_release(cc_kernel k);
 

@@ -289,3 +289,23 @@ def test_deep_chains_do_not_overflow_the_stack():
     assert k.info.kind == 1
     del x, k
     assert cuda.live_tensors() >= 0
+
+
+def test_kernel_cache_policy():
+    """kernelCache (Tensors.scala:1267-1289): unbounded by default, an optional LRU limit, clearCache"""
+    cuda.kernel_cache_clear()
+    assert cuda.kernel_cache_size() == 0
+    ks = [(T.fill(float(i), [8]) + rnd([8])).compile() for i in range(6)]  # literals are part of the key: 6 kernels
+    assert cuda.kernel_cache_size() == 6
+    cuda.kernel_cache_limit(3)
+    assert cuda.kernel_cache_size() == 3
+    assert ks[0].source  # evicted from the cache but the caller's handle keeps it alive
+    before = cuda.stats()["compiles"]
+    again = (T.fill(5.0, [8]) + rnd([8])).compile()  # most recent: still cached
+    assert again.info.cache_hit == 1 and cuda.stats()["compiles"] == before
+    evicted = (T.fill(0.0, [8]) + rnd([8])).compile()  # oldest: compiled again
+    assert cuda.stats()["compiles"] == before + 1 and evicted.handle != ks[0].handle
+    assert cuda.kernel_cache_size() == 3
+    cuda.kernel_cache_limit(0)
+    cuda.kernel_cache_clear()
+    assert cuda.kernel_cache_size() == 0

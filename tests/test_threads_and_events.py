@@ -1,0 +1,97 @@
+"""GPU: the boundary's threading contract. The reference is driven by arbitrary threads (ExecutionContext.global,
+OpenCL.scala:414-416; JMH Threads.MAX, benchmarks.scala:56), orders commands by event wait lists rather than submission order
+(Tensors.scala:1363,1374) and resumes continuations from driver threads (clSetEventCallback, OpenCL.scala:379-392, 1246-1263)."""
+import ctypes as C
+import threading
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def cuda():
+    from compute.scala_b200 import cuda as c
+
+    c.init()
+    yield c
+    c.synchronize()
+
+
+def test_concurrent_callers(cuda):
+    T = cuda.Tensor
+    errors = []
+
+    def worker(tid):
+        try:
+            rng = np.random.default_rng(tid)
+            for it in range(25):
+                n = 48 + 8 * tid + it % 3
+                a = rng.integers(-4, 5, (n, n)).astype(np.float32)
+                b = rng.integers(-4, 5, (n, n)).astype(np.float32)
+                ta, tb = T(a), T(b)
+                got = (ta * tb + T.fill(float(tid), [n, n])).flatArray().reshape(n, n)
+                assert np.array_equal(got, a * b + np.float32(tid)), ("fused", tid, it)
+                assert (ta + tb).sum().flatArray()[0] == np.float32((a + b).astype(np.int64).sum()), ("sum", tid, it)
+                # out[i, j] = a[j + 1, i - 1] or padding 0 (permute then translate, one composed matrix)
+                v = ta.permute([1, 0]).translate([1, -1]).flatArray().reshape(n, n)
+                want = np.zeros((n, n), np.float32)
+                want[1:, : n - 1] = a.T[: n - 1, 1:]
+                assert np.array_equal(v, want), ("view", tid, it)
+                parts = ta.split(0)
+                acc = parts[0]
+                for p in parts[1:]:
+                    acc = acc + p
+                assert np.array_equal(acc.flatArray(), a.astype(np.int64).sum(axis=0).astype(np.float32)), ("axis", tid, it)
+        except BaseException as e:  # noqa: BLE001 — collected and re-raised on the main thread
+            errors.append(e)
+
+    threads = [threading.Thread(target=worker, args=(i,)) for i in range(8)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    if errors:
+        raise errors[0]
+    cuda.synchronize()
+
+
+def test_event_wait_lists_and_completion_callbacks(cuda):
+    L = cuda._L()
+    n = 1 << 20
+    host_in = np.arange(n, dtype=np.float32) % 251
+    host_out = np.zeros(n, np.float32)
+    # upload -> (event) -> kernel that waits on it -> (event) -> read-back that waits on it -> callback from a driver thread
+    buf, ev_up = C.c_uint64(), C.c_uint64()
+    cuda.check(L.cc_buffer_from_host(host_in.ctypes.data, n, C.byref(buf), C.byref(ev_up)))
+    src = cuda.Tensor.fromBuffer(cuda.Buffer(buf.value).share(), [n])
+    k = (src * cuda.Tensor.fill(2.0, [n]) + cuda.Tensor.fill(1.0, [n])).compile()
+    assert k.info.n_args == 1
+    out = cuda.Buffer.alloc(n)
+    ev_k, ev_down = C.c_uint64(), C.c_uint64()
+    args = (C.c_uint64 * 1)(buf.value)
+    waits = (C.c_uint64 * 1)(ev_up.value)
+    cuda.check(L.cc_launch(k.handle, args, 1, out.handle, waits, 1, C.byref(ev_k)))
+    waits2 = (C.c_uint64 * 1)(ev_k.value)
+    cuda.check(L.cc_buffer_to_host(out.handle, 0, host_out.ctypes.data, n, waits2, 1, C.byref(ev_down)))
+    fired = threading.Event()
+    seen = {}
+
+    @C.CFUNCTYPE(None, C.c_void_p, C.c_int)
+    def on_done(user, status):
+        seen["status"] = status
+        seen["thread"] = threading.get_ident()
+        fired.set()
+
+    cuda.check(L.cc_event_on_complete(ev_down.value, C.cast(on_done, C.c_void_p), None))
+    assert fired.wait(30.0), "completion callback never ran"
+    assert seen["status"] == 0 and seen["thread"] != threading.get_ident()
+    done = C.c_int()
+    cuda.check(L.cc_event_query(ev_down.value, C.byref(done)))
+    assert done.value == 1
+    assert np.array_equal(host_out, host_in * 2 + 1)
+    for e in (ev_up, ev_k, ev_down):
+        cuda.check(L.cc_event_release(e.value))
+    cuda.check(L.cc_buffer_release(buf.value))
+    out.release()
