@@ -66,6 +66,10 @@ typedef CUresult (*TensorMapEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint3
 int launch_gemm_3xtf32(const float* a, const float* b, float* c, int64_t m, int64_t n, int64_t k,
                        const GemmWorkspace& ws, int sm_count, TensorMapEncodeFn encode, cudaStream_t stream,
                        bool b_panels_ready = false);
+// Only the tensor-core pipeline: ws already holds all four K-major hi / lo panels ([M,Kp] and [N,Kp], Kp = gemm_padded_k(k)),
+// written by generated gather kernels (general contraction: convolution as an implicit GEMM).
+int launch_gemm_3xtf32_panels(float* c, int64_t m, int64_t n, int64_t k, const GemmWorkspace& ws, int sm_count,
+                              TensorMapEncodeFn encode, cudaStream_t stream);
 // The row-sharded matmul fused with the all-gather of its result: this rank computes C[rank*m_shard .. +m_shard, :] = A_shard * B
 // and the epilogue TMA-stores every 32x32 block of it straight into gathered_c[d] (rank d's [world*m_shard, N] result; own HBM for
 // d == rank, peer HBM over NVLink otherwise), so the transfer overlaps the MMAs tile by tile. Needs N % 4 == 0. The caller runs a

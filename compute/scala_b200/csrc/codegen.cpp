@@ -1215,6 +1215,169 @@ void emit_reduce(Plan& plan, const Program& p, int n_args, const DeviceProps& de
   plan.source += e.s;
 }
 
+// ---- general contraction: operand panels gathered by generated kernels -----------------------------------------------------
+//
+// A re-rolled reduction whose term is `load_a * load_b`, where load_a ignores the trailing output dims (the "N" dims) and load_b
+// ignores the leading ones (the "M" dims), is a GEMM C[M, N] = A[M, K] * B[K, N] over gathered operands: A[m, k] = load_a at
+// (m's output indices, k's reduction digits), B^T[n, k] likewise. The convolution of benchmarks.scala:463-556 is the case in point
+// (M = batch x height x width pixels, N = filters, K = kernel row x kernel column x channel, load_a = the translated, zero-padded
+// input: an implicit im2col). Two generated kernels write the K-major TF32 hi / lo panels the tcgen05 pipeline consumes straight
+// from the affine maps (bounds tests and padding included), the pipeline runs on them, and a third generated kernel applies the
+// epilogue (e.g. `bias +`) in place.
+void emit_panel_kernel(Emit& e, const Program& p, const char* name, int load, const std::vector<int>& row_dims, int n_args) {
+  const int nd = (int)p.dims.size();
+  const int R = p.n_red, no = nd - R;
+  int64_t rows = 1, K = 1;
+  for (int x : row_dims) rows *= p.dims[x];
+  for (int x = no; x < nd; ++x) K *= p.dims[x];
+  const int64_t Kp = (K + 31) / 32 * 32;
+  const char* IDX = pick_idx_type(p, std::max(rows * Kp, (int64_t)1));
+  e("// operand panel %s: rows=%lld K=%lld (padded %lld), load %d\n", name, (long long)rows, (long long)K, (long long)Kp, load);
+  e("extern \"C\" __global__ void __launch_bounds__(256) %s(%s%sfloat* __restrict__ hi, float* __restrict__ lo) {\n", name, param_list(n_args, false).c_str(),
+    n_args ? ", " : "");
+  e("  const %s v = (%s)blockIdx.x * 256 + threadIdx.x;\n  if (v >= (%s)%lld) return;\n", IDX, IDX, IDX, (long long)(rows * (Kp / 4)));
+  e("  const %s row = v / %lld;\n  const %s k0 = (v - row * %lld) * 4;\n", IDX, (long long)(Kp / 4), IDX, (long long)(Kp / 4));
+  // output indices of this row
+  e("  %s rr_ = row;\n", IDX);
+  for (size_t i = row_dims.size(); i-- > 0;) {
+    const int x = row_dims[i];
+    if (i == 0)
+      e("  const %s g%d = rr_;\n", IDX, x);
+    else
+      e("  const %s g%d = rr_ %% (%s)%lld; rr_ /= (%s)%lld;\n", IDX, x, IDX, (long long)p.dims[x], IDX, (long long)p.dims[x]);
+  }
+  const bool vec = p.dims[nd - 1] % 4 == 0;  // the 4 k's of a thread share every digit but the innermost: one decode, one (vector) load
+  if (vec) {
+    e("  float x[4] = {0.f, 0.f, 0.f, 0.f};\n  if (k0 < (%s)%lld) {\n    %s kr_ = k0;\n", IDX, (long long)K, IDX);
+    for (int x = nd - 1; x >= no; --x) {
+      if (x == no)
+        e("    const %s g%d = kr_;\n", IDX, x);
+      else
+        e("    const %s g%d = kr_ %% (%s)%lld; kr_ /= (%s)%lld;\n", IDX, x, IDX, (long long)p.dims[x], IDX, (long long)p.dims[x]);
+    }
+    LoadCtx c{4, nd - 1, IDX};
+    emit_load(e, p, load, c, "    ");
+    e("    #pragma unroll\n    for (int q = 0; q < 4; ++q) x[q] = L%d[q];\n  }\n", load);
+    e("  float hv[4], lv[4];\n  #pragma unroll\n  for (int q = 0; q < 4; ++q) cc_split_tf32(x[q], hv[q], lv[q]);\n");
+  } else {
+    e("  float hv[4], lv[4];\n  #pragma unroll\n  for (int q = 0; q < 4; ++q) {\n    const %s k = k0 + q;\n    float x = 0.f;\n    if (k < (%s)%lld) {\n", IDX,
+      IDX, (long long)K);
+    e("      %s kr_ = k;\n", IDX);
+    for (int x = nd - 1; x >= no; --x) {
+      if (x == no)
+        e("      const %s g%d = kr_;\n", IDX, x);
+      else
+        e("      const %s g%d = kr_ %% (%s)%lld; kr_ /= (%s)%lld;\n", IDX, x, IDX, (long long)p.dims[x], IDX, (long long)p.dims[x]);
+    }
+    LoadCtx c{1, -1, IDX};
+    emit_load(e, p, load, c, "      ");
+    e("      x = L%d[0];\n    }\n    cc_split_tf32(x, hv[q], lv[q]);\n  }\n", load);
+  }
+  e("  cc_stg4(hi + v * 4, hv);\n  cc_stg4(lo + v * 4, lv);\n}\n");
+}
+
+void emit_post_kernel(Emit& e, const Program& p, int n_args) {
+  const int nd = (int)p.dims.size();
+  const int no = nd - p.n_red;
+  std::vector<int64_t> odims(p.dims.begin(), p.dims.begin() + no);
+  const int64_t NOUT = product(odims);
+  const int V = (no >= 1 && odims[no - 1] % 4 == 0) ? 4 : 1;
+  const char* IDX = pick_idx_type(p, NOUT);
+  e("// epilogue applied in place to the contraction's result\n");
+  e("extern \"C\" __global__ void __launch_bounds__(256) post_kernel(%s%sfloat* __restrict__ out) {\n", param_list(n_args, false).c_str(), n_args ? ", " : "");
+  e("  const %s v = (%s)blockIdx.x * 256 + threadIdx.x;\n  if (v >= (%s)%lld) return;\n", IDX, IDX, IDX, (long long)(NOUT / V));
+  emit_decode(e, odims, no, IDX, strprintf("v * %d", V).c_str(), "  ");
+  e("  float acc[%d];\n", V);
+  if (V == 4)
+    e("  { const float4 t_ = *reinterpret_cast<const float4*>(out + v * 4); acc[0] = t_.x; acc[1] = t_.y; acc[2] = t_.z; acc[3] = t_.w; }\n");
+  else
+    e("  acc[0] = out[v];\n");
+  LoadCtx c{V, no - 1, IDX};
+  for (size_t j = 0; j < p.loads.size(); ++j)
+    if (j < p.load_in_post.size() && p.load_in_post[j]) emit_load(e, p, (int)j, c, "  ");
+  e("  #pragma unroll\n  for (int l = 0; l < %d; ++l) {\n", V);
+  emit_op_list(e, p.post_ops, "    ", "l", "q", "acc[l]");
+  e("    acc[l] = q%d;\n  }\n", p.post_result);
+  if (V == 4)
+    e("  cc_stg4(out + v * 4, acc);\n}\n");
+  else
+    e("  out[v] = acc[0];\n}\n");
+}
+
+// Tries to lower the reduction program to gathered panels + the tcgen05 pipeline. Returns false if the shape of the term does not fit.
+bool try_general_contraction(Plan& plan, const Program& p, int n_args) {
+  const int nd = (int)p.dims.size();
+  const int R = p.n_red, no = nd - R;
+  if (R < 1 || no < 2 || p.ops.size() != 3 || p.results.size() != 1) return false;
+  const Op& mul = p.ops[p.results[0]];
+  if (mul.kind != K_TIMES || mul.a == mul.b || p.ops[mul.a].kind != K_EXTRACT || p.ops[mul.b].kind != K_EXTRACT) return false;
+  int la = p.ops[mul.a].load, lb = p.ops[mul.b].load;
+  auto uses = [&](const Load& L, int x) {
+    for (int y = 0; y < L.rows; ++y)
+      if (L.M[(size_t)y * (nd + 1) + x] != 0.0) return true;
+    return false;
+  };
+  auto split_point = [&](const Load& A, const Load& B) {
+    // dims [0, s) not used by B, dims [s, no) not used by A
+    int s = 0;
+    while (s < no && !uses(B, s)) ++s;
+    for (int x = s; x < no; ++x)
+      if (uses(A, x)) return -1;
+    return (s >= 1 && s < no) ? s : -1;
+  };
+  int s = split_point(p.loads[la], p.loads[lb]);
+  if (s < 0) {
+    std::swap(la, lb);
+    s = split_point(p.loads[la], p.loads[lb]);
+    if (s < 0) return false;
+  }
+  int64_t M = 1, N = 1, K = 1;
+  for (int x = 0; x < s; ++x) M *= p.dims[x];
+  for (int x = s; x < no; ++x) N *= p.dims[x];
+  for (int x = no; x < nd; ++x) K *= p.dims[x];
+  int64_t min_macs = (int64_t)1 << 25;
+  if (const char* ev = getenv("CC_TUNE_CONTRACTION_MIN_MACS")) min_macs = atoll(ev);
+  // the gathered panels cost 8 bytes of HBM traffic per (row, k) each way, so this pays off when N (the reuse of an A row) is large
+  if (M * N * K < min_macs || N < 32 || K < 32 || M >= ((int64_t)1 << 31) || N >= ((int64_t)1 << 31) || K >= ((int64_t)1 << 31) - 32) return false;
+  const int64_t Kp = (K + 31) / 32 * 32;
+  if (M * Kp >= ((int64_t)1 << 40)) return false;
+  std::vector<int> m_dims, n_dims;
+  for (int x = 0; x < s; ++x) m_dims.push_back(x);
+  for (int x = s; x < no; ++x) n_dims.push_back(x);
+  Emit e;
+  emit_panel_kernel(e, p, "panel_a", la, m_dims, n_args);
+  emit_panel_kernel(e, p, "panel_b", lb, n_dims, n_args);
+  const bool has_post = !p.post_ops.empty() && !p.trivial_post();
+  if (has_post) emit_post_kernel(e, p, n_args);
+  plan.source += e.s;
+  auto add = [&](const char* entry, int64_t threads, std::vector<int> extra) {
+    LaunchSpec ls;
+    ls.entry = entry;
+    ls.grid[0] = (uint32_t)std::max<int64_t>(1, (threads + 255) / 256);
+    ls.block[0] = 256;
+    for (int i = 0; i < n_args; ++i) ls.args.push_back(i);
+    for (int a : extra) ls.args.push_back(a);
+    plan.launches.push_back(ls);
+  };
+  if (M * (Kp / 4) + 255 >= ((int64_t)1 << 31) * 256) return false;
+  add("panel_a", M * (Kp / 4), {ARG_SCRATCH0, ARG_SCRATCH0 - 1});
+  add("panel_b", N * (Kp / 4), {ARG_SCRATCH0 - 2, ARG_SCRATCH0 - 3});
+  if (has_post) {
+    const int V = (p.dims[no - 1] % 4 == 0) ? 4 : 1;
+    add("post_kernel", M * N / V, {ARG_OUT});
+  }
+  plan.kind = PLAN_CONTRACTION;
+  plan.M = M;
+  plan.N = N;
+  plan.K = K;
+  plan.gathered_panels = true;
+  plan.flops = 2ull * (uint64_t)M * (uint64_t)N * (uint64_t)K;
+  plan.scratch_floats = {(uint64_t)(M * Kp), (uint64_t)(M * Kp), (uint64_t)(N * Kp), (uint64_t)(N * Kp)};
+  plan.note += strprintf("; general contraction %lldx%lldx%lld over gathered operand panels -> tcgen05 3xTF32%s", (long long)M, (long long)N,
+                         (long long)K, has_post ? " + in-place epilogue" : "");
+  return true;
+}
+
 // ---- whole-tensor fold (Tensor.sum and the other monoids) with the operand's closure fused in -----------------------------
 //
 // Same schedule as the precompiled reduce_sum_kernel (kernels_basic.cu): 512 threads, grid <= 4 CTAs per SM, U independent
@@ -1561,6 +1724,7 @@ Plan make_plan(const Tree& t, const DeviceProps& dev) {
         }
       }
     }
+    if (dev.contraction && try_general_contraction(plan, prog, n_args)) return plan;
     emit_reduce(plan, prog, n_args, dev);
   } else {
     const int td = transpose_dim(prog);

@@ -33,7 +33,7 @@ struct LaunchSpec {
 struct Plan {
   int kind = PLAN_ELEMENTWISE;
   std::string source;                  // generated CUDA C++ (without the template prelude)
-  std::vector<LaunchSpec> launches;    // empty for PLAN_CONTRACTION (runs the precompiled tcgen05 pipeline)
+  std::vector<LaunchSpec> launches;    // empty for a plain PLAN_CONTRACTION (runs the precompiled tcgen05 pipeline)
   std::vector<uint32_t> arg_params;    // tree parameter ordinal of each buffer argument
   std::vector<uint64_t> arg_min_floats;  // minimum length each argument buffer must have
   std::vector<uint64_t> scratch_floats;
@@ -41,6 +41,9 @@ struct Plan {
   uint64_t algorithmic_bytes = 0;
   uint64_t flops = 0;
   int64_t M = 0, N = 0, K = 0;  // contraction
+  // contraction whose K-major hi / lo operand panels are written by generated kernels (launches[0] = panel_a, [1] = panel_b,
+  // optional [2] = post_kernel applied in place to the result) instead of the precompiled split kernels
+  bool gathered_panels = false;
   std::string note;             // human-readable description of the choices made (kept in the kernel source header)
 };
 

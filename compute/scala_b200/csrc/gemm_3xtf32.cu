@@ -793,7 +793,7 @@ void launch_pair(const GemmWorkspace& ws, float* c, int64_t m, int64_t n, int64_
 
 template <bool kGather>
 int launch_pipeline(const float* a, const float* b, float* c, int64_t m, int64_t n, int64_t k, const GemmWorkspace& ws, int sm_count,
-                    TensorMapEncodeFn encode, cudaStream_t stream, bool b_panels_ready, const GatherMaps& gather) {
+                    TensorMapEncodeFn encode, cudaStream_t stream, bool b_panels_ready, const GatherMaps& gather, bool a_panels_ready = false) {
   CC_REQUIRE(m >= 1 && n >= 1 && k >= 1 && m < (1ll << 31) && n < (1ll << 31) && k < (1ll << 31) - BK, CC_ERR_UNSUPPORTED,
              "gemm_3xtf32: bad shape %lld x %lld x %lld", (long long)m, (long long)n, (long long)k);
   CC_REQUIRE(encode, CC_ERR_NO_DRIVER, "cuTensorMapEncodeTiled unavailable");
@@ -801,8 +801,10 @@ int launch_pipeline(const float* a, const float* b, float* c, int64_t m, int64_t
   const size_t nvec = (size_t)(m * kp) / 4;
   size_t blocks = (nvec + 255) / 256;
   if (blocks > (size_t)sm_count * 8) blocks = (size_t)sm_count * 8;
-  split_a_kernel<<<(unsigned)blocks, 256, 0, stream>>>(a, ws.a_hi, ws.a_lo, (int)m, (int)k, (int)kp);
-  check_launch("split_a");
+  if (!a_panels_ready) {
+    split_a_kernel<<<(unsigned)blocks, 256, 0, stream>>>(a, ws.a_hi, ws.a_lo, (int)m, (int)k, (int)kp);
+    check_launch("split_a");
+  }
   if (!b_panels_ready) {
     split_transpose_b_kernel<<<dim3((unsigned)((n + 31) / 32), (unsigned)(kp / 32)), 256, 0, stream>>>(b, ws.bt_hi, ws.bt_lo, (int)k, (int)n, (int)kp);
     check_launch("split_transpose_b");
@@ -819,9 +821,15 @@ int launch_pipeline(const float* a, const float* b, float* c, int64_t m, int64_t
     case 128: launch_main<128, kGather>(ws, c, m, n, kp, sm_count, encode, stream, gather); break;
     default: launch_main<64, kGather>(ws, c, m, n, kp, sm_count, encode, stream, gather); break;
   }
-  return b_panels_ready ? 2 : 3;
+  return 1 + (a_panels_ready ? 0 : 1) + (b_panels_ready ? 0 : 1);
 }
 }  // namespace
+
+int launch_gemm_3xtf32_panels(float* c, int64_t m, int64_t n, int64_t k, const GemmWorkspace& ws, int sm_count, TensorMapEncodeFn encode,
+                              cudaStream_t stream) {
+  GatherMaps none{};
+  return launch_pipeline<false>(nullptr, nullptr, c, m, n, k, ws, sm_count, encode, stream, true, none, true);
+}
 
 int launch_gemm_3xtf32(const float* a, const float* b, float* c, int64_t m, int64_t n, int64_t k, const GemmWorkspace& ws, int sm_count,
                        TensorMapEncodeFn encode, cudaStream_t stream, bool b_panels_ready) {

@@ -37,6 +37,15 @@ __device__ __forceinline__ void cc_stg4(float* p, const float (&v)[4]) {
   asm volatile("st.global.cs.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]) : "memory");
 }
 
+// x = hi + lo with hi exactly representable in TF32 (top 19 bits) and lo = tf32(x - hi): the operand split of the 3xTF32 contraction
+__device__ __forceinline__ void cc_split_tf32(float x, float& hi, float& lo) {
+  hi = __uint_as_float(__float_as_uint(x) & 0xffffe000u);
+  const float r = x - hi;
+  unsigned t;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(r));
+  lo = __uint_as_float(t);
+}
+
 // ---- math -------------------------------------------------------------------------------------------------------------
 // CUDA's expf / logf / tanhf are documented at <= 2 / 1 / 2 ulp; kept behind cc_* names so that leaner or tighter
 // implementations can be swapped in without touching the generator.

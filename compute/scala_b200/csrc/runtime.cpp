@@ -914,7 +914,8 @@ int cc_kernel_info(cc_kernel h, cc_kernel_info_t* out) {
     out->kind = k->plan.kind;
     out->cache_hit = k->last_hit;
     out->n_args = (int32_t)k->plan.arg_params.size();
-    out->n_launches = k->plan.kind == PLAN_CONTRACTION ? 3 : (int32_t)k->plan.launches.size();  // 2 when B's panels are cached
+    out->n_launches = k->plan.kind == PLAN_CONTRACTION ? (k->plan.gathered_panels ? 1 + (int32_t)k->plan.launches.size() : 3)  // (2 when B's panels are cached)
+                                                        : (int32_t)k->plan.launches.size();
     out->out_floats = k->plan.out_floats;
     out->algorithmic_bytes = k->plan.algorithmic_bytes;
     out->flops = k->plan.flops;
@@ -1030,6 +1031,51 @@ int cc_launch(cc_kernel h, const cc_buffer* args, int n_args, cc_buffer out, con
       in.push_back(b);
     }
     ensure_loaded(*k);
+    auto launch_spec = [&](size_t li, const std::vector<Buffer*>& scratch, Buffer* shared_partials, CUstream stream) {
+      const LaunchSpec& ls = p.launches[li];
+      std::vector<CUdeviceptr> ptrs;
+      std::vector<void*> argv;
+      ptrs.reserve(ls.args.size());
+      for (int a : ls.args) {
+        if (a >= 0)
+          ptrs.push_back(in[a]->ptr);
+        else if (a == ARG_OUT)
+          ptrs.push_back(ob->ptr);
+        else if (a == ARG_REDUCE_PARTIALS)
+          ptrs.push_back(shared_partials->ptr);
+        else if (a == ARG_REDUCE_COUNTER)
+          ptrs.push_back(r.reduce_counter);
+        else
+          ptrs.push_back(scratch[ARG_SCRATCH0 - a]->ptr);
+      }
+      for (CUdeviceptr& q : ptrs) argv.push_back(&q);
+      CC_CU(cuLaunchKernel(k->fns[li], ls.grid[0], ls.grid[1], ls.grid[2], ls.block[0], ls.block[1], ls.block[2], ls.smem, stream, argv.data(),
+                           nullptr));
+      r.stats.device_kernels++;
+    };
+    if (p.kind == PLAN_CONTRACTION && p.gathered_panels) {
+      // general contraction: generated kernels gather the operand panels, the tcgen05 pipeline runs on them, then the epilogue
+      std::vector<Buffer*> scratch;
+      try {
+        for (uint64_t n : p.scratch_floats) scratch.push_back(alloc_buffer(n));
+        Op op{pick_stream(), in, {ob}};
+        for (Buffer* s : scratch) op.writes.push_back(s);
+        op_begin(op, waits, n_waits);
+        launch_spec(0, scratch, nullptr, op.cu());
+        launch_spec(1, scratch, nullptr, op.cu());
+        GemmWorkspace ws{(float*)scratch[0]->ptr, (float*)scratch[1]->ptr, (float*)scratch[2]->ptr, (float*)scratch[3]->ptr};
+        r.stats.device_kernels += (uint64_t)launch_gemm_3xtf32_panels((float*)ob->ptr, p.M, p.N, p.K, ws, r.info.sm_count,
+                                                                      (TensorMapEncodeFn)driver().cuTensorMapEncodeTiled, (cudaStream_t)op.cu());
+        if (p.launches.size() > 2) launch_spec(2, scratch, nullptr, op.cu());
+        r.stats.launches++;
+        op_end(op, out_event);
+      } catch (...) {
+        for (Buffer* s : scratch) release(s);
+        throw;
+      }
+      for (Buffer* s : scratch) release(s);
+      return;
+    }
     if (p.kind == PLAN_CONTRACTION) {
       GemmRun g = gemm_prepare(in[1], p.M, p.N, p.K);
       bool launched = false;
@@ -1056,30 +1102,7 @@ int cc_launch(cc_kernel h, const cc_buffer* args, int n_args, cc_buffer out, con
     for (Buffer* s : scratch) op.writes.push_back(s);
     if (shared_partials) op.writes.push_back(shared_partials);
     op_begin(op, waits, n_waits);
-    {
-      for (size_t li = 0; li < p.launches.size(); ++li) {
-        const LaunchSpec& ls = p.launches[li];
-        std::vector<CUdeviceptr> ptrs;
-        std::vector<void*> argv;
-        ptrs.reserve(ls.args.size());
-        for (int a : ls.args) {
-          if (a >= 0)
-            ptrs.push_back(in[a]->ptr);
-          else if (a == ARG_OUT)
-            ptrs.push_back(ob->ptr);
-          else if (a == ARG_REDUCE_PARTIALS)
-            ptrs.push_back(shared_partials->ptr);
-          else if (a == ARG_REDUCE_COUNTER)
-            ptrs.push_back(r.reduce_counter);
-          else
-            ptrs.push_back(scratch[ARG_SCRATCH0 - a]->ptr);
-        }
-        for (CUdeviceptr& q : ptrs) argv.push_back(&q);
-        CC_CU(cuLaunchKernel(k->fns[li], ls.grid[0], ls.grid[1], ls.grid[2], ls.block[0], ls.block[1], ls.block[2], ls.smem, op.cu(),
-                             argv.data(), nullptr));
-        r.stats.device_kernels++;
-      }
-    }
+    for (size_t li = 0; li < p.launches.size(); ++li) launch_spec(li, scratch, shared_partials, op.cu());
     r.stats.launches++;
     op_end(op, out_event);
     for (Buffer* s : scratch) release(s);

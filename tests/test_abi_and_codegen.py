@@ -239,6 +239,11 @@ def test_convolution_is_a_nested_reduction_with_an_epilogue():
     assert "cc_ldc4(p1" in src  # the weights are reused by every output pixel: L1-cached loads
     # padding tests survive only where the 3x3 window can leave the image (rows / columns), never on batch or channel
     assert "i0_1 >= 0 && i0_1 < 32 && i0_2 >= 0 && i0_2 < 32" in src and "i0_0" not in src and "i0_3" not in src
+    # large enough (and enough filters to reuse each gathered row): an implicit GEMM over gathered operand panels
+    big = convolute(rnd([64, 56, 56, 64], 1), rnd([3, 3, 64, 64], 2), rnd([64], 3)).compile()
+    assert big.info.kind == 2 and big.info.n_launches == 4 and big.info.flops == 2 * 64 * 56 * 56 * 64 * 576
+    assert "general contraction 200704x64x576 over gathered operand panels" in big.source
+    assert "panel_a" in big.source and "panel_b" in big.source and "post_kernel" in big.source and "cc_split_tf32" in big.source
     # an epilogue around a plain per-axis sum
     x, b = rnd([64, 512], 1), rnd([512], 2)
     e = T.tanh(axis_sum(x, 0) + b)

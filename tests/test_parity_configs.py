@@ -387,7 +387,8 @@ def _convolute(T, inp, weight, bias):
     return T.join(outs)
 
 
-@pytest.mark.parametrize("batch,size,depth,filters,ks", [(4, 16, 8, 8, 3), (3, 9, 5, 6, 3), (2, 8, 16, 4, 1), (2, 12, 3, 7, 5)])
+@pytest.mark.parametrize("batch,size,depth,filters,ks", [(4, 16, 8, 8, 3), (3, 9, 5, 6, 3), (2, 8, 16, 4, 1), (2, 12, 3, 7, 5), (8, 24, 32, 32, 3),
+                                                         (5, 20, 24, 40, 3)])
 def test_convolution_nested_reduction(cuda, batch, size, depth, filters, ks):
     """the re-rolled (kernel row x kernel column x channel) reduction with its bias epilogue against a direct numpy convolution
     on exactly representable data (bit-exact in any order) and against the oracle's literal evaluation of the same graph"""
@@ -397,7 +398,9 @@ def test_convolution_nested_reduction(cuda, batch, size, depth, filters, ks):
     w = rng.integers(-3, 4, (ks, ks, depth, filters)).astype(np.float32)
     b = rng.integers(-8, 9, (filters,)).astype(np.float32) / np.float32(2.0)
     e = _convolute(T, T(inp), T(w), T(b))
-    assert e.compile().info.kind == (1 if ks * ks * depth >= 8 else 0)
+    macs = batch * size * size * filters * ks * ks * depth
+    implicit_gemm = macs >= 2**25 and filters >= 32 and ks * ks * depth >= 32  # gathered panels -> tcgen05 (an implicit im2col)
+    assert e.compile().info.kind == (2 if implicit_gemm else 1 if ks * ks * depth >= 8 else 0)
     got = e.flatArray().reshape(batch, size, size, filters)
     r = ks // 2
     padded = np.zeros((batch, size + 2 * r, size + 2 * r, depth), np.float64)
@@ -426,3 +429,28 @@ def test_epilogue_around_an_axis_sum(cuda):
     cols = dataset_e_np(64 * 512).reshape(64, 512).astype(np.int64).sum(axis=0).astype(np.float32)
     want = np.tanh((cols + ref.random_buffer(512, 2)).astype(np.float64))
     assert np.abs(got - want).max() <= 4e-7  # tanh within 2 ulp of values in [-1, 1]
+
+
+def test_general_contraction_over_views(cuda):
+    """a matmul whose operands are views (A stored transposed, B read through a translate with padding) is still a GEMM over gathered
+    operands: generated kernels write the K-major TF32 panels from the affine maps and the tcgen05 pipeline runs on them"""
+    T = cuda.Tensor
+    m, k, n = 384, 320, 288
+    rng = np.random.default_rng(7)
+    at = rng.integers(-4, 5, (k, m)).astype(np.float32)       # A^T in memory
+    b = rng.integers(-4, 5, (k, n)).astype(np.float32)
+    A = T(at).permute([1, 0])                                  # [m, k] view
+    Bs = T(b).translate([2, 0])                                # rows shifted down by 2, first two rows = padding 0
+    # written the way benchmarks.scala:188-191 writes it, over the views
+    a3 = A.broadcast([m, k, n])
+    b3 = Bs.nonInline().reshape([1, k, n]).broadcast([m, k, n])
+    acc = axis_sum(T, a3 * b3, 1)
+    bs_host = np.zeros_like(b)
+    bs_host[2:] = b[:-2]
+    want = (at.T.astype(np.float64) @ bs_host.astype(np.float64)).astype(np.float32)
+    assert np.array_equal(acc.flatArray().reshape(m, n), want)
+    # the transposed operand alone (no materialisation of A): general contraction
+    acc2 = axis_sum(T, A.broadcast([m, k, n]) * T(b).reshape([1, k, n]).broadcast([m, k, n]), 1)
+    kern = acc2.compile()
+    assert kern.info.kind == 2 and "general contraction" in kern.source, kern.source[:300]
+    assert np.array_equal(acc2.flatArray().reshape(m, n), (at.T.astype(np.float64) @ b.astype(np.float64)).astype(np.float32))
