@@ -128,3 +128,30 @@ def test_c4_views_512_cubed(cuda):
     assert np.array_equal(bits(T.join(t.split(1)).flatArray()), bits(ht.transpose(0, 2, 1)))
     assert np.array_equal(bits(T.join(t.split(1), 1).flatArray()), bits(ht))
     assert np.array_equal(bits(t.permute([2, 0, 1]).permute([1, 2, 0]).flatArray()), bits(ht))
+
+
+def test_c5_matmul_pattern_8192(cuda):
+    """C5 at BASELINE size THROUGH the Tensor API, written as the reference writes it (benchmarks.scala:188-191): broadcast both
+    operands to [i, j, k], multiply, split(1), fold with +. Dataset E (integers in {-4..5}: every summation order is exact), checked on
+    sampled rows and through the checksum identity sum(C) = colsum(A) . rowsum(B)."""
+    T = cuda.Tensor
+    n = 8192
+    nine, four, one = T.fill(9.0, [n, n]), T.fill(4.0, [n, n]), T.fill(1.0, [n, n])
+
+    def dataset_e(seed):
+        r = T.random([n, n], seed=seed) * nine
+        return ((r - r % one) - four).doCache()
+
+    A, B = dataset_e(9), dataset_e(10)
+    product = A.broadcast([n, n, n]) * B.reshape([1, n, n]).broadcast([n, n, n])  # lazy: 2 TiB if it were ever materialised
+    parts = product.split(1)
+    acc = parts[0]
+    for p in parts[1:]:
+        acc = acc + p
+    k = acc.compile()
+    assert k.info.kind == 2 and k.info.n_args == 2 and k.info.flops == 2 * n**3
+    c = acc.flatArray().reshape(n, n)
+    a, b = A.flatArray().reshape(n, n), B.flatArray().reshape(n, n)
+    rows = np.r_[0:4, 255:258, 4095:4098, 8188:8192]
+    assert np.array_equal(c[rows].astype(np.float64), a[rows].astype(np.float64) @ b.astype(np.float64))
+    assert float(c.astype(np.float64).sum()) == float(a.astype(np.float64).sum(axis=0) @ b.astype(np.float64).sum(axis=1))
