@@ -804,9 +804,13 @@ void emit_elementwise(Plan& plan, const Program& p, int n_args, const DeviceProp
   const int nd = (int)p.dims.size();
   const int64_t total = product(p.dims);
   const int nres = (int)p.results.size();
-  int V = (nd >= 1 && p.dims[nd - 1] % 4 == 0 && nres == 1) ? 4 : 1;
-  const int64_t NV = total / V;
   const bool flat = program_is_flat(p);
+  int V = (nd >= 1 && p.dims[nd - 1] % 4 == 0 && nres == 1) ? 4 : 1;
+  // every load reads src[flat index]: the shape is irrelevant, vectorise over the flat index; the <= 3 leftover elements of an odd
+  // element count are done by scalar code in block 0
+  if (flat && nres == 1 && total >= 4) V = 4;
+  const int64_t NV = total / V;
+  const int64_t tail = total - NV * V;
   const char* IDX = pick_idx_type(p, total * std::max(1, nres));
   const int nloads = (int)p.loads.size();
   // Measured on B200 (scripts/gpu_sweep_c2.sh, profiles/r01_sweep_c2.log): one CTA per chunk (no persistence), 2 vectors in
@@ -884,7 +888,14 @@ void emit_elementwise(Plan& plan, const Program& p, int n_args, const DeviceProp
   e("    } else {\n");
   e("      for (int u = 0; u < %d; ++u) {\n        const %s v = v0 + u * 256;\n        if (v < NV) { Regs r; ld(v%s%s, r); st(v, r, out); }\n      }\n", U, IDX,
     n_args ? ", " : "", arg_pass(n_args).c_str());
-  e("    }\n  }\n}\n");
+  e("    }\n  }\n");
+  if (tail > 0) {
+    e("  if (blockIdx.x == 0 && threadIdx.x < %lld) {\n    const %s i = (%s)%lld + threadIdx.x;\n", (long long)tail, IDX, IDX, (long long)(NV * V));
+    for (int j = 0; j < nloads; ++j) e("    const float L%d[1] = {cc_ldg(p%d + i)};\n", j, p.loads[j].arg);
+    emit_ops(e, p, "    ", "0");
+    e("    out[i] = _%d;\n  }\n", p.results[0]);
+  }
+  e("}\n");
   plan.source += e.s;
   LaunchSpec ls;
   ls.entry = "jit_kernel";
@@ -1397,9 +1408,10 @@ const char* monoid_type(uint32_t m) {
 void emit_full_reduce(Plan& plan, const Program& p, int n_args, const DeviceProps& dev, uint32_t monoid) {
   const int nd = (int)p.dims.size();
   const int64_t total = product(p.dims);
-  const int V = (nd >= 1 && p.dims[nd - 1] % 4 == 0) ? 4 : 1;
-  const int64_t NV = total / V;
   const bool flat = program_is_flat(p);
+  const int V = ((nd >= 1 && p.dims[nd - 1] % 4 == 0) || (flat && total >= 4)) ? 4 : 1;
+  const int64_t NV = total / V;
+  const int64_t tail = total - NV * V;  // flat programs only: <= 3 leftover elements, folded by one designated thread
   const char* IDX = pick_idx_type(p, total + (int64_t)4 * kFullReduceMaxBlocks * kFullReduceThreads);
   const int nloads = (int)p.loads.size();
   const int U = nloads * V <= 16 ? 4 : (nloads * V <= 32 ? 2 : 1);
@@ -1455,6 +1467,13 @@ void emit_full_reduce(Plan& plan, const Program& p, int n_args, const DeviceProp
     e("  float acc = M::ap(M::ap(q[0], q[1]), M::ap(q[2], q[3]));\n");
   else
     e("  float acc = q[0];\n");
+  if (tail > 0) {
+    // same place as reduce_sum_kernel's scalar tail: thread 0 of block 0, after its own vectors
+    e("  if (blockIdx.x == 0 && threadIdx.x == 0) {\n    for (%s i = (%s)%lld; i < (%s)%lld; ++i) {\n", IDX, IDX, (long long)(NV * V), IDX, (long long)total);
+    for (int j = 0; j < nloads; ++j) e("      const float L%d[1] = {cc_ldg(p%d + i)};\n", j, p.loads[j].arg);
+    emit_ops(e, p, "      ", "0");
+    e("      acc = M::ap(acc, _%d);\n    }\n  }\n", p.results[0]);
+  }
   e("  acc = cc_block_fold<M>(acc, smem);\n  cc_fold_finish<M>(acc, out, partials, counter, smem);\n}\n");
   plan.source += e.s;
   LaunchSpec ls;
