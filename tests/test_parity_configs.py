@@ -235,7 +235,8 @@ def axis_sum(T, x, axis):
     return acc
 
 
-@pytest.mark.parametrize("shape,axis", [((512, 1024), 0), ((512, 1024), 1), ((256, 8, 12), 0), ((33, 70), 1), ((6, 9), 0)])
+@pytest.mark.parametrize("shape,axis", [((512, 1024), 0), ((512, 1024), 1), ((256, 8, 12), 0), ((33, 70), 1), ((6, 9), 0), ((100, 64), 0),
+                                        ((4099, 260), 0), ((3000, 7), 0)])
 def test_c3_axis_sums(cuda, shape, axis):
     T = cuda.Tensor
     n = int(np.prod(shape))
@@ -419,15 +420,16 @@ def test_convolution_nested_reduction(cuda, batch, size, depth, filters, ks):
         assert np.array_equal(got.reshape(-1).view(np.uint32), lit.view(np.uint32))
 
 
-def test_epilogue_around_an_axis_sum(cuda):
+@pytest.mark.parametrize("rows", [64, 4096])  # one CTA covers all of T / partials + second stage (epilogue applied there)
+def test_epilogue_around_an_axis_sum(cuda, rows):
     T = cuda.Tensor
-    x = dataset_e(T, [64, 512]).doCache()
+    x = dataset_e(T, [rows, 512]).doCache()
     b = T.random([512], seed=2).doCache()
-    e = T.tanh(axis_sum(T, x, 0) + b)
+    e = T.tanh(axis_sum(T, x, 0) * T.fill(1.0 / 64.0, [512]) + b)
     assert e.compile().info.kind == 1
     got = e.flatArray()
-    cols = dataset_e_np(64 * 512).reshape(64, 512).astype(np.int64).sum(axis=0).astype(np.float32)
-    want = np.tanh((cols + ref.random_buffer(512, 2)).astype(np.float64))
+    cols = dataset_e_np(rows * 512).reshape(rows, 512).astype(np.int64).sum(axis=0).astype(np.float32)
+    want = np.tanh((cols * np.float32(1.0 / 64.0) + ref.random_buffer(512, 2)).astype(np.float64))
     assert np.abs(got - want).max() <= 4e-7  # tanh within 2 ulp of values in [-1, 1]
 
 
