@@ -169,6 +169,9 @@ def time_steps(cuda, fn, steps: int, warmup: int):
     return ms, s1["device_kernels"] - s0["device_kernels"], w0, w1
 
 
+SHORT_SIDE = False
+
+
 def side_configs(cuda, hbm_peak: float, tf_peak: float) -> dict:
     """C1, C3, C4 (and C5 when the contraction is built) — short device-resident measurements for the same JSON line"""
     T = cuda.Tensor
@@ -200,7 +203,9 @@ def side_configs(cuda, hbm_peak: float, tf_peak: float) -> dict:
     n1 = 1024
     a1, b1, c1 = (T.random([n1, n1], seed=s).doCache() for s in (1, 2, 3))
     # a 5 us step: enough warm-up and steps that the clock ramp after the idle CPU-baseline phase is not what gets timed
-    measure("C1 tanh(a*b+c) 1024^2", lambda: T.tanh(a1 * b1 + c1), 16 * n1 * n1, steps=2000, warmup=2000)
+    # (--short-side: a handful of steps only, so that an ncu launch list of the whole run stays short)
+    n_c1 = 5 if SHORT_SIDE else 2000
+    measure("C1 tanh(a*b+c) 1024^2", lambda: T.tanh(a1 * b1 + c1), 16 * n1 * n1, steps=n_c1, warmup=n_c1)
     del a1, b1, c1
     x = T.random([ROWS, COLS], seed=5).doCache()
     measure("C3 full sum 16384^2", lambda: x.sum(), 4 * ROWS * COLS + 4)
@@ -530,8 +535,11 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-side-configs", action="store_true")
+    ap.add_argument("--short-side", action="store_true", help="few steps per side config (for ncu launch lists)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    global SHORT_SIDE
+    SHORT_SIDE = args.short_side
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
