@@ -569,40 +569,176 @@ const char* op_expr(uint32_t kind) {
   return "?";
 }
 
-// Emits the SSA body of the program for one lane; value names are _<op>; loads read `ldname(j)` .
-void emit_op_list(Emit& e, const std::vector<Op>& ops, const char* indent, const std::string& lane, const char* prefix = "_",
-                  const char* acc = nullptr) {
-  for (size_t i = 0; i < ops.size(); ++i) {
-    const Op& op = ops[i];
-    if (op.kind == K_ACC) {
-      e("%sconst float %s%zu = %s;\n", indent, prefix, i, acc);
-    } else if (op.kind == K_LITERAL) {
-      e("%sconst float %s%zu = %s;\n", indent, prefix, i, flit(op.lit).c_str());
-    } else if (op.kind == K_EXTRACT) {
-      e("%sconst float %s%zu = L%d[%s];\n", indent, prefix, i, op.load, lane.c_str());
+// ---- iterated maps ------------------------------------------------------------------------------------------------------
+//
+// `(0 until n).foldLeft(x)(f)` (benchmarks.scala:100-108 `a * b + c` folded 100 times, :319-326 `tanh` folded 100 times) arrives
+// as n copies of f's ops in the SSA list.  Emitted literally that is n inlined bodies per lane (NVRTC: 1.8 s for 100 x tanhf);
+// a run of R >= 8 identical periods of P ops whose operands are loop invariants, values of the same period or values of the
+// previous period is emitted as a counted loop with the previous-period values carried in registers.  Same operations in the
+// same order, so the result does not change.
+struct OpLoop {
+  int s = 0, P = 0, R = 0;              // ops [s, s + P * R) are R repetitions of a P-op period
+  std::vector<int> cls_a, cls_b;        // per position: -1 no operand, 0 invariant, 1 same period, 2 previous period
+  std::vector<char> keep;               // per position: value needed after an iteration (carried or read after the loop)
+  std::vector<int> init;                // per position: op holding the value carried into the first iteration (-1: none)
+};
+
+bool op_periodic(const std::vector<Op>& ops, int i, int P) {
+  const Op& x = ops[(size_t)i];
+  const Op& y = ops[(size_t)(i + P)];
+  if (x.kind != y.kind || x.kind == K_EXTRACT || x.kind == K_ACC) return false;
+  if (x.kind == K_LITERAL) return memcmp(&x.lit, &y.lit, 4) == 0;
+  auto rel = [&](int a, int b) { return a < 0 ? b < 0 : (b == a || b == a + P); };
+  return rel(x.a, y.a) && rel(x.b, y.b);
+}
+
+bool validate_loop(const std::vector<Op>& ops, const std::vector<int>& live, OpLoop& L) {
+  const int s = L.s, P = L.P, R = L.R, end = s + P * R;
+  L.cls_a.assign((size_t)P, -1);
+  L.cls_b.assign((size_t)P, -1);
+  L.keep.assign((size_t)P, 0);
+  L.init.assign((size_t)P, -1);
+  auto classify = [&](int j, int a0, int a1, int& cls) {  // operand of position j in repetition 0 / 1
+    if (a1 < 0) return true;
+    if (a1 == a0) {
+      cls = 0;
+      return a0 < s;
+    }
+    if (a1 >= s + P) {
+      cls = 1;
+      return true;
+    }
+    if (a1 < s) return false;  // reaches further back than one period
+    cls = 2;
+    const int jp = a1 - s;
+    if (L.init[(size_t)jp] >= 0 && L.init[(size_t)jp] != a0) return false;
+    if (a0 >= s) return false;
+    L.init[(size_t)jp] = a0;
+    L.keep[(size_t)jp] = 1;
+    (void)j;
+    return true;
+  };
+  for (int j = 0; j < P; ++j) {
+    const Op& r0 = ops[(size_t)(s + j)];
+    const Op& r1 = ops[(size_t)(s + P + j)];
+    if (!classify(j, r0.a, r1.a, L.cls_a[(size_t)j]) || !classify(j, r0.b, r1.b, L.cls_b[(size_t)j])) return false;
+  }
+  // every later repetition follows the same classes
+  for (int r = 1; r + 1 < R; ++r)
+    for (int j = 0; j < P; ++j) {
+      const Op& x = ops[(size_t)(s + r * P + j)];
+      const Op& y = ops[(size_t)(s + (r + 1) * P + j)];
+      auto same = [&](int a, int b, int cls) { return cls < 0 ? b < 0 : (cls == 0 ? b == a : b == a + P); };
+      if (!same(x.a, y.a, L.cls_a[(size_t)j]) || !same(x.b, y.b, L.cls_b[(size_t)j])) return false;
+    }
+  // values read after the loop must belong to the last repetition
+  auto outside_ref = [&](int a) {
+    if (a < s || a >= end) return true;
+    if (a < end - P) return false;
+    L.keep[(size_t)(a - (end - P))] = 1;
+    return true;
+  };
+  for (size_t i = (size_t)end; i < ops.size(); ++i) {
+    if (ops[i].kind == K_LITERAL || ops[i].kind == K_EXTRACT || ops[i].kind == K_ACC) continue;
+    if (!outside_ref(ops[i].a)) return false;
+    if (ops[i].b >= 0 && !outside_ref(ops[i].b)) return false;
+  }
+  for (int a : live)
+    if (!outside_ref(a)) return false;
+  return true;
+}
+
+std::vector<OpLoop> find_op_loops(const std::vector<Op>& ops, const std::vector<int>& live) {
+  std::vector<OpLoop> loops;
+  const int n = (int)ops.size();
+  constexpr int kMinReps = 8, kMaxPeriod = 64;
+  if (n < kMinReps || n > 200000) return loops;
+  if (const char* ev = getenv("CC_NO_OP_LOOPS"))  // A/B switch for tests: emit iterated maps unrolled, as the reference does
+    if (atoi(ev) != 0) return loops;
+  long budget = 4000000;
+  int i = 0;
+  while (i + kMinReps <= n && budget > 0) {
+    OpLoop best;
+    for (int P = 1; P <= kMaxPeriod && i + P * kMinReps <= n; ++P) {
+      int m = 0;
+      while (i + m + P < n && op_periodic(ops, i + m, P)) ++m;
+      budget -= m + 1;
+      const int R = m / P + 1;
+      if (R < kMinReps || P * R <= best.P * best.R) continue;
+      OpLoop c;
+      c.s = i;
+      c.P = P;
+      c.R = R;
+      if (validate_loop(ops, live, c)) best = std::move(c);
+      budget -= n;
+    }
+    if (best.R > 0) {
+      i = best.s + best.P * best.R;
+      loops.push_back(std::move(best));
     } else {
-      std::string a = strprintf("%s%d", prefix, op.a), b = strprintf("%s%d", prefix, op.b);
+      ++i;
+    }
+  }
+  return loops;
+}
+
+// Emits the SSA body of the program for one lane; value names are <prefix><op>; loads read L<j>[lane].  `live` lists the ops the
+// caller reads afterwards.
+void emit_op_list(Emit& e, const std::vector<Op>& ops, const char* indent, const std::string& lane, const std::vector<int>& live,
+                  const char* prefix = "_", const char* acc = nullptr) {
+  const std::vector<OpLoop> loops = find_op_loops(ops, live);
+  size_t next_loop = 0;
+  auto one = [&](const Op& op, const std::string& name, const std::string& a, const std::string& b, const char* ind) {
+    if (op.kind == K_ACC) {
+      e("%sconst float %s = %s;\n", ind, name.c_str(), acc);
+    } else if (op.kind == K_LITERAL) {
+      e("%sconst float %s = %s;\n", ind, name.c_str(), flit(op.lit).c_str());
+    } else if (op.kind == K_EXTRACT) {
+      e("%sconst float %s = L%d[%s];\n", ind, name.c_str(), op.load, lane.c_str());
+    } else {
       std::string fmt = op_expr(op.kind);
       std::string ex = is_unary(op.kind) ? strprintf(fmt.c_str(), a.c_str()) : strprintf(fmt.c_str(), a.c_str(), b.c_str());
-      e("%sconst float %s%zu = %s;\n", indent, prefix, i, ex.c_str());
+      e("%sconst float %s = %s;\n", ind, name.c_str(), ex.c_str());
     }
+  };
+  for (size_t i = 0; i < ops.size();) {
+    if (next_loop < loops.size() && (size_t)loops[next_loop].s == i) {
+      const OpLoop& L = loops[next_loop++];
+      const int last = L.s + L.P * (L.R - 1);
+      for (int j = 0; j < L.P; ++j)
+        if (L.keep[(size_t)j]) {
+          if (L.init[(size_t)j] >= 0)
+            e("%sfloat %s%d = %s%d;\n", indent, prefix, last + j, prefix, L.init[(size_t)j]);
+          else
+            e("%sfloat %s%d = 0.f;\n", indent, prefix, last + j);
+        }
+      const int unroll = L.P <= 4 ? 4 : (L.P <= 16 ? 2 : 1);
+      e("%s#pragma unroll %d\n%sfor (int it_ = 0; it_ < %d; ++it_) {  // %d x a period of %d ops\n", indent, unroll, indent, L.R, L.R, L.P);
+      const std::string ind2 = std::string(indent) + "  ";
+      for (int j = 0; j < L.P; ++j) {
+        const Op& op = ops[(size_t)(L.s + L.P + j)];  // repetition 1: its operand indices are in canonical position
+        auto nm = [&](int a, int cls) -> std::string {
+          if (cls == 0) return strprintf("%s%d", prefix, a);
+          if (cls == 1) return strprintf("t%d_", a - (L.s + L.P));
+          if (cls == 2) return strprintf("%s%d", prefix, last + (a - L.s));
+          return "";
+        };
+        one(op, strprintf("t%d_", j), nm(op.a, L.cls_a[(size_t)j]), nm(op.b, L.cls_b[(size_t)j]), ind2.c_str());
+      }
+      for (int j = 0; j < L.P; ++j)
+        if (L.keep[(size_t)j]) e("%s%s%d = t%d_;\n", ind2.c_str(), prefix, last + j, j);
+      e("%s}\n", indent);
+      i = (size_t)(L.s + L.P * L.R);
+      continue;
+    }
+    const Op& op = ops[i];
+    one(op, strprintf("%s%zu", prefix, i), strprintf("%s%d", prefix, op.a), strprintf("%s%d", prefix, op.b), indent);
+    ++i;
   }
 }
 
 void emit_ops(Emit& e, const Program& p, const char* indent, const std::string& lane) {
-  for (size_t i = 0; i < p.ops.size(); ++i) {
-    const Op& op = p.ops[i];
-    if (op.kind == K_LITERAL) {
-      e("%sconst float _%zu = %s;\n", indent, i, flit(op.lit).c_str());
-    } else if (op.kind == K_EXTRACT) {
-      e("%sconst float _%zu = L%d[%s];\n", indent, i, op.load, lane.c_str());
-    } else {
-      std::string a = strprintf("_%d", op.a), b = strprintf("_%d", op.b);
-      std::string fmt = op_expr(op.kind);
-      std::string ex = is_unary(op.kind) ? strprintf(fmt.c_str(), a.c_str()) : strprintf(fmt.c_str(), a.c_str(), b.c_str());
-      e("%sconst float _%zu = %s;\n", indent, i, ex.c_str());
-    }
-  }
+  emit_op_list(e, p.ops, indent, lane, p.results);
 }
 
 struct LoadCtx {
@@ -1062,7 +1198,7 @@ void emit_reduce(Plan& plan, const Program& p, int n_args, const DeviceProps& de
     for (int j = 0; j < nloads; ++j)
       if (in_post(j)) emit_load(e, p, j, c, "  ");
     e("  #pragma unroll\n  for (int l = 0; l < %d; ++l) {\n", V);
-    emit_op_list(e, p.post_ops, "    ", "l", "q", "acc[l]");
+    emit_op_list(e, p.post_ops, "    ", "l", {p.post_result}, "q", "acc[l]");
     e("    acc[l] = q%d;\n  }\n}\n", p.post_result);
   };
   std::string rd;
@@ -1093,7 +1229,7 @@ void emit_reduce(Plan& plan, const Program& p, int n_args, const DeviceProps& de
     for (int j = 0; j < nloads; ++j)
       if (!in_post(j)) emit_load(e, p, j, c, "  ");
     e("  #pragma unroll\n  for (int l = 0; l < %d; ++l) {\n", V);
-    emit_op_list(e, p.ops, "    ", "l");
+    emit_op_list(e, p.ops, "    ", "l", p.results);
     e("    o[l] = _%d;\n  }\n}\n", p.results[0]);
     e("__device__ __forceinline__ void ev(const %s t", IDX);
     for (int x = 0; x < no; ++x) e(", const %s g%d", IDX, x);
@@ -1212,7 +1348,7 @@ void emit_reduce(Plan& plan, const Program& p, int n_args, const DeviceProps& de
     for (int j = 0; j < nloads; ++j)
       if (!in_post(j)) emit_load(e, p, j, c, "  ");
     e("  float o[%d];\n  #pragma unroll\n  for (int l = 0; l < %d; ++l) {\n", V, V);
-    emit_op_list(e, p.ops, "    ", "l");
+    emit_op_list(e, p.ops, "    ", "l", p.results);
     e("    o[l] = _%d;\n  }\n", p.results[0]);
     if (V == 4)
       e("  return (o[0] + o[1]) + (o[2] + o[3]);\n}\n");
@@ -1326,7 +1462,7 @@ void emit_post_kernel(Emit& e, const Program& p, int n_args) {
   for (size_t j = 0; j < p.loads.size(); ++j)
     if (j < p.load_in_post.size() && p.load_in_post[j]) emit_load(e, p, (int)j, c, "  ");
   e("  #pragma unroll\n  for (int l = 0; l < %d; ++l) {\n", V);
-  emit_op_list(e, p.post_ops, "    ", "l", "q", "acc[l]");
+  emit_op_list(e, p.post_ops, "    ", "l", {p.post_result}, "q", "acc[l]");
   e("    acc[l] = q%d;\n  }\n", p.post_result);
   if (V == 4)
     e("  cc_stg4(out + v * 4, acc);\n}\n");

@@ -119,6 +119,10 @@ struct Runtime {
   int stream_count = 4;
   int h2d = 0, d2h = 0, aux = 0;       // indices into `streams`
   std::vector<CUevent> event_pool;
+  // pinned host blocks (size classes: powers of two from 4 KiB): cuMemHostAlloc costs ~0.3 ms per MiB, a read-back must not pay it
+  std::map<size_t, std::vector<void*>> host_pool;     // idle blocks per class
+  std::unordered_map<void*, size_t> host_blocks;      // every live block -> its class
+  size_t host_bytes_idle = 0;
   std::map<size_t, std::vector<Block>> pool;
   size_t bytes_pooled = 0, bytes_in_use = 0;
   std::unordered_set<Buffer*> buffers;
@@ -552,6 +556,10 @@ int cc_shutdown(void) {
       r.reduce_counter = 0;
     }
     trim_pool();
+    for (auto& kv : r.host_blocks) driver().cuMemFreeHost(kv.first);  // pinned host memory goes with the context too
+    r.host_blocks.clear();
+    r.host_pool.clear();
+    r.host_bytes_idle = 0;
     // anything the caller still holds stays valid as a handle but its device memory is gone with the context
     for (Buffer* b : r.buffers)
       if (b->owned && b->ptr) {
@@ -726,19 +734,51 @@ int cc_buffer_to_host(cc_buffer h, uint64_t offset, float* host, uint64_t n_floa
   });
 }
 
+namespace {
+constexpr size_t kHostPoolIdleLimit = (size_t)4 << 30;  // idle pinned bytes kept for reuse
+size_t host_class(uint64_t bytes) {
+  size_t c = 4096;
+  while (c < bytes) c <<= 1;
+  return c;
+}
+}  // namespace
+
 int cc_host_alloc(uint64_t bytes, void** out) {
   return guarded([&] {
     Lock lock;
     require_init();
     CC_REQUIRE(out, CC_ERR_ILLEGAL_ARGUMENT, "null output");
-    CC_CU(cuMemHostAlloc(out, bytes ? bytes : 1, CU_MEMHOSTALLOC_PORTABLE));
+    Runtime& r = rt();
+    const size_t cls = host_class(bytes);
+    auto it = r.host_pool.find(cls);
+    if (it != r.host_pool.end() && !it->second.empty()) {
+      *out = it->second.back();
+      it->second.pop_back();
+      r.host_bytes_idle -= cls;
+      return;
+    }
+    CC_CU(cuMemHostAlloc(out, cls, CU_MEMHOSTALLOC_PORTABLE));
+    r.host_blocks[*out] = cls;
   });
 }
 int cc_host_free(void* p) {
   return guarded([&] {
     Lock lock;
     require_init();
-    if (p) CC_CU(cuMemFreeHost(p));
+    if (!p) return;
+    Runtime& r = rt();
+    auto it = r.host_blocks.find(p);
+    CC_REQUIRE(it != r.host_blocks.end(), CC_ERR_ILLEGAL_ARGUMENT, "cc_host_free of memory cc_host_alloc did not return");
+    const size_t cls = it->second;
+    for (void* q : r.host_pool[cls])
+      CC_REQUIRE(q != p, CC_ERR_ILLEGAL_ARGUMENT, "cc_host_free called twice on the same block");
+    if (r.host_bytes_idle + cls <= kHostPoolIdleLimit) {
+      r.host_pool[cls].push_back(p);
+      r.host_bytes_idle += cls;
+    } else {
+      r.host_blocks.erase(it);
+      CC_CU(cuMemFreeHost(p));
+    }
   });
 }
 

@@ -806,6 +806,24 @@ int ct_shape(ct_tensor t, int32_t* out, int capacity) {
 int ct_padding(ct_tensor t, float* out) {
   return guarded([&] { *out = ref(t)->padding; });
 }
+int ct_flat_buffer(ct_tensor t, float** out_host, uint64_t* out_n_floats) {
+  return guarded([&] {
+    CC_REQUIRE(out_host && out_n_floats, CC_ERR_ILLEGAL_ARGUMENT, "null output");
+    const uint64_t n = (uint64_t)ref(t)->size();
+    void* host = nullptr;
+    int st = cc_host_alloc(n * 4, &host);
+    if (st != CC_OK) throw Error(st, cc_last_error());
+    try {
+      ref(t)->flat_array_into((float*)host, n);
+    } catch (...) {
+      cc_host_free(host);
+      throw;
+    }
+    *out_host = (float*)host;
+    *out_n_floats = n;
+  });
+}
+int ct_flat_buffer_release(float* host) { return cc_host_free(host); }
 int ct_flat_array(ct_tensor t, float* host_out, uint64_t capacity) {
   return guarded([&] { ref(t)->flat_array_into(host_out, capacity); });
 }

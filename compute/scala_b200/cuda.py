@@ -48,6 +48,8 @@ def _L():
         L.ct_shape.argtypes = [h, ip, C.c_int]
         L.ct_padding.argtypes = [h, fp]
         L.ct_flat_array.argtypes = [h, C.c_void_p, u64]
+        L.ct_flat_buffer.argtypes = [h, C.POINTER(C.POINTER(C.c_float)), hp]
+        L.ct_flat_buffer_release.argtypes = [C.POINTER(C.c_float)]
         L.ct_to_string.argtypes = [h, C.c_char_p, u64, hp]
         L.ct_do_buffer.argtypes = [h, hp, hp]
         L.ct_compile.argtypes = [h, hp]
@@ -175,6 +177,34 @@ class PinnedArray:
             self.array = None
             check(_L().cc_host_free(self._p))
             self._p = C.c_void_p()
+
+
+class HostBuffer:
+    """`flatBuffer`'s result (T:1099-1109): callee-allocated pinned host memory holding the evaluated tensor, valid until
+    `release()` (the end of the reference's `Do` scope, O:691-715).  Usable as a context manager."""
+
+    def __init__(self, ptr, n_floats: int):
+        self._p = ptr
+        self.n = int(n_floats)
+        self.array = np.ctypeslib.as_array(ptr, shape=(max(self.n, 1),))[: self.n]
+
+    def release(self) -> None:
+        if self._p is not None:
+            self.array = None
+            p, self._p = self._p, None
+            check(_L().ct_flat_buffer_release(p))
+
+    def __enter__(self) -> np.ndarray:
+        return self.array
+
+    def __exit__(self, *exc) -> None:
+        self.release()
+
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:
+            pass
 
 
 class Kernel:
@@ -583,6 +613,13 @@ class Tensor:
         out = np.empty(n, dtype=np.float32)
         check(_L().ct_flat_array(self._h, out.ctypes.data, n))
         return out
+
+    def flatBuffer(self) -> HostBuffer:
+        """evaluate and read back into pooled pinned memory (no pageable staging copy): `with t.flatBuffer() as a: ...`"""
+        p = C.POINTER(C.c_float)()
+        n = u64()
+        check(_L().ct_flat_buffer(self._h, C.byref(p), C.byref(n)))
+        return HostBuffer(p, n.value)
 
     def flatArrayInto(self, host_ptr: int, capacity_floats: int) -> None:
         check(_L().ct_flat_array(self._h, host_ptr, int(capacity_floats)))

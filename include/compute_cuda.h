@@ -99,7 +99,9 @@ int cc_buffer_length(cc_buffer b, uint64_t* out_n_floats);
  * `offset_floats` after `waits`; `*out_event` completes when `host` is filled (NULL => blocking). */
 int cc_buffer_to_host(cc_buffer b, uint64_t offset_floats, float* host, uint64_t n_floats, const cc_event* waits,
                       int n_waits, cc_event* out_event);
-/* pinned host staging memory (replaces LWJGL memAllocFloat, Memory.scala:184-208) */
+/* pinned host staging memory (replaces LWJGL memAllocFloat, Memory.scala:184-208). Blocks are pooled by size class:
+ * cc_host_free returns a block to the pool (cuMemHostAlloc is far too slow for a per-read-back allocation); everything
+ * is unpinned and freed by cc_shutdown. */
 int cc_host_alloc(uint64_t bytes, void** out);
 int cc_host_free(void* p);
 
@@ -272,6 +274,11 @@ int ct_shape(ct_tensor t, int32_t* out, int capacity);
 int ct_padding(ct_tensor t, float* out);
 /* slow actions (T:1099-1118, 776-811) — evaluate, read back, block */
 int ct_flat_array(ct_tensor t, float* host_out, uint64_t capacity_floats);
+/* flatBuffer (T:1099-1109): evaluate and read back into callee-allocated PINNED host memory (the reference hands out an
+ * LWJGL-malloc'd FloatBuffer valid inside the Do scope, O:691-715); the caller ends the scope with ct_flat_buffer_release.
+ * D2H runs at PCIe speed with no staging copy, unlike ct_flat_array into pageable memory. */
+int ct_flat_buffer(ct_tensor t, float** out_host, uint64_t* out_n_floats);
+int ct_flat_buffer_release(float* host);
 int ct_to_string(ct_tensor t, char* out, uint64_t capacity, uint64_t* out_needed);
 /* evaluate and keep on the device: doBuffer (T:1401-1403); `*out_event` may be 0 when already complete */
 int ct_do_buffer(ct_tensor t, cc_buffer* out, cc_event* out_event);

@@ -32,6 +32,11 @@ if not args.no_parity:
 T = cuda.Tensor
 
 
+# randomNormal's pair 61 ^ seed is (+inf, NaN) by construction (hash(61) == 0, Tensors.scala:106-117, 398-429); seeds with bit 30
+# set put that pair beyond every size of the grid so the parity columns are about arithmetic, not about where the NaN lands
+SEED = 1 << 30
+
+
 def fold(n, x, f):
     for _ in range(n):
         x = f(x)
@@ -86,15 +91,15 @@ def cells():
         for nd in (3, 2):
             for size in (128, 32):
                 def b(T_, iters=iters, nd=nd, size=size):
-                    a, bb, c = (T_.randomNormal([size] * nd, seed=s) for s in (1, 2, 3))
+                    a, bb, c = (T_.randomNormal([size] * nd, seed=SEED + s) for s in (1, 2, 3))
                     return fold(iters, a, lambda x: x * bb + c)
                 yield "Issue137", f"iterations={iters} dims={nd} size={size}", b, "chain"
     for ind in (8, 32):
         for outd in (8, 32):
             for batch in (65536, 4096, 32):
                 def b(T_, ind=ind, outd=outd, batch=batch):
-                    w = T_.randomNormal([ind, outd], seed=1)
-                    x = T_.randomNormal([batch, ind], seed=2)
+                    w = T_.randomNormal([ind, outd], seed=SEED + 1)
+                    x = T_.randomNormal([batch, ind], seed=SEED + 2)
                     # benchmarks.scala:172-192: j and k unrolled when i >= maxComputeUnits * 128 (148 SMs), else only j
                     return matmul1(T_, x, w) if batch >= 148 * 128 else matmul2(T_, x, w)
                 yield "MatrixMultiplication", f"inputDepth={ind} outputDepth={outd} batchSize={batch}", b, "sum"
@@ -102,27 +107,30 @@ def cells():
         for nd in (2, 3):
             for size in (128, 32):
                 def b(T_, iters=iters, nd=nd, size=size):
-                    return fold(iters, T_.randomNormal([size] * nd, seed=1), T_.tanh)
+                    return fold(iters, T_.randomNormal([size] * nd, seed=SEED + 1), T_.tanh)
                 yield "Tanh", f"iterations={iters} dims={nd} size={size}", b, "ulp"
     for nd in (3, 2):
         for size in (512, 128, 32, 16):
             def b(T_, nd=nd, size=size):
-                return T_.randomNormal([size] * nd, seed=1).sum()
+                return T_.randomNormal([size] * nd, seed=SEED + 1).sum()
             yield "Sum", f"dims={nd} size={size}", b, "sum"
     for nd in (3, 2, 1):
         for size in (128, 32, 16):
             def b(T_, nd=nd, size=size):
-                return T_.randomNormal([size] * nd, seed=7)
+                return T_.randomNormal([size] * nd, seed=SEED + 7)
             yield "RandomNormal", f"dims={nd} size={size}", b, "ulp"
     for ks in (3, 1):
         for depth in (8, 3):
             for batch in (128, 32):
                 def b(T_, ks=ks, depth=depth, batch=batch):
-                    inp = T_.randomNormal([batch, 32, 32, depth], seed=1)
-                    wt = T_.randomNormal([ks, ks, depth, depth], seed=2)
-                    bias = T_.randomNormal([depth], seed=3)
+                    inp = T_.randomNormal([batch, 32, 32, depth], seed=SEED + 1)
+                    wt = T_.randomNormal([ks, ks, depth, depth], seed=SEED + 2)
+                    bias = T_.randomNormal([depth], seed=SEED + 3)
                     return convolute(T_, inp, wt, bias)
                 yield "Convolution", f"kernel={ks} depth={depth} batch={batch} image=32x32", b, "sum"
+
+
+LEAVES = {}  # (shape, seed) -> the values the device generated, so that the oracle evaluates the SAME inputs
 
 
 def cache_leaves(build):
@@ -134,8 +142,25 @@ def cache_leaves(build):
         @staticmethod
         def randomNormal(shape, seed):
             t = T.randomNormal(shape, seed=seed)
-            return t if args.compile_only else t.doCache()
+            if args.compile_only:
+                return t
+            t = t.doCache()
+            if not args.no_parity:
+                LEAVES[(tuple(shape), seed)] = t.flatArray()
+            return t
     return build(Cached())
+
+
+class OracleOnDeviceLeaves:
+    """the numpy oracle's Tensor with randomNormal replaced by the device's values (the RNG's own parity is the RandomNormal rows:
+    its log / cos / sin come from a different libm, <= 3 ulp apart, which would otherwise leak into every other row)"""
+
+    def __getattr__(self, name):
+        return getattr(ref.Tensor, name)
+
+    @staticmethod
+    def randomNormal(shape, seed):
+        return ref.Tensor(LEAVES[(tuple(shape), seed)].reshape(shape))
 
 
 out = {}
@@ -166,19 +191,32 @@ for klass, params, build, tol in cells():
             e.doBuffer().release()
         dev_us = cuda.timer_stop() / args.calls * 1e3
         row.update(flatArray_wall_us=wall_us, device_us=dev_us, ops_per_s=1e6 / wall_us, elements=int(got.size))
+        t4 = time.perf_counter()
+        for _ in range(args.calls):
+            (build(T) if klass == "RandomNormal" else e).flatBuffer().release()
+        row["flatBuffer_wall_us"] = (time.perf_counter() - t4) / args.calls * 1e6
         if not args.no_parity:
-            want = build(ref.Tensor).flat_array()
+            wants = []
+            for contract in (False, True):  # the reference builds with -cl-unsafe-math-optimizations: a*b+c may or may not fuse
+                ref.CONTRACT[0] = contract
+                try:
+                    wants.append(build(ref.Tensor if klass == "RandomNormal" else OracleOnDeviceLeaves()).flat_array())
+                finally:
+                    ref.CONTRACT[0] = False
+            g64 = got.astype(np.float64)
+            fin = np.isfinite(got)
+            row["nonfinite_agree"] = bool(all(np.array_equal(np.isfinite(w), fin) for w in wants))
             if tol == "ulp":
-                row["max_ulp_vs_oracle"] = int(ref.ulp_distance(got, want).max())
+                row["max_ulp_vs_oracle"] = int(min(ref.ulp_distance(got[fin], w[fin]).max() for w in wants))
             elif tol == "chain":
-                # a*b+c folded n times grows like |b|^n: compare relative to the magnitude, fma contraction allowed
-                d = np.abs(got.astype(np.float64) - want.astype(np.float64)) / np.maximum(np.abs(want.astype(np.float64)), 1e-30)
-                fin = np.isfinite(want) & np.isfinite(got)
-                row["max_rel_vs_oracle"] = float(d[fin].max()) if fin.any() else 0.0
-                row["nonfinite_agree"] = bool(np.array_equal(np.isfinite(want), np.isfinite(got)))
+                # x -> x*b + c folded n times: errors of earlier steps are multiplied by later b's and cancellation in the last
+                # add inflates them relative to the result; report the distribution of the distance to the nearer bracket end
+                d = np.minimum(*[ref.ulp_distance(got[fin], w[fin]) for w in wants]).astype(np.float64)
+                row["ulp_vs_oracle"] = {"median": float(np.median(d)), "p99": float(np.percentile(d, 99)), "max": float(d.max())}
             else:
-                scale = float(np.abs(want).max()) or 1.0
-                row["max_abs_err_over_max"] = float(np.abs(got.astype(np.float64) - want.astype(np.float64)).max() / scale)
+                scale = float(np.abs(wants[0][fin]).max()) or 1.0
+                row["max_abs_err_over_max"] = float(min(np.abs(g64[fin] - w.astype(np.float64)[fin]).max() for w in wants) / scale)
+    LEAVES.clear()
     out.setdefault(klass, {})[params] = row
     print(klass, params, json.dumps(row), flush=True)
 os.makedirs("gpurun_out", exist_ok=True)

@@ -296,6 +296,40 @@ def test_deep_chains_do_not_overflow_the_stack():
     assert cuda.live_tensors() >= 0
 
 
+def test_iterated_maps_become_counted_loops():
+    """`(0 until n).foldLeft(x)(f)` (benchmarks.scala:100-108, 319-326): n copies of f in the tree, one loop in the kernel"""
+    import time
+
+    def fold(n, x, f):
+        for _ in range(n):
+            x = f(x)
+        return x
+
+    t0 = time.perf_counter()
+    k = fold(100, rnd([128, 128]), T.tanh).compile()
+    assert time.perf_counter() - t0 < 1.0  # 100 inlined tanhf bodies took NVRTC 1.4-1.8 s
+    assert "for (int it_ = 0; it_ < 100; ++it_)" in k.source and k.source.count("= cc_tanh(") == 1
+    a, b, c = rnd([32, 32], 1), rnd([32, 32], 2), rnd([32, 32], 3)
+    k = fold(100, a, lambda v: v * b + c).compile()
+    assert "it_ < 99" in k.source and k.info.n_args == 3  # the first a*b+c interleaves the loads of b and c: 99 uniform periods
+    # intermediate values that are read again later keep the chain unrolled ...
+    steps = [a]
+    for _ in range(10):
+        steps.append(T.tanh(steps[-1]))
+    assert "int it_" not in (steps[-1] + steps[5]).compile().source
+    # ... but the last value of a loop may be used as often as needed, and short chains are left alone
+    e = fold(12, a, T.tanh)
+    assert "it_ < 12" in (e * e + e).compile().source
+    assert "int it_" not in fold(7, a, T.tanh).compile().source
+    # a period of several ops with two carried values: (p, q) -> (p + q, p * q) would need tuples; x -> exp(x) * x + b does not
+    k = fold(9, a, lambda v: T.exp(v) * v + b).compile()
+    assert "it_ < 8" in k.source or "it_ < 9" in k.source
+    # inside a re-rolled reduction's term
+    x = rnd([64, 256])
+    k = axis_sum(T.tanh(T.tanh(T.tanh(T.tanh(T.tanh(T.tanh(T.tanh(T.tanh(x)))))))).nonInline(), 0).compile()
+    assert k.info.kind == 1
+
+
 def test_kernel_cache_policy():
     """kernelCache (Tensors.scala:1267-1289): unbounded by default, an optional LRU limit, clearCache"""
     cuda.kernel_cache_clear()

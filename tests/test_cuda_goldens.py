@@ -155,6 +155,42 @@ def test_random_normal(cuda):  # TensorsSpec.scala:259-265, 411-434 — sqrt/log
     assert ((d <= 4) | (np.abs(odd - want_odd) <= 4e-7)).all()
 
 
+def test_random_normal_large_and_its_singular_pair(cuda):  # Tensors.scala:398-429 at benchmark sizes (benchmarks.scala:372-376)
+    """hash(61) == 0 (Tensors.scala:106-117), so the pair with index 61 ^ seed draws u1 = 0: r = sqrt(-2 log 0) = +inf,
+    theta = 0 -> z0 = +inf, z1 = inf * 0 = NaN.  The reference produces exactly that; so must we, and nothing else non-finite."""
+    n, seed = 1 << 16, 7
+    got = cuda.Tensor.randomNormal([n], seed=seed).flatArray()
+    want = ref.random_normal_buffer(n, seed)
+    p = 61 ^ seed
+    assert np.isposinf(got[2 * p]) and np.isnan(got[2 * p + 1]) and np.isposinf(want[2 * p]) and np.isnan(want[2 * p + 1])
+    fin = np.ones(n, bool)
+    fin[2 * p : 2 * p + 2] = False
+    assert np.isfinite(got[fin]).all() and np.isfinite(want[fin]).all()
+    d = ref.ulp_distance(got[fin], want[fin])
+    # cos / sin of a large-ish theta near a zero crossing: compare absolutely there (|z| <= r * 4 ulp(theta))
+    assert ((d <= 4) | (np.abs(got[fin] - want[fin]) <= 4e-6)).all(), d.max()
+    assert abs(float(got[fin].mean())) < 0.02 and abs(float(got[fin].std()) - 1.0) < 0.02
+
+
+def test_flat_buffer_is_pinned_and_pooled(cuda):  # flatBuffer, Tensors.scala:1099-1109; host memory O:691-715
+    T = cuda.Tensor
+    e = T.tanh(T.random([257, 129], seed=3) * T.fill(2.0, [257, 129]))
+    want = e.flatArray()
+    hb = e.flatBuffer()
+    assert hb.n == 257 * 129 and np.array_equal(hb.array.view(np.uint32), want.view(np.uint32))
+    first = hb.array.ctypes.data
+    hb.release()
+    hb.release()  # idempotent
+    with e.flatBuffer() as a:  # the block comes back from the pool: no new cuMemHostAlloc
+        assert a.ctypes.data == first and np.array_equal(a.view(np.uint32), want.view(np.uint32))
+    with T.scalar(3.0).flatBuffer() as a:
+        assert a.tolist() == [3.0]
+    # freeing memory the library did not hand out is an error, not a crash
+    import ctypes as C
+
+    assert cuda._L().cc_host_free(C.c_void_p(0x1000)) == -1
+
+
 def test_transpose(cuda):  # TensorsSpec.scala:436-466
     T = cuda.Tensor
     assert str(T.scalar(42.0).transpose()) == "42.0"

@@ -144,6 +144,50 @@ def test_all_elementwise_ops(cuda):
         assert d.max() <= 2, (shape, d.max())
 
 
+def test_iterated_maps_loop_equals_unrolled(cuda, monkeypatch):
+    """benchmarks.scala:100-108 / 319-326: the loop the generator emits for a folded map is the unrolled kernel, bit for bit,
+    and both sit within the oracle's bracket"""
+    T = cuda.Tensor
+
+    def fold(n, x, f):
+        for _ in range(n):
+            x = f(x)
+        return x
+
+    def issue137(T, n, shape):
+        a, b, c = (T.random(shape, seed=s) for s in (1, 2, 3))
+        return fold(n, a, lambda v: v * b + c)
+
+    def tanh_n(T, n, shape):
+        return fold(n, T.random(shape, seed=4) * T.fill(6.0, shape) - T.fill(3.0, shape), T.tanh)
+
+    def mixed(T, n, shape):
+        a, b = T.random(shape, seed=1), T.random(shape, seed=2)
+        e = fold(n, a, lambda v: T.exp(-v) * v + b)
+        return e * e - e
+
+    for build, n, shape in ((issue137, 100, [33, 65]), (tanh_n, 100, [64, 64]), (tanh_n, 10, [7, 5, 3]), (mixed, 30, [128, 36])):
+        cuda.kernel_cache_clear()
+        k = build(T, n, shape).compile()
+        assert "int it_" in k.source
+        looped = build(T, n, shape).flatArray()
+        monkeypatch.setenv("CC_NO_OP_LOOPS", "1")
+        cuda.kernel_cache_clear()
+        assert "int it_" not in build(T, n, shape).compile().source
+        unrolled = build(T, n, shape).flatArray()
+        monkeypatch.delenv("CC_NO_OP_LOOPS")
+        cuda.kernel_cache_clear()
+        assert np.array_equal(bits(looped), bits(unrolled)), build.__name__
+        if n <= 10:
+            assert min_ulp(looped, oracle_bracket(build, n, shape)).max() <= 2 * n
+    # a contracting affine map converges to its fixed point c / (1 - b) whatever the rounding of each step
+    got = issue137(T, 100, [33, 65]).flatArray().astype(np.float64)
+    b, c = (ref.random_buffer(33 * 65, s).astype(np.float64) for s in (2, 3))
+    fixed = c / (1.0 - b)
+    ok = b < 0.8
+    assert np.abs(got[ok] - fixed[ok]).max() <= 1e-5 * np.abs(fixed[ok]).max()
+
+
 # ---- C3: reductions ----------------------------------------------------------------------------------------------------------
 
 
