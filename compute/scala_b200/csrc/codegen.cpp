@@ -862,7 +862,9 @@ void emit_load(Emit& e, const Program& p, int j, const LoadCtx& c, const char* i
     e("%sL%d[1] = L%d[2] = L%d[3] = L%d[0];\n", indent, j, j, j, j);
     return;
   }
-  // per-lane scalar loads (strided / misaligned / lane-dependent bounds)
+  // per-lane scalar loads (strided / misaligned / lane-dependent bounds); lanes a few floats apart share 32-byte sectors, which
+  // a non-allocating load would fetch from L2 once per lane
+  if (std::llabs(coefV) <= 8) LD1 = "cc_ldc";
   e("%s#pragma unroll\n%sfor (int l = 0; l < %d; ++l) {\n", indent, indent, V);
   std::string cond = ucond;
   for (int y = 0; y < L.rows; ++y) {
@@ -953,6 +955,9 @@ void emit_elementwise(Plan& plan, const Program& p, int n_args, const DeviceProp
   // flight per thread and a register cap that keeps 8 CTAs/SM resident beats a persistent grid by ~15 % (7.0 vs 6.1 TB/s on C2).
   int U = 2;
   if (nloads > 8) U = 1;
+  // scalar lanes (a fastest dimension that is not a multiple of 4 under a view): 2 x 4 bytes per thread in flight cannot cover the
+  // HBM latency (1001x1003x127 translate: 0.68 of HBM); take 8 elements per thread
+  if (V == 1 && nloads <= 4) U = 8;
   while (U > 1 && NV < (int64_t)256 * U * dev.sm_count * 8) U /= 2;  // small tensors: more CTAs beats more vectors per thread
   int64_t grid_mult = (int64_t)1 << 40;
   int min_blocks = nloads * V * U <= 24 ? 8 : (nloads * V * U <= 40 ? 6 : 0);
@@ -1335,7 +1340,9 @@ void emit_reduce(Plan& plan, const Program& p, int n_args, const DeviceProps& de
     // --- row owner: G threads share one output and stride over t in 128-bit vectors -----------------------------------
     const int V = (p.dims[nd - 1] % 4 == 0) ? 4 : 1;
     const int64_t TV = T / V;
-    const int G = TV <= 64 ? 32 : 256;
+    // one warp per output while a lane gets <= 16 vectors and the outputs alone fill the machine (256x512x1024 summed over
+    // its last axis: 0.73 of HBM with 256 threads holding one vector each); a whole CTA per output for long rows
+    const int G = (TV <= 64 || (TV <= 512 && NOUT >= (int64_t)dev.sm_count * 64)) ? 32 : 256;
     const int OPB = 256 / G;  // outputs per block
     e("// axis reduction (row owner): out dims=[");
     for (int x = 0; x < no; ++x) e("%s%lld", x ? "," : "", (long long)odims[x]);
@@ -1840,6 +1847,15 @@ Plan make_plan(const Tree& t, const DeviceProps& dev) {
     for (int a = 0; a < n_args; ++a) bytes += 4 * std::min<uint64_t>(touched[a], plan.arg_min_floats[a]);
     plan.algorithmic_bytes = bytes;
     plan.flops = count_flops(prog) * (uint64_t)space + ((is_reduce || root.kind == K_REDUCE) ? (uint64_t)space : 0);
+  }
+
+  // A source read through several views in one kernel (stencils: x + x.translate(...)) would be fetched from L2 once per view
+  // with streaming loads (5-point stencil on 512^3: 0.27 ms, 0.62 of HBM); let those lines live in L1.
+  {
+    std::vector<int> uses((size_t)n_args, 0);
+    for (const Load& L : prog.loads) ++uses[(size_t)L.arg];
+    for (Load& L : prog.loads)
+      if (L.integer && uses[(size_t)L.arg] > 1) L.reuse = true;
   }
 
   if (root.kind == K_REDUCE) {

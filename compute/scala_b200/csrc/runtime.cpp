@@ -5,6 +5,7 @@
 #include <nccl.h>
 #include <nvrtc.h>
 
+#include <algorithm>
 #include <atomic>
 #include <cstdlib>
 #include <cstring>
@@ -132,6 +133,15 @@ struct Runtime {
   uint64_t cache_clock = 0;
   uint64_t cache_limit = 0;  // 0 = unbounded (the reference's default kernelCacheBuilder, Tensors.scala:1267-1277)
   cc_stats_t stats{};
+  // built-in command profiler (cc_profile_*): one timing-event pair per command while enabled
+  struct ProfRecord {
+    std::string label;
+    CUevent start, stop;
+    uint64_t bytes, flops;
+  };
+  bool profiling = false;
+  std::vector<ProfRecord> prof_records;
+  std::vector<CUevent> prof_event_pool;
   // B^T hi / lo panels of recent contractions, kept while the B buffer is unchanged (same uid and write version)
   struct Panels {
     uint64_t uid, version;
@@ -217,8 +227,24 @@ int pick_stream() {
 struct Op {
   int stream;
   std::vector<Buffer*> reads, writes;
+  // what the profiler files this command under, and the algorithmic work it does (0 = unknown)
+  std::string label = "command";
+  uint64_t bytes = 0, flops = 0;
+  CUevent prof_start = nullptr;
   CUstream cu() const { return rt().streams[(size_t)stream]; }
 };
+
+CUevent prof_event() {
+  Runtime& r = rt();
+  CUevent ev;
+  if (!r.prof_event_pool.empty()) {
+    ev = r.prof_event_pool.back();
+    r.prof_event_pool.pop_back();
+  } else {
+    CC_CU(cuEventCreate(&ev, CU_EVENT_DEFAULT));
+  }
+  return ev;
+}
 
 void need(int s, const Mark& m) {
   Runtime& r = rt();
@@ -244,10 +270,20 @@ void op_begin(Op& op, const cc_event* waits, int n_waits) {
     need(op.stream, b->last_write);                       // write after write
     for (const Mark& m : b->reads) need(op.stream, m);    // write after read (also covers pooled-memory reuse)
   }
+  if (rt().profiling) {  // after the waits: the interval measures the command, not its dependencies
+    op.prof_start = prof_event();
+    CC_CU(cuEventRecord(op.prof_start, op.cu()));
+  }
 }
 
 void op_end(Op& op, cc_event* out_event) {
   Runtime& r = rt();
+  if (op.prof_start) {
+    CUevent stop = prof_event();
+    CC_CU(cuEventRecord(stop, op.cu()));
+    r.prof_records.push_back(Runtime::ProfRecord{op.label, op.prof_start, stop, op.bytes, op.flops});
+    op.prof_start = nullptr;
+  }
   const uint64_t q = ++r.seq[(size_t)op.stream];
   for (Buffer* b : op.writes) {
     b->reads.clear();
@@ -576,6 +612,14 @@ int cc_shutdown(void) {
       }
     for (CUevent e : r.event_pool) driver().cuEventDestroy(e);
     r.event_pool.clear();
+    for (auto& rec : r.prof_records) {
+      driver().cuEventDestroy(rec.start);
+      driver().cuEventDestroy(rec.stop);
+    }
+    r.prof_records.clear();
+    for (CUevent e : r.prof_event_pool) driver().cuEventDestroy(e);
+    r.prof_event_pool.clear();
+    r.profiling = false;
     for (Event* e : r.events) {
       driver().cuEventDestroy(e->ev);
       e->ev = nullptr;
@@ -631,6 +675,8 @@ int cc_buffer_upload(cc_buffer buf, const float* host, uint64_t n_floats, const 
                  (unsigned long long)n_floats, (unsigned long long)b->n_floats);
       CC_REQUIRE(host || n_floats == 0, CC_ERR_ILLEGAL_ARGUMENT, "null host pointer");
       Op op{rt().h2d, {}, {b}};
+      op.label = "copy host -> device";
+      op.bytes = n_floats * 4;
       op_begin(op, waits, n_waits);
       if (n_floats) CC_CU(cuMemcpyHtoDAsync(b->ptr, host, (size_t)n_floats * 4, op.cu()));
       rt().stats.h2d_bytes += n_floats * 4;
@@ -717,6 +763,8 @@ int cc_buffer_to_host(cc_buffer h, uint64_t offset, float* host, uint64_t n_floa
                  (unsigned long long)offset, (unsigned long long)(offset + n_floats), (unsigned long long)b->n_floats);
       CC_REQUIRE(host || n_floats == 0, CC_ERR_ILLEGAL_ARGUMENT, "null host pointer");
       Op op{rt().d2h, {b}, {}};
+      op.label = "copy device -> host";
+      op.bytes = n_floats * 4;
       op_begin(op, waits, n_waits);
       if (n_floats) CC_CU(cuMemcpyDtoHAsync(host, b->ptr + offset * 4, (size_t)n_floats * 4, op.cu()));
       rt().stats.d2h_bytes += n_floats * 4;
@@ -1051,6 +1099,29 @@ void gemm_on_stream(Buffer* a, Buffer* b, Buffer* c, int64_t m, int64_t n, int64
 }
 }  // namespace
 
+namespace {
+const char* plan_kind_name(int kind) {
+  switch (kind) {
+    case PLAN_ELEMENTWISE: return "elementwise";
+    case PLAN_AXIS_REDUCE: return "axis reduction";
+    case PLAN_CONTRACTION: return "contraction 3xTF32";
+    case PLAN_TILED_TRANSPOSE: return "tiled transpose";
+    case PLAN_FULL_REDUCE: return "whole-tensor fold";
+  }
+  return "kernel";
+}
+// "<plan> #<structure hash>: <the generator's one-line description>"
+void label_kernel_op(Op& op, const Kernel& k) {
+  if (!rt().profiling) return;
+  std::string first = k.plan.source.substr(0, k.plan.source.find('\n'));
+  if (first.rfind("// ", 0) == 0) first = first.substr(3);
+  if (first.size() > 150) first.resize(150);
+  op.label = strprintf("%s #%08x: %s", plan_kind_name(k.plan.kind), (unsigned)(k.hash & 0xffffffffu), first.c_str());
+  op.bytes = k.plan.algorithmic_bytes;
+  op.flops = k.plan.flops;
+}
+}  // namespace
+
 int cc_launch(cc_kernel h, const cc_buffer* args, int n_args, cc_buffer out, const cc_event* waits, int n_waits, cc_event* out_event) {
   return guarded([&] {
     Lock lock;
@@ -1099,6 +1170,7 @@ int cc_launch(cc_kernel h, const cc_buffer* args, int n_args, cc_buffer out, con
       try {
         for (uint64_t n : p.scratch_floats) scratch.push_back(alloc_buffer(n));
         Op op{pick_stream(), in, {ob}};
+        label_kernel_op(op, *k);
         for (Buffer* s : scratch) op.writes.push_back(s);
         op_begin(op, waits, n_waits);
         launch_spec(0, scratch, nullptr, op.cu());
@@ -1121,6 +1193,7 @@ int cc_launch(cc_kernel h, const cc_buffer* args, int n_args, cc_buffer out, con
       bool launched = false;
       try {
         Op op{pick_stream(), in, {ob}};
+        label_kernel_op(op, *k);
         g.declare(op);
         op_begin(op, waits, n_waits);
         gemm_on_stream(in[0], in[1], ob, p.M, p.N, p.K, g, op.cu());
@@ -1139,6 +1212,7 @@ int cc_launch(cc_kernel h, const cc_buffer* args, int n_args, cc_buffer out, con
     // whole-tensor folds share the runtime's partials buffer and block counter: serialised on stream 0 like cc_reduce_sum
     Buffer* shared_partials = p.kind == PLAN_FULL_REDUCE ? reduce_scratch() : nullptr;
     Op op{shared_partials ? 0 : pick_stream(), in, {ob}};
+    label_kernel_op(op, *k);
     for (Buffer* s : scratch) op.writes.push_back(s);
     if (shared_partials) op.writes.push_back(shared_partials);
     op_begin(op, waits, n_waits);
@@ -1160,6 +1234,8 @@ int cc_reduce_sum(cc_buffer in, uint64_t n_floats, cc_buffer out, const cc_event
     Buffer* sc = reduce_scratch();
     // the shared scratch + counter serialise full reductions on one stream
     Op op{0, {ib}, {ob, sc}};
+    op.label = "sum (builtin reduce_sum)";
+    op.bytes = n_floats * 4 + 4;
     op_begin(op, waits, n_waits);
     launch_reduce_sum((const float*)ib->ptr, n_floats, (float*)ob->ptr, (float*)sc->ptr, (unsigned*)r.reduce_counter, r.info.sm_count,
                       (cudaStream_t)op.cu());
@@ -1176,6 +1252,8 @@ int cc_random(cc_buffer out, uint64_t n_floats, int32_t seed, cc_event* out_even
     Buffer* ob = as_buffer(out);
     CC_REQUIRE(n_floats <= ob->n_floats, CC_ERR_ILLEGAL_ARGUMENT, "random: buffer too small");
     Op op{pick_stream(), {}, {ob}};
+    op.label = "random (builtin)";
+    op.bytes = n_floats * 4;
     op_begin(op, nullptr, 0);
     launch_random((float*)ob->ptr, n_floats, seed, (cudaStream_t)op.cu());
     rt().stats.launches++;
@@ -1191,6 +1269,8 @@ int cc_random_normal(cc_buffer out, uint64_t n_floats, int32_t seed, cc_event* o
     Buffer* ob = as_buffer(out);
     CC_REQUIRE(n_floats <= ob->n_floats, CC_ERR_ILLEGAL_ARGUMENT, "randomNormal: buffer too small");
     Op op{pick_stream(), {}, {ob}};
+    op.label = "randomNormal (builtin)";
+    op.bytes = n_floats * 4;
     op_begin(op, nullptr, 0);
     launch_random_normal((float*)ob->ptr, n_floats, seed, (cudaStream_t)op.cu());
     rt().stats.launches++;
@@ -1216,6 +1296,9 @@ int cc_matmul_3xtf32(cc_buffer a, cc_buffer b, cc_buffer c, int64_t m, int64_t n
     bool launched = false;
     try {
       Op op{pick_stream(), {ab, bb}, {cb}};
+      op.label = "contraction 3xTF32 (cc_matmul_3xtf32)";
+      op.flops = 2ull * (uint64_t)m * (uint64_t)n * (uint64_t)k;
+      op.bytes = 4ull * (uint64_t)(m * k + k * n + m * n);
       g.declare(op);
       op_begin(op, waits, n_waits);
       gemm_on_stream(ab, bb, cb, m, n, k, g, op.cu());
@@ -1256,6 +1339,74 @@ int cc_stats_reset(void) {
   return guarded([&] {
     Lock lock;
     rt().stats = cc_stats_t{};
+  });
+}
+
+// ---- built-in command profiler ------------------------------------------------------------------------------------------------
+// The reference has no profiling at all (its queues are created without CL_QUEUE_PROFILING_ENABLE, OpenCL.scala:431-436). While
+// enabled, every command is bracketed by a pair of timing events on its own stream; the report aggregates device time per
+// kernel structure / copy direction / collective with the algorithmic GB/s and TFLOP/s the code generator attributes to it.
+int cc_profile_enable(int on) {
+  return guarded([&] {
+    Lock lock;
+    require_init();
+    rt().profiling = on != 0;
+  });
+}
+
+int cc_profile_report(char* out, uint64_t capacity, uint64_t* out_needed) {
+  return guarded([&] {
+    static thread_local std::string text;  // built on the sizing call, handed out on the copying call
+    Lock lock;
+    require_init();
+    Runtime& r = rt();
+    if (!out || capacity == 0 || text.empty()) {
+      driver().cuCtxSynchronize();
+      struct Agg {
+        uint64_t count = 0, bytes = 0, flops = 0;
+        double total_ms = 0, min_ms = 1e30, max_ms = 0;
+      };
+      std::map<std::string, Agg> agg;
+      for (auto& rec : r.prof_records) {
+        float ms = 0.f;
+        if (driver().cuEventElapsedTime(&ms, rec.start, rec.stop) == CUDA_SUCCESS) {
+          Agg& a = agg[rec.label];
+          a.count++;
+          a.total_ms += ms;
+          a.min_ms = std::min<double>(a.min_ms, ms);
+          a.max_ms = std::max<double>(a.max_ms, ms);
+          a.bytes = rec.bytes;
+          a.flops = rec.flops;
+        }
+        r.prof_event_pool.push_back(rec.start);
+        r.prof_event_pool.push_back(rec.stop);
+      }
+      r.prof_records.clear();
+      std::vector<std::pair<std::string, Agg>> rows(agg.begin(), agg.end());
+      std::sort(rows.begin(), rows.end(), [](auto& x, auto& y) { return x.second.total_ms > y.second.total_ms; });
+      text = "[";
+      for (size_t i = 0; i < rows.size(); ++i) {
+        const Agg& a = rows[i].second;
+        std::string name;
+        for (char c : rows[i].first) {
+          if (c == '"' || c == '\\') name += '\\';
+          name += c;
+        }
+        const double avg_ms = a.total_ms / (double)a.count;
+        text += strprintf("%s\n {\"name\": \"%s\", \"count\": %llu, \"total_ms\": %.6f, \"avg_us\": %.3f, \"min_us\": %.3f, \"max_us\": %.3f, "
+                          "\"algorithmic_bytes\": %llu, \"flops\": %llu, \"GBs\": %.1f, \"TFLOPs\": %.3f}",
+                          i ? "," : "", name.c_str(), (unsigned long long)a.count, a.total_ms, avg_ms * 1e3, a.min_ms * 1e3, a.max_ms * 1e3,
+                          (unsigned long long)a.bytes, (unsigned long long)a.flops, avg_ms > 0 ? (double)a.bytes / avg_ms / 1e6 : 0.0,
+                          avg_ms > 0 ? (double)a.flops / avg_ms / 1e9 : 0.0);
+      }
+      text += "\n]";
+    }
+    if (out_needed) *out_needed = text.size() + 1;
+    if (out && capacity > 0) {
+      CC_REQUIRE(capacity > text.size(), CC_ERR_ILLEGAL_ARGUMENT, "profile report needs %zu bytes", text.size() + 1);
+      memcpy(out, text.c_str(), text.size() + 1);
+      text.clear();
+    }
   });
 }
 
@@ -1406,6 +1557,8 @@ int cc_reduce_sum_allreduce(cc_buffer in, uint64_t n_floats, cc_buffer out, cons
     CC_REQUIRE(n_floats <= ib->n_floats && ob->n_floats >= 1 && ib != ob, CC_ERR_ILLEGAL_ARGUMENT, "bad reduce_sum arguments");
     Buffer* sc = reduce_scratch();
     Op op{0, {ib}, {ob, sc}};
+    op.label = "sum + all-reduce over NVLink (one kernel)";
+    op.bytes = n_floats * 4 + 4;
     op_begin(op, waits, n_waits);
     if (n.comm && n.peer_enabled) {
       // ONE kernel: local reduction + all-reduce of its result over NVLink peer memory
@@ -1497,6 +1650,8 @@ int cc_matmul_3xtf32_allgather(cc_buffer a, cc_buffer b, cc_buffer gathered, int
     bool launched = false;
     try {
       Op op{0, {ab, bb}, {gb}};  // collectives stay on stream 0, in call order
+      op.label = "contraction 3xTF32 + all-gather epilogue";
+      op.flops = 2ull * (uint64_t)m_shard * (uint64_t)n * (uint64_t)k;
       g.declare(op);
       op_begin(op, waits, n_waits);
       // entry barrier: every rank has finished whatever still read its copy of `gathered` (stream order on each rank) ...
@@ -1549,6 +1704,8 @@ int cc_allreduce_sum(cc_buffer buf, uint64_t n_floats, const cc_event* waits, in
     Buffer* b = as_buffer(buf);
     CC_REQUIRE(n_floats <= b->n_floats, CC_ERR_ILLEGAL_ARGUMENT, "allreduce: buffer too small");
     Op op{0, {}, {b}};
+    op.label = "all-reduce";
+    op.bytes = n_floats * 4;
     op_begin(op, waits, n_waits);
     if (n.comm && n.peer_enabled && n_floats <= (uint64_t)kPeerCapFloats) {
       launch_peer_allreduce((float*)b->ptr, n_floats, n.mb, ++n.epoch, (cudaStream_t)op.cu());
@@ -1569,6 +1726,8 @@ int cc_allgather(cc_buffer send, cc_buffer recv, uint64_t n_per_rank, const cc_e
     int ranks = n.comm ? n.n_ranks : 1;
     CC_REQUIRE(n_per_rank <= s->n_floats && n_per_rank * ranks <= d->n_floats && s != d, CC_ERR_ILLEGAL_ARGUMENT, "allgather: bad buffers");
     Op op{0, {s}, {d}};
+    op.label = "all-gather";
+    op.bytes = n_per_rank * 4 * (uint64_t)ranks;
     op_begin(op, waits, n_waits);
     if (n.comm)
       n.check(n.AllGather((const void*)s->ptr, (void*)d->ptr, n_per_rank, ncclFloat, n.comm, (cudaStream_t)op.cu()), "ncclAllGather");
@@ -1585,6 +1744,8 @@ int cc_broadcast(cc_buffer buf, uint64_t n_floats, int root, const cc_event* wai
     Buffer* b = as_buffer(buf);
     CC_REQUIRE(n_floats <= b->n_floats, CC_ERR_ILLEGAL_ARGUMENT, "broadcast: buffer too small");
     Op op{0, {}, {b}};
+    op.label = "broadcast";
+    op.bytes = n_floats * 4;
     op_begin(op, waits, n_waits);
     if (n.comm) n.check(n.Broadcast((const void*)b->ptr, (void*)b->ptr, n_floats, ncclFloat, root, n.comm, (cudaStream_t)op.cu()), "ncclBroadcast");
     op_end(op, out_event);

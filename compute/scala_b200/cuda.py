@@ -55,6 +55,8 @@ def _L():
         L.ct_compile.argtypes = [h, hp]
         L.ct_release.argtypes = [h]
         L.ct_live_tensors.argtypes = [C.POINTER(C.c_int64)]
+        L.cc_profile_enable.argtypes = [C.c_int]
+        L.cc_profile_report.argtypes = [C.c_char_p, u64, hp]
         L.cc_init.argtypes = [C.c_int]
         L.cc_set_stream_count.argtypes = [C.c_int]
         L.cc_device_info.argtypes = [C.POINTER(_lib.DeviceInfo)]
@@ -143,6 +145,22 @@ def stats() -> dict:
 
 def stats_reset() -> None:
     check(_L().cc_stats_reset())
+
+
+def profile(on: bool = True) -> None:
+    """built-in command profiler: while on, every kernel launch / copy / collective is timed on the device"""
+    check(_L().cc_profile_enable(1 if on else 0))
+
+
+def profile_report() -> list:
+    """device time per kernel structure / copy direction / collective since the last report (consumes the records)"""
+    import json
+
+    need = u64()
+    check(_L().cc_profile_report(None, 0, C.byref(need)))
+    buf = C.create_string_buffer(need.value)
+    check(_L().cc_profile_report(buf, need.value, None))
+    return json.loads(buf.value.decode())
 
 
 def synchronize() -> None:

@@ -200,6 +200,14 @@ typedef struct cc_stats_t {
 } cc_stats_t;
 int cc_stats(cc_stats_t* out);
 int cc_stats_reset(void);
+/* Built-in command profiler. The reference has none (queues are created without CL_QUEUE_PROFILING_ENABLE, O:431-436).
+ * While enabled every command (kernel launch, copy, collective) is bracketed by timing events on its own stream.
+ * cc_profile_report synchronises and writes a JSON array aggregated per kernel structure / copy direction / collective:
+ * count, total / avg / min / max device time, the algorithmic bytes and flops the code generator attributes to one launch
+ * and the resulting GB/s, TFLOP/s. Call with out = NULL to size (*out_needed), then with a buffer; the records are
+ * consumed by the report. */
+int cc_profile_enable(int on);
+int cc_profile_report(char* out, uint64_t capacity, uint64_t* out_needed);
 /* device-side stopwatch: joins every pool stream, records a timing event; stop returns elapsed milliseconds */
 int cc_timer_start(void);
 int cc_timer_stop(float* out_ms);

@@ -95,3 +95,33 @@ def test_event_wait_lists_and_completion_callbacks(cuda):
         cuda.check(L.cc_event_release(e.value))
     cuda.check(L.cc_buffer_release(buf.value))
     out.release()
+
+
+def test_builtin_profiler(cuda):
+    """cc_profile_*: per-command device time, aggregated per kernel structure (the reference's queues have no profiling, O:431-436)"""
+    import numpy as np
+
+    T = cuda.Tensor
+    a, b = T.random([1024, 1024], seed=1).doCache(), T.random([1024, 1024], seed=2).doCache()
+    e = T.tanh(a * b)
+    e.flatArray()  # compiled and warm
+    cuda.profile(True)
+    try:
+        for _ in range(5):
+            e.doBuffer().release()
+        s = a.sum().flatArray()
+        host = e.flatArray()
+        rep = cuda.profile_report()
+    finally:
+        cuda.profile(False)
+    by = {r["name"].split(":")[0].split(" #")[0]: r for r in rep}
+    ew = by["elementwise"]
+    assert ew["count"] == 6 and ew["algorithmic_bytes"] == 3 * 4 * 1024 * 1024
+    assert 1.0 < ew["avg_us"] < 200.0 and ew["min_us"] <= ew["avg_us"] <= ew["max_us"] and ew["GBs"] > 50.0
+    assert "dims=[1024,1024]" in [r["name"] for r in rep if r["name"].startswith("elementwise")][0]
+    assert by["copy device -> host"]["count"] == 2 and by["copy device -> host"]["algorithmic_bytes"] in (4, 4 * 1024 * 1024)
+    assert any(k.startswith("sum") or k.startswith("whole-tensor fold") for k in by)
+    assert np.isfinite(s).all() and host.shape == (1024 * 1024,)
+    assert cuda.profile_report() == []  # consumed; nothing recorded while off
+    e.doBuffer().release()
+    assert cuda.profile_report() == []
