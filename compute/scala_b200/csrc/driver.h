@@ -29,6 +29,7 @@ namespace cc {
   X(cuMemsetD32Async)               \
   X(cuMemHostAlloc)                 \
   X(cuMemFreeHost)                  \
+  X(cuMemHostGetDevicePointer)      \
   X(cuStreamCreate)                 \
   X(cuStreamDestroy)                \
   X(cuStreamSynchronize)            \

@@ -805,8 +805,19 @@ int cc_host_alloc(uint64_t bytes, void** out) {
       r.host_bytes_idle -= cls;
       return;
     }
-    CC_CU(cuMemHostAlloc(out, cls, CU_MEMHOSTALLOC_PORTABLE));
+    CC_CU(cuMemHostAlloc(out, cls, CU_MEMHOSTALLOC_PORTABLE | CU_MEMHOSTALLOC_DEVICEMAP));
     r.host_blocks[*out] = cls;
+  });
+}
+int cc_host_device_ptr(void* host, uint64_t* out) {
+  return guarded([&] {
+    Lock lock;
+    require_init();
+    CC_REQUIRE(host && out, CC_ERR_ILLEGAL_ARGUMENT, "null argument");
+    CC_REQUIRE(rt().host_blocks.count(host), CC_ERR_ILLEGAL_ARGUMENT, "not a cc_host_alloc block");
+    CUdeviceptr d = 0;
+    CC_CU(cuMemHostGetDevicePointer(&d, host, 0));
+    *out = (uint64_t)d;
   });
 }
 int cc_host_free(void* p) {

@@ -128,7 +128,8 @@ struct PlanCache {
   }
 };
 void resolve_plan(PlanCache& pc, Tensor::EmitCtx& ctx, uint32_t root, const Shape& out_shape);
-PendingBuffer enqueue_plan(Session& s, const PlanCache& pc, const Shape& out_shape);
+PendingBuffer enqueue_plan(Session& s, const PlanCache& pc, const Shape& out_shape, cc_buffer out_override = 0, cc_event* out_event = nullptr);
+bool plan_output_redirectable(const PlanCache& pc);
 
 // InlineTensor (Tensors.scala:1400-1411)
 struct InlineTensor : Counted {
@@ -144,6 +145,19 @@ struct InlineTensor : Counted {
       }
     }
     return enqueue_plan(s, plan, shape);
+  }
+  bool evaluate_into(Session& s, cc_buffer out, cc_event* out_event) const override {
+    {
+      std::lock_guard<std::mutex> lock(plan.mu);
+      if (!plan.kernel) {
+        EmitCtx ctx;
+        uint32_t root = closure(ctx);
+        resolve_plan(plan, ctx, root, shape);
+      }
+    }
+    if (!plan_output_redirectable(plan)) return false;
+    enqueue_plan(s, plan, shape, out, out_event);
+    return true;
   }
 };
 
@@ -256,6 +270,26 @@ struct ReduceTensor final : NonInlineTensor {
     }
     return enqueue_plan(s, plan, shape);
   }
+  bool evaluate_into(Session& s, cc_buffer out, cc_event* out_event) const override {
+    if (monoid == cc::K_PLUS && !base->is_inline()) {
+      PendingBuffer in = base->do_buffer(s);
+      int st = cc_reduce_sum(in.buffer, (uint64_t)base->size(), out, nullptr, 0, out_event);
+      std::string m = st == CC_OK ? "" : cc_last_error();
+      cc_buffer_release(in.buffer);
+      if (st != CC_OK) throw Error(st, m);
+      return true;
+    }
+    {
+      std::lock_guard<std::mutex> lock(plan.mu);
+      if (!plan.kernel) {
+        EmitCtx ctx;
+        resolve_plan(plan, ctx, emit_root(ctx), shape);
+      }
+    }
+    if (!plan_output_redirectable(plan)) return false;
+    enqueue_plan(s, plan, shape, out, out_event);
+    return true;
+  }
   uint32_t emit_root(EmitCtx& ctx) const { return ctx.w.reduce(monoid, base->closure(ctx), base->shape); }
 };
 
@@ -281,6 +315,19 @@ struct JoinTensor final : NonInlineTensor {
       }
     }
     return enqueue_plan(s, plan, shape);
+  }
+  bool evaluate_into(Session& s, cc_buffer out, cc_event* out_event) const override {
+    {
+      std::lock_guard<std::mutex> lock(plan.mu);
+      if (!plan.kernel) {
+        EmitCtx ctx;
+        uint32_t root = emit_root(ctx);
+        resolve_plan(plan, ctx, root, shape);
+      }
+    }
+    if (!plan_output_redirectable(plan)) return false;
+    enqueue_plan(s, plan, shape, out, out_event);
+    return true;
   }
 };
 
@@ -330,17 +377,28 @@ void resolve_plan(PlanCache& pc, Tensor::EmitCtx& ctx, uint32_t root, const Shap
   }
 }
 
+// The contraction pipeline stores through TMA maps / rewrites its output in place; every other plan writes `out` exactly once
+// with plain stores, so `out` may be any device-visible memory.
+bool plan_output_redirectable(const PlanCache& pc) {
+  cc_kernel_info_t info;
+  check(cc_kernel_info(pc.kernel, &info));
+  return info.kind != 2;
+}
+
 // enqueueClosure (Tensors.scala:1291-1392)
-PendingBuffer enqueue_plan(Session& s, const PlanCache& pc, const Shape& out_shape) {
+PendingBuffer enqueue_plan(Session& s, const PlanCache& pc, const Shape& out_shape, cc_buffer out_override, cc_event* out_event) {
   std::vector<cc_buffer> args;
   cc_buffer out = 0;
   try {
     // upvalues.traverse(tree.id.asInstanceOf[Tensor].doBuffer) — Tensors.scala:1336-1340
     for (const Tensor* t : pc.args) args.push_back(t->do_buffer(s).buffer);
-    check(cc_buffer_alloc((uint64_t)product(out_shape), &out));
-    check(cc_launch(pc.kernel, args.data(), (int)args.size(), out, nullptr, 0, nullptr));
+    if (out_override)
+      out = out_override;
+    else
+      check(cc_buffer_alloc((uint64_t)product(out_shape), &out));
+    check(cc_launch(pc.kernel, args.data(), (int)args.size(), out, nullptr, 0, out_event));
   } catch (...) {
-    if (out) cc_buffer_release(out);
+    if (out && !out_override) cc_buffer_release(out);
     for (cc_buffer b : args) cc_buffer_release(b);
     throw;
   }
@@ -609,10 +667,66 @@ TensorPtr Tensor::do_cache() {
 
 // ---- slow actions ---------------------------------------------------------------------------------------------------------------
 
+// Results up to this many floats are stored into pinned host memory by the producing kernel itself: a 4 KB read-back costs one
+// launch + one wait (~11 us) instead of launch + copy command + wait (~18 us; scripts/gpu_call_overhead.py). Beyond it the copy
+// engine's PCIe efficiency wins.
+constexpr uint64_t kDirectToHostFloats = 16384;
+
+void Tensor::read_into_pinned(float* pinned, uint64_t n) const {
+  if (n > 0 && n <= kDirectToHostFloats) {
+    uint64_t dptr = 0;
+    cc_buffer wrapped = 0;
+    if (cc_host_device_ptr(pinned, &dptr) == CC_OK && cc_buffer_wrap(dptr, n, &wrapped) == CC_OK) {
+      cc_event ev = 0;
+      bool direct = false;
+      try {
+        Session s;
+        direct = evaluate_into(s, wrapped, &ev);
+        if (direct) check(cc_event_wait(ev));
+      } catch (...) {
+        if (ev) cc_event_release(ev);
+        cc_buffer_release(wrapped);
+        throw;
+      }
+      if (ev) cc_event_release(ev);
+      cc_buffer_release(wrapped);
+      if (direct) return;
+    }
+  }
+  flat_array_into(pinned, n);
+}
+
 void Tensor::flat_array_into(float* host, uint64_t capacity) const {
   const uint64_t n = (uint64_t)size();
   CC_REQUIRE(capacity >= n, CC_ERR_ILLEGAL_ARGUMENT, "flatArray needs room for %llu floats, got %llu", (unsigned long long)n,
              (unsigned long long)capacity);
+  if (n > 0 && n <= kDirectToHostFloats) {
+    // small result: let the kernel store into pooled pinned memory, then one memcpy into the caller's (pageable) array
+    void* pinned = nullptr;
+    if (cc_host_alloc(n * 4, &pinned) == CC_OK) {
+      uint64_t dptr = 0;
+      cc_buffer wrapped = 0;
+      bool direct = false;
+      if (cc_host_device_ptr(pinned, &dptr) == CC_OK && cc_buffer_wrap(dptr, n, &wrapped) == CC_OK) {
+        cc_event ev = 0;
+        try {
+          Session s;
+          direct = evaluate_into(s, wrapped, &ev);
+          if (direct) check(cc_event_wait(ev));
+        } catch (...) {
+          if (ev) cc_event_release(ev);
+          cc_buffer_release(wrapped);
+          cc_host_free(pinned);
+          throw;
+        }
+        if (ev) cc_event_release(ev);
+        cc_buffer_release(wrapped);
+      }
+      if (direct) memcpy(host, pinned, (size_t)n * 4);
+      cc_host_free(pinned);
+      if (direct) return;
+    }
+  }
   Session s;
   PendingBuffer p = do_buffer(s);
   int st = cc_buffer_to_host(p.buffer, 0, host, n, nullptr, 0, nullptr);
@@ -814,7 +928,7 @@ int ct_flat_buffer(ct_tensor t, float** out_host, uint64_t* out_n_floats) {
     int st = cc_host_alloc(n * 4, &host);
     if (st != CC_OK) throw Error(st, cc_last_error());
     try {
-      ref(t)->flat_array_into((float*)host, n);
+      ref(t)->read_into_pinned((float*)host, n);
     } catch (...) {
       cc_host_free(host);
       throw;

@@ -52,6 +52,12 @@ class Tensor : public std::enable_shared_from_this<Tensor> {
   // doBuffer (Tensors.scala:1401-1403 etc.): the returned buffer is retained for the caller
   PendingBuffer do_buffer(Session& s) const;
   virtual PendingBuffer evaluate(Session& s) const = 0;
+  // evaluate with the kernel storing straight into `out` (a wrapped, device-visible buffer — pinned host memory for small
+  // read-backs); `*out_event` completes when `out` is written. false = this tensor has no kernel of its own to redirect
+  virtual bool evaluate_into(Session& s, cc_buffer out, cc_event* out_event) const {
+    (void)s, (void)out, (void)out_event;
+    return false;
+  }
   // compile only (no device work): the kernel this tensor's closure maps to
   cc_kernel compile_only() const;
 
@@ -74,6 +80,8 @@ class Tensor : public std::enable_shared_from_this<Tensor> {
   // ---- slow actions (Tensors.scala:776-811, 1099-1118) ----
   std::vector<float> flat_array() const;
   void flat_array_into(float* host, uint64_t capacity) const;
+  // evaluate into pinned host memory from cc_host_alloc; small results are stored there by the kernel itself (no copy command)
+  void read_into_pinned(float* pinned, uint64_t n) const;
   std::string to_string() const;
 };
 

@@ -71,6 +71,7 @@ def _L():
         L.cc_buffer_to_host.argtypes = [h, u64, C.c_void_p, u64, hp, C.c_int, hp]
         L.cc_host_alloc.argtypes = [u64, C.POINTER(C.c_void_p)]
         L.cc_host_free.argtypes = [C.c_void_p]
+        L.cc_host_device_ptr.argtypes = [C.c_void_p, hp]
         for n in ("cc_event_retain", "cc_event_release", "cc_event_wait"):
             getattr(L, n).argtypes = [h]
         L.cc_event_query.argtypes = [h, C.POINTER(C.c_int)]

@@ -104,6 +104,9 @@ int cc_buffer_to_host(cc_buffer b, uint64_t offset_floats, float* host, uint64_t
  * is unpinned and freed by cc_shutdown. */
 int cc_host_alloc(uint64_t bytes, void** out);
 int cc_host_free(void* p);
+/* the device-side address of a cc_host_alloc block (mapped pinned memory): with cc_buffer_wrap it lets a kernel store a
+ * small result straight into host memory instead of paying a separate copy command */
+int cc_host_device_ptr(void* host, uint64_t* out_device_ptr);
 
 /* ---- events ----------------------------------------------------------------------------------------------- */
 

@@ -191,6 +191,55 @@ def test_flat_buffer_is_pinned_and_pooled(cuda):  # flatBuffer, Tensors.scala:10
     assert cuda._L().cc_host_free(C.c_void_p(0x1000)) == -1
 
 
+def test_small_results_are_stored_into_host_memory_by_the_kernel(cuda):
+    """flatArray / flatBuffer of <= 16384 floats: the kernel's output buffer IS pinned host memory (no copy command); the values
+    are those of the ordinary device-buffer route"""
+    T = cuda.Tensor
+    a, b = T.random([96, 128], seed=1).doCache(), T.random([96, 128], seed=2).doCache()
+    cases = {
+        "elementwise": T.tanh(a * b) + a,
+        "view": (a * b).permute([1, 0]).translate([1, -1]),
+        "transpose": a.transpose(),
+        "fold": (a * b).sum(),
+        "sum of a buffer": a.sum(),
+        "max": a.reduce("max"),
+        "join": T.join([a, b, a * b]).split(0)[3],
+        "axis sum": _chain(a.split(0)),
+        "small matmul (generic reduction)": _chain((a.broadcast([96, 128, 128]) * T.random([128, 128], seed=3).reshape([1, 128, 128]).broadcast([96, 128, 128])).split(1)),
+        "matmul (tensor cores: not redirected)": _chain(
+            (T.random([128, 2048], seed=5).broadcast([128, 2048, 128]) * T.random([2048, 128], seed=6).reshape([1, 2048, 128]).broadcast([128, 2048, 128])).split(1)
+        ),
+        "random": T.random([100], seed=9),
+        "scalar": T.scalar(2.5) * T.scalar(4.0),
+    }
+    for name, e in cases.items():
+        buf = e.doBuffer()
+        n = int(np.prod(e.shape)) if e.shape else 1
+        via_device = buf.to_host(n)
+        buf.release()
+        before = cuda.stats()["d2h_bytes"]
+        got = e.flatArray()
+        with e.flatBuffer() as pinned:
+            assert np.array_equal(pinned.view(np.uint32), via_device.view(np.uint32)), name
+        copied = cuda.stats()["d2h_bytes"] - before
+        assert np.array_equal(got.view(np.uint32), via_device.view(np.uint32)), name
+        if name in ("elementwise", "view", "transpose", "fold", "sum of a buffer", "max", "axis sum", "scalar", "small matmul (generic reduction)"):
+            assert copied == 0, (name, copied)  # no copy command was issued
+        elif name in ("random",) or name.startswith("matmul"):
+            assert copied == 2 * 4 * n, (name, copied)
+    big = T.tanh(T.random([129, 128], seed=4))  # 16512 floats: over the threshold, ordinary route
+    before = cuda.stats()["d2h_bytes"]
+    big.flatArray()
+    assert cuda.stats()["d2h_bytes"] - before == 4 * 129 * 128
+
+
+def _chain(parts):
+    acc = parts[0]
+    for p in parts[1:]:
+        acc = acc + p
+    return acc
+
+
 def test_transpose(cuda):  # TensorsSpec.scala:436-466
     T = cuda.Tensor
     assert str(T.scalar(42.0).transpose()) == "42.0"
