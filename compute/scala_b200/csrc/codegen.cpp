@@ -82,6 +82,7 @@ struct Program {
   std::vector<Op> ops;        // the term (evaluated for every point of the index space)
   std::vector<Load> loads;
   std::vector<int> results;
+  int64_t tuple_inner = 1;    // several results (un-rolled join): the result index sits before the last dims whose product this is
   // reductions only
   int n_red = 0;              // number of trailing reduction dims
   std::vector<Op> post_ops;   // epilogue applied once per output element to the folded value (K_ACC); may use loads
@@ -146,6 +147,31 @@ void analyze_load(Load& L, const std::vector<int64_t>& dims) {
     for (int x = 0; x < nd; ++x)
       if (dims[x] > 1 && L.coef[x] == 0) L.reuse = true;
   }
+}
+
+// Moves index dimension `from` to position `to` (the dimensions in between shift by one): the same program over a permuted
+// index space, i.e. a permuted output layout. Used to put a re-rolled join index where Tensor.join(tensors, dimension) wants it.
+void move_index_dim(Program& p, int from, int to) {
+  if (from == to) return;
+  const int nd = (int)p.dims.size();
+  std::vector<int> order;  // new position -> old position
+  for (int x = 0; x < nd; ++x)
+    if (x != from) order.push_back(x);
+  order.insert(order.begin() + to, from);
+  std::vector<int64_t> dims(nd);
+  for (int x = 0; x < nd; ++x) dims[x] = p.dims[order[x]];
+  for (Load& L : p.loads) {
+    const int rows = (int)L.src_shape.size(), cols = nd + 1;
+    std::vector<double> M(L.M.size());
+    for (int y = 0; y < rows; ++y) {
+      for (int x = 0; x < nd; ++x) M[(size_t)y * cols + x] = L.M[(size_t)y * cols + order[x]];
+      M[(size_t)y * cols + nd] = L.M[(size_t)y * cols + nd];
+    }
+    L.M = std::move(M);
+    L.reuse = false;
+    analyze_load(L, dims);
+  }
+  p.dims = std::move(dims);
 }
 
 // ---- program construction ---------------------------------------------------------------------------------------
@@ -1012,7 +1038,13 @@ void emit_elementwise(Plan& plan, const Program& p, int n_args, const DeviceProp
     else
       e("  out[v] = o[0][0];\n");
   } else {
-    for (int r = 0; r < nres; ++r) e("  out[v * %d + %d] = o[%d][0];\n", nres, r, r);
+    if (p.tuple_inner == 1) {
+      for (int r = 0; r < nres; ++r) e("  out[v * %d + %d] = o[%d][0];\n", nres, r, r);
+    } else {
+      e("  const %s vo = v / (%s)%lld, vi = v - vo * (%s)%lld;\n", IDX, IDX, (long long)p.tuple_inner, IDX, (long long)p.tuple_inner);
+      for (int r = 0; r < nres; ++r)
+        e("  out[(vo * %d + %d) * (%s)%lld + vi] = o[%d][0];\n", nres, r, IDX, (long long)p.tuple_inner, r);
+    }
   }
   e("}\n");
   if (min_blocks > 0)
@@ -1698,10 +1730,19 @@ Plan make_plan(const Tree& t, const DeviceProps& dev) {
     StepMap step_c;
     bool rolled_c = false;
     uint32_t base = t.root;
+    // where the element index lands in the output: last (Tensor.join(tensors), T:577-598) or `position` (join(tensors, dimension),
+    // T:560-575: the reference joins last and gathers a permuted view in a second kernel)
+    int join_pos = -1;
+    std::vector<int64_t> final_odims = odims;
     if (joined) {
-      CC_REQUIRE(!odims.empty() && odims.back() == (int64_t)root.kids.size(), CC_ERR_BAD_TREE,
-                 "Concatenate of %zu elements needs an output shape ending in %zu", root.kids.size(), root.kids.size());
+      CC_REQUIRE(!odims.empty(), CC_ERR_BAD_TREE, "Concatenate needs an output shape of rank >= 1");
+      join_pos = root.position < 0 ? (int)odims.size() - 1 : root.position;
+      CC_REQUIRE(join_pos < (int)odims.size() && odims[(size_t)join_pos] == (int64_t)root.kids.size(), CC_ERR_BAD_TREE,
+                 "Concatenate of %zu elements at dimension %d does not match the output shape", root.kids.size(), join_pos);
       nd_base = (int)odims.size() - 1;
+      // build over head dims + [element index]; moved into place afterwards
+      odims.erase(odims.begin() + join_pos);
+      odims.push_back((int64_t)root.kids.size());
       rolled_c = root.kids.size() >= 2 && reroll(t, root.kids, step_c);
       base = root.kids[0];
     }
@@ -1709,6 +1750,7 @@ Plan make_plan(const Tree& t, const DeviceProps& dev) {
       Builder b{t, {}, nd_base, {}, {}, &arg_of_param, &arg_nodes};
       b.prog.dims.assign(odims.begin(), odims.end() - 1);
       for (uint32_t k : root.kids) b.prog.results.push_back(b.export_node(k));
+      for (int x = join_pos; x < nd_base; ++x) b.prog.tuple_inner *= odims[(size_t)x];
       prog = std::move(b.prog);
       plan.note = "join as per-index tuple stores";
     } else {
@@ -1739,7 +1781,9 @@ Plan make_plan(const Tree& t, const DeviceProps& dev) {
         if (rolled_c) plan.note = "join re-rolled into an output dimension";
       }
       prog = std::move(b.prog);
+      if (joined && join_pos != nd_base) move_index_dim(prog, nd_base, join_pos);
     }
+    odims = final_odims;
   }
 
   if (is_reduce && prog.trivial_post() && prog.n_red == 1) {

@@ -140,9 +140,15 @@ Tree parse_tree(const void* blob, uint64_t n_bytes) {
       nd.kids.push_back(kid());
       uint32_t ak = t.nodes[nd.kids[0]].kind;
       CC_REQUIRE(ak == K_PARAM || ak == K_TRANSFORM, CC_ERR_BAD_TREE, "Extract of a non-array node");
-    } else if (nd.kind == K_CONCAT) {
+    } else if (nd.kind == K_CONCAT || nd.kind == K_CONCAT_AT) {
       uint32_t m = r.u32();
       CC_REQUIRE(m >= 1 && m <= (1u << 24), CC_ERR_BAD_TREE, "bad Concatenate length");
+      if (nd.kind == K_CONCAT_AT) {
+        uint32_t pos = r.u32();
+        CC_REQUIRE(pos < 16, CC_ERR_BAD_TREE, "bad Concatenate position %u", pos);
+        nd.position = (int32_t)pos;
+        nd.kind = K_CONCAT;
+      }
       for (uint32_t j = 0; j < m; ++j) nd.kids.push_back(kid());
     } else if (nd.kind == K_REDUCE) {
       nd.monoid = r.u32();
@@ -255,6 +261,11 @@ void canonicalize(Tree& t) {
         put32((uint32_t)nd.shape.size());
         for (int32_t s : nd.shape) put32((uint32_t)s);
         break;
+      case K_CONCAT:
+        put32((uint32_t)nd.kids.size());
+        for (uint32_t k : nd.kids) put32((uint32_t)canon[k]);
+        put32((uint32_t)(nd.position + 1));
+        break;
       default:
         put32((uint32_t)nd.kids.size());
         for (uint32_t k : nd.kids) put32((uint32_t)canon[k]);
@@ -316,9 +327,10 @@ uint32_t TreeWriter::extract(uint32_t array) {
   u32(array);
   return i;
 }
-uint32_t TreeWriter::concatenate(const std::vector<uint32_t>& elements) {
-  uint32_t i = begin(K_CONCAT);
+uint32_t TreeWriter::concatenate(const std::vector<uint32_t>& elements, int32_t position) {
+  uint32_t i = begin(position < 0 ? K_CONCAT : K_CONCAT_AT);
   u32((uint32_t)elements.size());
+  if (position >= 0) u32((uint32_t)position);
   for (uint32_t e : elements) u32(e);
   return i;
 }

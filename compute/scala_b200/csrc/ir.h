@@ -18,6 +18,10 @@ enum Kind : uint32_t {
   K_TRANSFORM = 3,
   K_EXTRACT = 4,
   K_CONCAT = 5,
+  // Concatenate whose element index lands at output dimension `position` instead of last: Tensor.join(tensors, dimension)
+  // (Tensors.scala:560-575) in ONE kernel; the reference materialises the join and gathers a permuted view of it. Parsed into
+  // a K_CONCAT node with `position` set.
+  K_CONCAT_AT = 6,
   K_EXP = 10,
   K_LOG = 11,
   K_ABS = 12,
@@ -51,6 +55,7 @@ struct Node {
   uint32_t rows = 0, cols = 0; // transform matrix, row-major rows x cols (cols = view rank + 1)
   std::vector<double> matrix;
   std::vector<uint32_t> kids;  // operands / array / concatenate elements
+  int32_t position = -1;       // K_CONCAT: output dimension of the element index (-1 = last, Tensors.scala:577-598)
   uint32_t monoid = 0;         // K_REDUCE: K_PLUS / K_MIN / K_MAX / K_TIMES (shape = index space of the operand)
 };
 
@@ -78,7 +83,7 @@ class TreeWriter {
   uint32_t parameter(uint64_t id, float padding, const std::vector<int32_t>& shape, int32_t def_root = -1);
   uint32_t transform(uint32_t array, uint32_t rows, uint32_t cols, const double* m);
   uint32_t extract(uint32_t array);
-  uint32_t concatenate(const std::vector<uint32_t>& elements);
+  uint32_t concatenate(const std::vector<uint32_t>& elements, int32_t position = -1);
   uint32_t unary(uint32_t kind, uint32_t a);
   uint32_t binary(uint32_t kind, uint32_t a, uint32_t b);
   uint32_t reduce(uint32_t monoid, uint32_t operand, const std::vector<int32_t>& operand_shape);

@@ -296,13 +296,14 @@ struct ReduceTensor final : NonInlineTensor {
 // Tensor.join (Tensors.scala:577-598): one kernel over the head shape whose root is Concatenate(elements)
 struct JoinTensor final : NonInlineTensor {
   std::vector<TensorPtr> tensors;
+  int32_t position = -1;  // output dimension of the element index; -1 = last
   ~JoinTensor() override {
     for (auto& t : tensors) bury(std::move(t));
   }
   uint32_t emit_root(EmitCtx& ctx) const {
     std::vector<uint32_t> e;
     for (auto& t : tensors) e.push_back(t->closure(ctx));
-    return ctx.w.concatenate(e);
+    return ctx.w.concatenate(e, position);
   }
   mutable PlanCache plan;
   PendingBuffer evaluate(Session& s) const override {
@@ -532,14 +533,19 @@ TensorPtr join(const std::vector<TensorPtr>& tensors) {
   return j;
 }
 
+// Tensors.scala:560-575 is `join(tensors).permute(...)`: a join kernel, then a gather of the permuted view. Here the join kernel
+// itself stores with the element index at `dimension` (one kernel, one pass; node ConcatenateAt).
 TensorPtr join(const std::vector<TensorPtr>& tensors, int dimension) {
   TensorPtr j = join(tensors);
   const int n = (int)j->shape.size();
   CC_REQUIRE(dimension >= 0 && dimension < n, CC_ERR_ILLEGAL_ARGUMENT, "join dimension %d out of range", dimension);
   if (n - 1 == dimension) return j;
-  std::vector<int32_t> perm(n);
-  for (int i = 0; i < n; ++i) perm[i] = i < dimension ? i : (i == dimension ? n - 1 : i - 1);
-  return j->permute(perm);
+  Shape s = tensors[0]->shape;
+  s.insert(s.begin() + dimension, (int32_t)tensors.size());
+  auto at = make<JoinTensor>(s, tensors[0]->padding);
+  at->tensors = tensors;
+  at->position = dimension;
+  return at;
 }
 
 // ---- delayed operators ---------------------------------------------------------------------------------------------------------

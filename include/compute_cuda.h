@@ -132,6 +132,8 @@ int cc_synchronize(void);
  *     3 Transform       u32 array, u32 rows, u32 cols, f64 matrix[rows*cols]   R:676-690
  *     4 Extract         u32 array                                             R:660-672
  *     5 Concatenate     u32 n, u32 element[n]                                 R:953-973
+ *     6 ConcatenateAt   u32 n, u32 position, u32 element[n]   (root only) the element index becomes output dimension
+ *                       `position` instead of the last one: Tensor.join(tensors, dimension), T:560-575, in one kernel
  *     10 Exp 11 Log 12 Abs 13 Tanh 14 Sqrt 15 UnaryMinus     u32 operand       R:384-470,620-658
  *     20 Min 21 Max 22 Plus 23 Minus 24 Times 25 Div 26 Percent   u32 lhs, u32 rhs   R:472-618
  *     30 Reduce         u32 monoid (22 Plus | 20 Min | 21 Max | 24 Times), u32 operand, u32 rank, i32 shape[rank]

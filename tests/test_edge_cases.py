@@ -75,6 +75,38 @@ def test_ranks_above_three(cuda):
     assert g.shape == (1,)
 
 
+def test_join_at_every_dimension(cuda):
+    """Tensor.join(tensors, dimension) (T:560-575): the reference joins last and gathers a permuted view (two kernels); here the
+    join kernel stores with the element index at `dimension` — re-rolled joins, tuple-store joins, joins of reductions"""
+    for d in (0, 1, 2, 3):
+        same(cuda, lambda T: T.join(T.random([3, 4, 5, 6], seed=1).split(d), d))          # round trip = identity
+        same(cuda, lambda T: T.join(T.random([3, 4, 5, 6], seed=1).split((d + 1) % 4), d))  # moves a dimension
+    for d in (0, 1, 2):
+        # unrelated elements: per-index stores
+        same(cuda, lambda T: T.join([T.abs(-T.random([4, 6], seed=1)), T.random([4, 6], seed=2) * T.random([4, 6], seed=3), T.fill(2.0, [4, 6])], d))
+        # elements that are per-axis sums (matmul1-style join of folds)
+        def folds(T):
+            r = T.random([9, 5, 8], seed=4) * T.fill(9.0, [9, 5, 8])
+            x = r - r % T.fill(1.0, [9, 5, 8])  # integers 0..8: sums are exact in any order
+            cols = []
+            for part in x.split(1):
+                rows = part.split(0)
+                acc = rows[0]
+                for r in rows[1:]:
+                    acc = acc + r
+                cols.append(acc)
+            return T.join(cols, d) if d < 2 else T.join(cols)
+        same(cuda, folds)
+    same(cuda, lambda T: T.join([T.scalar(1.0), T.scalar(2.0)], 0))
+    same(cuda, lambda T: T.join([T.random([7], seed=1), T.random([7], seed=2)], 0))
+    same(cuda, lambda T: T.join([T.random([7], seed=1), T.random([7], seed=2)], 0).translate([0, 1]) * T.fill(2.0, [2, 7]))
+    # big enough for the vector / tiled-transpose templates
+    g = same(cuda, lambda T: T.join(T.random([64, 96, 128], seed=5).split(0), 2))
+    assert g.shape == (64 * 96 * 128,)
+    k = cuda.Tensor.join(cuda.Tensor.random([64, 96, 128], seed=5).split(1), 1).compile()
+    assert k.info.kind == 0 and "flat=1" in k.source  # split(d) joined back at d is the identity copy, one kernel
+
+
 def test_views_that_leave_the_source(cuda):
     for pad in (0.0, -1.5, float("inf")):
         same(cuda, lambda T: T.random([4, 6], seed=1, padding=pad).translate([4, 0]))       # entirely padding
