@@ -34,6 +34,34 @@ def test_no_cpu_fallback_without_a_gpu():
         cuda.Buffer.alloc(16)
 
 
+def _build_c_consumer(tmp_path):
+    import os
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    libdir = os.path.join(root, "compute", "scala_b200")
+    exe = str(tmp_path / "c1_from_c")
+    cmd = ["gcc", "-O2", "-std=c11", "-Wall", "-Wextra", "-pedantic", "-Werror", "-D_POSIX_C_SOURCE=200809L", "-I", os.path.join(root, "include"),
+           os.path.join(root, "examples", "c1_from_c.c"), "-o", exe, "-L", libdir, "-lcompute_cuda", f"-Wl,-rpath,{libdir}", "-lm"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return exe
+
+
+def test_header_is_plain_c_and_a_c_caller_fails_loudly_without_a_gpu(tmp_path):
+    """include/compute_cuda.h compiles as strict C11 (scalars and pointers only) and links against the library; the C program
+    that drives BASELINE config 1 through it refuses to run without a driver instead of falling back to the CPU"""
+    import subprocess
+
+    import torch
+
+    exe = _build_c_consumer(tmp_path)
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present: the run itself is tests/test_threads_and_events.py::test_c_consumer_runs_config_1")
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 3 and "no CPU fallback" in r.stderr and b"sm_100a".decode() in r.stdout
+
+
 def test_product_does_not_import_the_oracle():
     import os
     import re

@@ -126,3 +126,19 @@ def test_builtin_profiler(cuda):
     assert cuda.profile_report() == []  # consumed; nothing recorded while off
     e.doBuffer().release()
     assert cuda.profile_report() == []
+
+
+def test_c_consumer_runs_config_1(cuda, tmp_path):
+    """examples/c1_from_c.c: BASELINE config 1 built and evaluated from plain C through include/compute_cuda.h, in its own process"""
+    import re
+    import subprocess
+
+    from test_abi_and_codegen import _build_c_consumer
+
+    exe = _build_c_consumer(tmp_path)
+    r = subprocess.run([exe, "3000"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, (r.stdout, r.stderr)
+    m = re.search(r"C1 device-resident from C: ([0-9.]+) us/step", r.stdout)
+    assert m and 0.5 < float(m.group(1)) < 100.0, r.stdout
+    assert "compiles=" in r.stdout and "max relative error" in r.stdout
+    print(r.stdout)
