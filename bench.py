@@ -337,9 +337,9 @@ def sharded_configs(cuda, dist, rank: int, world: int, hbm_peak: float, tf_peak:
         measure(f"C3 full sum 16384^2 sharded + allreduce(1 float) [{tag}]", lambda: comm.full_sum(x).release(), alg_bytes=4 * ROWS * COLS, steps=50)
         measure(f"C3 axis-0 sum 16384^2 sharded + allreduce(16384 floats) [{tag}]", lambda: comm.axis0_sum(col_sums).release(),
                 alg_bytes=4 * ROWS * COLS, steps=50)
+        measure(f"C3 axis-1 sum 16384^2 sharded + allgather [{tag}]", lambda: comm.axis1_sum(row_sums).release(), alg_bytes=4 * ROWS * COLS, steps=50)
     if had_peer:
         comm.route_peer(True)
-    measure("C3 axis-1 sum 16384^2 sharded + allgather [NCCL]", lambda: comm.axis1_sum(row_sums).release(), alg_bytes=4 * ROWS * COLS, steps=50)
     del x, col_sums, row_sums
     n5 = 8192
     m5 = sharding.shard_rows(n5, world, rank)[1]

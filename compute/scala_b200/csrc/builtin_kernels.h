@@ -35,6 +35,8 @@ size_t peer_mailbox_bytes(int world);
 size_t peer_mailbox_flag_offset(int world);  // byte offset of the flags inside one mailbox allocation
 // in-place all-reduce(sum) of v[0..n), n <= kPeerCapFloats; `epoch` must increase by one per collective call on every rank
 void launch_peer_allreduce(float* v, uint64_t n, const PeerMailboxes& mb, unsigned epoch, cudaStream_t stream);
+// one-shot all-gather of <= kPeerCapFloats floats per rank over the same mailboxes: recv[r*n .. (r+1)*n) = rank r's send
+void launch_peer_allgather(const float* send, float* recv, uint64_t n_per_rank, const PeerMailboxes& mb, unsigned epoch, cudaStream_t stream);
 // cross-rank barrier over the mailbox flags (one tiny kernel): returns on the stream once every rank has reached it
 void launch_peer_barrier(const PeerMailboxes& mb, unsigned epoch, cudaStream_t stream);
 // Tensor.sum over a sharded tensor as ONE kernel: local two-stage reduction whose last block pushes the partial into every

@@ -173,6 +173,48 @@ __global__ void __launch_bounds__(256) peer_allreduce_kernel(float* __restrict__
   }
 }
 
+// one-shot all-gather: recv[r * n .. (r + 1) * n) = rank r's send[0 .. n). Same exchange as the all-reduce above (block b pushes its
+// 1024 floats into slot [rank] of every peer's mailbox over NVLink, raises the epoch flags, waits for the peers' flags in its own
+// mailbox) with the rank-ordered sum replaced by a copy of every slot into place.
+__global__ void __launch_bounds__(256) peer_allgather_kernel(const float* __restrict__ send, float* __restrict__ recv, uint64_t n, PeerMailboxes mb,
+                                                             unsigned epoch) {
+  const int parity = (int)(epoch & 1u);
+  const int b = blockIdx.x;
+  const size_t i = (size_t)b * kPeerChunk + (size_t)threadIdx.x * 4;
+  const bool vec = (n & 3u) == 0 && i + 3 < n;  // n % 4 == 0 keeps every rank's slice of recv 16-byte aligned
+  float t[4] = {0.f, 0.f, 0.f, 0.f};
+  if (vec) {
+    const float4 x = *reinterpret_cast<const float4*>(send + i);
+    t[0] = x.x, t[1] = x.y, t[2] = x.z, t[3] = x.w;
+  } else {
+    for (int j = 0; j < 4; ++j)
+      if (i + j < n) t[j] = send[i + j];
+  }
+  if (i < n)
+    for (int peer = 0; peer < mb.world; ++peer)
+      *reinterpret_cast<float4*>(mb.data[peer] + mb_data_index(parity, mb.world, mb.rank, i)) = make_float4(t[0], t[1], t[2], t[3]);
+  __threadfence_system();
+  __syncthreads();
+  if ((int)threadIdx.x < mb.world) {
+    const int peer = threadIdx.x;
+    st_release_sys(mb.flags[peer] + mb_flag_index(parity, mb.world, mb.rank, b), epoch);
+    wait_flag(mb.flags[mb.rank] + mb_flag_index(parity, mb.world, peer, b), epoch);
+  }
+  __syncthreads();
+  if (i >= n) return;
+  for (int r = 0; r < mb.world; ++r) {
+    const float4 x = __ldcv(reinterpret_cast<const float4*>(mb.data[mb.rank] + mb_data_index(parity, mb.world, r, i)));
+    float* dst = recv + (size_t)r * n + i;
+    if (vec) {
+      *reinterpret_cast<float4*>(dst) = x;
+    } else {
+      const float y[4] = {x.x, x.y, x.z, x.w};
+      for (int j = 0; j < 4; ++j)
+        if (i + j < n) dst[j] = y[j];
+    }
+  }
+}
+
 // every rank raises its epoch flag in every peer's mailbox (after a system-scope fence, so everything this GPU wrote before —
 // including the previous kernel's stores into peer memory — is visible first) and waits for all peers' flags in its own
 __global__ void __launch_bounds__(32) peer_barrier_kernel(PeerMailboxes mb, unsigned epoch) {
@@ -269,6 +311,14 @@ void launch_peer_allreduce(float* v, uint64_t n, const PeerMailboxes& mb, unsign
   const unsigned blocks = (unsigned)((n + kPeerChunk - 1) / kPeerChunk);
   peer_allreduce_kernel<<<blocks, 256, 0, stream>>>(v, n, mb, epoch);
   check_launch("peer_allreduce");
+}
+
+void launch_peer_allgather(const float* send, float* recv, uint64_t n_per_rank, const PeerMailboxes& mb, unsigned epoch, cudaStream_t stream) {
+  CC_REQUIRE(n_per_rank <= (uint64_t)kPeerCapFloats, CC_ERR_UNSUPPORTED, "peer all-gather carries at most %d floats per rank", kPeerCapFloats);
+  if (n_per_rank == 0) return;
+  const unsigned blocks = (unsigned)((n_per_rank + kPeerChunk - 1) / kPeerChunk);
+  peer_allgather_kernel<<<blocks, 256, 0, stream>>>(send, recv, n_per_rank, mb, epoch);
+  check_launch("peer_allgather");
 }
 
 void launch_peer_barrier(const PeerMailboxes& mb, unsigned epoch, cudaStream_t stream) {

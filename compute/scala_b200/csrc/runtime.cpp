@@ -1740,7 +1740,11 @@ int cc_allgather(cc_buffer send, cc_buffer recv, uint64_t n_per_rank, const cc_e
     op.label = "all-gather";
     op.bytes = n_per_rank * 4 * (uint64_t)ranks;
     op_begin(op, waits, n_waits);
-    if (n.comm)
+    if (n.comm && n.peer_enabled && n_per_rank <= (uint64_t)kPeerCapFloats) {
+      // small blocks (the row sums of a sharded tensor): one kernel over the NVLink mailboxes instead of an NCCL call
+      launch_peer_allgather((const float*)s->ptr, (float*)d->ptr, n_per_rank, n.mb, ++n.epoch, (cudaStream_t)op.cu());
+      rt().stats.device_kernels++;
+    } else if (n.comm)
       n.check(n.AllGather((const void*)s->ptr, (void*)d->ptr, n_per_rank, ncclFloat, n.comm, (cudaStream_t)op.cu()), "ncclAllGather");
     else
       CC_CU(cuMemcpyDtoDAsync(d->ptr, s->ptr, (size_t)n_per_rank * 4, op.cu()));

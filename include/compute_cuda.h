@@ -246,7 +246,8 @@ int cc_comm_symmetric_alloc(uint64_t n_floats, cc_buffer* out);
  * bracketed by two flag barriers over the peer mailboxes. Needs N % 4 == 0. */
 int cc_matmul_3xtf32_allgather(cc_buffer a_shard, cc_buffer b, cc_buffer gathered, int64_t m_shard, int64_t n, int64_t k,
                                const cc_event* waits, int n_waits, cc_event* out_event);
-/* recv[rank*n .. (rank+1)*n) = send[0..n) of every rank */
+/* recv[rank*n .. (rank+1)*n) = send[0..n) of every rank. With peer mailboxes enabled, blocks of <= 65536 floats per rank go through
+ * a one-shot kernel over NVLink peer memory (like cc_allreduce_sum); larger ones through ncclAllGather. */
 int cc_allgather(cc_buffer send, cc_buffer recv, uint64_t n_floats_per_rank, const cc_event* waits, int n_waits,
                  cc_event* out_event);
 int cc_broadcast(cc_buffer buf, uint64_t n_floats, int root, const cc_event* waits, int n_waits, cc_event* out_event);

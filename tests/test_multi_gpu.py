@@ -63,6 +63,24 @@ def _worker(rank, world, port):
             expect = ((base * world + sum(range(world))) * world) * world
             assert np.array_equal(got, expect), (length, got[:4], expect[:4])
             buf.release()
+        # ragged one-shot all-gathers over the same mailboxes, back to back, against the NCCL route
+        for length in (1, 3, 1000, 1024, 1025, 4099, 65536, 65537):  # 65537 floats per rank: above the mailbox capacity -> NCCL
+            v = (np.arange(length, dtype=np.float32) % 251) + 1000 * rank
+            send = cuda.Buffer.from_host(v)
+            expect = np.concatenate([(np.arange(length, dtype=np.float32) % 251) + 1000 * r for r in range(world)])
+            for route in (True, False, True):
+                comm.route_peer(route)
+                recv = cuda.Buffer.from_host(np.full(length * world + 8, -1.0, np.float32))
+                before = cuda.stats()["device_kernels"]
+                cuda.allgather(send, recv, length)
+                got = recv.to_host(length * world + 8)
+                assert np.array_equal(got[: length * world], expect), (length, route)
+                assert (got[length * world :] == -1.0).all()  # nothing written past the gathered vector
+                if route and length <= 65536:
+                    assert cuda.stats()["device_kernels"] == before + 1  # our kernel, not an NCCL call
+                recv.release()
+            send.release()
+        comm.route_peer(True)
         s = comm.full_sum(shard)
         c0 = comm.axis0_sum(col_sums)
         c1 = comm.axis1_sum(_axis_sum(shard, 1), gather=True)
