@@ -816,11 +816,24 @@ using namespace compute::cuda;
 using cc::guarded;
 
 namespace {
+// every handle given out is registered: a stale or made-up ct_tensor is an IllegalArgument, not a wild pointer dereference
+// inside the caller's JVM
+std::mutex g_handles_mu;
+std::unordered_set<TensorPtr*> g_handles;
+
 TensorPtr& ref(ct_tensor h) {
   CC_REQUIRE(h, CC_ERR_ILLEGAL_ARGUMENT, "null tensor handle");
-  return *(TensorPtr*)(uintptr_t)h;
+  TensorPtr* p = (TensorPtr*)(uintptr_t)h;
+  std::lock_guard<std::mutex> lock(g_handles_mu);
+  CC_REQUIRE(g_handles.count(p), CC_ERR_ILLEGAL_ARGUMENT, "invalid tensor handle");
+  return *p;
 }
-ct_tensor wrap(TensorPtr t) { return (ct_tensor)(uintptr_t) new TensorPtr(std::move(t)); }
+ct_tensor wrap(TensorPtr t) {
+  TensorPtr* p = new TensorPtr(std::move(t));
+  std::lock_guard<std::mutex> lock(g_handles_mu);
+  g_handles.insert(p);
+  return (ct_tensor)(uintptr_t)p;
+}
 Shape to_shape(const int32_t* s, int rank) {
   CC_REQUIRE(rank >= 0 && (rank == 0 || s), CC_ERR_ILLEGAL_ARGUMENT, "bad shape arguments");
   return Shape(s, s + rank);
@@ -972,7 +985,11 @@ int ct_compile(ct_tensor t, cc_kernel* out) {
 int ct_release(ct_tensor t) {
   return guarded([&] {
     TensorPtr* p = &ref(t);
-    delete p;
+    {
+      std::lock_guard<std::mutex> lock(g_handles_mu);
+      g_handles.erase(p);
+    }
+    delete p;  // outside the lock: may cascade into a whole graph's destruction
   });
 }
 int ct_live_tensors(int64_t* out) {
