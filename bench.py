@@ -531,7 +531,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--rows", type=int, default=ROWS, help="rows of the [rows,16384] shard per GPU (default = the full config)")
-    ap.add_argument("--e2e-chunks", type=int, default=8)
+    ap.add_argument("--e2e-chunks", type=int, default=16)
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-side-configs", action="store_true")
