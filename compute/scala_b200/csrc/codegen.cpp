@@ -85,6 +85,7 @@ struct Program {
   int64_t tuple_inner = 1;    // several results (un-rolled join): the result index sits before the last dims whose product this is
   // reductions only
   int n_red = 0;              // number of trailing reduction dims
+  uint32_t red_monoid = K_PLUS;  // what the re-rolled chain folds with: K_PLUS / K_TIMES / K_MIN / K_MAX
   std::vector<Op> post_ops;   // epilogue applied once per output element to the folded value (K_ACC); may use loads
   int post_result = -1;
   std::vector<char> load_in_post;  // per load: referenced by the epilogue (1) or by the term (0)
@@ -358,11 +359,16 @@ bool reroll(const Tree& t, const std::vector<uint32_t>& elems, std::unordered_ma
   return true;
 }
 
-// left-leaning Plus chain (((e0 + e1) + e2) + ...) -> [e0, e1, ...]
+// The monoids of MonoidPrograms (Tensors.scala:308-311). Users fold a split with any of them: `t.split(axis).reduce(_ + _)`
+// (README.md:301-310), and equally `.reduce(Tensor.max)`, `.reduce(Tensor.min)`, `.reduce(_ * _)`.
+inline bool is_monoid(uint32_t k) { return k == K_PLUS || k == K_TIMES || k == K_MIN || k == K_MAX; }
+
+// left-leaning chain (((e0 op e1) op e2) op ...) of root's own operator -> [e0, e1, ...]
 std::vector<uint32_t> plus_chain(const Tree& t, uint32_t root) {
   std::vector<uint32_t> elems;
   uint32_t cur = root;
-  while (t.nodes[cur].kind == K_PLUS) {
+  const uint32_t kind = t.nodes[root].kind;
+  while (t.nodes[cur].kind == kind && is_monoid(kind)) {
     elems.push_back(t.nodes[cur].kids[1]);
     cur = t.nodes[cur].kids[0];
   }
@@ -383,6 +389,7 @@ struct Chain {
   std::vector<uint32_t> terms;
   std::vector<int64_t> levels;
   std::vector<StepMap> steps;  // keyed by the Transform nodes of terms[0]
+  uint32_t monoid = K_PLUS;    // the chain's operator
 };
 
 bool nested_reroll(const Tree& t, Chain& ch) {
@@ -474,7 +481,7 @@ bool find_chain(const Tree& t, uint32_t root, Chain& best) {
     if (seen.count(i)) continue;
     seen[i] = 1;
     const Node& nd = t.nodes[i];
-    if (nd.kind == K_PLUS) {
+    if (is_monoid(nd.kind)) {
       std::vector<uint32_t> terms = plus_chain(t, i);
       if (terms.size() >= kMinRerollTerms) tops.push_back(i);
       for (uint32_t term : terms) stack.push_back(term);  // the chain's own Plus nodes are not candidates
@@ -486,6 +493,7 @@ bool find_chain(const Tree& t, uint32_t root, Chain& best) {
   for (uint32_t top : tops) {
     Chain c;
     c.top = top;
+    c.monoid = t.nodes[top].kind;
     c.terms = plus_chain(t, top);
     if (c.terms.size() <= best_len) continue;
     if (!nested_reroll(t, c)) {
@@ -1200,6 +1208,19 @@ void emit_reduce(Plan& plan, const Program& p, int n_args, const DeviceProps& de
   const int nloads = (int)p.loads.size();
   const bool has_post = !p.post_ops.empty() && !p.trivial_post();
   auto in_post = [&](int j) { return j < (int)p.load_in_post.size() && p.load_in_post[j]; };
+  // the fold: `+` stays a plain C `+` (it may contract with the term's multiply into an fma, as the reference's build allows);
+  // min / max start from NaN, which fminf / fmaxf ignore, so a chain of NaNs still folds to NaN as the unrolled chain would
+  const uint32_t mono = p.red_monoid;
+  const char* ZERO = mono == K_PLUS ? "0.f" : (mono == K_TIMES ? "1.f" : "__int_as_float(0x7fc00000)");
+  const char* MSTRUCT = mono == K_PLUS ? "cc_plus" : (mono == K_TIMES ? "cc_times" : (mono == K_MIN ? "cc_min_nan" : "cc_max_nan"));
+  auto AP = [&](const std::string& a, const std::string& b) {
+    switch (mono) {
+      case K_TIMES: return "(" + a + " * " + b + ")";
+      case K_MIN: return "fminf(" + a + ", " + b + ")";
+      case K_MAX: return "fmaxf(" + a + ", " + b + ")";
+      default: return "(" + a + " + " + b + ")";
+    }
+  };
   // choose the orientation: which index do neighbouring threads walk?
   bool any_t_contig = false, any_o_contig = false;
   for (int j = 0; j < nloads; ++j) {
@@ -1252,7 +1273,7 @@ void emit_reduce(Plan& plan, const Program& p, int n_args, const DeviceProps& de
     S = (T + TCH - 1) / TCH;
     e("// axis reduction (column owner): out dims=[");
     for (int x = 0; x < no; ++x) e("%s%lld", x ? "," : "", (long long)odims[x]);
-    e("] T=%s V=%d splits=%lld chunk=%lld idx=%s epilogue=%d\n", rd.c_str(), V, (long long)S, (long long)TCH, IDX, (int)has_post);
+    e("] T=%s V=%d splits=%lld chunk=%lld idx=%s epilogue=%d fold=%s\n", rd.c_str(), V, (long long)S, (long long)TCH, IDX, (int)has_post, kind_name(mono));
     // evd: the term at explicit reduction digits; ev: the same from the flat reduction index (used when T is split)
     std::string rgs, rgdecl;
     for (int x = no; x < nd; ++x) {
@@ -1293,7 +1314,7 @@ void emit_reduce(Plan& plan, const Program& p, int n_args, const DeviceProps& de
     if (S == 1) {
       // one thread folds the whole chain: nested loops over the reduction digits (bounds tests and address terms of the outer
       // digits hoist out of the inner loop), left to right = the reference's order; `0 + e_0` is exact
-      e("  float acc[%d];\n  #pragma unroll\n  for (int l = 0; l < %d; ++l) acc[l] = 0.f;\n", V, V);
+      e("  float acc[%d];\n  #pragma unroll\n  for (int l = 0; l < %d; ++l) acc[l] = %s;\n", V, V, ZERO);
       std::string ind = "  ";
       for (int x = no; x < nd; ++x) {
         if (T <= 96)
@@ -1306,7 +1327,7 @@ void emit_reduce(Plan& plan, const Program& p, int n_args, const DeviceProps& de
         ind += "  ";
       }
       e("%sfloat x[%d];\n%sevd(%s%s%s, x);\n", ind.c_str(), V, ind.c_str(), rgs.c_str(), gs.c_str(), pass.c_str());
-      e("%s#pragma unroll\n%sfor (int l = 0; l < %d; ++l) acc[l] = acc[l] + x[l];\n", ind.c_str(), ind.c_str(), V);
+      e("%s#pragma unroll\n%sfor (int l = 0; l < %d; ++l) acc[l] = %s;\n", ind.c_str(), ind.c_str(), V, AP("acc[l]", "x[l]").c_str());
       for (int x = no; x < nd; ++x) {
         ind.resize(ind.size() - 2);
         e("%s}\n", ind.c_str());
@@ -1315,12 +1336,12 @@ void emit_reduce(Plan& plan, const Program& p, int n_args, const DeviceProps& de
       e("  float* d = dst + v * %d;\n", V);
     } else {
       e("  const int t0 = blockIdx.y * %lld;\n  const int t1 = min(%lld, t0 + %lld);\n", (long long)TCHb, (long long)T, (long long)TCHb);
-      e("  float acc[%d];\n  #pragma unroll\n  for (int l = 0; l < %d; ++l) acc[l] = 0.f;\n", V, V);
+      e("  float acc[%d];\n  #pragma unroll\n  for (int l = 0; l < %d; ++l) acc[l] = %s;\n", V, V, ZERO);
       e("  if (live) {\n    #pragma unroll 4\n    for (int t = t0 + qy; t < t1; t += %d) {\n      float x[%d];\n      ev(t%s%s, x);\n", QS, V, gs.c_str(), pass.c_str());
-      e("      #pragma unroll\n      for (int l = 0; l < %d; ++l) acc[l] = acc[l] + x[l];\n    }\n  }\n", V);
+      e("      #pragma unroll\n      for (int l = 0; l < %d; ++l) acc[l] = %s;\n    }\n  }\n", V, AP("acc[l]", "x[l]").c_str());
       e("  if (qy > 0) {\n    #pragma unroll\n    for (int l = 0; l < %d; ++l) comb[qy - 1][cx][l] = acc[l];\n  }\n  __syncthreads();\n", V);
       e("  if (qy > 0 || !live) return;\n");
-      e("  #pragma unroll\n  for (int q = 0; q < %d; ++q)\n    #pragma unroll\n    for (int l = 0; l < %d; ++l) acc[l] = acc[l] + comb[q][cx][l];\n", QS - 1, V);
+      e("  #pragma unroll\n  for (int q = 0; q < %d; ++q)\n    #pragma unroll\n    for (int l = 0; l < %d; ++l) acc[l] = %s;\n", QS - 1, V, AP("acc[l]", "comb[q][cx][l]").c_str());
       if (Sy == 1 && has_post) e("  post(acc%s%s);\n", gs.c_str(), pass.c_str());  // the sub-splits of one CTA covered all of T
       e("  float* d = dst + (%s)blockIdx.y * %lld + v * %d;\n", "long long", (long long)NOUT, V);
     }
@@ -1347,9 +1368,10 @@ void emit_reduce(Plan& plan, const Program& p, int n_args, const DeviceProps& de
       if (V == 4) {
         e("  cc_ldg4(part + v * 4, acc);\n  #pragma unroll 8\n  for (int s = 1; s < %lld; ++s) {\n    float x[4];\n    cc_ldg4(part + (long long)s * %lld + v * 4, x);\n", (long long)S,
           (long long)NOUT);
-        e("    #pragma unroll\n    for (int l = 0; l < 4; ++l) acc[l] = acc[l] + x[l];\n  }\n");
+        e("    #pragma unroll\n    for (int l = 0; l < 4; ++l) acc[l] = %s;\n  }\n", AP("acc[l]", "x[l]").c_str());
       } else {
-        e("  acc[0] = part[v];\n  #pragma unroll 8\n  for (int s = 1; s < %lld; ++s) acc[0] = acc[0] + part[(long long)s * %lld + v];\n", (long long)S, (long long)NOUT);
+        e("  acc[0] = part[v];\n  #pragma unroll 8\n  for (int s = 1; s < %lld; ++s) acc[0] = %s;\n", (long long)S,
+          AP("acc[0]", strprintf("part[(long long)s * %lld + v]", (long long)NOUT)).c_str());
       }
       if (has_post) {
         emit_decode(e, odims, no, IDX, strprintf("(%s)v * %d", IDX, V).c_str(), "  ");
@@ -1378,7 +1400,7 @@ void emit_reduce(Plan& plan, const Program& p, int n_args, const DeviceProps& de
     const int OPB = 256 / G;  // outputs per block
     e("// axis reduction (row owner): out dims=[");
     for (int x = 0; x < no; ++x) e("%s%lld", x ? "," : "", (long long)odims[x]);
-    e("] T=%s V=%d threads/output=%d idx=%s epilogue=%d\n", rd.c_str(), V, G, IDX, (int)has_post);
+    e("] T=%s V=%d threads/output=%d idx=%s epilogue=%d fold=%s\n", rd.c_str(), V, G, IDX, (int)has_post, kind_name(mono));
     e("__device__ __forceinline__ float ev(const %s t", IDX);
     for (int x = 0; x < no; ++x) e(", const %s g%d", IDX, x);
     e("%s) {\n", params.c_str());
@@ -1390,7 +1412,7 @@ void emit_reduce(Plan& plan, const Program& p, int n_args, const DeviceProps& de
     emit_op_list(e, p.ops, "    ", "l", p.results);
     e("    o[l] = _%d;\n  }\n", p.results[0]);
     if (V == 4)
-      e("  return (o[0] + o[1]) + (o[2] + o[3]);\n}\n");
+      e("  return %s;\n}\n", AP(AP("o[0]", "o[1]"), AP("o[2]", "o[3]")).c_str());
     else
       e("  return o[0];\n}\n");
     emit_post_fn(1, -1);
@@ -1399,12 +1421,15 @@ void emit_reduce(Plan& plan, const Program& p, int n_args, const DeviceProps& de
     e("  const %s oidx = (%s)blockIdx.x * %d + threadIdx.x / %d;\n", IDX, IDX, OPB, G);
     e("  const bool live = oidx < %lld;\n  const %s oc = live ? oidx : 0;\n", (long long)NOUT, IDX);
     emit_decode(e, odims, no, IDX, "oc", "  ");
-    e("  float acc = 0.f;\n  #pragma unroll 4\n  for (int tv = lane; tv < %lld; tv += %d) acc += ev((%s)tv * %d%s%s);\n", (long long)TV, G, IDX, V, gs.c_str(),
-      pass.c_str());
-    if (G == 32)
-      e("  acc = cc_warp_sum(acc);\n");
-    else
-      e("  acc = cc_block_sum_256(acc);\n");
+    e("  float acc = %s;\n  #pragma unroll 4\n  for (int tv = lane; tv < %lld; tv += %d) acc = %s;\n", ZERO, (long long)TV, G,
+      AP("acc", strprintf("ev((%s)tv * %d%s%s)", IDX, V, gs.c_str(), pass.c_str())).c_str());
+    if (mono == K_PLUS) {
+      e(G == 32 ? "  acc = cc_warp_sum(acc);\n" : "  acc = cc_block_sum_256(acc);\n");
+    } else if (G == 32) {
+      e("  acc = cc_warp_fold<%s>(acc);\n", MSTRUCT);
+    } else {
+      e("  __shared__ float red_[32];\n  acc = cc_block_fold<%s>(acc, red_);\n", MSTRUCT);
+    }
     if (has_post)
       e("  if (lane == 0 && live) {\n    float a1[1] = {acc};\n    post(a1%s%s);\n    out[oidx] = a1[0];\n  }\n}\n", gs.c_str(), pass.c_str());
     else
@@ -1768,14 +1793,15 @@ Plan make_plan(const Tree& t, const DeviceProps& dev) {
       if (found) {
         for (int64_t n : ch.levels) b.prog.dims.push_back(n);
         b.prog.n_red = (int)ch.levels.size();
+        b.prog.red_monoid = ch.monoid;
         b.prog.results.push_back(b.export_node(ch.terms[0]));
         b.begin_post(ch.top);
         b.prog.post_result = b.export_node(base);
         is_reduce = true;
         std::string lv;
         for (size_t j = 0; j < ch.levels.size(); ++j) lv += strprintf("%s%lld", j ? " x " : "", (long long)ch.levels[j]);
-        plan.note = strprintf("%sPlus chain of %zu congruent terms re-rolled into a reduction over %s%s", rolled_c ? "join re-rolled into an output dimension; " : "",
-                              ch.terms.size(), lv.c_str(), b.prog.trivial_post() ? "" : " with an elementwise epilogue");
+        plan.note = strprintf("%s%s chain of %zu congruent terms re-rolled into a reduction over %s%s", rolled_c ? "join re-rolled into an output dimension; " : "",
+                              kind_name(ch.monoid), ch.terms.size(), lv.c_str(), b.prog.trivial_post() ? "" : " with an elementwise epilogue");
       } else {
         b.prog.results.push_back(b.export_node(base));
         if (rolled_c) plan.note = "join re-rolled into an output dimension";
@@ -1864,6 +1890,7 @@ Plan make_plan(const Tree& t, const DeviceProps& dev) {
     if (changed) {
       np.results.push_back(remap[prog.results[0]]);
       np.n_red = prog.n_red;
+      np.red_monoid = prog.red_monoid;
       np.post_ops = prog.post_ops;
       np.post_result = prog.post_result;
       np.load_in_post.assign(np.loads.size(), 0);
@@ -1912,7 +1939,7 @@ Plan make_plan(const Tree& t, const DeviceProps& dev) {
     plan.kind = PLAN_AXIS_REDUCE;
     // contraction: sum_t A[i,t] * B[t,k] with A [M,K] and B [K,N] row-major
     const int nd = (int)prog.dims.size();
-    if (dev.contraction && nd == 3 && prog.n_red == 1 && prog.trivial_post() && prog.ops.size() == 3 && prog.loads.size() == 2 &&
+    if (dev.contraction && prog.red_monoid == K_PLUS && nd == 3 && prog.n_red == 1 && prog.trivial_post() && prog.ops.size() == 3 && prog.loads.size() == 2 &&
         prog.ops[prog.results[0]].kind == K_TIMES) {
       const Op& mul = prog.ops[prog.results[0]];
       if (prog.ops[mul.a].kind == K_EXTRACT && prog.ops[mul.b].kind == K_EXTRACT && mul.a != mul.b) {
@@ -1958,7 +1985,7 @@ Plan make_plan(const Tree& t, const DeviceProps& dev) {
         }
       }
     }
-    if (dev.contraction && try_general_contraction(plan, prog, n_args)) return plan;
+    if (dev.contraction && prog.red_monoid == K_PLUS && try_general_contraction(plan, prog, n_args)) return plan;
     emit_reduce(plan, prog, n_args, dev);
   } else {
     const int td = transpose_dim(prog);

@@ -89,6 +89,10 @@ struct cc_times { static __device__ __forceinline__ float zero() { return 1.f; }
 struct cc_min { static __device__ __forceinline__ float zero() { return __int_as_float(0x7f800000); } static __device__ __forceinline__ float ap(float a, float b) { return fminf(a, b); } };
 struct cc_max { static __device__ __forceinline__ float zero() { return __int_as_float(0xff800000); } static __device__ __forceinline__ float ap(float a, float b) { return fmaxf(a, b); } };
 
+// min / max as re-rolled chains fold them (`t.split(axis).reduce(Tensor.max)`): NaN is the neutral element of fminf / fmaxf
+struct cc_min_nan { static __device__ __forceinline__ float zero() { return __int_as_float(0x7fc00000); } static __device__ __forceinline__ float ap(float a, float b) { return fminf(a, b); } };
+struct cc_max_nan { static __device__ __forceinline__ float zero() { return __int_as_float(0x7fc00000); } static __device__ __forceinline__ float ap(float a, float b) { return fmaxf(a, b); } };
+
 template <class M>
 __device__ __forceinline__ float cc_warp_fold(float v) {
   v = M::ap(v, __shfl_xor_sync(0xffffffffu, v, 16));

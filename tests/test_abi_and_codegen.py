@@ -174,6 +174,35 @@ def matmul2(a, b):
     return axis_sum(product, 1)
 
 
+def test_min_max_times_chains_are_rerolled_like_plus_chains():
+    """MonoidPrograms is generic over append / zero (Tensors.scala:308-311): `t.split(axis).reduce(Tensor.max)` etc. are the same
+    idiom as the per-axis sum and must not become a 4096-term unrolled kernel"""
+    x = rnd([4096, 64])
+
+    def chain(parts, f):
+        acc = parts[0]
+        for p in parts[1:]:
+            acc = f(acc, p)
+        return acc
+
+    for f, name in ((T.max, "Max"), (T.min, "Min"), (lambda a, b: a * b, "Times")):
+        for axis, owner in ((0, "column owner"), (1, "row owner")):
+            k = chain(x.split(axis), f).compile()
+            assert k.info.kind == 1 and owner in k.source and f"fold={name}" in k.source, (name, axis)
+    # an epilogue around a max chain (the softmax numerator's shift) and a max chain that never becomes a contraction
+    m = chain(x.split(1), T.max)
+    k = (T.exp(m) - T.fill(1.0, [4096])).compile()
+    assert k.info.kind == 1 and "epilogue=1" in k.source and "fold=Max" in k.source
+    a, b = rnd([256, 512], 1), rnd([512, 256], 2)
+    prod = a.broadcast([256, 512, 256]) * b.reshape([1, 512, 256]).broadcast([256, 512, 256])
+    k = chain(prod.split(1), T.max).compile()  # max_t a[i,t] * b[t,k]: "tropical" product, generic reduction, not tcgen05
+    assert k.info.kind == 1 and "fold=Max" in k.source
+    # mixed operators do not form one chain
+    parts = x.split(1)
+    mixed = T.max(T.max(parts[0] + parts[1], parts[2]), parts[3])
+    assert mixed.compile().info.kind == 0
+
+
 def test_matmul_pattern_is_recognised_through_the_fusion_barrier():
     k = matmul2(rnd([64, 48], 1), rnd([48, 32], 2)).compile()
     info = k.info

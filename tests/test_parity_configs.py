@@ -299,6 +299,60 @@ def test_c3_axis_sums(cuda, shape, axis):
     assert np.abs(got_u - left_fold.astype(np.float64)).max() <= 2e-5 * np.abs(truth).max()
 
 
+def test_axis_folds_with_every_monoid(cuda):
+    """t.split(axis).reduce(max | min | *) (MonoidPrograms, T:308-311): min / max are order-independent -> bit-exact vs the
+    oracle's unrolled chain, NaN handling included; products within 1e-5"""
+    T = cuda.Tensor
+
+    def chain(parts, f):
+        acc = parts[0]
+        for p in parts[1:]:
+            acc = f(acc, p)
+        return acc
+
+    def data(T, shape):
+        return T.random(shape, seed=21) * T.fill(2.0, shape) - T.fill(1.0, shape)
+
+    for shape in ([64, 33], [9, 40, 12], [300, 8]):
+        for axis in range(len(shape)):
+            if shape[axis] < 8:
+                continue
+            for f in ("max", "min"):
+                def build(T):
+                    return chain(data(T, shape).split(axis), getattr(T, f))
+                got, want = build(T).flatArray(), build(ref.Tensor).flat_array()
+                assert build(T).compile().info.kind == 1
+                assert np.array_equal(bits(got), bits(want)), (shape, axis, f)
+
+            def prod(T):
+                x = data(T, shape) * T.fill(0.25, shape) + T.fill(1.0, shape)  # factors in [0.75, 1.25]
+                return chain(x.split(axis), lambda a, b: a * b)
+            got, want = prod(T).flatArray().astype(np.float64), prod(ref.Tensor).flat_array().astype(np.float64)
+            assert np.abs(got - want).max() <= 1e-5 * np.abs(want).max()
+    # NaN semantics of fmin / fmax (K:271-325 -> OpenCL fmin/fmax): NaNs are ignored unless every term is NaN
+    x = np.arange(24 * 16, dtype=np.float32).reshape(24, 16) % 7 - 3
+    x[3, :] = np.nan      # one whole reduction column of the axis-1 fold ...
+    x[:, 5] = np.nan      # ... and one of the axis-0 fold; scattered ones elsewhere
+    x[7, 2] = np.nan
+    for axis in (0, 1):
+        for f in ("max", "min"):
+            got = chain(T(x).split(axis), getattr(T, f)).flatArray()
+            want = chain(ref.Tensor(x).split(axis), getattr(ref.Tensor, f)).flat_array()
+            assert np.array_equal(np.isnan(got), np.isnan(want)) and np.array_equal(got[~np.isnan(got)], want[~np.isnan(want)]), (axis, f)
+            assert np.isnan(got).sum() == 1
+    # the softmax idiom, rows of 512: max-shift, exponentials, row sums, quotient -- three reductions / epilogues, no unrolled kernels
+    def softmax(T):
+        shape = [96, 512]
+        z = data(T, shape) * T.fill(8.0, shape)
+        m = chain(z.split(1), T.max)
+        e = T.exp(z - m.broadcast(shape))
+        s = chain(e.split(1), lambda a, b: a + b)
+        return e / s.broadcast(shape)
+    got = softmax(T).flatArray().astype(np.float64).reshape(96, 512)
+    want = softmax(ref.Tensor).flat_array().astype(np.float64).reshape(96, 512)
+    assert np.abs(got.sum(axis=1) - 1.0).max() < 1e-5 and np.abs(got - want).max() <= 1e-6
+
+
 # ---- C4: views ------------------------------------------------------------------------------------------------------------------
 
 
