@@ -43,7 +43,7 @@ class KernelInfo(C.Structure):
 
 class Stats(C.Structure):
     _fields_ = [(n, u64) for n in ("compiles", "cache_hits", "launches", "device_kernels", "h2d_bytes", "d2h_bytes", "alloc_calls",
-                                   "pool_hits", "bytes_in_use", "bytes_pooled")]
+                                   "pool_hits", "bytes_in_use", "bytes_pooled", "nvrtc_compiles", "disk_cache_hits")]
 
 
 def declared_symbols() -> list[str]:

@@ -377,6 +377,37 @@ std::vector<uint32_t> plus_chain(const Tree& t, uint32_t root) {
   return elems;
 }
 
+// every leaf, left to right, of the maximal tree of root's own operator: ((e0 op e1) op (e2 op e3)) -> [e0, e1, e2, e3]
+// (`parts.par.reduce(_ + _)`, reduceRight, hand-written pairwise sums). A node reached twice (a shared partial sum) is a leaf.
+std::vector<uint32_t> monoid_tree_leaves(const Tree& t, uint32_t root) {
+  std::vector<uint32_t> leaves;
+  const uint32_t kind = t.nodes[root].kind;
+  if (!is_monoid(kind)) return {root};
+  std::unordered_map<uint32_t, int> visits;
+  {
+    std::vector<uint32_t> st{root};
+    while (!st.empty()) {
+      uint32_t i = st.back();
+      st.pop_back();
+      if (++visits[i] > 1 || t.nodes[i].kind != kind) continue;
+      st.push_back(t.nodes[i].kids[0]);
+      st.push_back(t.nodes[i].kids[1]);
+    }
+  }
+  std::vector<uint32_t> st{root};
+  while (!st.empty()) {
+    uint32_t i = st.back();
+    st.pop_back();
+    if (t.nodes[i].kind == kind && (i == root || visits[i] == 1)) {
+      st.push_back(t.nodes[i].kids[1]);
+      st.push_back(t.nodes[i].kids[0]);
+    } else {
+      leaves.push_back(i);
+    }
+  }
+  return leaves;
+}
+
 constexpr size_t kMinRerollTerms = 8;  // shorter chains stay unrolled in one elementwise kernel, as the reference runs them
 
 // A re-rolled reduction found inside an expression: `top` is the root of a left-leaning Plus chain whose terms are all
@@ -473,7 +504,7 @@ bool nested_reroll(const Tree& t, Chain& ch) {
 // Finds the longest re-rollable Plus chain inside the float term `root` (searching through unary / binary nodes only).
 bool find_chain(const Tree& t, uint32_t root, Chain& best) {
   std::vector<uint32_t> tops;
-  std::unordered_map<uint32_t, char> seen;
+  std::unordered_map<uint32_t, char> seen, inner;
   std::vector<uint32_t> stack{root};
   while (!stack.empty()) {
     uint32_t i = stack.back();
@@ -483,8 +514,12 @@ bool find_chain(const Tree& t, uint32_t root, Chain& best) {
     const Node& nd = t.nodes[i];
     if (is_monoid(nd.kind)) {
       std::vector<uint32_t> terms = plus_chain(t, i);
-      if (terms.size() >= kMinRerollTerms) tops.push_back(i);
-      for (uint32_t term : terms) stack.push_back(term);  // the chain's own Plus nodes are not candidates
+      // candidates: long left folds, and the ROOTS of other same-operator trees (their inner nodes are not candidates of their own)
+      if (terms.size() >= kMinRerollTerms || (!inner.count(i) && terms.size() >= 2 && t.nodes[terms.back()].kind == nd.kind)) tops.push_back(i);
+      for (uint32_t term : terms) {
+        if (t.nodes[term].kind == nd.kind) inner[term] = 1;
+        stack.push_back(term);  // the chain's own Plus nodes are not candidates
+      }
     } else if (is_unary(nd.kind) || is_binary(nd.kind)) {
       for (uint32_t k : nd.kids) stack.push_back(k);
     }
@@ -495,8 +530,8 @@ bool find_chain(const Tree& t, uint32_t root, Chain& best) {
     c.top = top;
     c.monoid = t.nodes[top].kind;
     c.terms = plus_chain(t, top);
-    if (c.terms.size() <= best_len) continue;
-    if (!nested_reroll(t, c)) {
+    if (c.terms.size() <= best_len && t.nodes[c.terms.back()].kind != c.monoid) continue;
+    if (c.terms.size() < kMinRerollTerms || !nested_reroll(t, c)) {
       // `chain + other` parses as one longer left-leaning chain: keep the leading terms that are congruent to the first one
       // (their Plus node sits further down the left spine); the rest becomes part of the epilogue
       size_t m = 1;
@@ -504,14 +539,29 @@ bool find_chain(const Tree& t, uint32_t root, Chain& best) {
         StepMap d;
         if (!congruent(t, c.terms[0], c.terms[m], d)) break;
       }
-      if (m == c.terms.size() || m < kMinRerollTerms || m <= best_len) continue;
-      uint32_t spine = top;
-      for (size_t k = c.terms.size(); k > m; --k) spine = t.nodes[spine].kids[0];
-      c.top = spine;
-      c.terms.resize(m);
-      c.levels.clear();
-      c.steps.clear();
-      if (!nested_reroll(t, c)) continue;
+      bool ok = false;
+      if (m != c.terms.size() && m >= kMinRerollTerms && m > best_len) {
+        Chain part = c;
+        uint32_t spine = top;
+        for (size_t k = c.terms.size(); k > m; --k) spine = t.nodes[spine].kids[0];
+        part.top = spine;
+        part.terms.resize(m);
+        part.levels.clear();
+        part.steps.clear();
+        if (nested_reroll(t, part)) {
+          c = std::move(part);
+          ok = true;
+        }
+      }
+      if (!ok) {
+        // not a left fold: any tree of the same operator (pairwise / parallel reduce, reduceRight) folds its leaves left to right
+        Chain tree;
+        tree.top = top;
+        tree.monoid = c.monoid;
+        tree.terms = monoid_tree_leaves(t, top);
+        if (tree.terms.size() < kMinRerollTerms || tree.terms.size() <= best_len || !nested_reroll(t, tree)) continue;
+        c = std::move(tree);
+      }
     }
     best_len = c.terms.size();
     best = std::move(c);

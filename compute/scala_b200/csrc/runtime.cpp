@@ -5,6 +5,9 @@
 #include <nccl.h>
 #include <nvrtc.h>
 
+#include <sys/stat.h>
+#include <unistd.h>
+
 #include <algorithm>
 #include <atomic>
 #include <cstdlib>
@@ -394,8 +397,72 @@ void release(Buffer* b) {
 
 // ---- NVRTC ----------------------------------------------------------------------------------------------------------------
 
+// ---- on-disk cubin cache (opt-in) ------------------------------------------------------------------------------------------
+// The reference's kernel cache lives and dies with the process (Guava cache, Tensors.scala:1267-1289): every run pays the JIT
+// again (30-130 ms per expression structure here). With CC_KERNEL_CACHE_DIR / cc_kernel_disk_cache set, the cubin of each
+// generated source is kept under <dir>/<fnv1a-64 of source + compiler identity>.cubin and NVRTC is skipped on a hit.
+std::string& disk_cache_dir() {
+  static std::string dir = [] {
+    const char* e = getenv("CC_KERNEL_CACHE_DIR");
+    std::string d = e ? e : "";
+    if (!d.empty()) mkdir(d.c_str(), 0777);  // best effort; an unusable directory only means no hits
+    return d;
+  }();
+  return dir;
+}
+uint64_t fnv1a(const std::string& s, uint64_t h = 1469598103934665603ull) {
+  for (unsigned char c : s) {
+    h ^= c;
+    h *= 1099511628211ull;
+  }
+  return h;
+}
+std::string disk_cache_path(const std::string& full_source) {
+  int major = 0, minor = 0;
+  nvrtcVersion(&major, &minor);
+  const std::string identity = strprintf("nvrtc %d.%d sm_100a fmad lineinfo extra-device-vectorization|%s|", major, minor, cc_version());
+  return strprintf("%s/%016llx.cubin", disk_cache_dir().c_str(), (unsigned long long)fnv1a(full_source, fnv1a(identity)));
+}
+bool disk_cache_load(const std::string& path, const std::string& full_source, std::vector<char>& cubin) {
+  FILE* f = fopen(path.c_str(), "rb");
+  if (!f) return false;
+  // layout: u64 source length, u64 source hash (guards against a path collision), cubin bytes
+  uint64_t hdr[2] = {0, 0};
+  bool ok = fread(hdr, 8, 2, f) == 2 && hdr[0] == full_source.size() && hdr[1] == fnv1a(full_source, 0x9e3779b97f4a7c15ull);
+  if (ok) {
+    fseek(f, 0, SEEK_END);
+    long end = ftell(f);
+    ok = end > 16;
+    if (ok) {
+      cubin.resize((size_t)end - 16);
+      fseek(f, 16, SEEK_SET);
+      ok = fread(cubin.data(), 1, cubin.size(), f) == cubin.size();
+    }
+  }
+  fclose(f);
+  if (!ok) cubin.clear();
+  return ok;
+}
+void disk_cache_store(const std::string& path, const std::string& full_source, const std::vector<char>& cubin) {
+  const std::string tmp = path + strprintf(".tmp%d", (int)getpid());  // write + rename: concurrent processes never see half a file
+  FILE* f = fopen(tmp.c_str(), "wb");
+  if (!f) return;  // an unwritable cache directory costs a recompile next time, nothing else
+  uint64_t hdr[2] = {full_source.size(), fnv1a(full_source, 0x9e3779b97f4a7c15ull)};
+  bool ok = fwrite(hdr, 8, 2, f) == 2 && fwrite(cubin.data(), 1, cubin.size(), f) == cubin.size();
+  ok = (fclose(f) == 0) && ok;
+  if (!ok || rename(tmp.c_str(), path.c_str()) != 0) remove(tmp.c_str());
+}
+
 void nvrtc_compile(Kernel& k) {
   k.full_source = std::string("// ") + k.plan.note + "\n" + kJitTemplates + "\n" + k.plan.source;
+  std::string cache_path;
+  if (!disk_cache_dir().empty()) {
+    cache_path = disk_cache_path(k.full_source);
+    if (disk_cache_load(cache_path, k.full_source, k.cubin)) {
+      rt().stats.disk_cache_hits++;
+      return;
+    }
+  }
   nvrtcProgram prog;
   nvrtcResult r = nvrtcCreateProgram(&prog, k.full_source.c_str(), "jit_kernel.cu", 0, nullptr, nullptr);
   CC_REQUIRE(r == NVRTC_SUCCESS, CC_ERR_COMPILE, "nvrtcCreateProgram: %s", nvrtcGetErrorString(r));
@@ -415,6 +482,8 @@ void nvrtc_compile(Kernel& k) {
   k.cubin.resize(n);
   nvrtcGetCUBIN(prog, k.cubin.data());
   nvrtcDestroyProgram(&prog);
+  rt().stats.nvrtc_compiles++;
+  if (!cache_path.empty()) disk_cache_store(cache_path, k.full_source, k.cubin);
 }
 
 void ensure_loaded(Kernel& k) {
@@ -963,6 +1032,20 @@ int cc_compile_ex(const void* blob, uint64_t n_bytes, cc_kernel* out, uint64_t* 
     r.cache.emplace(std::move(t.key), raw);
     evict_kernels();
     *out = (cc_kernel)(uintptr_t)raw;
+  });
+}
+
+int cc_kernel_disk_cache(const char* directory) {
+  return guarded([&] {
+    Lock lock;
+    disk_cache_dir() = directory ? directory : "";
+    while (disk_cache_dir().size() > 1 && disk_cache_dir().back() == '/') disk_cache_dir().pop_back();
+    if (!disk_cache_dir().empty()) {
+      struct stat st;
+      if (stat(disk_cache_dir().c_str(), &st) != 0) mkdir(disk_cache_dir().c_str(), 0777);
+      CC_REQUIRE(stat(disk_cache_dir().c_str(), &st) == 0 && S_ISDIR(st.st_mode), CC_ERR_ILLEGAL_ARGUMENT, "kernel cache directory %s does not exist and cannot be created",
+                 disk_cache_dir().c_str());
+    }
   });
 }
 

@@ -57,6 +57,7 @@ def _L():
         L.ct_live_tensors.argtypes = [C.POINTER(C.c_int64)]
         L.cc_profile_enable.argtypes = [C.c_int]
         L.cc_profile_report.argtypes = [C.c_char_p, u64, hp]
+        L.cc_kernel_disk_cache.argtypes = [C.c_char_p]
         L.cc_init.argtypes = [C.c_int]
         L.cc_set_stream_count.argtypes = [C.c_int]
         L.cc_device_info.argtypes = [C.POINTER(_lib.DeviceInfo)]
@@ -351,6 +352,11 @@ def matmul_3xtf32_allgather(a: "Buffer", b: "Buffer", gathered: "Buffer", m_shar
 def kernel_cache_limit(max_kernels: int) -> None:
     """0 = unbounded (reference default); otherwise LRU eviction (kernelCacheBuilder.maximumSize, Tensors.scala:1267-1277)"""
     check(_L().cc_kernel_cache_limit(int(max_kernels)))
+
+
+def kernel_disk_cache(directory: str | None) -> None:
+    """opt-in on-disk cubin cache (None / "" = off): a later process skips NVRTC for every structure it has seen before"""
+    check(_L().cc_kernel_disk_cache(directory.encode() if directory else None))
 
 
 def kernel_cache_clear() -> None:

@@ -151,6 +151,11 @@ int cc_compile_ex(const void* tree_blob, uint64_t n_bytes, cc_kernel* out, uint6
                   int* n_params_out);
 /* kernelCache policy (T:1267-1289): the reference's cache is an overridable Guava CacheBuilder, unbounded by default. A non-zero
  * limit evicts least-recently-used kernels (their modules unload once no caller holds them); clear = clearCache (T:1282-1285). */
+/* Opt-in on-disk cubin cache (also: environment variable CC_KERNEL_CACHE_DIR). The reference's kernel cache dies
+ * with the process (T:1267-1289) so every run pays the JIT again; with a directory set, the cubin of each generated source is kept
+ * under <dir>/<hash of source + compiler identity>.cubin (written atomically, verified against the source on load) and NVRTC is
+ * skipped on a hit. NULL or "" turns it off. */
+int cc_kernel_disk_cache(const char* directory);
 int cc_kernel_cache_limit(uint64_t max_kernels);
 int cc_kernel_cache_clear(void);
 int cc_kernel_cache_size(uint64_t* out);
@@ -202,6 +207,7 @@ int cc_set_operand_cache(int on);
 typedef struct cc_stats_t {
   uint64_t compiles, cache_hits, launches, device_kernels, h2d_bytes, d2h_bytes, alloc_calls, pool_hits,
       bytes_in_use, bytes_pooled;
+  uint64_t nvrtc_compiles, disk_cache_hits; /* of `compiles` (structures planned): how many ran NVRTC / came from the disk cache */
 } cc_stats_t;
 int cc_stats(cc_stats_t* out);
 int cc_stats_reset(void);

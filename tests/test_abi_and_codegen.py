@@ -197,6 +197,28 @@ def test_min_max_times_chains_are_rerolled_like_plus_chains():
     prod = a.broadcast([256, 512, 256]) * b.reshape([1, 512, 256]).broadcast([256, 512, 256])
     k = chain(prod.split(1), T.max).compile()  # max_t a[i,t] * b[t,k]: "tropical" product, generic reduction, not tcgen05
     assert k.info.kind == 1 and "fold=Max" in k.source
+    # any tree of one operator folds its leaves left to right: pairwise (parallel-collection) reduce, reduceRight
+    def pairwise(parts, f):
+        while len(parts) > 1:
+            parts = [f(parts[i], parts[i + 1]) if i + 1 < len(parts) else parts[i] for i in range(0, len(parts), 2)]
+        return parts[0]
+
+    def right(parts, f):
+        acc = parts[-1]
+        for q in reversed(parts[:-1]):
+            acc = f(q, acc)
+        return acc
+
+    import time
+
+    t0 = time.perf_counter()
+    for red in (pairwise, right):
+        for f, name in ((lambda a, b: a + b, "Plus"), (T.min, "Min")):
+            k = red(x.split(0), f).compile()  # 4096 leaves
+            assert k.info.kind == 1 and f"fold={name}" in k.source and "T=4096" in k.source
+    assert time.perf_counter() - t0 < 20.0  # linear, not quadratic, in the number of leaves
+    shared = x.split(0)[0] + x.split(0)[1]
+    assert pairwise([shared, shared] + x.split(0)[2:12], lambda a, b: a + b).compile().info.kind == 0  # a shared partial sum is a leaf: no step
     # mixed operators do not form one chain
     parts = x.split(1)
     mixed = T.max(T.max(parts[0] + parts[1], parts[2]), parts[3])
@@ -385,6 +407,61 @@ def test_iterated_maps_become_counted_loops():
     x = rnd([64, 256])
     k = axis_sum(T.tanh(T.tanh(T.tanh(T.tanh(T.tanh(T.tanh(T.tanh(T.tanh(x)))))))).nonInline(), 0).compile()
     assert k.info.kind == 1
+
+
+def test_on_disk_cubin_cache(tmp_path):
+    """opt-in: the cubin of a generated source survives the process; a hit skips NVRTC; a corrupt entry is recompiled"""
+    import os
+    import subprocess
+    import sys
+
+    d = str(tmp_path / "cubins")
+    cuda.kernel_disk_cache(d)
+    try:
+        cuda.kernel_cache_clear()
+        s0 = cuda.stats()
+        k = (T.fill(1234.5, [8, 8]) * rnd([8, 8]) + rnd([8, 8], 2)).compile()
+        s1 = cuda.stats()
+        assert s1["nvrtc_compiles"] == s0["nvrtc_compiles"] + 1 and s1["disk_cache_hits"] == s0["disk_cache_hits"]
+        files = [f for f in os.listdir(d) if f.endswith(".cubin")]
+        assert len(files) == 1 and os.path.getsize(os.path.join(d, files[0])) > 1000
+        # same process, in-memory cache dropped: served from disk, no NVRTC
+        cuda.kernel_cache_clear()
+        k2 = (T.fill(1234.5, [8, 8]) * rnd([8, 8]) + rnd([8, 8], 2)).compile()
+        s2 = cuda.stats()
+        assert s2["nvrtc_compiles"] == s1["nvrtc_compiles"] and s2["disk_cache_hits"] == s1["disk_cache_hits"] + 1
+        assert k2.source == k.source
+        # another process finds it through the environment variable
+        code = (
+            "from compute.scala_b200 import cuda; T = cuda.Tensor\n"
+            "k = (T.fill(1234.5, [8, 8]) * T.random([8, 8], seed=1) + T.random([8, 8], seed=2)).compile()\n"
+            "s = cuda.stats(); print(s['nvrtc_compiles'], s['disk_cache_hits'])"
+        )
+        root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+        # (the key includes the NVRTC version: a process that imported torch first resolves torch's bundled libnvrtc, a fresh one the
+        # system's, so the first fresh process may compile once more; the second one must not)
+        for attempt in range(2):
+            r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=root, env=dict(os.environ, CC_KERNEL_CACHE_DIR=d))
+            assert r.returncode == 0, r.stderr[-500:]
+        assert r.stdout.split() == ["0", "1"], (r.stdout, r.stderr[-500:])
+        files = sorted(os.listdir(d), key=lambda f: os.path.getmtime(os.path.join(d, f)))[:1]  # the entry this process wrote
+        # a damaged entry is ignored and rewritten
+        path = os.path.join(d, files[0])
+        with open(path, "r+b") as f:
+            f.seek(8)
+            f.write(b"\x00" * 8)
+        cuda.kernel_cache_clear()
+        (T.fill(1234.5, [8, 8]) * rnd([8, 8]) + rnd([8, 8], 2)).compile()
+        s3 = cuda.stats()
+        assert s3["nvrtc_compiles"] == s2["nvrtc_compiles"] + 1
+        with open(path, "rb") as f:
+            assert f.read(16)[8:] != b"\x00" * 8
+    finally:
+        cuda.kernel_disk_cache(None)
+        cuda.kernel_cache_clear()
+    before = cuda.stats()["disk_cache_hits"]
+    (T.fill(1234.5, [8, 8]) * rnd([8, 8]) + rnd([8, 8], 2)).compile()
+    assert cuda.stats()["disk_cache_hits"] == before  # off again
 
 
 def test_kernel_cache_policy():

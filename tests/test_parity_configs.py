@@ -329,6 +329,24 @@ def test_axis_folds_with_every_monoid(cuda):
                 return chain(x.split(axis), lambda a, b: a * b)
             got, want = prod(T).flatArray().astype(np.float64), prod(ref.Tensor).flat_array().astype(np.float64)
             assert np.abs(got - want).max() <= 1e-5 * np.abs(want).max()
+    # other shapes of the same fold: pairwise (parallel reduce) and right fold, exact data so that the order cannot matter
+    def pairwise(parts, f):
+        while len(parts) > 1:
+            parts = [f(parts[i], parts[i + 1]) if i + 1 < len(parts) else parts[i] for i in range(0, len(parts), 2)]
+        return parts[0]
+
+    def right(parts, f):
+        acc = parts[-1]
+        for q in reversed(parts[:-1]):
+            acc = f(q, acc)
+        return acc
+
+    for red in (pairwise, right):
+        for axis in (0, 1):
+            def build(T):
+                return T.fill(0.5, [37 if axis == 0 else 50]) * red(dataset_e(T, [50, 37]).split(axis), lambda a, b: a + b)
+            got, want = build(T).flatArray(), build(ref.Tensor).flat_array()
+            assert build(T).compile().info.kind == 1 and np.array_equal(bits(got), bits(want)), (red.__name__, axis)
     # NaN semantics of fmin / fmax (K:271-325 -> OpenCL fmin/fmax): NaNs are ignored unless every term is NaN
     x = np.arange(24 * 16, dtype=np.float32).reshape(24, 16) % 7 - 3
     x[3, :] = np.nan      # one whole reduction column of the axis-1 fold ...
