@@ -5,6 +5,7 @@
 #include <nccl.h>
 #include <nvrtc.h>
 
+#include <nvtx3/nvToolsExt.h>
 #include <sys/stat.h>
 #include <unistd.h>
 
@@ -143,6 +144,7 @@ struct Runtime {
     uint64_t bytes, flops;
   };
   bool profiling = false;
+  bool nvtx = false;  // CC_NVTX=1: every command is an NVTX range named like the profiler's rows (ncu --nvtx --nvtx-include ...)
   std::vector<ProfRecord> prof_records;
   std::vector<CUevent> prof_event_pool;
   // B^T hi / lo panels of recent contractions, kept while the B buffer is unchanged (same uid and write version)
@@ -273,6 +275,7 @@ void op_begin(Op& op, const cc_event* waits, int n_waits) {
     need(op.stream, b->last_write);                       // write after write
     for (const Mark& m : b->reads) need(op.stream, m);    // write after read (also covers pooled-memory reuse)
   }
+  if (rt().nvtx) nvtxRangePushA(op.label.c_str());
   if (rt().profiling) {  // after the waits: the interval measures the command, not its dependencies
     op.prof_start = prof_event();
     CC_CU(cuEventRecord(op.prof_start, op.cu()));
@@ -281,6 +284,7 @@ void op_begin(Op& op, const cc_event* waits, int n_waits) {
 
 void op_end(Op& op, cc_event* out_event) {
   Runtime& r = rt();
+  if (r.nvtx) nvtxRangePop();
   if (op.prof_start) {
     CUevent stop = prof_event();
     CC_CU(cuEventRecord(stop, op.cu()));
@@ -580,6 +584,7 @@ int cc_init(int device_ordinal) {
     int count = 0;
     CC_CU(cuDeviceGetCount(&count));
     CC_REQUIRE(count > 0, CC_ERR_NO_DRIVER, "no CUDA device visible — this backend has no CPU fallback");
+    if (const char* nv = getenv("CC_NVTX")) r.nvtx = atoi(nv) != 0;
     if (device_ordinal < 0) {
       const char* lr = getenv("LOCAL_RANK");
       device_ordinal = lr ? atoi(lr) % count : 0;
@@ -1206,7 +1211,7 @@ const char* plan_kind_name(int kind) {
 }
 // "<plan> #<structure hash>: <the generator's one-line description>"
 void label_kernel_op(Op& op, const Kernel& k) {
-  if (!rt().profiling) return;
+  if (!rt().profiling && !rt().nvtx) return;
   std::string first = k.plan.source.substr(0, k.plan.source.find('\n'));
   if (first.rfind("// ", 0) == 0) first = first.substr(3);
   if (first.size() > 150) first.resize(150);

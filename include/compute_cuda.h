@@ -217,6 +217,8 @@ int cc_stats_reset(void);
  * count, total / avg / min / max device time, the algorithmic bytes and flops the code generator attributes to one launch
  * and the resulting GB/s, TFLOP/s. Call with out = NULL to size (*out_needed), then with a buffer; the records are
  * consumed by the report. */
+/* (With CC_NVTX=1 in the environment every command is also an NVTX range of the same name, so that an external profiler can
+ * select one expression's kernels: ncu --nvtx --nvtx-include "elementwise #1a2b3c4d/" ...) */
 int cc_profile_enable(int on);
 int cc_profile_report(char* out, uint64_t capacity, uint64_t* out_needed);
 /* device-side stopwatch: joins every pool stream, records a timing event; stop returns elapsed milliseconds */
