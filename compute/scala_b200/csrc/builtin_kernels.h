@@ -26,7 +26,7 @@ constexpr int kPeerCapFloats = 65536;  // largest vector the mailbox carries (th
 constexpr int kPeerChunk = 1024;       // floats per block
 constexpr int kPeerMaxBlocks = kPeerCapFloats / kPeerChunk;
 struct PeerMailboxes {
-  float* data[kPeerMaxRanks];      // data[r]: rank r's mailbox payload [2][world][kPeerCapFloats]
+  float* data[kPeerMaxRanks];      // data[r]: rank r's mailbox payload: LL slots {float value, u32 epoch} [2][world][kPeerCapFloats]
   unsigned* flags[kPeerMaxRanks];  // flags[r]: rank r's mailbox flags  [2][world][kPeerMaxBlocks]
   int world;
   int rank;

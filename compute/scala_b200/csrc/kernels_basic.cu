@@ -56,6 +56,34 @@ __device__ __forceinline__ void wait_flag(const unsigned* p, unsigned epoch) {
   while (ld_acquire_sys(p) != epoch)
     if (++spins > (1u << 27)) __trap();  // a peer that never shows up must abort this launch, not hang the GPU
 }
+// LL slots (the "low latency" protocol NCCL uses for small messages): every float travels as an 8-byte {value, epoch} pair, so the
+// payload carries its own ready flag -- no fence, no separate flag store, no extra NVLink round trip between data and flag. Two
+// slots are written / polled per 16-byte access; each 8-byte half is a single transaction, so a half is either old or new.
+__device__ __forceinline__ void ll_store2(uint2* p, float v0, float v1, unsigned e) {
+  asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(__float_as_uint(v0)), "r"(e), "r"(__float_as_uint(v1)), "r"(e) : "memory");
+}
+__device__ __forceinline__ void ll_store1(uint2* p, float v, unsigned e) {
+  asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(__float_as_uint(v)), "r"(e) : "memory");
+}
+__device__ __forceinline__ void ll_load2(const uint2* p, unsigned e, float& v0, float& v1) {
+  unsigned a, b, c, d, spins = 0;
+  do {
+    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "l"(p) : "memory");
+    if (++spins > (1u << 27)) __trap();  // a peer that never shows up must abort this launch, not hang the GPU
+  } while (b != e || d != e);
+  v0 = __uint_as_float(a);
+  v1 = __uint_as_float(c);
+}
+__device__ __forceinline__ float ll_load1(const uint2* p, unsigned e) {
+  unsigned a, b, spins = 0;
+  do {
+    asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(a), "=r"(b) : "l"(p) : "memory");
+    if (++spins > (1u << 27)) __trap();
+  } while (b != e);
+  return __uint_as_float(a);
+}
+__device__ __forceinline__ uint2* mb_slots(const PeerMailboxes& mb, int rank) { return reinterpret_cast<uint2*>(mb.data[rank]); }
+
 __device__ __forceinline__ size_t mb_data_index(int parity, int world, int src_rank, size_t i) {
   return ((size_t)parity * world + src_rank) * kPeerCapFloats + i;
 }
@@ -114,73 +142,63 @@ __global__ void __launch_bounds__(kReduceThreads) reduce_sum_kernel(const float*
     }
     return;
   }
-  // fused all-reduce: push this GPU's total into slot [rank] of every peer's mailbox over NVLink, raise the epoch flag, wait
-  // for every peer's flag in our own mailbox, then add the totals in rank order (same order, same bits on every rank)
+  // fused all-reduce: push this GPU's total as an LL slot {value, epoch} into slot [rank] of every peer's mailbox over NVLink, then
+  // poll our own mailbox for every rank's slot and add the totals in rank order (same order, same bits on every rank)
   const int parity = (int)(epoch & 1u);
   if (threadIdx.x == 0) smem[0] = p;
   __syncthreads();
-  if ((int)threadIdx.x < mb.world) {
-    const int peer = threadIdx.x;
-    mb.data[peer][mb_data_index(parity, mb.world, mb.rank, 0)] = smem[0];
-    __threadfence_system();
-    st_release_sys(mb.flags[peer] + mb_flag_index(parity, mb.world, mb.rank, 0), epoch);
-    wait_flag(mb.flags[mb.rank] + mb_flag_index(parity, mb.world, peer, 0), epoch);
-  }
-  __syncthreads();
+  if ((int)threadIdx.x < mb.world) ll_store1(mb_slots(mb, threadIdx.x) + mb_data_index(parity, mb.world, mb.rank, 0), smem[0], epoch);
   if (threadIdx.x == 0) {
     float total = 0.f;
-    for (int r = 0; r < mb.world; ++r) total += __ldcv(mb.data[mb.rank] + mb_data_index(parity, mb.world, r, 0));
+    for (int r = 0; r < mb.world; ++r) total += ll_load1(mb_slots(mb, mb.rank) + mb_data_index(parity, mb.world, r, 0), epoch);
     out[0] = total;
     *counter = 0u;
   }
 }
 
-// one-shot in-place all-reduce of a vector: block b owns floats [b*1024, (b+1)*1024)
+// one-shot in-place all-reduce of a vector: block b owns floats [b*1024, (b+1)*1024); every thread pushes its 4 floats as LL slots
+// into every peer's mailbox and polls the same 4 slots of every rank in its own -- threads never synchronise with each other
 __global__ void __launch_bounds__(256) peer_allreduce_kernel(float* __restrict__ v, uint64_t n, PeerMailboxes mb, unsigned epoch) {
   const int parity = (int)(epoch & 1u);
-  const int b = blockIdx.x;
-  const size_t i = (size_t)b * kPeerChunk + (size_t)threadIdx.x * 4;
-  float4 mine = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (i + 3 < n) {
-    mine = *reinterpret_cast<const float4*>(v + i);
+  const size_t i = (size_t)blockIdx.x * kPeerChunk + (size_t)threadIdx.x * 4;
+  if (i >= n) return;
+  const bool vec = i + 3 < n;
+  float t[4] = {0.f, 0.f, 0.f, 0.f};
+  if (vec) {
+    const float4 x = *reinterpret_cast<const float4*>(v + i);
+    t[0] = x.x, t[1] = x.y, t[2] = x.z, t[3] = x.w;
   } else {
-    float t[4] = {0.f, 0.f, 0.f, 0.f};
     for (int j = 0; j < 4; ++j)
       if (i + j < n) t[j] = v[i + j];
-    mine = make_float4(t[0], t[1], t[2], t[3]);
   }
-  for (int peer = 0; peer < mb.world; ++peer)
-    *reinterpret_cast<float4*>(mb.data[peer] + mb_data_index(parity, mb.world, mb.rank, i)) = mine;  // NVLink store (local for peer == rank)
-  __threadfence_system();
-  __syncthreads();
-  if ((int)threadIdx.x < mb.world) {
-    const int peer = threadIdx.x;
-    st_release_sys(mb.flags[peer] + mb_flag_index(parity, mb.world, mb.rank, b), epoch);
-    wait_flag(mb.flags[mb.rank] + mb_flag_index(parity, mb.world, peer, b), epoch);
+  for (int peer = 0; peer < mb.world; ++peer) {  // NVLink stores (local for peer == rank)
+    uint2* dst = mb_slots(mb, peer) + mb_data_index(parity, mb.world, mb.rank, i);
+    ll_store2(dst, t[0], t[1], epoch);
+    ll_store2(dst + 2, t[2], t[3], epoch);
   }
-  __syncthreads();
-  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
   for (int r = 0; r < mb.world; ++r) {
-    const float4 x = __ldcv(reinterpret_cast<const float4*>(mb.data[mb.rank] + mb_data_index(parity, mb.world, r, i)));
-    acc.x += x.x; acc.y += x.y; acc.z += x.z; acc.w += x.w;
+    const uint2* src = mb_slots(mb, mb.rank) + mb_data_index(parity, mb.world, r, i);
+    float x0, x1, x2, x3;
+    ll_load2(src, epoch, x0, x1);
+    ll_load2(src + 2, epoch, x2, x3);
+    acc[0] += x0, acc[1] += x1, acc[2] += x2, acc[3] += x3;
   }
-  if (i + 3 < n) {
-    *reinterpret_cast<float4*>(v + i) = acc;
+  if (vec) {
+    *reinterpret_cast<float4*>(v + i) = make_float4(acc[0], acc[1], acc[2], acc[3]);
   } else {
-    const float t[4] = {acc.x, acc.y, acc.z, acc.w};
     for (int j = 0; j < 4; ++j)
-      if (i + j < n) v[i + j] = t[j];
+      if (i + j < n) v[i + j] = acc[j];
   }
 }
 
-// one-shot all-gather: recv[r * n .. (r + 1) * n) = rank r's send[0 .. n). Same exchange as the all-reduce above (block b pushes its
-// 1024 floats into slot [rank] of every peer's mailbox over NVLink, raises the epoch flags, waits for the peers' flags in its own
-// mailbox) with the rank-ordered sum replaced by a copy of every slot into place.
+// one-shot all-gather: recv[r * n .. (r + 1) * n) = rank r's send[0 .. n). Same LL exchange as the all-reduce above with the
+// rank-ordered sum replaced by a copy of every rank's slots into place.
 __global__ void __launch_bounds__(256) peer_allgather_kernel(const float* __restrict__ send, float* __restrict__ recv, uint64_t n, PeerMailboxes mb,
                                                              unsigned epoch) {
   const int parity = (int)(epoch & 1u);
-  const int b = blockIdx.x;
-  const size_t i = (size_t)b * kPeerChunk + (size_t)threadIdx.x * 4;
+  const size_t i = (size_t)blockIdx.x * kPeerChunk + (size_t)threadIdx.x * 4;
+  if (i >= n) return;
   const bool vec = (n & 3u) == 0 && i + 3 < n;  // n % 4 == 0 keeps every rank's slice of recv 16-byte aligned
   float t[4] = {0.f, 0.f, 0.f, 0.f};
   if (vec) {
@@ -190,25 +208,20 @@ __global__ void __launch_bounds__(256) peer_allgather_kernel(const float* __rest
     for (int j = 0; j < 4; ++j)
       if (i + j < n) t[j] = send[i + j];
   }
-  if (i < n)
-    for (int peer = 0; peer < mb.world; ++peer)
-      *reinterpret_cast<float4*>(mb.data[peer] + mb_data_index(parity, mb.world, mb.rank, i)) = make_float4(t[0], t[1], t[2], t[3]);
-  __threadfence_system();
-  __syncthreads();
-  if ((int)threadIdx.x < mb.world) {
-    const int peer = threadIdx.x;
-    st_release_sys(mb.flags[peer] + mb_flag_index(parity, mb.world, mb.rank, b), epoch);
-    wait_flag(mb.flags[mb.rank] + mb_flag_index(parity, mb.world, peer, b), epoch);
+  for (int peer = 0; peer < mb.world; ++peer) {
+    uint2* dst = mb_slots(mb, peer) + mb_data_index(parity, mb.world, mb.rank, i);
+    ll_store2(dst, t[0], t[1], epoch);
+    ll_store2(dst + 2, t[2], t[3], epoch);
   }
-  __syncthreads();
-  if (i >= n) return;
   for (int r = 0; r < mb.world; ++r) {
-    const float4 x = __ldcv(reinterpret_cast<const float4*>(mb.data[mb.rank] + mb_data_index(parity, mb.world, r, i)));
+    const uint2* src = mb_slots(mb, mb.rank) + mb_data_index(parity, mb.world, r, i);
+    float y[4];
+    ll_load2(src, epoch, y[0], y[1]);
+    ll_load2(src + 2, epoch, y[2], y[3]);
     float* dst = recv + (size_t)r * n + i;
     if (vec) {
-      *reinterpret_cast<float4*>(dst) = x;
+      *reinterpret_cast<float4*>(dst) = make_float4(y[0], y[1], y[2], y[3]);
     } else {
-      const float y[4] = {x.x, x.y, x.z, x.w};
       for (int j = 0; j < 4; ++j)
         if (i + j < n) dst[j] = y[j];
     }
@@ -302,7 +315,7 @@ void launch_reduce_sum(const float* in, uint64_t n, float* out, float* scratch, 
   check_launch("reduce_sum");
 }
 
-size_t peer_mailbox_flag_offset(int world) { return (size_t)2 * world * kPeerCapFloats * sizeof(float); }
+size_t peer_mailbox_flag_offset(int world) { return (size_t)2 * world * kPeerCapFloats * sizeof(uint2); }  // LL slots: 8 bytes per float
 size_t peer_mailbox_bytes(int world) { return peer_mailbox_flag_offset(world) + (size_t)2 * world * kPeerMaxBlocks * sizeof(unsigned); }
 
 void launch_peer_allreduce(float* v, uint64_t n, const PeerMailboxes& mb, unsigned epoch, cudaStream_t stream) {
