@@ -865,6 +865,15 @@ size_t host_class(uint64_t bytes) {
 }
 }  // namespace
 
+int cc_memory_trim(void) {
+  return guarded([&] {
+    Lock lock;
+    require_init();
+    driver().cuCtxSynchronize();  // pooled blocks may still be in use by queued commands
+    trim_pool();
+  });
+}
+
 int cc_host_alloc(uint64_t bytes, void** out) {
   return guarded([&] {
     Lock lock;

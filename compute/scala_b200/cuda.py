@@ -145,6 +145,11 @@ def stats() -> dict:
     return {n: int(getattr(s, n)) for n, _ in s._fields_}
 
 
+def memory_trim() -> None:
+    """return idle pooled device memory to the driver"""
+    check(_L().cc_memory_trim())
+
+
 def stats_reset() -> None:
     check(_L().cc_stats_reset())
 

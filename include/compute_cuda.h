@@ -99,6 +99,8 @@ int cc_buffer_length(cc_buffer b, uint64_t* out_n_floats);
  * `offset_floats` after `waits`; `*out_event` completes when `host` is filled (NULL => blocking). */
 int cc_buffer_to_host(cc_buffer b, uint64_t offset_floats, float* host, uint64_t n_floats, const cc_event* waits,
                       int n_waits, cc_event* out_event);
+/* gives every idle pooled device block back to the driver (the pool also does this by itself when an allocation fails) */
+int cc_memory_trim(void);
 /* pinned host staging memory (replaces LWJGL memAllocFloat, Memory.scala:184-208). Blocks are pooled by size class:
  * cc_host_free returns a block to the pool (cuMemHostAlloc is far too slow for a per-read-back allocation); everything
  * is unpinned and freed by cc_shutdown. */

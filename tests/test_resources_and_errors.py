@@ -52,6 +52,8 @@ def test_the_pool_gives_memory_back_under_pressure(cuda):
     c.release()
     big = cuda.Buffer.alloc(chunk * 2 + (1 << 20))  # pool hit this time
     big.release()
+    cuda.memory_trim()  # do not sit on two thirds of the device for the rest of the session
+    assert cuda.stats()["bytes_pooled"] == 0
 
 
 def test_invalid_handles_and_arguments(cuda):
