@@ -82,6 +82,7 @@ struct Program {
   std::vector<Op> ops;        // the term (evaluated for every point of the index space)
   std::vector<Load> loads;
   std::vector<int> results;
+  int shifted_loads = 0;      // loads running along the lanes at a constant offset off the 16-byte grid (dense stencil windows)
   int64_t tuple_inner = 1;    // several results (un-rolled join): the result index sits before the last dims whose product this is
   // reductions only
   int n_red = 0;              // number of trailing reduction dims
@@ -408,7 +409,11 @@ std::vector<uint32_t> monoid_tree_leaves(const Tree& t, uint32_t root) {
   return leaves;
 }
 
-constexpr size_t kMinRerollTerms = 8;  // shorter chains stay unrolled in one elementwise kernel, as the reference runs them
+// shorter chains stay unrolled in one elementwise kernel, as the reference runs them (CC_TUNE_MIN_REROLL_TERMS: A/B knob)
+const size_t kMinRerollTerms = [] {
+  const char* e = getenv("CC_TUNE_MIN_REROLL_TERMS");
+  return (size_t)(e ? std::max(2, atoi(e)) : 8);
+}();
 
 // A re-rolled reduction found inside an expression: `top` is the root of a left-leaning Plus chain whose terms are all
 // congruent to terms[0], with Transform constants affine in a multi-index over `levels` (outermost first):
@@ -563,6 +568,10 @@ bool find_chain(const Tree& t, uint32_t root, Chain& best) {
         c = std::move(tree);
       }
     }
+    // a small dense window over ONE source (3x3 / 5x5 box sums, max pooling: bare translated views, two or more window axes) is
+    // faster unrolled -- its shifted loads share aligned vectors -- than as a reduction whose shift is a run-time value
+    // (3x3 on 4096^2: 43 vs 72 us, 5x5: 96 vs 185 us)
+    if (c.levels.size() >= 2 && c.terms.size() <= 32 && t.nodes[c.terms[0]].kind == K_EXTRACT) continue;
     best_len = c.terms.size();
     best = std::move(c);
   }
@@ -946,8 +955,51 @@ void emit_load(Emit& e, const Program& p, int j, const LoadCtx& c, const char* i
     e("%sL%d[1] = L%d[2] = L%d[3] = L%d[0];\n", indent, j, j, j, j);
     return;
   }
-  // per-lane scalar loads (strided / misaligned / lane-dependent bounds); lanes a few floats apart share 32-byte sectors, which
-  // a non-allocating load would fetch from L2 once per lane
+  // Unit stride along the lanes, but shifted off the 16-byte grid by a constant (a translation along the fastest dimension) and /
+  // or with bounds that differ per lane: read the (at most two) ALIGNED vectors that cover the four lanes and pick the lanes out of
+  // them -- 1-2 vector loads instead of 4 scalar ones, and the windows of a stencil (x.translate(dy, dx) for dx = -1, 0, 1) share
+  // their vectors. The addresses are clamped into the buffer instead of tested: a clamped vector only ever feeds lanes whose own
+  // index is out of range, and those take the padding.
+  {
+    const int64_t TOTAL = product(L.src_shape);
+    // (worth it from four such loads on: a 3x3 window 58 -> 43 us on 4096^2, 5x5 169 -> 96 us; with the two of a 5-point stencil the
+    // extra bytes pulled through L1 cost more than the saved instructions: 160 -> 183 us)
+    bool shifted = V == 4 && coefV == 1 && c.vdim >= 0 && TOTAL >= 8 && TOTAL % 4 == 0 && p.shifted_loads >= 4;
+    for (int x = 0; shifted && x < nd; ++x)
+      if (x != c.vdim && p.dims[x] > 1 && L.coef[x] % 4 != 0) shifted = false;
+    if (shifted) {
+      const int sft = (int)(((L.base % 4) + 4) % 4);
+      const char* I = c.idx_type;
+      e("%sconst %s oa%d = o%d - %d;\n", indent, I, j, j, sft);
+      e("%sfloat A%d[4], B%d[4];\n", indent, j, j);
+      e("%scc_ldc4(p%d + (oa%d < 0 ? (%s)0 : (oa%d > (%s)%lld ? (%s)%lld : oa%d)), A%d);\n", indent, L.arg, j, I, j, I, (long long)(TOTAL - 4), I,
+        (long long)(TOTAL - 4), j, j);
+      if (sft != 0)
+        e("%scc_ldc4(p%d + (oa%d + 4 < 0 ? (%s)0 : (oa%d + 4 > (%s)%lld ? (%s)%lld : oa%d + 4)), B%d);\n", indent, L.arg, j, I, j, I, (long long)(TOTAL - 4), I,
+          (long long)(TOTAL - 4), j, j);
+      e("%s#pragma unroll\n%sfor (int l = 0; l < 4; ++l) {\n", indent, indent);
+      std::string cond = ucond;
+      for (int y = 0; y < L.rows; ++y) {
+        if (!L.need_lo[y] && !L.need_hi[y]) continue;
+        if (L.M[(size_t)y * cols + c.vdim] == 0.0) continue;
+        e("%s  const %s k%d = %s;\n", indent, I, y, row_index_expr(L, y, nd, c.vdim, "l").c_str());
+        if (L.need_lo[y]) cond += strprintf("%sk%d >= 0", cond.empty() ? "" : " && ", y);
+        if (L.need_hi[y]) cond += strprintf("%sk%d < %lld", cond.empty() ? "" : " && ", y, (long long)L.src_shape[y]);
+      }
+      if (sft != 0)
+        e("%s  const float raw = (l + %d < 4) ? A%d[(l + %d) & 3] : B%d[(l + %d) & 3];\n", indent, sft, j, sft, j, sft);
+      else
+        e("%s  const float raw = A%d[l];\n", indent, j);
+      if (cond.empty())
+        e("%s  L%d[l] = raw;\n", indent, j);
+      else
+        e("%s  L%d[l] = (%s) ? raw : %s;\n", indent, j, cond.c_str(), pad.c_str());
+      e("%s}\n", indent);
+      return;
+    }
+  }
+  // per-lane scalar loads (strided / lane-dependent bounds on a non-unit stride); lanes a few floats apart share 32-byte sectors,
+  // which a non-allocating load would fetch from L2 once per lane
   if (std::llabs(coefV) <= 8) LD1 = "cc_ldc";
   e("%s#pragma unroll\n%sfor (int l = 0; l < %d; ++l) {\n", indent, indent, V);
   std::string cond = ucond;
@@ -1978,6 +2030,10 @@ Plan make_plan(const Tree& t, const DeviceProps& dev) {
     for (Load& L : prog.loads)
       if (L.integer && uses[(size_t)L.arg] > 1) L.reuse = true;
   }
+
+  if (!prog.dims.empty())
+    for (const Load& L : prog.loads)
+      if (L.integer && L.coef[prog.dims.size() - 1] == 1 && L.base % 4 != 0) ++prog.shifted_loads;
 
   if (root.kind == K_REDUCE) {
     plan.kind = PLAN_FULL_REDUCE;

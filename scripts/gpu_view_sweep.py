@@ -60,6 +60,24 @@ case("transpose 8192x8191 (odd)", lambda: XT2.transpose(), 2 * 4 * 8192 * 8191)
 case("broadcast row [512] -> 512^3 times x", lambda: X3 * R3, 2 * B3)
 case("join(split(0)) along dim 0 512^3", lambda: T.join(X3.split(0), 0), 2 * B3)
 case("join(split(2)) along dim 2 512^3 (last dim)", lambda: T.join(X3.split(2)), 2 * B3)
+S2 = [4096, 4096]
+
+
+def window(x, f):
+    terms = [x.translate([dy, dx]) for dy in (-1, 0, 1) for dx in (-1, 0, 1)]
+    return chain_with(terms, f)
+
+
+def chain_with(parts, f):
+    acc = parts[0]
+    for q in parts[1:]:
+        acc = f(acc, q)
+    return acc
+
+
+case("3x3 box sum (9 translated views) 4096^2", lambda: window(XS, lambda a, b: a + b), 2 * 4 * 4096 * 4096)
+case("3x3 max pool, stride 1 (9 translated views) 4096^2", lambda: window(XS, T.max), 2 * 4 * 4096 * 4096)
+case("5x5 box sum (25 translated views) 4096^2", lambda: chain_with([XS.translate([dy, dx]) for dy in range(-2, 3) for dx in range(-2, 3)], lambda a, b: a + b), 2 * 4 * 4096 * 4096)
 M3 = [256, 512, 1024]
 case("sum over middle axis 256x512x1024", lambda: chain_sum(XM.split(1)), 4 * n_of(M3) + 4 * 256 * 1024)
 case("sum over last axis 256x512x1024", lambda: chain_sum(XM.split(2)), 4 * n_of(M3) + 4 * 256 * 512)
@@ -77,6 +95,7 @@ XT = T.random([8192, 8200], seed=5).doCache()
 XT2 = T.random([8192, 8191], seed=6).doCache()
 ROW = T.random([512], seed=7).doCache()
 XM = T.random(M3, seed=8).doCache()
+XS = T.random(S2, seed=13).doCache()
 XA = T.random([16384, 4096], seed=9).doCache()
 XB = T.random([16384, 4096], seed=10).doCache()
 XC = T.random([1024, 1024, 3], seed=11).doCache()
