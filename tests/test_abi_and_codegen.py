@@ -409,6 +409,50 @@ def test_iterated_maps_become_counted_loops():
     assert k.info.kind == 1
 
 
+def test_tuned_template_choices_are_stable():
+    """the template decisions the B200 measurements settled (profiles/r01_view_sweep.json), pinned through the generated source"""
+    def gen(e):
+        src = e.compile().source
+        return src[src.rindex("\n// ", 0, src.rindex('extern "C"')):]
+
+    x = rnd([512, 512])
+    # a source read through several views: L1-allocating loads; a single translated view keeps streaming (no_allocate) loads
+    two = gen(x + x.translate([1, 0]))
+    assert "cc_ldc4(" in two and "cc_ldg4(" not in two
+    assert "cc_ldg4(" in gen(x.translate([1, 0]) * rnd([512, 512], 2))
+    # 5-point stencil: two shifted views -> per-lane loads; dense 3x3 window: stays unrolled, aligned vector pairs with static picks
+    five = gen(x + x.translate([0, 1]) + x.translate([0, -1]) + x.translate([1, 0]) + x.translate([-1, 0]))
+    assert "elementwise" in five and "oa1" not in five and "float A" not in five
+    terms = [x.translate([dy, dx]) for dy in (-1, 0, 1) for dx in (-1, 0, 1)]
+    acc = terms[0]
+    for t in terms[1:]:
+        acc = T.max(acc, t)
+    win = acc.compile()
+    assert win.info.kind == 0 and "float A" in win.source and "& 3]" in win.source
+    # ... while a weighted window (the convolution idiom) is still a re-rolled reduction
+    w = rnd([3, 3], 5)
+    wt = [x.translate([dy, dx]) * w.split(0)[dy + 1].split(0)[dx + 1].broadcast([512, 512]) for dy in (-1, 0, 1) for dx in (-1, 0, 1)]
+    acc = wt[0]
+    for t in wt[1:]:
+        acc = acc + t
+    assert acc.compile().info.kind == 1
+    # odd fastest dimension under a view: scalar lanes, 8 elements in flight per thread
+    odd = gen(rnd([1001, 1003, 127]).translate([0, 0, 1]))
+    assert "V=1 U=8" in odd
+    # short rows: a warp per output; long rows: a CTA per output
+    def rowsum(shape):
+        parts = rnd(shape).split(len(shape) - 1)
+        a = parts[0]
+        for q in parts[1:]:
+            a = a + q
+        return gen(a)
+    assert "threads/output=32" in rowsum([16384, 1024]) and "threads/output=256" in rowsum([16384, 4096])
+    # join(split(d), d) is the identity copy whatever d
+    y = rnd([64, 96, 128])
+    for d in (0, 1, 2):
+        assert "flat=1" in gen(T.join(y.split(d), d))
+
+
 def test_on_disk_cubin_cache(tmp_path):
     """opt-in: the cubin of a generated source survives the process; a hit skips NVRTC; a corrupt entry is recompiled"""
     import os
