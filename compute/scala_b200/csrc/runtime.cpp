@@ -276,7 +276,9 @@ void op_begin(Op& op, const cc_event* waits, int n_waits) {
     for (const Mark& m : b->reads) need(op.stream, m);    // write after read (also covers pooled-memory reuse)
   }
   if (rt().nvtx) nvtxRangePushA(op.label.c_str());
-  if (rt().profiling) {  // after the waits: the interval measures the command, not its dependencies
+  // after the waits: the interval measures the command, not its dependencies. (At most 2^18 unreported records are kept: a caller
+  // that never asks for the report must not grow an event list without bound.)
+  if (rt().profiling && rt().prof_records.size() < ((size_t)1 << 18)) {
     op.prof_start = prof_event();
     CC_CU(cuEventRecord(op.prof_start, op.cu()));
   }
