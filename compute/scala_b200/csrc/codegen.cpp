@@ -1293,6 +1293,162 @@ void emit_tiled_transpose(Plan& plan, const Program& p, int n_args, const Device
   if (total > 0) plan.launches.push_back(ls);
 }
 
+// ---- stencil tile: dense windows over one source -------------------------------------------------------------------------
+//
+// An elementwise program that reads ONE same-shape source through many pure translations differing in the last two dimensions
+// (box sums, max pooling, Laplacians: `x.translate(dy, dx)` for a window of (dy, dx)) re-reads every element once per window
+// position through L1. Here a CTA stages the 16 x 128 output tile plus its halo into shared memory once -- bounds tests and the
+// padding are applied while staging, with 128-bit loads -- and every window position is then a conflict-free shared-memory read.
+// Other operands of the expression are loaded per output as in the elementwise template.
+bool try_emit_stencil_tile(Plan& plan, const Program& p, int n_args, const DeviceProps& dev) {
+  const int nd = (int)p.dims.size();
+  if (getenv("CC_NO_STENCIL_TILE")) return false;
+  if (nd < 2 || p.results.size() != 1) return false;
+  const int64_t H = p.dims[nd - 2], W = p.dims[nd - 1];
+  if (W % 4 != 0 || W < 128 || H < 8) return false;
+  std::vector<int64_t> stride(nd, 1);
+  for (int x = nd - 2; x >= 0; --x) stride[x] = stride[x + 1] * p.dims[x + 1];
+  auto is_translation = [&](const Load& L) {
+    if (!L.integer || (int)L.src_shape.size() != nd) return false;
+    for (int x = 0; x < nd; ++x)
+      if (L.src_shape[x] != p.dims[x] || L.coef[x] != stride[x]) return false;
+    // the matrix itself must be the identity (coef == stride could also come from a degenerate mixture)
+    for (int y = 0; y < nd; ++y)
+      for (int x = 0; x < nd; ++x)
+        if (L.M[(size_t)y * (nd + 1) + x] != (x == y ? 1.0 : 0.0)) return false;
+    return true;
+  };
+  // the window source: the argument with the most translated loads
+  std::vector<int> count((size_t)n_args, 0);
+  for (const Load& L : p.loads)
+    if (is_translation(L)) ++count[(size_t)L.arg];
+  int wa = -1;
+  for (int a = 0; a < n_args; ++a)
+    if (count[(size_t)a] >= 6 && (wa < 0 || count[(size_t)a] > count[(size_t)wa])) wa = a;
+  if (wa < 0) return false;
+  const int nloads = (int)p.loads.size();
+  std::vector<char> in_window((size_t)nloads, 0);
+  int64_t ymin = 0, ymax = 0, xmin = 0, xmax = 0;
+  std::vector<int64_t> lead_off;
+  float padding = 0.f;
+  bool first = true;
+  for (int j = 0; j < nloads; ++j) {
+    const Load& L = p.loads[j];
+    if (L.arg != wa || !is_translation(L)) continue;
+    std::vector<int64_t> off(nd);
+    for (int y = 0; y < nd; ++y) off[y] = (int64_t)L.M[(size_t)y * (nd + 1) + nd];
+    std::vector<int64_t> lo(off.begin(), off.end() - 2);
+    if (first) {
+      lead_off = lo;
+      padding = L.padding;
+      ymin = ymax = off[nd - 2];
+      xmin = xmax = off[nd - 1];
+      first = false;
+    } else if (lo != lead_off || memcmp(&padding, &L.padding, 4) != 0) {
+      continue;  // a translation along a leading dimension: read like any other operand
+    }
+    in_window[(size_t)j] = 1;
+    ymin = std::min(ymin, off[nd - 2]), ymax = std::max(ymax, off[nd - 2]);
+    xmin = std::min(xmin, off[nd - 1]), xmax = std::max(xmax, off[nd - 1]);
+  }
+  int nwin = 0;
+  for (char c : in_window) nwin += c;
+  // (from six views on: with the five of a 5-point stencil the L1-resident elementwise kernel already runs at the HBM rate)
+  if (nwin < 6 || ymax - ymin > 16 || xmax - xmin > 32) return false;
+  auto floor4 = [](int64_t v) { return v >= 0 ? v / 4 * 4 : -((-v + 3) / 4 * 4); };
+  // 256 threads = 8 row groups x 32 column vectors; each thread owns RT rows of 4 columns -> tile of 8 * RT rows x 128 columns
+  int RT = 4;
+  if (const char* ev = getenv("CC_TUNE_STENCIL_RT")) RT = std::max(1, std::min(8, atoi(ev)));  // tuning knob
+  const int TW = 128;
+  const int TH = 8 * RT;
+  const int64_t HX0 = floor4(xmin), HX1 = -floor4(-xmax);  // halo columns rounded outwards to the 16-byte grid
+  const int SH = TH + (int)(ymax - ymin), SW = TW + (int)(HX1 - HX0);
+  const int64_t total = product(p.dims);
+  const char* IDX = pick_idx_type(p, total);
+  int64_t lead = 1;
+  for (int x = 0; x < nd - 2; ++x) lead *= p.dims[x];
+  const int64_t tilesY = (H + TH - 1) / TH, tilesX = (W + TW - 1) / TW;
+  const int64_t ntiles = lead * tilesY * tilesX;
+  const int64_t grid = std::max<int64_t>(1, std::min<int64_t>(ntiles, 0x7fffffff));
+  (void)dev;
+
+  Emit e;
+  e("// stencil tile: dims=[");
+  for (int x = 0; x < nd; ++x) e("%s%lld", x ? "," : "", (long long)p.dims[x]);
+  e("] %d window loads of p%d, dy=[%lld,%lld] dx=[%lld,%lld], tile %dx%d + halo -> shared %dx%d, %d other loads, idx=%s grid=%lld\n", nwin, wa, (long long)ymin,
+    (long long)ymax, (long long)xmin, (long long)xmax, TH, TW, SH, SW, nloads - nwin, IDX, (long long)grid);
+  e("extern \"C\" __global__ void __launch_bounds__(256) jit_kernel(%s) {\n", param_list(n_args, true).c_str());
+  e("  __shared__ __align__(16) float tile[%d][%d];\n", SH, SW);
+  e("  for (%s t_ = blockIdx.x; t_ < (%s)%lld; t_ += gridDim.x) {\n", IDX, IDX, (long long)ntiles);
+  e("    %s r_ = t_;\n    const %s c0 = (r_ %% (%s)%lld) * %d; r_ /= (%s)%lld;\n    const %s r0 = (r_ %% (%s)%lld) * %d; r_ /= (%s)%lld;\n", IDX, IDX, IDX,
+    (long long)tilesX, TW, IDX, (long long)tilesX, IDX, IDX, (long long)tilesY, TH, IDX, (long long)tilesY);
+  for (int x = nd - 3; x >= 0; --x)
+    e("    const %s g%d = r_ %% (%s)%lld; r_ /= (%s)%lld;\n", IDX, x, IDX, (long long)p.dims[x], IDX, (long long)p.dims[x]);
+  // leading part of the window source's address, and whether the leading indices are in range at all
+  std::string lead_ok = "true", lead_base = strprintf("(%s)0", IDX);
+  for (int x = 0; x < nd - 2; ++x) {
+    if (lead_off[(size_t)x] != 0)
+      lead_ok += strprintf(" && g%d + %lld >= 0 && g%d + %lld < %lld", x, (long long)lead_off[(size_t)x], x, (long long)lead_off[(size_t)x], (long long)p.dims[x]);
+    lead_base += strprintf(" + (g%d + (%s)%lld) * (%s)%lld", x, IDX, (long long)lead_off[(size_t)x], IDX, (long long)stride[x]);
+  }
+  const std::string pad = flit(padding);
+  e("    const bool lead_ok = %s;\n    const %s lead_base = %s;\n", lead_ok.c_str(), IDX, lead_base.c_str());
+  // ---- staging: SH rows of SW/4 vectors
+  e("    for (int i_ = threadIdx.x; i_ < %d; i_ += 256) {\n", SH * (SW / 4));
+  e("      const int sy = i_ / %d, sx = (i_ %% %d) * 4;\n", SW / 4, SW / 4);
+  e("      const %s yy = r0 + sy + (%s)%lld;\n      const %s xx = c0 + sx + (%s)%lld;\n", IDX, IDX, (long long)ymin, IDX, IDX, (long long)HX0);
+  e("      float v4[4] = {%s, %s, %s, %s};\n", pad.c_str(), pad.c_str(), pad.c_str(), pad.c_str());
+  e("      if (lead_ok && yy >= 0 && yy < (%s)%lld) {\n", IDX, (long long)H);
+  e("        const float* src = p%d + lead_base + yy * (%s)%lld + xx;\n", wa, IDX, (long long)W);
+  e("        if (xx >= 0 && xx + 3 < (%s)%lld) {\n          cc_ldg4(src, v4);\n        } else {\n", IDX, (long long)W);
+  e("          #pragma unroll\n          for (int l = 0; l < 4; ++l)\n            if (xx + l >= 0 && xx + l < (%s)%lld) v4[l] = cc_ldg(src + l);\n        }\n      }\n", IDX,
+    (long long)W);
+  e("      *reinterpret_cast<float4*>(&tile[sy][sx]) = make_float4(v4[0], v4[1], v4[2], v4[3]);\n    }\n    __syncthreads();\n");
+  // ---- compute: a thread owns RT rows x 4 adjacent columns. It pulls the RT + (ymax - ymin) rows of covering aligned vectors out of
+  // shared memory once (conflict-free 128-bit reads; a row is shared by the RT outputs above and below it, which is what takes the
+  // shared-memory pipe off the critical path: ncu showed it 75 % busy with one row of outputs per thread) and every window position
+  // is a static pick from those registers
+  const int NC = 4 + (int)(HX1 - HX0);
+  const int WY = (int)(ymax - ymin);
+  e("    {\n      const int ly0 = (threadIdx.x / %d) * %d, lx = (threadIdx.x %% %d) * 4;\n", TW / 4, RT, TW / 4);
+  e("      const %s g%d = c0 + lx;\n", IDX, nd - 1);
+  e("      if (g%d < (%s)%lld && r0 + ly0 < (%s)%lld) {\n", nd - 1, IDX, (long long)W, IDX, (long long)H);
+  for (int r = 0; r < RT + WY; ++r)
+    e("        float R%d[%d];\n        #pragma unroll\n        for (int k = 0; k < %d; ++k) *reinterpret_cast<float4*>(&R%d[4 * k]) = *reinterpret_cast<const float4*>(&tile[ly0 + %d][lx + 4 * k]);\n",
+      r, NC, NC / 4, r, r);
+  LoadCtx c{4, nd - 1, IDX};
+  std::string lin = strprintf("(%s)0", "long long");
+  for (int x = 0; x < nd; ++x) lin += strprintf(" + (long long)g%d * %lldLL", x, (long long)stride[x]);
+  for (int i = 0; i < RT; ++i) {
+    e("        if (r0 + ly0 + %d < (%s)%lld) {\n          const %s g%d = r0 + ly0 + %d;\n", i, IDX, (long long)H, IDX, nd - 2, i);
+    for (int j = 0; j < nloads; ++j) {
+      if (in_window[(size_t)j]) {
+        const Load& L = p.loads[j];
+        const int64_t dy = (int64_t)L.M[(size_t)(nd - 2) * (nd + 1) + nd], dx = (int64_t)L.M[(size_t)(nd - 1) * (nd + 1) + nd];
+        const int r = i + (int)(dy - ymin), cx = (int)(dx - HX0);
+        e("          const float L%d[4] = {R%d[%d], R%d[%d], R%d[%d], R%d[%d]};\n", j, r, cx, r, cx + 1, r, cx + 2, r, cx + 3);
+      } else {
+        emit_load(e, p, j, c, "          ");
+      }
+    }
+    e("          float o_[4];\n          #pragma unroll\n          for (int l = 0; l < 4; ++l) {\n");
+    emit_ops(e, p, "            ", "l");
+    e("            o_[l] = _%d;\n          }\n", p.results[0]);
+    e("          cc_stg4(out + (%s), o_);\n        }\n", lin.c_str());
+  }
+  e("      }\n    }\n    __syncthreads();\n  }\n}\n");
+  plan.source += e.s;
+  LaunchSpec ls;
+  ls.entry = "jit_kernel";
+  ls.grid[0] = (uint32_t)grid;
+  ls.block[0] = 256;
+  for (int i = 0; i < n_args; ++i) ls.args.push_back(i);
+  ls.args.push_back(ARG_OUT);
+  if (total > 0) plan.launches.push_back(ls);
+  plan.note += "; dense window staged through shared memory";
+  return true;
+}
+
 // ---- reductions over the re-rolled index --------------------------------------------------------------------------
 
 // out[g] = sum_t E(g, t).  dims = out dims + [T].
@@ -2095,7 +2251,9 @@ Plan make_plan(const Tree& t, const DeviceProps& dev) {
     emit_reduce(plan, prog, n_args, dev);
   } else {
     const int td = transpose_dim(prog);
-    if (td >= 0) {
+    if (try_emit_stencil_tile(plan, prog, n_args, dev)) {
+      plan.kind = PLAN_ELEMENTWISE;
+    } else if (td >= 0) {
       plan.kind = PLAN_TILED_TRANSPOSE;
       emit_tiled_transpose(plan, prog, n_args, dev, td);
     } else {

@@ -420,15 +420,23 @@ def test_tuned_template_choices_are_stable():
     two = gen(x + x.translate([1, 0]))
     assert "cc_ldc4(" in two and "cc_ldg4(" not in two
     assert "cc_ldg4(" in gen(x.translate([1, 0]) * rnd([512, 512], 2))
-    # 5-point stencil: two shifted views -> per-lane loads; dense 3x3 window: stays unrolled, aligned vector pairs with static picks
+    # dense windows over one source (>= 4 translated views, extents >= 8 x 128): staged through shared memory; narrower tensors stay
+    # unrolled with shifted views read as aligned vector pairs and static lane picks
     five = gen(x + x.translate([0, 1]) + x.translate([0, -1]) + x.translate([1, 0]) + x.translate([-1, 0]))
-    assert "elementwise" in five and "oa1" not in five and "float A" not in five
+    assert "elementwise" in five and "float A" not in five  # five views: L1-resident elementwise kernel, per-lane shifted loads
     terms = [x.translate([dy, dx]) for dy in (-1, 0, 1) for dx in (-1, 0, 1)]
     acc = terms[0]
     for t in terms[1:]:
         acc = T.max(acc, t)
     win = acc.compile()
-    assert win.info.kind == 0 and "float A" in win.source and "& 3]" in win.source
+    assert win.info.kind == 0 and "stencil tile" in win.source and "R2[5], R2[6], R2[7], R2[8]" in win.source and "R5[3]" in win.source  # 4 output rows + 2 halo rows per thread
+    narrow = rnd([512, 64])
+    nt = [narrow.translate([dy, dx]) for dy in (-1, 0, 1) for dx in (-1, 0, 1)]
+    acc = nt[0]
+    for t in nt[1:]:
+        acc = T.max(acc, t)
+    nw = acc.compile()
+    assert nw.info.kind == 0 and "float A" in nw.source and "& 3]" in nw.source
     # ... while a weighted window (the convolution idiom) is still a re-rolled reduction
     w = rnd([3, 3], 5)
     wt = [x.translate([dy, dx]) * w.split(0)[dy + 1].split(0)[dx + 1].broadcast([512, 512]) for dy in (-1, 0, 1) for dx in (-1, 0, 1)]

@@ -107,6 +107,53 @@ def test_join_at_every_dimension(cuda):
     assert k.info.kind == 0 and "flat=1" in k.source  # split(d) joined back at d is the identity copy, one kernel
 
 
+def test_dense_windows_through_the_stencil_tile(cuda):
+    """box sums / max pooling written as translated views of one source: staged through shared memory (tile + halo, bounds and
+    padding applied while staging). Integer-valued data and max keep every result exact -> bit for bit vs the oracle."""
+    def data(shape, seed):
+        return (np.floor(ref.random_buffer(int(np.prod(shape)), seed) * np.float32(9.0)) - np.float32(4.0)).astype(np.float32).reshape(shape)
+
+    def fold(terms, f):
+        acc = terms[0]
+        for t in terms[1:]:
+            acc = f(acc, t)
+        return acc
+
+    cases = []
+    for shape, pad in (([40, 256], 0.0), ([17, 128], -2.0), ([2, 3, 37, 132], 5.0), ([64, 384], -7.0)):
+        rank = len(shape)
+        lead = [0] * (rank - 2)
+        x_np, y_np = data(shape, 3), data(shape, 4)
+
+        def window(T, offsets, f, lead=lead, extra=False, x_np=x_np, y_np=y_np, pad=pad, rank=rank):
+            x = T(x_np, padding=pad)
+            e = fold([x.translate(lead + [dy, dx]) for dy, dx in offsets], f)
+            return e * T(y_np) + T(y_np).translate([0] * (rank - 2) + [1, 0]) if extra else e
+
+        w3 = [(dy, dx) for dy in (-1, 0, 1) for dx in (-1, 0, 1)]
+        w5 = [(dy, dx) for dy in range(-2, 3) for dx in range(-2, 3)]
+        skew = [(dy, dx) for dy in (0, 1, 2) for dx in (-5, -1, 0, 3)]
+        row6 = [(0, dx) for dx in (-3, -2, -1, 1, 2, 3)]
+        cases += [
+            (lambda T, o=w3, w=window: w(T, o, lambda a, b: a + b), "3x3 sum"),
+            (lambda T, o=w3, w=window: w(T, o, T.max), "3x3 max"),
+            (lambda T, o=w5, w=window: w(T, o, lambda a, b: a + b, extra=True), "5x5 sum with other operands"),
+            (lambda T, o=skew, w=window: w(T, o, T.min), "skewed window"),
+            (lambda T, o=row6, w=window: w(T, o, lambda a, b: a + b), "1-D window of 6"),
+        ]
+        if rank > 2:
+            cases.append((lambda T, o=w3, w=window, rank=rank: w(T, o, T.max, lead=[1] + [0] * (rank - 3)), "window shifted along a leading dimension"))
+    for build, name in cases:
+        k = build(cuda.Tensor).compile()
+        assert "stencil tile" in k.source, name
+        same(cuda, build)
+    # too small / too few views: the ordinary templates
+    x = cuda.Tensor.random([16, 64], seed=1)
+    assert "stencil tile" not in fold([x.translate([dy, dx]) for dy in (-1, 0, 1) for dx in (-1, 0, 1)], cuda.Tensor.max).compile().source
+    y = cuda.Tensor.random([64, 256], seed=1)
+    assert "stencil tile" not in (y + y.translate([0, 1])).compile().source
+
+
 def test_views_that_leave_the_source(cuda):
     for pad in (0.0, -1.5, float("inf")):
         same(cuda, lambda T: T.random([4, 6], seed=1, padding=pad).translate([4, 0]))       # entirely padding
