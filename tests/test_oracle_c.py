@@ -80,3 +80,26 @@ def test_matmul_left_fold_and_gather(L):
     shp = np.asarray([d, d, d], np.int64)
     lib.oracle_affine_gather_3d(t.ctypes.data, shp.ctypes.data, 3, mat.ctypes.data, shp.ctypes.data, 0.0, out.ctypes.data)
     assert np.array_equal(out.view(np.uint32), want.view(np.uint32))
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU port of the generated kernel on the host cores): one JSON line with the keys the driver
+    reads; run here on a small sample so that the contract is checked without a GPU"""
+    import json
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "bench.py", "--impl", "reference", "--steps", "2", "--warmup", "3"], capture_output=True, text=True, cwd=root,
+                       env=dict(os.environ, BENCH_REFERENCE_SAMPLE_LOG2="20"), timeout=300)
+    assert r.returncode == 0, r.stderr[-1000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "GB/s" and d["higher_is_better"] is True and d["n_gpus"] == 1
+    assert d["steps"] == 2 and d["warmup"] >= 3 and d["value"] > 0 and d["ms_per_step"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in d["config"] and "model" not in d["config"]
+    assert d["metric"].startswith("fused elementwise HBM GB/s")
