@@ -242,3 +242,39 @@ def test_random_expression_graphs_match_the_oracle_bit_for_bit(cuda, block):
 def test_larger_random_graphs(cuda, block):
     """extents up to 64 and rank <= 3: vector lanes, tiled transposes, chains long enough to be re-rolled"""
     _run(cuda, [50000 + 100 * block + case for case in range(15)], dims=DIMS_BIG, max_rank=3)
+
+
+def test_random_windows_match_the_oracle(cuda):
+    """random dense windows (6-25 translated views of one source, random paddings, leading offsets, extra operands, ragged tiles):
+    the stencil tile and the shifted-vector paths against the oracle's unrolled evaluation, bit for bit (integer-valued data)"""
+    T, R = cuda.Tensor, ref.Tensor
+    rng = np.random.RandomState(11)
+    tiles = 0
+    for case in range(24):
+        rank = int(rng.randint(2, 5))
+        wide = case % 4 != 3
+        shape = [int(rng.choice((1, 2, 3))) for _ in range(rank - 2)] + [int(rng.choice((8, 17, 40))), int(rng.choice((128, 132, 256) if wide else (16, 32, 64)))]
+        pad = float(rng.choice((0.0, -2.0, 7.0)))
+        x_np = rng.randint(-4, 5, size=shape).astype(np.float32)
+        y_np = rng.randint(-4, 5, size=shape).astype(np.float32)
+        n = int(rng.randint(6, 26))
+        lead = [int(rng.randint(-1, 2)) for _ in range(rank - 2)] if rng.rand() < 0.3 else [0] * (rank - 2)
+        offs = sorted({(int(rng.randint(-3, 4)), int(rng.randint(-6, 7))) for _ in range(n)})
+        use_max = rng.rand() < 0.5
+        extra = rng.rand() < 0.5
+
+        def build(B):
+            x = B(x_np, padding=pad)
+            terms = [x.translate(lead + [dy, dx]) for dy, dx in offs]
+            acc = terms[0]
+            for t in terms[1:]:
+                acc = B.max(acc, t) if use_max else acc + t
+            if extra:
+                acc = acc * B(y_np) - B(y_np).translate([0] * (rank - 1) + [1])
+            return acc
+
+        g = build(T)
+        tiles += "stencil tile" in g.compile().source
+        got, want = g.flatArray(), build(R).flat_array()
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32)) or np.array_equal(got, want), (case, shape, pad, lead, offs, use_max, extra)
+    assert tiles >= 8
