@@ -8,7 +8,20 @@
 //   * warp-shuffle and shared-memory block reductions.
 
 // ---- memory ---------------------------------------------------------------------------------------------------------
-
+// (CC_HOST_EMULATION is defined only by tests/kernel_emulator, which compiles generated kernels for the host to check the code
+// generator's arithmetic and indexing without a GPU; NVRTC never sees it. The four PTX wrappers get plain C++ bodies there.)
+#ifdef CC_HOST_EMULATION
+__device__ __forceinline__ float cc_ldg(const float* p) { return *p; }
+__device__ __forceinline__ void cc_ldg4(const float* p, float (&v)[4]) { v[0] = p[0], v[1] = p[1], v[2] = p[2], v[3] = p[3]; }
+__device__ __forceinline__ void cc_stg4(float* p, const float (&v)[4]) { p[0] = v[0], p[1] = v[1], p[2] = v[2], p[3] = v[3]; }
+__device__ __forceinline__ void cc_split_tf32(float x, float& hi, float& lo) {
+  hi = __uint_as_float(__float_as_uint(x) & 0xffffe000u);
+  const float r = x - hi;
+  unsigned u = __float_as_uint(r);
+  u = (u + 0x1000u) & 0xffffe000u;  // round to nearest, ties away: cvt.rna.tf32
+  lo = __uint_as_float(u);
+}
+#else
 __device__ __forceinline__ float cc_ldg(const float* p) {
   float v;
   asm("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
@@ -21,6 +34,7 @@ __device__ __forceinline__ void cc_ldg4(const float* p, float (&v)[4]) {
       : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3])
       : "l"(p));
 }
+#endif
 
 // cached flavours (allocate in L1) for data that is reused across the index space: broadcast operands, the operands of a
 // re-rolled reduction whose address does not depend on every output index (matmul / convolution patterns)
@@ -33,6 +47,7 @@ __device__ __forceinline__ void cc_ldc4(const float* p, float (&v)[4]) {
   v[3] = x.w;
 }
 
+#ifndef CC_HOST_EMULATION
 __device__ __forceinline__ void cc_stg4(float* p, const float (&v)[4]) {
   asm volatile("st.global.cs.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]) : "memory");
 }
@@ -45,6 +60,7 @@ __device__ __forceinline__ void cc_split_tf32(float x, float& hi, float& lo) {
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(r));
   lo = __uint_as_float(t);
 }
+#endif
 
 // ---- math -------------------------------------------------------------------------------------------------------------
 // CUDA's expf / logf / tanhf are documented at <= 2 / 1 / 2 ulp; kept behind cc_* names so that leaner or tighter

@@ -1135,6 +1135,23 @@ int cc_kernel_arg_param(cc_kernel h, int i, int32_t* out) {
     *out = (int32_t)k->plan.arg_params[i];
   });
 }
+int cc_kernel_launch_info(cc_kernel h, int i, cc_launch_info_t* out) {
+  return guarded([&] {
+    Lock lock;
+    Kernel* k = as_kernel(h);
+    CC_REQUIRE(out && i >= 0 && i < (int)k->plan.launches.size(), CC_ERR_ILLEGAL_ARGUMENT, "launch index %d out of range", i);
+    const LaunchSpec& ls = k->plan.launches[(size_t)i];
+    memset(out, 0, sizeof *out);
+    snprintf(out->entry, sizeof out->entry, "%s", ls.entry.c_str());
+    for (int d = 0; d < 3; ++d) out->grid[d] = ls.grid[d], out->block[d] = ls.block[d];
+    out->smem = ls.smem;
+    CC_REQUIRE(ls.args.size() <= 32, CC_ERR_UNSUPPORTED, "launch has %zu arguments", ls.args.size());
+    out->n_args = (int32_t)ls.args.size();
+    for (size_t a = 0; a < ls.args.size(); ++a) out->args[a] = ls.args[a];
+    out->n_scratch = (int32_t)k->plan.scratch_floats.size();
+    for (size_t q = 0; q < k->plan.scratch_floats.size() && q < 8; ++q) out->scratch_floats[q] = k->plan.scratch_floats[q];
+  });
+}
 int cc_kernel_source(cc_kernel h, const char** out) {
   return guarded([&] {
     Lock lock;

@@ -180,6 +180,18 @@ int cc_kernel_info(cc_kernel k, cc_kernel_info_t* out);
 int cc_kernel_arg_param(cc_kernel k, int i, int32_t* out_param_ordinal);
 /* generated CUDA C++ (NULL-terminated, owned by the kernel) */
 int cc_kernel_source(cc_kernel k, const char** out);
+/* Launch geometry of the i-th kernel of a compiled plan (i < cc_kernel_info_t.n_launches) — introspection for tests and tools:
+ * the entry point inside the generated module, grid / block / dynamic shared memory, and its argument list (>= 0: plan argument,
+ * -1: the output buffer, -2-k: scratch buffer k of `scratch_floats`, -100 / -101: the runtime's fold partials / block counter). */
+typedef struct cc_launch_info_t {
+  char entry[64];
+  uint32_t grid[3], block[3], smem;
+  int32_t n_args;
+  int32_t args[32];
+  int32_t n_scratch;
+  uint64_t scratch_floats[8];
+} cc_launch_info_t;
+int cc_kernel_launch_info(cc_kernel k, int i, cc_launch_info_t* out);
 
 /* Kernel.enqueue + dispatch (O:788-844, 1298-1329; T:1342-1375): args in cc_kernel_arg_param order. */
 int cc_launch(cc_kernel k, const cc_buffer* args, int n_args, cc_buffer out, const cc_event* waits, int n_waits,

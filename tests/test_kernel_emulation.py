@@ -1,0 +1,145 @@
+"""CPU-only: generated kernels run on the host emulator (tests/kernel_emulator, test infrastructure only) against the oracle.
+Exactly the CUDA text NVRTC compiles for sm_100a is compiled with g++ instead and executed with one host thread per CUDA thread,
+so the code generator's indexing, bounds tests, padding, lane picks, tiles, shuffles and fold orders are exercised where no GPU
+exists.  Integer-valued data keeps every case bit-exact whatever the evaluation order.  (The GPU tier repeats all of this on the
+device; this tier makes no parity or performance claim.)"""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "kernel_emulator"))
+from run import arg_ordinals, emulate  # noqa: E402
+
+from compute.scala_b200 import cuda  # noqa: E402
+from oracle import reference as ref  # noqa: E402
+
+T, R = cuda.Tensor, ref.Tensor
+
+
+def ints(B, shape, seed, padding=0.0):
+    """integers in {-4..4} from the bit-reproducible hash RNG, materialised as a leaf on either backend (lazy on the cuda side)"""
+    r = B.random(shape, seed=seed, padding=padding) * B.fill(9.0, shape)
+    e = r - r % B.fill(1.0, shape) - B.fill(4.0, shape)
+    return e
+
+
+def oracle_params(rt):
+    if isinstance(rt, ref._Transformed) and isinstance(rt.checkpoint, ref._Join):  # join(…, dimension) = permuted view of the last-dim join (T:560-575)
+        rt = rt.checkpoint
+    if isinstance(rt, ref._Join):
+        seen, out = set(), []
+        for t in rt._tensors:
+            for p in ref.parameter_descendants(t.closure()):
+                if id(p) not in seen:
+                    seen.add(id(p))
+                    out.append(p)
+        return out
+    if isinstance(rt, ref._Sum):
+        return ref.parameter_descendants(rt._base.closure())
+    return ref.parameter_descendants(rt.closure())
+
+
+def check(build, expect_in_source=None, kind=None):
+    """build(B, leaf) -> expression; leaf(shape, seed, padding) makes an integer-valued NON-INLINE leaf on backend B"""
+    def leaf_r(shape, seed, padding=0.0):
+        data = ints(R, shape, seed).flat_array().reshape(shape)
+        return R(data, padding=padding)
+
+    def leaf_t(shape, seed, padding=0.0):
+        return T.random(shape, seed=seed, padding=padding)  # stands in for the leaf: only its position in the argument list matters
+
+    want_t = build(R, leaf_r)
+    want = want_t.flat_array()
+    expr = build(T, leaf_t)
+    params = oracle_params(want_t)
+    k0 = expr.compile()
+    ords = arg_ordinals(cuda, k0)
+    assert all(0 <= o < len(params) for o in ords), (ords, len(params))
+    leaves = [params[o].id.buffer() for o in ords]
+    got, k = emulate(cuda, expr, leaves)
+    if expect_in_source:
+        assert expect_in_source in k.source, expect_in_source
+    if kind is not None:
+        assert k.info.kind == kind
+    assert tuple(expr.shape) == tuple(want_t.shape)
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32)) or np.array_equal(got, want), (got[:16], want[:16])
+
+
+def chain(parts, f=lambda a, b: a + b):
+    acc = parts[0]
+    for p in parts[1:]:
+        acc = f(acc, p)
+    return acc
+
+
+def test_elementwise_vector_and_scalar_lanes():
+    check(lambda B, leaf: B.abs(leaf([12, 16], 1) * leaf([12, 16], 2) - leaf([12, 16], 3)), "flat=1", 0)
+    check(lambda B, leaf: B.max(leaf([5, 7], 1), -leaf([5, 7], 2)) + leaf([5, 7], 3), None, 0)            # 35 elements: vector body + scalar tail
+    check(lambda B, leaf: leaf([6, 9], 1, 2.0).translate([1, -2]) * leaf([6, 9], 2), "V=1", 0)             # odd fastest dimension under a view
+    check(lambda B, leaf: leaf([3], 1).broadcast([3, 8]) + leaf([3, 8], 2), None, 0)                       # trailing broadcast: one scalar feeds 4 lanes
+    check(lambda B, leaf: leaf([2, 8], 1).reshape([1, 2, 8]).broadcast([3, 2, 8]) - leaf([3, 2, 8], 2), None, 0)
+
+
+def test_translations_paddings_and_shifted_vector_loads():
+    for off in ([0, 1], [0, -1], [1, 3], [-2, 4], [0, 5], [3, 0]):
+        check(lambda B, leaf, off=off: leaf([6, 16], 1, -2.0).translate(off), None, 0)
+    # several shifted views of one narrow source: aligned vector pairs with static lane picks and clamped addresses
+    def window(B, leaf):
+        x = leaf([9, 32], 4, 3.0)
+        return chain([x.translate([dy, dx]) for dy in (-1, 0, 1) for dx in (-1, 0, 1)], B.max)
+    check(window, "float A", 0)
+    check(lambda B, leaf: leaf([4, 4, 8], 1, 1.0).translate([1, 0, -1]).translate([0, -1, 2]), None, 0)
+
+
+def test_tiled_transposes():
+    check(lambda B, leaf: leaf([40, 36], 1).transpose(), "tiled transpose", 3)
+    check(lambda B, leaf: leaf([3, 34, 33], 2).permute([0, 2, 1]) + leaf([3, 33, 34], 3), "tiled transpose", 3)
+    check(lambda B, leaf: leaf([33, 2, 40], 2, 5.0).permute([2, 1, 0]).translate([1, 0, -1]), "tiled transpose", 3)
+    check(lambda B, leaf: B.join(leaf([34, 3, 36], 5).split(1)), None, None)  # join of a split: re-rolled into an output dimension
+
+
+def test_stencil_tile():
+    def window(B, leaf, shape=(20, 132), pad=-2.0, lead=()):
+        x = leaf(list(shape), 4, pad)
+        offs = [(dy, dx) for dy in (-1, 0, 2) for dx in (-5, -1, 0, 3)]
+        e = chain([x.translate(list(lead) + [dy, dx]) for dy, dx in offs])
+        return e * leaf(list(shape), 5) - leaf(list(shape), 6).translate([0] * (len(shape) - 1) + [1])
+    check(window, "stencil tile", 0)
+    check(lambda B, leaf: window(B, leaf, (2, 9, 128), 0.0, (1,)), "stencil tile", 0)
+
+
+def test_axis_reductions_every_owner_and_monoid():
+    check(lambda B, leaf: chain(leaf([12, 128], 1).split(0)), "column owner", 1)
+    check(lambda B, leaf: chain(leaf([12, 40], 1).split(0)), "row owner", 1)                          # < 64 outputs: a warp per output
+    check(lambda B, leaf: chain(leaf([300, 64], 1).split(0)), "column owner", 1)                     # T split over blockIdx.y + second stage
+    check(lambda B, leaf: chain(leaf([9, 64], 1).split(1)), "row owner", 1)
+    check(lambda B, leaf: chain(leaf([6, 2048], 1).split(1)), "threads/output=256", 1)
+    check(lambda B, leaf: chain(leaf([12, 128], 1).split(0), B.max), "fold=Max", 1)
+    check(lambda B, leaf: chain(leaf([9, 64], 1).split(1), B.min), "fold=Min", 1)
+    check(lambda B, leaf: B.fill(2.0, [128]) * chain(leaf([12, 128], 1).split(0)) - leaf([128], 2), "epilogue=1", 1)
+    # a nested (3 x 3 x channel) weighted window: the convolution idiom, re-rolled over three digits
+    def conv(B, leaf):
+        x, w = leaf([2, 6, 8, 3], 1), leaf([3, 3, 3], 2)
+        terms = [x.split(3)[c].translate([0, dy - 1, dx - 1]) * w.split(0)[dy].split(0)[dx].split(0)[c].broadcast([2, 6, 8]) for dy in range(3) for dx in range(3) for c in range(3)]
+        return chain(terms)
+    check(conv, "T=3x3x3", 1)
+
+
+def test_whole_tensor_folds_and_iterated_maps():
+    check(lambda B, leaf: (leaf([33, 20], 1) * leaf([33, 20], 2)).sum(), "whole-tensor fold", 4)
+    check(lambda B, leaf: B.abs(leaf([4099], 3)).sum(), "whole-tensor fold", 4)
+
+    def iterated(B, leaf):
+        x, b = leaf([8, 12], 1), leaf([8, 12], 2)
+        for _ in range(12):
+            x = B.max(x - b, -x)
+        return x
+    check(iterated, "int it_", 0)
+
+
+def test_joins_at_every_dimension_and_tuple_stores():
+    for d in (0, 1, 2):
+        check(lambda B, leaf, d=d: B.join([B.abs(leaf([4, 8], 1)), leaf([4, 8], 2) * leaf([4, 8], 3), B.fill(2.0, [4, 8])], d), None, 0)
+        check(lambda B, leaf, d=d: B.join(leaf([5, 4, 8], 4).split(1), d), None, None)
