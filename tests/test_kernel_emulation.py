@@ -25,10 +25,10 @@ def ints(B, shape, seed, padding=0.0):
     return e
 
 
-def oracle_params(rt):
-    if isinstance(rt, ref._Transformed) and isinstance(rt.checkpoint, ref._Join):  # join(…, dimension) = permuted view of the last-dim join (T:560-575)
+def oracle_params(rt, root_is_join=True):
+    if root_is_join and isinstance(rt, ref._Transformed) and isinstance(rt.checkpoint, ref._Join):  # join(…, dimension) = permuted view of the last-dim join (T:560-575)
         rt = rt.checkpoint
-    if isinstance(rt, ref._Join):
+    if root_is_join and isinstance(rt, ref._Join):
         seen, out = set(), []
         for t in rt._tensors:
             for p in ref.parameter_descendants(t.closure()):
@@ -143,3 +143,88 @@ def test_joins_at_every_dimension_and_tuple_stores():
     for d in (0, 1, 2):
         check(lambda B, leaf, d=d: B.join([B.abs(leaf([4, 8], 1)), leaf([4, 8], 2) * leaf([4, 8], 3), B.fill(2.0, [4, 8])], d), None, 0)
         check(lambda B, leaf, d=d: B.join(leaf([5, 4, 8], 4).split(1), d), None, None)
+
+
+# ---- random graphs: the differential fuzzer's generator, run on the emulator -------------------------------------------------------
+from test_fuzz_differential import DIMS_BIG, Gen, Pair  # noqa: E402
+
+
+class EmuGen(Gen):
+    """single-kernel graphs only: leaves are positions in the argument list (T.random on the cuda side, integer data on the oracle's),
+    no evaluation barriers (nonInline / reshape / inner sums) inside the graph"""
+
+    def leaf(self, shape=None):
+        shape = self.shape() if shape is None else list(shape)
+        pad = float(self.choice((0.0, 0.0, 3.0, -2.0)))
+        kind = self.rng.randint(3)
+        self.note(f"leaf{shape} pad={pad} kind={kind}")
+        if kind == 1 or not shape:
+            v = float(self.rng.randint(-3, 4))
+            if not shape:
+                return Pair(self.T.scalar(v, padding=pad), self.R.scalar(v, padding=pad), 4)
+            return Pair(self.T.fill(v, shape, padding=pad), self.R.fill(v, shape, padding=pad), 4)
+        data = self.rng.randint(-4, 5, size=int(np.prod(shape))).astype(np.float32).reshape(shape)
+        return Pair(self.T.random(shape, seed=1, padding=pad), self.R(data, padding=pad), 4)
+
+    def view(self, p):
+        for _ in range(8):
+            before = len(self.trace)
+            q = super().view(p)
+            if not (self.trace[before].startswith("nonInline") or self.trace[before].startswith("reshape")):
+                return q
+            del self.trace[before:]
+        return p
+
+    def fold(self, p):
+        for _ in range(8):
+            before = len(self.trace)
+            q = super().fold(p)
+            if len(self.trace) == before or self.trace[before] != "sum":
+                return q
+            del self.trace[before:]
+        return p
+
+
+def _emulated_fuzz(seeds, **kw):
+    ran, kinds = 0, {}
+    for seed in seeds:
+        gen = EmuGen(cuda, seed, **kw)
+        p = gen.expr(depth=2)
+        if isinstance(p.r, (ref._Fill,)) or int(np.prod(p.shape)) > 20000:
+            continue
+        if any(t.startswith("join") for t in gen.trace[:-1]):
+            continue  # an inner join is an evaluation barrier whose buffer layout differs between the backends (one-kernel join at a dimension)
+        params = oracle_params(p.r, root_is_join=gen.trace[-1].startswith("join"))
+        try:
+            k0 = p.g.compile()
+        except cuda.ComputeCudaError as e:
+            raise AssertionError((seed, gen.trace, str(e)[:1500])) from None
+        if k0.info.kind == 2 or k0.info.n_launches == 0:
+            continue
+        ords = arg_ordinals(cuda, k0)
+        if sorted(ords) != list(range(len(params))):
+            continue  # a view of an unevaluated inline tensor: the cuda side composes the closure (its leaves are the arguments), the oracle evaluates the checkpoint first
+        try:
+            got, k = emulate(cuda, p.g, [params[o].id.buffer() for o in ords], max_threads=1 << 18)
+        except AssertionError as e:
+            if "too large" in str(e):
+                continue
+            raise AssertionError((seed, gen.trace, str(e))) from None
+        want = p.r.flat_array()
+        ok = tuple(p.g.shape) == tuple(p.r.shape) and (np.array_equal(got.view(np.uint32), want.view(np.uint32)) or np.array_equal(got, want))
+        assert ok, (seed, gen.trace, got[:8].tolist(), want[:8].tolist())
+        ran += 1
+        kinds[int(k.info.kind)] = kinds.get(int(k.info.kind), 0) + 1
+    return ran, kinds
+
+
+@pytest.mark.parametrize("block", range(3))
+def test_random_graphs_on_the_emulator(block):
+    ran, kinds = _emulated_fuzz([300000 + 100 * block + case for case in range(14)])
+    assert ran >= 8, (ran, kinds)
+
+
+@pytest.mark.parametrize("block", range(2))
+def test_larger_random_graphs_on_the_emulator(block):
+    ran, kinds = _emulated_fuzz([310000 + 100 * block + case for case in range(10)], dims=DIMS_BIG, max_rank=3)
+    assert ran >= 5, (ran, kinds)
