@@ -44,6 +44,7 @@ namespace cc {
   X(cuModuleUnload)                 \
   X(cuModuleGetFunction)            \
   X(cuLaunchKernel)                 \
+  X(cuLaunchKernelEx)               \
   X(cuFuncSetAttribute)             \
   X(cuLaunchHostFunc)               \
   X(cuGetErrorString)               \

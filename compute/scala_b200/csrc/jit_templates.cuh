@@ -36,6 +36,17 @@ __device__ __forceinline__ void cc_ldg4(const float* p, float (&v)[4]) {
 }
 #endif
 
+// First statement of every generated entry point when the runtime launches with programmatic stream serialisation (CC_PDL=1):
+// let the next kernel's CTAs be scheduled, then wait until everything this grid depends on has completed and is visible.
+#ifdef CC_HOST_EMULATION
+__device__ __forceinline__ void cc_pdl_entry() {}
+#else
+__device__ __forceinline__ void cc_pdl_entry() {
+  asm volatile("griddepcontrol.launch_dependents;");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+#endif
+
 // cached flavours (allocate in L1) for data that is reused across the index space: broadcast operands, the operands of a
 // re-rolled reduction whose address does not depend on every output index (matmul / convolution patterns)
 __device__ __forceinline__ float cc_ldc(const float* p) { return __ldg(p); }

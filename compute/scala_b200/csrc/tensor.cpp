@@ -60,10 +60,27 @@ void bury(TensorPtr&& p) {
 int64_t live_tensors() { return g_live.load(); }
 
 Session::~Session() {
-  for (auto& kv : done) {
+  for (auto& kv : done_) {
     if (kv.second.buffer) cc_buffer_release(kv.second.buffer);
     if (kv.second.event) cc_event_release(kv.second.event);
   }
+}
+PendingBuffer* Session::find(const Tensor* t) {
+  if (done_.size() <= kLinear) {
+    for (auto& kv : done_)
+      if (kv.first == t) return &kv.second;
+    return nullptr;
+  }
+  auto it = index_.find(t);
+  return it == index_.end() ? nullptr : &done_[it->second].second;
+}
+PendingBuffer* Session::add(const Tensor* t, const PendingBuffer& p) {
+  done_.emplace_back(t, p);
+  if (done_.size() == kLinear + 1)
+    for (size_t i = 0; i < done_.size(); ++i) index_.emplace(done_[i].first, i);
+  else if (done_.size() > kLinear + 1)
+    index_.emplace(t, done_.size() - 1);
+  return &done_.back().second;
 }
 
 // ---- closure emission ----------------------------------------------------------------------------------------------------
@@ -209,6 +226,7 @@ struct BufferTensor final : NonInlineTensor {
   ~BufferTensor() override {
     if (buffer) cc_buffer_release(buffer);
   }
+  cc_buffer resident_buffer() const override { return buffer; }
   PendingBuffer evaluate(Session&) const override {
     check(cc_buffer_retain(buffer));
     return {buffer, 0};
@@ -389,10 +407,11 @@ bool plan_output_redirectable(const PlanCache& pc) {
 // enqueueClosure (Tensors.scala:1291-1392)
 PendingBuffer enqueue_plan(Session& s, const PlanCache& pc, const Shape& out_shape, cc_buffer out_override, cc_event* out_event) {
   std::vector<cc_buffer> args;
+  args.reserve(pc.args.size());
   cc_buffer out = 0;
   try {
-    // upvalues.traverse(tree.id.asInstanceOf[Tensor].doBuffer) — Tensors.scala:1336-1340
-    for (const Tensor* t : pc.args) args.push_back(t->do_buffer(s).buffer);
+    // upvalues.traverse(tree.id.asInstanceOf[Tensor].doBuffer) — Tensors.scala:1336-1340; the session owns the references
+    for (const Tensor* t : pc.args) args.push_back(t->borrow_buffer(s));
     if (out_override)
       out = out_override;
     else
@@ -400,10 +419,8 @@ PendingBuffer enqueue_plan(Session& s, const PlanCache& pc, const Shape& out_sha
     check(cc_launch(pc.kernel, args.data(), (int)args.size(), out, nullptr, 0, out_event));
   } catch (...) {
     if (out && !out_override) cc_buffer_release(out);
-    for (cc_buffer b : args) cc_buffer_release(b);
     throw;
   }
-  for (cc_buffer b : args) cc_buffer_release(b);
   return {out, 0};
 }
 
@@ -418,14 +435,20 @@ std::shared_ptr<T> make(const Shape& shape, float padding) {
 
 }  // namespace
 
-PendingBuffer Tensor::do_buffer(Session& s) const {
-  auto it = s.done.find(this);
-  if (it == s.done.end()) {
-    PendingBuffer p = evaluate(s);
-    it = s.done.emplace(this, p).first;  // the session keeps evaluate()'s reference
+cc_buffer Tensor::borrow_buffer(Session& s) const {
+  if (const cc_buffer own = resident_buffer()) return own;
+  PendingBuffer* p = s.find(this);
+  if (!p) {
+    PendingBuffer fresh = evaluate(s);
+    p = s.add(this, fresh);  // the session keeps evaluate()'s reference
   }
-  check(cc_buffer_retain(it->second.buffer));
-  return {it->second.buffer, 0};
+  return p->buffer;
+}
+
+PendingBuffer Tensor::do_buffer(Session& s) const {
+  const cc_buffer b = borrow_buffer(s);
+  check(cc_buffer_retain(b));
+  return {b, 0};
 }
 
 cc_kernel Tensor::compile_only() const {

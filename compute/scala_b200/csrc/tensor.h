@@ -30,7 +30,15 @@ struct PendingBuffer {
 class Session {
  public:
   ~Session();
-  std::unordered_map<const Tensor*, PendingBuffer> done;
+  // a slow action touches a handful of tensors (the kernel's arguments): a flat table searched linearly beats a hash map's node
+  // allocations; graphs with many non-inline inputs fall over to the index
+  PendingBuffer* find(const Tensor* t);
+  PendingBuffer* add(const Tensor* t, const PendingBuffer& p);
+
+ private:
+  std::vector<std::pair<const Tensor*, PendingBuffer>> done_;
+  std::unordered_map<const Tensor*, size_t> index_;  // built once done_ outgrows kLinear
+  static constexpr size_t kLinear = 16;
 };
 
 class Tensor : public std::enable_shared_from_this<Tensor> {
@@ -52,6 +60,12 @@ class Tensor : public std::enable_shared_from_this<Tensor> {
   // ---- evaluation ----
   // doBuffer (Tensors.scala:1401-1403 etc.): the returned buffer is retained for the caller
   PendingBuffer do_buffer(Session& s) const;
+  // the same evaluation, but the handle stays owned by the session (valid until the session ends): what a kernel launch inside
+  // the session needs for its arguments, without a retain / release pair per argument
+  cc_buffer borrow_buffer(Session& s) const;
+  // a tensor that owns its device buffer for its whole life (Tensor.apply, doCache) lends it without any reference counting: the
+  // graph being evaluated keeps the tensor, and so the buffer, alive for the session
+  virtual cc_buffer resident_buffer() const { return 0; }
   virtual PendingBuffer evaluate(Session& s) const = 0;
   // evaluate with the kernel storing straight into `out` (a wrapped, device-visible buffer — pinned host memory for small
   // read-backs); `*out_event` completes when `out` is written. false = this tensor has no kernel of its own to redirect

@@ -265,6 +265,8 @@ class Kernel:
 class Buffer:
     """DeviceBuffer[Float] handle (OpenCL.scala:636-715)"""
 
+    __slots__ = ("handle",)
+
     def __init__(self, handle: int):
         self.handle = handle
 
@@ -322,16 +324,38 @@ class Buffer:
         check(_L().cc_event_release(ev.value))
 
     def release(self) -> None:
-        if self.handle:
-            check(_L().cc_buffer_release(self.handle))
+        h = self.handle
+        if h:
             self.handle = 0
+            st = (_HOT.buffer_release or _hot().buffer_release)(h)
+            if st:
+                check(st)
 
     def __del__(self):
-        try:
-            if _lib._lib is not None:
-                self.release()
-        except Exception:
-            pass
+        if self.handle:
+            try:
+                if _lib._lib is not None:
+                    self.release()
+            except Exception:
+                pass
+
+
+class _Hot:
+    """bound entry points of the calls a launch loop makes every step (a launch-bound step is ~5 us: attribute lookups count)"""
+
+    __slots__ = ("buffer_release", "do_buffer")
+
+    def __init__(self):
+        self.buffer_release = self.do_buffer = None
+
+
+_HOT = _Hot()
+
+
+def _hot() -> _Hot:
+    L = _L()
+    _HOT.buffer_release, _HOT.do_buffer = L.cc_buffer_release, L.ct_do_buffer
+    return _HOT
 
 
 def reduce_sum(src: Buffer, n_floats: int, dst: Buffer) -> None:
@@ -665,7 +689,9 @@ class Tensor:
 
     def doBuffer(self) -> Buffer:
         h = u64()
-        check(_L().ct_do_buffer(self._h, C.byref(h), None))
+        st = (_HOT.do_buffer or _hot().do_buffer)(self._h, h, None)  # a u64 instance is passed by reference (argtypes: POINTER(u64))
+        if st:
+            check(st)
         return Buffer(h.value)
 
     def compile(self) -> Kernel:
