@@ -1,7 +1,7 @@
 /* A plain-C consumer of include/compute_cuda.h: BASELINE config 1, tanh(a*b+c) on 1024x1024, built and evaluated through the
  * drop-in boundary exactly as a JVM caller would through LWJGL (scalars and pointers only, no C++ types, no Python).
  *
- *   gcc -O2 -std=c11 -Iinclude examples/c1_from_c.c -o /tmp/c1_from_c -Lcompute/scala_b200 -lcompute_cuda -Wl,-rpath,$PWD/compute/scala_b200 -lm
+ *   gcc -O2 -std=c11 -D_POSIX_C_SOURCE=200809L -Iinclude examples/c1_from_c.c -o /tmp/c1_from_c -Lcompute/scala_b200 -lcompute_cuda -Wl,-rpath,$PWD/compute/scala_b200 -lm
  *   /tmp/c1_from_c [steps]
  *
  * Without a GPU it must fail loudly (CC_ERR_NO_DRIVER) — tests/test_abi_and_codegen.py builds and runs it for exactly that.
