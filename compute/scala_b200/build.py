@@ -12,6 +12,9 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libcompute_cuda.so")
 OBJ = os.path.join(HERE, "build")
 
+import sysconfig
+
+HOTCALLS = os.path.join(HERE, "_hotcalls" + (sysconfig.get_config_var("EXT_SUFFIX") or ".so"))
 SOURCES = ["ir.cpp", "codegen.cpp", "driver.cpp", "runtime.cpp", "tensor.cpp", "kernels_basic.cu", "gemm_3xtf32.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
@@ -38,12 +41,29 @@ def _stamp() -> str:
     return h.hexdigest()
 
 
+def _build_hotcalls() -> None:
+    """csrc/py_hotcalls.c -> _hotcalls.<abi>.so: CPython binding of the two per-step calls (cuda.py uses ctypes for everything else, and
+    for these two as well if the interpreter's headers are missing)."""
+    inc = sysconfig.get_paths()["include"]
+    if not os.path.exists(os.path.join(inc, "Python.h")):
+        sys.stderr.write("Python.h not found: cuda.py binds its hot calls through ctypes\n")
+        return
+    cmd = ["gcc", "-O2", "-std=c11", "-shared", "-fPIC", "-Wall", "-I", inc, os.path.join(CSRC, "py_hotcalls.c"), "-o", HOTCALLS,
+           "-L", HERE, "-lcompute_cuda", "-Wl,-rpath,$ORIGIN"]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout)
+        raise RuntimeError("building the _hotcalls extension failed")
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     _embed_templates()
     os.makedirs(OBJ, exist_ok=True)
     stamp_file = os.path.join(OBJ, "stamp")
     stamp = _stamp()
     if not force and os.path.exists(LIB) and os.path.exists(stamp_file) and open(stamp_file).read() == stamp:
+        if not os.path.exists(HOTCALLS):
+            _build_hotcalls()
         return LIB
     objs = []
     procs = []
@@ -70,6 +90,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if r.returncode != 0:
         sys.stderr.write(r.stdout)
         raise RuntimeError("link failed")
+    _build_hotcalls()
     open(stamp_file, "w").write(stamp)
     return LIB
 

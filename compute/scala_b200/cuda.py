@@ -327,9 +327,8 @@ class Buffer:
         h = self.handle
         if h:
             self.handle = 0
-            st = (_HOT.buffer_release or _hot().buffer_release)(h)
-            if st:
-                check(st)
+            if (_HOT.buffer_release or _hot().buffer_release)(h):
+                check(_L().cc_buffer_release(h))  # failed (stale handle): the ctypes call reports the same status with its message
 
     def __del__(self):
         if self.handle:
@@ -353,8 +352,23 @@ _HOT = _Hot()
 
 
 def _hot() -> _Hot:
+    """do_buffer(tensor handle) -> buffer handle or a negative cc_status; buffer_release(buffer handle) -> cc_status.  Bound through the
+    _hotcalls CPython extension (csrc/py_hotcalls.c, ~0.1 us per call) when it is built, else through ctypes (~0.55 us per call);
+    either way the call lands in libcompute_cuda.so."""
     L = _L()
-    _HOT.buffer_release, _HOT.do_buffer = L.cc_buffer_release, L.ct_do_buffer
+    try:
+        from . import _hotcalls
+
+        _HOT.buffer_release, _HOT.do_buffer = _hotcalls.buffer_release, _hotcalls.do_buffer
+    except ImportError:
+        ct_do_buffer = L.ct_do_buffer
+
+        def do_buffer(t: int) -> int:
+            h = u64()
+            st = ct_do_buffer(t, h, None)
+            return st if st else h.value
+
+        _HOT.buffer_release, _HOT.do_buffer = L.cc_buffer_release, do_buffer
     return _HOT
 
 
@@ -688,11 +702,10 @@ class Tensor:
     __str__ = toString
 
     def doBuffer(self) -> Buffer:
-        h = u64()
-        st = (_HOT.do_buffer or _hot().do_buffer)(self._h, h, None)  # a u64 instance is passed by reference (argtypes: POINTER(u64))
-        if st:
-            check(st)
-        return Buffer(h.value)
+        h = (_HOT.do_buffer or _hot().do_buffer)(self._h)
+        if h < 0:
+            check(h)
+        return Buffer(h)
 
     def compile(self) -> Kernel:
         h = u64()

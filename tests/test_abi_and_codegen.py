@@ -534,3 +534,35 @@ def test_kernel_cache_policy():
     cuda.kernel_cache_limit(0)
     cuda.kernel_cache_clear()
     assert cuda.kernel_cache_size() == 0
+
+
+def test_hot_calls_are_bound_natively_and_report_typed_errors(monkeypatch):
+    """doBuffer / Buffer.release go through the _hotcalls CPython extension (csrc/py_hotcalls.c) when it is built and through ctypes
+    otherwise; both land in libcompute_cuda.so and report the same typed errors (no GPU here: the calls must fail loudly)."""
+    import importlib
+    import sys
+
+    def probe():
+        e = cuda.Tensor.fill(1.0, [4, 4]) + cuda.Tensor.fill(2.0, [4, 4])
+        with pytest.raises(cuda.ComputeCudaError) as ei:
+            e.doBuffer()
+        assert "CC_ERR_NOT_INITIALIZED" in str(ei.value) or "CC_ERR_NO_DRIVER" in str(ei.value)
+        stale = cuda.Buffer(0x1234560)
+        with pytest.raises(cuda.IllegalArgumentException):
+            stale.release()
+        assert stale.handle == 0  # a failed release is not retried by __del__
+
+    hot = cuda._hot()
+    assert type(hot.do_buffer).__name__ == "builtin_function_or_method", "the _hotcalls extension is not built (python -m compute.scala_b200.build)"
+    probe()
+    # the ctypes binding of the same two entry points
+    import compute.scala_b200 as package
+
+    monkeypatch.setitem(sys.modules, "compute.scala_b200._hotcalls", None)
+    monkeypatch.delattr(package, "_hotcalls")
+    hot = cuda._hot()
+    assert type(hot.do_buffer).__name__ == "function"
+    probe()
+    monkeypatch.undo()
+    importlib.invalidate_caches()
+    assert type(cuda._hot().do_buffer).__name__ == "builtin_function_or_method"
