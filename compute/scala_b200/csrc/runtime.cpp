@@ -9,7 +9,10 @@
 #include <sys/stat.h>
 #include <unistd.h>
 
+#include <time.h>
+
 #include <algorithm>
+#include <array>
 #include <atomic>
 #include <cstdlib>
 #include <cstring>
@@ -121,6 +124,7 @@ struct Runtime {
   std::vector<CUstream> streams;       // compute streams [0, stream_count), then h2d, d2h, aux
   std::vector<uint64_t> seq;           // commands submitted per stream
   std::vector<std::vector<uint64_t>> synced;  // synced[s][a]: stream s already waits for the first synced[s][a] commands of a
+  std::vector<std::array<uint64_t, 8>> submit_ns;  // host time at which each stream's last 8 commands were submitted (stream affinity)
   size_t next_stream = 0;
   int stream_count = 4;
   int h2d = 0, d2h = 0, aux = 0;       // indices into `streams`
@@ -231,18 +235,34 @@ int pick_stream() {
 }
 
 // Stream choice with affinity. Round-robin over the compute streams (the reference's "5 queues per device", cpu.scala:115) lets
-// independent commands overlap, but a command whose buffers were last touched on ONE stream gains nothing from another: the hazard
-// tracker would serialise it behind that stream with an event record + wait (two driver calls), and kernels on different streams can
-// not use programmatic dependent launch. The typical case is the steady state of a loop: the output block comes back from the pool
-// carrying the mark of the previous iteration's kernel. So: run on the compute stream that needs the fewest cross-stream waits for
-// these buffers; ties (fresh memory, long-synced inputs) rotate as before.
+// independent commands overlap, but a command whose buffers were JUST touched on one compute stream gains nothing from another: the
+// hazard tracker would serialise it behind that stream with an event record + wait (two driver calls), and kernels on different
+// streams cannot use programmatic dependent launch. The typical case is the steady state of a loop: the output block comes back from
+// the pool carrying the mark of the previous iteration's kernel. So: run on the compute stream that needs the fewest cross-stream
+// waits for the HOT hazards of these buffers -- marks among the last 8 commands of a compute stream, submitted a few milliseconds ago at most.
+// Older marks (inputs uploaded or computed long ago) cost a stream one wait ever and must not pin independent work to one stream;
+// marks on the copy streams cannot be avoided by any choice. Ties rotate as before.
+// a cheap monotonic tick for "was this submitted a moment ago": the TSC where there is one (1-4 ticks per ns), else nanoseconds
+uint64_t now_ns() {
+#if defined(__x86_64__)
+  return __builtin_ia32_rdtsc();
+#else
+  timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return (uint64_t)ts.tv_sec * 1000000000ull + (uint64_t)ts.tv_nsec;
+#endif
+}
+constexpr uint64_t kHotHazardTicks = 6000000ull;  // ~2-6 ms of TSC ticks (or 6 ms of nanoseconds)
 int pick_stream_for(const std::vector<Buffer*>& reads, const std::vector<Buffer*>& writes) {
   Runtime& r = rt();
   const int n = r.stream_count;
   if (n <= 1 || n > 32) return pick_stream();
   int cost[32] = {0};
+  uint64_t now = 0;
   auto add = [&](const Mark& m) {
-    if (m.stream < 0) return;
+    if (m.stream < 0 || m.stream >= n || r.seq[(size_t)m.stream] - m.seq >= 8) return;
+    if (!now) now = now_ns();
+    if (now - r.submit_ns[(size_t)m.stream][m.seq & 7] > kHotHazardTicks) return;
     for (int s = 0; s < n; ++s)
       if (m.stream != s && r.synced[(size_t)s][(size_t)m.stream] < m.seq) cost[s]++;
   };
@@ -325,6 +345,7 @@ void op_end(Op& op, cc_event* out_event) {
     op.prof_start = nullptr;
   }
   const uint64_t q = ++r.seq[(size_t)op.stream];
+  if (op.stream < r.stream_count) r.submit_ns[(size_t)op.stream][q & 7] = now_ns();
   for (Buffer* b : op.writes) {
     b->reads.clear();
     b->last_write = Mark{op.stream, q};
@@ -699,6 +720,7 @@ int cc_init(int device_ordinal) {
     r.d2h = r.stream_count + 1;
     r.aux = r.stream_count + 2;
     r.seq.assign(r.streams.size(), 0);
+    r.submit_ns.assign(r.streams.size(), std::array<uint64_t, 8>{});
     r.synced.assign(r.streams.size(), std::vector<uint64_t>(r.streams.size(), 0));
     CC_CU(cuEventCreate(&r.timer0, CU_EVENT_DEFAULT));
     CC_CU(cuEventCreate(&r.timer1, CU_EVENT_DEFAULT));

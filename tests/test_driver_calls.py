@@ -1,0 +1,108 @@
+"""CPU-only: which driver calls the runtime turns a command into.  A driver spy (tests/driver_spy, test infrastructure only: it counts
+calls and executes nothing) stands in front of libcuda for a child process that drives the public API; the counters are the assertion.
+This is the launch path's logic -- stream affinity, hazard events, pooled memory, the programmatic-dependent-launch attribute, the
+structural kernel cache, direct-to-host small results, resource balance on shutdown -- checked where no GPU exists.  No values are
+computed (kernels never run), so nothing here is a parity or performance claim."""
+import hashlib
+import json
+import os
+import subprocess
+import sys
+import tempfile
+
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SPY_SRC = os.path.join(HERE, "driver_spy", "spy_libcuda.c")
+SCENARIOS = os.path.join(HERE, "driver_spy", "scenarios.py")
+
+
+@pytest.fixture(scope="module")
+def spy_dir():
+    key = hashlib.sha1(open(SPY_SRC, "rb").read()).hexdigest()[:16]
+    d = os.path.join(tempfile.gettempdir(), "compute_cuda_driver_spy_" + key)
+    so = os.path.join(d, "libcuda.so.1")
+    if not os.path.exists(so):
+        os.makedirs(d, exist_ok=True)
+        cmd = ["gcc", "-O2", "-Wall", "-Werror", "-shared", "-fPIC", "-I/usr/local/cuda/include", SPY_SRC, "-o", so + ".tmp"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        os.replace(so + ".tmp", so)
+    return d
+
+
+def run(spy_dir, scenario, **env):
+    e = dict(os.environ, LD_LIBRARY_PATH=spy_dir + os.pathsep + os.environ.get("LD_LIBRARY_PATH", ""), **env)
+    e.pop("CC_KERNEL_CACHE_DIR", None)
+    r = subprocess.run([sys.executable, SCENARIOS, scenario], env=e, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, (r.stdout[-2000:], r.stderr[-4000:])
+    return json.loads(r.stdout.strip().splitlines()[-1])
+
+
+def test_a_steady_loop_is_one_launch_per_step_and_nothing_else(spy_dir):
+    """BASELINE config 1 in miniature: the output block returns from the pool carrying the previous step's mark, the step follows it
+    onto the same stream (no event record / wait), the kernel is launched with the dependent-launch attribute, memory comes from the pool"""
+    r = run(spy_dir, "steady_loop")
+    assert r["pdl_launches"] == 100 and r["plain_launches"] == 0 and r["cuLaunchKernelEx"] == 100
+    assert r["streams_launched_on"] == 1
+    assert r["cuEventRecord"] == 0 and r["cuStreamWaitEvent"] == 0
+    assert r["cuMemAlloc"] == 0 and r["alloc_calls"] == 100 and r["pool_hits"] == 100
+    assert r["compiles"] == 0 and r["cuModuleLoadData"] == 0
+    assert r["cuCtxSetCurrent"] <= 200
+
+
+def test_pdl_can_be_switched_off(spy_dir):
+    r = run(spy_dir, "steady_loop", CC_PDL="0")
+    assert r["pdl_launches"] == 0 and r["plain_launches"] == 100
+    assert r.get("cuLaunchKernelEx", 0) == 0 and r["cuLaunchKernel"] == 100
+    assert r["cuEventRecord"] == 0 and r["cuStreamWaitEvent"] == 0
+
+
+def test_independent_commands_still_rotate_over_the_streams(spy_dir):
+    """affinity follows HOT hazards only: eight independent expressions over one long-uploaded input spread over the four compute
+    streams (the reference's several queues per device), each stream paying its one wait for the copy stream"""
+    r = run(spy_dir, "independent_rotate")
+    assert r["pdl_launches"] == 8
+    assert r["streams_launched_on"] == 4
+    assert r["cuEventRecord"] == 4 and r["cuStreamWaitEvent"] == 4
+
+
+def test_hazards_on_uploaded_inputs_cost_one_wait_once(spy_dir):
+    r = run(spy_dir, "first_use_of_uploaded_inputs")
+    # three inputs written by the H2D stream: one event covers all of them
+    assert r["first"]["cuEventRecord"] == 1 and r["first"]["cuStreamWaitEvent"] == 1 and r["first"]["pdl_launches"] == 1
+    assert r["second"]["cuEventRecord"] == 0 and r["second"]["cuStreamWaitEvent"] == 0 and r["second"]["pdl_launches"] == 1
+    assert r["second"]["cuMemAlloc"] == 0
+
+
+def test_small_results_are_stored_by_the_kernel_large_ones_are_copied(spy_dir):
+    r = run(spy_dir, "read_back")
+    assert r["small"]["pdl_launches"] == 1 and r["small"]["cuMemcpyDtoHAsync"] == 0 and r["small"]["cuMemHostAlloc"] == 0
+    assert r["big"]["pdl_launches"] == 1 and r["big"]["cuMemcpyDtoHAsync"] == 1 and r["big"]["cuMemHostAlloc"] == 0
+    assert r["small"]["cuEventSynchronize"] == 1 and r["big"]["cuEventSynchronize"] == 1
+
+
+def test_multi_launch_plans_and_folds_stay_on_their_stream(spy_dir):
+    r = run(spy_dir, "two_launch_plan_and_fold")
+    assert r["axis_launches_per_step"] == 2
+    assert r["axis"]["pdl_launches"] == 100 and r["axis"]["cuEventRecord"] == 0 and r["axis"]["cuStreamWaitEvent"] == 0 and r["axis"]["cuMemAlloc"] == 0
+    assert r["fold"]["pdl_launches"] == 50 and r["fold"]["cuEventRecord"] == 0 and r["fold"]["cuStreamWaitEvent"] == 0
+    assert r["fold"]["cuMemsetD32Async"] == 0  # the fold's block counter resets itself
+
+
+def test_structurally_equal_expressions_share_one_module(spy_dir):
+    r = run(spy_dir, "structural_cache")
+    assert r["compiles"] == 2 and r["cache_hits"] == 1
+    assert r["cuModuleLoadData"] == 2 and r["pdl_launches"] == 3
+
+
+def test_every_driver_resource_is_given_back_on_shutdown(spy_dir):
+    r = run(spy_dir, "balance_on_shutdown")
+    assert r["live_tensors"] == 0
+    assert r["bytes_in_use_before_shutdown"] <= 8192  # the runtime's own fold scratch
+    assert r["cuMemAlloc"] == r["cuMemFree"] > 0
+    assert r["cuMemHostAlloc"] == r["cuMemFreeHost"] > 0
+    assert r["cuStreamCreate"] == r["cuStreamDestroy"] > 0
+    assert r["cuEventCreate"] == r["cuEventDestroy"]
+    assert r["cuModuleLoadData"] == r["cuModuleUnload"] > 0
+    assert r["cuDevicePrimaryCtxRetain"] == r["cuDevicePrimaryCtxRelease"] == 1
