@@ -6,6 +6,8 @@ here and nothing falls back to numpy.
 from __future__ import annotations
 
 import ctypes as C
+import math
+import os
 from typing import Iterable, Sequence
 
 import numpy as np
@@ -208,16 +210,20 @@ class HostBuffer:
     """`flatBuffer`'s result (T:1099-1109): callee-allocated pinned host memory holding the evaluated tensor, valid until
     `release()` (the end of the reference's `Do` scope, O:691-715).  Usable as a context manager."""
 
-    def __init__(self, ptr, n_floats: int):
+    __slots__ = ("_p", "n", "array")
+
+    def __init__(self, ptr: int, view):
         self._p = ptr
-        self.n = int(n_floats)
-        self.array = np.ctypeslib.as_array(ptr, shape=(max(self.n, 1),))[: self.n]
+        self.array = np.frombuffer(view, dtype=np.float32) if len(view) else np.empty(0, dtype=np.float32)
+        self.n = self.array.size
 
     def release(self) -> None:
         if self._p is not None:
             self.array = None
             p, self._p = self._p, None
-            check(_L().ct_flat_buffer_release(p))
+            st = (_HOT.flat_buffer_release or _hot().flat_buffer_release)(p)
+            if st:
+                check(st)
 
     def __enter__(self) -> np.ndarray:
         return self.array
@@ -340,36 +346,69 @@ class Buffer:
 
 
 class _Hot:
-    """bound entry points of the calls a launch loop makes every step (a launch-bound step is ~5 us: attribute lookups count)"""
+    """entry points on per-call hot paths (a launch-bound step is ~3 us, a small read-back ~15: marshalling counts), bound once"""
 
-    __slots__ = ("buffer_release", "do_buffer")
+    __slots__ = ("buffer_release", "do_buffer", "unary", "binary", "tensor_release", "flat_array_into", "flat_buffer", "flat_buffer_release", "native")
 
     def __init__(self):
-        self.buffer_release = self.do_buffer = None
+        for n in self.__slots__:
+            setattr(self, n, None)
 
 
 _HOT = _Hot()
 
 
 def _hot() -> _Hot:
-    """do_buffer(tensor handle) -> buffer handle or a negative cc_status; buffer_release(buffer handle) -> cc_status.  Bound through the
-    _hotcalls CPython extension (csrc/py_hotcalls.c, ~0.1 us per call) when it is built, else through ctypes (~0.55 us per call);
+    """Handle-returning calls give the handle (> 0) or the negative cc_status; the others give the cc_status.  Bound through the
+    _hotcalls CPython extension (csrc/py_hotcalls.c, ~0.1 us per call) when it is built, else through ctypes (>= 0.55 us per call);
     either way the call lands in libcompute_cuda.so."""
     L = _L()
+    H = _HOT
     try:
-        from . import _hotcalls
+        if os.environ.get("CC_PY_NO_HOTCALLS"):  # A/B switch and test hook: bind everything through ctypes
+            raise ImportError("disabled")
+        from . import _hotcalls as X
 
-        _HOT.buffer_release, _HOT.do_buffer = _hotcalls.buffer_release, _hotcalls.do_buffer
+        H.buffer_release, H.do_buffer, H.unary, H.binary, H.tensor_release = X.buffer_release, X.do_buffer, X.unary, X.binary, X.tensor_release
+        H.flat_array_into, H.flat_buffer, H.flat_buffer_release = X.flat_array_into, X.flat_buffer, X.flat_buffer_release
+        H.native = True
     except ImportError:
-        ct_do_buffer = L.ct_do_buffer
+        fp = C.POINTER(C.c_float)
 
         def do_buffer(t: int) -> int:
             h = u64()
-            st = ct_do_buffer(t, h, None)
+            st = L.ct_do_buffer(t, h, None)
             return st if st else h.value
 
-        _HOT.buffer_release, _HOT.do_buffer = L.cc_buffer_release, do_buffer
-    return _HOT
+        def unary(op: int, t: int) -> int:
+            h = u64()
+            st = L.ct_unary(op, t, h)
+            return st if st else h.value
+
+        def binary(op: int, l: int, r: int) -> int:
+            h = u64()
+            st = L.ct_binary(op, l, r, h)
+            return st if st else h.value
+
+        def flat_array_into(t: int, out: np.ndarray) -> int:
+            return L.ct_flat_array(t, out.ctypes.data, out.size)
+
+        def flat_buffer(t: int):
+            p, n = fp(), u64()
+            st = L.ct_flat_buffer(t, C.byref(p), C.byref(n))
+            if st:
+                return st
+            addr = C.cast(p, C.c_void_p).value or 0
+            view = memoryview((C.c_float * n.value).from_address(addr)).cast("B") if n.value else memoryview(b"")
+            return addr, view
+
+        def flat_buffer_release(addr: int) -> int:
+            return L.ct_flat_buffer_release(C.cast(addr, fp))
+
+        H.buffer_release, H.do_buffer, H.unary, H.binary, H.tensor_release = L.cc_buffer_release, do_buffer, unary, binary, L.ct_release
+        H.flat_array_into, H.flat_buffer, H.flat_buffer_release = flat_array_into, flat_buffer, flat_buffer_release
+        H.native = False
+    return H
 
 
 def reduce_sum(src: Buffer, n_floats: int, dst: Buffer) -> None:
@@ -484,9 +523,10 @@ def _flatten(elements):
 class Tensor:
     """`cuda.Tensor` — lazily evaluated N-dimensional float32 array."""
 
-    __slots__ = ("_h", "__weakref__")
+    __slots__ = ("_h", "_shape", "__weakref__")
 
     def __init__(self, elements=None, padding: float = 0.0, *, _handle: int | None = None):
+        self._shape = None
         if _handle is not None:
             self._h = _handle
             return
@@ -499,7 +539,14 @@ class Tensor:
     # -- construction (object Tensor) --
     @staticmethod
     def _wrap(h: u64) -> "Tensor":
-        return Tensor(_handle=h.value)
+        return Tensor._of(h.value)
+
+    @staticmethod
+    def _of(handle: int) -> "Tensor":
+        t = object.__new__(Tensor)
+        t._h = handle
+        t._shape = None
+        return t
 
     @staticmethod
     def scalar(value: float, padding: float = 0.0) -> "Tensor":
@@ -537,15 +584,17 @@ class Tensor:
 
     @staticmethod
     def _un(op: str, t: "Tensor") -> "Tensor":
-        h = u64()
-        check(_L().ct_unary(_UNARY[op], t._h, C.byref(h)))
-        return Tensor._wrap(h)
+        h = (_HOT.unary or _hot().unary)(_UNARY[op], t._h)
+        if h < 0:
+            check(h)
+        return Tensor._of(h)
 
     @staticmethod
     def _bin(op: str, l: "Tensor", r: "Tensor") -> "Tensor":
-        h = u64()
-        check(_L().ct_binary(_BINARY[op], l._h, r._h, C.byref(h)))
-        return Tensor._wrap(h)
+        h = (_HOT.binary or _hot().binary)(_BINARY[op], l._h, r._h)
+        if h < 0:
+            check(h)
+        return Tensor._of(h)
 
     abs = staticmethod(lambda t: Tensor._un("abs", t))
     sqrt = staticmethod(lambda t: Tensor._un("sqrt", t))
@@ -663,11 +712,14 @@ class Tensor:
     # -- properties --
     @property
     def shape(self) -> tuple:
-        r = C.c_int()
-        check(_L().ct_rank(self._h, C.byref(r)))
-        arr = (i32 * max(1, r.value))()
-        check(_L().ct_shape(self._h, arr, r.value))
-        return tuple(arr[i] for i in range(r.value))
+        s = self._shape
+        if s is None:  # a tensor's shape never changes: asked of the library once
+            r = C.c_int()
+            check(_L().ct_rank(self._h, C.byref(r)))
+            arr = (i32 * max(1, r.value))()
+            check(_L().ct_shape(self._h, arr, r.value))
+            s = self._shape = tuple(arr[i] for i in range(r.value))
+        return s
 
     @property
     def padding(self) -> float:
@@ -677,17 +729,18 @@ class Tensor:
 
     # -- slow actions --
     def flatArray(self) -> np.ndarray:
-        n = int(np.prod(self.shape, dtype=np.int64)) if self.shape else 1
-        out = np.empty(n, dtype=np.float32)
-        check(_L().ct_flat_array(self._h, out.ctypes.data, n))
+        out = np.empty(math.prod(self.shape), dtype=np.float32)
+        st = (_HOT.flat_array_into or _hot().flat_array_into)(self._h, out)
+        if st:
+            check(st)
         return out
 
     def flatBuffer(self) -> HostBuffer:
         """evaluate and read back into pooled pinned memory (no pageable staging copy): `with t.flatBuffer() as a: ...`"""
-        p = C.POINTER(C.c_float)()
-        n = u64()
-        check(_L().ct_flat_buffer(self._h, C.byref(p), C.byref(n)))
-        return HostBuffer(p, n.value)
+        r = (_HOT.flat_buffer or _hot().flat_buffer)(self._h)
+        if r.__class__ is int:
+            check(r)
+        return HostBuffer(r[0], r[1])
 
     def flatArrayInto(self, host_ptr: int, capacity_floats: int) -> None:
         check(_L().ct_flat_array(self._h, host_ptr, int(capacity_floats)))
@@ -713,9 +766,12 @@ class Tensor:
         return Kernel(h.value)
 
     def release(self) -> None:
-        if getattr(self, "_h", 0):
-            check(_L().ct_release(self._h))
+        h = getattr(self, "_h", 0)
+        if h:
             self._h = 0
+            st = (_HOT.tensor_release or _hot().tensor_release)(h)
+            if st:
+                check(st)
 
     def __del__(self):
         try:

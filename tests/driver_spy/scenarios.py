@@ -95,6 +95,43 @@ def read_back():
     return {"small": rs, "big": rb}
 
 
+def read_back_values():
+    """the spy's device-to-host copy writes 42.0f into every float it is asked to deliver"""
+    x = leaf([300, 256])
+    e = T.abs(x) + x
+    arr = e.flatArray()
+    hb = e.flatBuffer()
+    in_scope = hb.array
+    out = {"flat_array": [str(arr.dtype), list(arr.shape), float(arr.min()), float(arr.max())],
+           "flat_buffer": [str(in_scope.dtype), list(in_scope.shape), float(in_scope.min()), float(in_scope.max()), hb.n]}
+    hb.release()
+    out["released"] = hb.array is None
+    hb.release()  # idempotent
+    pin = cuda.PinnedArray(300 * 256 + 8)
+    pin.array[:] = -1.0
+    e.flatArrayInto(pin.ptr, 300 * 256)
+    out["into"] = [float(pin.array[: 300 * 256].min()), float(pin.array[: 300 * 256].max()), float(pin.array[300 * 256:].max())]
+    pin.free()
+    small = (leaf([4, 4]) * leaf([4, 4])).flatArray()  # stored by the kernel itself (which never runs here): shape only
+    out["small"] = [str(small.dtype), list(small.shape)]
+    empty = leaf([0, 4])
+    out["empty"] = [list((T.abs(empty)).flatArray().shape), T.abs(empty).flatBuffer().n]
+    with pytest_raises_illegal():
+        T.fill(1.0, [2, 3]) + T.fill(1.0, [4, 5])
+    out["typed_error"] = True
+    out["native_binding"] = bool(cuda._hot().native)
+    return out
+
+
+class pytest_raises_illegal:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, et, ev, tb):
+        assert et is cuda.IllegalArgumentException, et
+        return True
+
+
 def two_launch_plan_and_fold():
     x = leaf([300, 64])
     e = chain(x.split(0))

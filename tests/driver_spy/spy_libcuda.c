@@ -66,6 +66,15 @@ static CUresult s_cuEventCreate(CUevent* e, unsigned f) { COUNT(cuEventCreate); 
 static CUresult s_cuEventElapsedTime(float* ms, CUevent a, CUevent b) { COUNT(cuEventElapsedTime); (void)a, (void)b; *ms = 1.0f; return 0; }
 static CUresult s_cuModuleLoadData(CUmodule* m, const void* img) { COUNT(cuModuleLoadData); (void)img; g_handle += 16; *m = (CUmodule)g_handle; return 0; }
 static CUresult s_cuModuleGetFunction(CUfunction* f, CUmodule m, const char* n) { COUNT(cuModuleGetFunction); (void)m, (void)n; g_handle += 16; *f = (CUfunction)g_handle; return 0; }
+/* a device-to-host copy delivers a recognisable pattern (42.0f in every float), so that a test can tell that the read-back landed in
+ * the caller's memory, whole and at the right place; nothing is computed */
+static CUresult s_cuMemcpyDtoHAsync(void* dst, CUdeviceptr src, size_t bytes, CUstream s) {
+  COUNT(cuMemcpyDtoHAsync);
+  (void)src, (void)s;
+  float* f = (float*)dst;
+  for (size_t i = 0; i < bytes / 4; ++i) f[i] = 42.0f;
+  return 0;
+}
 static CUresult s_cuLaunchHostFunc(CUstream s, CUhostFn fn, void* u) { COUNT(cuLaunchHostFunc); (void)s; fn(u); return 0; }
 static CUresult s_cuGetErrorString(CUresult r, const char** s) { (void)r; *s = "driver spy"; return 0; }
 static CUresult s_cuGetErrorName(CUresult r, const char** s) { (void)r; *s = "SPY"; return 0; }
@@ -90,7 +99,7 @@ static CUresult s_cuLaunchKernelEx(const CUlaunchConfig* cfg, CUfunction f, void
 
 /* ---- everything else: counted, succeeds, does nothing. One trampoline per name so that the count knows who was called. ---- */
 #define GENERIC_LIST(X) \
-  X(cuInit) X(cuDevicePrimaryCtxRelease) X(cuCtxSetCurrent) X(cuCtxSynchronize) X(cuMemFree) X(cuMemcpyHtoDAsync) X(cuMemcpyDtoHAsync) \
+  X(cuInit) X(cuDevicePrimaryCtxRelease) X(cuCtxSetCurrent) X(cuCtxSynchronize) X(cuMemFree) X(cuMemcpyHtoDAsync) \
   X(cuMemcpyDtoDAsync) X(cuMemsetD32Async) X(cuStreamDestroy) X(cuStreamSynchronize) X(cuStreamWaitEvent) X(cuEventDestroy) X(cuEventRecord) \
   X(cuEventSynchronize) X(cuEventQuery) X(cuModuleUnload) X(cuFuncSetAttribute) X(cuTensorMapEncodeTiled) X(cuIpcGetMemHandle) \
   X(cuIpcOpenMemHandle) X(cuIpcCloseMemHandle) X(cuMemcpyHtoD) X(cuMemcpyDtoH)
@@ -106,7 +115,7 @@ GENERIC_LIST(GENERIC)
 #define SPECIFIC_LIST(X) \
   X(cuDeviceGetCount) X(cuDeviceGet) X(cuDevicePrimaryCtxRetain) X(cuDeviceGetAttribute) X(cuDeviceTotalMem) X(cuDeviceGetName) X(cuDriverGetVersion) \
   X(cuMemAlloc) X(cuMemGetInfo) X(cuMemHostAlloc) X(cuMemFreeHost) X(cuMemHostGetDevicePointer) X(cuStreamCreate) X(cuEventCreate) \
-  X(cuEventElapsedTime) X(cuModuleLoadData) X(cuModuleGetFunction) X(cuLaunchHostFunc) X(cuGetErrorString) X(cuGetErrorName) X(cuLaunchKernel) \
+  X(cuEventElapsedTime) X(cuMemcpyDtoHAsync) X(cuModuleLoadData) X(cuModuleGetFunction) X(cuLaunchHostFunc) X(cuGetErrorString) X(cuGetErrorName) X(cuLaunchKernel) \
   X(cuLaunchKernelEx)
 
 CUresult cuGetProcAddress_v2(const char* name, void** fn, int version, cuuint64_t flags, CUdriverProcAddressQueryResult* status) {

@@ -82,6 +82,21 @@ def test_small_results_are_stored_by_the_kernel_large_ones_are_copied(spy_dir):
     assert r["small"]["cuEventSynchronize"] == 1 and r["big"]["cuEventSynchronize"] == 1
 
 
+@pytest.mark.parametrize("binding", ["native", "ctypes"])
+def test_read_backs_land_in_the_callers_memory(spy_dir, binding):
+    """flatArray / flatBuffer / flatArrayInto through the native binding: dtype, length, placement (the spy's copies deliver 42.0f),
+    release semantics, the empty tensor, and a typed error from graph construction"""
+    r = run(spy_dir, "read_back_values", **({"CC_PY_NO_HOTCALLS": "1"} if binding == "ctypes" else {}))
+    assert r["native_binding"] is (binding == "native")
+    assert r["flat_array"] == ["float32", [76800], 42.0, 42.0]
+    assert r["flat_buffer"] == ["float32", [76800], 42.0, 42.0, 76800]
+    assert r["released"] is True
+    assert r["into"] == [42.0, 42.0, -1.0]  # nothing written past the requested floats
+    assert r["small"] == ["float32", [16]]
+    assert r["empty"] == [[0], 0]
+    assert r["typed_error"] is True
+
+
 def test_multi_launch_plans_and_folds_stay_on_their_stream(spy_dir):
     r = run(spy_dir, "two_launch_plan_and_fold")
     assert r["axis_launches_per_step"] == 2
