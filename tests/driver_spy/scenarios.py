@@ -177,6 +177,119 @@ def balance_on_shutdown():
     return {**report(), "live_tensors": live, "bytes_in_use_before_shutdown": in_use}
 
 
+def threads():
+    """calls come from arbitrary threads (ExecutionContext.global, OpenCL.scala:414-416; JMH Threads.MAX, benchmarks.scala:56): eight
+    threads build, evaluate, read back and release concurrently (the native binding releases the GIL around the calls)"""
+    import threading
+
+    a, b = leaf([64, 64]), leaf([64, 64], 2.0)
+    shared = T.tanh(a * b)
+    shared.doBuffer().release()
+    cuda.synchronize()
+    base = cuda.stats()
+    reset()
+    failures = []
+
+    def work(tid):
+        try:
+            for i in range(200):
+                shared.doBuffer().release()                       # one plan, many threads
+                e = T.abs(a + T.fill(float(tid), [64, 64])) * b   # per-thread structure (the literal is part of the key)
+                if i % 4 == 0:
+                    assert e.flatArray().shape == (4096,)
+                elif i % 4 == 1:
+                    e.flatBuffer().release()
+                else:
+                    e.doBuffer().release()
+                e.release()
+        except Exception as ex:  # noqa: BLE001
+            failures.append(repr(ex)[:300])
+
+    ts = [threading.Thread(target=work, args=(t,)) for t in range(8)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join(timeout=120)
+    hung = sum(t.is_alive() for t in ts)
+    cuda.synchronize()
+    s1 = cuda.stats()
+    return {**report(), "failures": failures, "hung": hung, "launches": s1["launches"] - base["launches"], "compiles": s1["compiles"] - base["compiles"],
+            "bytes_in_use_delta": s1["bytes_in_use"] - base["bytes_in_use"], "live_tensors": cuda.live_tensors()}
+
+
+def arm(name: str, skip: int, code: int, times: int = 1) -> None:
+    SPY.spy_arm.argtypes = [ctypes.c_char_p, ctypes.c_long, ctypes.c_int, ctypes.c_long]
+    SPY.spy_arm(name.encode(), skip, code, times)
+
+
+def faults():
+    """one driver entry point is armed to fail in the middle of the work; the scenario keeps going and reports what the caller saw"""
+    case = sys.argv[2]
+    errors, ok = [], 0
+    a, b, c = (leaf([64, 64]) for _ in range(3))
+    e = T.tanh(a * b + c)
+    e.doBuffer().release()
+    cuda.synchronize()
+    base = cuda.stats()["bytes_in_use"]
+
+    def attempt(fn):
+        nonlocal ok
+        try:
+            fn()
+            ok += 1
+        except cuda.ComputeCudaError as ex:
+            errors.append([ex.status, str(ex)[:160]])
+
+    if case == "launch":
+        arm("cuLaunchKernelEx", 12, 719)
+        for _ in range(30):
+            attempt(lambda: e.doBuffer().release())
+    elif case == "module":
+        arm("cuModuleLoadData", 0, 200)
+        f = T.exp(a) - b
+        for _ in range(5):
+            attempt(lambda: f.doBuffer().release())  # the failed load is retried by the next evaluation
+        del f
+    elif case in ("alloc_once", "alloc_always"):
+        arm("cuMemAlloc", 2, 2, 1 if case == "alloc_once" else 1000)  # CUDA_ERROR_OUT_OF_MEMORY
+        def fresh(i):  # new size classes: the input and the result each need a fresh cuMemAlloc
+            x = leaf([128 << i, 32])
+            try:
+                (T.abs(x) + x).doBuffer().release()
+            finally:
+                x.release()
+
+        for i in range(6):
+            attempt(lambda: fresh(i))
+        arm("cuMemAlloc", 0, 2, 0)  # disarm
+    elif case in ("d2h", "sync"):
+        big = leaf([300, 256])
+        g = T.abs(big) + big
+        g.flatArray()
+        arm("cuMemcpyDtoHAsync" if case == "d2h" else "cuEventSynchronize", 1, 719)
+        for _ in range(4):
+            attempt(lambda: g.flatArray())
+        for _ in range(4):
+            attempt(lambda: g.flatBuffer().release())
+        big.release()
+        del g
+    cuda.synchronize()
+    mid = cuda.stats()["bytes_in_use"]
+    after_ok = 0
+    for _ in range(5):  # the runtime is still usable after the failure
+        try:
+            e.doBuffer().release()
+            after_ok += 1
+        except cuda.ComputeCudaError:
+            pass
+    del e
+    a.release(), b.release(), c.release()
+    out = {"errors": errors, "ok": ok, "after_ok": after_ok, "bytes_in_use_base": base, "bytes_in_use_after": mid, "live_tensors": cuda.live_tensors()}
+    cuda.shutdown()
+    out.update(report())
+    return out
+
+
 if __name__ == "__main__":
     cuda.init(0)
     out = globals()[sys.argv[1]]()

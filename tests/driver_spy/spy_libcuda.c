@@ -6,10 +6,14 @@
 #include <string.h>
 
 #define MAX_NAMES 128
-static struct {
+typedef struct {
   char name[48];
   long count;
-} g_counts[MAX_NAMES];
+  /* fault injection (SPY_FAIL=name:skip:code[:times],...): after `skip` successful calls the next `times` calls return `code` */
+  long skip, times;
+  int code;
+} Entry;
+static Entry g_counts[MAX_NAMES];
 static int g_n = 0;
 static long g_pdl_launches = 0, g_plain_launches = 0;
 static uintptr_t g_streams_seen[64];
@@ -17,12 +21,33 @@ static int g_nstreams = 0;
 static uintptr_t g_bump = 0x7000000000ull;
 static uintptr_t g_handle = 0x1000;
 
-static long* counter(const char* name) {
+static Entry* counter(const char* name) {
   for (int i = 0; i < g_n; ++i)
-    if (!strcmp(g_counts[i].name, name)) return &g_counts[i].count;
+    if (!strcmp(g_counts[i].name, name)) return &g_counts[i];
   if (g_n == MAX_NAMES) abort();
-  snprintf(g_counts[g_n].name, sizeof g_counts[g_n].name, "%s", name);
-  return &g_counts[g_n++].count;
+  Entry* e = &g_counts[g_n++];
+  snprintf(e->name, sizeof e->name, "%s", name);
+  const char* spec = getenv("SPY_FAIL");
+  const size_t len = strlen(name);
+  while (spec && *spec) {
+    if (!strncmp(spec, name, len) && spec[len] == ':') {
+      long skip = 0, times = 1;
+      int code = 999;
+      const int got = sscanf(spec + len + 1, "%ld:%d:%ld", &skip, &code, &times);
+      if (got >= 2) e->skip = skip, e->code = code, e->times = got >= 3 ? times : 1;
+      break;
+    }
+    spec = strchr(spec, ',');
+    if (spec) ++spec;
+  }
+  return e;
+}
+static int fault(Entry* e) {  /* called after the count was incremented */
+  if (e->times > 0 && e->count > e->skip) {
+    --e->times;
+    return e->code;
+  }
+  return 0;
 }
 static void saw_stream(void* s) {
   for (int i = 0; i < g_nstreams; ++i)
@@ -32,9 +57,10 @@ static void saw_stream(void* s) {
 
 /* ---- entry points that must hand something back ---- */
 #define COUNT(name) \
-  static long* c_ = NULL; \
+  static Entry* c_ = NULL; \
   if (!c_) c_ = counter(#name); \
-  ++*c_
+  ++c_->count; \
+  { const int f_ = fault(c_); if (f_) return (CUresult)f_; }
 static CUresult s_cuDeviceGetCount(int* n) { COUNT(cuDeviceGetCount); *n = 1; return 0; }
 static CUresult s_cuDeviceGet(CUdevice* d, int o) { COUNT(cuDeviceGet); (void)o; *d = 0; return 0; }
 static CUresult s_cuDevicePrimaryCtxRetain(CUcontext* c, CUdevice d) { COUNT(cuDevicePrimaryCtxRetain); (void)d; *c = (CUcontext)0x1234; return 0; }
@@ -76,8 +102,8 @@ static CUresult s_cuMemcpyDtoHAsync(void* dst, CUdeviceptr src, size_t bytes, CU
   return 0;
 }
 static CUresult s_cuLaunchHostFunc(CUstream s, CUhostFn fn, void* u) { COUNT(cuLaunchHostFunc); (void)s; fn(u); return 0; }
-static CUresult s_cuGetErrorString(CUresult r, const char** s) { (void)r; *s = "driver spy"; return 0; }
-static CUresult s_cuGetErrorName(CUresult r, const char** s) { (void)r; *s = "SPY"; return 0; }
+static CUresult s_cuGetErrorString(CUresult r, const char** s) { *s = r == CUDA_ERROR_OUT_OF_MEMORY ? "out of memory (injected)" : "injected by the driver spy"; return 0; }
+static CUresult s_cuGetErrorName(CUresult r, const char** s) { *s = r == CUDA_ERROR_OUT_OF_MEMORY ? "CUDA_ERROR_OUT_OF_MEMORY" : "CUDA_ERROR_INJECTED"; return 0; }
 static CUresult s_cuLaunchKernel(CUfunction f, unsigned gx, unsigned gy, unsigned gz, unsigned bx, unsigned by, unsigned bz, unsigned smem, CUstream s,
                                  void** params, void** extra) {
   COUNT(cuLaunchKernel);
@@ -105,10 +131,10 @@ static CUresult s_cuLaunchKernelEx(const CUlaunchConfig* cfg, CUfunction f, void
   X(cuIpcOpenMemHandle) X(cuIpcCloseMemHandle) X(cuMemcpyHtoD) X(cuMemcpyDtoH)
 #define GENERIC(name) \
   static CUresult g_##name(void) { \
-    static long* c_ = NULL; \
+    static Entry* c_ = NULL; \
     if (!c_) c_ = counter(#name); \
-    ++*c_; \
-    return 0; \
+    ++c_->count; \
+    return (CUresult)fault(c_); \
   }
 GENERIC_LIST(GENERIC)
 
@@ -136,8 +162,18 @@ int spy_report(char* out, int capacity) {
   if (n < capacity) n += snprintf(out + n, (size_t)(capacity - n), "}");
   return n;
 }
-void spy_reset(void) {
-  for (int i = 0; i < g_n; ++i) g_counts[i].count = 0;
+/* arm a fault from the test itself: after `skip` more successful calls of `name`, the next `times` calls return `code` */
+void spy_arm(const char* name, long skip, int code, long times) {
+  Entry* e = counter(name);
+  e->skip = e->count + skip;
+  e->code = code;
+  e->times = times;
+}
+void spy_reset(void) {  /* counts only: an armed fault keeps counting calls from the process start */
+  for (int i = 0; i < g_n; ++i) {
+    if (g_counts[i].times > 0) g_counts[i].skip -= g_counts[i].count;
+    g_counts[i].count = 0;
+  }
   g_pdl_launches = g_plain_launches = 0;
   g_nstreams = 0;
 }

@@ -31,10 +31,10 @@ def spy_dir():
     return d
 
 
-def run(spy_dir, scenario, **env):
+def run(spy_dir, scenario, *args, **env):
     e = dict(os.environ, LD_LIBRARY_PATH=spy_dir + os.pathsep + os.environ.get("LD_LIBRARY_PATH", ""), **env)
     e.pop("CC_KERNEL_CACHE_DIR", None)
-    r = subprocess.run([sys.executable, SCENARIOS, scenario], env=e, capture_output=True, text=True, timeout=300)
+    r = subprocess.run([sys.executable, SCENARIOS, scenario, *args], env=e, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, (r.stdout[-2000:], r.stderr[-4000:])
     return json.loads(r.stdout.strip().splitlines()[-1])
 
@@ -121,3 +121,62 @@ def test_every_driver_resource_is_given_back_on_shutdown(spy_dir):
     assert r["cuEventCreate"] == r["cuEventDestroy"]
     assert r["cuModuleLoadData"] == r["cuModuleUnload"] > 0
     assert r["cuDevicePrimaryCtxRetain"] == r["cuDevicePrimaryCtxRelease"] == 1
+
+
+def test_eight_threads_share_the_runtime(spy_dir):
+    r = run(spy_dir, "threads")
+    assert r["failures"] == [] and r["hung"] == 0
+    assert r["launches"] == 8 * 200 * 2 and r["pdl_launches"] == 8 * 200 * 2
+    assert r["compiles"] == 8  # one structure per thread, compiled once
+    assert r["bytes_in_use_delta"] == 0
+    assert r["live_tensors"] == 4  # a, b, a * b, shared
+
+
+# ---- fault injection: a driver call fails in the middle of the work (checkErrorCode -> typed exception, OpenCL.scala:251-312) -------------
+CC_ERR_CUDA, CC_ERR_OUT_OF_MEMORY = -4, -9
+
+
+def _balanced(r, failed_allocs=0):
+    assert r["live_tensors"] == 0
+    assert r["bytes_in_use_after"] == r["bytes_in_use_base"], "a failed command leaked device memory"
+    assert r["after_ok"] == 5, "the runtime was not usable after the failure"
+    assert r["cuMemAlloc"] - failed_allocs == r["cuMemFree"]
+    assert r.get("cuMemHostAlloc", 0) == r.get("cuMemFreeHost", 0)
+    assert r["cuEventCreate"] == r["cuEventDestroy"]
+    assert r["cuStreamCreate"] == r["cuStreamDestroy"]
+
+
+def test_a_failed_launch_is_a_typed_error_and_leaks_nothing(spy_dir):
+    r = run(spy_dir, "faults", "launch")
+    assert r["ok"] == 29 and len(r["errors"]) == 1
+    status, msg = r["errors"][0]
+    assert status == CC_ERR_CUDA and "cuLaunchKernelEx" in msg and "(719)" in msg
+    _balanced(r)
+    assert r["cuModuleLoadData"] == r["cuModuleUnload"]
+
+
+def test_a_failed_module_load_is_retried_by_the_next_evaluation(spy_dir):
+    r = run(spy_dir, "faults", "module")
+    assert r["ok"] == 4 and len(r["errors"]) == 1 and r["errors"][0][0] == CC_ERR_CUDA and "cuModuleLoadData" in r["errors"][0][1]
+    _balanced(r)
+    assert r["cuModuleLoadData"] - 1 == r["cuModuleUnload"]  # the failed load produced no module
+
+
+def test_out_of_memory_trims_the_pool_and_retries(spy_dir):
+    r = run(spy_dir, "faults", "alloc_once")
+    assert r["errors"] == [] and r["ok"] == 6  # the caller never saw it (pool trimmed, allocation retried)
+    _balanced(r, failed_allocs=1)
+
+
+def test_persistent_out_of_memory_is_reported_as_such(spy_dir):
+    r = run(spy_dir, "faults", "alloc_always")
+    assert r["ok"] >= 1 and len(r["errors"]) >= 4
+    assert all(st == CC_ERR_OUT_OF_MEMORY and "CUDA_ERROR_OUT_OF_MEMORY" in msg for st, msg in r["errors"])
+    _balanced(r, failed_allocs=2 * len(r["errors"]))  # each failed evaluation tried twice (before and after trimming the pool)
+
+
+@pytest.mark.parametrize("case,entry", [("d2h", "cuMemcpyDtoHAsync"), ("sync", "cuEventSynchronize")])
+def test_a_failed_read_back_is_a_typed_error_and_leaks_nothing(spy_dir, case, entry):
+    r = run(spy_dir, "faults", case)
+    assert r["ok"] == 7 and len(r["errors"]) == 1 and r["errors"][0][0] == CC_ERR_CUDA and entry in r["errors"][0][1]
+    _balanced(r)
