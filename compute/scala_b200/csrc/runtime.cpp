@@ -14,6 +14,7 @@
 #include <algorithm>
 #include <array>
 #include <atomic>
+#include <condition_variable>
 #include <cstdlib>
 #include <cstring>
 #include <map>
@@ -139,6 +140,12 @@ struct Runtime {
   std::unordered_set<Event*> events;
   std::unordered_set<Kernel*> kernels;
   std::unordered_map<std::string, Kernel*> cache;
+  struct InFlight {  // a structure some thread is compiling right now (outside the lock)
+    std::mutex mu;
+    std::condition_variable cv;
+    bool done = false;
+  };
+  std::unordered_map<std::string, std::shared_ptr<InFlight>> compiling;
   uint64_t cache_clock = 0;
   uint64_t cache_limit = 0;  // 0 = unbounded (the reference's default kernelCacheBuilder, Tensors.scala:1267-1277)
   cc_stats_t stats{};
@@ -475,11 +482,11 @@ uint64_t fnv1a(const std::string& s, uint64_t h = 1469598103934665603ull) {
   }
   return h;
 }
-std::string disk_cache_path(const std::string& full_source) {
+std::string disk_cache_path(const std::string& dir, const std::string& full_source) {
   int major = 0, minor = 0;
   nvrtcVersion(&major, &minor);
   const std::string identity = strprintf("nvrtc %d.%d sm_100a fmad lineinfo extra-device-vectorization|%s|", major, minor, cc_version());
-  return strprintf("%s/%016llx.cubin", disk_cache_dir().c_str(), (unsigned long long)fnv1a(full_source, fnv1a(identity)));
+  return strprintf("%s/%016llx.cubin", dir.c_str(), (unsigned long long)fnv1a(full_source, fnv1a(identity)));
 }
 bool disk_cache_load(const std::string& path, const std::string& full_source, std::vector<char>& cubin) {
   FILE* f = fopen(path.c_str(), "rb");
@@ -541,23 +548,22 @@ std::string with_pdl_entries(const std::string& src) {
   return out;
 }
 
-void nvrtc_compile(Kernel& k) {
+// Runs WITHOUT the runtime lock (cc_compile_ex): touches only `k`; `cache_dir` is the on-disk cache directory as it was under the lock
+// ("" = none). Returns true if the cubin came from the on-disk cache.
+bool nvrtc_compile(Kernel& k, const std::string& cache_dir) {
   k.pdl = pdl_enabled();
   k.full_source = std::string("// ") + k.plan.note + "\n" + kJitTemplates + "\n" + (k.pdl ? with_pdl_entries(k.plan.source) : k.plan.source);
   std::string cache_path;
-  if (!disk_cache_dir().empty()) {
-    cache_path = disk_cache_path(k.full_source);
-    if (disk_cache_load(cache_path, k.full_source, k.cubin)) {
-      rt().stats.disk_cache_hits++;
-      return;
-    }
+  if (!cache_dir.empty()) {
+    cache_path = disk_cache_path(cache_dir, k.full_source);
+    if (disk_cache_load(cache_path, k.full_source, k.cubin)) return true;
   }
   nvrtcProgram prog;
   nvrtcResult r = nvrtcCreateProgram(&prog, k.full_source.c_str(), "jit_kernel.cu", 0, nullptr, nullptr);
   CC_REQUIRE(r == NVRTC_SUCCESS, CC_ERR_COMPILE, "nvrtcCreateProgram: %s", nvrtcGetErrorString(r));
   // --minimal (NVRTC >= 12.4) leaves out the texture / runtime-API / lambda support declarations no generated kernel uses: 10-25 %
   // off the JIT time of a small kernel; older compilers reject the option and are asked again without it
-  static bool minimal_ok = true;
+  static std::atomic<bool> minimal_ok{true};
   const char* opts[] = {"--gpu-architecture=sm_100a", "--std=c++17", "--fmad=true", "-lineinfo", "--extra-device-vectorization", "--minimal"};
   r = nvrtcCompileProgram(prog, minimal_ok ? 6 : 5, opts);
   if (r == NVRTC_ERROR_INVALID_OPTION && minimal_ok) {
@@ -578,8 +584,8 @@ void nvrtc_compile(Kernel& k) {
   k.cubin.resize(n);
   nvrtcGetCUBIN(prog, k.cubin.data());
   nvrtcDestroyProgram(&prog);
-  rt().stats.nvrtc_compiles++;
   if (!cache_path.empty()) disk_cache_store(cache_path, k.full_source, k.cubin);
+  return false;
 }
 
 void ensure_loaded(Kernel& k) {
@@ -1106,36 +1112,80 @@ int cc_compile_ex(const void* blob, uint64_t n_bytes, cc_kernel* out, uint64_t* 
       CC_REQUIRE(capacity >= (int)t.params.size(), CC_ERR_ILLEGAL_ARGUMENT, "param id capacity %d < %zu", capacity, t.params.size());
       for (size_t i = 0; i < t.params.size(); ++i) ids_out[i] = t.nodes[t.params[i]].param_id;
     }
-    Lock lock;
+    // The JIT (planning + NVRTC, 40-100 ms) runs OUTSIDE the runtime lock: other threads keep launching, and different structures
+    // compile in parallel (the reference builds programs inside `Do` blocks on its execution context, Tensors.scala:1321-1329).
+    // Threads asking for a structure that is being compiled wait for that compilation instead of starting a second one.
     Runtime& r = rt();
-    auto it = r.cache.find(t.key);
-    if (it != r.cache.end()) {
-      Kernel* k = it->second;
-      k->rc.fetch_add(1);
-      k->last_hit = 1;
-      k->last_use = ++r.cache_clock;
-      r.stats.cache_hits++;
-      *out = (cc_kernel)(uintptr_t)k;
-      return;
-    }
+    std::shared_ptr<Runtime::InFlight> mine;
     DeviceProps dp;
-    dp.contraction = gemm_available() && !getenv("CC_DISABLE_CONTRACTION");
-    if (r.initialized) {
-      dp.sm_count = r.info.sm_count;
-      dp.max_smem = r.info.max_smem_per_block;
+    std::string cache_dir;
+    for (;;) {
+      std::shared_ptr<Runtime::InFlight> theirs;
+      {
+        Lock lock;
+        auto it = r.cache.find(t.key);
+        if (it != r.cache.end()) {
+          Kernel* k = it->second;
+          k->rc.fetch_add(1);
+          k->last_hit = 1;
+          k->last_use = ++r.cache_clock;
+          r.stats.cache_hits++;
+          *out = (cc_kernel)(uintptr_t)k;
+          return;
+        }
+        auto fl = r.compiling.find(t.key);
+        if (fl != r.compiling.end()) {
+          theirs = fl->second;
+        } else {
+          mine = std::make_shared<Runtime::InFlight>();
+          r.compiling.emplace(t.key, mine);
+          cache_dir = disk_cache_dir();
+          dp.contraction = gemm_available() && !getenv("CC_DISABLE_CONTRACTION");
+          if (r.initialized) {
+            dp.sm_count = r.info.sm_count;
+            dp.max_smem = r.info.max_smem_per_block;
+          }
+        }
+      }
+      if (!theirs) break;
+      std::unique_lock<std::mutex> wait(theirs->mu);
+      theirs->cv.wait(wait, [&] { return theirs->done; });
+      // compiled (next lookup hits) or failed (this thread compiles it itself and reports its own error)
     }
+    auto finish = [&](Kernel* ready) {  // under the runtime lock
+      r.compiling.erase(t.key);
+      {
+        std::lock_guard<std::mutex> g(mine->mu);
+        mine->done = true;
+      }
+      mine->cv.notify_all();
+      (void)ready;
+    };
     std::unique_ptr<Kernel> k(new Kernel());
-    k->plan = make_plan(t, dp);
-    k->hash = t.hash;
-    if (!k->plan.launches.empty())
-      nvrtc_compile(*k);
-    else
-      k->full_source = std::string("// ") + k->plan.note + "\n" + k->plan.source;
+    bool disk_hit = false, compiled = false;
+    try {
+      k->plan = make_plan(t, dp);
+      k->hash = t.hash;
+      if (!k->plan.launches.empty()) {
+        disk_hit = nvrtc_compile(*k, cache_dir);
+        compiled = !disk_hit;
+      } else {
+        k->full_source = std::string("// ") + k->plan.note + "\n" + k->plan.source;
+      }
+    } catch (...) {
+      Lock lock;
+      finish(nullptr);
+      throw;
+    }
+    Lock lock;
     r.stats.compiles++;
+    if (disk_hit) r.stats.disk_cache_hits++;
+    if (compiled) r.stats.nvrtc_compiles++;
     Kernel* raw = k.release();
     raw->rc.store(2);  // cache + caller
     raw->last_use = ++r.cache_clock;
     r.kernels.insert(raw);
+    finish(raw);  // (erases by t.key: before the key moves into the cache)
     r.cache.emplace(std::move(t.key), raw);
     evict_kernels();
     *out = (cc_kernel)(uintptr_t)raw;

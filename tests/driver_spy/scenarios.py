@@ -217,6 +217,63 @@ def threads():
             "bytes_in_use_delta": s1["bytes_in_use"] - base["bytes_in_use"], "live_tensors": cuda.live_tensors()}
 
 
+def compile_does_not_block_launches():
+    """one thread JIT-compiles new structures (tens of ms each, outside the runtime lock) while another keeps stepping a cached plan"""
+    import threading
+    import time
+
+    a, b = leaf([64, 64]), leaf([64, 64], 2.0)
+    e = T.tanh(a * b)
+    e.doBuffer().release()
+    stop, worst, steps, compile_ms = [False], [0.0], [0], []
+
+    def stepper():
+        while not stop[0]:
+            t0 = time.perf_counter()
+            e.doBuffer().release()
+            worst[0] = max(worst[0], time.perf_counter() - t0)
+            steps[0] += 1
+
+    th = threading.Thread(target=stepper)
+    th.start()
+    time.sleep(0.02)
+    for i in range(6):
+        big = a
+        for j in range(12):
+            big = T.tanh(big * b + T.fill(float(i * 100 + j), [64, 64]))
+        t0 = time.perf_counter()
+        big.compile().release()
+        compile_ms.append((time.perf_counter() - t0) * 1e3)
+    stop[0] = True
+    th.join()
+    return {"worst_step_ms": worst[0] * 1e3, "steps": steps[0], "compile_ms": compile_ms}
+
+
+def same_structure_from_many_threads():
+    import threading
+
+    a = leaf([64, 64])
+    s0 = cuda.stats()
+    e = T.exp(a) * T.fill(3.0, [64, 64]) - a
+    failures = []
+
+    def work():
+        try:
+            e.doBuffer().release()
+            (T.exp(a) * T.fill(3.0, [64, 64]) - a).doBuffer().release()  # a structurally equal twin built by this thread
+        except Exception as ex:  # noqa: BLE001
+            failures.append(repr(ex)[:200])
+
+    ts = [threading.Thread(target=work) for _ in range(8)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    s1 = cuda.stats()
+    return {**report(), "failures": failures, "compiles": s1["compiles"] - s0["compiles"], "nvrtc_compiles": s1["nvrtc_compiles"] - s0["nvrtc_compiles"],
+            "launches": s1["launches"] - s0["launches"]}
+
+
 def arm(name: str, skip: int, code: int, times: int = 1) -> None:
     SPY.spy_arm.argtypes = [ctypes.c_char_p, ctypes.c_long, ctypes.c_int, ctypes.c_long]
     SPY.spy_arm(name.encode(), skip, code, times)

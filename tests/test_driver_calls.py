@@ -132,6 +132,19 @@ def test_eight_threads_share_the_runtime(spy_dir):
     assert r["live_tensors"] == 4  # a, b, a * b, shared
 
 
+def test_the_jit_runs_outside_the_runtime_lock(spy_dir):
+    """a thread stepping a cached plan is not held up by another thread's NVRTC compilations (Tensors.scala:1321-1329 builds programs
+    asynchronously too); a structure requested by eight threads at once is compiled once"""
+    r = run(spy_dir, "compile_does_not_block_launches")
+    assert min(r["compile_ms"]) > 20.0, r  # the compilations were real
+    assert r["worst_step_ms"] < 0.5 * min(r["compile_ms"]), r  # no step waited for one
+    assert r["steps"] > 1000
+    r = run(spy_dir, "same_structure_from_many_threads")
+    assert r["failures"] == []
+    assert r["compiles"] == 1 and r["nvrtc_compiles"] == 1 and r["cuModuleLoadData"] == 1
+    assert r["launches"] == 16 and r["pdl_launches"] == 16
+
+
 # ---- fault injection: a driver call fails in the middle of the work (checkErrorCode -> typed exception, OpenCL.scala:251-312) -------------
 CC_ERR_CUDA, CC_ERR_OUT_OF_MEMORY = -4, -9
 
