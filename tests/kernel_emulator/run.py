@@ -23,9 +23,13 @@ def launches_of(cuda, kernel):
     L = cuda._L()
     L.cc_kernel_launch_info.argtypes = [C.c_uint64, C.c_int, C.POINTER(LaunchInfo)]
     out = []
-    for i in range(kernel.info.n_launches):
+    info = kernel.info
+    for i in range(info.n_launches):
         li = LaunchInfo()
-        cuda.check(L.cc_kernel_launch_info(kernel.handle, i, C.byref(li)))
+        st = L.cc_kernel_launch_info(kernel.handle, i, C.byref(li))
+        if st != 0 and info.kind == 2:
+            break  # a contraction's n_launches also counts the precompiled tcgen05 kernels, which have no generated entry
+        cuda.check(st)
         out.append(li)
     return out
 
@@ -72,12 +76,35 @@ def _build(source: str, launches) -> C.CDLL:
     return C.CDLL(so)
 
 
+def _call(lib, i, li, args, out, scratch, partials, counter):
+    ptrs = (C.c_void_p * li.n_args)()
+    for j in range(li.n_args):
+        a = li.args[j]
+        if a >= 0:
+            ptrs[j] = args[a].ctypes.data
+        elif a == ARG_OUT:
+            ptrs[j] = out.ctypes.data
+        elif a == ARG_PARTIALS:
+            ptrs[j] = partials.ctypes.data
+        elif a == ARG_COUNTER:
+            ptrs[j] = counter.ctypes.data
+        else:
+            ptrs[j] = scratch[ARG_SCRATCH0 - a].ctypes.data
+    fn = getattr(lib, f"emu_launch_{i}")
+    fn.argtypes = [C.POINTER(C.c_void_p)]
+    fn.restype = None
+    fn(ptrs)
+
+
 def emulate(cuda, expr, leaf_arrays, max_threads=1 << 16):
-    """Runs the plan `expr` compiles to on host threads. leaf_arrays[j] = data of the plan's j-th buffer argument."""
+    """Runs the plan `expr` compiles to on host threads. leaf_arrays[j] = data of the plan's j-th buffer argument.
+    A contraction over gathered operand panels (kind 2 with generated panel kernels) runs its generated kernels here -- the panel
+    gathers with their bounds tests / padding / TF32 split, and the in-place epilogue -- around a float64 product of the hi + lo panels
+    standing in for the tcgen05 pipeline (which the GPU tier tests on its own); the precompiled plain contraction is not emulated."""
     k = expr.compile()
     info = k.info
-    assert info.kind != 2, "the tensor-core contraction is not emulated"
     launches = launches_of(cuda, k)
+    assert info.kind != 2 or launches, "the precompiled tensor-core contraction is not emulated"
     total = sum(int(np.prod(list(li.grid))) * int(np.prod(list(li.block))) for li in launches)
     assert total <= max_threads, f"{total} CUDA threads: too large for the host emulation"
     lib = _build(k.source, launches)
@@ -85,26 +112,30 @@ def emulate(cuda, expr, leaf_arrays, max_threads=1 << 16):
     assert len(args) == info.n_args
     out = np.full(max(int(info.out_floats), 1) + 16, np.float32(-12345.0), np.float32)  # guard words past the end
     scratch = [np.zeros(int(n) + 16, np.float32) for n in list(launches[0].scratch_floats)[: launches[0].n_scratch]] if launches else []
+    for sbuf in scratch:
+        sbuf[-16:] = np.float32(-54321.0)
     partials = np.zeros(FOLD_PARTIALS + 16, np.float32)
     counter = np.zeros(4, np.uint32)
-    for i, li in enumerate(launches):
-        ptrs = (C.c_void_p * li.n_args)()
-        for j in range(li.n_args):
-            a = li.args[j]
-            if a >= 0:
-                ptrs[j] = args[a].ctypes.data
-            elif a == ARG_OUT:
-                ptrs[j] = out.ctypes.data
-            elif a == ARG_PARTIALS:
-                ptrs[j] = partials.ctypes.data
-            elif a == ARG_COUNTER:
-                ptrs[j] = counter.ctypes.data
-            else:
-                ptrs[j] = scratch[ARG_SCRATCH0 - a].ctypes.data
-        fn = getattr(lib, f"emu_launch_{i}")
-        fn.argtypes = [C.POINTER(C.c_void_p)]
-        fn.restype = None
-        fn(ptrs)
     n = int(info.out_floats)
+    if info.kind == 2:
+        m = re.search(r"general contraction (\d+)x(\d+)x(\d+) over gathered operand panels", k.source)
+        assert m, "not a gathered-panel contraction"
+        M, N, K = (int(g) for g in m.groups())
+        Kp = (K + 31) // 32 * 32
+        assert [li.entry.decode() for li in launches[:2]] == ["panel_a", "panel_b"] and M * N == n
+        _call(lib, 0, launches[0], args, out, scratch, partials, counter)
+        _call(lib, 1, launches[1], args, out, scratch, partials, counter)
+        a_hi, a_lo, b_hi, b_lo = (sc[: rows * Kp].reshape(rows, Kp).astype(np.float64) for sc, rows in zip(scratch, (M, M, N, N)))
+        for sc in scratch:
+            assert (sc[-16:] == np.float32(-54321.0)).all(), "a panel kernel wrote past its panel"
+        assert not a_hi[:, K:].any() and not a_lo[:, K:].any() and not b_hi[:, K:].any() and not b_lo[:, K:].any(), "K padding must be zero"
+        for hi in (a_hi, b_hi):  # hi parts are exactly TF32 (10 explicit mantissa bits)
+            assert not (hi.astype(np.float32).view(np.uint32) & 0x1FFF).any()
+        out[:n] = ((a_hi + a_lo) @ (b_hi + b_lo).T).astype(np.float32).reshape(-1)
+        for i in range(2, len(launches)):
+            _call(lib, i, launches[i], args, out, scratch, partials, counter)
+    else:
+        for i, li in enumerate(launches):
+            _call(lib, i, li, args, out, scratch, partials, counter)
     assert (out[n:] == np.float32(-12345.0)).all(), "the kernel wrote past its output"
     return out[:n], k
