@@ -1805,13 +1805,20 @@ bool try_general_contraction(Plan& plan, const Program& p, int n_args) {
       if (L.M[(size_t)y * (nd + 1) + x] != 0.0) return true;
     return false;
   };
+  // Leading output dims BOTH operands depend on are batch dims: `C[b, i, k] = sum_t A[b, i, t] * B[b, t, k]` is `batch` independent
+  // products over panels that carry the batch index in their rows. (Opt-in until it has been through the GPU tier:
+  // CC_BATCHED_CONTRACTION=1; without it such terms stay on the generic re-rolled reduction.)
+  int nb = 0;
+  if (const char* ev = getenv("CC_BATCHED_CONTRACTION"))
+    if (atoi(ev) != 0)
+      while (nb < no - 2 && uses(p.loads[la], nb) && uses(p.loads[lb], nb)) ++nb;
   auto split_point = [&](const Load& A, const Load& B) {
-    // dims [0, s) not used by B, dims [s, no) not used by A
-    int s = 0;
+    // dims [nb, s) not used by B, dims [s, no) not used by A
+    int s = nb;
     while (s < no && !uses(B, s)) ++s;
     for (int x = s; x < no; ++x)
       if (uses(A, x)) return -1;
-    return (s >= 1 && s < no) ? s : -1;
+    return (s >= nb + 1 && s < no) ? s : -1;
   };
   int s = split_point(p.loads[la], p.loads[lb]);
   if (s < 0) {
@@ -1819,8 +1826,9 @@ bool try_general_contraction(Plan& plan, const Program& p, int n_args) {
     s = split_point(p.loads[la], p.loads[lb]);
     if (s < 0) return false;
   }
-  int64_t M = 1, N = 1, K = 1;
-  for (int x = 0; x < s; ++x) M *= p.dims[x];
+  int64_t BATCH = 1, M = 1, N = 1, K = 1;
+  for (int x = 0; x < nb; ++x) BATCH *= p.dims[x];
+  for (int x = nb; x < s; ++x) M *= p.dims[x];
   for (int x = s; x < no; ++x) N *= p.dims[x];
   for (int x = no; x < nd; ++x) K *= p.dims[x];
   int64_t min_macs = (int64_t)1 << 25;
@@ -1828,9 +1836,10 @@ bool try_general_contraction(Plan& plan, const Program& p, int n_args) {
   // the gathered panels cost 8 bytes of HBM traffic per (row, k) each way, so this pays off when N (the reuse of an A row) is large
   if (M * N * K < min_macs || N < 32 || K < 32 || M >= ((int64_t)1 << 31) || N >= ((int64_t)1 << 31) || K >= ((int64_t)1 << 31) - 32) return false;
   const int64_t Kp = (K + 31) / 32 * 32;
-  if (M * Kp >= ((int64_t)1 << 40)) return false;
-  std::vector<int> m_dims, n_dims;
+  if (BATCH * M * Kp >= ((int64_t)1 << 40) || BATCH * N * Kp >= ((int64_t)1 << 40) || BATCH > 65535) return false;
+  std::vector<int> m_dims, n_dims;  // the rows of a panel: batch dims first, so batch b's rows are one contiguous block
   for (int x = 0; x < s; ++x) m_dims.push_back(x);
+  for (int x = 0; x < nb; ++x) n_dims.push_back(x);
   for (int x = s; x < no; ++x) n_dims.push_back(x);
   Emit e;
   emit_panel_kernel(e, p, "panel_a", la, m_dims, n_args);
@@ -1847,22 +1856,24 @@ bool try_general_contraction(Plan& plan, const Program& p, int n_args) {
     for (int a : extra) ls.args.push_back(a);
     plan.launches.push_back(ls);
   };
-  if (M * (Kp / 4) + 255 >= ((int64_t)1 << 31) * 256) return false;
-  add("panel_a", M * (Kp / 4), {ARG_SCRATCH0, ARG_SCRATCH0 - 1});
-  add("panel_b", N * (Kp / 4), {ARG_SCRATCH0 - 2, ARG_SCRATCH0 - 3});
+  if (BATCH * M * (Kp / 4) + 255 >= ((int64_t)1 << 31) * 256 || BATCH * N * (Kp / 4) + 255 >= ((int64_t)1 << 31) * 256) return false;
+  add("panel_a", BATCH * M * (Kp / 4), {ARG_SCRATCH0, ARG_SCRATCH0 - 1});
+  add("panel_b", BATCH * N * (Kp / 4), {ARG_SCRATCH0 - 2, ARG_SCRATCH0 - 3});
   if (has_post) {
     const int V = (p.dims[no - 1] % 4 == 0) ? 4 : 1;
-    add("post_kernel", M * N / V, {ARG_OUT});
+    add("post_kernel", BATCH * M * N / V, {ARG_OUT});
   }
   plan.kind = PLAN_CONTRACTION;
   plan.M = M;
   plan.N = N;
   plan.K = K;
   plan.gathered_panels = true;
-  plan.flops = 2ull * (uint64_t)M * (uint64_t)N * (uint64_t)K;
-  plan.scratch_floats = {(uint64_t)(M * Kp), (uint64_t)(M * Kp), (uint64_t)(N * Kp), (uint64_t)(N * Kp)};
+  plan.batch = BATCH;
+  plan.flops = 2ull * (uint64_t)BATCH * (uint64_t)M * (uint64_t)N * (uint64_t)K;
+  plan.scratch_floats = {(uint64_t)(BATCH * M * Kp), (uint64_t)(BATCH * M * Kp), (uint64_t)(BATCH * N * Kp), (uint64_t)(BATCH * N * Kp)};
   plan.note += strprintf("; general contraction %lldx%lldx%lld over gathered operand panels -> tcgen05 3xTF32%s", (long long)M, (long long)N,
                          (long long)K, has_post ? " + in-place epilogue" : "");
+  if (BATCH > 1) plan.note += strprintf(" (batch of %lld)", (long long)BATCH);
   return true;
 }
 

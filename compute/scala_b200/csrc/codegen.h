@@ -44,6 +44,7 @@ struct Plan {
   // contraction whose K-major hi / lo operand panels are written by generated kernels (launches[0] = panel_a, [1] = panel_b,
   // optional [2] = post_kernel applied in place to the result) instead of the precompiled split kernels
   bool gathered_panels = false;
+  int64_t batch = 1;  // gathered panels only: leading output dims both operands depend on = that many independent M x N x K products
   std::string note;             // human-readable description of the choices made (kept in the kernel source header)
 };
 

@@ -1457,9 +1457,13 @@ int cc_launch(cc_kernel h, const cc_buffer* args, int n_args, cc_buffer out, con
         op_begin(op, waits, n_waits);
         launch_spec(0, scratch, nullptr, op.cu());
         launch_spec(1, scratch, nullptr, op.cu());
-        GemmWorkspace ws{(float*)scratch[0]->ptr, (float*)scratch[1]->ptr, (float*)scratch[2]->ptr, (float*)scratch[3]->ptr};
-        r.stats.device_kernels += (uint64_t)launch_gemm_3xtf32_panels((float*)ob->ptr, p.M, p.N, p.K, ws, r.info.sm_count,
-                                                                      (TensorMapEncodeFn)driver().cuTensorMapEncodeTiled, (cudaStream_t)op.cu());
+        const int64_t Kp = (p.K + 31) / 32 * 32;
+        for (int64_t b = 0; b < p.batch; ++b) {  // batch b: rows [b*M, (b+1)*M) of A's panels, [b*N, (b+1)*N) of B's, block b of the result
+          GemmWorkspace ws{(float*)scratch[0]->ptr + b * p.M * Kp, (float*)scratch[1]->ptr + b * p.M * Kp, (float*)scratch[2]->ptr + b * p.N * Kp,
+                           (float*)scratch[3]->ptr + b * p.N * Kp};
+          r.stats.device_kernels += (uint64_t)launch_gemm_3xtf32_panels((float*)ob->ptr + b * p.M * p.N, p.M, p.N, p.K, ws, r.info.sm_count,
+                                                                        (TensorMapEncodeFn)driver().cuTensorMapEncodeTiled, (cudaStream_t)op.cu());
+        }
         if (p.launches.size() > 2) launch_spec(2, scratch, nullptr, op.cu());
         r.stats.launches++;
         op_end(op, out_event);

@@ -121,17 +121,20 @@ def emulate(cuda, expr, leaf_arrays, max_threads=1 << 16):
         m = re.search(r"general contraction (\d+)x(\d+)x(\d+) over gathered operand panels", k.source)
         assert m, "not a gathered-panel contraction"
         M, N, K = (int(g) for g in m.groups())
+        mb = re.search(r"\(batch of (\d+)\)", k.source)
+        batch = int(mb.group(1)) if mb else 1
         Kp = (K + 31) // 32 * 32
-        assert [li.entry.decode() for li in launches[:2]] == ["panel_a", "panel_b"] and M * N == n
+        assert [li.entry.decode() for li in launches[:2]] == ["panel_a", "panel_b"] and batch * M * N == n
         _call(lib, 0, launches[0], args, out, scratch, partials, counter)
         _call(lib, 1, launches[1], args, out, scratch, partials, counter)
-        a_hi, a_lo, b_hi, b_lo = (sc[: rows * Kp].reshape(rows, Kp).astype(np.float64) for sc, rows in zip(scratch, (M, M, N, N)))
+        a_hi, a_lo, b_hi, b_lo = (sc[: batch * rows * Kp].reshape(batch * rows, Kp).astype(np.float64) for sc, rows in zip(scratch, (M, M, N, N)))
         for sc in scratch:
             assert (sc[-16:] == np.float32(-54321.0)).all(), "a panel kernel wrote past its panel"
         assert not a_hi[:, K:].any() and not a_lo[:, K:].any() and not b_hi[:, K:].any() and not b_lo[:, K:].any(), "K padding must be zero"
         for hi in (a_hi, b_hi):  # hi parts are exactly TF32 (10 explicit mantissa bits)
             assert not (hi.astype(np.float32).view(np.uint32) & 0x1FFF).any()
-        out[:n] = ((a_hi + a_lo) @ (b_hi + b_lo).T).astype(np.float32).reshape(-1)
+        a, bt = (a_hi + a_lo).reshape(batch, M, Kp), (b_hi + b_lo).reshape(batch, N, Kp)  # batch b: its own block of rows in each panel
+        out[:n] = np.einsum("bmk,bnk->bmn", a, bt).astype(np.float32).reshape(-1)
         for i in range(2, len(launches)):
             _call(lib, i, launches[i], args, out, scratch, partials, counter)
     else:

@@ -236,3 +236,32 @@ def test_full_size_8192_rows_sampled(cuda):
     assert total == float(a.astype(np.float64).sum(axis=0) @ b.astype(np.float64).sum(axis=1))
     for x in (ab, bb, cb):
         x.release()
+
+
+@pytest.mark.skipif(not __import__("os").environ.get("CC_TEST_BATCHED"), reason="opt-in lowering (CC_BATCHED_CONTRACTION=1): run with CC_TEST_BATCHED=1 once it is being validated on a GPU")
+@pytest.mark.parametrize("b,m,k,n", [(3, 128, 96, 256), (8, 200, 130, 72), (2, 512, 512, 512)])
+def test_batched_matmul_lowers_to_one_pipeline_launch_per_batch(cuda, monkeypatch, b, m, k, n):
+    """C[b, i, k] = sum_t A[b, i, t] * B[b, t, k] (matmul2 with a leading batch dim): batch dims go into the rows of both operand
+    panels and the tcgen05 pipeline runs once per batch on its block of rows.  Exact on small integers.  The panel gathers and the
+    per-batch blocking are checked on the CPU tier (tests/test_kernel_emulation.py); this is the device half."""
+    monkeypatch.setenv("CC_BATCHED_CONTRACTION", "1")
+    monkeypatch.setenv("CC_TUNE_CONTRACTION_MIN_MACS", "1")
+    cuda.kernel_cache_clear()
+    try:
+        rng = np.random.default_rng(b * 1000 + m)
+        A = rng.integers(-4, 5, (b, m, k)).astype(np.float32)
+        B = rng.integers(-4, 5, (b, k, n)).astype(np.float32)
+        T = cuda.Tensor
+        a4 = T(A).broadcast([b, m, k, n])
+        b4 = T(B).reshape([b, 1, k, n]).broadcast([b, m, k, n])
+        parts = (a4 * b4).split(2)
+        acc = parts[0]
+        for p in parts[1:]:
+            acc = acc + p
+        kern = acc.compile()
+        assert kern.info.kind == 2 and f"(batch of {b})" in kern.source
+        got = acc.flatArray().reshape(b, m, n)
+        want = np.einsum("bmk,bkn->bmn", A.astype(np.int64), B.astype(np.int64)).astype(np.float32)
+        assert np.array_equal(got, want)
+    finally:
+        cuda.kernel_cache_clear()

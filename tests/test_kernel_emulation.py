@@ -158,6 +158,18 @@ def test_general_contraction_panels_and_epilogue(monkeypatch):
             b3 = b.translate([1, 0]).reshape([1, 40, 64]).broadcast([36, 40, 64])
             return chain((a3 * b3).split(1))
         check(matmul_over_views, "over gathered operand panels", 2)
+
+        # batched matmul C[b, i, k] = sum_t A[b, i, t] * B[b, t, k]: opt-in (CC_BATCHED_CONTRACTION=1) until it has run on the GPU tier
+        def batched(B, leaf):
+            a, b = leaf([3, 36, 40], 6), leaf([3, 40, 64], 7)
+            a4 = a.broadcast([3, 36, 40, 64])
+            b4 = b.reshape([3, 1, 40, 64]).broadcast([3, 36, 40, 64])
+            return chain((a4 * b4).split(2))
+        check(batched, "column owner", 1)  # off by default: the generic re-rolled reduction
+        monkeypatch.setenv("CC_BATCHED_CONTRACTION", "1")
+        cuda.kernel_cache_clear()
+        check(batched, "(batch of 3)", 2)
+        monkeypatch.delenv("CC_BATCHED_CONTRACTION")
     finally:
         monkeypatch.delenv("CC_TUNE_CONTRACTION_MIN_MACS")
         cuda.kernel_cache_clear()
