@@ -1560,7 +1560,13 @@ void emit_reduce(Plan& plan, const Program& p, int n_args, const DeviceProps& de
     const int64_t TCHb = S > 1 ? (T + Sb - 1) / Sb : T;         // rows per CTA
     const int64_t Sy = S > 1 ? (T + TCHb - 1) / TCHb : 1;       // partials per output
     const int CW = S > 1 ? 64 : 256;                            // column vectors per CTA
-    e("extern \"C\" __global__ void __launch_bounds__(256) reduce_cols(%s) {\n", param_list(n_args, true, "dst").c_str());
+    // Opt-in (CC_FUSE_COL_STAGE=1, until it has been timed on a GPU): the second stage runs inside reduce_cols -- the last CTA to
+    // finish a block of columns (a self-resetting counter per blockIdx.x) folds that block's partials, so the plan is one launch.
+    const int64_t gridx = (NV + CW - 1) / CW;
+    bool fused = false;
+    if (const char* ev = getenv("CC_FUSE_COL_STAGE")) fused = atoi(ev) != 0 && Sy > 1 && gridx <= kColCounters;
+    e("extern \"C\" __global__ void __launch_bounds__(256) reduce_cols(%s%s) {\n", param_list(n_args, true, "dst").c_str(),
+      fused ? ", float* __restrict__ out, unsigned* __restrict__ counters" : "");
     if (S == 1) {
       e("  const %s v = (%s)blockIdx.x * 256 + threadIdx.x;\n  if (v >= %lld) return;\n", IDX, IDX, (long long)NV);
     } else {
@@ -1598,10 +1604,34 @@ void emit_reduce(Plan& plan, const Program& p, int n_args, const DeviceProps& de
       e("  if (live) {\n    #pragma unroll 4\n    for (int t = t0 + qy; t < t1; t += %d) {\n      float x[%d];\n      ev(t%s%s, x);\n", QS, V, gs.c_str(), pass.c_str());
       e("      #pragma unroll\n      for (int l = 0; l < %d; ++l) acc[l] = %s;\n    }\n  }\n", V, AP("acc[l]", "x[l]").c_str());
       e("  if (qy > 0) {\n    #pragma unroll\n    for (int l = 0; l < %d; ++l) comb[qy - 1][cx][l] = acc[l];\n  }\n  __syncthreads();\n", V);
-      e("  if (qy > 0 || !live) return;\n");
-      e("  #pragma unroll\n  for (int q = 0; q < %d; ++q)\n    #pragma unroll\n    for (int l = 0; l < %d; ++l) acc[l] = %s;\n", QS - 1, V, AP("acc[l]", "comb[q][cx][l]").c_str());
-      if (Sy == 1 && has_post) e("  post(acc%s%s);\n", gs.c_str(), pass.c_str());  // the sub-splits of one CTA covered all of T
-      e("  float* d = dst + (%s)blockIdx.y * %lld + v * %d;\n", "long long", (long long)NOUT, V);
+      const std::string combine = strprintf("  #pragma unroll\n  for (int q = 0; q < %d; ++q)\n    #pragma unroll\n    for (int l = 0; l < %d; ++l) acc[l] = %s;\n", QS - 1, V,
+                                            AP("acc[l]", "comb[q][cx][l]").c_str());
+      if (!fused) {
+        e("  if (qy > 0 || !live) return;\n");
+        e("%s", combine.c_str());
+        if (Sy == 1 && has_post) e("  post(acc%s%s);\n", gs.c_str(), pass.c_str());  // the sub-splits of one CTA covered all of T
+        e("  float* d = dst + (%s)blockIdx.y * %lld + v * %d;\n", "long long", (long long)NOUT, V);
+      } else {
+        // stage 1: this CTA's partial (plain stores: they are read back through L2 by another SM in a moment)
+        e("  if (qy == 0 && live) {\n%s", combine.c_str());
+        e("    float* d = dst + (long long)blockIdx.y * %lld + v * %d;\n    #pragma unroll\n    for (int l = 0; l < %d; ++l) d[l] = acc[l];\n  }\n", (long long)NOUT, V, V);
+        e("  __threadfence();\n  __syncthreads();\n  __shared__ unsigned last_;\n");
+        e("  if (threadIdx.x == 0) last_ = atomicAdd(counters + blockIdx.x, 1u) == gridDim.y - 1 ? 1u : 0u;\n  __syncthreads();\n  if (!last_) return;\n  __threadfence();\n");
+        // stage 2 (last CTA of this column block): the %lld partials, sub-split s takes partials s, s + QS, ...; combined in a fixed order
+        e("  #pragma unroll\n  for (int l = 0; l < %d; ++l) acc[l] = %s;\n", V, ZERO);
+        e("  if (live) {\n    #pragma unroll 4\n    for (int s = qy; s < %lld; s += %d) {\n      const float* q_ = dst + (long long)s * %lld + v * %d;\n      float x[%d];\n", (long long)Sy, QS,
+          (long long)NOUT, V, V);
+        if (V == 4)
+          e("      { const float4 t_ = __ldcg(reinterpret_cast<const float4*>(q_)); x[0] = t_.x; x[1] = t_.y; x[2] = t_.z; x[3] = t_.w; }\n");
+        else
+          e("      x[0] = __ldcg(q_);\n");
+        e("      #pragma unroll\n      for (int l = 0; l < %d; ++l) acc[l] = %s;\n    }\n  }\n", V, AP("acc[l]", "x[l]").c_str());
+        e("  if (qy > 0) {\n    #pragma unroll\n    for (int l = 0; l < %d; ++l) comb[qy - 1][cx][l] = acc[l];\n  }\n  __syncthreads();\n", V);
+        e("  if (threadIdx.x == 0) counters[blockIdx.x] = 0u;  // ready for the next launch on this stream\n");
+        e("  if (qy > 0 || !live) return;\n%s", combine.c_str());
+        if (has_post) e("  post(acc%s%s);\n", gs.c_str(), pass.c_str());
+        e("  float* d = out + v * %d;\n", V);
+      }
     }
     if (V == 4)
       e("  cc_stg4(d, acc);\n");
@@ -1615,8 +1645,14 @@ void emit_reduce(Plan& plan, const Program& p, int n_args, const DeviceProps& de
     ls.block[0] = 256;
     for (int i = 0; i < n_args; ++i) ls.args.push_back(i);
     ls.args.push_back(Sy == 1 ? ARG_OUT : ARG_SCRATCH0);
+    if (fused) {
+      ls.args.push_back(ARG_OUT);
+      ls.args.push_back(ARG_COL_COUNTERS);
+      plan.scratch_floats.push_back((uint64_t)(Sy * NOUT));
+      plan.note += "; second stage fused into reduce_cols (last CTA per column block)";
+    }
     plan.launches.push_back(ls);
-    S = Sy;  // what the second stage folds
+    S = fused ? 1 : Sy;  // what the second-stage kernel folds
     if (S > 1) {
       plan.scratch_floats.push_back((uint64_t)(S * NOUT));
       e("extern \"C\" __global__ void __launch_bounds__(256) reduce_partials(const float* __restrict__ part, float* __restrict__ out%s) {\n",

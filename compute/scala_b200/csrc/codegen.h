@@ -17,8 +17,11 @@ enum {
   ARG_SCRATCH0 = -2 /* -2-k = scratch k */,
   // PLAN_FULL_REDUCE: the runtime's shared partials buffer and its self-resetting block counter (serialised on stream 0)
   ARG_REDUCE_PARTIALS = -100,
-  ARG_REDUCE_COUNTER = -101
+  ARG_REDUCE_COUNTER = -101,
+  // fused second stage of a split axis reduction (opt-in): self-resetting per-stream block counters, one per blockIdx.x (<= kColCounters)
+  ARG_COL_COUNTERS = -102
 };
+constexpr int kColCounters = 4096;
 constexpr int kFullReduceThreads = 512;
 constexpr int kFullReduceMaxBlocks = 148 * 4 * 2;  // = kReduceMaxBlocks of kernels_basic.cu: the partials buffer holds this many floats
 

@@ -173,6 +173,7 @@ struct Runtime {
   // builtin scratch
   Buffer* reduce_scratch = nullptr;
   CUdeviceptr reduce_counter = 0;
+  CUdeviceptr col_counters = 0;  // kColCounters self-resetting block counters per compute stream (fused axis-reduction second stage)
   CUevent timer0 = nullptr, timer1 = nullptr;
   Nccl nccl;
 };
@@ -639,6 +640,17 @@ Buffer* reduce_scratch() {
   return r.reduce_scratch;
 }
 
+CUdeviceptr col_counters_for(int stream) {
+  Runtime& r = rt();
+  if (!r.col_counters) {
+    const size_t words = (size_t)kColCounters * (size_t)r.stream_count;
+    CC_CU(cuMemAlloc(&r.col_counters, words * 4));
+    CC_CU(cuMemsetD32Async(r.col_counters, 0, words, r.streams[0]));
+    CC_CU(cuStreamSynchronize(r.streams[0]));
+  }
+  return r.col_counters + (size_t)stream * kColCounters * 4;
+}
+
 }  // namespace
 }  // namespace cc
 
@@ -763,6 +775,8 @@ int cc_shutdown(void) {
       r.reduce_scratch = nullptr;
       driver().cuMemFree(r.reduce_counter);
       r.reduce_counter = 0;
+      if (r.col_counters) driver().cuMemFree(r.col_counters);
+      r.col_counters = 0;
     }
     trim_pool();
     for (auto& kv : r.host_blocks) driver().cuMemFreeHost(kv.first);  // pinned host memory goes with the context too
@@ -1410,6 +1424,7 @@ int cc_launch(cc_kernel h, const cc_buffer* args, int n_args, cc_buffer out, con
       in.push_back(b);
     }
     ensure_loaded(*k);
+    int launch_stream = 0;  // index of the stream the launches below go to (per-stream counters)
     auto launch_spec = [&](size_t li, const std::vector<Buffer*>& scratch, Buffer* shared_partials, CUstream stream) {
       const LaunchSpec& ls = p.launches[li];
       std::vector<CUdeviceptr> ptrs;
@@ -1424,6 +1439,8 @@ int cc_launch(cc_kernel h, const cc_buffer* args, int n_args, cc_buffer out, con
           ptrs.push_back(shared_partials->ptr);
         else if (a == ARG_REDUCE_COUNTER)
           ptrs.push_back(r.reduce_counter);
+        else if (a == ARG_COL_COUNTERS)
+          ptrs.push_back(col_counters_for(launch_stream));
         else
           ptrs.push_back(scratch[ARG_SCRATCH0 - a]->ptr);
       }
@@ -1501,10 +1518,16 @@ int cc_launch(cc_kernel h, const cc_buffer* args, int n_args, cc_buffer out, con
     label_kernel_op(op, *k);
     for (Buffer* s : scratch) op.writes.push_back(s);
     if (shared_partials) op.writes.push_back(shared_partials);
-    op_begin(op, waits, n_waits);
-    for (size_t li = 0; li < p.launches.size(); ++li) launch_spec(li, scratch, shared_partials, op.cu());
-    r.stats.launches++;
-    op_end(op, out_event);
+    launch_stream = op.stream;
+    try {
+      op_begin(op, waits, n_waits);
+      for (size_t li = 0; li < p.launches.size(); ++li) launch_spec(li, scratch, shared_partials, op.cu());
+      r.stats.launches++;
+      op_end(op, out_event);
+    } catch (...) {
+      for (Buffer* s : scratch) release(s);  // a failed launch must not strand the plan's scratch buffers
+      throw;
+    }
     for (Buffer* s : scratch) release(s);
   });
 }

@@ -182,7 +182,8 @@ int cc_kernel_arg_param(cc_kernel k, int i, int32_t* out_param_ordinal);
 int cc_kernel_source(cc_kernel k, const char** out);
 /* Launch geometry of the i-th kernel of a compiled plan (i < cc_kernel_info_t.n_launches) — introspection for tests and tools:
  * the entry point inside the generated module, grid / block / dynamic shared memory, and its argument list (>= 0: plan argument,
- * -1: the output buffer, -2-k: scratch buffer k of `scratch_floats`, -100 / -101: the runtime's fold partials / block counter). */
+ * -1: the output buffer, -2-k: scratch buffer k of `scratch_floats`, -100 / -101: the runtime's fold partials / block counter,
+ * -102: the per-stream block counters of a fused axis-reduction second stage). */
 typedef struct cc_launch_info_t {
   char entry[64];
   uint32_t grid[3], block[3], smem;

@@ -168,6 +168,9 @@ def balance_on_shutdown():
         e.doBuffer().release()
     e.flatArray()
     chain(a.split(0)).flatArray()
+    big = leaf([300, 64])
+    chain(big.split(0)).flatArray()  # a split axis reduction (second stage: its own launch, or fused with CC_FUSE_COL_STAGE=1)
+    big.release()
     (a * b).sum().flatBuffer().release()
     del e
     a.release(), b.release(), c.release()

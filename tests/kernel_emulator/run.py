@@ -10,7 +10,8 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 _CACHE = os.path.join(tempfile.gettempdir(), "compute_cuda_kernel_emulator")
-ARG_OUT, ARG_SCRATCH0, ARG_PARTIALS, ARG_COUNTER = -1, -2, -100, -101
+ARG_OUT, ARG_SCRATCH0, ARG_PARTIALS, ARG_COUNTER, ARG_COL_COUNTERS = -1, -2, -100, -101, -102
+COL_COUNTERS = np.zeros(4096, np.uint32)  # persistent and self-resetting, like the runtime's
 FOLD_PARTIALS = 148 * 4 * 2
 
 
@@ -88,6 +89,8 @@ def _call(lib, i, li, args, out, scratch, partials, counter):
             ptrs[j] = partials.ctypes.data
         elif a == ARG_COUNTER:
             ptrs[j] = counter.ctypes.data
+        elif a == ARG_COL_COUNTERS:
+            ptrs[j] = COL_COUNTERS.ctypes.data
         else:
             ptrs[j] = scratch[ARG_SCRATCH0 - a].ctypes.data
     fn = getattr(lib, f"emu_launch_{i}")
@@ -141,4 +144,5 @@ def emulate(cuda, expr, leaf_arrays, max_threads=1 << 16):
         for i, li in enumerate(launches):
             _call(lib, i, li, args, out, scratch, partials, counter)
     assert (out[n:] == np.float32(-12345.0)).all(), "the kernel wrote past its output"
+    assert not COL_COUNTERS.any(), "a fused second stage left its block counter set"
     return out[:n], k

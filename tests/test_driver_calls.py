@@ -105,6 +105,17 @@ def test_multi_launch_plans_and_folds_stay_on_their_stream(spy_dir):
     assert r["fold"]["cuMemsetD32Async"] == 0  # the fold's block counter resets itself
 
 
+def test_fused_second_stage_is_one_launch_and_its_counters_are_given_back(spy_dir):
+    """opt-in CC_FUSE_COL_STAGE=1 (kernel side: tests/test_kernel_emulation.py): one launch per step, the per-stream block counters are
+    allocated and cleared once, and freed at shutdown"""
+    r = run(spy_dir, "two_launch_plan_and_fold", CC_FUSE_COL_STAGE="1")
+    assert r["axis_launches_per_step"] == 1
+    assert r["axis"]["pdl_launches"] == 50 and r["axis"]["cuMemAlloc"] == 0 and r["axis"]["cuMemsetD32Async"] == 0
+    assert r["axis"]["cuEventRecord"] == 0 and r["axis"]["cuStreamWaitEvent"] == 0
+    r = run(spy_dir, "balance_on_shutdown", CC_FUSE_COL_STAGE="1")
+    assert r["cuMemAlloc"] == r["cuMemFree"] > 0 and r["live_tensors"] == 0
+
+
 def test_structurally_equal_expressions_share_one_module(spy_dir):
     r = run(spy_dir, "structural_cache")
     assert r["compiles"] == 2 and r["cache_hits"] == 1

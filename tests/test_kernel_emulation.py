@@ -175,6 +175,26 @@ def test_general_contraction_panels_and_epilogue(monkeypatch):
         cuda.kernel_cache_clear()
 
 
+def test_fused_second_stage_of_a_split_axis_reduction(monkeypatch):
+    """opt-in (CC_FUSE_COL_STAGE=1): the last CTA to finish a block of columns folds that block's partials inside reduce_cols -- one
+    launch instead of two; the block counters reset themselves (checked by the emulator after every run)"""
+    monkeypatch.setenv("CC_FUSE_COL_STAGE", "1")
+    cuda.kernel_cache_clear()
+    try:
+        for _ in range(2):  # twice: the second run starts from the counters the first one left
+            check(lambda B, leaf: chain(leaf([300, 64], 1).split(0)), "second stage fused into reduce_cols", 1)
+        check(lambda B, leaf: chain(leaf([200, 260], 1).split(0)), "second stage fused into reduce_cols", 1)       # ragged column block
+        check(lambda B, leaf: chain(leaf([300, 66], 1).split(0), B.max), "second stage fused into reduce_cols", 1)  # V = 1 lanes, max
+        check(lambda B, leaf: B.abs(chain(leaf([300, 64], 1).split(0))) - leaf([64], 2), "second stage fused into reduce_cols", 1)  # epilogue in stage 2
+        k = chain(T.random([300, 64], seed=1).split(0)).compile()
+        assert k.info.n_launches == 1
+    finally:
+        monkeypatch.delenv("CC_FUSE_COL_STAGE")
+        cuda.kernel_cache_clear()
+    k = chain(T.random([300, 64], seed=1).split(0)).compile()
+    assert k.info.n_launches == 2 and "fused into reduce_cols" not in k.source  # off by default
+
+
 def test_whole_tensor_folds_and_iterated_maps():
     check(lambda B, leaf: (leaf([33, 20], 1) * leaf([33, 20], 2)).sum(), "whole-tensor fold", 4)
     check(lambda B, leaf: B.abs(leaf([4099], 3)).sum(), "whole-tensor fold", 4)
