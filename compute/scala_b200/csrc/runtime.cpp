@@ -1166,41 +1166,40 @@ int cc_compile_ex(const void* blob, uint64_t n_bytes, cc_kernel* out, uint64_t* 
       theirs->cv.wait(wait, [&] { return theirs->done; });
       // compiled (next lookup hits) or failed (this thread compiles it itself and reports its own error)
     }
-    auto finish = [&](Kernel* ready) {  // under the runtime lock
-      r.compiling.erase(t.key);
-      {
-        std::lock_guard<std::mutex> g(mine->mu);
-        mine->done = true;
+    // whatever happens from here on (planning or NVRTC failing, allocation failure), the marker goes and the waiters wake up
+    struct Finisher {
+      Runtime& r;
+      const std::string key;  // a copy: t.key moves into the cache below
+      std::shared_ptr<Runtime::InFlight> mine;
+      ~Finisher() {
+        Lock lock;
+        r.compiling.erase(key);
+        {
+          std::lock_guard<std::mutex> g(mine->mu);
+          mine->done = true;
+        }
+        mine->cv.notify_all();
       }
-      mine->cv.notify_all();
-      (void)ready;
-    };
+    } finisher{r, t.key, mine};
     std::unique_ptr<Kernel> k(new Kernel());
     bool disk_hit = false, compiled = false;
-    try {
-      k->plan = make_plan(t, dp);
-      k->hash = t.hash;
-      if (!k->plan.launches.empty()) {
-        disk_hit = nvrtc_compile(*k, cache_dir);
-        compiled = !disk_hit;
-      } else {
-        k->full_source = std::string("// ") + k->plan.note + "\n" + k->plan.source;
-      }
-    } catch (...) {
-      Lock lock;
-      finish(nullptr);
-      throw;
+    k->plan = make_plan(t, dp);
+    k->hash = t.hash;
+    if (!k->plan.launches.empty()) {
+      disk_hit = nvrtc_compile(*k, cache_dir);
+      compiled = !disk_hit;
+    } else {
+      k->full_source = std::string("// ") + k->plan.note + "\n" + k->plan.source;
     }
-    Lock lock;
+    Lock lock;  // (recursive: the finisher takes it again on the way out, after the kernel is in the cache)
     r.stats.compiles++;
     if (disk_hit) r.stats.disk_cache_hits++;
     if (compiled) r.stats.nvrtc_compiles++;
+    r.kernels.insert(k.get());
+    r.cache.emplace(std::move(t.key), k.get());
     Kernel* raw = k.release();
     raw->rc.store(2);  // cache + caller
     raw->last_use = ++r.cache_clock;
-    r.kernels.insert(raw);
-    finish(raw);  // (erases by t.key: before the key moves into the cache)
-    r.cache.emplace(std::move(t.key), raw);
     evict_kernels();
     *out = (cc_kernel)(uintptr_t)raw;
   });

@@ -566,3 +566,29 @@ def test_hot_calls_are_bound_natively_and_report_typed_errors(monkeypatch):
     monkeypatch.undo()
     importlib.invalidate_caches()
     assert type(cuda._hot().do_buffer).__name__ == "builtin_function_or_method"
+
+
+def test_a_failing_compilation_wakes_its_waiters():
+    """the JIT runs outside the runtime lock with an in-flight marker per structure: a structure whose planning fails must release the
+    marker and report the error to every thread that asked for it (none may wait forever), and leave the compiler usable"""
+    import threading
+
+    L = cuda._L()
+    # parses, but a Reduce root must produce exactly one float: rejected by the planner (after the marker is set)
+    blob = struct.pack("<4I", 0x31544343, 2, 1, 1) + struct.pack("<i", 2) + struct.pack("<If", 1, 1.0) + struct.pack("<4I", 30, 22, 0, 0)
+    results = []
+
+    def ask():
+        h = C.c_uint64()
+        results.append(L.cc_compile(blob, len(blob), C.byref(h)))
+
+    for _ in range(3):
+        ts = [threading.Thread(target=ask) for _ in range(8)]
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join(timeout=60)
+        assert not any(t.is_alive() for t in ts), "a waiter was never woken"
+    assert results == [-6] * 24
+    k = (cuda.Tensor.random([8, 8], seed=1) + cuda.Tensor.fill(1.0, [8, 8])).compile()
+    assert k.info.kind == 0
