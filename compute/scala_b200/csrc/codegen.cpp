@@ -1560,6 +1560,86 @@ void emit_reduce(Plan& plan, const Program& p, int n_args, const DeviceProps& de
     const int64_t TCHb = S > 1 ? (T + Sb - 1) / Sb : T;         // rows per CTA
     const int64_t Sy = S > 1 ? (T + TCHb - 1) / TCHb : 1;       // partials per output
     const int CW = S > 1 ? 64 : 256;                            // column vectors per CTA
+    // Opt-in register tiling (CC_TUNE_RED_P=2|4, until it has been timed on a GPU): a thread owns P positions along the output
+    // dimension next to the fastest one as well as its V adjacent outputs. Operands that do not depend on that dimension -- the
+    // weights of a convolution, the broadcast operand of a matmul-like term -- are loaded once per reduction step for all P
+    // positions (the P inlined copies of the term read the same address; the compiler keeps one load), which raises the FMAs per
+    // load of the load-issue-bound small convolutions from 2 to 4P / (P + 1).
+    int tileP = 1;
+    if (const char* ev = getenv("CC_TUNE_RED_P")) tileP = atoi(ev);
+    const int dp = no - 2;
+    if (S == 1 && (tileP == 2 || tileP == 4) && dp >= 0 && odims[(size_t)dp] % tileP == 0 && NV / tileP >= 1) {
+      bool shared_operand = false, all_integer = true;
+      for (int j = 0; j < nloads; ++j) {
+        if (in_post(j)) continue;
+        all_integer &= p.loads[j].integer;
+        if (p.loads[j].integer && p.loads[j].coef[dp] == 0) shared_operand = true;
+      }
+      if (shared_operand && all_integer) {
+        const int P = tileP;
+        std::vector<int64_t> tdims = odims;  // the thread index space: dimension dp counts tiles of P
+        tdims[(size_t)dp] /= P;
+        const int64_t NVP = NV / P;
+        std::vector<int64_t> ostride((size_t)no, 1);
+        for (int x = no - 2; x >= 0; --x) ostride[(size_t)x] = ostride[(size_t)x + 1] * odims[(size_t)x + 1];
+        std::string gsp;  // ", g0, ..., (gt_ + p_), ..., g{no-1}"
+        for (int x = 0; x < no; ++x) gsp += x == dp ? std::string(", (gt_ + p_)") : strprintf(", g%d", x);
+        e("// register tile: %d positions along g%d per thread\n", P, dp);
+        e("extern \"C\" __global__ void __launch_bounds__(256) reduce_cols(%s) {\n", param_list(n_args, true, "dst").c_str());
+        e("  const %s v = (%s)blockIdx.x * 256 + threadIdx.x;\n  if (v >= %lld) return;\n", IDX, IDX, (long long)NVP);
+        // decode over the tiled index space; g{dp} becomes the tile's first position gt_
+        e("  %s rem_ = v * %d;\n", IDX, V);
+        for (int x = no - 1; x >= 1; --x) {
+          if (x == dp)
+            e("  const %s gt_ = (rem_ %% (%s)%lld) * %d; rem_ /= (%s)%lld;\n", IDX, IDX, (long long)tdims[(size_t)x], P, IDX, (long long)tdims[(size_t)x]);
+          else
+            e("  const %s g%d = rem_ %% (%s)%lld; rem_ /= (%s)%lld;\n", IDX, x, IDX, (long long)tdims[(size_t)x], IDX, (long long)tdims[(size_t)x]);
+        }
+        if (dp == 0)
+          e("  const %s gt_ = rem_ * %d;\n", IDX, P);
+        else
+          e("  const %s g0 = rem_;\n", IDX);
+        e("  float acc[%d][%d];\n  #pragma unroll\n  for (int p_ = 0; p_ < %d; ++p_)\n    #pragma unroll\n    for (int l = 0; l < %d; ++l) acc[p_][l] = %s;\n", P, V, P, V, ZERO);
+        std::string ind = "  ";
+        for (int x = no; x < nd; ++x) {
+          if (T <= 96)
+            e("%s#pragma unroll\n", ind.c_str());
+          else if (x == nd - 1)
+            e("%s#pragma unroll %d\n", ind.c_str(), (int)std::min<int64_t>(8, p.dims[x]));
+          else
+            e("%s#pragma unroll 1\n", ind.c_str());
+          e("%sfor (%s g%d = 0; g%d < %lld; ++g%d) {\n", ind.c_str(), IDX, x, x, (long long)p.dims[x], x);
+          ind += "  ";
+        }
+        e("%s#pragma unroll\n%sfor (int p_ = 0; p_ < %d; ++p_) {\n", ind.c_str(), ind.c_str(), P);
+        e("%s  float x[%d];\n%s  evd(%s%s%s, x);\n", ind.c_str(), V, ind.c_str(), rgs.c_str(), gsp.c_str(), pass.c_str());
+        e("%s  #pragma unroll\n%s  for (int l = 0; l < %d; ++l) acc[p_][l] = %s;\n%s}\n", ind.c_str(), ind.c_str(), V, AP("acc[p_][l]", "x[l]").c_str(), ind.c_str());
+        for (int x = no; x < nd; ++x) {
+          ind.resize(ind.size() - 2);
+          e("%s}\n", ind.c_str());
+        }
+        std::string lin = "(long long)0";
+        for (int x = 0; x < no; ++x) lin += x == dp ? strprintf(" + (long long)(gt_ + p_) * %lldLL", (long long)ostride[(size_t)x]) : strprintf(" + (long long)g%d * %lldLL", x, (long long)ostride[(size_t)x]);
+        e("  #pragma unroll\n  for (int p_ = 0; p_ < %d; ++p_) {\n", P);
+        if (has_post) e("    post(acc[p_]%s%s);\n", gsp.c_str(), pass.c_str());
+        e("    float* d = dst + (%s);\n", lin.c_str());
+        if (V == 4)
+          e("    cc_stg4(d, acc[p_]);\n");
+        else
+          e("    d[0] = acc[p_][0];\n");
+        e("  }\n}\n");
+        LaunchSpec ls;
+        ls.entry = "reduce_cols";
+        ls.grid[0] = (uint32_t)((NVP + 255) / 256);
+        ls.block[0] = 256;
+        for (int i = 0; i < n_args; ++i) ls.args.push_back(i);
+        ls.args.push_back(ARG_OUT);
+        plan.launches.push_back(ls);
+        plan.note += strprintf("; register tile of %d along output dim %d", P, dp);
+        plan.source += e.s;
+        return;
+      }
+    }
     // Opt-in (CC_FUSE_COL_STAGE=1, until it has been timed on a GPU): the second stage runs inside reduce_cols -- the last CTA to
     // finish a block of columns (a self-resetting counter per blockIdx.x) folds that block's partials, so the plan is one launch.
     const int64_t gridx = (NV + CW - 1) / CW;

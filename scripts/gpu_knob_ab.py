@@ -2,6 +2,7 @@
   python scripts/gpu_knob_ab.py fuse_col     CC_FUSE_COL_STAGE      split axis reductions: second stage inside reduce_cols
   python scripts/gpu_knob_ab.py batched      CC_BATCHED_CONTRACTION batched matmul on the tcgen05 pipeline (one launch per batch)
   python scripts/gpu_knob_ab.py pdl          CC_PDL (default on)    programmatic dependent launch
+  python scripts/gpu_knob_ab.py red_p2|red_p4 CC_TUNE_RED_P=2|4     register tiling of column-owner reductions (small convolutions)
 Per workload: device time per step (CUDA events around the loop, best of 3), max |a - b| between the arms relative to max |a|.
 Writes gpurun_out/knob_<name>.json.  (scripts/gpu_pdl.py is the earlier, PDL-only version with host submission times.)"""
 import json
@@ -12,7 +13,8 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-KNOBS = {"fuse_col": ("CC_FUSE_COL_STAGE", "0", "1"), "batched": ("CC_BATCHED_CONTRACTION", "0", "1"), "pdl": ("CC_PDL", "0", "1")}
+KNOBS = {"fuse_col": ("CC_FUSE_COL_STAGE", "0", "1"), "batched": ("CC_BATCHED_CONTRACTION", "0", "1"), "pdl": ("CC_PDL", "0", "1"),
+         "red_p2": ("CC_TUNE_RED_P", "1", "2"), "red_p4": ("CC_TUNE_RED_P", "1", "4")}
 
 
 def chain(parts):
@@ -38,6 +40,23 @@ def workloads(name, T):
                 return chain((A.broadcast([b, m, k, n]) * B.reshape([b, 1, k, n]).broadcast([b, m, k, n])).split(2))
             out.append((f"batched matmul {b}x{m}x{k}x{n}", build, 20))
         return out
+    if name.startswith("red_p"):
+        def conv(batch, size, depth, filters):  # benchmarks.scala:463-556
+            x, w, bias = T.random([batch, size, size, depth], seed=1).doCache(), T.random([3, 3, depth, filters], seed=2).doCache(), T.random([filters], seed=3).doCache()
+            xs, bs = x.split(3), bias.split(0)
+            ws = [[[wc.split(0) for wc in wx.split(0)] for wx in wy.split(0)] for wy in w.split(0)]
+
+            def build():
+                outs = []
+                for f in range(filters):
+                    terms = [xs[c].translate([0, dy - 1, dx - 1]) * ws[dy][dx][c][f].broadcast([batch, size, size]) for dy in range(3) for dx in range(3) for c in range(depth)]
+                    outs.append(chain(terms) + bs[f].broadcast([batch, size, size]))
+                return T.join(outs)
+            return build
+        A, B = T.random([512, 64], seed=4).doCache(), T.random([64, 512], seed=5).doCache()
+        return [("conv 3x3 batch 128 32x32 depth 8", conv(128, 32, 8, 8), 500), ("conv 3x3 batch 32 32x32 depth 3", conv(32, 32, 3, 3), 1000),
+                ("conv 3x3 batch 64 64x64 depth 16", conv(64, 64, 16, 16), 100),
+                ("matmul 512x64x512 (generic reduction)", lambda: chain((A.broadcast([512, 64, 512]) * B.reshape([1, 64, 512]).broadcast([512, 64, 512])).split(1)), 500)]
     a, b, c = (T.random([1024, 1024], seed=s).doCache() for s in (1, 2, 3))
     x = T.random([4096, 4096], seed=5).doCache()
     return [("C1 tanh(a*b+c) 1024^2", lambda: T.tanh(a * b + c), 3000), ("axis-0 sum 4096^2", lambda: chain(x.split(0)), 500),

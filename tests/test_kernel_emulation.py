@@ -195,6 +195,39 @@ def test_fused_second_stage_of_a_split_axis_reduction(monkeypatch):
     assert k.info.n_launches == 2 and "fused into reduce_cols" not in k.source  # off by default
 
 
+@pytest.mark.parametrize("P", [2, 4])
+def test_register_tiled_reduction(monkeypatch, P):
+    """opt-in (CC_TUNE_RED_P): a thread owns P positions along the output dimension next to the fastest one; operands that do not depend
+    on it (convolution weights) are shared by the P copies of the term"""
+    monkeypatch.setenv("CC_TUNE_RED_P", str(P))
+    cuda.kernel_cache_clear()
+    try:
+        def conv(B, leaf, filters=8, depth=3):
+            x, w, bias = leaf([2, 6, 8, depth], 1, 1.0), leaf([3, 3, depth, filters], 2), leaf([filters], 3)
+            xs = x.split(3)
+            ws = [[[wc.split(0) for wc in wx.split(0)] for wx in wy.split(0)] for wy in w.split(0)]
+            bs = bias.split(0)
+            outs = []
+            for f in range(filters):
+                terms = [xs[c].translate([0, dy - 1, dx - 1]) * ws[dy][dx][c][f].broadcast([2, 6, 8]) for dy in range(3) for dx in range(3) for c in range(depth)]
+                outs.append(B.max(chain(terms) + bs[f].broadcast([2, 6, 8]), B.fill(0.0, [2, 6, 8])))  # bias + relu epilogue
+            return B.join(outs)
+        check(conv, f"register tile of {P} along output dim 2", 1)
+        # a matmul-like term small enough to stay on the generic reduction: A[i, t] is shared along k's neighbour dimension
+        def small_matmul(B, leaf):
+            a, b = leaf([8, 12], 4), leaf([12, 16], 5)
+            a3 = a.broadcast([8, 12, 16])
+            b3 = b.reshape([1, 12, 16]).broadcast([8, 12, 16])
+            return chain((a3 * b3).split(1))
+        check(small_matmul, f"register tile of {P} along output dim 0", 1)
+        # no operand is shared along the tiled dimension: the plan stays untiled
+        check(lambda B, leaf: chain(leaf([12, 8, 128], 6).split(0)), "column owner", 1)
+    finally:
+        monkeypatch.delenv("CC_TUNE_RED_P")
+        cuda.kernel_cache_clear()
+    assert "register tile" not in chain(T.random([12, 8, 128], seed=1).split(0)).compile().source
+
+
 def test_whole_tensor_folds_and_iterated_maps():
     check(lambda B, leaf: (leaf([33, 20], 1) * leaf([33, 20], 2)).sum(), "whole-tensor fold", 4)
     check(lambda B, leaf: B.abs(leaf([4099], 3)).sum(), "whole-tensor fold", 4)
