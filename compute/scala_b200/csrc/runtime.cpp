@@ -54,7 +54,7 @@ struct Buffer {
   bool owned = true;
   std::atomic<int> rc{1};
   Mark last_write;
-  std::vector<Mark> reads;  // at most one per stream
+  SmallVec<Mark, 4> reads;  // at most one per stream
   std::vector<CUdeviceptr> peers;  // symmetric buffers only: the same allocation on every rank (own pointer at own rank)
   uint64_t uid = 0;         // never reused: identity for the operand-panel cache
   uint64_t version = 0;     // bumped by every command that writes the buffer
@@ -63,7 +63,7 @@ struct Buffer {
 struct Block {
   CUdeviceptr ptr;
   size_t bytes;
-  std::vector<Mark> pending;
+  SmallVec<Mark, 4> pending;
 };
 
 struct Kernel {
@@ -242,6 +242,8 @@ int pick_stream() {
   return s;
 }
 
+using BufferList = SmallVec<Buffer*, 8>;
+
 // Stream choice with affinity. Round-robin over the compute streams (the reference's "5 queues per device", cpu.scala:115) lets
 // independent commands overlap, but a command whose buffers were JUST touched on one compute stream gains nothing from another: the
 // hazard tracker would serialise it behind that stream with an event record + wait (two driver calls), and kernels on different
@@ -261,7 +263,7 @@ uint64_t now_ns() {
 #endif
 }
 constexpr uint64_t kHotHazardTicks = 6000000ull;  // ~2-6 ms of TSC ticks (or 6 ms of nanoseconds)
-int pick_stream_for(const std::vector<Buffer*>& reads, const std::vector<Buffer*>& writes) {
+int pick_stream_for(const BufferList& reads, const BufferList& writes) {
   Runtime& r = rt();
   const int n = r.stream_count;
   if (n <= 1 || n > 32) return pick_stream();
@@ -290,7 +292,7 @@ int pick_stream_for(const std::vector<Buffer*>& reads, const std::vector<Buffer*
 
 struct Op {
   int stream;
-  std::vector<Buffer*> reads, writes;
+  BufferList reads, writes;
   // what the profiler files this command under, and the algorithmic work it does (0 = unknown)
   std::string label = "command";
   uint64_t bytes = 0, flops = 0;
@@ -1414,7 +1416,7 @@ int cc_launch(cc_kernel h, const cc_buffer* args, int n_args, cc_buffer out, con
     Buffer* ob = as_buffer(out);
     CC_REQUIRE(ob->n_floats >= p.out_floats, CC_ERR_ILLEGAL_ARGUMENT, "output buffer has %llu floats, kernel writes %llu",
                (unsigned long long)ob->n_floats, (unsigned long long)p.out_floats);
-    std::vector<Buffer*> in;
+    BufferList in;
     for (int i = 0; i < n_args; ++i) {
       Buffer* b = as_buffer(args[i]);
       CC_REQUIRE(b->n_floats >= p.arg_min_floats[i], CC_ERR_ILLEGAL_ARGUMENT, "argument %d has %llu floats, kernel reads up to %llu", i,
@@ -1426,9 +1428,8 @@ int cc_launch(cc_kernel h, const cc_buffer* args, int n_args, cc_buffer out, con
     int launch_stream = 0;  // index of the stream the launches below go to (per-stream counters)
     auto launch_spec = [&](size_t li, const std::vector<Buffer*>& scratch, Buffer* shared_partials, CUstream stream) {
       const LaunchSpec& ls = p.launches[li];
-      std::vector<CUdeviceptr> ptrs;
-      std::vector<void*> argv;
-      ptrs.reserve(ls.args.size());
+      SmallVec<CUdeviceptr, 24> ptrs;
+      SmallVec<void*, 24> argv;
       for (int a : ls.args) {
         if (a >= 0)
           ptrs.push_back(in[a]->ptr);

@@ -60,27 +60,27 @@ void bury(TensorPtr&& p) {
 int64_t live_tensors() { return g_live.load(); }
 
 Session::~Session() {
-  for (auto& kv : done_) {
-    if (kv.second.buffer) cc_buffer_release(kv.second.buffer);
-    if (kv.second.event) cc_event_release(kv.second.event);
+  for (Entry& e : done_) {
+    if (e.buffer.buffer) cc_buffer_release(e.buffer.buffer);
+    if (e.buffer.event) cc_event_release(e.buffer.event);
   }
 }
 PendingBuffer* Session::find(const Tensor* t) {
   if (done_.size() <= kLinear) {
-    for (auto& kv : done_)
-      if (kv.first == t) return &kv.second;
+    for (Entry& e : done_)
+      if (e.tensor == t) return &e.buffer;
     return nullptr;
   }
   auto it = index_.find(t);
-  return it == index_.end() ? nullptr : &done_[it->second].second;
+  return it == index_.end() ? nullptr : &done_[it->second].buffer;
 }
 PendingBuffer* Session::add(const Tensor* t, const PendingBuffer& p) {
-  done_.emplace_back(t, p);
+  done_.push_back(Entry{t, p});
   if (done_.size() == kLinear + 1)
-    for (size_t i = 0; i < done_.size(); ++i) index_.emplace(done_[i].first, i);
+    for (size_t i = 0; i < done_.size(); ++i) index_.emplace(done_[i].tensor, i);
   else if (done_.size() > kLinear + 1)
     index_.emplace(t, done_.size() - 1);
-  return &done_.back().second;
+  return &done_.back().buffer;
 }
 
 // ---- closure emission ----------------------------------------------------------------------------------------------------
@@ -406,8 +406,7 @@ bool plan_output_redirectable(const PlanCache& pc) {
 
 // enqueueClosure (Tensors.scala:1291-1392)
 PendingBuffer enqueue_plan(Session& s, const PlanCache& pc, const Shape& out_shape, cc_buffer out_override, cc_event* out_event) {
-  std::vector<cc_buffer> args;
-  args.reserve(pc.args.size());
+  cc::SmallVec<cc_buffer, 16> args;
   cc_buffer out = 0;
   try {
     // upvalues.traverse(tree.id.asInstanceOf[Tensor].doBuffer) — Tensors.scala:1336-1340; the session owns the references

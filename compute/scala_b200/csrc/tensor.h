@@ -36,7 +36,11 @@ class Session {
   PendingBuffer* add(const Tensor* t, const PendingBuffer& p);
 
  private:
-  std::vector<std::pair<const Tensor*, PendingBuffer>> done_;
+  struct Entry {
+    const Tensor* tensor;
+    PendingBuffer buffer;
+  };
+  cc::SmallVec<Entry, 8> done_;
   std::unordered_map<const Tensor*, size_t> index_;  // built once done_ outgrows kLinear
   static constexpr size_t kLinear = 16;
 };
