@@ -46,3 +46,17 @@ PY
 for knob in "CC_NOOP=1" "CC_FUSE_COL_STAGE=1" "CC_TUNE_RED_P=4" "CC_BATCHED_CONTRACTION=1 CC_TUNE_CONTRACTION_MIN_MACS=1" "CC_PDL=0"; do
   echo "compile fuzz [$knob]: $(LD_PRELOAD="$PRE" ASAN_OPTIONS=detect_leaks=0 env $knob python "$W/fuzz.py" 2>&1 | grep -E "AddressSanitizer|SUMMARY|Traceback|compiled" | head -3 | tr '\n' ' ')"
 done
+
+# ---- ThreadSanitizer over the multi-threaded scenarios (the runtime lock, the in-flight compile table, atomics on handles) ----------------
+cd "$W/pkg/compute/scala_b200"
+for f in ir codegen driver runtime tensor; do
+  g++ -std=c++17 -O1 -g -fsanitize=thread -fno-omit-frame-pointer -fPIC -I/usr/local/cuda/include -c csrc/$f.cpp -o build/$f.tsan.o &
+done
+wait
+nvcc -shared -o libcompute_cuda.so build/{ir,codegen,driver,runtime,tensor}.tsan.o build/kernels_basic.cu.o build/gemm_3xtf32.cu.o \
+  -gencode arch=compute_100a,code=sm_100a -cudart static -lnvrtc -ldl -lpthread -Xlinker -rpath,/usr/local/cuda/lib64 -Xcompiler -fsanitize=thread || exit 1
+cd "$W/pkg"
+PRE="$(gcc -print-file-name=libtsan.so) $(gcc -print-file-name=libstdc++.so)"
+for sc in threads same_structure_from_many_threads compile_does_not_block_launches; do
+  echo "tsan scenario: $sc $(LD_PRELOAD="$PRE" TSAN_OPTIONS=report_signal_unsafe=0 LD_LIBRARY_PATH="$W/spy" python tests/driver_spy/scenarios.py $sc 2>&1 | grep -E "ThreadSanitizer|SUMMARY|Traceback" | sort | uniq -c | head -5 | tr '\n' ' ')"
+done
