@@ -99,6 +99,21 @@ def test_translations_paddings_and_shifted_vector_loads():
     check(lambda B, leaf: leaf([4, 4, 8], 1, 1.0).translate([1, 0, -1]).translate([0, -1, 2]), None, 0)
 
 
+def test_ranks_zero_to_six_and_non_integer_coefficients():
+    # rank 0 (a scalar kernel: `*out = term`, K:149-161) and unit dimensions
+    check(lambda B, leaf: B.abs(leaf([], 1)) + B.scalar(2.0), None, 0)
+    check(lambda B, leaf: leaf([1, 5, 1], 1) * leaf([1, 5, 1], 2), None, 0)
+    # ranks 5 and 6: more than three dimensions fold into the flat index space (K:177-211)
+    check(lambda B, leaf: leaf([2, 3, 2, 3, 4], 1).permute([4, 0, 3, 1, 2]).translate([1, 0, -1, 0, 1]), None, None)
+    check(lambda B, leaf: leaf([2, 2, 3, 2, 2, 4], 1, -1.0).translate([0, 1, 0, -1, 0, 2]) + leaf([2, 2, 3, 2, 2, 4], 2), None, 0)
+    # fractional offsets: DecimalFormat rounding of the coefficient, double arithmetic, (int) truncation toward zero (K:14-32, 372-386)
+    for off in ([0.5, -1.5], [-0.25, 2.75], [1.0006, -0.9994]):
+        check(lambda B, leaf, off=off: leaf([6, 8], 1, 9.0).translate(off), None, 0)
+    # scale: the view matrix has non-integer diagonal coefficients (T:950-965)
+    check(lambda B, leaf: leaf([4, 6], 1, 7.0).scale([6, 9]), None, 0)
+    check(lambda B, leaf: leaf([5, 8], 1).scale([3, 4]) * leaf([3, 4], 2), None, 0)
+
+
 def test_tiled_transposes():
     check(lambda B, leaf: leaf([40, 36], 1).transpose(), "tiled transpose", 3)
     check(lambda B, leaf: leaf([3, 34, 33], 2).permute([0, 2, 1]) + leaf([3, 33, 34], 3), "tiled transpose", 3)
