@@ -2153,7 +2153,7 @@ Plan make_plan(const Tree& t, const DeviceProps& dev) {
       // build over head dims + [element index]; moved into place afterwards
       odims.erase(odims.begin() + join_pos);
       odims.push_back((int64_t)root.kids.size());
-      rolled_c = root.kids.size() >= 2 && reroll(t, root.kids, step_c);
+      rolled_c = root.kids.size() >= 2 && reroll(t, std::vector<uint32_t>(root.kids.begin(), root.kids.end()), step_c);
       base = root.kids[0];
     }
     if (joined && !rolled_c) {

@@ -85,6 +85,7 @@ class SmallVec {
   T& operator[](size_t i) { return p_[i]; }
   const T& operator[](size_t i) const { return p_[i]; }
   T& back() { return p_[n_ - 1]; }
+  void pop_back() { --n_; }
 
  private:
   void grow(size_t cap) {

@@ -50,11 +50,11 @@ struct Node {
   uint32_t kind = 0;
   float value = 0.f;           // literal value, or padding of a parameter
   uint64_t param_id = 0;       // identity of the producing tensor (Tensors.scala:1259)
-  std::vector<int32_t> shape;  // parameter shape
+  SmallVec<int32_t, 4> shape;  // parameter shape
   int32_t def_root = -1;       // optional closure of the producing (not yet evaluated) inline tensor
   uint32_t rows = 0, cols = 0; // transform matrix, row-major rows x cols (cols = view rank + 1)
   std::vector<double> matrix;
-  std::vector<uint32_t> kids;  // operands / array / concatenate elements
+  SmallVec<uint32_t, 2> kids;  // operands / array / concatenate elements (inline for every node but a long Concatenate)
   int32_t position = -1;       // K_CONCAT: output dimension of the element index (-1 = last, Tensors.scala:577-598)
   uint32_t monoid = 0;         // K_REDUCE: K_PLUS / K_MIN / K_MAX / K_TIMES (shape = index space of the operand)
 };
@@ -79,6 +79,11 @@ void canonicalize(Tree& t);
 // Incremental writer used by the host-side mirror (tensor.cpp) — the same bytes a JVM front end would write.
 class TreeWriter {
  public:
+  TreeWriter() {
+    body_.reserve(512);
+    offsets_.reserve(32);
+    def_field_.reserve(32);
+  }
   uint32_t literal(float v);
   uint32_t parameter(uint64_t id, float padding, const std::vector<int32_t>& shape, int32_t def_root = -1);
   uint32_t transform(uint32_t array, uint32_t rows, uint32_t cols, const double* m);

@@ -85,18 +85,55 @@ PendingBuffer* Session::add(const Tensor* t, const PendingBuffer& p) {
 
 // ---- closure emission ----------------------------------------------------------------------------------------------------
 
+// tensor -> node index. Expressions evaluated once and thrown away (the reference's benchmarks rebuild theirs on every call) have a
+// handful of nodes: a flat array searched linearly, with a hash index only once the graph outgrows it (chains of thousands of terms).
+class NodeOfTensor {
+ public:
+  const uint32_t* find(const Tensor* t) const {
+    if (entries_.size() <= kLinear) {
+      for (const Entry& e : entries_)
+        if (e.tensor == t) return &e.node;
+      return nullptr;
+    }
+    auto it = index_.find(t);
+    return it == index_.end() ? nullptr : &entries_[it->second].node;
+  }
+  bool count(const Tensor* t) const { return find(t) != nullptr; }
+  uint32_t at(const Tensor* t) const {
+    const uint32_t* n = find(t);
+    CC_REQUIRE(n, CC_ERR_BAD_TREE, "tensor has no emitted node");
+    return *n;
+  }
+  void set(const Tensor* t, uint32_t node) {  // t is not present yet
+    entries_.push_back(Entry{t, node});
+    if (entries_.size() == kLinear + 1)
+      for (size_t i = 0; i < entries_.size(); ++i) index_.emplace(entries_[i].tensor, i);
+    else if (entries_.size() > kLinear + 1)
+      index_.emplace(t, entries_.size() - 1);
+  }
+
+ private:
+  struct Entry {
+    const Tensor* tensor;
+    uint32_t node;
+  };
+  static constexpr size_t kLinear = 24;
+  cc::SmallVec<Entry, 24> entries_;
+  std::unordered_map<const Tensor*, size_t> index_;
+};
+
 struct Tensor::EmitCtx {
   cc::TreeWriter w;
-  std::unordered_map<const Tensor*, uint32_t> closures;
-  std::unordered_map<const Tensor*, uint32_t> param_nodes;
+  NodeOfTensor closures;
+  NodeOfTensor param_nodes;
   std::vector<const Tensor*> params;  // in creation order
+  EmitCtx() { params.reserve(8); }
 
   uint32_t param(const Tensor* t) {
-    auto it = param_nodes.find(t);
-    if (it != param_nodes.end()) return it->second;
+    if (const uint32_t* known = param_nodes.find(t)) return *known;
     // ArrayParameter(id = the tensor itself, padding, shape) — Tensors.scala:1254-1260
     uint32_t n = w.parameter((uint64_t)(uintptr_t)t, t->padding, t->shape, -1);
-    param_nodes[t] = n;
+    param_nodes.set(t, n);
     params.push_back(t);
     return n;
   }
@@ -107,23 +144,29 @@ Tensor::~Tensor() { g_live.fetch_sub(1); }
 int64_t Tensor::size() const { return product(shape); }
 
 uint32_t Tensor::closure(EmitCtx& ctx) const {
-  std::vector<std::pair<const Tensor*, bool>> stack{{this, false}};
+  struct Frame {
+    const Tensor* t;
+    bool expanded;
+  };
+  cc::SmallVec<Frame, 16> stack{Frame{this, false}};
   std::vector<const Tensor*> ops;
+  std::vector<uint32_t> ids;
   while (!stack.empty()) {
-    auto [t, expanded] = stack.back();
+    const Frame f = stack.back();
     stack.pop_back();
+    const Tensor* t = f.t;
     if (ctx.closures.count(t)) continue;
     ops.clear();
     t->closure_operands(ops);
-    if (!expanded && !ops.empty()) {
-      stack.push_back({t, true});
+    if (!f.expanded && !ops.empty()) {
+      stack.push_back(Frame{t, true});
       for (size_t k = ops.size(); k-- > 0;)
-        if (!ctx.closures.count(ops[k])) stack.push_back({ops[k], false});
+        if (!ctx.closures.count(ops[k])) stack.push_back(Frame{ops[k], false});
       continue;
     }
-    std::vector<uint32_t> ids;
+    ids.clear();
     for (const Tensor* o : ops) ids.push_back(ctx.closures.at(o));
-    ctx.closures[t] = t->emit_closure(ctx, ids);
+    ctx.closures.set(t, t->emit_closure(ctx, ids));
   }
   return ctx.closures.at(this);
 }
@@ -382,6 +425,7 @@ void resolve_plan(PlanCache& pc, Tensor::EmitCtx& ctx, uint32_t root, const Shap
     cc_kernel_info_t info;
     check(cc_kernel_info(k, &info));
     std::vector<const Tensor*> args;
+    args.reserve((size_t)info.n_args);
     for (int i = 0; i < info.n_args; ++i) {
       int32_t ord = -1;
       check(cc_kernel_arg_param(k, i, &ord));
