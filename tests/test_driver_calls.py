@@ -205,3 +205,24 @@ def test_a_failed_read_back_is_a_typed_error_and_leaks_nothing(spy_dir, case, en
     r = run(spy_dir, "faults", case)
     assert r["ok"] == 7 and len(r["errors"]) == 1 and r["errors"][0][0] == CC_ERR_CUDA and entry in r["errors"][0][1]
     _balanced(r)
+
+
+def test_heap_allocations_per_launch_stay_low(spy_dir, tmp_path):
+    """a launch-bound step is ~3 us, of which the library's own share was mostly malloc / free (14 allocations per launch before the
+    short lists moved into cc::SmallVec): a regression guard on the counts, which are deterministic (C driver program, malloc counted by
+    an LD_PRELOAD shim, the driver spy in front of libcuda)"""
+    root = os.path.dirname(HERE)
+    libdir = os.path.join(root, "compute", "scala_b200")
+    shim, exe = str(tmp_path / "libmalloc_count.so"), str(tmp_path / "host_cost")
+    for cmd in (["gcc", "-O2", "-shared", "-fPIC", os.path.join(HERE, "driver_spy", "malloc_count.c"), "-o", shim, "-ldl"],
+                ["gcc", "-O2", "-std=c11", "-D_POSIX_C_SOURCE=200809L", "-I", os.path.join(root, "include"), os.path.join(HERE, "driver_spy", "host_cost.c"), "-o", exe,
+                 "-L", libdir, "-lcompute_cuda", "-ldl", f"-Wl,-rpath,{libdir}"]):
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+    env = dict(os.environ, LD_PRELOAD=shim, LD_LIBRARY_PATH=spy_dir + os.pathsep + os.environ.get("LD_LIBRARY_PATH", ""))
+    env.pop("CC_KERNEL_CACHE_DIR", None)
+    r = subprocess.run([exe], env=env, capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, (r.stdout, r.stderr[-2000:])
+    counts = json.loads(r.stdout.strip().splitlines()[-1])
+    assert counts["mallocs_per_steady_step"] <= 3.0, counts       # measured: 2 (the Buffer object and its registry node)
+    assert counts["mallocs_per_fresh_expression"] <= 52.0, counts  # measured: 44 (16 for three nodes, 25 for the first evaluation, 3 to launch and release)
