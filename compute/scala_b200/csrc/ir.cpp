@@ -192,12 +192,12 @@ Tree parse_tree(const void* blob, uint64_t n_bytes) {
 
 void canonicalize(Tree& t) {
   const uint32_t n = (uint32_t)t.nodes.size();
-  std::vector<int32_t> canon(n, -1);
-  std::vector<uint32_t> order;
-  order.reserve(n);
-  std::vector<int32_t> param_ordinal(n, -1);
+  // per-call index tables: inline for the small trees of throw-away expressions (no heap traffic), on the heap for long chains
+  SmallVec<int32_t, 64> canon, param_ordinal;
+  SmallVec<uint32_t, 64> order, stack;
+  for (uint32_t i = 0; i < n; ++i) canon.push_back(-1), param_ordinal.push_back(-1);
   t.params.clear();
-  std::vector<uint32_t> stack;
+  t.params.reserve(8);
   auto dfs = [&](uint32_t root) {
     stack.push_back(root);
     while (!stack.empty()) {
