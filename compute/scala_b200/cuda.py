@@ -596,13 +596,13 @@ class Tensor:
             check(h)
         return Tensor._of(h)
 
-    abs = staticmethod(lambda t: Tensor._un("abs", t))
-    sqrt = staticmethod(lambda t: Tensor._un("sqrt", t))
-    tanh = staticmethod(lambda t: Tensor._un("tanh", t))
-    exp = staticmethod(lambda t: Tensor._un("exp", t))
-    log = staticmethod(lambda t: Tensor._un("log", t))
-    min = staticmethod(lambda l, r: Tensor._bin("min", l, r))
-    max = staticmethod(lambda l, r: Tensor._bin("max", l, r))
+    abs = staticmethod(lambda t: _unop(12, t))
+    sqrt = staticmethod(lambda t: _unop(14, t))
+    tanh = staticmethod(lambda t: _unop(13, t))
+    exp = staticmethod(lambda t: _unop(10, t))
+    log = staticmethod(lambda t: _unop(11, t))
+    min = staticmethod(lambda l, r: _binop(20, l, r))
+    max = staticmethod(lambda l, r: _binop(21, l, r))
 
     @staticmethod
     def join(tensors: Iterable["Tensor"], dimension: int | None = None) -> "Tensor":
@@ -617,22 +617,22 @@ class Tensor:
 
     # -- operators --
     def __add__(self, o):
-        return Tensor._bin("+", self, o)
+        return _binop(22, self, o)
 
     def __sub__(self, o):
-        return Tensor._bin("-", self, o)
+        return _binop(23, self, o)
 
     def __mul__(self, o):
-        return Tensor._bin("*", self, o)
+        return _binop(24, self, o)
 
     def __truediv__(self, o):
-        return Tensor._bin("/", self, o)
+        return _binop(25, self, o)
 
     def __mod__(self, o):
-        return Tensor._bin("%", self, o)
+        return _binop(26, self, o)
 
     def __neg__(self):
-        return Tensor._un("neg", self)
+        return _unop(15, self)
 
     def __pos__(self):
         return self
@@ -766,7 +766,10 @@ class Tensor:
         return Kernel(h.value)
 
     def release(self) -> None:
-        h = getattr(self, "_h", 0)
+        try:
+            h = self._h
+        except AttributeError:  # construction failed before the handle existed
+            return
         if h:
             self._h = 0
             st = (_HOT.tensor_release or _hot().tensor_release)(h)
@@ -779,6 +782,31 @@ class Tensor:
                 self.release()
         except Exception:
             pass
+
+
+def _unop(code: int, t: Tensor) -> Tensor:
+    """one elementwise node (codes = _UNARY's: the C ABI's CT_* constants); the operators above call this directly"""
+    h = (_HOT.unary or _hot().unary)(code, t._h)
+    if h < 0:
+        check(h)
+    r = object.__new__(Tensor)
+    r._h = h
+    r._shape = None
+    return r
+
+
+def _binop(code: int, l: Tensor, r: Tensor) -> Tensor:
+    h = (_HOT.binary or _hot().binary)(code, l._h, r._h)
+    if h < 0:
+        check(h)
+    t = object.__new__(Tensor)
+    t._h = h
+    t._shape = None
+    return t
+
+
+assert (_UNARY["exp"], _UNARY["log"], _UNARY["abs"], _UNARY["tanh"], _UNARY["sqrt"], _UNARY["neg"]) == (10, 11, 12, 13, 14, 15)
+assert [_BINARY[k] for k in ("min", "max", "+", "-", "*", "/", "%")] == [20, 21, 22, 23, 24, 25, 26]
 
 
 def live_tensors() -> int:
