@@ -592,3 +592,18 @@ def test_a_failing_compilation_wakes_its_waiters():
     assert results == [-6] * 24
     k = (cuda.Tensor.random([8, 8], seed=1) + cuda.Tensor.fill(1.0, [8, 8])).compile()
     assert k.info.kind == 0
+
+
+def test_every_python_operator_reaches_its_node_kind():
+    """the Python view binds its operators to the C ABI's node codes directly: each must produce its own operation in the kernel text"""
+    import re
+
+    T = cuda.Tensor
+    a, b = T.random([8, 8], seed=1), T.random([8, 8], seed=2)
+    want = {"+": (a + b, "(_0+_1)"), "-": (a - b, "(_0-_1)"), "*": (a * b, "(_0*_1)"), "/": (a / b, "(_0/_1)"), "%": (a % b, "fmodf(_0,_1)"),
+            "neg": (-a, "(-_0)"), "min": (T.min(a, b), "fminf(_0,_1)"), "max": (T.max(a, b), "fmaxf(_0,_1)"), "abs": (T.abs(a), "fabsf(_0)"),
+            "sqrt": (T.sqrt(a), "sqrtf(_0)"), "tanh": (T.tanh(a), "cc_tanh(_0)"), "exp": (T.exp(a), "cc_exp(_0)"), "log": (T.log(a), "cc_log(_0)")}
+    for name, (e, text) in want.items():
+        lines = [l.replace(" ", "") for l in e.compile().source.split("\n") if re.match(r"\s*const float _[12] = ", l)]
+        assert lines and text in lines[-1], (name, lines[-1:])
+    assert (+a) is a
