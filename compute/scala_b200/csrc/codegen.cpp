@@ -1584,6 +1584,61 @@ void emit_reduce(Plan& plan, const Program& p, int n_args, const DeviceProps& de
         for (int x = no - 2; x >= 0; --x) ostride[(size_t)x] = ostride[(size_t)x + 1] * odims[(size_t)x + 1];
         std::string gsp;  // ", g0, ..., (gt_ + p_), ..., g{no-1}"
         for (int x = 0; x < no; ++x) gsp += x == dp ? std::string(", (gt_ + p_)") : strprintf(", g%d", x);
+        // Sliding window: a load whose address and bounds depend on the tiled dimension and on ONE reduction digit dk only through
+        // their sum or difference (the translated input of a convolution: pixel p with kernel column kx reads what pixel p + 1
+        // reads with kx + 1 ... ) is read once per distinct element into a register window, outside the dk loop, instead of P x KW
+        // times; neither NVVM nor ptxas merges those loads on its own. Only for fully unrolled reductions with a small window.
+        int jw = -1, dk = -1, sgn = 0;
+        int64_t inner = 1;  // product of the reduction digits nested inside dk
+        for (int j = 0; j < nloads && jw < 0 && T <= 96; ++j) {
+          const Load& L = p.loads[j];
+          if (in_post(j) || !L.integer || L.coef[dp] == 0 || L.coef[no - 1] != 0) continue;  // (scalar across the V lanes)
+          bool lane_free = true;
+          for (int y = 0; y < L.rows; ++y) lane_free &= L.M[(size_t)y * (nd + 1) + (no - 1)] == 0.0;
+          if (!lane_free) continue;
+          for (int x = no; x < nd && jw < 0; ++x) {
+            for (int sg : {1, -1}) {
+              if (L.coef[x] != sg * L.coef[dp]) continue;
+              bool rows_ok = true;
+              for (int y = 0; y < L.rows; ++y) rows_ok &= L.M[(size_t)y * (nd + 1) + x] == sg * L.M[(size_t)y * (nd + 1) + dp];
+              if (!rows_ok) continue;
+              int64_t in_ = 1;
+              for (int z = x + 1; z < nd; ++z) in_ *= p.dims[z];
+              if (in_ * (P + p.dims[x] - 1) > 64 || p.dims[x] < 2) continue;
+              jw = j, dk = x, sgn = sg, inner = in_;
+              break;
+            }
+          }
+        }
+        if (jw >= 0) {
+          const int KW = (int)p.dims[dk], WN = P + KW - 1, umin = sgn > 0 ? 0 : -(KW - 1);
+          // ldw: the windowed operand alone, as a scalar; evw: the term with that operand handed in
+          e("__device__ __forceinline__ float ldw(%s", rgdecl.c_str());
+          for (int x = 0; x < no; ++x) e(", const %s g%d", IDX, x);
+          e("%s) {\n", params.c_str());
+          LoadCtx cs{1, -1, IDX};
+          emit_load(e, p, jw, cs, "  ");
+          e("  return L%d[0];\n}\n", jw);
+          e("__device__ __forceinline__ void evw(%s", rgdecl.c_str());
+          for (int x = 0; x < no; ++x) e(", const %s g%d", IDX, x);
+          e("%s, const float in_, float (&o)[%d]) {\n", params.c_str(), V);
+          LoadCtx cv{V, no - 1, IDX};
+          for (int j = 0; j < nloads; ++j) {
+            if (in_post(j)) continue;
+            if (j == jw)
+              e("  float L%d[%d];\n  #pragma unroll\n  for (int l = 0; l < %d; ++l) L%d[l] = in_;\n", j, V, V, j);
+            else
+              emit_load(e, p, j, cv, "  ");
+          }
+          e("  #pragma unroll\n  for (int l = 0; l < %d; ++l) {\n", V);
+          emit_op_list(e, p.ops, "    ", "l", p.results);
+          e("    o[l] = _%d;\n  }\n}\n", p.results[0]);
+          plan.note += strprintf("; sliding window of %d over reduction digit %d", WN, dk - no);
+        }
+        // reduction digits passed to ldw: g{dk} = 0 and the tiled position carries the whole offset
+        std::string rgs_w, gs_w;
+        for (int x = no; x < nd; ++x) rgs_w += std::string(x > no ? ", " : "") + (x == dk ? std::string("0") : strprintf("g%d", x));
+        for (int x = 0; x < no; ++x) gs_w += x == dp ? std::string(", (gt_ + u_)") : strprintf(", g%d", x);
         e("// register tile: %d positions along g%d per thread\n", P, dp);
         e("extern \"C\" __global__ void __launch_bounds__(256) reduce_cols(%s) {\n", param_list(n_args, true, "dst").c_str());
         e("  const %s v = (%s)blockIdx.x * 256 + threadIdx.x;\n  if (v >= %lld) return;\n", IDX, IDX, (long long)NVP);
@@ -1601,7 +1656,7 @@ void emit_reduce(Plan& plan, const Program& p, int n_args, const DeviceProps& de
           e("  const %s g0 = rem_;\n", IDX);
         e("  float acc[%d][%d];\n  #pragma unroll\n  for (int p_ = 0; p_ < %d; ++p_)\n    #pragma unroll\n    for (int l = 0; l < %d; ++l) acc[p_][l] = %s;\n", P, V, P, V, ZERO);
         std::string ind = "  ";
-        for (int x = no; x < nd; ++x) {
+        auto open_loop = [&](int x) {
           if (T <= 96)
             e("%s#pragma unroll\n", ind.c_str());
           else if (x == nd - 1)
@@ -1610,13 +1665,33 @@ void emit_reduce(Plan& plan, const Program& p, int n_args, const DeviceProps& de
             e("%s#pragma unroll 1\n", ind.c_str());
           e("%sfor (%s g%d = 0; g%d < %lld; ++g%d) {\n", ind.c_str(), IDX, x, x, (long long)p.dims[x], x);
           ind += "  ";
-        }
-        e("%s#pragma unroll\n%sfor (int p_ = 0; p_ < %d; ++p_) {\n", ind.c_str(), ind.c_str(), P);
-        e("%s  float x[%d];\n%s  evd(%s%s%s, x);\n", ind.c_str(), V, ind.c_str(), rgs.c_str(), gsp.c_str(), pass.c_str());
-        e("%s  #pragma unroll\n%s  for (int l = 0; l < %d; ++l) acc[p_][l] = %s;\n%s}\n", ind.c_str(), ind.c_str(), V, AP("acc[p_][l]", "x[l]").c_str(), ind.c_str());
-        for (int x = no; x < nd; ++x) {
+        };
+        auto close_loop = [&]() {
           ind.resize(ind.size() - 2);
           e("%s}\n", ind.c_str());
+        };
+        if (jw < 0) {
+          for (int x = no; x < nd; ++x) open_loop(x);
+          e("%s#pragma unroll\n%sfor (int p_ = 0; p_ < %d; ++p_) {\n", ind.c_str(), ind.c_str(), P);
+          e("%s  float x[%d];\n%s  evd(%s%s%s, x);\n", ind.c_str(), V, ind.c_str(), rgs.c_str(), gsp.c_str(), pass.c_str());
+          e("%s  #pragma unroll\n%s  for (int l = 0; l < %d; ++l) acc[p_][l] = %s;\n%s}\n", ind.c_str(), ind.c_str(), V, AP("acc[p_][l]", "x[l]").c_str(), ind.c_str());
+          for (int x = no; x < nd; ++x) close_loop();
+        } else {
+          const int KW = (int)p.dims[dk], WN = P + KW - 1, umin = sgn > 0 ? 0 : -(KW - 1);
+          // flat index of the digits nested inside dk (row-major), for the window's first subscript
+          std::string wi = "0";
+          for (int x = dk + 1; x < nd; ++x) wi = strprintf("(%s) * %lld + g%d", wi.c_str(), (long long)p.dims[x], x);
+          for (int x = no; x < dk; ++x) open_loop(x);
+          e("%sfloat win_[%lld][%d];\n", ind.c_str(), (long long)inner, WN);
+          for (int x = dk + 1; x < nd; ++x) open_loop(x);
+          e("%s#pragma unroll\n%sfor (int w_ = 0; w_ < %d; ++w_) {\n%s  const int u_ = w_ + (%d);\n%s  win_[%s][w_] = ldw(%s%s%s);\n%s}\n", ind.c_str(), ind.c_str(), WN, ind.c_str(), umin,
+            ind.c_str(), wi.c_str(), rgs_w.c_str(), gs_w.c_str(), pass.c_str(), ind.c_str());
+          for (int x = dk + 1; x < nd; ++x) close_loop();
+          for (int x = dk; x < nd; ++x) open_loop(x);  // the reference's term order: dk, then the digits nested inside it
+          e("%s#pragma unroll\n%sfor (int p_ = 0; p_ < %d; ++p_) {\n", ind.c_str(), ind.c_str(), P);
+          e("%s  float x[%d];\n%s  evw(%s%s%s, win_[%s][p_ + (%d) * (int)g%d - (%d)], x);\n", ind.c_str(), V, ind.c_str(), rgs.c_str(), gsp.c_str(), pass.c_str(), wi.c_str(), sgn, dk, umin);
+          e("%s  #pragma unroll\n%s  for (int l = 0; l < %d; ++l) acc[p_][l] = %s;\n%s}\n", ind.c_str(), ind.c_str(), V, AP("acc[p_][l]", "x[l]").c_str(), ind.c_str());
+          for (int x = no; x < nd; ++x) close_loop();
         }
         std::string lin = "(long long)0";
         for (int x = 0; x < no; ++x) lin += x == dp ? strprintf(" + (long long)(gt_ + p_) * %lldLL", (long long)ostride[(size_t)x]) : strprintf(" + (long long)g%d * %lldLL", x, (long long)ostride[(size_t)x]);

@@ -228,6 +228,23 @@ def test_register_tiled_reduction(monkeypatch, P):
                 outs.append(B.max(chain(terms) + bs[f].broadcast([2, 6, 8]), B.fill(0.0, [2, 6, 8])))  # bias + relu epilogue
             return B.join(outs)
         check(conv, f"register tile of {P} along output dim 2", 1)
+        check(conv, f"sliding window of {P + 2} over reduction digit 1", 1)  # the translated input: one load per distinct element of a kernel row
+
+        def conv_general(B, leaf, kh, kw, flip, depth, filters=4, shape=(1, 5, 12)):
+            """kh x kw window, correlation (flip = -1: x[w + kx - r], the window slides the other way) or convolution (flip = +1)"""
+            x, w = leaf(list(shape) + [depth], 1, -3.0), leaf([kh, kw, depth, filters], 2)
+            xs = x.split(3)
+            ws = [[[wc.split(0) for wc in wx.split(0)] for wx in wy.split(0)] for wy in w.split(0)]
+            outs = []
+            for f in range(filters):
+                terms = [xs[c].translate([0, flip * (dy - kh // 2), flip * (dx - kw // 2)]) * ws[dy][dx][c][f].broadcast(list(shape))
+                         for dy in range(kh) for dx in range(kw) for c in range(depth)]
+                outs.append(chain(terms))
+            return B.join(outs)
+        check(lambda B, leaf: conv_general(B, leaf, 1, 5, +1, 2), f"sliding window of {P + 4} over reduction digit 0", 1)   # 1 x 5 (digits: kx, c), padding -3
+        check(lambda B, leaf: conv_general(B, leaf, 3, 3, -1, 2), f"sliding window of {P + 2} over reduction digit 1", 1)   # the window slides the other way
+        check(lambda B, leaf: conv_general(B, leaf, 1, 3, +1, 20), f"register tile of {P} along output dim 2", 1)            # window too large for registers: tiled, not windowed
+        assert "sliding window" not in conv_general(T, lambda s, seed, pad=0.0: T.random(s, seed=seed, padding=pad), 1, 3, +1, 20).compile().source
         # a matmul-like term small enough to stay on the generic reduction: A[i, t] is shared along k's neighbour dimension
         def small_matmul(B, leaf):
             a, b = leaf([8, 12], 4), leaf([12, 16], 5)
