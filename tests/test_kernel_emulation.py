@@ -260,6 +260,21 @@ def test_register_tiled_reduction(monkeypatch, P):
     assert "register tile" not in chain(T.random([12, 8, 128], seed=1).split(0)).compile().source
 
 
+def test_matmul1_join_of_folds_rerolled_twice():
+    """benchmarks.scala:176-187: the result's columns are separate left folds over t of A[:, t] * B[t, c] (a scalar broadcast), joined:
+    the join is re-rolled into the output dimension c and every fold into a reduction over t -- one kernel, one reduction"""
+    def matmul1(B, leaf, m=24, k=9, n=16):
+        a, b = leaf([m, k], 1), leaf([k, n], 2)
+        cols_a = a.split(1)                      # k tensors of shape [m]
+        rows_b = [r.split(0) for r in b.split(0)]  # rows_b[t][c]: scalars
+        outs = []
+        for c in range(n):
+            outs.append(chain([cols_a[t] * rows_b[t][c].broadcast([m]) for t in range(k)]))
+        return B.join(outs)                      # [m, n]
+    check(matmul1, "join re-rolled into an output dimension", 1)
+    check(lambda B, leaf: matmul1(B, leaf, m=40, k=12, n=6), "join re-rolled into an output dimension", 1)  # n % 4 != 0: scalar lanes
+
+
 def test_whole_tensor_folds_and_iterated_maps():
     check(lambda B, leaf: (leaf([33, 20], 1) * leaf([33, 20], 2)).sum(), "whole-tensor fold", 4)
     check(lambda B, leaf: B.abs(leaf([4099], 3)).sum(), "whole-tensor fold", 4)
