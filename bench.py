@@ -112,44 +112,118 @@ def convolute(T, inp, weight, bias):
 # ---- reference arm: the CPU port of the generated kernel on the host cores -----------------------------------------------
 
 
-def cpu_c2(sample_elems: int, reps: int):
+def host_threads() -> int:
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
+
+
+def cpu_lib():
+    """the timed CPU baseline: oracle/oracle_cpu.c built ON THIS MACHINE with -O3 -march=native -fopenmp -ffast-math (BASELINE.md section 4;
+    -ffast-math is the host analogue of the reference's -cl-unsafe-math-optimizations and lets gcc call glibc's vector expf / logf / tanhf the
+    way POCL's work-group vectoriser would). The thread count is set explicitly: torchrun exports OMP_NUM_THREADS=1 to every rank."""
     from oracle import build as ob
 
-    ob.build()
-    L = ob.load("fma")
-    n = sample_elems
+    L = ob.load("native")
+    L.oracle_set_num_threads(host_threads())
+    return L
+
+
+def cpu_c2(n: int, warmup: int, reps: int, budget_s: float | None = None):
+    """reps timed passes of the generated C2 kernel over n elements on all host threads (after `warmup` untimed ones);
+    with a budget, reps shrinks so that the timed passes take about that long (never below 3)"""
+    L = cpu_lib()
     a, b, c, out = (np.empty(n, np.float32) for _ in range(4))
     for arr, seed in ((a, 1), (b, 2), (c, 3)):
         L.oracle_random(arr.ctypes.data, n, seed)
-    L.oracle_c2(a.ctypes.data, b.ctypes.data, c.ctypes.data, out.ctypes.data, n)  # warm-up (page faults, libm)
+    t0 = time.perf_counter()
+    L.oracle_c2(a.ctypes.data, b.ctypes.data, c.ctypes.data, out.ctypes.data, n)  # first pass: page faults of `out`, libm set-up
+    first = time.perf_counter() - t0
+    for _ in range(max(0, warmup - 1)):
+        L.oracle_c2(a.ctypes.data, b.ctypes.data, c.ctypes.data, out.ctypes.data, n)
+    if budget_s is not None:
+        reps = int(max(3, min(reps, budget_s / max(first, 1e-3))))
     times = []
     for _ in range(reps):
         t0 = time.perf_counter()
         L.oracle_c2(a.ctypes.data, b.ctypes.data, c.ctypes.data, out.ctypes.data, n)
         times.append(time.perf_counter() - t0)
+    # the fast-math build is the same kernel: its output stays within a few ulp-sized steps of the strict port's on a sample
+    from oracle import build as ob
+
+    m = min(n, 1 << 16)
+    strict = np.empty(m, np.float32)
+    ob.load("strict").oracle_c2(a.ctypes.data, b.ctypes.data, c.ctypes.data, strict.ctypes.data, m)
+    drift = float(np.abs(out[:m] - strict).max())
+    assert drift <= 5e-6, f"the -ffast-math CPU baseline drifted {drift} from the strict port"
     return times, int(L.oracle_num_threads()), out
+
+
+C2_WORKLOAD = "C2 long fused elementwise chain tanh(log(exp(a*b+c)+a)*b)+c"
+CPU_NOTE = ("the reference (Scala + LWJGL OpenCL on POCL) cannot run in this image (no JVM, no OpenCL ICD); this is the C/OpenMP port of the kernel it "
+            "generates (oracle/oracle_cpu.c), gcc -O3 -march=native -fopenmp -ffast-math built on this host, all host threads")
 
 
 def run_reference(args, rank: int):
     if rank != 0:
         return
-    log2n = int(os.environ.get("BENCH_REFERENCE_SAMPLE_LOG2", "26"))  # (shrunk by the CPU-only contract test)
+    # each step = one pass of the generated kernel over the FULL per-GPU workload (2^28 elements, the cuda arm's config);
+    # BENCH_REFERENCE_SAMPLE_LOG2 shrinks it for the CPU-only contract test
+    log2n = int(os.environ.get("BENCH_REFERENCE_SAMPLE_LOG2", "28"))
     n = 1 << log2n
-    # each step = one pass of the generated kernel over a 2^26-element sample (1/4 of the per-GPU workload)
-    times, cores, _ = cpu_c2(n, args.warmup + args.steps)
-    times = times[args.warmup:]
+    times, cores, _ = cpu_c2(n, args.warmup, args.steps)
     sec = sum(times) / len(times)
     gbs = BYTES_PER_ELEMENT * n / sec / 1e9
     line = {
         "impl": "reference", "metric": METRIC, "value": gbs, "unit": "GB/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "C2 long fused elementwise chain tanh(log(exp(a*b+c)+a)*b)+c", "elements_per_step": n,
-                   "note": "the reference (Scala + OpenCL/POCL) cannot run in this image (no JVM, no OpenCL ICD); this is the C/OpenMP port "
-                           "of the kernel it generates (oracle/oracle_cpu.c), all host threads"},
-        "cpu_baseline": {"value": gbs, "unit": "GB/s", "cores": cores, "kind": "port", "sample": f"2^{log2n} of 2^28 elements per step, {len(times)} steps"},
+        "config": {"workload": C2_WORKLOAD, "shape_per_gpu": [n // COLS, COLS] if n >= COLS else [1, n], "elements_per_gpu": n,
+                   "inputs": "Tensor.random seeds 1,2,3 (Wang hash), resident in host memory", "note": CPU_NOTE},
+        "cpu_baseline": {"value": gbs, "unit": "GB/s", "cores": cores, "kind": "port",
+                         "sample": f"all 2^{log2n} elements per step, {len(times)} timed steps after {args.warmup} warm-up passes"},
         "e2e": {"value": gbs, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     emit(line)
+
+
+def cpu_side_baselines() -> dict:
+    """C3 and C5 on the host, the way the reference's `cpu` backend runs them (bounded samples; reported beside the GPU figures)"""
+    L = cpu_lib()
+    cores = int(L.oracle_num_threads())
+    out = {}
+    n = 1 << 28
+    x = np.empty(n, np.float32)
+    L.oracle_random(x.ctypes.data, n, 5)
+    L.oracle_sum_cpu_order(x.ctypes.data, 1 << 20)
+    t0 = time.perf_counter()
+    L.oracle_sum_cpu_order(x.ctypes.data, n)
+    sec = time.perf_counter() - t0
+    out["C3 full sum 16384^2"] = {"value": 4 * n / sec / 1e9, "unit": "GB/s", "cores": 1, "kind": "port",
+                                 "sample": "one pass over all 2^28 elements; ONE thread, as the reference launches its CPU reduction "
+                                           "(global = local = 1, Tensors.scala:690-695)"}
+    for axis in (0, 1):
+        res = np.empty(ROWS, np.float32)
+        t0 = time.perf_counter()
+        L.oracle_axis_sum_2d(x.ctypes.data, ROWS, COLS, axis, res.ctypes.data)
+        sec = time.perf_counter() - t0
+        out[f"C3 axis-{axis} sum 16384^2"] = {"value": 4 * n / sec / 1e9, "unit": "GB/s", "cores": cores, "kind": "port",
+                                              "sample": "one pass; one work-item per output element, fp32 left fold over the split index"}
+    del x
+    m = 1024
+    a, b, c = (np.empty(m * m, np.float32) for _ in range(3))
+    L.oracle_random(a.ctypes.data, m * m, 9)
+    L.oracle_random(b.ctypes.data, m * m, 10)
+    L.oracle_matmul_left_fold(a.ctypes.data, b.ctypes.data, c.ctypes.data, m, m, m)
+    reps = 5
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        L.oracle_matmul_left_fold(a.ctypes.data, b.ctypes.data, c.ctypes.data, m, m, m)
+    sec = (time.perf_counter() - t0) / reps
+    out["C5 matmul as split/broadcast/sum"] = {"value": 2 * m**3 / sec / 1e12, "unit": "TFLOP/s", "cores": cores, "kind": "port",
+                                               "sample": f"1024^3 (the full 8192^3 cannot run on the reference at all: SURVEY finding 2), mean of {reps} passes, "
+                                                         "fp32 left fold per output row"}
+    return out
 
 
 # ---- cuda arm ---------------------------------------------------------------------------------------------------------------------
@@ -254,7 +328,12 @@ def side_configs(cuda, hbm_peak: float, tf_peak: float) -> dict:
         # C5 exactly as BASELINE.json words it: the matmul written as split / broadcast / sum (benchmarks.scala:188-191) through the lazy
         # Tensor API; the code generator re-rolls the 8192-term chain, sees the contraction through the fusion barrier and runs the
         # tcgen05 pipeline (the i*j*k product is never materialised)
-        A, B = T.randomNormal([n5, n5], seed=9).doCache(), T.randomNormal([n5, n5], seed=10).doCache()
+        # dataset N: randomNormal(seed 9, 10); its singular pair (+inf, NaN — in the reference too) is zeroed on the host
+        def dataset_n(seed):
+            h = np.nan_to_num(T.randomNormal([n5, n5], seed=seed).flatArray(), nan=0.0, posinf=0.0, neginf=0.0).reshape(n5, n5)
+            return T(h).doCache(), h
+
+        (A, ha5), (B, hb5) = dataset_n(9), dataset_n(10)
         product = A.broadcast([n5, n5, n5]) * B.reshape([1, n5, n5]).broadcast([n5, n5, n5])
         parts = product.split(1)
         acc = parts[0]
@@ -264,6 +343,17 @@ def side_configs(cuda, hbm_peak: float, tf_peak: float) -> dict:
         k = acc.compile()
         kind = k.info.kind
         k.release()
+        # value check BEFORE timing, on the kernel that is timed: sampled rows (both CTAs of a pair, first / middle / last tiles) against fp64
+        # on the scale |A|.|B| (north star: <= 1e-5), and the whole result through the checksum identity sum(C) = colsum(A) . rowsum(B)
+        c5 = acc.flatArray().reshape(n5, n5)
+        rows5 = np.r_[0:2, 127:130, 255:257, 4095:4097, 8190:8192]
+        a64, b64 = ha5[rows5].astype(np.float64), hb5.astype(np.float64)
+        err5 = float((np.abs(c5[rows5].astype(np.float64) - a64 @ b64) / (np.abs(a64) @ np.abs(b64))).max())
+        total, want_total = float(c5.astype(np.float64).sum()), float(ha5.astype(np.float64).sum(axis=0) @ b64.sum(axis=1))
+        scale_total = float(np.abs(ha5).astype(np.float64).sum(axis=0) @ np.abs(b64).sum(axis=1))
+        c5_check = {"max_err_over_absA_absB_sampled_rows": err5, "bar": 1e-5, "checksum_rel_err": abs(total - want_total) / scale_total,
+                    "verified": bool(err5 <= 1e-5 and abs(total - want_total) <= 1e-5 * scale_total)}
+        del c5, a64, b64, ha5, hb5
 
         def step():
             acc.doBuffer().release()
@@ -274,7 +364,8 @@ def side_configs(cuda, hbm_peak: float, tf_peak: float) -> dict:
         per = ms / 5
         tf = 2 * n5**3 / per / 1e9
         out["C5 matmul 8192^3 as split/broadcast/sum (3xTF32 tcgen05, CTA pairs)"] = {
-            "ms": per, "tflops": tf, "frac_of_3xtf32_peak": tf / tf_peak, "kernels_per_step": launches / 5, "plan": kind}
+            "ms": per, "tflops": tf, "frac_of_3xtf32_peak": tf / tf_peak, "kernels_per_step": launches / 5, "plan": kind,
+            "data": "dataset N: randomNormal(seed 9, 10), non-finite pair zeroed", "check": c5_check}
         # ... and with B unchanged between steps (weights): its panels are split once and kept by the runtime
         cuda.set_operand_cache(True)
         ms, launches, _, _ = time_steps(cuda, step, 5, 2)
@@ -466,7 +557,7 @@ def run_cuda(args, rank: int, local_rank: int, world: int):
         line = {
             "metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "C2 long fused elementwise chain tanh(log(exp(a*b+c)+a)*b)+c", "shape_per_gpu": shape, "elements_per_gpu": n,
+            "config": {"workload": C2_WORKLOAD, "shape_per_gpu": shape, "elements_per_gpu": n,
                        "inputs": "Tensor.random seeds 1,2,3 (Wang hash), cached in HBM", "l2": "inputs (3 GiB) and output (1 GiB) are far larger than the 126 MB L2",
                        "sharding": "leading axis, no collective", "e2e_chunks": chunks},
             "gpu_launches": int(launches),
@@ -477,10 +568,14 @@ def run_cuda(args, rank: int, local_rank: int, world: int):
             "e2e": {"value": e2e_value, "unit": "GB/s", "h2d_bytes_per_step": 3 * n * 4, "d2h_bytes_per_step": n * 4, "ms_per_step": e2e_sec * 1e3,
                     "steps": e2e_steps, "result_matches_device_path": e2e_ok},
         }
+        # dram__bytes_read.sum + dram__bytes_write.sum of this kernel cannot be measured by a plain run: the figure is the constant that the
+        # committed `ncu --set full` capture of the same kernel / same shape reports (profiles/), labelled as such
         traffic_file = os.path.join(ROOT, "profiles", "c2_traffic_bytes.json")
-        if os.path.exists(traffic_file):
+        if os.path.exists(traffic_file) and rows == ROWS:
             try:
-                line["roofline"]["traffic"] = json.load(open(traffic_file)).get("dram_bytes_per_launch")
+                tj = json.load(open(traffic_file))
+                line["roofline"]["traffic"] = tj.get("dram_bytes_per_launch")
+                line["roofline"]["traffic_source"] = "constant from profiles/c2_traffic_bytes.json <- " + str(tj.get("source", "ncu --set full capture")) + " (not measured in this run)"
             except Exception:
                 pass
     for h in (ha, hb, hc, ho):
@@ -490,13 +585,21 @@ def run_cuda(args, rank: int, local_rank: int, world: int):
         if not args.no_side_configs:
             del a, b, c, expr
             line["configs"] = side_configs(cuda, hbm_peak, tf_peak)
-        if not args.no_cpu_baseline:  # last: ~5 s during which the GPU idles and drops its clocks
-            reps = 40  # each pass: 2^26 elements = 1 GiB of algorithmic bytes
-            times, cores, _ = cpu_c2(1 << 26, reps)
-            sec = min(times)
-            line["cpu_baseline"] = {"value": BYTES_PER_ELEMENT * (1 << 26) / sec / 1e9, "unit": "GB/s", "cores": cores, "kind": "port",
-                                    "sample": f"2^26 of 2^28 elements, best of {reps} passes ({sum(times):.1f} s of wall clock on {cores} threads), "
-                                              "C/OpenMP port of the generated kernel (oracle/oracle_cpu.c)"}
+        if not args.no_cpu_baseline:  # last: ~20 s during which the GPU idles and drops its clocks
+            log2n = int(os.environ.get("BENCH_REFERENCE_SAMPLE_LOG2", "28"))
+            times, cores, _ = cpu_c2(1 << log2n, 1, 40, budget_s=10.0)
+            sec = sum(times) / len(times)
+            line["cpu_baseline"] = {"value": BYTES_PER_ELEMENT * (1 << log2n) / sec / 1e9, "unit": "GB/s", "cores": cores, "kind": "port",
+                                    "sample": f"all 2^{log2n} elements per pass (the cuda arm's workload), mean of {len(times)} passes "
+                                              f"({sum(times):.1f} s of wall clock on {cores} threads); " + CPU_NOTE}
+            if not args.no_side_configs and log2n == 28:
+                try:
+                    for name, rec in cpu_side_baselines().items():
+                        for key in line.get("configs", {}):
+                            if key.startswith(name):
+                                line["configs"][key]["cpu_baseline"] = rec
+                except Exception as e:
+                    line["cpu_baseline"]["side_error"] = str(e)[:200]
     if world > 1 and not args.no_side_configs:
         pk2, _ = peaks()
         sc = sharded_configs(cuda, dist, rank, world, float(pk2["hbm_gbs"]), float(pk2.get("bf16_tflops", 1590.0)) / 6)
@@ -538,7 +641,9 @@ def main():
     ap.add_argument("--no-side-configs", action="store_true")
     ap.add_argument("--short-side", action="store_true", help="few steps per side config (for ncu launch lists)")
     args = ap.parse_args()
-    args.warmup = max(args.warmup, 3)
+    if args.warmup < 3:
+        sys.stderr.write(f"bench.py: --warmup {args.warmup} raised to 3 (the timing rules require W >= 3); the JSON line reports 3\n")
+        args.warmup = 3
     global SHORT_SIDE
     SHORT_SIDE = args.short_side
     rank = int(os.environ.get("RANK", "0"))

@@ -1,6 +1,10 @@
 """TEST INFRASTRUCTURE ONLY — builds oracle/oracle_cpu.c (gcc + OpenMP) into oracle/_build/.
 Two variants bracket what FP_CONTRACT ON + -cl-unsafe-math-optimizations allow the reference's OpenCL compiler to do
-(OpenCL.scala:1131-1135): `strict` (-ffp-contract=off) and `fma` (-ffp-contract=fast -mfma)."""
+(OpenCL.scala:1131-1135): `strict` (-ffp-contract=off) and `fma` (-ffp-contract=fast -mfma); they are the CHECKERS.
+A third, `native` (-O3 -march=native -fopenmp -ffast-math: the flags BASELINE.md section 4 states plus the host analogue of
+-cl-unsafe-math-optimizations, which lets gcc call glibc's vector expf / logf / tanhf as POCL's vectoriser would), is the one bench.py
+TIMES as the CPU baseline. -march=native code must not travel between machines, so that variant is built on the machine that runs it
+(file name keyed by the CPU's flag set) and never by __graft_entry__.build()."""
 from __future__ import annotations
 
 import ctypes as C
@@ -16,8 +20,38 @@ VARIANTS = {
 }
 
 
+NATIVE_FLAGS = ["-O3", "-march=native", "-fopenmp", "-ffast-math"]
+
+
+def _cpu_tag() -> str:
+    import hashlib
+
+    try:
+        flags = next(l for l in open("/proc/cpuinfo") if l.startswith("flags"))
+    except Exception:
+        flags = "unknown"
+    return hashlib.sha1(flags.encode()).hexdigest()[:10]
+
+
 def lib_path(variant: str = "strict") -> str:
+    if variant == "native":
+        return os.path.join(OUT, f"liboracle_cpu_native_{_cpu_tag()}.so")
     return os.path.join(OUT, f"liboracle_cpu_{variant}.so")
+
+
+def build_native() -> str:
+    """the timed CPU baseline: built where it runs (see the module docstring); falls back to the `fma` variant's flags + -ffast-math if
+    this gcc rejects -march=native for the host"""
+    os.makedirs(OUT, exist_ok=True)
+    out = lib_path("native")
+    if os.path.exists(out) and os.path.getmtime(out) >= os.path.getmtime(SRC):
+        return out
+    for flags in (NATIVE_FLAGS, ["-O3", "-mavx2", "-mfma", "-fopenmp", "-ffast-math"]):
+        r = subprocess.run(["gcc", "-shared", "-fPIC", SRC, "-o", out + ".tmp", "-lm"] + flags, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+        if r.returncode == 0:
+            os.replace(out + ".tmp", out)
+            return out
+    raise RuntimeError("building the native oracle variant failed:\n" + r.stdout.decode(errors="replace"))
 
 
 def build(force: bool = False) -> None:
@@ -34,11 +68,14 @@ _libs: dict = {}
 
 def load(variant: str = "strict") -> C.CDLL:
     if variant not in _libs:
-        if not os.path.exists(lib_path(variant)):
+        if variant == "native":
+            build_native()
+        elif not os.path.exists(lib_path(variant)):
             build()
         L = C.CDLL(lib_path(variant))
         fp, i64 = C.c_void_p, C.c_int64
         L.oracle_num_threads.restype = C.c_int
+        L.oracle_set_num_threads.argtypes = [C.c_int]
         L.oracle_random.argtypes = [fp, i64, C.c_uint32]
         L.oracle_c1.argtypes = [fp, fp, fp, fp, i64]
         L.oracle_c2.argtypes = [fp, fp, fp, fp, i64]

@@ -28,6 +28,16 @@ int oracle_num_threads(void) {
 #endif
 }
 
+/* torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU baseline must still use all host cores (as POCL spreads work-groups over
+ * every core, README.md:26-34), so bench.py sets the count explicitly */
+void oracle_set_num_threads(int n) {
+#ifdef _OPENMP
+  if (n >= 1) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
 /* T:106-117 */
 static inline uint32_t wang_hash(uint32_t value) {
   value = (value ^ 61u) ^ (value >> 16);

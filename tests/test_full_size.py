@@ -155,3 +155,48 @@ def test_c5_matmul_pattern_8192(cuda):
     rows = np.r_[0:4, 255:258, 4095:4098, 8188:8192]
     assert np.array_equal(c[rows].astype(np.float64), a[rows].astype(np.float64) @ b.astype(np.float64))
     assert float(c.astype(np.float64).sum()) == float(a.astype(np.float64).sum(axis=0) @ b.astype(np.float64).sum(axis=1))
+
+
+def test_c5_matmul_pattern_8192_dataset_n(cuda):
+    """C5 at BASELINE size on dataset N (A, B = randomNormal(seed 9, 10)) THROUGH the split / broadcast / sum pattern
+    (benchmarks.scala:188-191), i.e. on the CTA-pair kernel with non-zero lo panels. Bar: max|D| / (|A| . |B|) <= 1e-5 against the
+    reference's fp32 left fold (oracle_matmul_left_fold restates the generated kernel's `acc = acc + a*b` chain) and against fp64,
+    on sampled rows spread over both CTAs of a pair, several tiles and the matrix edges; plus the checksum identity in fp64."""
+    T = cuda.Tensor
+    n = 8192
+    # randomNormal's singular pair (hash(61) = 0 => elements 2 * (61 ^ seed), +1 are (+inf, NaN), in the reference too) is zeroed on the host
+    def dataset_n(seed):
+        h = T.randomNormal([n, n], seed=seed).flatArray()
+        assert np.allclose(h[:4096], ref.random_normal_buffer(4096, seed), rtol=1e-4, atol=1e-6, equal_nan=True)  # the reference's stream
+        assert (~np.isfinite(h)).sum() <= 2
+        h = np.nan_to_num(h, nan=0.0, posinf=0.0, neginf=0.0).reshape(n, n)
+        return T(h).doCache(), h
+
+    (A, a), (B, b) = dataset_n(9), dataset_n(10)
+    product = A.broadcast([n, n, n]) * B.reshape([1, n, n]).broadcast([n, n, n])
+    parts = product.split(1)
+    acc = parts[0]
+    for p in parts[1:]:
+        acc = acc + p
+    kern = acc.compile()
+    assert kern.info.kind == 2 and kern.info.flops == 2 * n**3
+    c = acc.flatArray().reshape(n, n)
+    rows = np.r_[0:2, 127:130, 255:258, 4000:4002, 6143:6146, 8190:8192]
+    ar = np.ascontiguousarray(a[rows])
+    a64, b64 = ar.astype(np.float64), b.astype(np.float64)
+    truth = a64 @ b64
+    scale = np.abs(a64) @ np.abs(b64)
+    got = c[rows].astype(np.float64)
+    err64 = float((np.abs(got - truth) / scale).max())
+    lf = np.empty((len(rows), n), np.float32)
+    ob.load("strict").oracle_matmul_left_fold(ar.ctypes.data, b.ctypes.data, lf.ctypes.data, len(rows), n, n)
+    err_lf = float((np.abs(got - lf.astype(np.float64)) / scale).max())
+    ref_err = float((np.abs(lf.astype(np.float64) - truth) / scale).max())
+    print(f"C5 dataset N: cuda vs fp64 {err64:.2e}, cuda vs reference left fold {err_lf:.2e}, reference left fold vs fp64 {ref_err:.2e}")
+    assert err_lf <= 1e-5 and err64 <= 1e-5  # the north star's bar
+    assert err64 <= 2e-6  # what 3xTF32 delivers; single-pass TF32 would sit near 2e-4
+    # checksum over the whole result (every tile of every CTA): sum(C) = colsum(A) . rowsum(B), both sides in fp64
+    total = float(c.astype(np.float64).sum())
+    want_total = float(a.astype(np.float64).sum(axis=0) @ b.astype(np.float64).sum(axis=1))
+    bound = 1e-5 * float(np.abs(a).astype(np.float64).sum(axis=0) @ np.abs(b).astype(np.float64).sum(axis=1)) / n  # errors average out
+    assert abs(total - want_total) <= bound, (total, want_total, bound)

@@ -150,6 +150,56 @@ def test_fp32_accuracy_3xtf32(cuda, m, n, k):
     assert (np.abs(got - lf.astype(np.float64)) / scale).max() <= 1e-5
 
 
+def accuracy(got, a, b):
+    """max |got - truth| / (|A| . |B|), truth in fp64 — the scale BASELINE.md section 3 (C5, dataset N) states the 1e-5 bar on"""
+    a64, b64 = a.astype(np.float64), b.astype(np.float64)
+    return float((np.abs(got.astype(np.float64) - a64 @ b64) / (np.abs(a64) @ np.abs(b64))).max())
+
+
+@pytest.mark.parametrize("config", [512, 256, 128, 64])
+@pytest.mark.parametrize("m,n,k", [(512, 768, 2048), (384, 520, 8192)])
+def test_fp32_accuracy_on_normal_data_every_tile_configuration(cuda, monkeypatch, config, m, n, k):
+    """dataset N (randomNormal: lo panels non-zero) on EVERY tile configuration incl. the CTA-pair kernel that carries the C5 number:
+    a wrong lo tile, descriptor or half of B on CTA 1 shows up here as a TF32-sized (1e-4..1e-3) error"""
+    monkeypatch.setenv("CC_GEMM_FORCE_CONFIG", str(config))
+    a = finite_normal(m * k, 9).reshape(m, k)
+    b = finite_normal(k * n, 10).reshape(k, n)
+    got = run_matmul(cuda, a, b)
+    err = accuracy(got, a, b)
+    assert err <= 5e-6, err  # north star 1e-5; 3xTF32 measured 2.8e-6 at K = 2048
+    from oracle import build as ob
+
+    lf = np.empty((m, n), np.float32)
+    ob.load("strict").oracle_matmul_left_fold(a.ctypes.data, b.ctypes.data, lf.ctypes.data, m, k, n)
+    scale = np.abs(a.astype(np.float64)) @ np.abs(b.astype(np.float64))
+    assert (np.abs(got.astype(np.float64) - lf.astype(np.float64)) / scale).max() <= 1e-5  # vs the reference's fp32 left fold
+
+
+@pytest.mark.parametrize("config", [512, 256, 128, 64])
+@pytest.mark.parametrize("which", ["a_lo", "b_lo", "both"])
+def test_each_cross_term_is_needed(cuda, monkeypatch, config, which):
+    """lo-sensitivity: entries 1 + j * 2^-16 (j < 64) have hi = 1 and ALL their information in lo. With `a_lo` only A carries such entries
+    (B is small integers, exactly TF32), so the result is right only if the A_lo . B_hi MMAs ran on the right tiles; `b_lo` is the mirror
+    image for A_hi . B_lo. Dropping either cross term leaves an error of ~5e-4 relative, 100x the bar; lo . lo (dropped by design) is
+    2^-22. Values depend on the position, so a swapped half of B on CTA 1 or a stale stage cannot cancel."""
+    monkeypatch.setenv("CC_GEMM_FORCE_CONFIG", str(config))
+    m, n, k = 512, 768, 512
+    rng = np.random.default_rng(config + len(which))
+    fine = lambda shape: (1.0 + rng.integers(0, 64, shape) * 2.0**-16).astype(np.float32)
+    ints = lambda shape: rng.integers(1, 5, shape).astype(np.float32)
+    a = fine((m, k)) if which in ("a_lo", "both") else ints((m, k))
+    b = fine((k, n)) if which in ("b_lo", "both") else ints((k, n))
+    got = run_matmul(cuda, a, b)
+    truth = a.astype(np.float64) @ b.astype(np.float64)
+    rel = float((np.abs(got.astype(np.float64) - truth) / truth).max())  # all entries positive: |A|.|B| = A.B
+    assert rel <= 5e-6, rel  # fp32 accumulation over K = 512 (the tensor core's adds), far below the 3e-4 of a missing term
+    # the same product with the lo information removed is far outside the bar, i.e. the assertion above has teeth
+    hi_only = lambda x: (x.view(np.uint32) & np.uint32(0xFFFFE000)).view(np.float32)
+    a_h = hi_only(a) if which in ("a_lo", "both") else a
+    b_h = hi_only(b) if which in ("b_lo", "both") else b
+    assert float((np.abs(a_h.astype(np.float64) @ b_h.astype(np.float64) - truth) / truth).max()) >= 2e-4
+
+
 def test_pattern_lowers_to_tcgen05(cuda):
     """matmul written the way benchmarks.scala:188-191 writes it runs on the tensor cores and never materialises i*j*k"""
     T = cuda.Tensor

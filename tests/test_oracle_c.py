@@ -92,14 +92,17 @@ def test_bench_reference_arm_prints_the_contract_line():
 
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, "bench.py", "--impl", "reference", "--steps", "2", "--warmup", "3"], capture_output=True, text=True, cwd=root,
-                       env=dict(os.environ, BENCH_REFERENCE_SAMPLE_LOG2="20"), timeout=300)
+                       env=dict(os.environ, BENCH_REFERENCE_SAMPLE_LOG2="20", OMP_NUM_THREADS="1"), timeout=300)
     assert r.returncode == 0, r.stderr[-1000:]
     lines = [l for l in r.stdout.splitlines() if l.strip()]
     assert len(lines) == 1
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["unit"] == "GB/s" and d["higher_is_better"] is True and d["n_gpus"] == 1
     assert d["steps"] == 2 and d["warmup"] >= 3 and d["value"] > 0 and d["ms_per_step"] > 0
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] == d["value"]
+    # torchrun exports OMP_NUM_THREADS=1 to every rank (as this test does): the reference arm still uses every host thread
+    assert d["cpu_baseline"]["cores"] == len(os.sched_getaffinity(0))
+    assert d["config"]["workload"].startswith("C2 long fused elementwise chain") and d["config"]["elements_per_gpu"] == 1 << 20
     assert d["e2e"] == {"value": d["value"], "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"] and "model" not in d["config"]
     assert d["metric"].startswith("fused elementwise HBM GB/s")
