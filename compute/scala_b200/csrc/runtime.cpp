@@ -1248,6 +1248,42 @@ int cc_kernel_cache_size(uint64_t* out) {
   });
 }
 
+int cc_kernel_cache_lookup(const void* blob, uint64_t n_bytes, int any_out_shape, cc_kernel* out) {
+  return guarded([&] {
+    CC_REQUIRE(out, CC_ERR_ILLEGAL_ARGUMENT, "null output");
+    *out = 0;
+    Tree t = parse_tree(blob, n_bytes);
+    canonicalize(t);
+    Lock lock;
+    Runtime& r = rt();
+    Kernel* found = nullptr;
+    if (!any_out_shape) {
+      auto it = r.cache.find(t.key);
+      if (it != r.cache.end()) found = it->second;
+    } else {
+      // the key starts with the output shape (u32 rank, u32 dims[rank]); everything after it is the structure of the term
+      auto tail = [](const std::string& key) {
+        uint32_t rank = 0;
+        if (key.size() >= 4) memcpy(&rank, key.data(), 4);
+        const size_t skip = 4 + 4 * (size_t)rank;
+        return skip <= key.size() ? std::make_pair(key.data() + skip, key.size() - skip) : std::make_pair(key.data(), (size_t)0);
+      };
+      const auto want = tail(t.key);
+      for (auto& kv : r.cache) {
+        const auto have = tail(kv.first);
+        if (have.second == want.second && memcmp(have.first, want.first, want.second) == 0) {
+          found = kv.second;
+          break;
+        }
+      }
+    }
+    if (found) {
+      found->rc.fetch_add(1);
+      *out = (cc_kernel)(uintptr_t)found;
+    }
+  });
+}
+
 int cc_kernel_retain(cc_kernel h) {
   return guarded([&] {
     Lock lock;

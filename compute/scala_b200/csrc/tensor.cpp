@@ -393,8 +393,7 @@ struct JoinTensor final : NonInlineTensor {
   }
 };
 
-cc_kernel compile_closure(Tensor::EmitCtx& ctx, uint32_t root, const Shape& out_shape, bool attach_definitions,
-                          std::vector<uint64_t>* ids) {
+std::string finish_blob(Tensor::EmitCtx& ctx, uint32_t root, const Shape& out_shape, bool attach_definitions) {
   if (attach_definitions) {
     // let the code generator look through the fusion barrier: an ArrayParameter produced by a not-yet-evaluated
     // InlineTensor carries that tensor's closure (one level deep)
@@ -405,7 +404,12 @@ cc_kernel compile_closure(Tensor::EmitCtx& ctx, uint32_t root, const Shape& out_
         ctx.w.set_definition(ctx.param_nodes.at(p), (int32_t)def);
       }
   }
-  std::string blob = ctx.w.finish(root, out_shape);
+  return ctx.w.finish(root, out_shape);
+}
+
+cc_kernel compile_closure(Tensor::EmitCtx& ctx, uint32_t root, const Shape& out_shape, bool attach_definitions,
+                          std::vector<uint64_t>* ids) {
+  std::string blob = finish_blob(ctx, root, out_shape, attach_definitions);
   cc_kernel k = 0;
   int n = 0;
   std::vector<uint64_t> tmp(ctx.params.size() + 1);
@@ -494,18 +498,22 @@ PendingBuffer Tensor::do_buffer(Session& s) const {
   return {b, 0};
 }
 
+uint32_t Tensor::emit_root_for_compile(EmitCtx& ctx) const {
+  if (auto j = dynamic_cast<const JoinTensor*>(this)) return j->emit_root(ctx);
+  if (auto r = dynamic_cast<const ReduceTensor*>(this)) return r->emit_root(ctx);
+  return closure(ctx);
+}
+
 cc_kernel Tensor::compile_only() const {
   EmitCtx ctx;
-  if (auto j = dynamic_cast<const JoinTensor*>(this)) {
-    uint32_t root = j->emit_root(ctx);
-    return compile_closure(ctx, root, shape, true, nullptr);
-  }
-  if (auto r = dynamic_cast<const ReduceTensor*>(this)) {
-    uint32_t root = r->emit_root(ctx);
-    return compile_closure(ctx, root, shape, true, nullptr);
-  }
-  uint32_t root = closure(ctx);
+  uint32_t root = emit_root_for_compile(ctx);
   return compile_closure(ctx, root, shape, true, nullptr);
+}
+
+std::string Tensor::tree_blob() const {
+  EmitCtx ctx;
+  uint32_t root = emit_root_for_compile(ctx);
+  return finish_blob(ctx, root, shape, true);
 }
 
 // ---- factories ----------------------------------------------------------------------------------------------------------------
@@ -551,9 +559,13 @@ Shape auto_broadcast_shape(const Shape& s1, const Shape& s2) {
   Shape out;
   const size_t n = std::max(s1.size(), s2.size());
   for (size_t i = 0; i < n; ++i) {
-    if (i >= s1.size() || s1[i] == 1)
+    if (i >= s1.size() || s1[i] == 1) {
+      // (a unit dimension of the longer shape facing no dimension at all: the reference indexes past the shorter array here and dies
+      // with ArrayIndexOutOfBoundsException, Tensors.scala:210-211)
+      CC_REQUIRE(i < s2.size(), CC_ERR_ILLEGAL_ARGUMENT, "Failed to automatically broadcast between shape %s and %s", shape_str(s1).c_str(),
+                 shape_str(s2).c_str());
       out.push_back(s2[i]);
-    else if (i >= s2.size() || s2[i] == 1)
+    } else if (i >= s2.size() || s2[i] == 1)
       out.push_back(s1[i]);
     else if (s1[i] == s2[i])
       out.push_back(s1[i]);
@@ -1047,6 +1059,16 @@ int ct_do_buffer(ct_tensor t, cc_buffer* out, cc_event* out_event) {
 }
 int ct_compile(ct_tensor t, cc_kernel* out) {
   return guarded([&] { *out = ref(t)->compile_only(); });
+}
+int ct_tree_blob(ct_tensor t, void* out, uint64_t capacity, uint64_t* out_needed) {
+  return guarded([&] {
+    std::string blob = ref(t)->tree_blob();
+    if (out_needed) *out_needed = blob.size();
+    if (out) {
+      CC_REQUIRE(capacity >= blob.size(), CC_ERR_ILLEGAL_ARGUMENT, "blob of %zu bytes does not fit in %llu", blob.size(), (unsigned long long)capacity);
+      memcpy(out, blob.data(), blob.size());
+    }
+  });
 }
 int ct_release(ct_tensor t) {
   return guarded([&] {

@@ -79,6 +79,8 @@ class Tensor : public std::enable_shared_from_this<Tensor> {
   }
   // compile only (no device work): the kernel this tensor's closure maps to
   cc_kernel compile_only() const;
+  std::string tree_blob() const;  // the blob compile_only() hands to cc_compile_ex
+  uint32_t emit_root_for_compile(EmitCtx& ctx) const;
 
   // ---- delayed operators (Tensors.scala:816-1074) ----
   TensorPtr broadcast(const Shape& new_shape);

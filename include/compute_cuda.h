@@ -161,6 +161,10 @@ int cc_kernel_disk_cache(const char* directory);
 int cc_kernel_cache_limit(uint64_t max_kernels);
 int cc_kernel_cache_clear(void);
 int cc_kernel_cache_size(uint64_t* out);
+/* kernelCache.getIfPresent (T:1293; TensorsSpec.scala:50-52): probe only, never compiles. `*out` = the cached kernel with the
+ * blob's structure, retained for the caller, or 0. The library's key includes the output shape (the reference's kernels take it at
+ * launch, T:1373); with `any_out_shape` != 0 the shape in the blob header is ignored and any cached output shape matches. */
+int cc_kernel_cache_lookup(const void* tree_blob, uint64_t n_bytes, int any_out_shape, cc_kernel* out);
 int cc_kernel_retain(cc_kernel k);
 int cc_kernel_release(cc_kernel k);
 
@@ -321,6 +325,9 @@ int ct_to_string(ct_tensor t, char* out, uint64_t capacity, uint64_t* out_needed
 int ct_do_buffer(ct_tensor t, cc_buffer* out, cc_event* out_event);
 /* the kernel the tensor's closure compiles to, without running it (for tests of cache / pattern behaviour) */
 int ct_compile(ct_tensor t, cc_kernel* out);
+/* the tree blob ct_compile hands to cc_compile_ex for this tensor (definitions attached) — introspection: tests pin the blob a JVM
+ * front end must write (scala/.../CudaTreeWriter.scala) against it. Call with out = NULL to size (*out_needed). */
+int ct_tree_blob(ct_tensor t, void* out, uint64_t capacity, uint64_t* out_needed);
 int ct_release(ct_tensor t);
 int ct_live_tensors(int64_t* out);
 
