@@ -379,9 +379,28 @@ def side_configs(cuda, hbm_peak: float, tf_peak: float) -> dict:
     return out
 
 
+def np_random(n: int, seed: int, first: int = 0) -> np.ndarray:
+    """Tensor.random's stream on the host (Tensors.scala:106-117, 432-443): wang_hash(i ^ seed) / 2^32 for i in [first, first + n) — the
+    checker of the sharded legs (numpy only: the cuda arm never touches oracle/)"""
+    v = (np.arange(first, first + n, dtype=np.uint64) & 0xFFFFFFFF).astype(np.uint32) ^ np.uint32(seed & 0xFFFFFFFF)
+    v = (v ^ np.uint32(61)) ^ (v >> np.uint32(16))
+    v = v * np.uint32(9)
+    v = v ^ (v << np.uint32(4))
+    v = v * np.uint32(0x27D4EB2D)
+    v = v ^ (v >> np.uint32(15))
+    return (v.astype(np.float32) / np.float32(4294967296.0)).astype(np.float32)
+
+
+def np_dataset_e(n: int, seed: int, first: int = 0) -> np.ndarray:
+    """dataset E: floor(random * 9) - 4, integers in {-4..5}: every summation order is exact"""
+    return np.floor(np_random(n, seed, first) * np.float32(9.0)) - np.float32(4.0)
+
+
 def sharded_configs(cuda, dist, rank: int, world: int, hbm_peak: float, tf_peak: float) -> dict:
-    """C3 (16384^2, rows/N per GPU, NCCL combine of the partials) and C5 (8192^3, A and C row-sharded, B replicated) at N GPUs.
-    Strong scaling of the fixed BASELINE sizes; every time is the max over ranks of the device time including the collective."""
+    """C3 (16384^2, rows/N per GPU, partial sums combined over NVLink) and C5 (8192^3, A and C row-sharded, B replicated) at N GPUs, written
+    as the SAME Tensor-API expressions as on one GPU over `.shard()`ed row blocks (include/compute_cuda.h: ct_shard / ct_gather). Strong
+    scaling of the fixed BASELINE sizes; every time is the max over ranks of the device time including the exchange. Every result is
+    compared with numpy on dataset E (exact in any order) BEFORE it is timed; `verified` records it."""
     import torch
 
     from compute.scala_b200 import sharding
@@ -389,15 +408,24 @@ def sharded_configs(cuda, dist, rank: int, world: int, hbm_peak: float, tf_peak:
     T = cuda.Tensor
     comm = sharding.Communicator(cuda, dist)
     out = {}
+    dev = torch.device("cuda", torch.cuda.current_device())
 
-    def axis_sum(x, axis):
-        parts = x.split(axis)
-        acc = parts[0]
-        for p in parts[1:]:
-            acc = acc + p
-        return acc
+    def all_sum_i64(a: np.ndarray) -> np.ndarray:
+        t = torch.from_numpy(np.ascontiguousarray(a, dtype=np.int64)).to(dev)
+        dist.all_reduce(t)
+        return t.cpu().numpy()
 
-    def measure(name, step, alg_bytes=None, flops=None, steps=10):
+    def all_true(ok: bool) -> bool:
+        t = torch.tensor([1 if ok else 0], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        return bool(t.item())
+
+    def measure(name, expr, alg_bytes=None, flops=None, steps=10, verified=None):
+        k = expr.compile() if hasattr(expr, "compile") else None
+
+        def step():
+            expr.doBuffer().release()
+
         for _ in range(3):
             step()
         cuda.synchronize()
@@ -409,7 +437,7 @@ def sharded_configs(cuda, dist, rank: int, world: int, hbm_peak: float, tf_peak:
         t = torch.tensor([ms], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-        rec = {"ms": ms, "n_gpus": world}
+        rec = {"ms": ms, "n_gpus": world, "verified": verified, "distribution": expr.distribution}
         if flops:
             rec["tflops"] = flops / ms / 1e9
             rec["frac_of_3xtf32_peak_all_gpus"] = rec["tflops"] / (tf_peak * world)
@@ -417,36 +445,74 @@ def sharded_configs(cuda, dist, rank: int, world: int, hbm_peak: float, tf_peak:
             rec["gbs"] = alg_bytes / ms / 1e6
             rec["frac_of_hbm_all_gpus"] = rec["gbs"] / (hbm_peak * world)
         out[name] = rec
+        return rec
 
+    # ---- C3: dataset E, this rank's rows of the [16384, 16384] tensor --------------------------------------------------------------
     rows = sharding.shard_rows(ROWS, world, rank)[1]
-    x = T.random([rows, COLS], seed=5 + 16 * rank).doCache()
-    col_sums, row_sums = axis_sum(x, 0), axis_sum(x, 1)  # lazy graphs, built once
+    seed3 = 5 + 16 * rank
+    r3 = T.random([rows, COLS], seed=seed3)
+    nine, one, four = (T.fill(v, [rows, COLS]) for v in (9.0, 1.0, 4.0))
+    x = ((r3 * nine) - (r3 * nine) % one - four).doCache().shard()
+    hx = np_dataset_e(rows * COLS, seed3).reshape(rows, COLS).astype(np.int64)
+    want_total = int(all_sum_i64(np.asarray([hx.sum()]))[0])
+    want_cols = all_sum_i64(hx.sum(axis=0))
+    want_rows = hx.sum(axis=1)
+    total, col_sums, row_sums = x.sum(), comm.fold(x.split(0)), comm.fold(x.split(1))
+    row_sums_gathered = row_sums.gather()
     had_peer = comm.peer
     for route, tag in ((True, "fused / one-shot over NVLink peer memory"), (False, "NCCL")):
         if route and not comm.peer:
             continue
         comm.route_peer(route)
-        measure(f"C3 full sum 16384^2 sharded + allreduce(1 float) [{tag}]", lambda: comm.full_sum(x).release(), alg_bytes=4 * ROWS * COLS, steps=50)
-        measure(f"C3 axis-0 sum 16384^2 sharded + allreduce(16384 floats) [{tag}]", lambda: comm.axis0_sum(col_sums).release(),
-                alg_bytes=4 * ROWS * COLS, steps=50)
-        measure(f"C3 axis-1 sum 16384^2 sharded + allgather [{tag}]", lambda: comm.axis1_sum(row_sums).release(), alg_bytes=4 * ROWS * COLS, steps=50)
+        ok = all_true(float(total.flatArray()[0]) == float(want_total))
+        measure(f"C3 full sum 16384^2 sharded + allreduce(1 float) [{tag}]", total, alg_bytes=4 * ROWS * COLS, steps=50, verified=ok)
+        ok = all_true(np.array_equal(col_sums.flatArray().astype(np.int64), want_cols))
+        measure(f"C3 axis-0 sum 16384^2 sharded + allreduce(16384 floats) [{tag}]", col_sums, alg_bytes=4 * ROWS * COLS, steps=50, verified=ok)
+        got = row_sums_gathered.flatArray().astype(np.int64)
+        ok = all_true(np.array_equal(got[rank * rows:(rank + 1) * rows], want_rows) and int(got.sum()) == want_total) if ROWS % world == 0 else None
+        measure(f"C3 axis-1 sum 16384^2 sharded + allgather [{tag}]", row_sums_gathered, alg_bytes=4 * ROWS * COLS, steps=50, verified=ok)
     if had_peer:
         comm.route_peer(True)
-    del x, col_sums, row_sums
+    del x, total, col_sums, row_sums, row_sums_gathered, r3, nine, one, four, hx
+    # ---- C5: A and C row-sharded, B replicated; the reference's formulation (benchmarks.scala:188-191) on this rank's rows ---------------
     n5 = 8192
     m5 = sharding.shard_rows(n5, world, rank)[1]
-    if m5 > 0:
-        A = T.randomNormal([m5, n5], seed=9 + 16 * rank).doCache()
-        B = T.randomNormal([n5, n5], seed=10).doCache()
-        ab, bb = A.doBuffer(), B.doBuffer()
-        measure("C5 matmul 8192^3 row-sharded (B replicated, C left sharded)", lambda: comm.matmul_rows(ab, bb, m5, n5, n5).release(),
-                flops=2 * n5**3, steps=5)
-        if comm.peer and n5 % world == 0:
-            measure("C5 matmul 8192^3 row-sharded + allgather(C) [fused into the contraction's epilogue: TMA stores over NVLink peer memory]",
-                    lambda: comm.matmul_rows(ab, bb, m5, n5, n5, gather=True, fused=True).release(), flops=2 * n5**3, steps=5)
-        measure("C5 matmul 8192^3 row-sharded + allgather(C) [contraction, then ncclAllGather]",
-                lambda: comm.matmul_rows(ab, bb, m5, n5, n5, gather=True, fused=False).release(), flops=2 * n5**3, steps=5)
-        ab.release(), bb.release()
+    if m5 > 0 and n5 % world == 0:
+        def e_tensor(shape, seed):
+            r = T.random(shape, seed=seed)
+            return ((r * T.fill(9.0, shape)) - (r * T.fill(9.0, shape)) % T.fill(1.0, shape) - T.fill(4.0, shape)).doCache()
+
+        seed_a = lambda r: 9 + 16 * r  # noqa: E731
+        A = e_tensor([m5, n5], seed_a(rank)).shard()
+        B = e_tensor([n5, n5], 10)
+        hb = np_dataset_e(n5 * n5, 10).reshape(n5, n5).astype(np.float64)
+        c = comm.matmul_pattern(A, B)
+        kinfo = c.compile().info
+
+        def rows_ok(got_rows: np.ndarray, owner: int, local_rows) -> bool:
+            ha = np.stack([np_dataset_e(n5, seed_a(owner), first=int(r) * n5) for r in local_rows]).astype(np.float64)
+            return bool(np.array_equal(got_rows.astype(np.float64), ha @ hb))
+
+        sample = np.r_[0:2, 127:129, m5 - 2:m5]
+        got = c.flatArray().reshape(m5, n5)
+        ok = all_true(rows_ok(got[sample], rank, sample))
+        rec = measure("C5 matmul 8192^3 as split/broadcast/sum on row blocks (B replicated, C left sharded)", c, flops=2 * n5**3, steps=5, verified=ok)
+        rec["plan"] = int(kinfo.kind)
+        del got
+        for route, tag in ((True, "fused into the contraction's epilogue: TMA stores over NVLink peer memory"), (False, "contraction, then ncclAllGather")):
+            if route and not comm.peer:
+                continue
+            comm.route_peer(route)
+            cg = c.gather(zero_copy=True)
+            whole = cg.flatArray().reshape(n5, n5)
+            ok = all_true(all(rows_ok(whole[o * m5 + sample], o, sample) for o in range(world)))
+            del whole
+            rec = measure(f"C5 matmul 8192^3 row-sharded + allgather(C) [{tag}]", cg, flops=2 * n5**3, steps=5, verified=ok)
+            rec["plan"] = int(kinfo.kind)
+            del cg
+        if had_peer:
+            comm.route_peer(True)
+        del A, B, c
     cuda.synchronize()
     comm.close()
     return out

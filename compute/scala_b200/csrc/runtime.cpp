@@ -680,6 +680,8 @@ void close_peers(Nccl& n) {
 }
 }  // namespace
 
+std::atomic<uint64_t> g_comm_generation{0};  // bumped by every cc_comm_init: front ends drop what they cached per communicator
+
 extern "C" {
 
 const char* cc_last_error(void) { return last_error_cstr(); }
@@ -1809,6 +1811,13 @@ int cc_comm_init(const void* id, int n_ranks, int rank) {
     n.check(n.CommInitRank(&n.comm, n_ranks, uid, rank), "ncclCommInitRank");
     n.n_ranks = n_ranks;
     n.rank = rank;
+    ++g_comm_generation;
+  });
+}
+int cc_comm_generation(uint64_t* out) {
+  return guarded([&] {
+    CC_REQUIRE(out, CC_ERR_ILLEGAL_ARGUMENT, "null output");
+    *out = g_comm_generation.load();
   });
 }
 int cc_comm_enable_peer(void) {
@@ -2099,6 +2108,108 @@ int cc_broadcast(cc_buffer buf, uint64_t n_floats, int root, const cc_event* wai
     if (n.comm) n.check(n.Broadcast((const void*)b->ptr, (void*)b->ptr, n_floats, ncclFloat, root, n.comm, (cudaStream_t)op.cu()), "ncclBroadcast");
     op_end(op, out_event);
   });
+}
+
+int cc_buffer_copy(cc_buffer dst, cc_buffer src, uint64_t n_floats, const cc_event* waits, int n_waits, cc_event* out_event) {
+  return guarded([&] {
+    Lock lock;
+    require_init();
+    Buffer* d = as_buffer(dst);
+    Buffer* s = as_buffer(src);
+    CC_REQUIRE(d != s && n_floats <= d->n_floats && n_floats <= s->n_floats, CC_ERR_ILLEGAL_ARGUMENT, "copy: bad buffers");
+    BufferList in;
+    in.push_back(s);
+    Op op{pick_stream_for(in, {d}), in, {d}};
+    op.label = "device-to-device copy";
+    op.bytes = n_floats * 8;
+    op_begin(op, waits, n_waits);
+    CC_CU(cuMemcpyDtoDAsync(d->ptr, s->ptr, (size_t)n_floats * 4, op.cu()));
+    op_end(op, out_event);
+  });
+}
+
+// ---- leading-axis sharding ---------------------------------------------------------------------------------------------------------
+
+int cc_shard_rows(int64_t rows, int n_ranks, int rank, int64_t* out_first, int64_t* out_count) {
+  return guarded([&] {
+    CC_REQUIRE(rows >= 0 && n_ranks >= 1 && rank >= 0 && rank < n_ranks && out_first && out_count, CC_ERR_ILLEGAL_ARGUMENT, "bad shard request");
+    const int64_t base = rows / n_ranks, extra = rows % n_ranks;
+    *out_first = rank * base + std::min<int64_t>(rank, extra);
+    *out_count = base + (rank < extra ? 1 : 0);
+  });
+}
+
+int cc_shard_agree(uint64_t value, int* out_all_equal) {
+  int st = guarded([&] { CC_REQUIRE(out_all_equal, CC_ERR_ILLEGAL_ARGUMENT, "null output"); });
+  if (st != CC_OK) return st;
+  int world = 1, rank = 0;
+  st = cc_comm_info(&world, &rank);
+  if (st != CC_OK) return st;
+  if (world == 1) {
+    *out_all_equal = 1;
+    return CC_OK;
+  }
+  // four 16-bit digits, each exactly representable in a float: the exchange is a plain all-gather of floats
+  float mine[4];
+  for (int d = 0; d < 4; ++d) mine[d] = (float)((value >> (16 * d)) & 0xffffu);
+  cc_buffer send = 0, recv = 0;
+  st = cc_buffer_from_host(mine, 4, &send, nullptr);
+  if (st == CC_OK) st = cc_buffer_alloc(4ull * (uint64_t)world, &recv);
+  if (st == CC_OK) st = cc_allgather(send, recv, 4, nullptr, 0, nullptr);
+  std::vector<float> all(4 * (size_t)world, 0.f);
+  if (st == CC_OK) st = cc_buffer_to_host(recv, 0, all.data(), all.size(), nullptr, 0, nullptr);
+  if (send) cc_buffer_release(send);
+  if (recv) cc_buffer_release(recv);
+  if (st != CC_OK) return st;
+  int equal = 1;
+  for (int r = 0; r < world; ++r)
+    for (int d = 0; d < 4; ++d)
+      if (all[(size_t)r * 4 + d] != mine[d]) equal = 0;
+  *out_all_equal = equal;
+  return CC_OK;
+}
+
+int cc_shard_launch_allreduce(cc_kernel h, const cc_buffer* args, int n_args, cc_buffer out, const cc_event* waits, int n_waits, cc_event* out_event) {
+  uint64_t n = 0;
+  int st = guarded([&] {
+    Lock lock;
+    n = as_kernel(h)->plan.out_floats;
+  });
+  if (st != CC_OK) return st;
+  st = cc_launch(h, args, n_args, out, waits, n_waits, nullptr);
+  if (st != CC_OK) return st;
+  // the hazard tracker orders the combine after the launch (it writes the buffer the launch wrote)
+  return cc_allreduce_sum(out, n, nullptr, 0, out_event);
+}
+
+int cc_shard_launch_allgather(cc_kernel h, const cc_buffer* args, int n_args, cc_buffer gathered, const cc_event* waits, int n_waits, cc_event* out_event,
+                              int* out_fused) {
+  bool fuse = false;
+  uint64_t n = 0;
+  int64_t M = 0, N = 0, K = 0;
+  int st = guarded([&] {
+    Lock lock;
+    require_init();
+    const Plan& p = as_kernel(h)->plan;
+    Nccl& nc = rt().nccl;
+    Buffer* gb = as_buffer(gathered);
+    const int ranks = nc.comm ? nc.n_ranks : 1;
+    n = p.out_floats;
+    CC_REQUIRE(gb->n_floats >= n * (uint64_t)ranks, CC_ERR_ILLEGAL_ARGUMENT, "gathered buffer has %llu floats, %d blocks of %llu are needed",
+               (unsigned long long)gb->n_floats, ranks, (unsigned long long)n);
+    M = p.M, N = p.N, K = p.K;
+    fuse = p.kind == PLAN_CONTRACTION && !p.gathered_panels && n_args == 2 && nc.comm && nc.peer_mapped && nc.peer_enabled &&
+           (int)gb->peers.size() == nc.n_ranks && N % 4 == 0;
+  });
+  if (st != CC_OK) return st;
+  if (out_fused) *out_fused = fuse ? 1 : 0;
+  if (fuse) return cc_matmul_3xtf32_allgather(args[0], args[1], gathered, M, N, K, waits, n_waits, out_event);
+  cc_buffer part = 0;
+  st = cc_buffer_alloc(n, &part);
+  if (st == CC_OK) st = cc_launch(h, args, n_args, part, waits, n_waits, nullptr);
+  if (st == CC_OK) st = cc_allgather(part, gathered, n, nullptr, 0, out_event);
+  if (part) cc_buffer_release(part);  // (deferred by the runtime until the commands reading it have run)
+  return st;
 }
 
 }  // extern "C"

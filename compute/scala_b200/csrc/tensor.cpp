@@ -188,7 +188,8 @@ struct PlanCache {
   }
 };
 void resolve_plan(PlanCache& pc, Tensor::EmitCtx& ctx, uint32_t root, const Shape& out_shape);
-PendingBuffer enqueue_plan(Session& s, const PlanCache& pc, const Shape& out_shape, cc_buffer out_override = 0, cc_event* out_event = nullptr);
+PendingBuffer enqueue_plan(Session& s, const PlanCache& pc, const Shape& out_shape, cc_buffer out_override = 0, cc_event* out_event = nullptr,
+                           bool allreduce = false);
 bool plan_output_redirectable(const PlanCache& pc);
 
 // InlineTensor (Tensors.scala:1400-1411)
@@ -306,6 +307,7 @@ struct RandomTensor final : NonInlineTensor {
 struct ReduceTensor final : NonInlineTensor {
   TensorPtr base;
   uint32_t monoid = cc::K_PLUS;
+  bool across_ranks = false;  // the operand is a row block: the fold is completed by an all-reduce of its one float (Plus only)
   mutable PlanCache plan;
   ~ReduceTensor() override { bury(std::move(base)); }
   PendingBuffer evaluate(Session& s) const override {
@@ -313,7 +315,10 @@ struct ReduceTensor final : NonInlineTensor {
       PendingBuffer in = base->do_buffer(s);
       cc_buffer out = 0;
       int st = cc_buffer_alloc(1, &out);
-      if (st == CC_OK) st = cc_reduce_sum(in.buffer, (uint64_t)base->size(), out, nullptr, 0, nullptr);
+      // a row block: ONE kernel folds the block and all-reduces the result over NVLink peer memory (NCCL if the mailboxes are not mapped)
+      if (st == CC_OK)
+        st = across_ranks ? cc_reduce_sum_allreduce(in.buffer, (uint64_t)base->size(), out, nullptr, 0, nullptr)
+                          : cc_reduce_sum(in.buffer, (uint64_t)base->size(), out, nullptr, 0, nullptr);
       std::string m = st == CC_OK ? "" : cc_last_error();
       cc_buffer_release(in.buffer);
       if (st != CC_OK) {
@@ -329,9 +334,10 @@ struct ReduceTensor final : NonInlineTensor {
         resolve_plan(plan, ctx, emit_root(ctx), shape);
       }
     }
-    return enqueue_plan(s, plan, shape);
+    return enqueue_plan(s, plan, shape, 0, nullptr, across_ranks);
   }
   bool evaluate_into(Session& s, cc_buffer out, cc_event* out_event) const override {
+    if (across_ranks) return false;  // the combine runs on a device buffer
     if (monoid == cc::K_PLUS && !base->is_inline()) {
       PendingBuffer in = base->do_buffer(s);
       int st = cc_reduce_sum(in.buffer, (uint64_t)base->size(), out, nullptr, 0, out_event);
@@ -453,7 +459,7 @@ bool plan_output_redirectable(const PlanCache& pc) {
 }
 
 // enqueueClosure (Tensors.scala:1291-1392)
-PendingBuffer enqueue_plan(Session& s, const PlanCache& pc, const Shape& out_shape, cc_buffer out_override, cc_event* out_event) {
+PendingBuffer enqueue_plan(Session& s, const PlanCache& pc, const Shape& out_shape, cc_buffer out_override, cc_event* out_event, bool allreduce) {
   cc::SmallVec<cc_buffer, 16> args;
   cc_buffer out = 0;
   try {
@@ -463,13 +469,132 @@ PendingBuffer enqueue_plan(Session& s, const PlanCache& pc, const Shape& out_sha
       out = out_override;
     else
       check(cc_buffer_alloc((uint64_t)product(out_shape), &out));
-    check(cc_launch(pc.kernel, args.data(), (int)args.size(), out, nullptr, 0, out_event));
+    if (allreduce)
+      check(cc_shard_launch_allreduce(pc.kernel, args.data(), (int)args.size(), out, nullptr, 0, out_event));
+    else
+      check(cc_launch(pc.kernel, args.data(), (int)args.size(), out, nullptr, 0, out_event));
   } catch (...) {
     if (out && !out_override) cc_buffer_release(out);
     throw;
   }
   return {out, 0};
 }
+
+// ---- sharded tensors: combine / gather nodes ------------------------------------------------------------------------------------------
+
+int comm_world() {
+  int world = 1, rank = 0;
+  check(cc_comm_info(&world, &rank));
+  return world;
+}
+
+// partial sum -> whole tensor: a fusion barrier whose evaluation is (inline partial expression, evaluated) + all-reduce
+struct AllReduceTensor final : NonInlineTensor {
+  TensorPtr base;  // an inline partial sum
+  ~AllReduceTensor() override { bury(std::move(base)); }
+  PendingBuffer evaluate(Session& s) const override { return base->do_buffer(s); }  // borrow_buffer() of a partial sum all-reduces it
+};
+
+// row block -> the whole tensor on every rank
+struct GatherTensor final : NonInlineTensor {
+  TensorPtr base;
+  bool zero_copy = false;
+  ~GatherTensor() override { bury(std::move(base)); }
+  PendingBuffer evaluate(Session& s) const override {
+    const int world = comm_world();
+    if (world == 1) return base->do_buffer(s);
+    const uint64_t n = (uint64_t)base->size();
+    // equal blocks on every rank, checked once per size (collective, so every rank fails together instead of hanging in the exchange)
+    if (!per_communicator().agreed.count(n)) {
+      int equal = 0;
+      check(cc_shard_agree(n, &equal));
+      CC_REQUIRE(equal, CC_ERR_ILLEGAL_ARGUMENT,
+                 "gather needs equal row blocks on every rank (this rank holds %llu floats): pad the leading axis to a multiple of the number of ranks",
+                 (unsigned long long)n);
+      per_communicator().agreed.insert(n);
+    }
+    int peer = 0;
+    check(cc_comm_peer_enabled(&peer));
+    const InlineTensor* inl = dynamic_cast<const InlineTensor*>(base.get());
+    if (inl && peer) {
+      // the block's own kernel: a contraction stores every accumulator tile into every rank's copy from its epilogue
+      {
+        std::lock_guard<std::mutex> lock(inl->plan.mu);
+        if (!inl->plan.kernel) {
+          EmitCtx ctx;
+          uint32_t root = inl->closure(ctx);
+          resolve_plan(inl->plan, ctx, root, inl->shape);
+        }
+      }
+      cc_kernel_info_t info;
+      check(cc_kernel_info(inl->plan.kernel, &info));
+      if (info.kind == 2 && inl->shape.size() == 2 && inl->shape[1] % 4 == 0) {
+        cc_buffer arena = symmetric_arena(n * (uint64_t)world);
+        cc::SmallVec<cc_buffer, 16> args;
+        for (const Tensor* t : inl->plan.args) args.push_back(t->borrow_buffer(s));
+        int fused = 0;
+        check(cc_shard_launch_allgather(inl->plan.kernel, args.data(), (int)args.size(), arena, nullptr, 0, nullptr, &fused));
+        if (zero_copy) {
+          check(cc_buffer_retain(arena));
+          return {arena, 0};
+        }
+        return {copy_of(arena, n * (uint64_t)world), 0};
+      }
+    }
+    PendingBuffer part = base->do_buffer(s);
+    cc_buffer whole = 0;
+    int st = cc_buffer_alloc(n * (uint64_t)world, &whole);
+    if (st == CC_OK) st = cc_allgather(part.buffer, whole, n, nullptr, 0, nullptr);
+    std::string m = st == CC_OK ? "" : cc_last_error();
+    cc_buffer_release(part.buffer);
+    if (st != CC_OK) {
+      if (whole) cc_buffer_release(whole);
+      throw Error(st, m);
+    }
+    return {whole, 0};
+  }
+
+  // What is cached per communicator (collective evaluations run in the same order on every rank, one at a time): the block sizes all
+  // ranks agreed on, and one symmetric (peer-mapped) arena per size — cuMemAlloc + an IPC handle exchange, far too slow per evaluation;
+  // cc_shard_launch_allgather's entry barrier protects an arena against the previous gather's readers.
+  struct PerCommunicator {
+    uint64_t generation = 0;
+    std::unordered_set<uint64_t> agreed;
+    std::unordered_map<uint64_t, cc_buffer> arenas;
+  };
+  static PerCommunicator& per_communicator() {
+    static PerCommunicator pc;
+    uint64_t now = 0;
+    check(cc_comm_generation(&now));
+    if (now != pc.generation) {  // a new communicator: the old arenas' memory went with the old one
+      for (auto& kv : pc.arenas) cc_buffer_release(kv.second);
+      pc.arenas.clear();
+      pc.agreed.clear();
+      pc.generation = now;
+    }
+    return pc;
+  }
+  static cc_buffer symmetric_arena(uint64_t n_floats) {
+    PerCommunicator& pc = per_communicator();
+    auto it = pc.arenas.find(n_floats);
+    if (it != pc.arenas.end()) return it->second;
+    cc_buffer b = 0;
+    check(cc_comm_symmetric_alloc(n_floats, &b));
+    pc.arenas.emplace(n_floats, b);
+    return b;
+  }
+  static cc_buffer copy_of(cc_buffer src, uint64_t n_floats) {
+    cc_buffer dst = 0;
+    check(cc_buffer_alloc(n_floats, &dst));
+    int st = cc_buffer_copy(dst, src, n_floats, nullptr, 0, nullptr);
+    if (st != CC_OK) {
+      std::string m = cc_last_error();
+      cc_buffer_release(dst);
+      throw Error(st, m);
+    }
+    return dst;
+  }
+};
 
 template <class T>
 std::shared_ptr<T> make(const Shape& shape, float padding) {
@@ -487,6 +612,15 @@ cc_buffer Tensor::borrow_buffer(Session& s) const {
   PendingBuffer* p = s.find(this);
   if (!p) {
     PendingBuffer fresh = evaluate(s);
+    if (dist == kPartialSum) {
+      // a partial sum is only ever an inline expression (split(0) views folded with +), so `fresh` is this evaluation's own output
+      int st = cc_allreduce_sum(fresh.buffer, (uint64_t)size(), nullptr, 0, nullptr);
+      if (st != CC_OK) {
+        std::string m = cc_last_error();
+        cc_buffer_release(fresh.buffer);
+        throw Error(st, m);
+      }
+    }
     p = s.add(this, fresh);  // the session keeps evaluate()'s reference
   }
   return p->buffer;
@@ -576,24 +710,31 @@ Shape auto_broadcast_shape(const Shape& s1, const Shape& s2) {
   return out;
 }
 
-TensorPtr unary(uint32_t kind, const TensorPtr& t) {
-  CC_REQUIRE(t, CC_ERR_ILLEGAL_ARGUMENT, "null tensor");
+TensorPtr unary(uint32_t kind, const TensorPtr& t0) {
+  CC_REQUIRE(t0, CC_ERR_ILLEGAL_ARGUMENT, "null tensor");
   CC_REQUIRE(cc::is_unary(kind), CC_ERR_ILLEGAL_ARGUMENT, "not a unary operator: %u", kind);
+  TensorPtr t = t0->combined();  // f(partial sum) needs the sum
   auto d = make<DerivedTensor>(t->shape, t->padding);
   d->kind = kind;
   d->a = t;
+  d->dist = t->dist;
   return d;
 }
 
 TensorPtr binary(uint32_t kind, const TensorPtr& l, const TensorPtr& r) {
   CC_REQUIRE(l && r, CC_ERR_ILLEGAL_ARGUMENT, "null tensor");
   CC_REQUIRE(cc::is_binary(kind), CC_ERR_ILLEGAL_ARGUMENT, "not a binary operator: %u", kind);
-  Shape ns = auto_broadcast_shape(l->shape, r->shape);
-  TensorPtr bl = l->broadcast(ns), br = r->broadcast(ns);
+  // partial sums stay partial only under + with another partial sum (the fold of split(0) slices); anything else needs the sum itself
+  const bool partial = kind == cc::K_PLUS && l->dist == Tensor::kPartialSum && r->dist == Tensor::kPartialSum;
+  TensorPtr lc = partial ? l : l->combined(), rc = partial ? r : r->combined();
+  Shape ns = auto_broadcast_shape(lc->shape, rc->shape);
+  TensorPtr bl = lc->broadcast(ns), br = rc->broadcast(ns);
   auto d = make<DerivedTensor>(bl->shape, bl->padding);
   d->kind = kind;
   d->a = bl;
   d->b = br;
+  // a row block combined with a replicated operand (B of the row-sharded matmul, a constant) is a row block
+  d->dist = partial ? Tensor::kPartialSum : (bl->dist == Tensor::kRowBlock || br->dist == Tensor::kRowBlock) ? Tensor::kRowBlock : Tensor::kWhole;
   return d;
 }
 
@@ -607,7 +748,11 @@ TensorPtr join(const std::vector<TensorPtr>& tensors) {
   Shape s = tensors[0]->shape;
   s.push_back((int32_t)tensors.size());
   auto j = make<JoinTensor>(s, tensors[0]->padding);
-  j->tensors = tensors;
+  j->tensors.reserve(tensors.size());
+  for (auto& t : tensors) {
+    j->tensors.push_back(t->combined());
+    if (j->tensors.back()->dist == Tensor::kRowBlock) j->dist = Tensor::kRowBlock;  // the new dimension is the LAST one: the leading axis stays
+  }
   return j;
 }
 
@@ -618,25 +763,55 @@ TensorPtr join(const std::vector<TensorPtr>& tensors, int dimension) {
   const int n = (int)j->shape.size();
   CC_REQUIRE(dimension >= 0 && dimension < n, CC_ERR_ILLEGAL_ARGUMENT, "join dimension %d out of range", dimension);
   if (n - 1 == dimension) return j;
+  CC_REQUIRE(!(j->dist == Tensor::kRowBlock && dimension == 0), CC_ERR_UNSUPPORTED,
+             "join at dimension 0 would put the new dimension in front of the sharded leading axis: gather first");
   Shape s = tensors[0]->shape;
   s.insert(s.begin() + dimension, (int32_t)tensors.size());
   auto at = make<JoinTensor>(s, tensors[0]->padding);
-  at->tensors = tensors;
+  at->tensors = static_cast<JoinTensor*>(j.get())->tensors;
   at->position = dimension;
+  at->dist = j->dist;
   return at;
 }
 
 // ---- delayed operators ---------------------------------------------------------------------------------------------------------
 
+namespace {
+// What a view `matrix1` (rows = dimensions of `t`, columns = dimensions of the view + constant) of a row block is:
+// still a row block if the view's dimension 0 IS t's dimension 0 and nothing else touches it; a partial contribution if it fixes
+// t's dimension 0 to a constant (split(0): the local rows, to be folded with +); anything else would need rows of other ranks.
+Tensor::Distribution view_of_row_block(const Tensor& t, const Shape& new_shape, const std::vector<double>& m) {
+  const size_t rows = t.shape.size(), cols = new_shape.size() + 1;
+  CC_REQUIRE(rows >= 1 && m.size() == rows * cols, CC_ERR_ILLEGAL_ARGUMENT, "transform matrix has %zu entries, expected %zu", m.size(), rows * cols);
+  bool row0_identity = cols >= 2 && m[0] == 1.0, row0_constant = true;
+  for (size_t c = 0; c < cols; ++c) {
+    if (c != 0 && m[c] != 0.0) row0_identity = false;
+    if (c + 1 < cols && m[c] != 0.0) row0_constant = false;
+  }
+  bool others_use_dim0 = false;
+  for (size_t r = 1; r < rows; ++r)
+    if (cols >= 2 && m[r * cols] != 0.0) others_use_dim0 = true;
+  if (row0_identity && !others_use_dim0 && !new_shape.empty() && new_shape[0] == t.shape[0]) return Tensor::kRowBlock;
+  if (row0_constant) return Tensor::kPartialSum;
+  fail(CC_ERR_UNSUPPORTED, strprintf("this view of a row block %s mixes the sharded leading axis (it moves, shifts, scales or broadcasts over "
+                                     "dimension 0): gather it or use a replicated tensor (SURVEY 8e)", shape_str(t.shape).c_str()));
+  return Tensor::kWhole;
+}
+}  // namespace
+
 TensorPtr Tensor::transform(const Shape& new_shape, const std::vector<double>& matrix1) {
+  if (dist == kPartialSum) return combined()->transform(new_shape, matrix1);  // (padding would be added once per rank)
+  const Distribution view_dist = dist == kRowBlock ? view_of_row_block(*this, new_shape, matrix1) : kWhole;
   // Tensors.scala:978-1003: views of views are composed on the host and keep the ORIGINAL checkpoint
   if (auto tt = dynamic_cast<TransformedTensor*>(this)) {
     auto t = make<TransformedTensor>(new_shape, padding);
     t->matrix = cc::ndat::pre_concatenate(matrix1, tt->matrix, new_shape.size());
     t->checkpoint = tt->checkpoint;
+    t->dist = view_dist;
     return t;
   }
   auto t = make<TransformedTensor>(new_shape, padding);
+  t->dist = view_dist;
   CC_REQUIRE(matrix1.size() == shape.size() * (new_shape.size() + 1), CC_ERR_ILLEGAL_ARGUMENT, "transform matrix has %zu entries, expected %zu",
              matrix1.size(), shape.size() * (new_shape.size() + 1));
   t->matrix = matrix1;
@@ -663,15 +838,48 @@ TensorPtr Tensor::reshape(const Shape& new_shape) {
   check_shape(new_shape);
   CC_REQUIRE(product(new_shape) == size(), CC_ERR_ILLEGAL_ARGUMENT, "cannot reshape %s to %s", shape_str(shape).c_str(),
              shape_str(new_shape).c_str());
+  if (dist == kPartialSum) return combined()->reshape(new_shape);
+  CC_REQUIRE(dist != kRowBlock || (!new_shape.empty() && new_shape[0] == shape[0]), CC_ERR_UNSUPPORTED,
+             "reshape of a row block %s to %s changes the sharded leading axis: gather first", shape_str(shape).c_str(), shape_str(new_shape).c_str());
   auto a = make<AliasTensor>(new_shape, padding);
   a->base = shared_from_this();
+  a->dist = dist;
   return a;
 }
 
 TensorPtr Tensor::non_inline() {
+  if (dist == kPartialSum) return combined();
   auto a = make<AliasTensor>(shape, padding);
   a->base = shared_from_this();
+  a->dist = dist;
   return a;
+}
+
+TensorPtr Tensor::as_row_block() {
+  CC_REQUIRE(dist == kWhole, CC_ERR_ILLEGAL_ARGUMENT, "the tensor is already sharded");
+  CC_REQUIRE(!shape.empty(), CC_ERR_ILLEGAL_ARGUMENT, "a scalar has no leading axis to shard");
+  auto a = make<AliasTensor>(shape, padding);
+  a->base = shared_from_this();
+  a->dist = kRowBlock;
+  return a;
+}
+
+TensorPtr Tensor::combined() {
+  if (dist != kPartialSum) return shared_from_this();
+  auto a = make<AllReduceTensor>(shape, padding);
+  a->base = shared_from_this();
+  return a;
+}
+
+TensorPtr Tensor::gather(bool zero_copy) {
+  if (dist == kPartialSum) return combined();
+  if (dist == kWhole) return shared_from_this();
+  Shape whole = shape;
+  whole[0] = (int32_t)((int64_t)shape[0] * comm_world());
+  auto g = make<GatherTensor>(whole, padding);
+  g->base = shared_from_this();
+  g->zero_copy = zero_copy;
+  return g;
 }
 
 TensorPtr Tensor::scale(const Shape& new_shape) {
@@ -733,9 +941,12 @@ std::vector<TensorPtr> Tensor::split(int dimension) {
 TensorPtr Tensor::reduce(uint32_t monoid) {
   CC_REQUIRE(monoid == cc::K_PLUS || monoid == cc::K_MIN || monoid == cc::K_MAX || monoid == cc::K_TIMES, CC_ERR_ILLEGAL_ARGUMENT,
              "reduce needs a monoid: Plus, Min, Max or Times (got %u)", monoid);
+  if (dist == kPartialSum) return combined()->reduce(monoid);
+  CC_REQUIRE(dist != kRowBlock || monoid == cc::K_PLUS, CC_ERR_UNSUPPORTED, "only + is combined across ranks: gather a row block before reducing it with another monoid");
   auto s = make<ReduceTensor>({}, padding);
   s->base = shared_from_this();
   s->monoid = monoid;
+  s->across_ranks = dist == kRowBlock;
   return s;
 }
 
@@ -743,9 +954,10 @@ TensorPtr Tensor::sum() { return reduce(cc::K_PLUS); }
 
 TensorPtr Tensor::do_cache() {
   Session s;
-  PendingBuffer p = do_buffer(s);
+  PendingBuffer p = do_buffer(s);  // (a partial sum comes back all-reduced: whole)
   auto t = make<BufferTensor>(shape, padding);
   t->buffer = p.buffer;
+  t->dist = dist == kRowBlock ? kRowBlock : kWhole;
   return t;
 }
 
@@ -757,7 +969,7 @@ TensorPtr Tensor::do_cache() {
 constexpr uint64_t kDirectToHostFloats = 16384;
 
 void Tensor::read_into_pinned(float* pinned, uint64_t n) const {
-  if (n > 0 && n <= kDirectToHostFloats) {
+  if (n > 0 && n <= kDirectToHostFloats && dist != kPartialSum) {
     uint64_t dptr = 0;
     cc_buffer wrapped = 0;
     if (cc_host_device_ptr(pinned, &dptr) == CC_OK && cc_buffer_wrap(dptr, n, &wrapped) == CC_OK) {
@@ -784,7 +996,7 @@ void Tensor::flat_array_into(float* host, uint64_t capacity) const {
   const uint64_t n = (uint64_t)size();
   CC_REQUIRE(capacity >= n, CC_ERR_ILLEGAL_ARGUMENT, "flatArray needs room for %llu floats, got %llu", (unsigned long long)n,
              (unsigned long long)capacity);
-  if (n > 0 && n <= kDirectToHostFloats) {
+  if (n > 0 && n <= kDirectToHostFloats && dist != kPartialSum) {
     // small result: let the kernel store into pooled pinned memory, then one memcpy into the caller's (pageable) array
     void* pinned = nullptr;
     if (cc_host_alloc(n * 4, &pinned) == CC_OK) {
@@ -1069,6 +1281,15 @@ int ct_tree_blob(ct_tensor t, void* out, uint64_t capacity, uint64_t* out_needed
       memcpy(out, blob.data(), blob.size());
     }
   });
+}
+int ct_shard(ct_tensor local, ct_tensor* out) {
+  return guarded([&] { *out = wrap(ref(local)->as_row_block()); });
+}
+int ct_distribution(ct_tensor t, int* out) {
+  return guarded([&] { *out = (int)ref(t)->dist; });
+}
+int ct_gather(ct_tensor t, int zero_copy, ct_tensor* out) {
+  return guarded([&] { *out = wrap(ref(t)->gather(zero_copy != 0)); });
 }
 int ct_release(ct_tensor t) {
   return guarded([&] {

@@ -49,6 +49,10 @@ class Tensor : public std::enable_shared_from_this<Tensor> {
  public:
   Shape shape;
   float padding = 0.f;
+  // how this tensor is spread over the ranks of the communicator: the whole tensor on every rank (also: no communicator),
+  // this rank's block of rows of a tensor sharded along its leading axis, or this rank's additive contribution to a sum over that axis
+  enum Distribution : uint8_t { kWhole = 0, kRowBlock = 1, kPartialSum = 2 };
+  Distribution dist = kWhole;
   virtual ~Tensor();
 
   int64_t size() const;
@@ -97,6 +101,10 @@ class Tensor : public std::enable_shared_from_this<Tensor> {
   virtual TensorPtr non_inline();
   TensorPtr do_cache();
   TensorPtr transform(const Shape& new_shape, const std::vector<double>& matrix1);
+  // ---- sharding (include/compute_cuda.h: ct_shard / ct_gather) ----
+  TensorPtr as_row_block();            // declare this (whole, non-scalar) tensor to be this rank's row block
+  TensorPtr combined();                // partial sum -> whole: evaluates, then all-reduces across ranks (identity for anything else)
+  TensorPtr gather(bool zero_copy);    // row block -> whole tensor on every rank
 
   // ---- slow actions (Tensors.scala:776-811, 1099-1118) ----
   std::vector<float> flat_array() const;

@@ -107,6 +107,17 @@ def _L():
         L.cc_comm_route_peer.argtypes = [C.c_int]
         L.cc_allgather.argtypes = [h, h, u64, hp, C.c_int, hp]
         L.cc_broadcast.argtypes = [h, u64, C.c_int, hp, C.c_int, hp]
+        L.cc_buffer_copy.argtypes = [h, h, u64, hp, C.c_int, hp]
+        L.cc_kernel_cache_lookup.argtypes = [C.c_void_p, u64, C.c_int, hp]
+        L.cc_comm_generation.argtypes = [hp]
+        L.cc_shard_rows.argtypes = [C.c_int64, C.c_int, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+        L.cc_shard_agree.argtypes = [u64, C.POINTER(C.c_int)]
+        L.cc_shard_launch_allreduce.argtypes = [h, hp, C.c_int, h, hp, C.c_int, hp]
+        L.cc_shard_launch_allgather.argtypes = [h, hp, C.c_int, h, hp, C.c_int, hp, C.POINTER(C.c_int)]
+        L.ct_tree_blob.argtypes = [h, C.c_void_p, u64, hp]
+        L.ct_shard.argtypes = [h, hp]
+        L.ct_distribution.argtypes = [h, C.POINTER(C.c_int)]
+        L.ct_gather.argtypes = [h, C.c_int, hp]
         _configured = True
     return L
 
@@ -451,6 +462,39 @@ def kernel_cache_size() -> int:
     return n.value
 
 
+def kernel_cache_lookup(tree_blob: bytes, any_out_shape: bool = False) -> "Kernel | None":
+    """probe only (kernelCache.getIfPresent, Tensors.scala:1293): the cached kernel with the blob's structure, or None"""
+    h = u64()
+    check(_L().cc_kernel_cache_lookup(tree_blob, len(tree_blob), 1 if any_out_shape else 0, C.byref(h)))
+    return Kernel(h.value) if h.value else None
+
+
+def compile_blob(tree_blob: bytes) -> "Kernel":
+    """cc_compile on a raw tree blob (what a JVM front end hands over)"""
+    h = u64()
+    check(_L().cc_compile(tree_blob, len(tree_blob), C.byref(h)))
+    return Kernel(h.value)
+
+
+def shard_rows(rows: int, n_ranks: int, rank: int) -> tuple[int, int]:
+    first, count = C.c_int64(), C.c_int64()
+    check(_L().cc_shard_rows(rows, n_ranks, rank, C.byref(first), C.byref(count)))
+    return first.value, count.value
+
+
+def shard_agree(value: int) -> bool:
+    """collective: did every rank pass the same value?"""
+    out = C.c_int()
+    check(_L().cc_shard_agree(value, C.byref(out)))
+    return bool(out.value)
+
+
+def comm_info() -> tuple[int, int]:
+    n, r = C.c_int(), C.c_int()
+    check(_L().cc_comm_info(C.byref(n), C.byref(r)))
+    return n.value, r.value
+
+
 def set_operand_cache(on: bool) -> None:
     """keep (True, default) or drop (False) the TF32 hi / lo panels of recently used, unchanged B operands"""
     check(_L().cc_set_operand_cache(1 if on else 0))
@@ -764,6 +808,34 @@ class Tensor:
         h = u64()
         check(_L().ct_compile(self._h, C.byref(h)))
         return Kernel(h.value)
+
+    def treeBlob(self) -> bytes:
+        """the tree blob compile() hands to cc_compile_ex (definitions attached) — what CudaTreeWriter.scala must write"""
+        need = u64()
+        check(_L().ct_tree_blob(self._h, None, 0, C.byref(need)))
+        buf = C.create_string_buffer(need.value)
+        check(_L().ct_tree_blob(self._h, buf, need.value, C.byref(need)))
+        return buf.raw[: need.value]
+
+    # ---- sharding over the GPUs of one box (include/compute_cuda.h: ct_shard / ct_gather) ----
+
+    def shard(self) -> "Tensor":
+        """declares this tensor to be THIS rank's row block of a tensor sharded along its leading axis"""
+        h = u64()
+        check(_L().ct_shard(self._h, C.byref(h)))
+        return Tensor._wrap(h)
+
+    @property
+    def distribution(self) -> str:
+        d = C.c_int()
+        check(_L().ct_distribution(self._h, C.byref(d)))
+        return ("whole", "row block", "partial sum")[d.value]
+
+    def gather(self, zero_copy: bool = False) -> "Tensor":
+        """row block -> the whole tensor on every rank (a sharded matmul result is gathered by the contraction's own epilogue)"""
+        h = u64()
+        check(_L().ct_gather(self._h, 1 if zero_copy else 0, C.byref(h)))
+        return Tensor._wrap(h)
 
     def release(self) -> None:
         try:

@@ -6,6 +6,11 @@ and, on request, the row blocks of a sharded result.  The collectives are the li
 include/compute_cuda.h); `torch.distributed` — any backend — is used for nothing but handing rank 0's NCCL unique id to
 the other ranks.
 
+Since round 2 the sharding itself lives behind the Tensor API (`Tensor.shard()` / `.gather()`, include/compute_cuda.h: ct_shard,
+ct_gather, cc_shard_*): a row block carries its distribution through the lazy graph, `shard.sum()` is the global sum, the fold of
+`shard.split(0)` is all-reduced when evaluated, and the split / broadcast / sum matmul over a row block of A gathers from the
+contraction's own epilogue. `Communicator` sets the communicator up and keeps the explicit, buffer-level routes for A/B timing.
+
 Host-side logic only: nothing here computes on the CPU.
 """
 from __future__ import annotations
@@ -62,6 +67,37 @@ class Communicator:
                 cuda.comm_enable_peer()
                 self.peer = cuda.comm_peer_enabled()
 
+    def _require_equal_blocks(self, n_floats: int) -> None:
+        """gathers need the same block size on every rank; checked collectively once per size, so that uneven shards are an
+        IllegalArgument on every rank instead of a hang inside the exchange"""
+        seen = self.__dict__.setdefault("_agreed", set())
+        if self.world > 1 and n_floats not in seen:
+            if not self.cuda.shard_agree(n_floats):
+                raise ValueError(f"gather needs equal blocks on every rank (this rank holds {n_floats} floats): pad the leading axis to a "
+                                 "multiple of the number of ranks, or leave the result sharded")
+            seen.add(n_floats)
+
+    # ---- the same three exchanges through the Tensor API (what user code looks like) ----------------------------------------
+
+    @staticmethod
+    def fold(parts):
+        acc = parts[0]
+        for p in parts[1:]:
+            acc = acc + p
+        return acc
+
+    def sharded(self, local_tensor):
+        """this rank's row block as a sharded tensor (identity semantics at world size 1)"""
+        return local_tensor.shard()
+
+    def matmul_pattern(self, a_block, b):
+        """benchmarks.scala:188-191 verbatim on a row block of A and a replicated B: one tcgen05 contraction per rank, C stays a row block"""
+        i, j = a_block.shape
+        j2, k = b.shape
+        assert j == j2
+        product = a_block.broadcast([i, j, k]) * b.reshape([1, j, k]).broadcast([i, j, k])
+        return self.fold(product.split(1))
+
     def route_peer(self, on: bool) -> None:
         """A/B switch: small combines over the NVLink peer mailboxes (True) or over NCCL (False)"""
         if self.world > 1:
@@ -115,6 +151,7 @@ class Communicator:
         n = 1
         for s in local_row_sums.shape:
             n *= s
+        self._require_equal_blocks(n)
         whole = cuda.Buffer.alloc(n * self.world)
         cuda.allgather(part, whole, n)
         part.release()
@@ -135,6 +172,8 @@ class Communicator:
         cuda = self.cuda
         if fused is None:
             fused = self.peer
+        if gather:
+            self._require_equal_blocks(m_shard * n)
         if gather and self.world > 1 and fused and self.peer and n % 4 == 0:
             whole = self.gather_arena(m_shard * n * self.world)
             cuda.matmul_3xtf32_allgather(a_shard, b_full, whole, m_shard, n, k)

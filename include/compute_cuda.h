@@ -99,6 +99,8 @@ int cc_buffer_length(cc_buffer b, uint64_t* out_n_floats);
  * `offset_floats` after `waits`; `*out_event` completes when `host` is filled (NULL => blocking). */
 int cc_buffer_to_host(cc_buffer b, uint64_t offset_floats, float* host, uint64_t n_floats, const cc_event* waits,
                       int n_waits, cc_event* out_event);
+/* dst[0..n) = src[0..n) on the device, ordered like every other command (after the writers of src, after the users of dst) */
+int cc_buffer_copy(cc_buffer dst, cc_buffer src, uint64_t n_floats, const cc_event* waits, int n_waits, cc_event* out_event);
 /* gives every idle pooled device block back to the driver (the pool also does this by itself when an allocation fails) */
 int cc_memory_trim(void);
 /* pinned host staging memory (replaces LWJGL memAllocFloat, Memory.scala:184-208). Blocks are pooled by size class:
@@ -250,6 +252,8 @@ int cc_comm_unique_id(void* out_128_bytes);                       /* rank 0; shi
 int cc_comm_init(const void* id_128_bytes, int n_ranks, int rank); /* ncclCommInitRank on this process' device */
 int cc_comm_destroy(void);
 int cc_comm_info(int* out_n_ranks, int* out_rank);
+/* counts cc_comm_init calls: a front end that caches per-communicator objects (symmetric arenas) drops them when it changes */
+int cc_comm_generation(uint64_t* out);
 /* Our own collective over NVLink peer memory (B200 HGX: every peer at full bandwidth through NVSwitch): maps one small
  * CUDA-IPC mailbox per rank into every other rank (handles exchanged once through the communicator). Afterwards
  * cc_allreduce_sum routes vectors of <= 65536 floats through a one-shot kernel (peers store straight into each other's
@@ -278,6 +282,31 @@ int cc_matmul_3xtf32_allgather(cc_buffer a_shard, cc_buffer b, cc_buffer gathere
 int cc_allgather(cc_buffer send, cc_buffer recv, uint64_t n_floats_per_rank, const cc_event* waits, int n_waits,
                  cc_event* out_event);
 int cc_broadcast(cc_buffer buf, uint64_t n_floats, int root, const cc_event* waits, int n_waits, cc_event* out_event);
+
+/* ---- leading-axis sharding over the GPUs of one box --------------------------------------------------- */
+/* Row-major tensors shard into contiguous row blocks, one per rank (process); elementwise graphs and views that do not mix the
+ * leading axis need no exchange. These entry points are what a front end needs besides cc_launch to evaluate a kernel on its row
+ * block and combine across ranks; the ct_* mirror (ct_shard / ct_gather below) and scala/.../CudaSharding.scala are built on them.
+ * All of them except cc_shard_rows are COLLECTIVE: every rank of the communicator calls them in the same order. */
+
+/* the block of `rank`: the first rows % n_ranks ranks own one extra row */
+int cc_shard_rows(int64_t rows, int n_ranks, int rank, int64_t* out_first_row, int64_t* out_row_count);
+/* *out_all_equal = 1 iff every rank passed the same `value` (exact for the full 64 bits). Gathers need equal blocks on every rank:
+ * front ends call this once per block size before the first cc_allgather / cc_shard_launch_allgather of that size, so that uneven
+ * shards are an IllegalArgument on EVERY rank instead of a hang in the exchange. */
+int cc_shard_agree(uint64_t value, int* out_all_equal);
+/* cc_launch, then all-reduce (sum) of the kernel's output across ranks, in place: partial reductions over the sharded axis
+ * (column sums `shard.split(0).reduce(_ + _)`, sums of inline expressions). Vectors of <= 65536 floats go through the one-shot
+ * kernel over the NVLink peer mailboxes when those are mapped, NCCL otherwise. */
+int cc_shard_launch_allreduce(cc_kernel k, const cc_buffer* args, int n_args, cc_buffer out, const cc_event* waits, int n_waits,
+                              cc_event* out_event);
+/* cc_launch on this rank's row block with the result gathered on every rank: `gathered` holds n_ranks blocks of
+ * cc_kernel_info_t.out_floats floats, block r = rank r's output. A contraction plan (kind 2, what the split / broadcast / sum matmul
+ * compiles to) with `gathered` from cc_comm_symmetric_alloc, peer mailboxes mapped and N % 4 == 0 runs the exchange INSIDE the
+ * tensor-core kernel's epilogue (cc_matmul_3xtf32_allgather); everything else launches into a temporary and all-gathers it.
+ * `*out_fused` (may be NULL) reports which route ran. */
+int cc_shard_launch_allgather(cc_kernel k, const cc_buffer* args, int n_args, cc_buffer gathered, const cc_event* waits, int n_waits,
+                              cc_event* out_event, int* out_fused);
 
 /* ---- host-side mirror of the Tensor API (flat C view of compute::cuda::Tensor, see tensor.h) ------------------- */
 /* These build the same lazy graphs as T:395-1442 and evaluate them through the cc_* functions above. */
@@ -328,6 +357,23 @@ int ct_compile(ct_tensor t, cc_kernel* out);
 /* the tree blob ct_compile hands to cc_compile_ex for this tensor (definitions attached) — introspection: tests pin the blob a JVM
  * front end must write (scala/.../CudaTreeWriter.scala) against it. Call with out = NULL to size (*out_needed). */
 int ct_tree_blob(ct_tensor t, void* out, uint64_t capacity, uint64_t* out_needed);
+/* Sharded tensors. `ct_shard(local)` declares `local` ([rows on this rank, ...]) to be this rank's row block of a tensor sharded along
+ * its leading axis; the property follows the tensor through the lazy graph (ct_distribution: 0 = whole / replicated, 1 = row block,
+ * 2 = partial sum):
+ *   - elementwise operators, broadcast / permute / translate / split(d > 0) / reshape / join that keep the leading axis in place, and
+ *     operations with replicated operands keep a row block a row block — no exchange, each rank runs its own kernel, and the
+ *     split / broadcast / sum matmul of a row block of A with a replicated B is still ONE tcgen05 contraction per rank;
+ *   - sum / reduce(+) of a row block is the GLOBAL sum: local fold + all-reduce of one float (one fused kernel over NVLink peer memory);
+ *   - split(0) of a row block yields the LOCAL rows as partial contributions: folding them with + (`t.split(0).reduce(_ + _)`, the column
+ *     sums) gives a partial sum, which is all-reduced when it is evaluated or used by anything that is not + of partial sums;
+ *   - a view that would mix the sharded axis (permute moving dimension 0, translate along it, broadcast over it) is CC_ERR_UNSUPPORTED:
+ *     gather or replicate first.
+ * `ct_gather(t, zero_copy)` is the whole tensor on every rank ([n_ranks * rows, ...]; needs equal blocks): a sharded matmul result is
+ * gathered by the contraction's own epilogue. zero_copy != 0 returns a view of the communicator's symmetric arena, valid until the next
+ * gather of the same size; 0 copies it out. With no communicator (one GPU) all of this degenerates to the identity. */
+int ct_shard(ct_tensor local, ct_tensor* out);
+int ct_distribution(ct_tensor t, int* out);
+int ct_gather(ct_tensor t, int zero_copy, ct_tensor* out);
 int ct_release(ct_tensor t);
 int ct_live_tensors(int64_t* out);
 

@@ -116,10 +116,69 @@ def _worker(rank, world, port):
                 x.release()
         for x in (s, c0, c1, A, B, Cw):
             x.release()
+        _api_level(cuda, comm, sharding, ref, rank, world)
         cuda.synchronize()
         comm.close()
     finally:
         dist.destroy_process_group()
+
+
+def _api_level(cuda, comm, sharding, ref, rank, world):
+    """the same exchanges through the Tensor API: a row block declared with .shard() carries its distribution through the lazy graph
+    (include/compute_cuda.h: ct_shard / ct_gather); user code is the single-GPU code (benchmarks.scala:188-191, README.md:301-310)"""
+    T = cuda.Tensor
+    rows, cols = 1024, 2048
+    full = (np.floor(ref.random_buffer(rows * cols, 5) * np.float32(9.0)) - np.float32(4.0)).astype(np.float32).reshape(rows, cols)
+    start, n = sharding.shard_rows(rows, world, rank)
+    x = T(full[start : start + n]).shard()
+    i64 = full.astype(np.int64)
+    for route in (True, False):
+        comm.route_peer(route)
+        assert x.sum().flatArray()[0] == np.float32(i64.sum())  # global sum: local fold + all-reduce of one float
+        assert (x * x + x).sum().flatArray()[0] == np.float32((i64 * i64 + i64).sum())  # inline operand: fused fold, then all-reduce
+        col = comm.fold(x.split(0))
+        assert col.distribution == "partial sum"
+        assert np.array_equal(col.flatArray(), i64.sum(axis=0).astype(np.float32))  # all-reduced when evaluated
+        assert np.array_equal((col * col).flatArray(), (i64.sum(axis=0) ** 2).astype(np.float32))  # ... or used by anything but +
+        row = comm.fold(x.split(1))
+        assert row.distribution == "row block"
+        assert np.array_equal(row.flatArray(), i64[start : start + n].sum(axis=1).astype(np.float32))  # stays sharded: no exchange
+        assert np.array_equal(row.gather().flatArray(), i64.sum(axis=1).astype(np.float32))
+        assert np.array_equal((x * x - x).gather().flatArray().reshape(rows, cols), full * full - full)  # elementwise: no exchange until gathered
+    comm.route_peer(True)
+    for (m, k, nn) in ((512, 256, 512), (2 * 200, 96, 132), (1024, 512, 1024)):
+        a = (np.floor(ref.random_buffer(m * k, 9) * 9) - 4).astype(np.float32).reshape(m, k)
+        b = (np.floor(ref.random_buffer(k * nn, 10) * 9) - 4).astype(np.float32).reshape(k, nn)
+        ms, mn = sharding.shard_rows(m, world, rank)
+        want = (a.astype(np.float64) @ b.astype(np.float64)).astype(np.float32)
+        c = comm.matmul_pattern(T(a[ms : ms + mn]).shard(), T(b))
+        assert c.distribution == "row block"
+        big = m * k * nn >= 2**25
+        assert c.compile().info.kind == (2 if big else 1)  # the pattern, on this rank's rows: the tcgen05 contraction from 2^25 multiply-adds
+        assert np.array_equal(c.flatArray().reshape(mn, nn), want[ms : ms + mn])
+        for zero_copy in (False, True):
+            s0 = cuda.stats()["device_kernels"]
+            g = c.gather(zero_copy=zero_copy)
+            got = g.flatArray().reshape(m, nn)
+            assert np.array_equal(got, want), (m, k, nn, zero_copy)
+        assert g.distribution == "whole"
+    # uneven row blocks: a gather is an IllegalArgument on EVERY rank (no hang); sums and sharded results still work
+    urows = 2 * 100 + 1
+    ufull = (np.floor(ref.random_buffer(urows * 64, 6) * 9) - 4).astype(np.float32).reshape(urows, 64)
+    us, un = sharding.shard_rows(urows, world, rank)
+    u = T(ufull[us : us + un]).shard()
+    assert u.sum().flatArray()[0] == np.float32(ufull.astype(np.int64).sum())
+    assert np.array_equal(comm.fold(u.split(0)).flatArray(), ufull.astype(np.int64).sum(axis=0).astype(np.float32))
+    try:
+        comm.fold(u.split(1)).gather().flatArray()
+        raise AssertionError("uneven blocks were gathered")
+    except cuda.ComputeCudaError as e:
+        assert "equal row blocks" in str(e)
+    try:
+        comm.axis1_sum(comm.fold(u.split(1)))
+        raise AssertionError("uneven blocks were gathered")
+    except ValueError as e:
+        assert "equal blocks" in str(e)
 
 
 def test_sharded_reductions_and_matmul_two_gpus():

@@ -80,3 +80,40 @@ def _worker(rank, world, port, rows, cols):
 def test_world_size_2_gloo(rows, cols):
     port = _free_port()
     mp.spawn(_worker, args=(2, port, rows, cols), nprocs=2, join=True)
+
+
+def test_distribution_follows_the_lazy_graph():
+    """host logic of the sharded Tensor API (no device work: nothing is evaluated): which operations keep a row block a row block,
+    which produce partial sums, which need the sum, and which are refused because they would mix the sharded leading axis"""
+    from compute.scala_b200 import cuda
+
+    T = cuda.Tensor
+    x = T.random([8, 6], seed=1).shard()
+    assert x.distribution == "row block" and T.random([8, 6], seed=1).distribution == "whole"
+    assert (x + x).distribution == "row block" and T.tanh(x).distribution == "row block" and (-x).distribution == "row block"
+    assert (x * T.fill(2.0, [8, 6])).distribution == "row block"  # replicated operand
+    assert x.sum().distribution == "whole"  # the global sum
+    acc = x.split(0)[0]
+    for p in x.split(0)[1:]:
+        acc = acc + p
+    assert acc.distribution == "partial sum"  # the fold of the local rows
+    assert T.tanh(acc).distribution == "whole" and (acc * acc).distribution == "whole" and (acc - acc).distribution == "whole"
+    assert acc.nonInline().distribution == "whole" and acc.reshape([2, 3]).distribution == "whole" and acc.broadcast([6, 2]).distribution == "whole"
+    for view in (x.split(1)[0], x.permute([0, 1]), x.translate([0, 2]), x.reshape([8, 2, 3]), x.broadcast([8, 6, 4]), T.join([x, x]), T.join([x, x], 1), x.nonInline()):
+        assert view.distribution == "row block"
+    for refused in (lambda: x.permute([1, 0]), lambda: x.translate([1, 0]), lambda: x.reshape([6, 8]), lambda: x.reduce("max"), lambda: T.join([x, x], 0),
+                    lambda: x.scale([4, 6]), lambda: x.shard(), lambda: T.scalar(1.0).shard()):
+        with pytest.raises(cuda.ComputeCudaError):
+            refused()
+    # the matmul pattern over a row block of A and a replicated B stays a row block and is still the pattern
+    b = T.random([6, 5], seed=2)
+    prod = x.broadcast([8, 6, 5]) * b.reshape([1, 6, 5]).broadcast([8, 6, 5])
+    c = prod.split(1)[0]
+    for p in prod.split(1)[1:]:
+        c = c + p
+    assert c.distribution == "row block" and tuple(c.shape) == (8, 5)
+    assert tuple(x.gather().shape) == (8, 6) and x.gather().distribution == "whole"  # one rank: the identity
+    for rows in (0, 1, 7, 8, 16385):
+        for world in (1, 2, 3, 8):
+            for r in range(world):
+                assert cuda.shard_rows(rows, world, r) == sharding.shard_rows(rows, world, r)
