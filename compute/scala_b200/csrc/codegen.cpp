@@ -1560,166 +1560,15 @@ void emit_reduce(Plan& plan, const Program& p, int n_args, const DeviceProps& de
     const int64_t TCHb = S > 1 ? (T + Sb - 1) / Sb : T;         // rows per CTA
     const int64_t Sy = S > 1 ? (T + TCHb - 1) / TCHb : 1;       // partials per output
     const int CW = S > 1 ? 64 : 256;                            // column vectors per CTA
-    // Opt-in register tiling (CC_TUNE_RED_P=2|4, until it has been timed on a GPU): a thread owns P positions along the output
-    // dimension next to the fastest one as well as its V adjacent outputs. Operands that do not depend on that dimension -- the
-    // weights of a convolution, the broadcast operand of a matmul-like term -- are loaded once per reduction step for all P
-    // positions (the P inlined copies of the term read the same address; the compiler keeps one load), which raises the FMAs per
-    // load of the load-issue-bound small convolutions from 2 to 4P / (P + 1).
-    int tileP = 1;
-    if (const char* ev = getenv("CC_TUNE_RED_P")) tileP = atoi(ev);
-    const int dp = no - 2;
-    if (S == 1 && (tileP == 2 || tileP == 4) && dp >= 0 && odims[(size_t)dp] % tileP == 0 && NV / tileP >= 1) {
-      bool shared_operand = false, all_integer = true;
-      for (int j = 0; j < nloads; ++j) {
-        if (in_post(j)) continue;
-        all_integer &= p.loads[j].integer;
-        if (p.loads[j].integer && p.loads[j].coef[dp] == 0) shared_operand = true;
-      }
-      if (shared_operand && all_integer) {
-        const int P = tileP;
-        std::vector<int64_t> tdims = odims;  // the thread index space: dimension dp counts tiles of P
-        tdims[(size_t)dp] /= P;
-        const int64_t NVP = NV / P;
-        std::vector<int64_t> ostride((size_t)no, 1);
-        for (int x = no - 2; x >= 0; --x) ostride[(size_t)x] = ostride[(size_t)x + 1] * odims[(size_t)x + 1];
-        std::string gsp;  // ", g0, ..., (gt_ + p_), ..., g{no-1}"
-        for (int x = 0; x < no; ++x) gsp += x == dp ? std::string(", (gt_ + p_)") : strprintf(", g%d", x);
-        // Sliding window: a load whose address and bounds depend on the tiled dimension and on ONE reduction digit dk only through
-        // their sum or difference (the translated input of a convolution: pixel p with kernel column kx reads what pixel p + 1
-        // reads with kx + 1 ... ) is read once per distinct element into a register window, outside the dk loop, instead of P x KW
-        // times; neither NVVM nor ptxas merges those loads on its own. Only for fully unrolled reductions with a small window.
-        int jw = -1, dk = -1, sgn = 0;
-        int64_t inner = 1;  // product of the reduction digits nested inside dk
-        for (int j = 0; j < nloads && jw < 0 && T <= 96; ++j) {
-          const Load& L = p.loads[j];
-          if (in_post(j) || !L.integer || L.coef[dp] == 0 || L.coef[no - 1] != 0) continue;  // (scalar across the V lanes)
-          bool lane_free = true;
-          for (int y = 0; y < L.rows; ++y) lane_free &= L.M[(size_t)y * (nd + 1) + (no - 1)] == 0.0;
-          if (!lane_free) continue;
-          for (int x = no; x < nd && jw < 0; ++x) {
-            for (int sg : {1, -1}) {
-              if (L.coef[x] != sg * L.coef[dp]) continue;
-              bool rows_ok = true;
-              for (int y = 0; y < L.rows; ++y) rows_ok &= L.M[(size_t)y * (nd + 1) + x] == sg * L.M[(size_t)y * (nd + 1) + dp];
-              if (!rows_ok) continue;
-              int64_t in_ = 1;
-              for (int z = x + 1; z < nd; ++z) in_ *= p.dims[z];
-              if (in_ * (P + p.dims[x] - 1) > 64 || p.dims[x] < 2) continue;
-              jw = j, dk = x, sgn = sg, inner = in_;
-              break;
-            }
-          }
-        }
-        if (jw >= 0) {
-          const int KW = (int)p.dims[dk], WN = P + KW - 1, umin = sgn > 0 ? 0 : -(KW - 1);
-          // ldw: the windowed operand alone, as a scalar; evw: the term with that operand handed in
-          e("__device__ __forceinline__ float ldw(%s", rgdecl.c_str());
-          for (int x = 0; x < no; ++x) e(", const %s g%d", IDX, x);
-          e("%s) {\n", params.c_str());
-          LoadCtx cs{1, -1, IDX};
-          emit_load(e, p, jw, cs, "  ");
-          e("  return L%d[0];\n}\n", jw);
-          e("__device__ __forceinline__ void evw(%s", rgdecl.c_str());
-          for (int x = 0; x < no; ++x) e(", const %s g%d", IDX, x);
-          e("%s, const float in_, float (&o)[%d]) {\n", params.c_str(), V);
-          LoadCtx cv{V, no - 1, IDX};
-          for (int j = 0; j < nloads; ++j) {
-            if (in_post(j)) continue;
-            if (j == jw)
-              e("  float L%d[%d];\n  #pragma unroll\n  for (int l = 0; l < %d; ++l) L%d[l] = in_;\n", j, V, V, j);
-            else
-              emit_load(e, p, j, cv, "  ");
-          }
-          e("  #pragma unroll\n  for (int l = 0; l < %d; ++l) {\n", V);
-          emit_op_list(e, p.ops, "    ", "l", p.results);
-          e("    o[l] = _%d;\n  }\n}\n", p.results[0]);
-          plan.note += strprintf("; sliding window of %d over reduction digit %d", WN, dk - no);
-        }
-        // reduction digits passed to ldw: g{dk} = 0 and the tiled position carries the whole offset
-        std::string rgs_w, gs_w;
-        for (int x = no; x < nd; ++x) rgs_w += std::string(x > no ? ", " : "") + (x == dk ? std::string("0") : strprintf("g%d", x));
-        for (int x = 0; x < no; ++x) gs_w += x == dp ? std::string(", (gt_ + u_)") : strprintf(", g%d", x);
-        e("// register tile: %d positions along g%d per thread\n", P, dp);
-        e("extern \"C\" __global__ void __launch_bounds__(256) reduce_cols(%s) {\n", param_list(n_args, true, "dst").c_str());
-        e("  const %s v = (%s)blockIdx.x * 256 + threadIdx.x;\n  if (v >= %lld) return;\n", IDX, IDX, (long long)NVP);
-        // decode over the tiled index space; g{dp} becomes the tile's first position gt_
-        e("  %s rem_ = v * %d;\n", IDX, V);
-        for (int x = no - 1; x >= 1; --x) {
-          if (x == dp)
-            e("  const %s gt_ = (rem_ %% (%s)%lld) * %d; rem_ /= (%s)%lld;\n", IDX, IDX, (long long)tdims[(size_t)x], P, IDX, (long long)tdims[(size_t)x]);
-          else
-            e("  const %s g%d = rem_ %% (%s)%lld; rem_ /= (%s)%lld;\n", IDX, x, IDX, (long long)tdims[(size_t)x], IDX, (long long)tdims[(size_t)x]);
-        }
-        if (dp == 0)
-          e("  const %s gt_ = rem_ * %d;\n", IDX, P);
-        else
-          e("  const %s g0 = rem_;\n", IDX);
-        e("  float acc[%d][%d];\n  #pragma unroll\n  for (int p_ = 0; p_ < %d; ++p_)\n    #pragma unroll\n    for (int l = 0; l < %d; ++l) acc[p_][l] = %s;\n", P, V, P, V, ZERO);
-        std::string ind = "  ";
-        auto open_loop = [&](int x) {
-          if (T <= 96)
-            e("%s#pragma unroll\n", ind.c_str());
-          else if (x == nd - 1)
-            e("%s#pragma unroll %d\n", ind.c_str(), (int)std::min<int64_t>(8, p.dims[x]));
-          else
-            e("%s#pragma unroll 1\n", ind.c_str());
-          e("%sfor (%s g%d = 0; g%d < %lld; ++g%d) {\n", ind.c_str(), IDX, x, x, (long long)p.dims[x], x);
-          ind += "  ";
-        };
-        auto close_loop = [&]() {
-          ind.resize(ind.size() - 2);
-          e("%s}\n", ind.c_str());
-        };
-        if (jw < 0) {
-          for (int x = no; x < nd; ++x) open_loop(x);
-          e("%s#pragma unroll\n%sfor (int p_ = 0; p_ < %d; ++p_) {\n", ind.c_str(), ind.c_str(), P);
-          e("%s  float x[%d];\n%s  evd(%s%s%s, x);\n", ind.c_str(), V, ind.c_str(), rgs.c_str(), gsp.c_str(), pass.c_str());
-          e("%s  #pragma unroll\n%s  for (int l = 0; l < %d; ++l) acc[p_][l] = %s;\n%s}\n", ind.c_str(), ind.c_str(), V, AP("acc[p_][l]", "x[l]").c_str(), ind.c_str());
-          for (int x = no; x < nd; ++x) close_loop();
-        } else {
-          const int KW = (int)p.dims[dk], WN = P + KW - 1, umin = sgn > 0 ? 0 : -(KW - 1);
-          // flat index of the digits nested inside dk (row-major), for the window's first subscript
-          std::string wi = "0";
-          for (int x = dk + 1; x < nd; ++x) wi = strprintf("(%s) * %lld + g%d", wi.c_str(), (long long)p.dims[x], x);
-          for (int x = no; x < dk; ++x) open_loop(x);
-          e("%sfloat win_[%lld][%d];\n", ind.c_str(), (long long)inner, WN);
-          for (int x = dk + 1; x < nd; ++x) open_loop(x);
-          e("%s#pragma unroll\n%sfor (int w_ = 0; w_ < %d; ++w_) {\n%s  const int u_ = w_ + (%d);\n%s  win_[%s][w_] = ldw(%s%s%s);\n%s}\n", ind.c_str(), ind.c_str(), WN, ind.c_str(), umin,
-            ind.c_str(), wi.c_str(), rgs_w.c_str(), gs_w.c_str(), pass.c_str(), ind.c_str());
-          for (int x = dk + 1; x < nd; ++x) close_loop();
-          for (int x = dk; x < nd; ++x) open_loop(x);  // the reference's term order: dk, then the digits nested inside it
-          e("%s#pragma unroll\n%sfor (int p_ = 0; p_ < %d; ++p_) {\n", ind.c_str(), ind.c_str(), P);
-          e("%s  float x[%d];\n%s  evw(%s%s%s, win_[%s][p_ + (%d) * (int)g%d - (%d)], x);\n", ind.c_str(), V, ind.c_str(), rgs.c_str(), gsp.c_str(), pass.c_str(), wi.c_str(), sgn, dk, umin);
-          e("%s  #pragma unroll\n%s  for (int l = 0; l < %d; ++l) acc[p_][l] = %s;\n%s}\n", ind.c_str(), ind.c_str(), V, AP("acc[p_][l]", "x[l]").c_str(), ind.c_str());
-          for (int x = no; x < nd; ++x) close_loop();
-        }
-        std::string lin = "(long long)0";
-        for (int x = 0; x < no; ++x) lin += x == dp ? strprintf(" + (long long)(gt_ + p_) * %lldLL", (long long)ostride[(size_t)x]) : strprintf(" + (long long)g%d * %lldLL", x, (long long)ostride[(size_t)x]);
-        e("  #pragma unroll\n  for (int p_ = 0; p_ < %d; ++p_) {\n", P);
-        if (has_post) e("    post(acc[p_]%s%s);\n", gsp.c_str(), pass.c_str());
-        e("    float* d = dst + (%s);\n", lin.c_str());
-        if (V == 4)
-          e("    cc_stg4(d, acc[p_]);\n");
-        else
-          e("    d[0] = acc[p_][0];\n");
-        e("  }\n}\n");
-        LaunchSpec ls;
-        ls.entry = "reduce_cols";
-        ls.grid[0] = (uint32_t)((NVP + 255) / 256);
-        ls.block[0] = 256;
-        for (int i = 0; i < n_args; ++i) ls.args.push_back(i);
-        ls.args.push_back(ARG_OUT);
-        plan.launches.push_back(ls);
-        plan.note += strprintf("; register tile of %d along output dim %d", P, dp);
-        plan.source += e.s;
-        return;
-      }
-    }
-    // Opt-in (CC_FUSE_COL_STAGE=1, until it has been timed on a GPU): the second stage runs inside reduce_cols -- the last CTA to
-    // finish a block of columns (a self-resetting counter per blockIdx.x) folds that block's partials, so the plan is one launch.
+    // (A register-tiled variant of this kernel — a thread owning P positions along the next-to-fastest output dimension, with a sliding
+    // register window over the translated input — was built in round 1 and timed in round 2 (profiles/r02_knob_ab.json): 1.08x on the
+    // 3x3 depth-8 convolution at P = 2, 0.82x at depth 16, 0.64x at P = 4 (registers 32 -> 61 -> 80, occupancy). Not a win; removed.)
+    // The second stage runs inside reduce_cols: the last CTA to finish a block of columns (a self-resetting counter per blockIdx.x) folds
+    // that block's partials, so the plan is ONE launch (timed in round 2, profiles/r02_knob_ab.json: 1.02-1.23x against the two-launch
+    // plan, 16384x4096: 55.4 -> 45.2 us). CC_FUSE_COL_STAGE=0 brings the separate reduce_partials launch back.
     const int64_t gridx = (NV + CW - 1) / CW;
-    bool fused = false;
-    if (const char* ev = getenv("CC_FUSE_COL_STAGE")) fused = atoi(ev) != 0 && Sy > 1 && gridx <= kColCounters;
+    bool fused = Sy > 1 && gridx <= kColCounters;
+    if (const char* ev = getenv("CC_FUSE_COL_STAGE")) fused = fused && atoi(ev) != 0;
     e("extern \"C\" __global__ void __launch_bounds__(256) reduce_cols(%s%s) {\n", param_list(n_args, true, "dst").c_str(),
       fused ? ", float* __restrict__ out, unsigned* __restrict__ counters" : "");
     if (S == 1) {
@@ -1997,12 +1846,13 @@ bool try_general_contraction(Plan& plan, const Program& p, int n_args) {
     return false;
   };
   // Leading output dims BOTH operands depend on are batch dims: `C[b, i, k] = sum_t A[b, i, t] * B[b, t, k]` is `batch` independent
-  // products over panels that carry the batch index in their rows. (Opt-in until it has been through the GPU tier:
-  // CC_BATCHED_CONTRACTION=1; without it such terms stay on the generic re-rolled reduction.)
+  // products over panels that carry the batch index in their rows: one tcgen05 pipeline launch per batch (timed in round 2,
+  // profiles/r02_knob_ab.json: 4 x 2048 x 1024 x 2048 2.56 -> 0.22 ms, 8 x 512^3 1.4x, small batches unchanged — they stay below the
+  // contraction threshold). CC_BATCHED_CONTRACTION=0 keeps such terms on the generic re-rolled reduction.
   int nb = 0;
-  if (const char* ev = getenv("CC_BATCHED_CONTRACTION"))
-    if (atoi(ev) != 0)
-      while (nb < no - 2 && uses(p.loads[la], nb) && uses(p.loads[lb], nb)) ++nb;
+  const char* batched_env = getenv("CC_BATCHED_CONTRACTION");
+  if (!batched_env || atoi(batched_env) != 0)
+    while (nb < no - 2 && uses(p.loads[la], nb) && uses(p.loads[lb], nb)) ++nb;
   auto split_point = [&](const Load& A, const Load& B) {
     // dims [nb, s) not used by B, dims [s, no) not used by A
     int s = nb;

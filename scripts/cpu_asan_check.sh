@@ -43,7 +43,7 @@ for seed in range(91000, 91120):
         p.g.compile(); n += 1
 print("compiled", n, "random graphs")
 PY
-for knob in "CC_NOOP=1" "CC_FUSE_COL_STAGE=1" "CC_TUNE_RED_P=4" "CC_BATCHED_CONTRACTION=1 CC_TUNE_CONTRACTION_MIN_MACS=1" "CC_PDL=0"; do
+for knob in "CC_NOOP=1" "CC_FUSE_COL_STAGE=1" "CC_BATCHED_CONTRACTION=1 CC_TUNE_CONTRACTION_MIN_MACS=1" "CC_PDL=0"; do
   echo "compile fuzz [$knob]: $(LD_PRELOAD="$PRE" ASAN_OPTIONS=detect_leaks=0 env $knob python "$W/fuzz.py" 2>&1 | grep -E "AddressSanitizer|SUMMARY|Traceback|compiled" | head -3 | tr '\n' ' ')"
 done
 

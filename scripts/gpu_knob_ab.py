@@ -2,7 +2,6 @@
   python scripts/gpu_knob_ab.py fuse_col     CC_FUSE_COL_STAGE      split axis reductions: second stage inside reduce_cols
   python scripts/gpu_knob_ab.py batched      CC_BATCHED_CONTRACTION batched matmul on the tcgen05 pipeline (one launch per batch)
   python scripts/gpu_knob_ab.py pdl          CC_PDL (default on)    programmatic dependent launch
-  python scripts/gpu_knob_ab.py red_p2|red_p4 CC_TUNE_RED_P=2|4     register tiling of column-owner reductions (small convolutions)
 Per workload: device time per step (CUDA events around the loop, best of 3), max |a - b| between the arms relative to max |a|.
 Writes gpurun_out/knob_<name>.json.  (scripts/gpu_pdl.py is the earlier, PDL-only version with host submission times.)"""
 import json
@@ -13,8 +12,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-KNOBS = {"fuse_col": ("CC_FUSE_COL_STAGE", "0", "1"), "batched": ("CC_BATCHED_CONTRACTION", "0", "1"), "pdl": ("CC_PDL", "0", "1"),
-         "red_p2": ("CC_TUNE_RED_P", "1", "2"), "red_p4": ("CC_TUNE_RED_P", "1", "4")}
+KNOBS = {"fuse_col": ("CC_FUSE_COL_STAGE", "0", "1"), "batched": ("CC_BATCHED_CONTRACTION", "0", "1"), "pdl": ("CC_PDL", "0", "1")}
 
 
 def chain(parts):

@@ -98,7 +98,7 @@ def test_read_backs_land_in_the_callers_memory(spy_dir, binding):
 
 
 def test_multi_launch_plans_and_folds_stay_on_their_stream(spy_dir):
-    r = run(spy_dir, "two_launch_plan_and_fold")
+    r = run(spy_dir, "two_launch_plan_and_fold", CC_FUSE_COL_STAGE="0")  # the separate second stage (the default fuses it, next test)
     assert r["axis_launches_per_step"] == 2
     assert r["axis"]["pdl_launches"] == 100 and r["axis"]["cuEventRecord"] == 0 and r["axis"]["cuStreamWaitEvent"] == 0 and r["axis"]["cuMemAlloc"] == 0
     assert r["fold"]["pdl_launches"] == 50 and r["fold"]["cuEventRecord"] == 0 and r["fold"]["cuStreamWaitEvent"] == 0
@@ -106,13 +106,13 @@ def test_multi_launch_plans_and_folds_stay_on_their_stream(spy_dir):
 
 
 def test_fused_second_stage_is_one_launch_and_its_counters_are_given_back(spy_dir):
-    """opt-in CC_FUSE_COL_STAGE=1 (kernel side: tests/test_kernel_emulation.py): one launch per step, the per-stream block counters are
+    """the default since round 2 (kernel side: tests/test_kernel_emulation.py): one launch per step, the per-stream block counters are
     allocated and cleared once, and freed at shutdown"""
-    r = run(spy_dir, "two_launch_plan_and_fold", CC_FUSE_COL_STAGE="1")
+    r = run(spy_dir, "two_launch_plan_and_fold")
     assert r["axis_launches_per_step"] == 1
     assert r["axis"]["pdl_launches"] == 50 and r["axis"]["cuMemAlloc"] == 0 and r["axis"]["cuMemsetD32Async"] == 0
     assert r["axis"]["cuEventRecord"] == 0 and r["axis"]["cuStreamWaitEvent"] == 0
-    r = run(spy_dir, "balance_on_shutdown", CC_FUSE_COL_STAGE="1")
+    r = run(spy_dir, "balance_on_shutdown")
     assert r["cuMemAlloc"] == r["cuMemFree"] > 0 and r["live_tensors"] == 0
 
 

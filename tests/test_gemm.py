@@ -288,14 +288,12 @@ def test_full_size_8192_rows_sampled(cuda):
         x.release()
 
 
-@pytest.mark.skipif(not __import__("os").environ.get("CC_TEST_BATCHED"), reason="opt-in lowering (CC_BATCHED_CONTRACTION=1): run with CC_TEST_BATCHED=1 once it is being validated on a GPU")
 @pytest.mark.parametrize("b,m,k,n", [(3, 128, 96, 256), (8, 200, 130, 72), (2, 512, 512, 512)])
 def test_batched_matmul_lowers_to_one_pipeline_launch_per_batch(cuda, monkeypatch, b, m, k, n):
     """C[b, i, k] = sum_t A[b, i, t] * B[b, t, k] (matmul2 with a leading batch dim): batch dims go into the rows of both operand
     panels and the tcgen05 pipeline runs once per batch on its block of rows.  Exact on small integers.  The panel gathers and the
     per-batch blocking are checked on the CPU tier (tests/test_kernel_emulation.py); this is the device half."""
-    monkeypatch.setenv("CC_BATCHED_CONTRACTION", "1")
-    monkeypatch.setenv("CC_TUNE_CONTRACTION_MIN_MACS", "1")
+    monkeypatch.setenv("CC_TUNE_CONTRACTION_MIN_MACS", "1")  # (the default threshold keeps the first two shapes on the generic reduction)
     cuda.kernel_cache_clear()
     try:
         rng = np.random.default_rng(b * 1000 + m)

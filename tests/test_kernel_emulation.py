@@ -174,16 +174,16 @@ def test_general_contraction_panels_and_epilogue(monkeypatch):
             return chain((a3 * b3).split(1))
         check(matmul_over_views, "over gathered operand panels", 2)
 
-        # batched matmul C[b, i, k] = sum_t A[b, i, t] * B[b, t, k]: opt-in (CC_BATCHED_CONTRACTION=1) until it has run on the GPU tier
+        # batched matmul C[b, i, k] = sum_t A[b, i, t] * B[b, t, k]: on the tensor-core pipeline by default since round 2 (profiles/r02_knob_ab.json)
         def batched(B, leaf):
             a, b = leaf([3, 36, 40], 6), leaf([3, 40, 64], 7)
             a4 = a.broadcast([3, 36, 40, 64])
             b4 = b.reshape([3, 1, 40, 64]).broadcast([3, 36, 40, 64])
             return chain((a4 * b4).split(2))
-        check(batched, "column owner", 1)  # off by default: the generic re-rolled reduction
-        monkeypatch.setenv("CC_BATCHED_CONTRACTION", "1")
-        cuda.kernel_cache_clear()
         check(batched, "(batch of 3)", 2)
+        monkeypatch.setenv("CC_BATCHED_CONTRACTION", "0")
+        cuda.kernel_cache_clear()
+        check(batched, "column owner", 1)  # switched off: the generic re-rolled reduction
         monkeypatch.delenv("CC_BATCHED_CONTRACTION")
     finally:
         monkeypatch.delenv("CC_TUNE_CONTRACTION_MIN_MACS")
@@ -191,9 +191,8 @@ def test_general_contraction_panels_and_epilogue(monkeypatch):
 
 
 def test_fused_second_stage_of_a_split_axis_reduction(monkeypatch):
-    """opt-in (CC_FUSE_COL_STAGE=1): the last CTA to finish a block of columns folds that block's partials inside reduce_cols -- one
-    launch instead of two; the block counters reset themselves (checked by the emulator after every run)"""
-    monkeypatch.setenv("CC_FUSE_COL_STAGE", "1")
+    """default since round 2 (profiles/r02_knob_ab.json): the last CTA to finish a block of columns folds that block's partials inside
+    reduce_cols -- one launch instead of two; the block counters reset themselves (checked by the emulator after every run)"""
     cuda.kernel_cache_clear()
     try:
         for _ in range(2):  # twice: the second run starts from the counters the first one left
@@ -203,61 +202,14 @@ def test_fused_second_stage_of_a_split_axis_reduction(monkeypatch):
         check(lambda B, leaf: B.abs(chain(leaf([300, 64], 1).split(0))) - leaf([64], 2), "second stage fused into reduce_cols", 1)  # epilogue in stage 2
         k = chain(T.random([300, 64], seed=1).split(0)).compile()
         assert k.info.n_launches == 1
-    finally:
-        monkeypatch.delenv("CC_FUSE_COL_STAGE")
+        monkeypatch.setenv("CC_FUSE_COL_STAGE", "0")
         cuda.kernel_cache_clear()
-    k = chain(T.random([300, 64], seed=1).split(0)).compile()
-    assert k.info.n_launches == 2 and "fused into reduce_cols" not in k.source  # off by default
-
-
-@pytest.mark.parametrize("P", [2, 4])
-def test_register_tiled_reduction(monkeypatch, P):
-    """opt-in (CC_TUNE_RED_P): a thread owns P positions along the output dimension next to the fastest one; operands that do not depend
-    on it (convolution weights) are shared by the P copies of the term"""
-    monkeypatch.setenv("CC_TUNE_RED_P", str(P))
-    cuda.kernel_cache_clear()
-    try:
-        def conv(B, leaf, filters=8, depth=3):
-            x, w, bias = leaf([2, 6, 8, depth], 1, 1.0), leaf([3, 3, depth, filters], 2), leaf([filters], 3)
-            xs = x.split(3)
-            ws = [[[wc.split(0) for wc in wx.split(0)] for wx in wy.split(0)] for wy in w.split(0)]
-            bs = bias.split(0)
-            outs = []
-            for f in range(filters):
-                terms = [xs[c].translate([0, dy - 1, dx - 1]) * ws[dy][dx][c][f].broadcast([2, 6, 8]) for dy in range(3) for dx in range(3) for c in range(depth)]
-                outs.append(B.max(chain(terms) + bs[f].broadcast([2, 6, 8]), B.fill(0.0, [2, 6, 8])))  # bias + relu epilogue
-            return B.join(outs)
-        check(conv, f"register tile of {P} along output dim 2", 1)
-        check(conv, f"sliding window of {P + 2} over reduction digit 1", 1)  # the translated input: one load per distinct element of a kernel row
-
-        def conv_general(B, leaf, kh, kw, flip, depth, filters=4, shape=(1, 5, 12)):
-            """kh x kw window, correlation (flip = -1: x[w + kx - r], the window slides the other way) or convolution (flip = +1)"""
-            x, w = leaf(list(shape) + [depth], 1, -3.0), leaf([kh, kw, depth, filters], 2)
-            xs = x.split(3)
-            ws = [[[wc.split(0) for wc in wx.split(0)] for wx in wy.split(0)] for wy in w.split(0)]
-            outs = []
-            for f in range(filters):
-                terms = [xs[c].translate([0, flip * (dy - kh // 2), flip * (dx - kw // 2)]) * ws[dy][dx][c][f].broadcast(list(shape))
-                         for dy in range(kh) for dx in range(kw) for c in range(depth)]
-                outs.append(chain(terms))
-            return B.join(outs)
-        check(lambda B, leaf: conv_general(B, leaf, 1, 5, +1, 2), f"sliding window of {P + 4} over reduction digit 0", 1)   # 1 x 5 (digits: kx, c), padding -3
-        check(lambda B, leaf: conv_general(B, leaf, 3, 3, -1, 2), f"sliding window of {P + 2} over reduction digit 1", 1)   # the window slides the other way
-        check(lambda B, leaf: conv_general(B, leaf, 1, 3, +1, 20), f"register tile of {P} along output dim 2", 1)            # window too large for registers: tiled, not windowed
-        assert "sliding window" not in conv_general(T, lambda s, seed, pad=0.0: T.random(s, seed=seed, padding=pad), 1, 3, +1, 20).compile().source
-        # a matmul-like term small enough to stay on the generic reduction: A[i, t] is shared along k's neighbour dimension
-        def small_matmul(B, leaf):
-            a, b = leaf([8, 12], 4), leaf([12, 16], 5)
-            a3 = a.broadcast([8, 12, 16])
-            b3 = b.reshape([1, 12, 16]).broadcast([8, 12, 16])
-            return chain((a3 * b3).split(1))
-        check(small_matmul, f"register tile of {P} along output dim 0", 1)
-        # no operand is shared along the tiled dimension: the plan stays untiled
-        check(lambda B, leaf: chain(leaf([12, 8, 128], 6).split(0)), "column owner", 1)
+        check(lambda B, leaf: chain(leaf([300, 64], 1).split(0)), "column owner", 1)  # switched off: reduce_cols + reduce_partials
+        k = chain(T.random([300, 64], seed=1).split(0)).compile()
+        assert k.info.n_launches == 2 and "fused into reduce_cols" not in k.source
     finally:
-        monkeypatch.delenv("CC_TUNE_RED_P")
+        monkeypatch.delenv("CC_FUSE_COL_STAGE", raising=False)
         cuda.kernel_cache_clear()
-    assert "register tile" not in chain(T.random([12, 8, 128], seed=1).split(0)).compile().source
 
 
 def test_matmul1_join_of_folds_rerolled_twice():
