@@ -86,16 +86,6 @@ private[compute] object CudaNative {
     }
   }
 
-  private def ints(stack: MemoryStack, values: Array[Int]): Long = {
-    if (values.isEmpty) MemoryUtil.NULL
-    else {
-      val buffer = stack.mallocInt(values.length)
-      buffer.put(values)
-      buffer.flip()
-      MemoryUtil.memAddress(buffer)
-    }
-  }
-
   // ---- library / device (compute_cuda.h: "library / device") -------------------------------------------------------------
 
   private val cc_init = address("cc_init")
@@ -516,6 +506,63 @@ private[compute] object CudaNative {
     }
   }
 
-  // (`ints` is used by the sharding entry points of CudaSharding.scala)
-  private[compute] def intArrayOnStack(stack: MemoryStack, values: Array[Int]): Long = ints(stack, values)
+  def commGeneration(): Long = withStack { stack =>
+    outHandle(stack)(out => call(cc_comm_generation).pointer(out).checked())
+  }
+
+  // ---- leading-axis sharding (compute_cuda.h: "leading-axis sharding over the GPUs of one box") ----------------------------------------
+
+  private val cc_comm_generation = address("cc_comm_generation")
+  private val cc_buffer_copy = address("cc_buffer_copy")
+  private val cc_shard_rows = address("cc_shard_rows")
+  private val cc_shard_agree = address("cc_shard_agree")
+  private val cc_shard_launch_allreduce = address("cc_shard_launch_allreduce")
+  private val cc_shard_launch_allgather = address("cc_shard_launch_allgather")
+
+  def bufferCopy(destination: Long, source: Long, numberOfFloats: Long, waits: Array[Long]): Long = withStack { stack =>
+    outHandle(stack) { out =>
+      call(cc_buffer_copy).long(destination).long(source).long(numberOfFloats).pointer(longs(stack, waits)).int(waits.length).pointer(out).checked()
+    }
+  }
+
+  /** `(first row, row count)` of `rank`'s block: the first `rows % numberOfRanks` ranks own one extra row */
+  def shardRows(rows: Long, numberOfRanks: Int, rank: Int): (Long, Long) = withStack { stack =>
+    val out = stack.mallocLong(2)
+    val base = MemoryUtil.memAddress(out)
+    call(cc_shard_rows).long(rows).int(numberOfRanks).int(rank).pointer(base).pointer(base + 8).checked()
+    (out.get(0), out.get(1))
+  }
+
+  /** collective: did every rank pass the same value? */
+  def shardAgree(value: Long): Boolean = withStack { stack =>
+    val out = stack.mallocInt(1)
+    call(cc_shard_agree).long(value).pointer(MemoryUtil.memAddress(out)).checked()
+    out.get(0) != 0
+  }
+
+  /** `cc_launch`, then all-reduce (sum) of the output across ranks, in place */
+  def shardLaunchAllReduce(kernel: Long, arguments: Array[Long], output: Long, waits: Array[Long]): Long = withStack { stack =>
+    outHandle(stack) { out =>
+      call(cc_shard_launch_allreduce).long(kernel).pointer(longs(stack, arguments)).int(arguments.length).long(output).pointer(longs(stack, waits)).int(waits.length).pointer(out).checked()
+    }
+  }
+
+  /** `cc_launch` on this rank's row block with the result gathered on every rank; returns `(event, fused)` — `fused` tells whether
+    * the exchange ran inside the contraction's epilogue */
+  def shardLaunchAllGather(kernel: Long, arguments: Array[Long], gathered: Long, waits: Array[Long]): (Long, Boolean) = withStack { stack =>
+    val fused = stack.mallocInt(1)
+    val event = outHandle(stack) { out =>
+      call(cc_shard_launch_allgather)
+        .long(kernel)
+        .pointer(longs(stack, arguments))
+        .int(arguments.length)
+        .long(gathered)
+        .pointer(longs(stack, waits))
+        .int(waits.length)
+        .pointer(out)
+        .pointer(MemoryUtil.memAddress(fused))
+        .checked()
+    }
+    (event, fused.get(0) != 0)
+  }
 }

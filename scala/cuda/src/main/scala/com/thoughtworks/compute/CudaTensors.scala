@@ -192,7 +192,7 @@ trait CudaTensors extends Cuda {
 
   /** enqueueClosure's second half (`Tensors.scala:1331-1381`): evaluate the argument tensors in parallel, allocate the output,
     * launch after the arguments' events. One call, one `cc_launch`; the library picks the stream from the buffers' hazards. */
-  private def enqueue(kernel: CompiledKernel, shape: Array[Int]): Do[PendingBuffer] = {
+  private def enqueue(kernel: CompiledKernel, shape: Array[Int], allReduce: Boolean = false): Do[PendingBuffer] = {
     kernel.arguments
       .traverse[ParallelDo, PendingBuffer] { tensor =>
         Parallel(tensor.doBuffer)
@@ -201,16 +201,80 @@ trait CudaTensors extends Cuda {
       .flatMap { arguments: List[PendingBuffer] =>
         allocateBuffer(numberOfElements(shape)).flatMap { outputBuffer =>
           Do.monadicCloseable {
+              val argumentHandles = arguments.map(_.buffer.handle).toArray
+              val waits = arguments.flatMap(_.eventOption.map(_.handle)).toArray
+              // a partial sum over the sharded axis is completed by an all-reduce of the freshly written output (cc_shard_launch_allreduce)
               new Event(
-                CudaNative.launch(kernel.handle,
-                                  arguments.map(_.buffer.handle).toArray,
-                                  outputBuffer.handle,
-                                  arguments.flatMap(_.eventOption.map(_.handle)).toArray))
+                if (allReduce) CudaNative.shardLaunchAllReduce(kernel.handle, argumentHandles, outputBuffer.handle, waits)
+                else CudaNative.launch(kernel.handle, argumentHandles, outputBuffer.handle, waits))
             }
             .map { event =>
               EventBuffer(outputBuffer, event): PendingBuffer
             }
         }
+      }
+  }
+
+  // ---- gathers of sharded tensors ------------------------------------------------------------------------------------------------------
+
+  /** What is cached per communicator (`GatherTensor::PerCommunicator` in tensor.cpp): the block sizes all ranks agreed on, and one
+    * symmetric (peer-mapped) arena per size — `cuMemAlloc` + an IPC handle exchange, far too slow per evaluation; the entry barrier of
+    * `cc_shard_launch_allgather` protects an arena against the previous gather's readers. Collective evaluations run one at a time. */
+  private object communicatorCache {
+    private var generation = 0L
+    private val agreed = scala.collection.mutable.Set.empty[Long]
+    private val arenas = scala.collection.mutable.Map.empty[Long, DeviceBuffer]
+    private def current(): Unit = {
+      val now = CudaNative.commGeneration()
+      if (now != generation) { // a new communicator: the old arenas' memory went with the old one
+        arenas.values.foreach(_.release())
+        arenas.clear()
+        agreed.clear()
+        generation = now
+      }
+    }
+    def requireEqualBlocks(blockFloats: Long): Unit = synchronized {
+      current()
+      if (!agreed(blockFloats)) {
+        if (!CudaNative.shardAgree(blockFloats)) {
+          throw new IllegalArgumentException(
+            s"gather needs equal row blocks on every rank (this rank holds $blockFloats floats): pad the leading axis to a multiple of the number of ranks")
+        }
+        agreed += blockFloats
+      }
+    }
+    def arena(numberOfFloats: Long): DeviceBuffer = synchronized {
+      current()
+      arenas.getOrElseUpdate(numberOfFloats, new DeviceBuffer(CudaNative.commSymmetricAlloc(numberOfFloats)))
+    }
+  }
+
+  /** A contraction over a row block, gathered from its own epilogue (`cc_shard_launch_allgather` -> `cc_matmul_3xtf32_allgather`):
+    * every accumulator tile is TMA-stored into every rank's copy of the symmetric arena, so the exchange overlaps the MMAs. */
+  private def gatherFromEpilogue(block: InlineTensor, wholeFloats: Long, zeroCopy: Boolean): Do[PendingBuffer] = {
+    val arena = communicatorCache.arena(wholeFloats)
+    block.plan.arguments
+      .traverse[ParallelDo, PendingBuffer](tensor => Parallel(tensor.doBuffer))
+      .unwrap
+      .flatMap { arguments: List[PendingBuffer] =>
+        Do.monadicCloseable {
+            val (event, _) = CudaNative.shardLaunchAllGather(block.plan.handle,
+                                                             arguments.map(_.buffer.handle).toArray,
+                                                             arena.handle,
+                                                             arguments.flatMap(_.eventOption.map(_.handle)).toArray)
+            new Event(event)
+          }
+          .flatMap { gathered =>
+            if (zeroCopy) {
+              arena.retain()
+              Do.monadicCloseable(new DeviceBuffer(arena.handle)).map(view => EventBuffer(view, gathered): PendingBuffer)
+            } else {
+              allocateBuffer(wholeFloats).flatMap { copy =>
+                Do.monadicCloseable(new Event(CudaNative.bufferCopy(copy.handle, arena.handle, wholeFloats, Array(gathered.handle))))
+                  .map(copied => EventBuffer(copy, copied): PendingBuffer)
+              }
+            }
+          }
       }
   }
 
@@ -281,11 +345,11 @@ trait CudaTensors extends Cuda {
     def randomNormal(shape: Array[Int], seed: Int = Random.nextInt(), padding: Float = 0.0f): NonInlineTensor =
       generated(shape, padding)((buffer, size) => CudaNative.randomNormal(buffer, size, seed))
 
-    def abs(operand: Tensor): InlineTensor = operand.derivedTensor(trees.float.abs(operand.floatClosure))
-    def sqrt(operand: Tensor): InlineTensor = operand.derivedTensor(trees.float.sqrt(operand.floatClosure))
-    def tanh(operand: Tensor): InlineTensor = operand.derivedTensor(trees.float.tanh(operand.floatClosure))
-    def exp(operand: Tensor): InlineTensor = operand.derivedTensor(trees.float.exp(operand.floatClosure))
-    def log(operand: Tensor): InlineTensor = operand.derivedTensor(trees.float.log(operand.floatClosure))
+    def abs(operand: Tensor): InlineTensor = operand.unary(trees.float.abs(_))
+    def sqrt(operand: Tensor): InlineTensor = operand.unary(trees.float.sqrt(_))
+    def tanh(operand: Tensor): InlineTensor = operand.unary(trees.float.tanh(_))
+    def exp(operand: Tensor): InlineTensor = operand.unary(trees.float.exp(_))
+    def log(operand: Tensor): InlineTensor = operand.unary(trees.float.log(_))
 
     def min(leftHandSide: Tensor, rightHandSide: Tensor): InlineTensor =
       leftHandSide.binary(rightHandSide)(trees.float.min(_, _))
@@ -305,9 +369,15 @@ trait CudaTensors extends Cuda {
         case Some(dimension) => head.shape.patch(dimension, Array(tensors.length), 0)
         case None            => head.shape :+ tensors.length
       }
+      val anyRowBlock = tensors.exists(_.distribution == Distribution.RowBlock)
+      if (anyRowBlock && position.contains(0)) {
+        throw new UnsupportedOperationException("join at dimension 0 would put the new dimension in front of the sharded leading axis: gather first")
+      }
       new NonInlineTensor {
         val shape: Array[Int] = joinedShape
         val padding: Float = head.padding
+        // the new dimension is never the leading one here: row blocks stay row blocks
+        override val distribution: Distribution = if (anyRowBlock) Distribution.RowBlock else Distribution.Whole
         private[compute] lazy val plan: CompiledKernel = compile(joinedShape) { writer =>
           val elements = tensors.map(tensor => writer.write(tensor.closure.tree))
           position match {
@@ -321,13 +391,13 @@ trait CudaTensors extends Cuda {
 
     /** `tensors` become the slices of a new LAST dimension (`Tensors.scala:577-598`): one kernel whose root is
       * `Concatenate(elements)` (`Trees.scala:953-973`). */
-    def join(tensors0: Seq[Tensor]): NonInlineTensor = joined(forced(tensors0), None)
+    def join(tensors0: Seq[Tensor]): NonInlineTensor = joined(forced(tensors0).map(_.combined), None)
 
     /** `tensors` become the slices of a new dimension at `dimension`. The reference joins last and then gathers a permuted
       * view of the result in a second kernel (`Tensors.scala:560-575`); here the element index is placed at `dimension` by the
       * same kernel (`ConcatenateAt`), with the same values and shape. */
     def join(tensors0: Seq[Tensor], dimension: Int): Tensor = {
-      val tensors = forced(tensors0)
+      val tensors = forced(tensors0).map(_.combined)
       if (dimension < 0 || dimension > tensors.head.shape.length) {
         throw new IllegalArgumentException
       }
@@ -346,6 +416,10 @@ trait CudaTensors extends Cuda {
 
     /** @group metadata */
     def padding: Float
+
+    /** How this tensor is spread over the ranks of the communicator; see [[shard]]. Follows the tensor through the lazy graph.
+      * @group metadata */
+    def distribution: Distribution = Distribution.Whole
 
     protected[compute] val closure: FloatTerm
 
@@ -373,6 +447,9 @@ trait CudaTensors extends Cuda {
           val cached: CachedTensor = new CachedTensor {
             val shape: Array[Int] = thisTensor.shape
             val padding: Float = thisTensor.padding
+            // (a partial sum comes back from doBuffer all-reduced: whole)
+            override val distribution: Distribution =
+              if (thisTensor.distribution == Distribution.RowBlock) Distribution.RowBlock else Distribution.Whole
             private[compute] val doBuffer: Do[PendingBuffer] = Do.resource {
               pendingBuffer.retain()
               Resource(pendingBuffer, UnitContinuation.delay { pendingBuffer.release() })
@@ -386,12 +463,88 @@ trait CudaTensors extends Cuda {
     /** @group delayed */
     def nonInline: NonInlineTensor
 
+    // ---- tensors sharded over the GPUs of one box (include/compute_cuda.h: ct_shard / ct_gather; C++ twin: tensor.cpp) --------------
+
+    /** Declares this tensor (`[rows on this rank, ...]`) to be THIS rank's row block of a tensor sharded along its leading axis.
+      * User code stays the single-GPU code: elementwise operators, views that keep the leading axis in place and operations with
+      * replicated operands keep a row block a row block (no exchange; the split / broadcast / sum matmul of a row block of A with a
+      * replicated B is still one tcgen05 contraction per rank); `sum` is the GLOBAL sum; `split(0)` yields the local rows as partial
+      * contributions whose fold is all-reduced when it is evaluated or used by anything but `+`; views that would mix the sharded
+      * axis throw (gather or replicate first, SURVEY §8e). Collective operations must run in the same order on every rank.
+      * @group delayed */
+    def shard: NonInlineTensor = {
+      if (distribution != Distribution.Whole || shape.isEmpty) {
+        throw new IllegalArgumentException("only a whole, non-scalar tensor can be declared a row block")
+      }
+      new NonInlineTensor {
+        val shape: Array[Int] = thisTensor.shape
+        val padding: Float = thisTensor.padding
+        override def distribution: Distribution = Distribution.RowBlock
+        private[compute] def doBuffer: Do[PendingBuffer] = thisTensor.doBuffer
+      }
+    }
+
+    /** partial sum -> the sum itself (a fusion barrier: evaluating a partial sum all-reduces it); identity for anything else */
+    private[CudaTensors] def combined: Tensor = {
+      if (distribution != Distribution.PartialSum) this
+      else
+        new NonInlineTensor {
+          val shape: Array[Int] = thisTensor.shape
+          val padding: Float = thisTensor.padding
+          private[compute] def doBuffer: Do[PendingBuffer] = thisTensor.doBuffer
+        }
+    }
+
+    /** The whole tensor on every rank (`[numberOfRanks * rows, ...]`; needs equal blocks — checked collectively, uneven blocks are an
+      * `IllegalArgumentException` on every rank). A sharded matmul result is gathered by the contraction's own epilogue (TMA stores
+      * into every rank's copy over NVLink). `zeroCopy` returns a view of the communicator's symmetric arena, valid until the next
+      * gather of the same size; otherwise the result is copied out of it.
+      * @group delayed */
+    def gather(zeroCopy: Boolean = false): Tensor = distribution match {
+      case Distribution.Whole      => this
+      case Distribution.PartialSum => combined
+      case Distribution.RowBlock =>
+        val (numberOfRanks, _) = CudaNative.commInfo()
+        val blockFloats = numberOfElements(shape)
+        new NonInlineTensor {
+          val shape: Array[Int] = (thisTensor.shape.head * numberOfRanks) +: thisTensor.shape.tail
+          val padding: Float = thisTensor.padding
+          private[compute] lazy val doBuffer: Do[PendingBuffer] = Do.suspend {
+            if (numberOfRanks == 1) {
+              thisTensor.doBuffer
+            } else {
+              communicatorCache.requireEqualBlocks(blockFloats)
+              thisTensor match {
+                case inline: InlineTensor
+                    if CudaNative.commPeerEnabled() && inline.plan.kind == 2 && inline.shape.length == 2 && inline.shape(1) % 4 == 0 =>
+                  gatherFromEpilogue(inline, blockFloats * numberOfRanks, zeroCopy)
+                case _ =>
+                  thisTensor.doBuffer.flatMap { block =>
+                    allocateBuffer(blockFloats * numberOfRanks).flatMap { whole =>
+                      Do.monadicCloseable(new Event(CudaNative.allGather(block.buffer.handle, whole.handle, blockFloats, block.eventOption.map(_.handle).toArray)))
+                        .map(event => EventBuffer(whole, event): PendingBuffer)
+                    }
+                  }
+              }
+            }
+          }.shared
+        }
+    }
+
     /** `Tensor.sum` and its siblings (`Tensors.scala:303-393, 673-771`; `MonoidPrograms` is generic over append / zero).
       * A materialised operand summed with `+` runs the library's reduction program over the buffer (`cc_reduce_sum`); an
       * inline operand is folded INSIDE one kernel (a `Reduce` root: one pass over the inputs, nothing materialised — the
       * reference always materialises first, `Tensors.scala:678`). Both fold in the same order, so `e.sum` and
       * `e.doCache.sum` agree bit for bit. */
     def reduce(monoid: Monoid): NonInlineTensor = {
+      if (distribution == Distribution.PartialSum) {
+        return combined.reduce(monoid)
+      }
+      // a row block folds to the GLOBAL result: local fold + all-reduce of its one float (only + is combined across ranks)
+      val acrossRanks = distribution == Distribution.RowBlock
+      if (acrossRanks && monoid != Monoid.Plus) {
+        throw new UnsupportedOperationException("only + is combined across ranks: gather a row block before reducing it with another monoid")
+      }
       new NonInlineTensor {
         val shape: Array[Int] = ScalarShape
         val padding: Float = thisTensor.padding
@@ -401,7 +554,12 @@ trait CudaTensors extends Cuda {
               buffered.doBuffer.flatMap { input =>
                 allocateBuffer(1L).flatMap { output =>
                   Do.monadicCloseable {
-                      new Event(CudaNative.reduceSum(input.buffer.handle, numberOfElements(thisTensor.shape), output.handle, input.eventOption.map(_.handle).toArray))
+                      val waits = input.eventOption.map(_.handle).toArray
+                      val length = numberOfElements(thisTensor.shape)
+                      // ONE kernel folds the block and all-reduces the result over NVLink peer memory (cc_reduce_sum_allreduce)
+                      new Event(
+                        if (acrossRanks) CudaNative.reduceSumAllReduce(input.buffer.handle, length, output.handle, waits)
+                        else CudaNative.reduceSum(input.buffer.handle, length, output.handle, waits))
                     }
                     .map { event =>
                       EventBuffer(output, event): PendingBuffer
@@ -413,7 +571,7 @@ trait CudaTensors extends Cuda {
                 val plan = compile(ScalarShape) { writer =>
                   writer.reduce(monoid.kind, writer.write(thisTensor.closure.tree), thisTensor.shape)
                 }
-                enqueue(plan, ScalarShape)
+                enqueue(plan, ScalarShape, allReduce = acrossRanks)
               }
           }
         }.shared
@@ -442,29 +600,44 @@ trait CudaTensors extends Cuda {
 
     // ---- shapes of binary operations (Tensors.scala:203-222): LEADING dimensions align, missing / unit ones stretch ----
 
-    private[CudaTensors] def binary(rightHandSide: Tensor)(operator: (FloatTerm, FloatTerm) => FloatTerm): InlineTensor = {
-      val commonShape = autoBroadcastShape(shape, rightHandSide.shape)
-      val left = broadcast(commonShape)
-      val right = rightHandSide.broadcast(commonShape)
-      left.derivedTensor(operator(left.floatClosure, right.floatClosure))
+    private[CudaTensors] def binary(rightHandSide: Tensor, keepsPartialSums: Boolean = false)(
+        operator: (FloatTerm, FloatTerm) => FloatTerm): InlineTensor = {
+      // partial sums stay partial only under + with another partial sum (the fold of split(0) slices); anything else needs the sum itself
+      val partial = keepsPartialSums && distribution == Distribution.PartialSum && rightHandSide.distribution == Distribution.PartialSum
+      val (leftOperand, rightOperand) = if (partial) (this, rightHandSide) else (combined, rightHandSide.combined)
+      val commonShape = autoBroadcastShape(leftOperand.shape, rightOperand.shape)
+      val left = leftOperand.broadcast(commonShape)
+      val right = rightOperand.broadcast(commonShape)
+      // a row block combined with a replicated operand (B of the row-sharded matmul, a constant) is a row block
+      val result =
+        if (partial) Distribution.PartialSum
+        else if (left.distribution == Distribution.RowBlock || right.distribution == Distribution.RowBlock) Distribution.RowBlock
+        else Distribution.Whole
+      left.derivedTensor(operator(left.floatClosure, right.floatClosure), result)
     }
 
-    private[CudaTensors] def derivedTensor(newClosure: FloatTerm): InlineTensor = {
+    private[CudaTensors] def unary(operator: FloatTerm => FloatTerm): InlineTensor = {
+      val operand = combined // f(partial sum) needs the sum
+      operand.derivedTensor(operator(operand.floatClosure), operand.distribution)
+    }
+
+    private[CudaTensors] def derivedTensor(newClosure: FloatTerm, newDistribution: Distribution): InlineTensor = {
       new InlineTensor {
         val shape: Array[Int] = thisTensor.shape
         val padding: Float = thisTensor.padding
+        override val distribution: Distribution = newDistribution
         protected[compute] val closure: FloatTerm = newClosure
       }
     }
 
     /** @group delayed */
-    def unary_- : InlineTensor = derivedTensor(-closure)
+    def unary_- : InlineTensor = unary(-_)
 
     /** @group delayed */
     def unary_+ : this.type = this
 
     /** @group delayed */
-    def +(rightHandSide: Tensor): InlineTensor = binary(rightHandSide)(_ + _)
+    def +(rightHandSide: Tensor): InlineTensor = binary(rightHandSide, keepsPartialSums = true)(_ + _)
 
     /** @group delayed */
     def -(rightHandSide: Tensor): InlineTensor = binary(rightHandSide)(_ - _)
@@ -485,6 +658,10 @@ trait CudaTensors extends Cuda {
 
     /** A view whose index `g` reads `this[matrix * (g, 1)]`, or `padding` outside (`Tensors.scala:978-1003`). */
     private[CudaTensors] def transform(newShape: Array[Int], viewToThis: MatrixData): TransformedTensor = {
+      if (distribution == Distribution.PartialSum) {
+        return combined.transform(newShape, viewToThis) // (the padding of a view would be added once per rank)
+      }
+      val viewDistribution = if (distribution == Distribution.RowBlock) viewOfRowBlock(shape, newShape, viewToThis) else Distribution.Whole
       thisTensor match {
         case view: TransformedTensor =>
           val composed = NDimensionalAffineTransform.preConcatenate(viewToThis, view.matrix, newShape.length)
@@ -493,6 +670,7 @@ trait CudaTensors extends Cuda {
             val matrix: MatrixData = composed
             val shape: Array[Int] = newShape
             val padding: Float = view.padding
+            override val distribution: Distribution = viewDistribution
           }
         case _ =>
           new TransformedTensor {
@@ -500,6 +678,7 @@ trait CudaTensors extends Cuda {
             val matrix: MatrixData = viewToThis
             val shape: Array[Int] = newShape
             def padding: Float = checkpoint.padding
+            override val distribution: Distribution = viewDistribution
           }
       }
     }
@@ -534,9 +713,16 @@ trait CudaTensors extends Cuda {
       if (numberOfElements(newShape) != numberOfElements(shape)) {
         throw new IllegalArgumentException
       }
+      if (distribution == Distribution.PartialSum) {
+        return combined.reshape(newShape)
+      }
+      if (distribution == Distribution.RowBlock && (newShape.isEmpty || newShape(0) != shape(0))) {
+        throw new UnsupportedOperationException("reshape of a row block changes the sharded leading axis: gather first")
+      }
       new NonInlineTensor {
         val shape: Array[Int] = newShape
         val padding: Float = thisTensor.padding
+        override def distribution: Distribution = thisTensor.distribution
         private[compute] def doBuffer: Do[PendingBuffer] = thisTensor.doBuffer
       }
     }
@@ -677,11 +863,15 @@ trait CudaTensors extends Cuda {
     @transient
     private[compute] lazy val plan: CompiledKernel = compile(shape)(_.write(closure.tree))
 
-    private[compute] lazy val doBuffer: Do[PendingBuffer] = Do.suspend(enqueue(plan, shape)).shared
+    private[compute] lazy val doBuffer: Do[PendingBuffer] =
+      Do.suspend(enqueue(plan, shape, allReduce = distribution == Distribution.PartialSum)).shared
 
     def nonInline: NonInlineTensor = new NonInlineTensor {
       val shape: Array[Int] = thisInlineTensor.shape
       val padding: Float = thisInlineTensor.padding
+      // (evaluating a partial sum all-reduces it: the materialised tensor is whole)
+      override val distribution: Distribution =
+        if (thisInlineTensor.distribution == Distribution.RowBlock) Distribution.RowBlock else Distribution.Whole
       private[compute] def doBuffer: Do[PendingBuffer] = thisInlineTensor.doBuffer
     }
 
@@ -690,8 +880,8 @@ trait CudaTensors extends Cuda {
       * read-back command disappears. The contraction pipeline is excluded: it stores through tensor maps. */
     override def flatBuffer: Do[FloatBuffer] = {
       val size = numberOfElements(shape)
-      if (size == 0 || size > DirectHostResultFloats || plan.kind == 2) {
-        super.flatBuffer
+      if (size == 0 || size > DirectHostResultFloats || plan.kind == 2 || distribution == Distribution.PartialSum) {
+        super.flatBuffer // (the combine of a partial sum runs on a device buffer)
       } else {
         plan.arguments
           .traverse[ParallelDo, PendingBuffer](tensor => Parallel(tensor.doBuffer))
@@ -774,6 +964,39 @@ object CudaTensors {
         case _                          => throw mismatch
       }
     }
+  }
+
+  /** What a view (`matrix`: rows = dimensions of the row block viewed, columns = dimensions of the view + constant) of a row block is
+    * (`view_of_row_block` in tensor.cpp): still a row block if the view's dimension 0 IS the block's dimension 0 and nothing else touches
+    * it; a partial contribution if it fixes the block's dimension 0 to a constant (`split(0)`: the local rows, to be folded with `+`);
+    * anything else would need rows of other ranks. */
+  private def viewOfRowBlock(blockShape: Array[Int], viewShape: Array[Int], matrix: MatrixData): Distribution = {
+    val columns = viewShape.length + 1
+    val row0 = matrix.slice(0, columns)
+    val row0IsIdentity = columns >= 2 && row0(0) == 1.0 && row0.tail.forall(_ == 0.0)
+    val row0IsConstant = row0.init.forall(_ == 0.0)
+    val othersUseDimension0 = columns >= 2 && (1 until blockShape.length).exists(row => matrix(row * columns) != 0.0)
+    if (row0IsIdentity && !othersUseDimension0 && viewShape.nonEmpty && viewShape(0) == blockShape(0)) Distribution.RowBlock
+    else if (row0IsConstant) Distribution.PartialSum
+    else
+      throw new UnsupportedOperationException(
+        s"this view of a row block [${blockShape.mkString(",")}] mixes the sharded leading axis (it moves, shifts, scales or broadcasts over " +
+          "dimension 0): gather it or use a replicated tensor")
+  }
+
+  /** How a tensor is spread over the ranks (one JVM per GPU) of the communicator — `Tensor::Distribution` of the C++ mirror,
+    * `ct_distribution` of the C ABI. Leading-axis sharding only (SURVEY §8e). */
+  sealed trait Distribution
+  object Distribution {
+
+    /** the whole tensor on every rank (also: no communicator) */
+    case object Whole extends Distribution
+
+    /** this rank's block of rows of a tensor sharded along its leading axis */
+    case object RowBlock extends Distribution
+
+    /** this rank's additive contribution to a sum over the sharded axis (the fold of `rowBlock.split(0)`) */
+    case object PartialSum extends Distribution
   }
 
   /** The monoids `reduce` folds with (`MonoidPrograms`, `Tensors.scala:308-311`; the reference instantiates `Plus` only). */
