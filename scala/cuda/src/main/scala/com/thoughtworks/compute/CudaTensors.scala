@@ -190,6 +190,15 @@ trait CudaTensors extends Cuda {
     } finally MemoryUtil.memFree(blob)
   }
 
+  /** The blob [[compile]] hands to `cc_compile_ex` for `tensor` (definitions attached), in off-heap memory the caller frees — the hook
+    * `CudaTreeWriterSpec` compares with the golden blobs of `tests/golden/tree_blobs/`. */
+  private[compute] def treeBlobOf(tensor: Tensor): java.nio.ByteBuffer = {
+    val writer = new CudaTreeWriter[trees.type](trees)
+    val root = tensor.writeRoot(writer)
+    attachDefinitions(writer)
+    writer.finish(root, tensor.shape)
+  }
+
   /** enqueueClosure's second half (`Tensors.scala:1331-1381`): evaluate the argument tensors in parallel, allocate the output,
     * launch after the arguments' events. One call, one `cc_launch`; the library picks the stream from the buffers' hazards. */
   private def enqueue(kernel: CompiledKernel, shape: Array[Int], allReduce: Boolean = false): Do[PendingBuffer] = {
@@ -378,13 +387,14 @@ trait CudaTensors extends Cuda {
         val padding: Float = head.padding
         // the new dimension is never the leading one here: row blocks stay row blocks
         override val distribution: Distribution = if (anyRowBlock) Distribution.RowBlock else Distribution.Whole
-        private[compute] lazy val plan: CompiledKernel = compile(joinedShape) { writer =>
+        private[compute] override def writeRoot(writer: CudaTreeWriter[trees.type]): Int = {
           val elements = tensors.map(tensor => writer.write(tensor.closure.tree))
           position match {
             case Some(dimension) if dimension != rank => writer.concatenateAt(elements, dimension)
             case _                                    => writer.write(trees.tuple.join(tensors.map(_.closure): _*).tree)
           }
         }
+        private[compute] lazy val plan: CompiledKernel = compile(joinedShape)(writeRoot)
         private[compute] lazy val doBuffer: Do[PendingBuffer] = Do.suspend(enqueue(plan, joinedShape)).shared
       }
     }
@@ -429,6 +439,10 @@ trait CudaTensors extends Cuda {
     private[compute] def getClosure: FloatTerm = closure
 
     private[compute] def doBuffer: Do[PendingBuffer]
+
+    /** Writes the tree this tensor's own kernel is compiled from and returns its root: the closure for most tensors, a `Concatenate` /
+      * `ConcatenateAt` root for joins, a `Reduce` root for folds of inline operands. */
+    private[compute] def writeRoot(writer: CudaTreeWriter[trees.type]): Int = writer.write(closure.tree)
 
     /** `array.parameter(this, float.literal(padding), shape)` (`Tensors.scala:1253-1260`): this tensor as a kernel parameter. */
     @transient
@@ -548,6 +562,8 @@ trait CudaTensors extends Cuda {
       new NonInlineTensor {
         val shape: Array[Int] = ScalarShape
         val padding: Float = thisTensor.padding
+        private[compute] override def writeRoot(writer: CudaTreeWriter[trees.type]): Int =
+          writer.reduce(monoid.kind, writer.write(thisTensor.closure.tree), thisTensor.shape)
         private[compute] lazy val doBuffer: Do[PendingBuffer] = {
           thisTensor match {
             case buffered: NonInlineTensor if monoid == Monoid.Plus =>
@@ -568,10 +584,7 @@ trait CudaTensors extends Cuda {
               }
             case _ =>
               Do.suspend {
-                val plan = compile(ScalarShape) { writer =>
-                  writer.reduce(monoid.kind, writer.write(thisTensor.closure.tree), thisTensor.shape)
-                }
-                enqueue(plan, ScalarShape, allReduce = acrossRanks)
+                enqueue(compile(ScalarShape)(writeRoot), ScalarShape, allReduce = acrossRanks)
               }
           }
         }.shared
@@ -861,7 +874,7 @@ trait CudaTensors extends Cuda {
       * tensors that kernel takes never change; they are resolved once per tensor, after which a slow action costs one
       * `cc_launch` and no tree walk (the reference re-hashes the whole tree on every evaluation, `Tensors.scala:1293`). */
     @transient
-    private[compute] lazy val plan: CompiledKernel = compile(shape)(_.write(closure.tree))
+    private[compute] lazy val plan: CompiledKernel = compile(shape)(writeRoot)
 
     private[compute] lazy val doBuffer: Do[PendingBuffer] =
       Do.suspend(enqueue(plan, shape, allReduce = distribution == Distribution.PartialSum)).shared
