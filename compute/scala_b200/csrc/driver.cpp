@@ -40,6 +40,14 @@ void Driver::load() {
   };
   CC_DRIVER_FUNCTIONS(CC_LOAD)
 #undef CC_LOAD
+#define CC_LOAD_OPTIONAL(name)                                                                       \
+  {                                                                                                  \
+    void* fn = nullptr;                                                                              \
+    CUdriverProcAddressQueryResult st;                                                               \
+    if (get(base_name(#name).c_str(), &fn, CUDA_VERSION, CU_GET_PROC_ADDRESS_DEFAULT, &st) == CUDA_SUCCESS) name = (decltype(name))fn; \
+  }
+  CC_DRIVER_OPTIONAL_FUNCTIONS(CC_LOAD_OPTIONAL)
+#undef CC_LOAD_OPTIONAL
   loaded = true;
 }
 

@@ -56,9 +56,19 @@ namespace cc {
   X(cuMemcpyHtoD)                   \
   X(cuMemcpyDtoH)
 
+// resolved if the driver has them; the features built on them (cc_graph_*) report CC_ERR_UNSUPPORTED otherwise
+#define CC_DRIVER_OPTIONAL_FUNCTIONS(X) \
+  X(cuStreamBeginCapture)               \
+  X(cuStreamEndCapture)                 \
+  X(cuGraphInstantiate)                 \
+  X(cuGraphLaunch)                      \
+  X(cuGraphExecDestroy)                 \
+  X(cuGraphDestroy)
+
 struct Driver {
 #define CC_DECL(name) decltype(&::name) name = nullptr;
   CC_DRIVER_FUNCTIONS(CC_DECL)
+  CC_DRIVER_OPTIONAL_FUNCTIONS(CC_DECL)
 #undef CC_DECL
   bool loaded = false;
   void load();  // throws CC_ERR_NO_DRIVER

@@ -176,6 +176,16 @@ struct Runtime {
   CUdeviceptr col_counters = 0;  // kColCounters self-resetting block counters per compute stream (fused axis-reduction second stage)
   CUevent timer0 = nullptr, timer1 = nullptr;
   Nccl nccl;
+  // cc_graph_begin .. cc_graph_end: commands are captured on compute stream 0 instead of executed
+  struct Graph {
+    CUgraph graph = nullptr;
+    CUgraphExec exec = nullptr;
+    std::vector<Buffer*> reads, writes;  // every buffer the captured commands touch (retained: their addresses are baked into the graph)
+    std::vector<Block> blocks;           // device blocks released while capturing: theirs too, so they stay out of the pool
+    uint64_t commands = 0;
+  };
+  Graph* capture = nullptr;
+  std::unordered_set<Graph*> graphs;
 };
 
 Runtime& rt() {
@@ -237,6 +247,7 @@ Kernel* as_kernel(cc_kernel h) {
 
 int pick_stream() {
   Runtime& r = rt();
+  if (r.capture) return 0;  // a captured sequence lives on one stream
   int s = (int)(r.next_stream % (size_t)r.stream_count);
   r.next_stream++;
   return s;
@@ -266,7 +277,7 @@ constexpr uint64_t kHotHazardTicks = 6000000ull;  // ~2-6 ms of TSC ticks (or 6 
 int pick_stream_for(const BufferList& reads, const BufferList& writes) {
   Runtime& r = rt();
   const int n = r.stream_count;
-  if (n <= 1 || n > 32) return pick_stream();
+  if (n <= 1 || n > 32 || r.capture) return pick_stream();
   int cost[32] = {0};
   uint64_t now = 0;
   auto add = [&](const Mark& m) {
@@ -329,6 +340,21 @@ void need(int s, const Mark& m) {
 }
 
 void op_begin(Op& op, const cc_event* waits, int n_waits) {
+  if (Runtime::Graph* g = rt().capture) {
+    // Only kernels on the capture stream can be part of a graph; copies and collectives run on their own streams / through NCCL.
+    CC_REQUIRE(op.stream == 0, CC_ERR_UNSUPPORTED, "%s cannot be captured into a graph (only kernel launches can): end the capture first", op.label.c_str());
+    CC_REQUIRE(n_waits == 0, CC_ERR_UNSUPPORTED, "captured commands take no wait lists: they run in capture order");
+    // (not retained yet: a buffer that dies during the capture hands its block to the capture's pool, where later captured commands may
+    // reuse it — the steady state of a loop; release() drops it from these lists. cc_graph_end retains what is still alive.)
+    auto note = [](std::vector<Buffer*>& list, Buffer* b) {
+      for (Buffer* x : list)
+        if (x == b) return;
+      list.push_back(b);
+    };
+    for (Buffer* b : op.reads) note(g->reads, b);
+    for (Buffer* b : op.writes) note(g->writes, b);
+    return;  // everything before the capture has completed (cc_graph_begin synchronises); inside it, stream order is the order
+  }
   for (int i = 0; i < n_waits; ++i)
     if (waits[i]) CC_CU(cuStreamWaitEvent(op.cu(), as_event(waits[i])->ev, 0));
   for (Buffer* b : op.reads) need(op.stream, b->last_write);  // read after write
@@ -347,6 +373,12 @@ void op_begin(Op& op, const cc_event* waits, int n_waits) {
 
 void op_end(Op& op, cc_event* out_event) {
   Runtime& r = rt();
+  if (r.capture) {
+    // nothing ran: no marks to leave, and no event to hand out (0 = nothing to wait for; the work happens at cc_graph_launch)
+    for (Buffer* b : op.writes) b->version++;
+    if (out_event) *out_event = 0;
+    return;
+  }
   if (r.nvtx) nvtxRangePop();
   if (op.prof_start) {
     CUevent stop = prof_event();
@@ -452,10 +484,14 @@ void release(Buffer* b) {
   if (b->rc.fetch_sub(1) != 1) return;
   Runtime& r = rt();
   r.buffers.erase(b);
+  if (r.capture)
+    for (std::vector<Buffer*>* list : {&r.capture->reads, &r.capture->writes})
+      list->erase(std::remove(list->begin(), list->end(), b), list->end());
   if (b->owned && !r.panel_cache.empty()) drop_panels_of(b->uid);
   if (b->owned && r.initialized) {
     Block blk{b->ptr, b->bytes, std::move(b->reads)};
     if (b->last_write.stream >= 0) blk.pending.push_back(b->last_write);
+    // (while capturing the pool is the capture's own: see cc_graph_begin)
     r.pool[b->bytes].push_back(std::move(blk));
     r.bytes_pooled += b->bytes;
     r.bytes_in_use -= b->bytes;
@@ -779,8 +815,24 @@ int cc_shutdown(void) {
       r.reduce_scratch = nullptr;
       driver().cuMemFree(r.reduce_counter);
       r.reduce_counter = 0;
-      if (r.col_counters) driver().cuMemFree(r.col_counters);
-      r.col_counters = 0;
+    }
+    // (allocated by the first fused axis-reduction second stage, with or without a whole-tensor fold ever having run; sized by the
+    // stream count of THIS initialisation)
+    if (r.col_counters) driver().cuMemFree(r.col_counters);
+    r.col_counters = 0;
+    if (r.capture) {  // a capture left open: abandon it
+      CUgraph dangling = nullptr;
+      if (driver().cuStreamEndCapture) driver().cuStreamEndCapture(r.streams[0], &dangling);
+      if (dangling && driver().cuGraphDestroy) driver().cuGraphDestroy(dangling);
+      r.graphs.insert(r.capture);
+      r.capture = nullptr;
+    }
+    for (Runtime::Graph* g : r.graphs) {
+      if (g->exec && driver().cuGraphExecDestroy) driver().cuGraphExecDestroy(g->exec);
+      if (g->graph && driver().cuGraphDestroy) driver().cuGraphDestroy(g->graph);
+      g->exec = nullptr, g->graph = nullptr;
+      for (Block& blk : g->blocks) driver().cuMemFree(blk.ptr);
+      g->blocks.clear();
     }
     trim_pool();
     for (auto& kv : r.host_blocks) driver().cuMemFreeHost(kv.first);  // pinned host memory goes with the context too
@@ -2107,6 +2159,129 @@ int cc_broadcast(cc_buffer buf, uint64_t n_floats, int root, const cc_event* wai
     op_begin(op, waits, n_waits);
     if (n.comm) n.check(n.Broadcast((const void*)b->ptr, (void*)b->ptr, n_floats, ncclFloat, root, n.comm, (cudaStream_t)op.cu()), "ncclBroadcast");
     op_end(op, out_event);
+  });
+}
+
+// ---- CUDA graphs over a caller-visible sequence of evaluations ------------------------------------------------------------------------
+
+namespace {
+Runtime::Graph* as_graph(cc_graph h) {
+  Runtime::Graph* g = (Runtime::Graph*)(uintptr_t)h;
+  CC_REQUIRE(g && rt().graphs.count(g), CC_ERR_ILLEGAL_ARGUMENT, "invalid graph handle");
+  return g;
+}
+// While a capture is open the memory pool is the capture's own: blocks freed by captured commands may be reused by later captured
+// commands (same order at every replay) but must never go back to the general pool while the graph lives — a replay writes them.
+std::map<size_t, std::vector<Block>>& parked_pool() {
+  static std::map<size_t, std::vector<Block>> p;
+  return p;
+}
+}  // namespace
+
+int cc_graph_begin(void) {
+  return guarded([&] {
+    Lock lock;
+    require_init();
+    Runtime& r = rt();
+    CC_REQUIRE(!r.capture, CC_ERR_ILLEGAL_ARGUMENT, "a graph capture is already open");
+    CC_REQUIRE(driver().cuStreamBeginCapture && driver().cuStreamEndCapture && driver().cuGraphInstantiate && driver().cuGraphLaunch,
+               CC_ERR_UNSUPPORTED, "this CUDA driver has no stream capture");
+    // everything submitted so far completes first, so the captured commands need no edges to the outside
+    CC_CU(cuCtxSynchronize());
+    for (size_t s = 0; s < r.synced.size(); ++s)
+      for (size_t a = 0; a < r.synced[s].size(); ++a) r.synced[s][a] = r.seq[a];
+    parked_pool().swap(r.pool);  // r.pool is now empty: the capture's own pool
+    CUresult res = driver().cuStreamBeginCapture(r.streams[0], CU_STREAM_CAPTURE_MODE_RELAXED);
+    if (res != CUDA_SUCCESS) {
+      parked_pool().swap(r.pool);
+      check_cu(res, "cuStreamBeginCapture");
+    }
+    r.capture = new Runtime::Graph();
+    r.capture->commands = r.stats.device_kernels;  // (the difference at cc_graph_end = kernels recorded)
+  });
+}
+
+int cc_graph_end(cc_graph* out) {
+  return guarded([&] {
+    Lock lock;
+    require_init();
+    Runtime& r = rt();
+    CC_REQUIRE(out, CC_ERR_ILLEGAL_ARGUMENT, "null output");
+    CC_REQUIRE(r.capture, CC_ERR_ILLEGAL_ARGUMENT, "no graph capture is open");
+    Runtime::Graph* g = r.capture;
+    r.capture = nullptr;
+    g->commands = r.stats.device_kernels - g->commands;
+    r.stats.device_kernels -= g->commands;  // recorded, not run: replays count them
+    for (Buffer* b : g->reads) b->rc.fetch_add(1);
+    for (Buffer* b : g->writes) b->rc.fetch_add(1);
+    // the capture's pool becomes the graph's property; the general pool comes back
+    for (auto& kv : r.pool)
+      for (Block& blk : kv.second) g->blocks.push_back(std::move(blk));
+    r.pool.clear();
+    parked_pool().swap(r.pool);
+    parked_pool().clear();
+    r.graphs.insert(g);
+    CUresult res = driver().cuStreamEndCapture(r.streams[0], &g->graph);
+    if (res == CUDA_SUCCESS) res = driver().cuGraphInstantiate(&g->exec, g->graph, 0);
+    if (res != CUDA_SUCCESS) {
+      cc_graph_release((cc_graph)(uintptr_t)g);
+      check_cu(res, "cuStreamEndCapture / cuGraphInstantiate");
+    }
+    *out = (cc_graph)(uintptr_t)g;
+  });
+}
+
+int cc_graph_launch(cc_graph h, const cc_event* waits, int n_waits, cc_event* out_event) {
+  return guarded([&] {
+    Lock lock;
+    require_init();
+    Runtime& r = rt();
+    Runtime::Graph* g = as_graph(h);
+    CC_REQUIRE(!r.capture, CC_ERR_UNSUPPORTED, "a graph cannot be launched while another one is being captured");
+    CC_REQUIRE(g->exec, CC_ERR_ILLEGAL_ARGUMENT, "the graph was not instantiated");
+    BufferList reads, writes;
+    for (Buffer* b : g->reads) reads.push_back(b);
+    for (Buffer* b : g->writes) writes.push_back(b);
+    Op op{0, reads, writes};
+    op.label = "graph replay";
+    op_begin(op, waits, n_waits);
+    CC_CU(cuGraphLaunch(g->exec, op.cu()));
+    r.stats.launches++;
+    r.stats.device_kernels += g->commands;
+    op_end(op, out_event);
+  });
+}
+
+int cc_graph_info(cc_graph h, uint64_t* out_commands, uint64_t* out_buffers) {
+  return guarded([&] {
+    Lock lock;
+    Runtime::Graph* g = as_graph(h);
+    if (out_commands) *out_commands = g->commands;
+    if (out_buffers) *out_buffers = g->reads.size() + g->writes.size();
+  });
+}
+
+int cc_graph_release(cc_graph h) {
+  return guarded([&] {
+    Lock lock;
+    Runtime& r = rt();
+    Runtime::Graph* g = as_graph(h);
+    r.graphs.erase(g);
+    if (r.initialized) {
+      CC_CU(cuCtxSetCurrent(r.ctx));
+      // replays still in flight read and write the graph's memory: let stream 0 drain before any of it can be handed out again
+      if (g->exec) driver().cuStreamSynchronize(r.streams[0]);
+      if (g->exec && driver().cuGraphExecDestroy) driver().cuGraphExecDestroy(g->exec);
+      if (g->graph && driver().cuGraphDestroy) driver().cuGraphDestroy(g->graph);
+      for (Block& blk : g->blocks) {
+        blk.pending.clear();
+        r.bytes_pooled += blk.bytes;
+        r.pool[blk.bytes].push_back(std::move(blk));
+      }
+    }
+    for (Buffer* b : g->reads) release(b);
+    for (Buffer* b : g->writes) release(b);
+    delete g;
   });
 }
 

@@ -114,6 +114,10 @@ def _L():
         L.cc_shard_agree.argtypes = [u64, C.POINTER(C.c_int)]
         L.cc_shard_launch_allreduce.argtypes = [h, hp, C.c_int, h, hp, C.c_int, hp]
         L.cc_shard_launch_allgather.argtypes = [h, hp, C.c_int, h, hp, C.c_int, hp, C.POINTER(C.c_int)]
+        L.cc_graph_end.argtypes = [hp]
+        L.cc_graph_launch.argtypes = [h, hp, C.c_int, hp]
+        L.cc_graph_info.argtypes = [h, hp, hp]
+        L.cc_graph_release.argtypes = [h]
         L.ct_tree_blob.argtypes = [h, C.c_void_p, u64, hp]
         L.ct_shard.argtypes = [h, hp]
         L.ct_distribution.argtypes = [h, C.POINTER(C.c_int)]
@@ -460,6 +464,52 @@ def kernel_cache_size() -> int:
     n = u64()
     check(_L().cc_kernel_cache_size(C.byref(n)))
     return n.value
+
+
+class Graph:
+    """A caller-visible sequence of evaluations captured once and replayed with one driver call each time (cc_graph_*):
+
+        with cuda.Graph() as g:
+            outs = [expr.doBuffer() for _ in range(50)]     # recorded, not run
+        g.launch()                                          # runs the 50 kernels; outs[i] now hold results, refreshed by every launch
+    """
+
+    def __init__(self):
+        self._h = 0
+
+    def __enter__(self) -> "Graph":
+        check(_L().cc_graph_begin())
+        return self
+
+    def __exit__(self, exc_type, exc, tb) -> None:
+        h = u64()
+        st = _L().cc_graph_end(C.byref(h))
+        if exc_type is None:
+            check(st)
+            self._h = h.value
+        elif st == 0:
+            _L().cc_graph_release(h.value)
+
+    def launch(self) -> None:
+        check(_L().cc_graph_launch(self._h, None, 0, None))
+
+    @property
+    def commands(self) -> int:
+        n, b = u64(), u64()
+        check(_L().cc_graph_info(self._h, C.byref(n), C.byref(b)))
+        return n.value
+
+    def release(self) -> None:
+        if self._h:
+            h, self._h = self._h, 0
+            check(_L().cc_graph_release(h))
+
+    def __del__(self):
+        try:
+            if _lib._lib is not None:
+                self.release()
+        except Exception:
+            pass
 
 
 def kernel_cache_lookup(tree_blob: bytes, any_out_shape: bool = False) -> "Kernel | None":

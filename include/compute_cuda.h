@@ -34,6 +34,7 @@ typedef uint64_t cc_buffer; /* DeviceBuffer[Float]            O:636-715 */
 typedef uint64_t cc_event;  /* Event                          O:565-612 */
 typedef uint64_t cc_kernel; /* Program + Kernel (CompiledKernel, T:1263-1265) */
 typedef uint64_t ct_tensor; /* a `Tensor` of the host-side mirror (T:636-1261) */
+typedef uint64_t cc_graph;  /* a captured sequence of kernel launches (CUDA graph) */
 
 typedef enum cc_status {
   CC_OK = 0,
@@ -222,6 +223,22 @@ int cc_matmul_3xtf32(cc_buffer a, cc_buffer b, cc_buffer c, int64_t m, int64_t n
  * last few B operands are kept while the B buffer has not been written since (tracked per buffer by the runtime; wrapped
  * memory is never cached), so a replicated / weight operand is split once. 1 = on (default), 0 = off and drop the panels. */
 int cc_set_operand_cache(int on);
+
+/* ---- replaying a sequence of evaluations as ONE CUDA graph ------------------------------------------------------- */
+/* The reference's API is one slow action = one kernel launch, and small expressions are bound by the host's launch rate (a fused
+ * tanh(a*b+c) over 1024^2 floats runs in ~2 us; submitting it costs ~3 us). A loop whose iterations evaluate the same expressions
+ * can be captured once and replayed: between cc_graph_begin and cc_graph_end every kernel launch (cc_launch, cc_reduce_sum,
+ * cc_random*, cc_matmul_3xtf32; through the ct_* mirror: doBuffer / doCache of any tensor) is RECORDED on one stream instead of
+ * executed — buffers are allocated and released as usual, but hold no results yet; copies and collectives are refused
+ * (CC_ERR_UNSUPPORTED). cc_graph_launch then runs the whole sequence with one driver call, in capture order; it can be launched any
+ * number of times. Buffers the captured commands touched stay alive (and keep their addresses) as long as the graph; a buffer the
+ * caller still holds from the capture is refreshed by every replay. cc_graph_begin synchronises the device; captures do not nest and
+ * are not concurrent with other threads' commands. */
+int cc_graph_begin(void);
+int cc_graph_end(cc_graph* out);
+int cc_graph_launch(cc_graph g, const cc_event* waits, int n_waits, cc_event* out_event);
+int cc_graph_info(cc_graph g, uint64_t* out_commands, uint64_t* out_buffers);
+int cc_graph_release(cc_graph g);
 
 /* ---- counters / timing -------------------------------------------------------------------------------------- */
 

@@ -150,6 +150,45 @@ def two_launch_plan_and_fold():
     return {"axis": re_, "fold": rf, "axis_launches_per_step": e.compile().info.n_launches}
 
 
+def graph_capture_and_replay():
+    """cc_graph_*: a loop's worth of evaluations recorded once (kernel launches go to the capture stream, nothing else does), then one
+    cuGraphLaunch per replay; memory the captured commands used never returns to the pool while the graph lives"""
+    a, b, c = leaf([64, 64]), leaf([64, 64], 2.0), leaf([64, 64], 3.0)
+    e = cuda.Tensor.tanh(a * b + c)
+    x = leaf([300, 64])
+    col = chain(x.split(0))
+    e.doBuffer().release()
+    col.doBuffer().release()
+    cuda.synchronize()
+    reset()
+    s0 = cuda.stats()
+    with cuda.Graph() as g:
+        for _ in range(20):
+            e.doBuffer().release()  # the same pooled block every time: the capture's own pool
+        kept = col.doBuffer()  # a result the caller keeps: refreshed by every replay
+        refused = False
+        try:
+            kept.to_host(64)  # a copy cannot be part of the graph
+        except cuda.ComputeCudaError as err:
+            refused = "cannot be captured" in str(err)
+    captured = report()
+    s1 = cuda.stats()
+    reset()
+    for _ in range(5):
+        g.launch()
+    replay = report()
+    s2 = cuda.stats()
+    in_use_with_graph = s2["bytes_in_use"]
+    commands = g.commands
+    g.release()
+    kept.release()
+    e.doBuffer().release()  # the runtime is back to normal launches
+    s3 = cuda.stats()
+    return {"captured": captured, "replay": replay, "commands": commands, "refused_copy": refused,
+            "kernels_counted_while_capturing": s1["device_kernels"] - s0["device_kernels"],
+            "kernels_counted_by_replays": s2["device_kernels"] - s1["device_kernels"], "launch_after": s3["launches"] - s2["launches"]}
+
+
 def structural_cache():
     a, b = leaf([16, 16]), leaf([16, 16], 2.0)
     reset()

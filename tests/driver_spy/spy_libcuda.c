@@ -123,12 +123,16 @@ static CUresult s_cuLaunchKernelEx(const CUlaunchConfig* cfg, CUfunction f, void
   return 0;
 }
 
+static CUresult s_cuStreamEndCapture(CUstream s, CUgraph* g) { COUNT(cuStreamEndCapture); (void)s; *g = (CUgraph)(g_handle += 16); return 0; }
+static CUresult s_cuGraphInstantiate(CUgraphExec* e, CUgraph g, unsigned long long flags) { COUNT(cuGraphInstantiate); (void)g, (void)flags; *e = (CUgraphExec)(g_handle += 16); return 0; }
+
 /* ---- everything else: counted, succeeds, does nothing. One trampoline per name so that the count knows who was called. ---- */
 #define GENERIC_LIST(X) \
   X(cuInit) X(cuDevicePrimaryCtxRelease) X(cuCtxSetCurrent) X(cuCtxSynchronize) X(cuMemFree) X(cuMemcpyHtoDAsync) \
   X(cuMemcpyDtoDAsync) X(cuMemsetD32Async) X(cuStreamDestroy) X(cuStreamSynchronize) X(cuStreamWaitEvent) X(cuEventDestroy) X(cuEventRecord) \
   X(cuEventSynchronize) X(cuEventQuery) X(cuModuleUnload) X(cuFuncSetAttribute) X(cuTensorMapEncodeTiled) X(cuIpcGetMemHandle) \
-  X(cuIpcOpenMemHandle) X(cuIpcCloseMemHandle) X(cuMemcpyHtoD) X(cuMemcpyDtoH)
+  X(cuIpcOpenMemHandle) X(cuIpcCloseMemHandle) X(cuMemcpyHtoD) X(cuMemcpyDtoH) X(cuStreamBeginCapture) X(cuGraphLaunch) X(cuGraphExecDestroy) \
+  X(cuGraphDestroy)
 #define GENERIC(name) \
   static CUresult g_##name(void) { \
     static Entry* c_ = NULL; \
@@ -142,11 +146,12 @@ GENERIC_LIST(GENERIC)
   X(cuDeviceGetCount) X(cuDeviceGet) X(cuDevicePrimaryCtxRetain) X(cuDeviceGetAttribute) X(cuDeviceTotalMem) X(cuDeviceGetName) X(cuDriverGetVersion) \
   X(cuMemAlloc) X(cuMemGetInfo) X(cuMemHostAlloc) X(cuMemFreeHost) X(cuMemHostGetDevicePointer) X(cuStreamCreate) X(cuEventCreate) \
   X(cuEventElapsedTime) X(cuMemcpyDtoHAsync) X(cuModuleLoadData) X(cuModuleGetFunction) X(cuLaunchHostFunc) X(cuGetErrorString) X(cuGetErrorName) X(cuLaunchKernel) \
-  X(cuLaunchKernelEx)
+  X(cuLaunchKernelEx) X(cuStreamEndCapture) X(cuGraphInstantiate)
 
 CUresult cuGetProcAddress_v2(const char* name, void** fn, int version, cuuint64_t flags, CUdriverProcAddressQueryResult* status) {
   (void)version, (void)flags;
   if (status) *status = CU_GET_PROC_ADDRESS_SUCCESS;
+  if (!strcmp(name, "cuGraphInstantiateWithFlags")) name = "cuGraphInstantiate";
 #define MATCH_S(n) if (!strcmp(name, #n)) { *fn = (void*)s_##n; return 0; }
 #define MATCH_G(n) if (!strcmp(name, #n)) { *fn = (void*)g_##n; return 0; }
   SPECIFIC_LIST(MATCH_S)

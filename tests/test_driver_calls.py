@@ -116,6 +116,21 @@ def test_fused_second_stage_is_one_launch_and_its_counters_are_given_back(spy_di
     assert r["cuMemAlloc"] == r["cuMemFree"] > 0 and r["live_tensors"] == 0
 
 
+def test_a_captured_sequence_is_one_graph_launch_per_replay(spy_dir):
+    """cc_graph_begin / cc_graph_end / cc_graph_launch: the 20 + 1 evaluations are recorded between cuStreamBeginCapture and
+    cuStreamEndCapture on ONE stream with no event traffic; each replay is a single cuGraphLaunch and launches no kernel by itself"""
+    r = run(spy_dir, "graph_capture_and_replay")
+    cap, rep = r["captured"], r["replay"]
+    assert cap["cuStreamBeginCapture"] == 1 and cap["cuStreamEndCapture"] == 1 and cap["cuGraphInstantiate"] == 1
+    assert cap["pdl_launches"] == 21 and cap["streams_launched_on"] == 1
+    assert cap.get("cuEventRecord", 0) == 0 and cap.get("cuStreamWaitEvent", 0) == 0 and cap.get("cuMemcpyDtoHAsync", 0) == 0
+    assert cap.get("cuMemAlloc", 0) <= 3  # the capture's own pool: ONE block for the 20 elementwise outputs, the column sums and their partials
+    assert r["refused_copy"] is True
+    assert r["commands"] == 21 and r["kernels_counted_while_capturing"] == 0 and r["kernels_counted_by_replays"] == 5 * 21
+    assert rep["cuGraphLaunch"] == 5 and rep["pdl_launches"] == 0 and rep["plain_launches"] == 0
+    assert r["launch_after"] == 1
+
+
 def test_structurally_equal_expressions_share_one_module(spy_dir):
     r = run(spy_dir, "structural_cache")
     assert r["compiles"] == 2 and r["cache_hits"] == 1

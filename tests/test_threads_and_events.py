@@ -142,3 +142,43 @@ def test_c_consumer_runs_config_1(cuda, tmp_path):
     assert m and 0.5 < float(m.group(1)) < 100.0, r.stdout
     assert "compiles=" in r.stdout and "max relative error" in r.stdout
     print(r.stdout)
+
+
+def test_graph_replay_matches_direct_evaluation_and_follows_its_inputs(cuda):
+    """cc_graph_*: evaluations recorded once and replayed as one CUDA graph give the same bits as direct evaluation, and a replay reads
+    the inputs' CURRENT contents (the graph bakes addresses, not values)"""
+    T = cuda.Tensor
+    n = 512
+    rng = np.random.default_rng(4)
+    ha, hb, hc = (rng.standard_normal((n, n)).astype(np.float32) for _ in range(3))
+    ba = cuda.Buffer.from_host(ha)
+    a, b, c = T.fromBuffer(ba, [n, n]), T(hb), T(hc)
+    e = T.tanh(a * b + c)
+    col = a.split(0)[0]
+    for p in a.split(0)[1:]:
+        col = col + p
+    direct, direct_col = e.flatArray(), col.flatArray()
+    with cuda.Graph() as g:
+        for _ in range(10):
+            e.doBuffer().release()
+        out = e.doBuffer()
+        out_col = col.doBuffer()
+        total = (a * b).sum().doBuffer()
+    assert g.commands >= 13
+    g.launch()
+    assert np.array_equal(out.to_host(n * n).view(np.uint32), direct.view(np.uint32))
+    assert np.array_equal(out_col.to_host(n), direct_col)
+    t1 = total.to_host(1)[0]
+    assert abs(t1 - float((ha.astype(np.float64) * hb).sum())) <= 1e-3 * n
+    # new input contents, same buffers: the replay recomputes from them
+    ha2 = (ha * 0.5 + 1.0).astype(np.float32)
+    ba.upload(ha2.ctypes.data, n * n)
+    for _ in range(3):
+        g.launch()
+    a2 = T(ha2)
+    assert np.array_equal(out.to_host(n * n).view(np.uint32), T.tanh(a2 * b + c).flatArray().view(np.uint32))
+    g.release()
+    for x in (out, out_col, total, ba):
+        x.release()
+    # the runtime launches normally again
+    assert np.array_equal(e.flatArray().view(np.uint32), T.tanh(a2 * b + c).flatArray().view(np.uint32))
