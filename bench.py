@@ -628,6 +628,34 @@ def run_cuda(args, rank: int, local_rank: int, world: int):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_sec = float(t.item())
     e2e_value = world * alg_bytes / e2e_sec / 1e9
+    # The ceiling of that number on this box: the same bytes (3 inputs up, 1 result down, both directions at once, every rank at once) with
+    # no kernel at all. It separates what the host / PCIe fabric gives N processes from what the staging design costs.
+    def copies_only():
+        for i in range(chunks):
+            off = i * cn * 4
+            da[i].upload(ha.ptr + off, cn)
+            db[i].upload(hb.ptr + off, cn)
+            dc[i].upload(hc.ptr + off, cn)
+            da[i].to_host_async(ho.ptr + off, cn)
+        cuda.synchronize()
+
+    copies_only()
+    if dist:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        copies_only()
+    copy_sec = (time.perf_counter() - t0) / 3
+    copy_sec_max = copy_sec
+    if dist:
+        import torch
+
+        t = torch.tensor([copy_sec], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        copy_sec_max = float(t.item())
+    e2e_ceiling = {"value": world * alg_bytes / copy_sec_max / 1e9, "unit": "GB/s", "h2d_gbs_per_rank": 3 * n * 4 / copy_sec_max / 1e9,
+                   "d2h_gbs_per_rank": n * 4 / copy_sec_max / 1e9,
+                   "what": "the step's copies alone (3 GiB up + 1 GiB down per rank, all ranks at once, no kernel): the host / PCIe ceiling of e2e on this box"}
     e2e_ok = None
     if rank == 0:
         # the bytes that came back are the chain's result (spot check against the device-resident evaluation)
@@ -652,7 +680,8 @@ def run_cuda(args, rank: int, local_rank: int, world: int):
                          "traffic": None, "peak_source": pk_kind, "kernel": "jit_kernel (fused elementwise template)",
                          "algorithmic_bytes_per_launch": alg_bytes},
             "e2e": {"value": e2e_value, "unit": "GB/s", "h2d_bytes_per_step": 3 * n * 4, "d2h_bytes_per_step": n * 4, "ms_per_step": e2e_sec * 1e3,
-                    "steps": e2e_steps, "result_matches_device_path": e2e_ok},
+                    "steps": e2e_steps, "result_matches_device_path": e2e_ok, "h2d_gbs_per_rank": 3 * n * 4 / e2e_sec / 1e9,
+                    "copy_ceiling": e2e_ceiling},
         }
         # dram__bytes_read.sum + dram__bytes_write.sum of this kernel cannot be measured by a plain run: the figure is the constant that the
         # committed `ncu --set full` capture of the same kernel / same shape reports (profiles/), labelled as such
