@@ -15,6 +15,9 @@
 //     `sum_t A[i,t] * B[t,k]` is lowered to the tcgen05 3xTF32 contraction.
 #include "codegen.h"
 
+#include <mutex>
+#include <unordered_map>
+
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
@@ -23,6 +26,39 @@
 #include <unordered_map>
 
 namespace cc {
+
+// ---- planning knobs ------------------------------------------------------------------------------------------------------------------
+// The CC_TUNE_* / CC_NO_* / CC_FUSE_* / CC_BATCHED_* environment switches shape the plan, but the kernel cache is keyed by the structure
+// of the tree alone. Reading them live would let a switch flipped after the first compile change new plans while the cache keeps serving
+// old ones for the same structure. They are therefore SAMPLED: once on first use, and again whenever the kernel cache is cleared
+// (cc_kernel_cache_clear, cc_init) — the moment at which a changed switch can take effect consistently.
+namespace {
+std::mutex g_knob_mu;
+std::unordered_map<std::string, std::string> g_knobs;
+bool g_knobs_sampled = false;
+const char* const kKnobNames[] = {"CC_BATCHED_CONTRACTION", "CC_FUSE_COL_STAGE", "CC_NO_OP_LOOPS", "CC_NO_STENCIL_TILE", "CC_TUNE_CONTRACTION_MIN_MACS",
+                                  "CC_TUNE_GRID_MULT", "CC_TUNE_MIN_BLOCKS", "CC_TUNE_MIN_REROLL_TERMS", "CC_TUNE_STENCIL_RT", "CC_TUNE_T_GRID_MULT",
+                                  "CC_TUNE_U", "CC_DISABLE_CONTRACTION"};
+void sample_knobs_locked() {
+  g_knobs.clear();
+  for (const char* name : kKnobNames)
+    if (const char* v = getenv(name)) g_knobs[name] = v;
+  g_knobs_sampled = true;
+}
+}  // namespace
+
+void plan_knobs_refresh() {
+  std::lock_guard<std::mutex> lock(g_knob_mu);
+  sample_knobs_locked();
+}
+
+const char* plan_knob(const char* name) {
+  std::lock_guard<std::mutex> lock(g_knob_mu);
+  if (!g_knobs_sampled) sample_knobs_locked();
+  auto it = g_knobs.find(name);
+  return it == g_knobs.end() ? nullptr : it->second.c_str();  // (the map only changes inside plan_knobs_refresh)
+}
+
 
 double java_decimal_round(double v) {
   if (!std::isfinite(v)) return v;
@@ -411,7 +447,7 @@ std::vector<uint32_t> monoid_tree_leaves(const Tree& t, uint32_t root) {
 
 // shorter chains stay unrolled in one elementwise kernel, as the reference runs them (CC_TUNE_MIN_REROLL_TERMS: A/B knob)
 const size_t kMinRerollTerms = [] {
-  const char* e = getenv("CC_TUNE_MIN_REROLL_TERMS");
+  const char* e = plan_knob("CC_TUNE_MIN_REROLL_TERMS");
   return (size_t)(e ? std::max(2, atoi(e)) : 8);
 }();
 
@@ -746,7 +782,7 @@ std::vector<OpLoop> find_op_loops(const std::vector<Op>& ops, const std::vector<
   const int n = (int)ops.size();
   constexpr int kMinReps = 8, kMaxPeriod = 64;
   if (n < kMinReps || n > 200000) return loops;
-  if (const char* ev = getenv("CC_NO_OP_LOOPS"))  // A/B switch for tests: emit iterated maps unrolled, as the reference does
+  if (const char* ev = plan_knob("CC_NO_OP_LOOPS"))  // A/B switch for tests: emit iterated maps unrolled, as the reference does
     if (atoi(ev) != 0) return loops;
   long budget = 4000000;
   int i = 0;
@@ -1097,9 +1133,9 @@ void emit_elementwise(Plan& plan, const Program& p, int n_args, const DeviceProp
   while (U > 1 && NV < (int64_t)256 * U * dev.sm_count * 8) U /= 2;  // small tensors: more CTAs beats more vectors per thread
   int64_t grid_mult = (int64_t)1 << 40;
   int min_blocks = nloads * V * U <= 24 ? 8 : (nloads * V * U <= 40 ? 6 : 0);
-  if (const char* e = getenv("CC_TUNE_U")) U = std::max(1, atoi(e));          // tuning knobs (scripts/gpu_sweep_c2.sh)
-  if (const char* e = getenv("CC_TUNE_GRID_MULT")) grid_mult = std::max(1, atoi(e));
-  if (const char* e = getenv("CC_TUNE_MIN_BLOCKS")) min_blocks = std::max(0, atoi(e));
+  if (const char* e = plan_knob("CC_TUNE_U")) U = std::max(1, atoi(e));          // tuning knobs (scripts/gpu_sweep_c2.sh)
+  if (const char* e = plan_knob("CC_TUNE_GRID_MULT")) grid_mult = std::max(1, atoi(e));
+  if (const char* e = plan_knob("CC_TUNE_MIN_BLOCKS")) min_blocks = std::max(0, atoi(e));
   const int64_t chunk = (int64_t)256 * U;
   const int64_t nchunks = (NV + chunk - 1) / chunk;
   int64_t grid = std::min<int64_t>(nchunks, std::min<int64_t>((int64_t)dev.sm_count * grid_mult, 0x7fffffff));
@@ -1236,7 +1272,7 @@ void emit_tiled_transpose(Plan& plan, const Program& p, int n_args, const Device
     if (x != d && x != L) outer *= p.dims[x];
   const int64_t ntiles = tilesL * tilesD * outer;
   int64_t tgm = (int64_t)1 << 30;
-  if (const char* ev = getenv("CC_TUNE_T_GRID_MULT")) tgm = std::max(1, atoi(ev));
+  if (const char* ev = plan_knob("CC_TUNE_T_GRID_MULT")) tgm = std::max(1, atoi(ev));
   int64_t grid = std::min<int64_t>(ntiles, std::min<int64_t>((int64_t)dev.sm_count * tgm, 0x7fffffff));
   if (grid < 1) grid = 1;
   std::vector<int64_t> ostride(nd, 1);
@@ -1302,7 +1338,7 @@ void emit_tiled_transpose(Plan& plan, const Program& p, int n_args, const Device
 // Other operands of the expression are loaded per output as in the elementwise template.
 bool try_emit_stencil_tile(Plan& plan, const Program& p, int n_args, const DeviceProps& dev) {
   const int nd = (int)p.dims.size();
-  if (getenv("CC_NO_STENCIL_TILE")) return false;
+  if (plan_knob("CC_NO_STENCIL_TILE")) return false;
   if (nd < 2 || p.results.size() != 1) return false;
   const int64_t H = p.dims[nd - 2], W = p.dims[nd - 1];
   if (W % 4 != 0 || W < 128 || H < 8) return false;
@@ -1358,7 +1394,7 @@ bool try_emit_stencil_tile(Plan& plan, const Program& p, int n_args, const Devic
   auto floor4 = [](int64_t v) { return v >= 0 ? v / 4 * 4 : -((-v + 3) / 4 * 4); };
   // 256 threads = 8 row groups x 32 column vectors; each thread owns RT rows of 4 columns -> tile of 8 * RT rows x 128 columns
   int RT = 4;
-  if (const char* ev = getenv("CC_TUNE_STENCIL_RT")) RT = std::max(1, std::min(8, atoi(ev)));  // tuning knob
+  if (const char* ev = plan_knob("CC_TUNE_STENCIL_RT")) RT = std::max(1, std::min(8, atoi(ev)));  // tuning knob
   const int TW = 128;
   const int TH = 8 * RT;
   const int64_t HX0 = floor4(xmin), HX1 = -floor4(-xmax);  // halo columns rounded outwards to the 16-byte grid
@@ -1568,7 +1604,7 @@ void emit_reduce(Plan& plan, const Program& p, int n_args, const DeviceProps& de
     // plan, 16384x4096: 55.4 -> 45.2 us). CC_FUSE_COL_STAGE=0 brings the separate reduce_partials launch back.
     const int64_t gridx = (NV + CW - 1) / CW;
     bool fused = Sy > 1 && gridx <= kColCounters;
-    if (const char* ev = getenv("CC_FUSE_COL_STAGE")) fused = fused && atoi(ev) != 0;
+    if (const char* ev = plan_knob("CC_FUSE_COL_STAGE")) fused = fused && atoi(ev) != 0;
     e("extern \"C\" __global__ void __launch_bounds__(256) reduce_cols(%s%s) {\n", param_list(n_args, true, "dst").c_str(),
       fused ? ", float* __restrict__ out, unsigned* __restrict__ counters" : "");
     if (S == 1) {
@@ -1850,7 +1886,7 @@ bool try_general_contraction(Plan& plan, const Program& p, int n_args) {
   // profiles/r02_knob_ab.json: 4 x 2048 x 1024 x 2048 2.56 -> 0.22 ms, 8 x 512^3 1.4x, small batches unchanged — they stay below the
   // contraction threshold). CC_BATCHED_CONTRACTION=0 keeps such terms on the generic re-rolled reduction.
   int nb = 0;
-  const char* batched_env = getenv("CC_BATCHED_CONTRACTION");
+  const char* batched_env = plan_knob("CC_BATCHED_CONTRACTION");
   if (!batched_env || atoi(batched_env) != 0)
     while (nb < no - 2 && uses(p.loads[la], nb) && uses(p.loads[lb], nb)) ++nb;
   auto split_point = [&](const Load& A, const Load& B) {
@@ -1873,7 +1909,7 @@ bool try_general_contraction(Plan& plan, const Program& p, int n_args) {
   for (int x = s; x < no; ++x) N *= p.dims[x];
   for (int x = no; x < nd; ++x) K *= p.dims[x];
   int64_t min_macs = (int64_t)1 << 25;
-  if (const char* ev = getenv("CC_TUNE_CONTRACTION_MIN_MACS")) min_macs = atoll(ev);
+  if (const char* ev = plan_knob("CC_TUNE_CONTRACTION_MIN_MACS")) min_macs = atoll(ev);
   // the gathered panels cost 8 bytes of HBM traffic per (row, k) each way, so this pays off when N (the reuse of an A row) is large
   if (M * N * K < min_macs || N < 32 || K < 32 || M >= ((int64_t)1 << 31) || N >= ((int64_t)1 << 31) || K >= ((int64_t)1 << 31) - 32) return false;
   const int64_t Kp = (K + 31) / 32 * 32;
@@ -2277,7 +2313,7 @@ Plan make_plan(const Tree& t, const DeviceProps& dev) {
         // generic kernel ~8-13 us; they cross near 2^24..2^25 multiply-adds (256^3: 15.5 vs 13.1 us, 8192x64x64: 15.3 vs
         // 16.7 us, 65536x32x32: 16.9 vs 29.1 us, 512^3: 20.9 vs 33.4 us).
         int64_t min_macs = (int64_t)1 << 25;
-        if (const char* ev = getenv("CC_TUNE_CONTRACTION_MIN_MACS")) min_macs = atoll(ev);
+        if (const char* ev = plan_knob("CC_TUNE_CONTRACTION_MIN_MACS")) min_macs = atoll(ev);
         const bool worth = M * N * K >= min_macs && N >= 32 && K >= 32;
         if (a_arg >= 0 && a_arg != b_arg && worth && M < ((int64_t)1 << 31) && N < ((int64_t)1 << 31) && K < ((int64_t)1 << 31) - 32) {
           const int64_t Kp = (K + 31) / 32 * 32;  // gemm_padded_k

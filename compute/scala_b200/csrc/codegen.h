@@ -59,6 +59,12 @@ struct DeviceProps {
 
 Plan make_plan(const Tree& t, const DeviceProps& dev);
 
+// The planning switches (CC_TUNE_*, CC_NO_*, CC_FUSE_COL_STAGE, CC_BATCHED_CONTRACTION, CC_DISABLE_CONTRACTION) as sampled from the
+// environment on first use and at every plan_knobs_refresh() (called when the kernel cache is cleared or the runtime initialised);
+// nullptr = unset. make_plan never reads the environment itself, so plans and the structural cache cannot disagree.
+const char* plan_knob(const char* name);
+void plan_knobs_refresh();
+
 // K:14-32 — `new DecimalFormat()` (<= 3 fraction digits, HALF_EVEN) as applied to every affine coefficient before it
 // is pasted into the kernel text; returns the value the generated code actually uses.
 double java_decimal_round(double v);

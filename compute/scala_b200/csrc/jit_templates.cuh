@@ -22,15 +22,26 @@ __device__ __forceinline__ void cc_split_tf32(float x, float& hi, float& lo) {
   lo = __uint_as_float(u);
 }
 #else
+// Loads of kernel arguments. A generated kernel never writes what it reads, so the non-coherent path (ld.global.nc) would do — when its
+// lifetime does not overlap the producer's. Under programmatic dependent launch it does: the grid is resident (parked at
+// griddepcontrol.wait) while its predecessor still writes the very buffers it is about to read, and an even older reader's lines of a
+// recycled pool block may sit in this SM's L1. PTX only promises .nc data to be read-only for the grid's whole lifetime, so kernels
+// launched with PDL (CC_COHERENT_LOADS, defined by the runtime) use ordinary coherent loads with the same cache hints: no L1
+// allocation for streamed data, default caching for reused operands. (Measured: same bandwidth, profiles/r02_coherent_loads.json.)
+#ifdef CC_COHERENT_LOADS
+#define CC_LD_NC ""
+#else
+#define CC_LD_NC ".nc"
+#endif
 __device__ __forceinline__ float cc_ldg(const float* p) {
   float v;
-  asm("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  asm("ld.global" CC_LD_NC ".L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
   return v;
 }
 
 // p must be 16-byte aligned
 __device__ __forceinline__ void cc_ldg4(const float* p, float (&v)[4]) {
-  asm("ld.global.nc.L1::no_allocate.L2::256B.v4.f32 {%0, %1, %2, %3}, [%4];"
+  asm("ld.global" CC_LD_NC ".L1::no_allocate.L2::256B.v4.f32 {%0, %1, %2, %3}, [%4];"
       : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3])
       : "l"(p));
 }
@@ -49,9 +60,17 @@ __device__ __forceinline__ void cc_pdl_entry() {
 
 // cached flavours (allocate in L1) for data that is reused across the index space: broadcast operands, the operands of a
 // re-rolled reduction whose address does not depend on every output index (matmul / convolution patterns)
+#if defined(CC_COHERENT_LOADS) && !defined(CC_HOST_EMULATION)
+__device__ __forceinline__ float cc_ldc(const float* p) { return *p; }
+#else
 __device__ __forceinline__ float cc_ldc(const float* p) { return __ldg(p); }
+#endif
 __device__ __forceinline__ void cc_ldc4(const float* p, float (&v)[4]) {
+#if defined(CC_COHERENT_LOADS) && !defined(CC_HOST_EMULATION)
+  const float4 x = *reinterpret_cast<const float4*>(p);
+#else
   const float4 x = __ldg(reinterpret_cast<const float4*>(p));
+#endif
   v[0] = x.x;
   v[1] = x.y;
   v[2] = x.z;

@@ -412,6 +412,25 @@ void op_end(Op& op, cc_event* out_event) {
   }
 }
 
+// A command that failed after part of it was queued (launch i > 0 of a multi-launch plan, an event record): the kernels already on the
+// stream still write its outputs and scratch buffers, so those carry the write mark of a command that "ran" before they can go back to the
+// pool or be read by anyone else; the NVTX range opened by op_begin is closed.
+void op_fail(Op& op) noexcept {
+  Runtime& r = rt();
+  if (r.capture) return;
+  if (r.nvtx) nvtxRangePop();
+  if (op.prof_start) {
+    r.prof_event_pool.push_back(op.prof_start);
+    op.prof_start = nullptr;
+  }
+  const uint64_t q = ++r.seq[(size_t)op.stream];
+  for (Buffer* b : op.writes) {
+    b->reads.clear();
+    b->last_write = Mark{op.stream, q};
+    b->version++;
+  }
+}
+
 // ---- memory pool ----------------------------------------------------------------------------------------------------------
 
 size_t size_class(size_t bytes) {
@@ -591,7 +610,14 @@ std::string with_pdl_entries(const std::string& src) {
 // ("" = none). Returns true if the cubin came from the on-disk cache.
 bool nvrtc_compile(Kernel& k, const std::string& cache_dir) {
   k.pdl = pdl_enabled();
-  k.full_source = std::string("// ") + k.plan.note + "\n" + kJitTemplates + "\n" + (k.pdl ? with_pdl_entries(k.plan.source) : k.plan.source);
+  // kernels launched with PDL read their arguments with coherent loads (jit_templates.cuh: CC_COHERENT_LOADS); CC_NC_LOADS=1 keeps the
+  // non-coherent path for A/B timing
+  static const bool force_nc = [] {
+    const char* e = getenv("CC_NC_LOADS");
+    return e && atoi(e) != 0;
+  }();
+  k.full_source = std::string("// ") + k.plan.note + "\n" + (k.pdl && !force_nc ? "#define CC_COHERENT_LOADS 1\n" : "") + kJitTemplates + "\n" +
+                  (k.pdl ? with_pdl_entries(k.plan.source) : k.plan.source);
   std::string cache_path;
   if (!cache_dir.empty()) {
     cache_path = disk_cache_path(cache_dir, k.full_source);
@@ -630,12 +656,22 @@ bool nvrtc_compile(Kernel& k, const std::string& cache_dir) {
 void ensure_loaded(Kernel& k) {
   if (k.loaded) return;
   if (!k.plan.launches.empty()) {
-    CC_CU(cuModuleLoadData(&k.mod, k.cubin.data()));
-    for (const LaunchSpec& ls : k.plan.launches) {
-      CUfunction f;
-      CC_CU(cuModuleGetFunction(&f, k.mod, ls.entry.c_str()));
-      k.fns.push_back(f);
+    // all or nothing: a failure part-way must not leave a module behind or half a function table for the retry to append to
+    CUmodule mod = nullptr;
+    std::vector<CUfunction> fns;
+    CC_CU(cuModuleLoadData(&mod, k.cubin.data()));
+    try {
+      for (const LaunchSpec& ls : k.plan.launches) {
+        CUfunction f;
+        CC_CU(cuModuleGetFunction(&f, mod, ls.entry.c_str()));
+        fns.push_back(f);
+      }
+    } catch (...) {
+      driver().cuModuleUnload(mod);
+      throw;
     }
+    k.mod = mod;
+    k.fns = std::move(fns);
   }
   k.loaded = true;
 }
@@ -644,7 +680,11 @@ void release(Kernel* k) {
   if (k->rc.fetch_sub(1) != 1) return;
   Runtime& r = rt();
   r.kernels.erase(k);
-  if (k->mod && r.initialized) driver().cuModuleUnload(k->mod);
+  if (k->mod && r.initialized) {
+    // launches from this module may still be queued (an evicted kernel, a handle released right after cc_launch): let them run first
+    driver().cuCtxSynchronize();
+    driver().cuModuleUnload(k->mod);
+  }
   delete k;
 }
 
@@ -1210,7 +1250,7 @@ int cc_compile_ex(const void* blob, uint64_t n_bytes, cc_kernel* out, uint64_t* 
           mine = std::make_shared<Runtime::InFlight>();
           r.compiling.emplace(t.key, mine);
           cache_dir = disk_cache_dir();
-          dp.contraction = gemm_available() && !getenv("CC_DISABLE_CONTRACTION");
+          dp.contraction = gemm_available() && !plan_knob("CC_DISABLE_CONTRACTION");
           if (r.initialized) {
             dp.sm_count = r.info.sm_count;
             dp.max_smem = r.info.max_smem_per_block;
@@ -1291,6 +1331,7 @@ int cc_kernel_cache_clear(void) {
     if (r.initialized) CC_CU(cuCtxSetCurrent(r.ctx));
     for (auto& kv : r.cache) release(kv.second);
     r.cache.clear();
+    plan_knobs_refresh();  // an empty cache is the one moment a changed planning switch can take effect consistently
   });
 }
 
@@ -1556,12 +1597,15 @@ int cc_launch(cc_kernel h, const cc_buffer* args, int n_args, cc_buffer out, con
     if (p.kind == PLAN_CONTRACTION && p.gathered_panels) {
       // general contraction: generated kernels gather the operand panels, the tcgen05 pipeline runs on them, then the epilogue
       std::vector<Buffer*> scratch;
+      Op op{0, in, {ob}};
+      bool begun = false;
       try {
         for (uint64_t n : p.scratch_floats) scratch.push_back(alloc_buffer(n));
-        Op op{pick_stream_for(in, {ob}), in, {ob}};
+        op.stream = pick_stream_for(in, {ob});
         label_kernel_op(op, *k);
         for (Buffer* s : scratch) op.writes.push_back(s);
         op_begin(op, waits, n_waits);
+        begun = true;
         launch_spec(0, scratch, nullptr, op.cu());
         launch_spec(1, scratch, nullptr, op.cu());
         const int64_t Kp = (p.K + 31) / 32 * 32;
@@ -1575,6 +1619,7 @@ int cc_launch(cc_kernel h, const cc_buffer* args, int n_args, cc_buffer out, con
         r.stats.launches++;
         op_end(op, out_event);
       } catch (...) {
+        if (begun) op_fail(op);  // whatever was queued still writes `out` and the scratch: they carry its mark into the pool
         for (Buffer* s : scratch) release(s);
         throw;
       }
@@ -1583,18 +1628,20 @@ int cc_launch(cc_kernel h, const cc_buffer* args, int n_args, cc_buffer out, con
     }
     if (p.kind == PLAN_CONTRACTION) {
       GemmRun g = gemm_prepare(in[1], p.M, p.N, p.K);
-      bool launched = false;
+      bool launched = false, begun = false;
+      Op op{pick_stream_for(in, {ob}), in, {ob}};
       try {
-        Op op{pick_stream_for(in, {ob}), in, {ob}};
         label_kernel_op(op, *k);
         g.declare(op);
         op_begin(op, waits, n_waits);
+        begun = true;
         gemm_on_stream(in[0], in[1], ob, p.M, p.N, p.K, g, op.cu());
         launched = true;
         r.stats.launches++;
         op_end(op, out_event);
       } catch (...) {
-        gemm_finish(g, in[1], p.N, p.K, launched);
+        if (begun) op_fail(op);
+        gemm_finish(g, in[1], p.N, p.K, false);  // (never cache panels of a failed run)
         throw;
       }
       gemm_finish(g, in[1], p.N, p.K, true);
@@ -1609,12 +1656,17 @@ int cc_launch(cc_kernel h, const cc_buffer* args, int n_args, cc_buffer out, con
     for (Buffer* s : scratch) op.writes.push_back(s);
     if (shared_partials) op.writes.push_back(shared_partials);
     launch_stream = op.stream;
+    bool begun = false;
     try {
       op_begin(op, waits, n_waits);
+      begun = true;
       for (size_t li = 0; li < p.launches.size(); ++li) launch_spec(li, scratch, shared_partials, op.cu());
       r.stats.launches++;
       op_end(op, out_event);
     } catch (...) {
+      // earlier launches of the plan may already be queued and still write `out` and the scratch buffers: they go back to the pool (and to
+      // the caller) carrying the mark of this command, never unmarked
+      if (begun) op_fail(op);
       for (Buffer* s : scratch) release(s);  // a failed launch must not strand the plan's scratch buffers
       throw;
     }
@@ -2186,6 +2238,9 @@ int cc_graph_begin(void) {
     CC_REQUIRE(!r.capture, CC_ERR_ILLEGAL_ARGUMENT, "a graph capture is already open");
     CC_REQUIRE(driver().cuStreamBeginCapture && driver().cuStreamEndCapture && driver().cuGraphInstantiate && driver().cuGraphLaunch,
                CC_ERR_UNSUPPORTED, "this CUDA driver has no stream capture");
+    // the runtime's lazily created scratch (fold partials, block counters) is set up with a memset + synchronise: not inside a capture
+    reduce_scratch();
+    col_counters_for(0);
     // everything submitted so far completes first, so the captured commands need no edges to the outside
     CC_CU(cuCtxSynchronize());
     for (size_t s = 0; s < r.synced.size(); ++s)
@@ -2221,9 +2276,15 @@ int cc_graph_end(cc_graph* out) {
     parked_pool().swap(r.pool);
     parked_pool().clear();
     r.graphs.insert(g);
+    const bool dbg = getenv("CC_GRAPH_DEBUG") != nullptr;
+    if (dbg) fprintf(stderr, "[graph] end: %llu kernels, %zu reads, %zu writes, %zu blocks\n", (unsigned long long)g->commands, g->reads.size(), g->writes.size(), g->blocks.size());
     CUresult res = driver().cuStreamEndCapture(r.streams[0], &g->graph);
+    if (dbg) fprintf(stderr, "[graph] cuStreamEndCapture -> %d graph=%p\n", (int)res, (void*)g->graph);
+    if (res == CUDA_SUCCESS && !g->graph) res = CUDA_ERROR_STREAM_CAPTURE_INVALIDATED;  // (a command that failed inside the capture)
     if (res == CUDA_SUCCESS) res = driver().cuGraphInstantiate(&g->exec, g->graph, 0);
+    if (dbg) fprintf(stderr, "[graph] cuGraphInstantiate -> %d exec=%p\n", (int)res, (void*)g->exec);
     if (res != CUDA_SUCCESS) {
+      g->exec = nullptr;
       cc_graph_release((cc_graph)(uintptr_t)g);
       check_cu(res, "cuStreamEndCapture / cuGraphInstantiate");
     }

@@ -607,3 +607,32 @@ def test_every_python_operator_reaches_its_node_kind():
         lines = [l.replace(" ", "") for l in e.compile().source.split("\n") if re.match(r"\s*const float _[12] = ", l)]
         assert lines and text in lines[-1], (name, lines[-1:])
     assert (+a) is a
+
+
+def test_planning_switches_are_sampled_with_the_kernel_cache_not_read_live(monkeypatch):
+    """make_plan read CC_* switches through getenv while the cache is keyed by structure alone, so a switch flipped after the
+    first compile changed new plans but not cached ones. They are sampled when the cache is empty (first use / cc_kernel_cache_clear):
+    flipping one without clearing changes NOTHING, clearing makes it take effect for everything."""
+    from compute.scala_b200 import cuda
+
+    T = cuda.Tensor
+
+    def column_sum(rows, cols):
+        parts = T.random([rows, cols], seed=1).split(0)
+        acc = parts[0]
+        for p in parts[1:]:
+            acc = acc + p
+        return acc
+
+    monkeypatch.delenv("CC_FUSE_COL_STAGE", raising=False)
+    cuda.kernel_cache_clear()
+    try:
+        assert column_sum(300, 64).compile().info.n_launches == 1  # default: second stage fused
+        monkeypatch.setenv("CC_FUSE_COL_STAGE", "0")
+        assert column_sum(300, 64).compile().info.n_launches == 1  # cached structure: unchanged
+        assert column_sum(320, 64).compile().info.n_launches == 1  # a NEW structure plans with the sampled switches too
+        cuda.kernel_cache_clear()
+        assert column_sum(300, 64).compile().info.n_launches == 2 and column_sum(320, 64).compile().info.n_launches == 2
+    finally:
+        monkeypatch.delenv("CC_FUSE_COL_STAGE", raising=False)
+        cuda.kernel_cache_clear()

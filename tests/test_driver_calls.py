@@ -124,7 +124,9 @@ def test_a_captured_sequence_is_one_graph_launch_per_replay(spy_dir):
     assert cap["cuStreamBeginCapture"] == 1 and cap["cuStreamEndCapture"] == 1 and cap["cuGraphInstantiate"] == 1
     assert cap["pdl_launches"] == 21 and cap["streams_launched_on"] == 1
     assert cap.get("cuEventRecord", 0) == 0 and cap.get("cuStreamWaitEvent", 0) == 0 and cap.get("cuMemcpyDtoHAsync", 0) == 0
-    assert cap.get("cuMemAlloc", 0) <= 3  # the capture's own pool: ONE block for the 20 elementwise outputs, the column sums and their partials
+    # the capture's own pool: ONE block for the 20 elementwise outputs, the column sums and their partials; plus the runtime's lazily created
+    # fold scratch + counter, which cc_graph_begin sets up before the capture starts (a memset + synchronise cannot be captured)
+    assert cap.get("cuMemAlloc", 0) <= 5
     assert r["refused_copy"] is True
     assert r["commands"] == 21 and r["kernels_counted_while_capturing"] == 0 and r["kernels_counted_by_replays"] == 5 * 21
     assert rep["cuGraphLaunch"] == 5 and rep["pdl_launches"] == 0 and rep["plain_launches"] == 0
