@@ -60,7 +60,7 @@ namespace cc {
 #define CC_DRIVER_OPTIONAL_FUNCTIONS(X) \
   X(cuStreamBeginCapture)               \
   X(cuStreamEndCapture)                 \
-  X(cuGraphInstantiate)                 \
+  X(cuGraphInstantiateWithFlags)        \
   X(cuGraphLaunch)                      \
   X(cuGraphExecDestroy)                 \
   X(cuGraphDestroy)

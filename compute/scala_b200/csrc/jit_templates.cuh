@@ -22,12 +22,10 @@ __device__ __forceinline__ void cc_split_tf32(float x, float& hi, float& lo) {
   lo = __uint_as_float(u);
 }
 #else
-// Loads of kernel arguments. A generated kernel never writes what it reads, so the non-coherent path (ld.global.nc) would do — when its
-// lifetime does not overlap the producer's. Under programmatic dependent launch it does: the grid is resident (parked at
-// griddepcontrol.wait) while its predecessor still writes the very buffers it is about to read, and an even older reader's lines of a
-// recycled pool block may sit in this SM's L1. PTX only promises .nc data to be read-only for the grid's whole lifetime, so kernels
-// launched with PDL (CC_COHERENT_LOADS, defined by the runtime) use ordinary coherent loads with the same cache hints: no L1
-// allocation for streamed data, default caching for reused operands. (Measured: same bandwidth, profiles/r02_coherent_loads.json.)
+// Loads of kernel arguments: non-coherent (ld.global.nc) — a generated kernel never writes what it reads, and the runtime launches it
+// with programmatic dependent launch (an early-resident grid) only when no command that could still be running writes its inputs
+// (runtime.cpp: pdl_now), so the data is read-only for the grid's whole lifetime as PTX requires of .nc. CC_COHERENT_LOADS (opt-in through
+// the environment variable of the same name) compiles them as ordinary coherent loads with the same cache hints, for A/B comparisons.
 #ifdef CC_COHERENT_LOADS
 #define CC_LD_NC ""
 #else

@@ -12,6 +12,9 @@
 #include <time.h>
 
 #include <algorithm>
+#include <csignal>
+#include <execinfo.h>
+#include <unistd.h>
 #include <array>
 #include <atomic>
 #include <condition_variable>
@@ -610,13 +613,14 @@ std::string with_pdl_entries(const std::string& src) {
 // ("" = none). Returns true if the cubin came from the on-disk cache.
 bool nvrtc_compile(Kernel& k, const std::string& cache_dir) {
   k.pdl = pdl_enabled();
-  // kernels launched with PDL read their arguments with coherent loads (jit_templates.cuh: CC_COHERENT_LOADS); CC_NC_LOADS=1 keeps the
-  // non-coherent path for A/B timing
-  static const bool force_nc = [] {
-    const char* e = getenv("CC_NC_LOADS");
+  // CC_COHERENT_LOADS=1 (opt-in, for A/B): argument loads without .nc (jit_templates.cuh). Not needed for correctness: a kernel is only
+  // launched with the PDL attribute when nothing it reads was written by the command right before it (cc_launch), so a grid whose
+  // lifetime starts early never overlaps a writer of its inputs. (Coherent loads cost the C2 chain 3 %: 7089 -> 6880 GB/s.)
+  static const bool coherent = [] {
+    const char* e = getenv("CC_COHERENT_LOADS");
     return e && atoi(e) != 0;
   }();
-  k.full_source = std::string("// ") + k.plan.note + "\n" + (k.pdl && !force_nc ? "#define CC_COHERENT_LOADS 1\n" : "") + kJitTemplates + "\n" +
+  k.full_source = std::string("// ") + k.plan.note + "\n" + (coherent ? "#define CC_COHERENT_LOADS 1\n" : "") + kJitTemplates + "\n" +
                   (k.pdl ? with_pdl_entries(k.plan.source) : k.plan.source);
   std::string cache_path;
   if (!cache_dir.empty()) {
@@ -764,11 +768,25 @@ const char* cc_last_error(void) { return last_error_cstr(); }
 const char* cc_version(void) { return "compute_cuda 0.1 (sm_100a)"; }
 int cc_is_initialized(void) { return rt().initialized ? 1 : 0; }
 
+namespace {
+// CC_SEGV_BACKTRACE=1: native frames on stderr when the process dies of SIGSEGV (the box has no debugger)
+void segv_backtrace(int sig) {
+  void* frames[64];
+  const int n = backtrace(frames, 64);
+  const char msg[] = "\n[compute_cuda] SIGSEGV, native frames:\n";
+  if (write(2, msg, sizeof msg - 1) < 0) {}
+  backtrace_symbols_fd(frames, n, 2);
+  signal(sig, SIG_DFL);
+  raise(sig);
+}
+}  // namespace
+
 int cc_init(int device_ordinal) {
   return guarded([&] {
     Lock lock;
     Runtime& r = rt();
     if (r.initialized) return;
+    if (getenv("CC_SEGV_BACKTRACE")) signal(SIGSEGV, segv_backtrace);
     driver().load();
     CC_CU(cuInit(0));
     int count = 0;
@@ -1576,7 +1594,18 @@ int cc_launch(cc_kernel h, const cc_buffer* args, int n_args, cc_buffer out, con
           ptrs.push_back(scratch[ARG_SCRATCH0 - a]->ptr);
       }
       for (CUdeviceptr& q : ptrs) argv.push_back(&q);
-      if (k->pdl) {
+      // Programmatic dependent launch lets this grid become resident while the previous command on the stream still runs. Its loads are
+      // non-coherent (ld.global.nc), which PTX only allows for data that is read-only during the grid's WHOLE lifetime: so the attribute
+      // is set only when nothing this launch reads was written by that previous command (later launches of a multi-launch plan read the
+      // scratch the launch before them wrote: plain stream order). Loops over long-lived inputs — the launch-bound case PDL is for —
+      // keep it; a producer -> consumer chain pays the ~1 us launch gap and stays within the letter of the memory model.
+      bool pdl_now = k->pdl && li == 0;
+      if (pdl_now) {
+        const uint64_t prev = r.seq[(size_t)launch_stream];
+        for (const Buffer* b : in)
+          if (b->last_write.stream == launch_stream && b->last_write.seq == prev && prev != 0) pdl_now = false;
+      }
+      if (pdl_now) {
         CUlaunchAttribute attr{};
         attr.id = CU_LAUNCH_ATTRIBUTE_PROGRAMMATIC_STREAM_SERIALIZATION;
         attr.value.programmaticStreamSerializationAllowed = 1;
@@ -1602,6 +1631,7 @@ int cc_launch(cc_kernel h, const cc_buffer* args, int n_args, cc_buffer out, con
       try {
         for (uint64_t n : p.scratch_floats) scratch.push_back(alloc_buffer(n));
         op.stream = pick_stream_for(in, {ob});
+        launch_stream = op.stream;
         label_kernel_op(op, *k);
         for (Buffer* s : scratch) op.writes.push_back(s);
         op_begin(op, waits, n_waits);
@@ -2236,7 +2266,7 @@ int cc_graph_begin(void) {
     require_init();
     Runtime& r = rt();
     CC_REQUIRE(!r.capture, CC_ERR_ILLEGAL_ARGUMENT, "a graph capture is already open");
-    CC_REQUIRE(driver().cuStreamBeginCapture && driver().cuStreamEndCapture && driver().cuGraphInstantiate && driver().cuGraphLaunch,
+    CC_REQUIRE(driver().cuStreamBeginCapture && driver().cuStreamEndCapture && driver().cuGraphInstantiateWithFlags && driver().cuGraphLaunch,
                CC_ERR_UNSUPPORTED, "this CUDA driver has no stream capture");
     // the runtime's lazily created scratch (fold partials, block counters) is set up with a memset + synchronise: not inside a capture
     reduce_scratch();
@@ -2281,7 +2311,7 @@ int cc_graph_end(cc_graph* out) {
     CUresult res = driver().cuStreamEndCapture(r.streams[0], &g->graph);
     if (dbg) fprintf(stderr, "[graph] cuStreamEndCapture -> %d graph=%p\n", (int)res, (void*)g->graph);
     if (res == CUDA_SUCCESS && !g->graph) res = CUDA_ERROR_STREAM_CAPTURE_INVALIDATED;  // (a command that failed inside the capture)
-    if (res == CUDA_SUCCESS) res = driver().cuGraphInstantiate(&g->exec, g->graph, 0);
+    if (res == CUDA_SUCCESS) res = driver().cuGraphInstantiateWithFlags(&g->exec, g->graph, 0);
     if (dbg) fprintf(stderr, "[graph] cuGraphInstantiate -> %d exec=%p\n", (int)res, (void*)g->exec);
     if (res != CUDA_SUCCESS) {
       g->exec = nullptr;

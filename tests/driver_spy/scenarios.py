@@ -189,6 +189,24 @@ def graph_capture_and_replay():
             "kernels_counted_by_replays": s2["device_kernels"] - s1["device_kernels"], "launch_after": s3["launches"] - s2["launches"]}
 
 
+def pdl_only_when_inputs_are_settled():
+    """an early-resident (PDL) grid may not read, through non-coherent loads, what the command right before it is still writing: a kernel that
+    consumes the previous kernel's output is launched in plain stream order; loops over long-lived inputs keep the attribute"""
+    a, b = leaf([64, 64]), leaf([64, 64], 2.0)
+    e = a * b + a
+    e.doBuffer().release()
+    reset()
+    for _ in range(20):
+        e.doBuffer().release()  # same old inputs every step
+    settled = report()
+    x = a
+    reset()
+    for _ in range(20):
+        x = (x * b).doCache()  # each step reads the previous step's output
+    chained = report()
+    return {"settled": settled, "chained": chained}
+
+
 def structural_cache():
     a, b = leaf([16, 16]), leaf([16, 16], 2.0)
     reset()

@@ -100,7 +100,9 @@ def test_read_backs_land_in_the_callers_memory(spy_dir, binding):
 def test_multi_launch_plans_and_folds_stay_on_their_stream(spy_dir):
     r = run(spy_dir, "two_launch_plan_and_fold", CC_FUSE_COL_STAGE="0")  # the separate second stage (the default fuses it, next test)
     assert r["axis_launches_per_step"] == 2
-    assert r["axis"]["pdl_launches"] == 100 and r["axis"]["cuEventRecord"] == 0 and r["axis"]["cuStreamWaitEvent"] == 0 and r["axis"]["cuMemAlloc"] == 0
+    # the second launch of each step reads the partials the first one just wrote: plain stream order, not an early-resident (PDL) grid
+    assert r["axis"]["pdl_launches"] == 50 and r["axis"]["plain_launches"] == 50
+    assert r["axis"]["cuEventRecord"] == 0 and r["axis"]["cuStreamWaitEvent"] == 0 and r["axis"]["cuMemAlloc"] == 0
     assert r["fold"]["pdl_launches"] == 50 and r["fold"]["cuEventRecord"] == 0 and r["fold"]["cuStreamWaitEvent"] == 0
     assert r["fold"]["cuMemsetD32Async"] == 0  # the fold's block counter resets itself
 
@@ -114,6 +116,13 @@ def test_fused_second_stage_is_one_launch_and_its_counters_are_given_back(spy_di
     assert r["axis"]["cuEventRecord"] == 0 and r["axis"]["cuStreamWaitEvent"] == 0
     r = run(spy_dir, "balance_on_shutdown")
     assert r["cuMemAlloc"] == r["cuMemFree"] > 0 and r["live_tensors"] == 0
+
+
+def test_pdl_is_not_used_for_a_kernel_that_reads_what_the_previous_command_wrote(spy_dir):
+    """ld.global.nc requires read-only data for the grid's whole lifetime, and a PDL grid's lifetime starts while its predecessor runs"""
+    r = run(spy_dir, "pdl_only_when_inputs_are_settled")
+    assert r["settled"]["pdl_launches"] == 20 and r["settled"]["plain_launches"] == 0
+    assert r["chained"]["pdl_launches"] <= 1 and r["chained"]["plain_launches"] >= 19
 
 
 def test_a_captured_sequence_is_one_graph_launch_per_replay(spy_dir):

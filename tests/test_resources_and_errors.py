@@ -126,3 +126,31 @@ def test_shutdown_and_reinit_in_a_fresh_process():
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=root, timeout=300)
     assert r.returncode == 0 and r.stdout.strip().endswith("ok"), (r.stdout[-2000:], r.stderr[-2000:])
+
+
+def test_ping_pong_chains_over_recycled_pool_blocks_stay_exact(cuda):
+    """tiny producer -> consumer chains whose buffers ping-pong between two or three recycled pool blocks, with programmatic
+    dependent launch on (the default). Every step adds exactly 1, so a kernel that ever read a stale or half-written input (a non-coherent
+    load of data its early-resident grid overlapped with) would leave the final value short. Streaming loads, L1-allocating loads of a
+    broadcast operand, and a two-stream variant."""
+    T = cuda.Tensor
+    steps = 3000
+    for n in (64, 4096, 65536):
+        x = T.fill(0.0, [n]).doCache()
+        one = T.fill(1.0, [n])
+        for _ in range(steps):
+            x = (x + one).doCache()
+        got = x.flatArray()
+        assert (got == float(steps)).all(), (n, got[:8])
+    rows, cols = 64, 256
+    x = T.fill(0.0, [rows, cols]).doCache()
+    row = T(np.ones(rows, np.float32))  # broadcast along the columns: read through the L1-allocating path
+    for _ in range(steps):
+        x = (x + row.broadcast([rows, cols])).doCache()
+    assert (x.flatArray() == float(steps)).all()
+    # reductions in the chain: the scalar result feeds the next step
+    s = T.fill(1.0, [1024]).doCache()
+    acc = T.scalar(0.0).doCache()
+    for _ in range(300):
+        acc = (acc + s.sum()).doCache()
+    assert acc.flatArray()[0] == 300 * 1024.0
