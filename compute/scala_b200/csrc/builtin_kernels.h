@@ -59,6 +59,10 @@ int64_t gemm_padded_k(int64_t k);
 // (tcgen05 cta_group::2), 256 / 128 / 64 = 128 x that many columns on single CTAs
 int gemm_pick_config(int64_t m, int64_t n, int sm_count, bool allow_pair);
 int gemm_pick_bn(int64_t m, int64_t n, int sm_count);
+// The final choice for launch_gemm_3xtf32(a, b, ...): as above, or 1024 = 256 x 256 tiles on CTA pairs with A read as the original fp32
+// matrix and split inside the kernel through tensor memory (no A panels: ws.a_hi / ws.a_lo may be null). CC_GEMM_FORCE_CONFIG and
+// CC_GEMM_TMEM_A=0 are honoured here.
+int gemm_config_for(const float* a, int64_t m, int64_t n, int64_t k, int sm_count, bool gather_epilogue);
 typedef CUresult (*TensorMapEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                       const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                       CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);

@@ -638,6 +638,266 @@ __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
   lo = __uint_as_float(t);
 }
 
+// ---- CTA pairs with A through tensor memory ("config 1024") ------------------------------------------------------------------------
+//
+// The pair kernel above reads A as hi / lo panels a prologue kernel wrote (A read once, written twice, read again: +0.135 ms and 768 MiB of
+// traffic at 8192^3, and a launch that dominates small products). tcgen05.mma can take A from TENSOR memory instead:
+//   * A is read as the ORIGINAL fp32 matrix (TMA, SWIZZLE_128B, out-of-bounds rows / k zero filled): no split_a prologue, no A_hi / A_lo
+//     panels in HBM, half the L2 -> shared-memory traffic for A. Eight converter warps per CTA (two groups taking alternate k blocks)
+//     pull each landed 128 x 32 tile out of shared memory, split it in registers (hi = top 19 bits, lo = tf32(x - hi)) and tcgen05.st the
+//     two halves into the stage's TMEM columns: [0, 256) = the accumulator, [256, 512) = four A stages of 64 columns.
+//   * B still comes as the K-major hi / lo panels of the (cached) prologue: it is the replicated / weight operand.
+//   * barriers per stage: a_full (own CTA: raw A landed) -> converters -> a_ready (leader: both CTAs' A is in TMEM);
+//     b_full (leader: both halves of B landed); the leader's MMA warp waits for both, issues 12 MMAs, and one multicast commit (empty)
+//     frees the B tiles, the raw A tile and the TMEM A stage in both CTAs.
+// Measured (scripts/gpu_gemm_v2.py, profiles/r02_gemm_tmem_a.json): 8192^3 304 vs 300 TFLOP/s (both at the power-limited tensor peak:
+// ncu has the tensor pipe 87 % active at 1.72 GHz), 4096^3 220 vs 210, 2048^3 175 vs 153, 1024 x 8192 x 8192 210 vs 193; same bits as the
+// panel kernels (same split, same accumulation order). One accumulator instead of two: the epilogue of a tile no longer overlaps the next
+// tile's MMAs (~2 % of a K = 8192 tile), which the saved prologue more than pays for.
+constexpr int TA_STAGES = 4;
+constexpr int TA_A_RAW_BYTES = BM * BK * 4;  // 16 KiB
+constexpr int TA_THREADS = 512;  // warp 0 TMA, 1 MMA, 2 TMEM allocator, 3 idle, 4-7 epilogue, 8-15 converters (two groups, alternating stages)
+constexpr uint32_t TA_A_COL0 = 256;  // TMEM columns [0, 256) = accumulator(s), [256, 512) = four A stages (hi 32 | lo 32 each)
+template <int BN>
+struct TaCfg {
+  static_assert(BN == 128 || BN == 256, "BN must be 128 or 256");
+  static constexpr int ACCS = 256 / BN;  // two 128-column accumulators (epilogue overlaps the next tile) or one of 256
+  static constexpr int B_HALF_BYTES = (BN / 2) * BK * 4;                      // 8 / 16 KiB
+  static constexpr int STAGE_BYTES = TA_A_RAW_BYTES + 2 * B_HALF_BYTES;      // 32 / 48 KiB per CTA
+  static constexpr int SMEM_BYTES = TA_STAGES * STAGE_BYTES + 1024 + 256;
+  static constexpr uint32_t kInstrDesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+};
+
+__device__ __forceinline__ void umma_tf32_pair_tmem_a(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      :
+      : "r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      :
+      : "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+        "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]),
+        "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+template <int BN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TA_THREADS, 1)
+gemm_3xtf32_tmema_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
+                         float* __restrict__ C, int M, int N, int Kp, int tiles_pm, int tiles_n) {
+  constexpr int ACCS = TaCfg<BN>::ACCS;
+  constexpr int B_HALF_BYTES = TaCfg<BN>::B_HALF_BYTES;
+  constexpr int STAGE_BYTES = TaCfg<BN>::STAGE_BYTES;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bars = smem_base + TA_STAGES * STAGE_BYTES;
+  // barrier layout (8 bytes each): a_full[S], b_full[S], a_ready[S], empty[S], tmem_full[2], tmem_empty[2], then the TMEM base address
+  auto a_full_bar = [&](int s) { return bars + 8u * s; };
+  auto b_full_bar = [&](int s) { return bars + 8u * (TA_STAGES + s); };
+  auto a_ready_bar = [&](int s) { return bars + 8u * (2 * TA_STAGES + s); };
+  auto empty_bar = [&](int s) { return bars + 8u * (3 * TA_STAGES + s); };
+  auto tmem_full_bar = [&](int a) { return bars + 8u * (4 * TA_STAGES + a); };
+  auto tmem_empty_bar = [&](int a) { return bars + 8u * (4 * TA_STAGES + 2 + a); };
+  const uint32_t tmem_slot = bars + 8u * (4 * TA_STAGES + 4);
+  uint8_t* smem_generic = smem_raw + (smem_base - smem_u32(smem_raw));
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_generic + TA_STAGES * STAGE_BYTES + 8 * (4 * TA_STAGES + 4));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();  // 0 = leader
+  const int pair = blockIdx.x >> 1;
+  const int num_pairs = gridDim.x >> 1;
+  const int num_tiles = tiles_pm * tiles_n;
+  const int num_kb = Kp / BK;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tensormap(&tm_a);
+    prefetch_tensormap(&tm_b_hi);
+    prefetch_tensormap(&tm_b_lo);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < TA_STAGES; ++s) {
+      mbar_init(a_full_bar(s), 1);   // own producer's arrive.expect_tx; bytes from this CTA's A load
+      mbar_init(b_full_bar(s), 1);   // leader only: its arrive.expect_tx; bytes from both CTAs' B loads
+      mbar_init(a_ready_bar(s), 8);  // leader only: 4 converter warps of each CTA
+      mbar_init(empty_bar(s), 1);    // one multicast commit
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tmem_full_bar(a), 1);
+      mbar_init(tmem_empty_bar(a), 256);  // leader only: the 128 epilogue threads of each CTA
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ===== TMA producer (both CTAs): own 128 rows of the original A, own half of the B^T hi / lo panels =====
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+        int m_blk, n_blk;
+        tile_coords(tile, tiles_pm, tiles_n, m_blk, n_blk);
+        const int row_a = m_blk * 256 + (int)rank * 128;
+        const int row_b = n_blk * BN + (int)rank * (BN / 2);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1);
+          const uint32_t st = smem_base + stage * STAGE_BYTES;
+          mbar_arrive_expect_tx(a_full_bar(stage), TA_A_RAW_BYTES);
+          tma_load_2d(st, &tm_a, a_full_bar(stage), kb * BK, row_a);
+          const uint32_t leader_b_full = map_to_cta(b_full_bar(stage), 0);
+          if (rank == 0) mbar_arrive_expect_tx(b_full_bar(stage), 2 * 2 * B_HALF_BYTES);
+          tma_load_2d_pair(st + TA_A_RAW_BYTES, &tm_b_hi, leader_b_full, kb * BK, row_b);
+          tma_load_2d_pair(st + TA_A_RAW_BYTES + B_HALF_BYTES, &tm_b_lo, leader_b_full, kb * BK, row_b);
+          if (++stage == TA_STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1 && rank == 0) {
+    // ===== MMA issuer (leader CTA only): A from tensor memory, B from shared memory =====
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
+      const int acc = ACCS == 2 ? (it & 1) : 0;
+      const uint32_t acc_phase = ACCS == 2 ? ((it >> 1) & 1) : (it & 1);
+      mbar_wait(tmem_empty_bar(acc), acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(b_full_bar(stage), phase);   // both halves of B have landed
+        mbar_wait(a_ready_bar(stage), phase);  // both CTAs' converters have written this stage's A into tensor memory
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t st = smem_base + stage * STAGE_BYTES;
+          const uint64_t b_hi = umma_desc_sw128(st + TA_A_RAW_BYTES);
+          const uint64_t b_lo = umma_desc_sw128(st + TA_A_RAW_BYTES + B_HALF_BYTES);
+          const uint32_t a_hi = tmem_base + TA_A_COL0 + (uint32_t)(stage * 64);
+          const uint32_t a_lo = a_hi + 32;
+#pragma unroll
+          for (int k = 0; k < BK / 8; ++k) {
+            const uint64_t adv = (uint64_t)((k * 8 * 4) >> 4);
+            umma_tf32_pair_tmem_a(tmem_d, a_lo + (uint32_t)(k * 8), b_hi + adv, TaCfg<BN>::kInstrDesc, (kb | k) != 0);
+            umma_tf32_pair_tmem_a(tmem_d, a_hi + (uint32_t)(k * 8), b_lo + adv, TaCfg<BN>::kInstrDesc, 1);
+            umma_tf32_pair_tmem_a(tmem_d, a_hi + (uint32_t)(k * 8), b_hi + adv, TaCfg<BN>::kInstrDesc, 1);
+          }
+          umma_commit_pair(empty_bar(stage));  // frees B, the raw A tile and the TMEM A stage in BOTH CTAs
+          if (kb == num_kb - 1) umma_commit_pair(tmem_full_bar(acc));
+        }
+        __syncwarp();
+        if (++stage == TA_STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp >= 8) {
+    // ===== converters (both CTAs): raw fp32 A tile in shared memory -> hi / lo in registers -> tensor memory. Two groups of four
+    // warps take alternate k blocks, so two stages are being converted at any time (one group alone is as slow as the MMAs) =====
+    const int group = (warp - 8) >> 2;
+    const int cw = (warp - 8) & 3;  // TMEM lanes [32 * cw, 32 * cw + 32) = rows of the A tile
+    const int row = cw * 32 + lane;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(cw * 32) << 16) + TA_A_COL0;
+    const long long total_kb = 0;
+    (void)total_kb;
+    long long j = 0;  // k blocks this CTA has seen, over all its tiles
+    for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+      for (int kb = 0; kb < num_kb; ++kb, ++j) {
+        if ((int)(j & 1) != group) continue;
+        const int stage = (int)(j % TA_STAGES);
+        const uint32_t phase = (uint32_t)((j / TA_STAGES) & 1);
+        mbar_wait(a_full_bar(stage), phase);  // (the producer only refilled this stage after `empty`: its TMEM columns are free too)
+        const uint32_t src = smem_base + stage * STAGE_BYTES + (uint32_t)(row * 128);
+        uint32_t hi[32], lo[32];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          uint32_t x0, x1, x2, x3;
+          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(x0), "=r"(x1), "=r"(x2), "=r"(x3) : "r"(src + (uint32_t)((c ^ (row & 7)) << 4)));
+          const uint32_t x[4] = {x0, x1, x2, x3};
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            float h, l;
+            split_tf32(__uint_as_float(x[q]), h, l);
+            hi[4 * c + q] = __float_as_uint(h);
+            lo[4 * c + q] = __float_as_uint(l);
+          }
+        }
+        tmem_st_32x32(lane_addr + (uint32_t)(stage * 64), hi);
+        tmem_st_32x32(lane_addr + (uint32_t)(stage * 64 + 32), lo);
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(map_to_cta(a_ready_bar(stage), 0));
+      }
+    }
+  } else if (warp >= 4 && warp < 8) {
+    // ===== epilogue (both CTAs): own TMEM (128 rows of the pair's 256) -> registers -> global =====
+    const int ew = warp - 4;
+    int it = 0;
+    for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
+      int m_blk, n_blk;
+      tile_coords(tile, tiles_pm, tiles_n, m_blk, n_blk);
+      const int acc = ACCS == 2 ? (it & 1) : 0;
+      const uint32_t acc_phase = ACCS == 2 ? ((it >> 1) & 1) : (it & 1);
+      mbar_wait(tmem_full_bar(acc), acc_phase);
+      tc_fence_after();
+      const int row = m_blk * 256 + (int)rank * 128 + ew * 32 + lane;
+      const int col0 = n_blk * BN;
+      const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * BN);
+      float* out = C + (size_t)row * (size_t)N + (size_t)col0;
+      const bool row_ok = row < M;
+      const bool vec_ok = (N & 3) == 0;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        if (col0 + c * 32 >= N) break;
+        uint32_t r[32];
+        tmem_ld_32x32(taddr + (uint32_t)(c * 32), r);
+        tmem_ld_wait();
+        if (!row_ok) {
+        } else if (vec_ok && col0 + c * 32 + 32 <= N) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            float4 v = make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]), __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
+            __stcs(reinterpret_cast<float4*>(out + c * 32) + q, v);
+          }
+        } else {
+#pragma unroll
+          for (int q = 0; q < 32; ++q)
+            if (col0 + c * 32 + q < N) __stcs(out + c * 32 + q, __uint_as_float(r[q]));
+        }
+        __syncwarp();
+      }
+      tc_fence_before();
+      mbar_arrive_cluster(map_to_cta(tmem_empty_bar(acc), 0));
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
 // A [M,K] row-major -> A_hi / A_lo [M,Kp] (Kp % 32 == 0, columns >= K zero). One thread per 4 output floats.
 __global__ void __launch_bounds__(256) split_a_kernel(const float* __restrict__ a, float* __restrict__ hi, float* __restrict__ lo, int M, int K, int Kp) {
   const size_t vec_per_row = (size_t)Kp / 4;
@@ -747,6 +1007,32 @@ int gemm_pick_bn(int64_t m, int64_t n, int sm_count) {
 }
 
 namespace {
+bool tmema_default();
+}
+
+int gemm_config_for(const float* a, int64_t m, int64_t n, int64_t k, int sm_count, bool gather_epilogue) {
+  // CC_GEMM_FORCE_CONFIG = 1024 | 512 | 256 | 128 | 64 pins the tile configuration (tests run every variant on the same shapes)
+  int config = gemm_pick_config(m, n, sm_count, true);
+  // 1024 = A through tensor memory: needs the original A (not pre-gathered panels), a TMA-able row pitch and more than one CTA of rows
+  const bool tmema_ok = !gather_epilogue && a && (k & 3) == 0 && ((uintptr_t)a & 15) == 0 && m > BM;
+  if (config == 512 && tmema_ok && tmema_default()) config = 1024;
+  if (const char* force = getenv("CC_GEMM_FORCE_CONFIG")) {
+    const int f = atoi(force);
+    if (f == 256 || f == 128 || f == 64 || (f == 512 && m > BM) || (f == 1024 && tmema_ok)) config = f;
+  }
+  return config;
+}
+
+namespace {
+// the tensor-memory-A kernel replaces the plain pair kernel wherever that one is picked, unless CC_GEMM_TMEM_A=0 (A/B timing)
+bool tmema_default() {
+  static const bool on = [] {
+    const char* e = getenv("CC_GEMM_TMEM_A");
+    return e ? atoi(e) != 0 : true;
+  }();
+  return on;
+}
+
 template <int BN, bool kGather>
 void launch_main(const GemmWorkspace& ws, float* c, int64_t m, int64_t n, int64_t kp, int sm_count, TensorMapEncodeFn encode, cudaStream_t stream,
                  const GatherMaps& gather) {
@@ -791,6 +1077,30 @@ void launch_pair(const GemmWorkspace& ws, float* c, int64_t m, int64_t n, int64_
   check_launch(kGather ? "gemm_3xtf32 (CTA pairs, all-gather epilogue)" : "gemm_3xtf32 (CTA pairs)");
 }
 
+// config 1024: CTA pairs, 256 x 256 tiles (one accumulator), A read as the original fp32 matrix and split inside the kernel (through tensor
+// memory). (The kernel also instantiates for 256 x 128 tiles with two accumulators; measured at 8192^3: 211 TFLOP/s, tensor pipe 56 % —
+// 128-column MMAs are too short to keep the pipe busy — against 304 for 256 x 256, so only the wide tile is dispatched.)
+template <int BN>
+void launch_tmema(const float* a, const GemmWorkspace& ws, float* c, int64_t m, int64_t n, int64_t k, int64_t kp, int sm_count, TensorMapEncodeFn encode,
+                  cudaStream_t stream) {
+  constexpr int SMEM = TaCfg<BN>::SMEM_BYTES;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_3xtf32_tmema_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    if (e != cudaSuccess) fail(CC_ERR_CUDA, strprintf("cudaFuncSetAttribute(tmem-A, smem=%d): %s", SMEM, cudaGetErrorString(e)));
+    attr_set = true;
+  }
+  CUtensorMap ma, mb_hi, mb_lo;
+  make_map(encode, &ma, a, m, k, BM);  // the ORIGINAL A [M, K]: rows past M and columns past K arrive as zeros (TMA out-of-bounds fill)
+  make_map(encode, &mb_hi, ws.bt_hi, n, kp, BN / 2);
+  make_map(encode, &mb_lo, ws.bt_lo, n, kp, BN / 2);
+  const int tiles_pm = (int)((m + 255) / 256), tiles_n = (int)((n + BN - 1) / BN);
+  int pairs = tiles_pm * tiles_n;
+  if (pairs > sm_count / 2) pairs = sm_count / 2;
+  gemm_3xtf32_tmema_kernel<BN><<<2 * pairs, TA_THREADS, SMEM, stream>>>(ma, mb_hi, mb_lo, c, (int)m, (int)n, (int)kp, tiles_pm, tiles_n);
+  check_launch("gemm_3xtf32 (CTA pairs, A through tensor memory)");
+}
+
 template <bool kGather>
 int launch_pipeline(const float* a, const float* b, float* c, int64_t m, int64_t n, int64_t k, const GemmWorkspace& ws, int sm_count,
                     TensorMapEncodeFn encode, cudaStream_t stream, bool b_panels_ready, const GatherMaps& gather, bool a_panels_ready = false) {
@@ -798,10 +1108,12 @@ int launch_pipeline(const float* a, const float* b, float* c, int64_t m, int64_t
              "gemm_3xtf32: bad shape %lld x %lld x %lld", (long long)m, (long long)n, (long long)k);
   CC_REQUIRE(encode, CC_ERR_NO_DRIVER, "cuTensorMapEncodeTiled unavailable");
   const int64_t kp = gemm_padded_k(k);
+  const int config = a_panels_ready ? gemm_config_for(nullptr, m, n, k, sm_count, kGather) : gemm_config_for(a, m, n, k, sm_count, kGather);
+  const bool split_a_needed = !a_panels_ready && config != 1024;
   const size_t nvec = (size_t)(m * kp) / 4;
   size_t blocks = (nvec + 255) / 256;
   if (blocks > (size_t)sm_count * 8) blocks = (size_t)sm_count * 8;
-  if (!a_panels_ready) {
+  if (split_a_needed) {
     split_a_kernel<<<(unsigned)blocks, 256, 0, stream>>>(a, ws.a_hi, ws.a_lo, (int)m, (int)k, (int)kp);
     check_launch("split_a");
   }
@@ -809,19 +1121,16 @@ int launch_pipeline(const float* a, const float* b, float* c, int64_t m, int64_t
     split_transpose_b_kernel<<<dim3((unsigned)((n + 31) / 32), (unsigned)(kp / 32)), 256, 0, stream>>>(b, ws.bt_hi, ws.bt_lo, (int)k, (int)n, (int)kp);
     check_launch("split_transpose_b");
   }
-  // CC_GEMM_FORCE_CONFIG = 512 | 256 | 128 | 64 pins the tile configuration (tests run every variant on the same shapes)
-  int config = gemm_pick_config(m, n, sm_count, true);
-  if (const char* force = getenv("CC_GEMM_FORCE_CONFIG")) {
-    const int f = atoi(force);
-    if (f == 256 || f == 128 || f == 64 || (f == 512 && m > BM)) config = f;
-  }
   switch (config) {
+    case 1024:
+      if constexpr (!kGather) launch_tmema<256>(a, ws, c, m, n, k, kp, sm_count, encode, stream);
+      break;
     case 512: launch_pair<kGather>(ws, c, m, n, kp, sm_count, encode, stream, gather); break;
     case 256: launch_main<256, kGather>(ws, c, m, n, kp, sm_count, encode, stream, gather); break;
     case 128: launch_main<128, kGather>(ws, c, m, n, kp, sm_count, encode, stream, gather); break;
     default: launch_main<64, kGather>(ws, c, m, n, kp, sm_count, encode, stream, gather); break;
   }
-  return 1 + (a_panels_ready ? 0 : 1) + (b_panels_ready ? 0 : 1);
+  return 1 + (split_a_needed ? 1 : 0) + (b_panels_ready ? 0 : 1);
 }
 }  // namespace
 

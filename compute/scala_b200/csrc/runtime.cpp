@@ -1465,17 +1465,18 @@ struct GemmRun {
   Buffer *a_hi = nullptr, *a_lo = nullptr, *bt_hi = nullptr, *bt_lo = nullptr;
   bool b_ready = false;
   void declare(Op& op) const {
-    op.writes.push_back(a_hi);
-    op.writes.push_back(a_lo);
+    if (a_hi) op.writes.push_back(a_hi);  // (none when the kernel splits A itself, through tensor memory)
+    if (a_lo) op.writes.push_back(a_lo);
     (b_ready ? op.reads : op.writes).push_back(bt_hi);
     (b_ready ? op.reads : op.writes).push_back(bt_lo);
   }
 };
 
-GemmRun gemm_prepare(Buffer* b, int64_t m, int64_t n, int64_t k) {
+GemmRun gemm_prepare(Buffer* b, int64_t m, int64_t n, int64_t k, const Buffer* a = nullptr, bool gather_epilogue = false) {
   Runtime& r = rt();
   GemmRun g;
   const int64_t kp = gemm_padded_k(k);
+  const bool a_panels = gemm_config_for(a ? (const float*)a->ptr : nullptr, m, n, k, r.info.sm_count, gather_epilogue) != 1024;
   if (r.panel_cache_on && b->owned)
     for (Runtime::Panels& p : r.panel_cache)
       if (p.uid == b->uid && p.version == b->version && p.k == k && p.n == n) {
@@ -1488,8 +1489,10 @@ GemmRun gemm_prepare(Buffer* b, int64_t m, int64_t n, int64_t k) {
         break;
       }
   try {
-    g.a_hi = alloc_buffer((uint64_t)(m * kp));
-    g.a_lo = alloc_buffer((uint64_t)(m * kp));
+    if (a_panels) {
+      g.a_hi = alloc_buffer((uint64_t)(m * kp));
+      g.a_lo = alloc_buffer((uint64_t)(m * kp));
+    }
     if (!g.b_ready) {
       g.bt_hi = alloc_buffer((uint64_t)(n * kp));
       g.bt_lo = alloc_buffer((uint64_t)(n * kp));
@@ -1524,7 +1527,7 @@ void gemm_finish(GemmRun& g, Buffer* b, int64_t n, int64_t k, bool launched) {
 }
 
 void gemm_on_stream(Buffer* a, Buffer* b, Buffer* c, int64_t m, int64_t n, int64_t k, const GemmRun& g, CUstream s) {
-  GemmWorkspace ws{(float*)g.a_hi->ptr, (float*)g.a_lo->ptr, (float*)g.bt_hi->ptr, (float*)g.bt_lo->ptr};
+  GemmWorkspace ws{g.a_hi ? (float*)g.a_hi->ptr : nullptr, g.a_lo ? (float*)g.a_lo->ptr : nullptr, (float*)g.bt_hi->ptr, (float*)g.bt_lo->ptr};
   int launched = launch_gemm_3xtf32((const float*)a->ptr, (const float*)b->ptr, (float*)c->ptr, m, n, k, ws, rt().info.sm_count,
                                     (TensorMapEncodeFn)driver().cuTensorMapEncodeTiled, (cudaStream_t)s, g.b_ready);
   rt().stats.device_kernels += (uint64_t)launched;
@@ -1657,7 +1660,7 @@ int cc_launch(cc_kernel h, const cc_buffer* args, int n_args, cc_buffer out, con
       return;
     }
     if (p.kind == PLAN_CONTRACTION) {
-      GemmRun g = gemm_prepare(in[1], p.M, p.N, p.K);
+      GemmRun g = gemm_prepare(in[1], p.M, p.N, p.K, in[0]);
       bool launched = false, begun = false;
       Op op{pick_stream_for(in, {ob}), in, {ob}};
       try {
@@ -1773,7 +1776,7 @@ int cc_matmul_3xtf32(cc_buffer a, cc_buffer b, cc_buffer c, int64_t m, int64_t n
     CC_REQUIRE(ab->n_floats >= (uint64_t)(m * k) && bb->n_floats >= (uint64_t)(k * n) && cb->n_floats >= (uint64_t)(m * n),
                CC_ERR_ILLEGAL_ARGUMENT, "matmul buffers too small");
     CC_REQUIRE(cb != ab && cb != bb, CC_ERR_ILLEGAL_ARGUMENT, "matmul output aliases an input");
-    GemmRun g = gemm_prepare(bb, m, n, k);
+    GemmRun g = gemm_prepare(bb, m, n, k, ab);
     bool launched = false;
     try {
       Op op{pick_stream_for({ab, bb}, {cb}), {ab, bb}, {cb}};
@@ -2134,7 +2137,7 @@ int cc_matmul_3xtf32_allgather(cc_buffer a, cc_buffer b, cc_buffer gathered, int
     CC_REQUIRE(ab->n_floats >= (uint64_t)(m_shard * k) && bb->n_floats >= (uint64_t)(k * n) &&
                    gb->n_floats >= (uint64_t)(m_shard * n) * (uint64_t)nc.n_ranks,
                CC_ERR_ILLEGAL_ARGUMENT, "matmul buffers too small");
-    GemmRun g = gemm_prepare(bb, m_shard, n, k);
+    GemmRun g = gemm_prepare(bb, m_shard, n, k, ab, /*gather_epilogue=*/true);
     bool launched = false;
     try {
       Op op{0, {ab, bb}, {gb}};  // collectives stay on stream 0, in call order
@@ -2144,7 +2147,7 @@ int cc_matmul_3xtf32_allgather(cc_buffer a, cc_buffer b, cc_buffer gathered, int
       op_begin(op, waits, n_waits);
       // entry barrier: every rank has finished whatever still read its copy of `gathered` (stream order on each rank) ...
       launch_peer_barrier(nc.mb, ++nc.epoch, (cudaStream_t)op.cu());
-      GemmWorkspace ws{(float*)g.a_hi->ptr, (float*)g.a_lo->ptr, (float*)g.bt_hi->ptr, (float*)g.bt_lo->ptr};
+      GemmWorkspace ws{g.a_hi ? (float*)g.a_hi->ptr : nullptr, g.a_lo ? (float*)g.a_lo->ptr : nullptr, (float*)g.bt_hi->ptr, (float*)g.bt_lo->ptr};
       float* dst[kPeerMaxRanks] = {nullptr};
       for (int q = 0; q < nc.n_ranks; ++q) dst[q] = (float*)gb->peers[(size_t)q];
       int kernels = launch_gemm_3xtf32_allgather((const float*)ab->ptr, (const float*)bb->ptr, dst, nc.n_ranks, nc.rank, m_shard, n, k, ws,

@@ -57,10 +57,12 @@ def test_exact_on_small_integers_any_shape(cuda, m, n, k):
     assert np.array_equal(got, want)
 
 
-@pytest.mark.parametrize("config", [512, 256, 128, 64])
-@pytest.mark.parametrize("m,n,k", [(300, 260, 40), (129, 1, 1), (1000, 513, 200), (2048, 2048, 96)])
+@pytest.mark.parametrize("config", [1024, 512, 256, 128, 64])
+@pytest.mark.parametrize("m,n,k", [(300, 260, 40), (129, 1, 1), (1000, 513, 200), (2048, 2048, 96), (1030, 136, 520), (4096, 4096, 128)])
 def test_every_tile_configuration_on_the_same_shapes(cuda, monkeypatch, config, m, n, k):
-    """512 = 256x256 tiles on CTA pairs (tcgen05.mma.cta_group::2, 3 stages), 256 / 128 / 64 = one CTA per 128 x that many columns"""
+    """1024 = 256x256 tiles on CTA pairs with A read as the original fp32 matrix and split through tensor memory inside the kernel (needs
+    K % 4 == 0, else the request falls back to the picker's choice); 512 = 256x256 tiles on CTA pairs (tcgen05.mma.cta_group::2, 3 stages),
+    256 / 128 / 64 = one CTA per 128 x that many columns"""
     monkeypatch.setenv("CC_GEMM_FORCE_CONFIG", str(config))
     rng = np.random.default_rng(m + n + k + config)
     a = rng.integers(-4, 5, (m, k)).astype(np.float32)
@@ -156,7 +158,7 @@ def accuracy(got, a, b):
     return float((np.abs(got.astype(np.float64) - a64 @ b64) / (np.abs(a64) @ np.abs(b64))).max())
 
 
-@pytest.mark.parametrize("config", [512, 256, 128, 64])
+@pytest.mark.parametrize("config", [1024, 512, 256, 128, 64])
 @pytest.mark.parametrize("m,n,k", [(512, 768, 2048), (384, 520, 8192)])
 def test_fp32_accuracy_on_normal_data_every_tile_configuration(cuda, monkeypatch, config, m, n, k):
     """dataset N (randomNormal: lo panels non-zero) on EVERY tile configuration incl. the CTA-pair kernel that carries the C5 number:
@@ -177,7 +179,7 @@ def test_fp32_accuracy_on_normal_data_every_tile_configuration(cuda, monkeypatch
     assert (np.abs(got.astype(np.float64) - lf.astype(np.float64)) / scale).max() <= 1e-5  # vs the reference's fp32 left fold
 
 
-@pytest.mark.parametrize("config", [512, 256, 128, 64])
+@pytest.mark.parametrize("config", [1024, 512, 256, 128, 64])
 @pytest.mark.parametrize("which", ["a_lo", "b_lo", "both"])
 def test_each_cross_term_is_needed(cuda, monkeypatch, config, which):
     """lo-sensitivity: entries 1 + j * 2^-16 (j < 64) have hi = 1 and ALL their information in lo. With `a_lo` only A carries such entries
