@@ -628,6 +628,11 @@ def run_cuda(args, rank: int, local_rank: int, world: int):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_sec = float(t.item())
     e2e_value = world * alg_bytes / e2e_sec / 1e9
+    e2e_ok = None
+    if rank == 0:
+        # the bytes that came back are the chain's result (spot check against the device-resident evaluation)
+        ref_out = expr.flatArray()
+        e2e_ok = bool(np.array_equal(ref_out[: 1 << 20].view(np.uint32), ho.array[: 1 << 20].view(np.uint32)))
     # The ceiling of that number on this box: the same bytes (3 inputs up, 1 result down, both directions at once, every rank at once) with
     # no kernel at all. It separates what the host / PCIe fabric gives N processes from what the staging design costs.
     def copies_only():
@@ -656,11 +661,6 @@ def run_cuda(args, rank: int, local_rank: int, world: int):
     e2e_ceiling = {"value": world * alg_bytes / copy_sec_max / 1e9, "unit": "GB/s", "h2d_gbs_per_rank": 3 * n * 4 / copy_sec_max / 1e9,
                    "d2h_gbs_per_rank": n * 4 / copy_sec_max / 1e9,
                    "what": "the step's copies alone (3 GiB up + 1 GiB down per rank, all ranks at once, no kernel): the host / PCIe ceiling of e2e on this box"}
-    e2e_ok = None
-    if rank == 0:
-        # the bytes that came back are the chain's result (spot check against the device-resident evaluation)
-        ref_out = expr.flatArray()
-        e2e_ok = bool(np.array_equal(ref_out[: 1 << 20].view(np.uint32), ho.array[: 1 << 20].view(np.uint32)))
     time.sleep(0.1)
     clocks = sampler.summary(w0, w1)
     sampler.stop()

@@ -292,7 +292,6 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
     // ===== epilogue: TMEM -> registers -> global =====
     const int ew = warp - 4;  // TMEM lanes [32*ew, 32*ew + 32)
     int it = 0;
-    int gchunk = 0;  // staging buffer parity (kGather)
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       int m_blk, n_blk;
       tile_coords(tile, tiles_m, tiles_n, m_blk, n_blk);
@@ -304,21 +303,27 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
       const int col0 = n_blk * BN;
       const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * BN);
       if constexpr (kGather) {
-        // TMEM -> registers -> swizzled smem staging -> one TMA store per rank (own HBM and every peer's over NVLink)
+        // TMEM -> registers -> shared-memory staging -> one TMA store per rank (own HBM and every peer's over NVLink). A store covers 32
+        // rows x 64 columns, i.e. 256 contiguous bytes per row: 128-byte row segments (the 32 x 32 boxes of round 1) halve the payload per
+        // NVLink packet, and the exchange — 7 peers x this rank's whole block — is what bounds the fused kernel from 4 ranks on. The staging
+        // tile is unswizzled (the 128-byte swizzle caps a box at 32 floats per row); its bank-conflicted fills are invisible next to a tile's MMAs.
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
-          if (col0 + c * 32 >= N) break;
-          const uint32_t buf = staging + (uint32_t)((ew * 2 + (gchunk & 1)) * 4096);
-          if (lane == 0) bulk_wait_read<1>();  // the stores issued from this buffer two chunks ago have read it
+        for (int c = 0; c < BN / 64; ++c) {
+          if (col0 + c * 64 >= N) break;
+          const uint32_t buf = staging + (uint32_t)(ew * 8192);
+          if (lane == 0) bulk_wait_read<0>();  // the stores issued from this buffer one step ago have read it
           __syncwarp();
-          uint32_t r[32];
-          tmem_ld_32x32(taddr + (uint32_t)(c * 32), r);
-          tmem_ld_wait();
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const uint32_t dst = buf + (uint32_t)(lane * 128 + ((q ^ (lane & 7)) << 4));
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(r[4 * q]), "r"(r[4 * q + 1]), "r"(r[4 * q + 2]), "r"(r[4 * q + 3])
-                         : "memory");
+          for (int h = 0; h < 2; ++h) {
+            uint32_t r[32];
+            tmem_ld_32x32(taddr + (uint32_t)(c * 64 + h * 32), r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const uint32_t dst = buf + (uint32_t)(lane * 256 + h * 128 + (q << 4));
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(r[4 * q]), "r"(r[4 * q + 1]), "r"(r[4 * q + 2]), "r"(r[4 * q + 3])
+                           : "memory");
+            }
           }
           fence_proxy_async_smem();
           __syncwarp();
@@ -327,11 +332,10 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
             for (int i = 0; i < gather.world; ++i) {
               int d = gather.rank + i;
               if (d >= gather.world) d -= gather.world;
-              tma_store_2d(&gather.dst[d], buf, col0 + c * 32, m_blk * BM + ew * 32);
+              tma_store_2d(&gather.dst[d], buf, col0 + c * 64, m_blk * BM + ew * 32);
             }
             bulk_commit();
           }
-          ++gchunk;
         }
       } else {
       float* out = C + (size_t)row * (size_t)N + (size_t)col0;
@@ -363,7 +367,6 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
       mbar_arrive(tmem_empty_bar(acc));
     }
     if (kGather && lane == 0) bulk_wait_all();  // every store (local and remote) has completed before this CTA retires
-    (void)gchunk;
   }
   tc_fence_before();
   __syncthreads();
@@ -550,7 +553,6 @@ gemm_3xtf32_pair_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __gri
     // ===== epilogue (both CTAs): own TMEM (128 rows of the pair's 256) -> registers -> global =====
     const int ew = warp - 4;
     int it = 0;
-    int gchunk = 0;
     for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
       int m_blk, n_blk;
       tile_coords(tile, tiles_pm, tiles_n, m_blk, n_blk);
@@ -563,19 +565,22 @@ gemm_3xtf32_pair_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __gri
       const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * PAIR_BN);
       if constexpr (kGather) {
 #pragma unroll 1
-        for (int c = 0; c < PAIR_BN / 32; ++c) {
-          if (col0 + c * 32 >= N) break;
-          const uint32_t buf = staging + (uint32_t)((ew * 2 + (gchunk & 1)) * 4096);
-          if (lane == 0) bulk_wait_read<1>();
+        for (int c = 0; c < PAIR_BN / 64; ++c) {  // 32 rows x 64 columns per store: see the one-CTA kernel
+          if (col0 + c * 64 >= N) break;
+          const uint32_t buf = staging + (uint32_t)(ew * 8192);
+          if (lane == 0) bulk_wait_read<0>();
           __syncwarp();
-          uint32_t r[32];
-          tmem_ld_32x32(taddr + (uint32_t)(c * 32), r);
-          tmem_ld_wait();
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const uint32_t dst = buf + (uint32_t)(lane * 128 + ((q ^ (lane & 7)) << 4));
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(r[4 * q]), "r"(r[4 * q + 1]), "r"(r[4 * q + 2]), "r"(r[4 * q + 3])
-                         : "memory");
+          for (int h = 0; h < 2; ++h) {
+            uint32_t r[32];
+            tmem_ld_32x32(taddr + (uint32_t)(c * 64 + h * 32), r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const uint32_t dst = buf + (uint32_t)(lane * 256 + h * 128 + (q << 4));
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(r[4 * q]), "r"(r[4 * q + 1]), "r"(r[4 * q + 2]), "r"(r[4 * q + 3])
+                           : "memory");
+            }
           }
           fence_proxy_async_smem();
           __syncwarp();
@@ -583,11 +588,10 @@ gemm_3xtf32_pair_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __gri
             for (int i = 0; i < gather.world; ++i) {  // staggered destinations, see the one-CTA kernel
               int d = gather.rank + i;
               if (d >= gather.world) d -= gather.world;
-              tma_store_2d(&gather.dst[d], buf, col0 + c * 32, m_blk * 256 + (int)rank * 128 + ew * 32);
+              tma_store_2d(&gather.dst[d], buf, col0 + c * 64, m_blk * 256 + (int)rank * 128 + ew * 32);
             }
             bulk_commit();
           }
-          ++gchunk;
         }
       } else {
       float* out = C + (size_t)row * (size_t)N + (size_t)col0;
@@ -618,7 +622,6 @@ gemm_3xtf32_pair_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __gri
       mbar_arrive_cluster(map_to_cta(tmem_empty_bar(acc), 0));  // the leader's barrier (a remote arrive from CTA 1)
     }
     if (kGather && lane == 0) bulk_wait_all();
-    (void)gchunk;
   }
   tc_fence_before();
   cluster_sync_all();  // nobody frees TMEM / exits while the peer may still read it or signal into it
@@ -1159,10 +1162,10 @@ int launch_gemm_3xtf32_allgather(const float* a, const float* b, float* const* g
     float* base = gathered_c[d] + (size_t)rank * (size_t)m_shard * (size_t)n;
     cuuint64_t dims[2] = {(cuuint64_t)n, (cuuint64_t)m_shard};
     cuuint64_t strides[1] = {(cuuint64_t)n * 4};
-    cuuint32_t box[2] = {32, 32};
+    cuuint32_t box[2] = {64, 32};  // 32 rows x 256 contiguous bytes, from an unswizzled staging tile
     cuuint32_t estr[2] = {1, 1};
     CUresult r = encode(&g.dst[d], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) fail(CC_ERR_CUDA, strprintf("cuTensorMapEncodeTiled(gather destination %d) failed (%d)", d, (int)r));
   }
   return launch_pipeline<true>(a, b, nullptr, m_shard, n, k, ws, sm_count, encode, stream, b_panels_ready, g);

@@ -99,6 +99,7 @@ def _worker(rank, world, port):
             ms, mn = sharding.shard_rows(m, world, rank)
             A2, B2 = cuda.Buffer.from_host(a[ms : ms + mn]), cuda.Buffer.from_host(b)
             want = (a.astype(np.float64) @ b.astype(np.float64)).astype(np.float32)
+            comm._require_equal_blocks(mn * nn)  # (its one-off agreement exchange is a kernel too: keep it out of the launch counts below)
             for rep, config in enumerate((None, None, "512", "256", "64")):  # back to back: the entry barrier protects the arena
                 # every tile configuration of the gather epilogue: CTA pairs (cta_group::2) and single CTAs
                 if config:
