@@ -175,7 +175,7 @@ template <int BN, bool kGather>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                    const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo, float* __restrict__ C, int M, int N, int Kp,
-                   int tiles_m, int tiles_n, const __grid_constant__ GatherMaps gather) {
+                   int tiles_m, int tiles_n, const __grid_constant__ GatherMaps gather, int kb_begin, int accumulate) {
   constexpr int STAGES = Cfg<BN>::STAGES;
   constexpr int STAGE_BYTES = Cfg<BN>::STAGE_BYTES;
   constexpr int B_TILE_BYTES = Cfg<BN>::B_TILE_BYTES;
@@ -198,7 +198,7 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int num_tiles = tiles_m * tiles_n;
-  const int num_kb = Kp / BK;
+  const int num_kb = Kp / BK;  // k blocks of THIS launch: [kb_begin, kb_begin + num_kb) of the panels (K chunks, see launch_pipeline)
 
   if (warp == 0 && lane == 0) {
     prefetch_tensormap(&tm_a_hi);
@@ -240,10 +240,10 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
           mbar_wait(empty_bar(stage), phase ^ 1);
           const uint32_t st = smem_base + stage * STAGE_BYTES;
           mbar_arrive_expect_tx(full_bar(stage), STAGE_BYTES);
-          tma_load_2d(st, &tm_a_hi, full_bar(stage), kb * BK, m_blk * BM);
-          tma_load_2d(st + A_TILE_BYTES, &tm_a_lo, full_bar(stage), kb * BK, m_blk * BM);
-          tma_load_2d(st + 2 * A_TILE_BYTES, &tm_b_hi, full_bar(stage), kb * BK, n_blk * BN);
-          tma_load_2d(st + 2 * A_TILE_BYTES + B_TILE_BYTES, &tm_b_lo, full_bar(stage), kb * BK, n_blk * BN);
+          tma_load_2d(st, &tm_a_hi, full_bar(stage), (kb_begin + kb) * BK, m_blk * BM);
+          tma_load_2d(st + A_TILE_BYTES, &tm_a_lo, full_bar(stage), (kb_begin + kb) * BK, m_blk * BM);
+          tma_load_2d(st + 2 * A_TILE_BYTES, &tm_b_hi, full_bar(stage), (kb_begin + kb) * BK, n_blk * BN);
+          tma_load_2d(st + 2 * A_TILE_BYTES + B_TILE_BYTES, &tm_b_lo, full_bar(stage), (kb_begin + kb) * BK, n_blk * BN);
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
@@ -353,12 +353,16 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
             float4 v = make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]), __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
+            if (accumulate) {  // a later K chunk: C += this chunk's product, added in fp32 with round-to-nearest
+              const float4 o = __ldcs(reinterpret_cast<const float4*>(out + c * 32) + q);
+              v.x += o.x, v.y += o.y, v.z += o.z, v.w += o.w;
+            }
             __stcs(reinterpret_cast<float4*>(out + c * 32) + q, v);
           }
         } else {
 #pragma unroll
           for (int q = 0; q < 32; ++q)
-            if (col0 + c * 32 + q < N) __stcs(out + c * 32 + q, __uint_as_float(r[q]));
+            if (col0 + c * 32 + q < N) __stcs(out + c * 32 + q, __uint_as_float(r[q]) + (accumulate ? __ldcs(out + c * 32 + q) : 0.f));
         }
         __syncwarp();
       }
@@ -435,7 +439,7 @@ template <bool kGather>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm_3xtf32_pair_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                         const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo, float* __restrict__ C, int M, int N,
-                        int Kp, int tiles_pm, int tiles_n, const __grid_constant__ GatherMaps gather) {
+                        int Kp, int tiles_pm, int tiles_n, const __grid_constant__ GatherMaps gather, int kb_begin, int accumulate) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   constexpr int STAGING_BYTES = kGather ? PAIR_STAGING_BYTES : 0;
@@ -501,10 +505,10 @@ gemm_3xtf32_pair_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __gri
           const uint32_t st = smem_base + stage * PAIR_STAGE_BYTES;
           const uint32_t leader_full = map_to_cta(full_bar(stage), 0);
           if (rank == 0) mbar_arrive_expect_tx(full_bar(stage), 2 * PAIR_STAGE_BYTES);
-          tma_load_2d_pair(st, &tm_a_hi, leader_full, kb * BK, row_a);
-          tma_load_2d_pair(st + A_TILE_BYTES, &tm_a_lo, leader_full, kb * BK, row_a);
-          tma_load_2d_pair(st + 2 * A_TILE_BYTES, &tm_b_hi, leader_full, kb * BK, row_b);
-          tma_load_2d_pair(st + 2 * A_TILE_BYTES + PAIR_B_HALF_BYTES, &tm_b_lo, leader_full, kb * BK, row_b);
+          tma_load_2d_pair(st, &tm_a_hi, leader_full, (kb_begin + kb) * BK, row_a);
+          tma_load_2d_pair(st + A_TILE_BYTES, &tm_a_lo, leader_full, (kb_begin + kb) * BK, row_a);
+          tma_load_2d_pair(st + 2 * A_TILE_BYTES, &tm_b_hi, leader_full, (kb_begin + kb) * BK, row_b);
+          tma_load_2d_pair(st + 2 * A_TILE_BYTES + PAIR_B_HALF_BYTES, &tm_b_lo, leader_full, (kb_begin + kb) * BK, row_b);
           if (++stage == PAIR_STAGES) {
             stage = 0;
             phase ^= 1;
@@ -608,12 +612,16 @@ gemm_3xtf32_pair_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __gri
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
             float4 v = make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]), __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
+            if (accumulate) {  // a later K chunk: C += this chunk's product, added in fp32 with round-to-nearest
+              const float4 o = __ldcs(reinterpret_cast<const float4*>(out + c * 32) + q);
+              v.x += o.x, v.y += o.y, v.z += o.z, v.w += o.w;
+            }
             __stcs(reinterpret_cast<float4*>(out + c * 32) + q, v);
           }
         } else {
 #pragma unroll
           for (int q = 0; q < 32; ++q)
-            if (col0 + c * 32 + q < N) __stcs(out + c * 32 + q, __uint_as_float(r[q]));
+            if (col0 + c * 32 + q < N) __stcs(out + c * 32 + q, __uint_as_float(r[q]) + (accumulate ? __ldcs(out + c * 32 + q) : 0.f));
         }
         __syncwarp();
       }
@@ -696,7 +704,7 @@ __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.
 template <int BN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TA_THREADS, 1)
 gemm_3xtf32_tmema_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
-                         float* __restrict__ C, int M, int N, int Kp, int tiles_pm, int tiles_n) {
+                         float* __restrict__ C, int M, int N, int Kp, int tiles_pm, int tiles_n, int kb_begin, int accumulate) {
   constexpr int ACCS = TaCfg<BN>::ACCS;
   constexpr int B_HALF_BYTES = TaCfg<BN>::B_HALF_BYTES;
   constexpr int STAGE_BYTES = TaCfg<BN>::STAGE_BYTES;
@@ -763,11 +771,11 @@ gemm_3xtf32_tmema_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
           mbar_wait(empty_bar(stage), phase ^ 1);
           const uint32_t st = smem_base + stage * STAGE_BYTES;
           mbar_arrive_expect_tx(a_full_bar(stage), TA_A_RAW_BYTES);
-          tma_load_2d(st, &tm_a, a_full_bar(stage), kb * BK, row_a);
+          tma_load_2d(st, &tm_a, a_full_bar(stage), (kb_begin + kb) * BK, row_a);
           const uint32_t leader_b_full = map_to_cta(b_full_bar(stage), 0);
           if (rank == 0) mbar_arrive_expect_tx(b_full_bar(stage), 2 * 2 * B_HALF_BYTES);
-          tma_load_2d_pair(st + TA_A_RAW_BYTES, &tm_b_hi, leader_b_full, kb * BK, row_b);
-          tma_load_2d_pair(st + TA_A_RAW_BYTES + B_HALF_BYTES, &tm_b_lo, leader_b_full, kb * BK, row_b);
+          tma_load_2d_pair(st + TA_A_RAW_BYTES, &tm_b_hi, leader_b_full, (kb_begin + kb) * BK, row_b);
+          tma_load_2d_pair(st + TA_A_RAW_BYTES + B_HALF_BYTES, &tm_b_lo, leader_b_full, (kb_begin + kb) * BK, row_b);
           if (++stage == TA_STAGES) {
             stage = 0;
             phase ^= 1;
@@ -880,12 +888,16 @@ gemm_3xtf32_tmema_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
             float4 v = make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]), __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
+            if (accumulate) {  // a later K chunk: C += this chunk's product, added in fp32 with round-to-nearest
+              const float4 o = __ldcs(reinterpret_cast<const float4*>(out + c * 32) + q);
+              v.x += o.x, v.y += o.y, v.z += o.z, v.w += o.w;
+            }
             __stcs(reinterpret_cast<float4*>(out + c * 32) + q, v);
           }
         } else {
 #pragma unroll
           for (int q = 0; q < 32; ++q)
-            if (col0 + c * 32 + q < N) __stcs(out + c * 32 + q, __uint_as_float(r[q]));
+            if (col0 + c * 32 + q < N) __stcs(out + c * 32 + q, __uint_as_float(r[q]) + (accumulate ? __ldcs(out + c * 32 + q) : 0.f));
         }
         __syncwarp();
       }
@@ -1038,7 +1050,7 @@ bool tmema_default() {
 
 template <int BN, bool kGather>
 void launch_main(const GemmWorkspace& ws, float* c, int64_t m, int64_t n, int64_t kp, int sm_count, TensorMapEncodeFn encode, cudaStream_t stream,
-                 const GatherMaps& gather) {
+                 const GatherMaps& gather, int64_t kb_begin = 0, int64_t kb_count = -1) {
   constexpr int SMEM = kGather ? Cfg<BN>::SMEM_BYTES_GATHER : Cfg<BN>::SMEM_BYTES;
   static bool attr_set = false;
   if (!attr_set) {
@@ -1054,13 +1066,15 @@ void launch_main(const GemmWorkspace& ws, float* c, int64_t m, int64_t n, int64_
   const int tiles_m = (int)((m + BM - 1) / BM), tiles_n = (int)((n + BN - 1) / BN);
   int grid = tiles_m * tiles_n;
   if (grid > sm_count) grid = sm_count;
-  gemm_3xtf32_kernel<BN, kGather><<<grid, GEMM_THREADS, SMEM, stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, c, (int)m, (int)n, (int)kp, tiles_m, tiles_n, gather);
+  const int64_t kbs = kb_count < 0 ? kp / BK : kb_count;
+  gemm_3xtf32_kernel<BN, kGather><<<grid, GEMM_THREADS, SMEM, stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, c, (int)m, (int)n, (int)(kbs * BK), tiles_m, tiles_n, gather,
+                                                                        (int)kb_begin, kb_begin > 0 ? 1 : 0);
   check_launch(kGather ? "gemm_3xtf32 (all-gather epilogue)" : "gemm_3xtf32");
 }
 
 template <bool kGather>
 void launch_pair(const GemmWorkspace& ws, float* c, int64_t m, int64_t n, int64_t kp, int sm_count, TensorMapEncodeFn encode, cudaStream_t stream,
-                 const GatherMaps& gather) {
+                 const GatherMaps& gather, int64_t kb_begin = 0, int64_t kb_count = -1) {
   constexpr int SMEM = kGather ? PAIR_SMEM_BYTES_GATHER : PAIR_SMEM_BYTES;
   static bool attr_set = false;
   if (!attr_set) {
@@ -1076,7 +1090,9 @@ void launch_pair(const GemmWorkspace& ws, float* c, int64_t m, int64_t n, int64_
   const int tiles_pm = (int)((m + 255) / 256), tiles_n = (int)((n + PAIR_BN - 1) / PAIR_BN);
   int pairs = tiles_pm * tiles_n;
   if (pairs > sm_count / 2) pairs = sm_count / 2;
-  gemm_3xtf32_pair_kernel<kGather><<<2 * pairs, GEMM_THREADS, SMEM, stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, c, (int)m, (int)n, (int)kp, tiles_pm, tiles_n, gather);
+  const int64_t kbs = kb_count < 0 ? kp / BK : kb_count;
+  gemm_3xtf32_pair_kernel<kGather><<<2 * pairs, GEMM_THREADS, SMEM, stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, c, (int)m, (int)n, (int)(kbs * BK), tiles_pm, tiles_n,
+                                                                              gather, (int)kb_begin, kb_begin > 0 ? 1 : 0);
   check_launch(kGather ? "gemm_3xtf32 (CTA pairs, all-gather epilogue)" : "gemm_3xtf32 (CTA pairs)");
 }
 
@@ -1085,7 +1101,7 @@ void launch_pair(const GemmWorkspace& ws, float* c, int64_t m, int64_t n, int64_
 // 128-column MMAs are too short to keep the pipe busy — against 304 for 256 x 256, so only the wide tile is dispatched.)
 template <int BN>
 void launch_tmema(const float* a, const GemmWorkspace& ws, float* c, int64_t m, int64_t n, int64_t k, int64_t kp, int sm_count, TensorMapEncodeFn encode,
-                  cudaStream_t stream) {
+                  cudaStream_t stream, int64_t kb_begin = 0, int64_t kb_count = -1) {
   constexpr int SMEM = TaCfg<BN>::SMEM_BYTES;
   static bool attr_set = false;
   if (!attr_set) {
@@ -1100,7 +1116,9 @@ void launch_tmema(const float* a, const GemmWorkspace& ws, float* c, int64_t m, 
   const int tiles_pm = (int)((m + 255) / 256), tiles_n = (int)((n + BN - 1) / BN);
   int pairs = tiles_pm * tiles_n;
   if (pairs > sm_count / 2) pairs = sm_count / 2;
-  gemm_3xtf32_tmema_kernel<BN><<<2 * pairs, TA_THREADS, SMEM, stream>>>(ma, mb_hi, mb_lo, c, (int)m, (int)n, (int)kp, tiles_pm, tiles_n);
+  const int64_t kbs = kb_count < 0 ? kp / BK : kb_count;
+  gemm_3xtf32_tmema_kernel<BN><<<2 * pairs, TA_THREADS, SMEM, stream>>>(ma, mb_hi, mb_lo, c, (int)m, (int)n, (int)(kbs * BK), tiles_pm, tiles_n, (int)kb_begin,
+                                                                        kb_begin > 0 ? 1 : 0);
   check_launch("gemm_3xtf32 (CTA pairs, A through tensor memory)");
 }
 
@@ -1124,16 +1142,27 @@ int launch_pipeline(const float* a, const float* b, float* c, int64_t m, int64_t
     split_transpose_b_kernel<<<dim3((unsigned)((n + 31) / 32), (unsigned)(kp / 32)), 256, 0, stream>>>(b, ws.bt_hi, ws.bt_lo, (int)k, (int)n, (int)kp);
     check_launch("split_transpose_b");
   }
-  switch (config) {
-    case 1024:
-      if constexpr (!kGather) launch_tmema<256>(a, ws, c, m, n, k, kp, sm_count, encode, stream);
-      break;
-    case 512: launch_pair<kGather>(ws, c, m, n, kp, sm_count, encode, stream, gather); break;
-    case 256: launch_main<256, kGather>(ws, c, m, n, kp, sm_count, encode, stream, gather); break;
-    case 128: launch_main<128, kGather>(ws, c, m, n, kp, sm_count, encode, stream, gather); break;
-    default: launch_main<64, kGather>(ws, c, m, n, kp, sm_count, encode, stream, gather); break;
+  // The tensor core accumulates the 3 * K / 8 partial products of an output in fp32 with TRUNCATION, so the error of one launch grows
+  // linearly in K (4.9e-6 |A||B| at K = 8192 on normal data; the bar is 1e-5). Beyond kMaxChunkK the product is computed in K chunks whose
+  // results are added in the epilogue with round-to-nearest (C += chunk): the error then stays at the one-chunk level for any K, for one
+  // extra read of C per chunk. (The all-gather epilogue stores through tensor maps and is not chunked.)
+  constexpr int64_t kMaxChunkK = 8192;
+  const int64_t kb_total = kp / BK;
+  const int64_t kb_chunk = kGather ? kb_total : std::min<int64_t>(kb_total, kMaxChunkK / BK);
+  int launches = 0;
+  for (int64_t kb0 = 0; kb0 < kb_total; kb0 += kb_chunk, ++launches) {
+    const int64_t kbs = std::min<int64_t>(kb_chunk, kb_total - kb0);
+    switch (config) {
+      case 1024:
+        if constexpr (!kGather) launch_tmema<256>(a, ws, c, m, n, k, kp, sm_count, encode, stream, kb0, kbs);
+        break;
+      case 512: launch_pair<kGather>(ws, c, m, n, kp, sm_count, encode, stream, gather, kb0, kbs); break;
+      case 256: launch_main<256, kGather>(ws, c, m, n, kp, sm_count, encode, stream, gather, kb0, kbs); break;
+      case 128: launch_main<128, kGather>(ws, c, m, n, kp, sm_count, encode, stream, gather, kb0, kbs); break;
+      default: launch_main<64, kGather>(ws, c, m, n, kp, sm_count, encode, stream, gather, kb0, kbs); break;
+    }
   }
-  return 1 + (split_a_needed ? 1 : 0) + (b_panels_ready ? 0 : 1);
+  return launches + (split_a_needed ? 1 : 0) + (b_panels_ready ? 0 : 1);
 }
 }  // namespace
 

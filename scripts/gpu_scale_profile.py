@@ -41,12 +41,12 @@ for name, e in legs:
     cuda.synchronize()
     rep = cuda.profile_report()
     cuda.profile(False)
-    out[name] = [{k: r[k] for k in ("label", "count", "avg_ms", "min_ms", "max_ms") if k in r} for r in rep]
+    out[name] = [{k: r[k] for k in ("name", "count", "avg_us", "min_us", "max_us") if k in r} for r in rep]
     dist.barrier()
 if rank == 0:
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     json.dump({"n_gpus": world, "how": __doc__.split("\n")[0], "legs": out}, open(os.path.join(ROOT, "gpurun_out", f"scale_profile_n{world}.json"), "w"), indent=1)
     for k, v in out.items():
-        print(k, [(r.get("label", "")[:50], round(r.get("avg_ms", 0) * 1000, 1)) for r in v])
+        print(k, [(r.get("name", "")[:50], round(r.get("avg_us", 0), 1)) for r in v])
 comm.close()
 dist.destroy_process_group()

@@ -204,6 +204,23 @@ def test_each_cross_term_is_needed(cuda, monkeypatch, config, which):
     assert float((np.abs(a_h.astype(np.float64) @ b_h.astype(np.float64) - truth) / truth).max()) >= 2e-4
 
 
+@pytest.mark.parametrize("config", [1024, 512, 128])
+def test_k_chunks_keep_the_error_at_the_one_chunk_level(cuda, monkeypatch, config):
+    """the tensor core's truncating fp32 accumulation makes one launch's error grow linearly in K (4.9e-6 at 8192): beyond 8192 the product
+    runs in K chunks added in the epilogue with round-to-nearest, so K = 20000 (three chunks, the last one ragged) is no worse than one chunk;
+    and integers stay exact through the C += chunk path"""
+    monkeypatch.setenv("CC_GEMM_FORCE_CONFIG", str(config))
+    m, n, k = 384, 264, 20000
+    a = finite_normal(m * k, 9).reshape(m, k)
+    b = finite_normal(k * n, 10).reshape(k, n)
+    err = accuracy(run_matmul(cuda, a, b), a, b)
+    assert err <= 6e-6, err
+    rng = np.random.default_rng(config)
+    ai = rng.integers(-4, 5, (m, k)).astype(np.float32)
+    bi = rng.integers(-4, 5, (k, n)).astype(np.float32)
+    assert np.array_equal(run_matmul(cuda, ai, bi), (ai.astype(np.float64) @ bi.astype(np.float64)).astype(np.float32))
+
+
 def test_pattern_lowers_to_tcgen05(cuda):
     """matmul written the way benchmarks.scala:188-191 writes it runs on the tensor cores and never materialises i*j*k"""
     T = cuda.Tensor
