@@ -82,6 +82,8 @@ int launch_gemm_3xtf32_panels(float* c, int64_t m, int64_t n, int64_t k, const G
 // cross-rank barrier (launch_peer_barrier) afterwards: when it completes every block of every rank has landed.
 int launch_gemm_3xtf32_allgather(const float* a, const float* b, float* const* gathered_c, int world, int rank, int64_t m_shard,
                                  int64_t n, int64_t k, const GemmWorkspace& ws, int sm_count, TensorMapEncodeFn encode,
-                                 cudaStream_t stream, bool b_panels_ready = false);
+                                 cudaStream_t stream, bool b_panels_ready = false, float* multicast_c = nullptr);
+// (multicast_c: the NVLS multicast mapping of the gathered C, if the symmetric buffer has one — then every block is stored ONCE through it
+// and gathered_c is not used)
 
 }  // namespace cc

@@ -63,7 +63,22 @@ namespace cc {
   X(cuGraphInstantiateWithFlags)        \
   X(cuGraphLaunch)                      \
   X(cuGraphExecDestroy)                 \
-  X(cuGraphDestroy)
+  X(cuGraphDestroy)                     \
+  X(cuMemCreate)                        \
+  X(cuMemRelease)                       \
+  X(cuMemAddressReserve)                \
+  X(cuMemAddressFree)                   \
+  X(cuMemMap)                           \
+  X(cuMemUnmap)                         \
+  X(cuMemSetAccess)                     \
+  X(cuMemGetAllocationGranularity)      \
+  X(cuMemExportToShareableHandle)       \
+  X(cuMemImportFromShareableHandle)     \
+  X(cuMulticastCreate)                  \
+  X(cuMulticastAddDevice)               \
+  X(cuMulticastBindMem)                 \
+  X(cuMulticastUnbind)                  \
+  X(cuMulticastGetGranularity)
 
 struct Driver {
 #define CC_DECL(name) decltype(&::name) name = nullptr;

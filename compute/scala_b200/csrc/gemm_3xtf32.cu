@@ -370,7 +370,10 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
       tc_fence_before();
       mbar_arrive(tmem_empty_bar(acc));
     }
-    if (kGather && lane == 0) bulk_wait_all();  // every store (local and remote) has completed before this CTA retires
+    if (kGather && lane == 0) {
+      bulk_wait_all();  // every store (local and remote) has completed before this CTA retires
+      __threadfence_system();
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -629,7 +632,10 @@ gemm_3xtf32_pair_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __gri
       tc_fence_before();
       mbar_arrive_cluster(map_to_cta(tmem_empty_bar(acc), 0));  // the leader's barrier (a remote arrive from CTA 1)
     }
-    if (kGather && lane == 0) bulk_wait_all();
+    if (kGather && lane == 0) {
+      bulk_wait_all();
+      __threadfence_system();
+    }
   }
   tc_fence_before();
   cluster_sync_all();  // nobody frees TMEM / exits while the peer may still read it or signal into it
@@ -1179,16 +1185,19 @@ int launch_gemm_3xtf32(const float* a, const float* b, float* c, int64_t m, int6
 }
 
 int launch_gemm_3xtf32_allgather(const float* a, const float* b, float* const* gathered_c, int world, int rank, int64_t m_shard, int64_t n, int64_t k,
-                                 const GemmWorkspace& ws, int sm_count, TensorMapEncodeFn encode, cudaStream_t stream, bool b_panels_ready) {
+                                 const GemmWorkspace& ws, int sm_count, TensorMapEncodeFn encode, cudaStream_t stream, bool b_panels_ready,
+                                 float* multicast_c) {
   CC_REQUIRE(world >= 1 && world <= kPeerMaxRanks && rank >= 0 && rank < world, CC_ERR_ILLEGAL_ARGUMENT, "bad world / rank");
   CC_REQUIRE(n % 4 == 0, CC_ERR_UNSUPPORTED, "the all-gather epilogue needs N %% 4 == 0 (16-byte row pitch for the TMA stores)");
   CC_REQUIRE(encode, CC_ERR_NO_DRIVER, "cuTensorMapEncodeTiled unavailable");
   GatherMaps g{};
-  g.world = world;
-  g.rank = rank;
-  for (int d = 0; d < world; ++d) {
+  // NVLS: ONE destination — the multicast mapping of the gathered C. A store through it is replicated by the NVSwitch into every rank's
+  // copy (this rank's own included), so a block leaves the GPU once instead of once per peer.
+  g.world = multicast_c ? 1 : world;
+  g.rank = multicast_c ? 0 : rank;
+  for (int d = 0; d < g.world; ++d) {
     // rank `rank`'s row block inside rank d's gathered C: [m_shard, N] at row offset rank * m_shard
-    float* base = gathered_c[d] + (size_t)rank * (size_t)m_shard * (size_t)n;
+    float* base = (multicast_c ? multicast_c : gathered_c[d]) + (size_t)rank * (size_t)m_shard * (size_t)n;
     cuuint64_t dims[2] = {(cuuint64_t)n, (cuuint64_t)m_shard};
     cuuint64_t strides[1] = {(cuuint64_t)n * 4};
     cuuint32_t box[2] = {64, 32};  // 32 rows x 256 contiguous bytes, from an unswizzled staging tile

@@ -8,6 +8,9 @@
 #include <nvtx3/nvToolsExt.h>
 #include <sys/stat.h>
 #include <unistd.h>
+#include <sys/socket.h>
+#include <sys/un.h>
+#include <cstddef>
 
 #include <time.h>
 
@@ -59,6 +62,11 @@ struct Buffer {
   Mark last_write;
   SmallVec<Mark, 4> reads;  // at most one per stream
   std::vector<CUdeviceptr> peers;  // symmetric buffers only: the same allocation on every rank (own pointer at own rank)
+  // multicast symmetric buffers (NVLS): `ptr` is this rank's own memory, `mc_ptr` a second mapping through which ONE store lands in the
+  // same offset of every rank's memory (replicated by the NVSwitch); created with the virtual-memory-management API, not the pool
+  CUdeviceptr mc_ptr = 0;
+  CUmemGenericAllocationHandle mc_handle = 0, mem_handle = 0;
+  size_t vmm_bytes = 0;
   uint64_t uid = 0;         // never reused: identity for the operand-panel cache
   uint64_t version = 0;     // bumped by every command that writes the buffer
 };
@@ -743,6 +751,20 @@ void close_peers(Nccl& n) {
   if (!n.peer_mapped) return;
   driver().cuCtxSynchronize();
   for (Buffer* b : n.symmetric) {
+    if (b->mc_ptr) {  // multicast buffer: unmap both views, unbind, drop the handles
+      Driver& d = driver();
+      d.cuMemUnmap(b->mc_ptr, b->vmm_bytes);
+      d.cuMemAddressFree(b->mc_ptr, b->vmm_bytes);
+      d.cuMulticastUnbind(b->mc_handle, rt().dev, 0, b->vmm_bytes);
+      d.cuMemUnmap(b->ptr, b->vmm_bytes);
+      d.cuMemAddressFree(b->ptr, b->vmm_bytes);
+      d.cuMemRelease(b->mem_handle);
+      d.cuMemRelease(b->mc_handle);
+      b->mc_ptr = 0;
+      b->ptr = 0;
+      release(b);
+      continue;
+    }
     for (int r = 0; r < (int)b->peers.size(); ++r)
       if (r != n.rank && b->peers[(size_t)r]) driver().cuIpcCloseMemHandle(b->peers[(size_t)r]);
     if (b->ptr) driver().cuMemFree(b->ptr);
@@ -2068,6 +2090,180 @@ int cc_reduce_sum_allreduce(cc_buffer in, uint64_t n_floats, cc_buffer out, cons
   });
 }
 
+namespace {
+// ---- NVLS multicast symmetric memory -------------------------------------------------------------------------------------------------
+// One multicast object over the ranks' devices (rank 0 creates it and hands its POSIX file descriptor to the other processes over an
+// abstract unix socket, SCM_RIGHTS), every rank binds `bytes` of its own device memory at offset 0 and maps two views: its own memory, and
+// the multicast address through which a store is replicated by the NVSwitch into every rank's memory at the same offset.
+
+int send_fd(int sock, int fd) {
+  char data = 'f';
+  iovec iov{&data, 1};
+  char ctrl[CMSG_SPACE(sizeof(int))] = {0};
+  msghdr msg{};
+  msg.msg_iov = &iov, msg.msg_iovlen = 1, msg.msg_control = ctrl, msg.msg_controllen = sizeof ctrl;
+  cmsghdr* c = CMSG_FIRSTHDR(&msg);
+  c->cmsg_level = SOL_SOCKET, c->cmsg_type = SCM_RIGHTS, c->cmsg_len = CMSG_LEN(sizeof(int));
+  memcpy(CMSG_DATA(c), &fd, sizeof(int));
+  return sendmsg(sock, &msg, 0) == 1 ? 0 : -1;
+}
+int recv_fd(int sock) {
+  char data = 0;
+  iovec iov{&data, 1};
+  char ctrl[CMSG_SPACE(sizeof(int))] = {0};
+  msghdr msg{};
+  msg.msg_iov = &iov, msg.msg_iovlen = 1, msg.msg_control = ctrl, msg.msg_controllen = sizeof ctrl;
+  if (recvmsg(sock, &msg, 0) != 1) return -1;
+  cmsghdr* c = CMSG_FIRSTHDR(&msg);
+  if (!c || c->cmsg_level != SOL_SOCKET || c->cmsg_type != SCM_RIGHTS) return -1;
+  int fd = -1;
+  memcpy(&fd, CMSG_DATA(c), sizeof(int));
+  return fd;
+}
+sockaddr_un abstract_address(uint64_t token, socklen_t* len) {
+  sockaddr_un a{};
+  a.sun_family = AF_UNIX;
+  const int n = snprintf(a.sun_path + 1, sizeof a.sun_path - 1, "compute_cuda_mc_%016llx", (unsigned long long)token);  // sun_path[0] = 0: abstract
+  *len = (socklen_t)(offsetof(sockaddr_un, sun_path) + 1 + (size_t)n);
+  return a;
+}
+
+// a barrier + an 8-byte broadcast through the communicator (stream 0, synchronised): the only coordination the set-up needs
+uint64_t comm_broadcast_u64(Nccl& n, uint64_t value) {
+  CUstream s0 = rt().streams[0];
+  CUdeviceptr d = 0;
+  CC_CU(cuMemAlloc(&d, 256));
+  CC_CU(cuMemcpyHtoD(d, &value, 8));
+  n.check(n.Broadcast((const void*)d, (void*)d, 8, ncclChar, 0, n.comm, (cudaStream_t)s0), "ncclBroadcast(multicast token)");
+  CC_CU(cuStreamSynchronize(s0));
+  CC_CU(cuMemcpyDtoH(&value, d, 8));
+  driver().cuMemFree(d);
+  rt().seq[0]++;
+  return value;
+}
+// every rank reports 1 (fine so far) or 0; returns true only if all did — so that a rank that cannot take part makes ALL fall back together
+bool comm_all_ok(Nccl& n, bool ok) {
+  CUstream s0 = rt().streams[0];
+  CUdeviceptr d = 0;
+  CC_CU(cuMemAlloc(&d, 256));
+  float v = ok ? 0.f : 1.f;
+  CC_CU(cuMemcpyHtoD(d, &v, 4));
+  n.check(n.AllReduce((const void*)d, (void*)d, 1, ncclFloat, ncclSum, n.comm, (cudaStream_t)s0), "ncclAllReduce(multicast agreement)");
+  CC_CU(cuStreamSynchronize(s0));
+  CC_CU(cuMemcpyDtoH(&v, d, 4));
+  driver().cuMemFree(d);
+  rt().seq[0]++;
+  return v == 0.f;
+}
+
+// Collective. Returns nullptr (on every rank alike) when multicast cannot be used here; the caller falls back to CUDA-IPC peer mappings.
+Buffer* multicast_alloc(uint64_t n_floats) {
+  Runtime& r = rt();
+  Nccl& n = r.nccl;
+  Driver& d = driver();
+  if (const char* e = getenv("CC_MULTICAST"))
+    if (atoi(e) == 0) return nullptr;  // (set identically on every rank, like every CC_* switch)
+  bool ok = d.cuMulticastCreate && d.cuMulticastAddDevice && d.cuMulticastBindMem && d.cuMulticastGetGranularity && d.cuMemCreate && d.cuMemMap &&
+            d.cuMemAddressReserve && d.cuMemSetAccess && d.cuMemExportToShareableHandle && d.cuMemImportFromShareableHandle;
+  int supported = 0;
+  if (ok) ok = d.cuDeviceGetAttribute(&supported, CU_DEVICE_ATTRIBUTE_MULTICAST_SUPPORTED, r.dev) == CUDA_SUCCESS && supported;
+  CUmulticastObjectProp prop{};
+  prop.numDevices = (unsigned)n.n_ranks;
+  prop.handleTypes = CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR;
+  size_t gran = 0;
+  prop.size = (size_t)n_floats * 4;
+  if (ok) ok = d.cuMulticastGetGranularity(&gran, &prop, CU_MULTICAST_GRANULARITY_RECOMMENDED) == CUDA_SUCCESS && gran > 0;
+  if (!comm_all_ok(n, ok)) return nullptr;
+  const size_t bytes = ((size_t)n_floats * 4 + gran - 1) / gran * gran;
+  prop.size = bytes;
+
+  // 1. the multicast object: created by rank 0, imported by the others through a file descriptor passed over an abstract unix socket
+  CUmemGenericAllocationHandle mc = 0;
+  uint64_t token = 0;
+  int listener = -1;
+  if (n.rank == 0) {
+    ok = d.cuMulticastCreate(&mc, &prop) == CUDA_SUCCESS;
+    if (ok) {
+      timespec ts;
+      clock_gettime(CLOCK_REALTIME, &ts);
+      token = ((uint64_t)getpid() << 32) ^ (uint64_t)ts.tv_nsec ^ ((uint64_t)ts.tv_sec << 20) ^ (uint64_t)r.next_uid;
+      listener = socket(AF_UNIX, SOCK_STREAM, 0);
+      socklen_t len = 0;
+      sockaddr_un addr = abstract_address(token, &len);
+      ok = listener >= 0 && bind(listener, (sockaddr*)&addr, len) == 0 && listen(listener, n.n_ranks) == 0;
+    }
+    if (!ok) token = 0;
+  }
+  token = comm_broadcast_u64(n, token);  // 0 = rank 0 could not create / listen: everybody falls back
+  if (token == 0) {
+    if (listener >= 0) close(listener);
+    if (mc) d.cuMemRelease(mc);
+    return nullptr;
+  }
+  if (n.rank == 0) {
+    int fd = -1;
+    ok = d.cuMemExportToShareableHandle(&fd, mc, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR, 0) == CUDA_SUCCESS;
+    for (int peer = 1; peer < n.n_ranks; ++peer) {
+      int c = accept(listener, nullptr, nullptr);
+      if (c < 0 || !ok || send_fd(c, fd) != 0) ok = false;
+      if (c >= 0) close(c);
+    }
+    if (fd >= 0) close(fd);
+    close(listener);
+  } else {
+    int sock = socket(AF_UNIX, SOCK_STREAM, 0);
+    socklen_t len = 0;
+    sockaddr_un addr = abstract_address(token, &len);
+    ok = sock >= 0 && connect(sock, (sockaddr*)&addr, len) == 0;  // (rank 0 was listening before the broadcast completed)
+    int fd = ok ? recv_fd(sock) : -1;
+    if (sock >= 0) close(sock);
+    ok = fd >= 0 && d.cuMemImportFromShareableHandle(&mc, (void*)(uintptr_t)fd, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR) == CUDA_SUCCESS;
+    if (fd >= 0) close(fd);
+  }
+  // 2. every device joins; only then may memory be bound
+  if (ok) ok = d.cuMulticastAddDevice(mc, r.dev) == CUDA_SUCCESS;
+  if (!comm_all_ok(n, ok)) {
+    if (mc) d.cuMemRelease(mc);
+    return nullptr;
+  }
+  // 3. this rank's memory (shareable, as an imported multicast object requires), bound at offset 0, and the two mappings
+  CUmemAllocationProp ap{};
+  ap.type = CU_MEM_ALLOCATION_TYPE_PINNED;
+  ap.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+  ap.location.id = r.ordinal;
+  ap.requestedHandleTypes = CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR;
+  CUmemGenericAllocationHandle mem = 0;
+  CUdeviceptr uc = 0, mcva = 0;
+  CUmemAccessDesc access{};
+  access.location = ap.location;
+  access.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+  ok = d.cuMemCreate(&mem, bytes, &ap, 0) == CUDA_SUCCESS;
+  if (ok) ok = d.cuMulticastBindMem(mc, 0, mem, 0, bytes, 0) == CUDA_SUCCESS;
+  if (ok) ok = d.cuMemAddressReserve(&uc, bytes, gran, 0, 0) == CUDA_SUCCESS && d.cuMemMap(uc, bytes, 0, mem, 0) == CUDA_SUCCESS &&
+               d.cuMemSetAccess(uc, bytes, &access, 1) == CUDA_SUCCESS;
+  if (ok) ok = d.cuMemAddressReserve(&mcva, bytes, gran, 0, 0) == CUDA_SUCCESS && d.cuMemMap(mcva, bytes, 0, mc, 0) == CUDA_SUCCESS &&
+               d.cuMemSetAccess(mcva, bytes, &access, 1) == CUDA_SUCCESS;
+  if (!comm_all_ok(n, ok)) {  // (also the barrier: every rank has bound its memory before anybody stores through the multicast address)
+    // (best effort clean-up of a half-built mapping; the process keeps working on the IPC route)
+    if (mcva) d.cuMemAddressFree(mcva, bytes);
+    if (uc) d.cuMemAddressFree(uc, bytes);
+    if (mem) d.cuMemRelease(mem);
+    if (mc) d.cuMemRelease(mc);
+    return nullptr;
+  }
+  Buffer* b = new Buffer();
+  b->ptr = uc;
+  b->mc_ptr = mcva;
+  b->mc_handle = mc;
+  b->mem_handle = mem;
+  b->vmm_bytes = bytes;
+  b->n_floats = n_floats;
+  b->owned = false;  // not pool memory: unmapped and released with the communicator
+  b->uid = r.next_uid++;
+  return b;
+}
+}  // namespace
+
 int cc_comm_symmetric_alloc(uint64_t n_floats, cc_buffer* out) {
   return guarded([&] {
     Lock lock;
@@ -2076,6 +2272,14 @@ int cc_comm_symmetric_alloc(uint64_t n_floats, cc_buffer* out) {
     Nccl& n = r.nccl;
     CC_REQUIRE(out && n_floats > 0, CC_ERR_ILLEGAL_ARGUMENT, "bad symmetric allocation request");
     CC_REQUIRE(n.comm && n.peer_mapped, CC_ERR_ILLEGAL_ARGUMENT, "cc_comm_symmetric_alloc needs cc_comm_enable_peer first");
+    // NVLS first: a multicast mapping lets the fused all-gather send every block ONCE (the switch replicates it) instead of once per peer
+    if (Buffer* mcb = multicast_alloc(n_floats)) {
+      mcb->rc.store(2);  // the caller's handle + the communicator's list
+      r.buffers.insert(mcb);
+      n.symmetric.push_back(mcb);
+      *out = (cc_buffer)(uintptr_t)mcb;
+      return;
+    }
     CUstream s0 = r.streams[0];
     const size_t bytes = ((size_t)n_floats * 4 + 1023) / 1024 * 1024;
     CUdeviceptr mine = 0;
@@ -2120,6 +2324,14 @@ int cc_comm_symmetric_alloc(uint64_t n_floats, cc_buffer* out) {
   });
 }
 
+int cc_buffer_is_multicast(cc_buffer b, int* out) {
+  return guarded([&] {
+    Lock lock;
+    CC_REQUIRE(out, CC_ERR_ILLEGAL_ARGUMENT, "null output");
+    *out = as_buffer(b)->mc_ptr ? 1 : 0;
+  });
+}
+
 int cc_matmul_3xtf32_allgather(cc_buffer a, cc_buffer b, cc_buffer gathered, int64_t m_shard, int64_t n, int64_t k, const cc_event* waits, int n_waits,
                                cc_event* out_event) {
   return guarded([&] {
@@ -2131,7 +2343,7 @@ int cc_matmul_3xtf32_allgather(cc_buffer a, cc_buffer b, cc_buffer gathered, int
     Buffer* bb = as_buffer(b);
     Buffer* gb = as_buffer(gathered);
     CC_REQUIRE(nc.comm && nc.peer_mapped, CC_ERR_ILLEGAL_ARGUMENT, "cc_matmul_3xtf32_allgather needs cc_comm_enable_peer");
-    CC_REQUIRE((int)gb->peers.size() == nc.n_ranks, CC_ERR_ILLEGAL_ARGUMENT, "`gathered` must come from cc_comm_symmetric_alloc");
+    CC_REQUIRE((int)gb->peers.size() == nc.n_ranks || gb->mc_ptr, CC_ERR_ILLEGAL_ARGUMENT, "`gathered` must come from cc_comm_symmetric_alloc");
     CC_REQUIRE(m_shard > 0 && n > 0 && k > 0 && n % 4 == 0, CC_ERR_UNSUPPORTED, "fused all-gather needs N %% 4 == 0 (got %lld x %lld x %lld)",
                (long long)m_shard, (long long)n, (long long)k);
     CC_REQUIRE(ab->n_floats >= (uint64_t)(m_shard * k) && bb->n_floats >= (uint64_t)(k * n) &&
@@ -2141,7 +2353,7 @@ int cc_matmul_3xtf32_allgather(cc_buffer a, cc_buffer b, cc_buffer gathered, int
     bool launched = false;
     try {
       Op op{0, {ab, bb}, {gb}};  // collectives stay on stream 0, in call order
-      op.label = "contraction 3xTF32 + all-gather epilogue";
+      op.label = gb->mc_ptr ? "contraction 3xTF32 + all-gather epilogue (NVLS multicast stores)" : "contraction 3xTF32 + all-gather epilogue";
       op.flops = 2ull * (uint64_t)m_shard * (uint64_t)n * (uint64_t)k;
       g.declare(op);
       op_begin(op, waits, n_waits);
@@ -2149,9 +2361,10 @@ int cc_matmul_3xtf32_allgather(cc_buffer a, cc_buffer b, cc_buffer gathered, int
       launch_peer_barrier(nc.mb, ++nc.epoch, (cudaStream_t)op.cu());
       GemmWorkspace ws{g.a_hi ? (float*)g.a_hi->ptr : nullptr, g.a_lo ? (float*)g.a_lo->ptr : nullptr, (float*)g.bt_hi->ptr, (float*)g.bt_lo->ptr};
       float* dst[kPeerMaxRanks] = {nullptr};
-      for (int q = 0; q < nc.n_ranks; ++q) dst[q] = (float*)gb->peers[(size_t)q];
+      for (int q = 0; q < nc.n_ranks && q < (int)gb->peers.size(); ++q) dst[q] = (float*)gb->peers[(size_t)q];
       int kernels = launch_gemm_3xtf32_allgather((const float*)ab->ptr, (const float*)bb->ptr, dst, nc.n_ranks, nc.rank, m_shard, n, k, ws,
-                                                 r.info.sm_count, (TensorMapEncodeFn)driver().cuTensorMapEncodeTiled, (cudaStream_t)op.cu(), g.b_ready);
+                                                 r.info.sm_count, (TensorMapEncodeFn)driver().cuTensorMapEncodeTiled, (cudaStream_t)op.cu(), g.b_ready,
+                                                 (float*)gb->mc_ptr);
       // ... exit barrier: every rank's blocks have landed in every copy
       launch_peer_barrier(nc.mb, ++nc.epoch, (cudaStream_t)op.cu());
       launched = true;
@@ -2468,7 +2681,7 @@ int cc_shard_launch_allgather(cc_kernel h, const cc_buffer* args, int n_args, cc
                (unsigned long long)gb->n_floats, ranks, (unsigned long long)n);
     M = p.M, N = p.N, K = p.K;
     fuse = p.kind == PLAN_CONTRACTION && !p.gathered_panels && n_args == 2 && nc.comm && nc.peer_mapped && nc.peer_enabled &&
-           (int)gb->peers.size() == nc.n_ranks && N % 4 == 0;
+           ((int)gb->peers.size() == nc.n_ranks || gb->mc_ptr) && N % 4 == 0;
   });
   if (st != CC_OK) return st;
   if (out_fused) *out_fused = fuse ? 1 : 0;

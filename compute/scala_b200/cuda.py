@@ -108,6 +108,7 @@ def _L():
         L.cc_allgather.argtypes = [h, h, u64, hp, C.c_int, hp]
         L.cc_broadcast.argtypes = [h, u64, C.c_int, hp, C.c_int, hp]
         L.cc_buffer_copy.argtypes = [h, h, u64, hp, C.c_int, hp]
+        L.cc_buffer_is_multicast.argtypes = [h, C.POINTER(C.c_int)]
         L.cc_kernel_cache_lookup.argtypes = [C.c_void_p, u64, C.c_int, hp]
         L.cc_comm_generation.argtypes = [hp]
         L.cc_shard_rows.argtypes = [C.c_int64, C.c_int, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
@@ -321,6 +322,13 @@ class Buffer:
         p = u64()
         check(_L().cc_buffer_length(self.handle, C.byref(p)))
         return p.value
+
+    @property
+    def is_multicast(self) -> bool:
+        """a symmetric buffer with an NVLS multicast mapping (cc_comm_symmetric_alloc on an NVSwitch system)"""
+        out = C.c_int()
+        check(_L().cc_buffer_is_multicast(self.handle, C.byref(out)))
+        return bool(out.value)
 
     def share(self) -> "Buffer":
         """another handle object on the same device buffer (DeviceBuffer.retain, OpenCL.scala:644)"""

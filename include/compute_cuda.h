@@ -287,6 +287,11 @@ int cc_allreduce_sum(cc_buffer buf, uint64_t n_floats, const cc_event* waits, in
 /* Symmetric memory: every rank allocates `n_floats` and maps every other rank's allocation (CUDA IPC over NVLink). Collective;
  * needs cc_comm_enable_peer. The handle behaves like any cc_buffer; the memory itself lives until cc_comm_destroy. */
 int cc_comm_symmetric_alloc(uint64_t n_floats, cc_buffer* out);
+/* *out = 1 if the symmetric buffer also has an NVLS multicast mapping (NVSwitch systems with multicast support: the allocation binds every
+ * rank's memory to one multicast object, so a store through that mapping is replicated into every rank's copy by the switch and the
+ * fused all-gather sends each block once instead of once per peer), 0 if it is mapped peer by peer over CUDA IPC. CC_MULTICAST=0 (on every
+ * rank) forces the peer-by-peer mapping. */
+int cc_buffer_is_multicast(cc_buffer b, int* out);
 /* The row-sharded matmul (A and C row-sharded, B replicated) fused with the all-gather of its result in ONE tensor-core
  * kernel: rank r computes C[r*m_shard .. (r+1)*m_shard, :] = A_shard * B and the epilogue TMA-stores every 32x32 block straight into
  * `gathered` ([n_ranks * m_shard, N], from cc_comm_symmetric_alloc) on EVERY rank — its own HBM and the peers' over NVLink — so the

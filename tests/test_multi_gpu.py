@@ -26,8 +26,10 @@ def _axis_sum(x, axis):
     return acc
 
 
-def _worker(rank, world, port):
+def _worker(rank, world, port, multicast):
     import torch.distributed as dist
+
+    os.environ["CC_MULTICAST"] = "1" if multicast else "0"  # NVLS multicast stores, or one store per peer over CUDA IPC mappings
 
     from compute.scala_b200 import cuda, sharding
     from oracle import reference as ref
@@ -100,6 +102,11 @@ def _worker(rank, world, port):
             A2, B2 = cuda.Buffer.from_host(a[ms : ms + mn]), cuda.Buffer.from_host(b)
             want = (a.astype(np.float64) @ b.astype(np.float64)).astype(np.float32)
             comm._require_equal_blocks(mn * nn)  # (its one-off agreement exchange is a kernel too: keep it out of the launch counts below)
+            arena = comm.gather_arena(mn * nn * world)
+            if not multicast:
+                assert not arena.is_multicast
+            elif rank == 0:
+                print("symmetric arena has an NVLS multicast mapping:", arena.is_multicast)
             for rep, config in enumerate((None, None, "512", "256", "64")):  # back to back: the entry barrier protects the arena
                 # every tile configuration of the gather epilogue: CTA pairs (cta_group::2) and single CTAs
                 if config:
@@ -182,10 +189,11 @@ def _api_level(cuda, comm, sharding, ref, rank, world):
         assert "equal blocks" in str(e)
 
 
-def test_sharded_reductions_and_matmul_two_gpus():
+@pytest.mark.parametrize("multicast", [True, False], ids=["nvls-multicast", "ipc-peer-stores"])
+def test_sharded_reductions_and_matmul_two_gpus(multicast):
     import torch
     import torch.multiprocessing as mp
 
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (run under `gpurun --gpus 2`)")
-    mp.spawn(_worker, args=(2, _free_port()), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, _free_port(), multicast), nprocs=2, join=True)
