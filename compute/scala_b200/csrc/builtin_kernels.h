@@ -52,6 +52,7 @@ struct GemmWorkspace {
   float* a_lo;   // [M,Kp]  tf32(A - a_hi)
   float* bt_hi;  // [N,Kp]  tf32_trunc(B)^T
   float* bt_lo;  // [N,Kp]  tf32(B - b_hi)^T
+  float* k_split_partials = nullptr;  // [gemm_k_splits, M, N] when the launcher may split K over CTA pairs (small products), else null
 };
 // K rounded up to the pipeline's K step (32 floats): the row length of the four workspace panels
 int64_t gemm_padded_k(int64_t k);
@@ -63,6 +64,9 @@ int gemm_pick_bn(int64_t m, int64_t n, int sm_count);
 // matrix and split inside the kernel through tensor memory (no A panels: ws.a_hi / ws.a_lo may be null). CC_GEMM_FORCE_CONFIG and
 // CC_GEMM_TMEM_A=0 are honoured here.
 int gemm_config_for(const float* a, int64_t m, int64_t n, int64_t k, int sm_count, bool gather_epilogue);
+// config 1024 only: how many ways K is split so that a product of few tiles still fills the CTA pairs (1 = not split); the caller then
+// provides ws.k_split_partials with room for that many M x N partial results, which a second kernel adds in a fixed order
+int gemm_k_splits(int64_t m, int64_t n, int64_t k, int sm_count);
 typedef CUresult (*TensorMapEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                       const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                       CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);

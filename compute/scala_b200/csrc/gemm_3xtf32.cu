@@ -710,7 +710,8 @@ __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.
 template <int BN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TA_THREADS, 1)
 gemm_3xtf32_tmema_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
-                         float* __restrict__ C, int M, int N, int Kp, int tiles_pm, int tiles_n, int kb_begin, int accumulate) {
+                         float* __restrict__ C, int M, int N, int Kp, int tiles_pm, int tiles_n, int kb_begin, int accumulate, int splits,
+                         long long split_stride) {
   constexpr int ACCS = TaCfg<BN>::ACCS;
   constexpr int B_HALF_BYTES = TaCfg<BN>::B_HALF_BYTES;
   constexpr int STAGE_BYTES = TaCfg<BN>::STAGE_BYTES;
@@ -733,8 +734,17 @@ gemm_3xtf32_tmema_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
   const uint32_t rank = cluster_ctarank();  // 0 = leader
   const int pair = blockIdx.x >> 1;
   const int num_pairs = gridDim.x >> 1;
-  const int num_tiles = tiles_pm * tiles_n;
-  const int num_kb = Kp / BK;
+  // Work units: (tile, K split). With `splits` > 1 a tile's K range is cut into that many pieces, each computed by another pair into its own
+  // partial result (C + split * split_stride) and summed afterwards in a fixed order: small products (1024^3 is 16 tiles for 74 pairs)
+  // fill the machine without giving up determinism.
+  const int num_tiles = tiles_pm * tiles_n * splits;
+  const int total_kb = Kp / BK;
+  const int kb_per_split = (total_kb + splits - 1) / splits;
+  auto unit_kb = [&](int unit, int& first) {
+    const int sp = unit % splits;
+    first = kb_begin + sp * kb_per_split;
+    return min(kb_per_split, total_kb - sp * kb_per_split);
+  };
 
   if (warp == 0 && lane == 0) {
     prefetch_tensormap(&tm_a);
@@ -769,19 +779,20 @@ gemm_3xtf32_tmema_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = pair; tile < num_tiles; tile += num_pairs) {
-        int m_blk, n_blk;
-        tile_coords(tile, tiles_pm, tiles_n, m_blk, n_blk);
+        int m_blk, n_blk, kb_first;
+        tile_coords(tile / splits, tiles_pm, tiles_n, m_blk, n_blk);
+        const int num_kb = unit_kb(tile, kb_first);
         const int row_a = m_blk * 256 + (int)rank * 128;
         const int row_b = n_blk * BN + (int)rank * (BN / 2);
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1);
           const uint32_t st = smem_base + stage * STAGE_BYTES;
           mbar_arrive_expect_tx(a_full_bar(stage), TA_A_RAW_BYTES);
-          tma_load_2d(st, &tm_a, a_full_bar(stage), (kb_begin + kb) * BK, row_a);
+          tma_load_2d(st, &tm_a, a_full_bar(stage), (kb_first + kb) * BK, row_a);
           const uint32_t leader_b_full = map_to_cta(b_full_bar(stage), 0);
           if (rank == 0) mbar_arrive_expect_tx(b_full_bar(stage), 2 * 2 * B_HALF_BYTES);
-          tma_load_2d_pair(st + TA_A_RAW_BYTES, &tm_b_hi, leader_b_full, (kb_begin + kb) * BK, row_b);
-          tma_load_2d_pair(st + TA_A_RAW_BYTES + B_HALF_BYTES, &tm_b_lo, leader_b_full, (kb_begin + kb) * BK, row_b);
+          tma_load_2d_pair(st + TA_A_RAW_BYTES, &tm_b_hi, leader_b_full, (kb_first + kb) * BK, row_b);
+          tma_load_2d_pair(st + TA_A_RAW_BYTES + B_HALF_BYTES, &tm_b_lo, leader_b_full, (kb_first + kb) * BK, row_b);
           if (++stage == TA_STAGES) {
             stage = 0;
             phase ^= 1;
@@ -800,6 +811,8 @@ gemm_3xtf32_tmema_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
       mbar_wait(tmem_empty_bar(acc), acc_phase ^ 1);
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+      int kb_first;
+      const int num_kb = unit_kb(tile, kb_first);
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(b_full_bar(stage), phase);   // both halves of B have landed
         mbar_wait(a_ready_bar(stage), phase);  // both CTAs' converters have written this stage's A into tensor memory
@@ -834,10 +847,10 @@ gemm_3xtf32_tmema_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
     const int cw = (warp - 8) & 3;  // TMEM lanes [32 * cw, 32 * cw + 32) = rows of the A tile
     const int row = cw * 32 + lane;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(cw * 32) << 16) + TA_A_COL0;
-    const long long total_kb = 0;
-    (void)total_kb;
     long long j = 0;  // k blocks this CTA has seen, over all its tiles
     for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+      int kb_first;
+      const int num_kb = unit_kb(tile, kb_first);
       for (int kb = 0; kb < num_kb; ++kb, ++j) {
         if ((int)(j & 1) != group) continue;
         const int stage = (int)(j % TA_STAGES);
@@ -872,7 +885,7 @@ gemm_3xtf32_tmema_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
     int it = 0;
     for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
       int m_blk, n_blk;
-      tile_coords(tile, tiles_pm, tiles_n, m_blk, n_blk);
+      tile_coords(tile / splits, tiles_pm, tiles_n, m_blk, n_blk);
       const int acc = ACCS == 2 ? (it & 1) : 0;
       const uint32_t acc_phase = ACCS == 2 ? ((it >> 1) & 1) : (it & 1);
       mbar_wait(tmem_full_bar(acc), acc_phase);
@@ -880,7 +893,7 @@ gemm_3xtf32_tmema_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
       const int row = m_blk * 256 + (int)rank * 128 + ew * 32 + lane;
       const int col0 = n_blk * BN;
       const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * BN);
-      float* out = C + (size_t)row * (size_t)N + (size_t)col0;
+      float* out = C + (size_t)(tile % splits) * (size_t)split_stride + (size_t)row * (size_t)N + (size_t)col0;
       const bool row_ok = row < M;
       const bool vec_ok = (N & 3) == 0;
 #pragma unroll 1
@@ -1000,7 +1013,8 @@ int64_t gemm_padded_k(int64_t k) { return (k + BK - 1) / BK * BK; }
 // Tile configuration for an M x N problem: 256 x 256 on CTA pairs, or 128 x {256, 128, 64} on single CTAs. Cost model = waves x
 // (tile time per SM) with the tensor-pipe efficiencies ncu measured for each variant (profiles/README.md): the wide tiles are the
 // most efficient per flop, the narrow ones fill the SMs on small problems.
-int gemm_pick_config(int64_t m, int64_t n, int sm_count, bool allow_pair) {
+namespace {
+int pick_config_and_cost(int64_t m, int64_t n, int sm_count, bool allow_pair, double* cost_out) {
   struct Cand {
     int code, bm, bn, units_div;
     double eff;
@@ -1019,8 +1033,18 @@ int gemm_pick_config(int64_t m, int64_t n, int sm_count, bool allow_pair) {
       best = c.code;
     }
   }
+  if (cost_out) *cost_out = best_cost;
   return best;
 }
+// waves x columns per SM / efficiency of the best unsplit configuration (the unit of the picker's cost model)
+double gemm_direct_cost(int64_t m, int64_t n, int sm_count, bool allow_pair) {
+  double cost;
+  pick_config_and_cost(m, n, sm_count, allow_pair, &cost);
+  return cost;
+}
+}  // namespace
+
+int gemm_pick_config(int64_t m, int64_t n, int sm_count, bool allow_pair) { return pick_config_and_cost(m, n, sm_count, allow_pair, nullptr); }
 
 int gemm_pick_bn(int64_t m, int64_t n, int sm_count) {
   const int c = gemm_pick_config(m, n, sm_count, false);
@@ -1031,12 +1055,39 @@ namespace {
 bool tmema_default();
 }
 
+// K splits for the tensor-memory-A kernel (256 x 256 pair tiles): the count (<= 8, each split at least 256 deep — below that the pipeline fill
+// and the epilogue dominate a unit) the time model below expects to beat every unsplit configuration by 5 %, else 1 = no split.
+int gemm_k_splits(int64_t m, int64_t n, int64_t k, int sm_count) {
+  if (const char* e = getenv("CC_GEMM_K_SPLITS")) return std::max(1, atoi(e));
+  if (k < 512) return 1;
+  // Time model in microseconds, fitted to graph replays on a B200 (profiles/r02_gemm_split_k.md): a launch costs its waves x the K range of a
+  // unit x the tile's columns per SM / the variant's tensor-pipe efficiency, plus a fixed part (launch, pipeline fill, epilogue); splitting
+  // adds the second launch and one pass over the partials (mostly in L2).
+  constexpr double kUsPerColumnK = 1.05e-4, kFixedUs = 5.5, kSumLaunchUs = 3.5, kSumBytesPerUs = 4e6;
+  const int64_t pairs = std::max(1, sm_count / 2);
+  const int64_t tiles = ((m + 255) / 256) * ((n + 255) / 256);
+  const double direct = gemm_direct_cost(m, n, sm_count, m > BM) * (double)k * kUsPerColumnK + kFixedUs;
+  int best_splits = 1;
+  double best = direct * 0.95;  // (a split must win clearly: the model is good to 5 - 10 %)
+  for (int s = 2; s <= 8 && k / s >= 256; ++s) {
+    const int64_t waves = (tiles * s + pairs - 1) / pairs;
+    const int64_t k_unit = ((k + BK - 1) / BK + s - 1) / s * BK;
+    const double cost = (double)waves * (double)k_unit * (256.0 / 0.92) * kUsPerColumnK + kFixedUs + kSumLaunchUs +
+                        (double)(s + 1) * (double)m * (double)n * 4.0 / kSumBytesPerUs;
+    if (cost < best) best = cost, best_splits = s;
+  }
+  return best_splits;
+}
+
 int gemm_config_for(const float* a, int64_t m, int64_t n, int64_t k, int sm_count, bool gather_epilogue) {
   // CC_GEMM_FORCE_CONFIG = 1024 | 512 | 256 | 128 | 64 pins the tile configuration (tests run every variant on the same shapes)
   int config = gemm_pick_config(m, n, sm_count, true);
   // 1024 = A through tensor memory: needs the original A (not pre-gathered panels), a TMA-able row pitch and more than one CTA of rows
   const bool tmema_ok = !gather_epilogue && a && (k & 3) == 0 && ((uintptr_t)a & 15) == 0 && m > BM;
   if (config == 512 && tmema_ok && tmema_default()) config = 1024;
+  // a product of few tiles: the tensor-memory-A kernel with K split over the CTA pairs beats a narrow-tile configuration that fills the SMs
+  // with inefficient tiles (1024^3: 16 tiles of 256 x 256, 4 splits -> 64 units for 74 pairs)
+  if (config != 1024 && tmema_ok && tmema_default() && gemm_k_splits(m, n, k, sm_count) > 1) config = 1024;
   if (const char* force = getenv("CC_GEMM_FORCE_CONFIG")) {
     const int f = atoi(force);
     if (f == 256 || f == 128 || f == 64 || (f == 512 && m > BM) || (f == 1024 && tmema_ok)) config = f;
@@ -1102,12 +1153,31 @@ void launch_pair(const GemmWorkspace& ws, float* c, int64_t m, int64_t n, int64_
   check_launch(kGather ? "gemm_3xtf32 (CTA pairs, all-gather epilogue)" : "gemm_3xtf32 (CTA pairs)");
 }
 
+// C = sum over s of partial[s] (fixed order: deterministic), 128-bit vectors; n is a multiple of 4 or the tail runs scalar
+__global__ void __launch_bounds__(256) sum_k_splits_kernel(const float* __restrict__ partials, float* __restrict__ c, size_t n, int splits, size_t stride) {
+  const size_t nvec = n / 4;
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < nvec; i += (size_t)gridDim.x * 256) {
+    float4 acc = __ldcs(reinterpret_cast<const float4*>(partials) + i);
+    for (int sp = 1; sp < splits; ++sp) {
+      const float4 v = __ldcs(reinterpret_cast<const float4*>(partials + (size_t)sp * stride) + i);
+      acc.x += v.x, acc.y += v.y, acc.z += v.z, acc.w += v.w;
+    }
+    __stcs(reinterpret_cast<float4*>(c) + i, acc);
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+    const size_t i = (n & ~(size_t)3) + threadIdx.x;
+    float acc = partials[i];
+    for (int sp = 1; sp < splits; ++sp) acc += partials[(size_t)sp * stride + i];
+    c[i] = acc;
+  }
+}
+
 // config 1024: CTA pairs, 256 x 256 tiles (one accumulator), A read as the original fp32 matrix and split inside the kernel (through tensor
 // memory). (The kernel also instantiates for 256 x 128 tiles with two accumulators; measured at 8192^3: 211 TFLOP/s, tensor pipe 56 % —
 // 128-column MMAs are too short to keep the pipe busy — against 304 for 256 x 256, so only the wide tile is dispatched.)
 template <int BN>
-void launch_tmema(const float* a, const GemmWorkspace& ws, float* c, int64_t m, int64_t n, int64_t k, int64_t kp, int sm_count, TensorMapEncodeFn encode,
-                  cudaStream_t stream, int64_t kb_begin = 0, int64_t kb_count = -1) {
+int launch_tmema(const float* a, const GemmWorkspace& ws, float* c, int64_t m, int64_t n, int64_t k, int64_t kp, int sm_count, TensorMapEncodeFn encode,
+                  cudaStream_t stream, int64_t kb_begin = 0, int64_t kb_count = -1, int splits = 1) {
   constexpr int SMEM = TaCfg<BN>::SMEM_BYTES;
   static bool attr_set = false;
   if (!attr_set) {
@@ -1123,9 +1193,28 @@ void launch_tmema(const float* a, const GemmWorkspace& ws, float* c, int64_t m, 
   int pairs = tiles_pm * tiles_n;
   if (pairs > sm_count / 2) pairs = sm_count / 2;
   const int64_t kbs = kb_count < 0 ? kp / BK : kb_count;
+  if (splits > 1) {
+    // every (tile, K split) unit goes to its own pair and writes its own partial result; the partials are then added in split order by a
+    // second kernel. (Adding them in the same launch — the units of a tile meeting on a counter, each summing a slice of rows — measured
+    // slower: 1024^3 23.7 us against 21.2 us replayed from a graph, profiles/r02_gemm_split_k.md; the waiting units idle their SMs.)
+    CC_REQUIRE(ws.k_split_partials, CC_ERR_ILLEGAL_ARGUMENT, "split-K needs a partials workspace");
+    pairs = tiles_pm * tiles_n * splits;
+    if (pairs > sm_count / 2) pairs = sm_count / 2;
+    const size_t out_floats = (size_t)m * (size_t)n;
+    gemm_3xtf32_tmema_kernel<BN><<<2 * pairs, TA_THREADS, SMEM, stream>>>(ma, mb_hi, mb_lo, ws.k_split_partials, (int)m, (int)n, (int)(kbs * BK), tiles_pm, tiles_n,
+                                                                          (int)kb_begin, 0, splits, (long long)out_floats);
+    check_launch("gemm_3xtf32 (CTA pairs, A through tensor memory, split K)");
+    size_t blocks = (out_floats / 4 + 255) / 256;
+    if (blocks > (size_t)sm_count * 8) blocks = (size_t)sm_count * 8;
+    if (blocks == 0) blocks = 1;
+    sum_k_splits_kernel<<<(unsigned)blocks, 256, 0, stream>>>(ws.k_split_partials, c, out_floats, splits, out_floats);
+    check_launch("sum_k_splits");
+    return 2;
+  }
   gemm_3xtf32_tmema_kernel<BN><<<2 * pairs, TA_THREADS, SMEM, stream>>>(ma, mb_hi, mb_lo, c, (int)m, (int)n, (int)(kbs * BK), tiles_pm, tiles_n, (int)kb_begin,
-                                                                        kb_begin > 0 ? 1 : 0);
+                                                                        kb_begin > 0 ? 1 : 0, 1, 0ll);
   check_launch("gemm_3xtf32 (CTA pairs, A through tensor memory)");
+  return 1;
 }
 
 template <bool kGather>
@@ -1155,12 +1244,14 @@ int launch_pipeline(const float* a, const float* b, float* c, int64_t m, int64_t
   constexpr int64_t kMaxChunkK = 8192;
   const int64_t kb_total = kp / BK;
   const int64_t kb_chunk = kGather ? kb_total : std::min<int64_t>(kb_total, kMaxChunkK / BK);
+  const int k_splits = config == 1024 && ws.k_split_partials ? gemm_k_splits(m, n, k, sm_count) : 1;
   int launches = 0;
   for (int64_t kb0 = 0; kb0 < kb_total; kb0 += kb_chunk, ++launches) {
     const int64_t kbs = std::min<int64_t>(kb_chunk, kb_total - kb0);
     switch (config) {
       case 1024:
-        if constexpr (!kGather) launch_tmema<256>(a, ws, c, m, n, k, kp, sm_count, encode, stream, kb0, kbs);
+        if constexpr (!kGather)
+          launches += launch_tmema<256>(a, ws, c, m, n, k, kp, sm_count, encode, stream, kb0, kbs, kb_total <= kb_chunk ? k_splits : 1) - 1;
         break;
       case 512: launch_pair<kGather>(ws, c, m, n, kp, sm_count, encode, stream, gather, kb0, kbs); break;
       case 256: launch_main<256, kGather>(ws, c, m, n, kp, sm_count, encode, stream, gather, kb0, kbs); break;

@@ -1485,10 +1485,12 @@ namespace {
 // has not been written since its last contraction (weights, the replicated operand of the row-sharded matmul) is split once.
 struct GemmRun {
   Buffer *a_hi = nullptr, *a_lo = nullptr, *bt_hi = nullptr, *bt_lo = nullptr;
+  Buffer* partials = nullptr;  // split-K partial results (small products on the tensor-memory-A kernel)
   bool b_ready = false;
   void declare(Op& op) const {
     if (a_hi) op.writes.push_back(a_hi);  // (none when the kernel splits A itself, through tensor memory)
     if (a_lo) op.writes.push_back(a_lo);
+    if (partials) op.writes.push_back(partials);
     (b_ready ? op.reads : op.writes).push_back(bt_hi);
     (b_ready ? op.reads : op.writes).push_back(bt_lo);
   }
@@ -1514,13 +1516,16 @@ GemmRun gemm_prepare(Buffer* b, int64_t m, int64_t n, int64_t k, const Buffer* a
     if (a_panels) {
       g.a_hi = alloc_buffer((uint64_t)(m * kp));
       g.a_lo = alloc_buffer((uint64_t)(m * kp));
+    } else {
+      const int splits = gemm_k_splits(m, n, k, r.info.sm_count);
+      if (splits > 1) g.partials = alloc_buffer((uint64_t)splits * (uint64_t)m * (uint64_t)n);
     }
     if (!g.b_ready) {
       g.bt_hi = alloc_buffer((uint64_t)(n * kp));
       g.bt_lo = alloc_buffer((uint64_t)(n * kp));
     }
   } catch (...) {
-    for (Buffer* x : {g.a_hi, g.a_lo, g.bt_hi, g.bt_lo})
+    for (Buffer* x : {g.a_hi, g.a_lo, g.bt_hi, g.bt_lo, g.partials})
       if (x) release(x);
     throw;
   }
@@ -1544,12 +1549,14 @@ void gemm_finish(GemmRun& g, Buffer* b, int64_t n, int64_t k, bool launched) {
     g.bt_lo->rc.fetch_add(1);
     r.panel_cache.push_back(Runtime::Panels{b->uid, b->version, k, n, g.bt_hi, g.bt_lo, ++r.panel_clock});
   }
-  for (Buffer* x : {g.a_hi, g.a_lo, g.bt_hi, g.bt_lo})
+  for (Buffer* x : {g.a_hi, g.a_lo, g.bt_hi, g.bt_lo, g.partials})
     if (x) release(x);
 }
 
-void gemm_on_stream(Buffer* a, Buffer* b, Buffer* c, int64_t m, int64_t n, int64_t k, const GemmRun& g, CUstream s) {
-  GemmWorkspace ws{g.a_hi ? (float*)g.a_hi->ptr : nullptr, g.a_lo ? (float*)g.a_lo->ptr : nullptr, (float*)g.bt_hi->ptr, (float*)g.bt_lo->ptr};
+void gemm_on_stream(Buffer* a, Buffer* b, Buffer* c, int64_t m, int64_t n, int64_t k, const GemmRun& g, const Op& op) {
+  CUstream s = op.cu();
+  GemmWorkspace ws{g.a_hi ? (float*)g.a_hi->ptr : nullptr, g.a_lo ? (float*)g.a_lo->ptr : nullptr, (float*)g.bt_hi->ptr, (float*)g.bt_lo->ptr,
+                   g.partials ? (float*)g.partials->ptr : nullptr};
   int launched = launch_gemm_3xtf32((const float*)a->ptr, (const float*)b->ptr, (float*)c->ptr, m, n, k, ws, rt().info.sm_count,
                                     (TensorMapEncodeFn)driver().cuTensorMapEncodeTiled, (cudaStream_t)s, g.b_ready);
   rt().stats.device_kernels += (uint64_t)launched;
@@ -1690,7 +1697,7 @@ int cc_launch(cc_kernel h, const cc_buffer* args, int n_args, cc_buffer out, con
         g.declare(op);
         op_begin(op, waits, n_waits);
         begun = true;
-        gemm_on_stream(in[0], in[1], ob, p.M, p.N, p.K, g, op.cu());
+        gemm_on_stream(in[0], in[1], ob, p.M, p.N, p.K, g, op);
         launched = true;
         r.stats.launches++;
         op_end(op, out_event);
@@ -1807,7 +1814,7 @@ int cc_matmul_3xtf32(cc_buffer a, cc_buffer b, cc_buffer c, int64_t m, int64_t n
       op.bytes = 4ull * (uint64_t)(m * k + k * n + m * n);
       g.declare(op);
       op_begin(op, waits, n_waits);
-      gemm_on_stream(ab, bb, cb, m, n, k, g, op.cu());
+      gemm_on_stream(ab, bb, cb, m, n, k, g, op);
       launched = true;
       rt().stats.launches++;
       op_end(op, out_event);

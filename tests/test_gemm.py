@@ -221,6 +221,27 @@ def test_k_chunks_keep_the_error_at_the_one_chunk_level(cuda, monkeypatch, confi
     assert np.array_equal(run_matmul(cuda, ai, bi), (ai.astype(np.float64) @ bi.astype(np.float64)).astype(np.float32))
 
 
+@pytest.mark.parametrize("m,n,k", [(1024, 1024, 1024), (512, 512, 4096), (700, 300, 1000), (1024, 518, 2052)])
+@pytest.mark.parametrize("splits", [None, 1, 3, 8])
+def test_split_k_on_small_products_is_exact_and_deterministic(cuda, monkeypatch, m, n, k, splits):
+    """a product of few 256 x 256 tiles runs the tensor-memory-A kernel with K split over the CTA pairs, each (tile, split) unit writing its own
+    partial result; the partials are added in split order by a second kernel: exact on integers, the same bits on every run, fp32-accurate on
+    normal data; ragged M / N / K, N % 4 != 0 and uneven splits included (CC_GEMM_K_SPLITS forces a count, None = the launcher's own choice)"""
+    monkeypatch.setenv("CC_GEMM_FORCE_CONFIG", "1024")
+    if splits is not None:
+        monkeypatch.setenv("CC_GEMM_K_SPLITS", str(splits))
+    rng = np.random.default_rng(m + n + k)
+    ai = rng.integers(-4, 5, (m, k)).astype(np.float32)
+    bi = rng.integers(-4, 5, (k, n)).astype(np.float32)
+    assert np.array_equal(run_matmul(cuda, ai, bi), (ai.astype(np.float64) @ bi.astype(np.float64)).astype(np.float32))
+    a = finite_normal(m * k, 9).reshape(m, k)
+    b = finite_normal(k * n, 10).reshape(k, n)
+    first = run_matmul(cuda, a, b)
+    assert accuracy(first, a, b) <= 4e-6
+    for _ in range(3):
+        assert np.array_equal(first.view(np.uint32), run_matmul(cuda, a, b).view(np.uint32))
+
+
 def test_pattern_lowers_to_tcgen05(cuda):
     """matmul written the way benchmarks.scala:188-191 writes it runs on the tensor cores and never materialises i*j*k"""
     T = cuda.Tensor
