@@ -38,7 +38,7 @@ std::unordered_map<std::string, std::string> g_knobs;
 bool g_knobs_sampled = false;
 const char* const kKnobNames[] = {"CC_BATCHED_CONTRACTION", "CC_FUSE_COL_STAGE", "CC_NO_OP_LOOPS", "CC_NO_STENCIL_TILE", "CC_TUNE_CONTRACTION_MIN_MACS",
                                   "CC_TUNE_GRID_MULT", "CC_TUNE_MIN_BLOCKS", "CC_TUNE_MIN_REROLL_TERMS", "CC_TUNE_STENCIL_RT", "CC_TUNE_T_GRID_MULT",
-                                  "CC_TUNE_U", "CC_DISABLE_CONTRACTION"};
+                                  "CC_TUNE_U", "CC_DISABLE_CONTRACTION", "CC_REDUCE_TILE_OWNER", "CC_TUNE_TILE_P", "CC_SMALL_N_MMA"};
 void sample_knobs_locked() {
   g_knobs.clear();
   for (const char* name : kKnobNames)
@@ -874,6 +874,9 @@ struct LoadCtx {
   int V;                 // lanes
   int vdim;              // index dim the lanes run along (-1: none)
   const char* idx_type;  // "int" or "long long"
+  // bounds-tested vector loads are issued unconditionally from a clamped address and the padding is selected afterwards: in the
+  // straight-line body of an unrolled reduction a branch around the load would pin it next to its use, exposing its whole latency
+  bool unconditional = false;
 };
 
 // index expression of source row y for lane `lane` ("" = lane 0 / no lane term)
@@ -978,7 +981,10 @@ void emit_load(Emit& e, const Program& p, int j, const LoadCtx& c, const char* i
   if (!lane_checks && aligned) {
     if (ucond.empty())
       e("%s%s(p%d + o%d, L%d);\n", indent, LD4, L.arg, j, j);
-    else
+    else if (c.unconditional) {
+      e("%sconst bool in%d = %s;\n%s%s(p%d + (in%d ? o%d : (%s)0), L%d);\n", indent, j, ucond.c_str(), indent, LD4, L.arg, j, j, c.idx_type, j);
+      e("%s#pragma unroll\n%sfor (int l = 0; l < 4; ++l) L%d[l] = in%d ? L%d[l] : %s;\n", indent, indent, j, j, j, pad.c_str());
+    } else
       e("%sif (%s) %s(p%d + o%d, L%d); else { L%d[0] = L%d[1] = L%d[2] = L%d[3] = %s; }\n", indent, ucond.c_str(), LD4,
         L.arg, j, j, j, j, j, j, pad.c_str());
     return;
@@ -1565,6 +1571,151 @@ void emit_reduce(Plan& plan, const Program& p, int n_args, const DeviceProps& de
     if (NV * 2 >= (int64_t)dev.sm_count * 2048) S = 1;  // the outputs alone fill the machine: no partials round trip
     const int64_t TCH = (T + S - 1) / S;
     S = (T + TCH - 1) / TCH;
+    // --- tile owner: small trailing output dimension (the filters of the reference's convolution benchmark, benchmarks.scala:463-556 at
+    // :612-630's sizes; the 32 columns of its skinny matmuls). A thread owns ALL F outputs along it (F / 4 vectors), so a load that ignores
+    // that dimension (the translated input) is issued once for F multiply-adds instead of once for 4, and when it runs along the
+    // innermost reduction digit (the channels of an NHWC image) it is fetched as ONE 128-bit vector for four reduction steps. Same terms
+    // in the same order per output as the column owner: bit-identical results.
+    {
+      const int64_t F = odims[no - 1];
+      const int inner = nd - 1;
+      const int NG = (int)(F / 4);
+      std::vector<char> kvec((size_t)nloads, 0);
+      // (CC_REDUCE_TILE_OWNER: 0 = never, 2 = whenever the shape allows, whatever the size -- the emulator tests; default: when the threads
+      // alone fill the machine, which is decided before the column owner would split T over CTAs)
+      const char* knob = plan_knob("CC_REDUCE_TILE_OWNER");
+      const int mode = knob ? atoi(knob) : 1;
+      bool ok = mode != 0 && V == 4 && F >= 4 && F <= 32 && T >= 4 && T <= 4096 && (mode == 2 || NOUT / F >= (int64_t)dev.sm_count * 128);
+      bool any_invariant = false, any_kvec = false;
+      const int cols = nd + 1;
+      for (int j = 0; ok && j < nloads; ++j) {
+        if (in_post(j)) continue;
+        const Load& L = p.loads[j];
+        if (!L.integer) {
+          ok = false;
+          break;
+        }
+        bool lane_free = L.coef[no - 1] == 0;
+        for (int y = 0; y < L.rows; ++y)
+          if (L.M[(size_t)y * cols + (no - 1)] != 0.0) lane_free = false;
+        if (!lane_free) continue;
+        any_invariant = true;
+        bool kv = R >= 1 && p.dims[inner] % 4 == 0 && L.coef[inner] == 1 && L.base % 4 == 0;
+        for (int x = 0; kv && x < nd; ++x)
+          if (x != inner && L.coef[x] % 4 != 0) kv = false;
+        for (int y = 0; kv && y < L.rows; ++y)
+          if ((L.need_lo[y] || L.need_hi[y]) && L.M[(size_t)y * cols + inner] != 0.0) kv = false;
+        if (kv) kvec[(size_t)j] = 1, any_kvec = true;
+      }
+      if (ok && ((NG >= 2 && any_invariant) || any_kvec)) {
+        const int KV = any_kvec ? 4 : 1;
+        // P positions along the next output dimension per thread: a load that ignores it (the weights) then serves P x 4 multiply-adds per
+        // vector, and translated windows along it share their vectors between neighbouring positions (identical loads are merged by the
+        // compiler). ncu on the 3 x 3 / depth 8 / batch 128 convolution: L1 write-back of the (uniform) weight vectors bounds P = 1.
+        int P = 1;
+        if (no >= 2 && any_kvec) {
+          const char* pk = plan_knob("CC_TUNE_TILE_P");
+          for (int cand : {4, 2})
+            if (P == 1 && odims[no - 2] % cand == 0 && NG * cand <= 8 && (mode == 2 || NOUT / F / cand >= (int64_t)dev.sm_count * 128)) P = cand;
+          if (pk) P = std::max(1, atoi(pk));
+          if (odims[no - 2] % P != 0) P = 1;
+        }
+        const int64_t NT = NOUT / F / P;  // threads
+        e("// axis reduction (tile owner): out dims=[");
+        for (int x = 0; x < no; ++x) e("%s%lld", x ? "," : "", (long long)odims[x]);
+        e("] T=%s F=%lld (%d vectors per thread) P=%d kvec=%d idx=%s epilogue=%d fold=%s\n", rd.c_str(), (long long)F, NG, P, KV, IDX, (int)has_post, kind_name(mono));
+        std::string rgdecl, kvdecl;
+        for (int x = no; x < nd; ++x) rgdecl += strprintf("%sconst %s g%d", x > no ? ", " : "", IDX, x);
+        for (int j = 0; j < nloads; ++j)
+          if (kvec[(size_t)j]) kvdecl += strprintf(", const float kv%d", j);
+        // evt: the term at explicit reduction digits for the four lanes from output index g{no-1} on; k-vector loads arrive as values
+        e("__device__ __forceinline__ void evt(%s", rgdecl.c_str());
+        for (int x = 0; x < no; ++x) e(", const %s g%d", IDX, x);
+        e("%s%s, float (&o)[4]) {\n", params.c_str(), kvdecl.c_str());
+        LoadCtx c{4, no - 1, IDX};
+        for (int j = 0; j < nloads; ++j) {
+          if (in_post(j)) continue;
+          if (kvec[(size_t)j])
+            e("  float L%d[4];\n  L%d[0] = L%d[1] = L%d[2] = L%d[3] = kv%d;\n", j, j, j, j, j, j);
+          else
+            emit_load(e, p, j, c, "  ");
+        }
+        e("  #pragma unroll\n  for (int l = 0; l < 4; ++l) {\n");
+        emit_op_list(e, p.ops, "    ", "l", p.results);
+        e("    o[l] = _%d;\n  }\n}\n", p.results[0]);
+        emit_post_fn(4, no - 1);
+        e("extern \"C\" __global__ void __launch_bounds__(128) reduce_cols(%s) {\n", param_list(n_args, true, "dst").c_str());
+        e("  const %s v = (%s)blockIdx.x * 128 + threadIdx.x;\n  if (v >= %lld) return;\n", IDX, IDX, (long long)NT);
+        emit_decode(e, odims, no, IDX, strprintf("v * %lld", (long long)(F * P)).c_str(), "  ");  // (P divides the next dimension: a tile never wraps)
+        if (P > 1) e("  const %s gb_ = g%d;\n", IDX, no - 2);
+        e("  float acc[%d][4];\n  #pragma unroll\n  for (int q = 0; q < %d; ++q)\n    #pragma unroll\n    for (int l = 0; l < 4; ++l) acc[q][l] = %s;\n", NG * P, NG * P, ZERO);
+        std::string ind = "  ";
+        for (int x = no; x < nd; ++x) {
+          const int step = x == inner ? KV : 1;
+          if (T <= 96)
+            e("%s#pragma unroll\n", ind.c_str());
+          else if (x == inner)
+            e("%s#pragma unroll %d\n", ind.c_str(), (int)std::max<int64_t>(1, std::min<int64_t>(8, p.dims[x]) / step));
+          else
+            e("%s#pragma unroll 1\n", ind.c_str());
+          e("%sfor (%s g%d = 0; g%d < %lld; g%d += %d) {\n", ind.c_str(), IDX, x, x, (long long)p.dims[x], x, step);
+          ind += "  ";
+        }
+        // (the k-vectors: in scope g{inner} is the first of the four reduction steps they cover; inside the position loop g{no-2} shadows
+        // the tile's first position with the current one)
+        LoadCtx ck{4, inner, IDX, true};
+        std::string digits, outs, kvpass;
+        for (int x = no; x < nd; ++x) digits += x == inner && KV > 1 ? strprintf("%sg%d + k", x > no ? ", " : "", x) : strprintf("%sg%d", x > no ? ", " : "", x);
+        for (int x = 0; x + 1 < no; ++x) outs += strprintf(", g%d", x);
+        outs += strprintf(", (%s)(4 * q)", IDX);
+        for (int j = 0; j < nloads; ++j)
+          if (kvec[(size_t)j]) kvpass += strprintf(", L%d[k]", j);
+        auto open_positions = [&](std::string& in) {
+          if (P == 1) return;
+          e("%s#pragma unroll\n%sfor (int pp = 0; pp < %d; ++pp) {\n%s  const %s g%d = gb_ + pp;\n", in.c_str(), in.c_str(), P, in.c_str(), IDX, no - 2);
+          in += "  ";
+        };
+        auto close_positions = [&](std::string& in) {
+          if (P == 1) return;
+          in.resize(in.size() - 2);
+          e("%s}\n", in.c_str());
+        };
+        const char* ACC = P == 1 ? "acc[q]" : "acc[pp * %d + q]";
+        const std::string accq = P == 1 ? std::string("acc[q]") : strprintf(ACC, NG);
+        open_positions(ind);
+        for (int j = 0; j < nloads; ++j)
+          if (!in_post(j) && kvec[(size_t)j]) emit_load(e, p, j, ck, ind.c_str());
+        e("%s#pragma unroll\n%sfor (int k = 0; k < %d; ++k) {\n", ind.c_str(), ind.c_str(), KV);
+        e("%s  #pragma unroll\n%s  for (int q = 0; q < %d; ++q) {\n", ind.c_str(), ind.c_str(), NG);
+        e("%s    float x[4];\n%s    evt(%s%s%s%s, x);\n", ind.c_str(), ind.c_str(), digits.c_str(), outs.c_str(), pass.c_str(), kvpass.c_str());
+        e("%s    #pragma unroll\n%s    for (int l = 0; l < 4; ++l) %s[l] = %s;\n", ind.c_str(), ind.c_str(), accq.c_str(), AP(accq + "[l]", "x[l]").c_str());
+        e("%s  }\n%s}\n", ind.c_str(), ind.c_str());
+        close_positions(ind);
+        for (int x = no; x < nd; ++x) {
+          ind.resize(ind.size() - 2);
+          e("%s}\n", ind.c_str());
+        }
+        open_positions(ind);
+        e("%s#pragma unroll\n%sfor (int q = 0; q < %d; ++q) {\n", ind.c_str(), ind.c_str(), NG);
+        if (has_post) e("%s  post(%s%s%s);\n", ind.c_str(), accq.c_str(), outs.c_str(), pass.c_str());
+        if (P == 1)
+          e("%s  cc_stg4(dst + v * %lld + 4 * q, acc[q]);\n%s}\n", ind.c_str(), (long long)F, ind.c_str());
+        else
+          e("%s  cc_stg4(dst + v * %lld + pp * %lld + 4 * q, %s);\n%s}\n", ind.c_str(), (long long)(F * P), (long long)F, accq.c_str(), ind.c_str());
+        close_positions(ind);
+        e("}\n");
+        LaunchSpec ls;
+        ls.entry = "reduce_cols";
+        ls.grid[0] = (uint32_t)((NT + 127) / 128);
+        ls.block[0] = 128;
+        for (int i = 0; i < n_args; ++i) ls.args.push_back(i);
+        ls.args.push_back(ARG_OUT);
+        plan.launches.push_back(ls);
+        plan.note += "; a thread owns the whole trailing output dimension";
+        plan.source += e.s;
+        return;
+      }
+    }
     e("// axis reduction (column owner): out dims=[");
     for (int x = 0; x < no; ++x) e("%s%lld", x ? "," : "", (long long)odims[x]);
     e("] T=%s V=%d splits=%lld chunk=%lld idx=%s epilogue=%d fold=%s\n", rd.c_str(), V, (long long)S, (long long)TCH, IDX, (int)has_post, kind_name(mono));
@@ -1868,6 +2019,107 @@ void emit_post_kernel(Emit& e, const Program& p, int n_args) {
     e("  out[v] = acc[0];\n}\n");
 }
 
+// ---- small-N contraction on warp-level tensor-core MMAs --------------------------------------------------------------------
+//
+// The reference's own convolution benchmark (benchmarks.scala:463-556 at :612-630's sizes: 128 x 32 x 32 pixels, 3 x 3 x 8 taps, 8 filters)
+// and its skinny products are contractions with a tiny N (8 - 32 outputs per row) and a short K (<= 256): far too small for operand panels
+// and the tcgen05 pipeline, and on the FMA pipe they are bound by operand delivery, not arithmetic — ncu on the generated reduction: L1
+// write-back of the weight vectors 59 % busy, FMA pipe 17 %, every output re-reading all K weights. Here a warp keeps ALL of B (hi / lo TF32
+// fragments for every k step and n tile) in registers for its whole life and streams rows of A through `mma.sync.m16n8k8.tf32` (3xTF32:
+// a_lo b_hi + a_hi b_lo + a_hi b_hi, as the large contraction does), so A is read once — straight through its affine map, bounds tests and
+// padding included: an implicit im2col — and B once per warp. K is permuted inside a k step (thread t holds k = 2t, 2t + 1 of both
+// operands) so a thread's two A elements of a row are adjacent in memory.
+// (B must fit in registers: k steps x n tiles x 4 registers; enough rows to fill the SMs with warps that each amortise loading it)
+bool small_n_mma_fits(int64_t M, int64_t N, int64_t K) {
+  if (const char* ev = plan_knob("CC_SMALL_N_MMA"))
+    if (atoi(ev) == 0) return false;
+  const int64_t KS = (K + 7) / 8, NT = (N + 7) / 8;
+  // (odd N — the depth-3 convolutions, N = 3 and K = 27 — was timed too: 4.4 -> 7.9 us, the padded tiles and the runtime index divisions cost
+  // more than the generic reduction's 27 multiply-adds per output)
+  return N >= 4 && N % 2 == 0 && N <= 32 && K >= 8 && KS * NT <= 24 && M >= 4096 && M * N * K >= ((int64_t)1 << 20) && M < ((int64_t)1 << 31) - 16;
+}
+
+bool try_small_n_mma(Plan& plan, const Program& p, int n_args, int la, int lb, int s, int64_t M, int64_t N, int64_t K) {
+  if (!small_n_mma_fits(M, N, K)) return false;
+  const int nd = (int)p.dims.size();
+  const int R = p.n_red, no = nd - R;
+  const int64_t KS = (K + 7) / 8, NT = (N + 7) / 8;
+  if (!p.loads[la].integer || !p.loads[lb].integer) return false;
+  const bool has_post = !p.post_ops.empty() && !p.trivial_post();
+  const char* IDX = pick_idx_type(p, std::max(M * N, M * K));
+  const std::string params = (n_args ? ", " : "") + param_list(n_args, false);
+  const std::string pass = (n_args ? ", " : "") + arg_pass(n_args);
+  Emit e;
+  e("// small-N contraction %lldx%lldx%lld on warp-level MMAs (m16n8k8 TF32, 3xTF32): B in registers (%lld k steps x %lld n tiles), rows of A streamed "
+    "through their affine map; idx=%s epilogue=%d\n", (long long)M, (long long)N, (long long)K, (long long)KS, (long long)NT, IDX, (int)has_post);
+  auto decode = [&](const char* src, int first, int last, const char* indent) {  // flat index -> g{first..last-1} (row-major)
+    e("%s%s r_%d = %s;\n", indent, IDX, first, src);
+    for (int x = last - 1; x > first; --x)
+      e("%sconst %s g%d = r_%d %% (%s)%lld; r_%d /= (%s)%lld;\n", indent, IDX, x, first, IDX, (long long)p.dims[x], first, IDX, (long long)p.dims[x]);
+    e("%sconst %s g%d = r_%d;\n", indent, IDX, first, first);
+  };
+  LoadCtx c1{1, -1, IDX};
+  e("__device__ __forceinline__ float ld_a(const %s m, const %s k%s) {\n  if (m >= (%s)%lld || k >= (%s)%lld) return 0.f;\n", IDX, IDX, params.c_str(), IDX,
+    (long long)M, IDX, (long long)K);
+  decode("m", 0, s, "  ");
+  decode("k", no, nd, "  ");
+  emit_load(e, p, la, c1, "  ");
+  e("  return L%d[0];\n}\n", la);
+  e("__device__ __forceinline__ float ld_b(const %s n, const %s k%s) {\n  if (n >= (%s)%lld || k >= (%s)%lld) return 0.f;\n", IDX, IDX, params.c_str(), IDX,
+    (long long)N, IDX, (long long)K);
+  decode("n", s, no, "  ");
+  decode("k", no, nd, "  ");
+  emit_load(e, p, lb, c1, "  ");
+  e("  return L%d[0];\n}\n", lb);
+  if (has_post) {
+    e("__device__ __forceinline__ float post1(const float acc0, const %s m, const %s n%s) {\n", IDX, IDX, params.c_str());
+    decode("m", 0, s, "  ");
+    decode("n", s, no, "  ");
+    for (size_t j = 0; j < p.loads.size(); ++j)
+      if (j < p.load_in_post.size() && p.load_in_post[j]) emit_load(e, p, (int)j, c1, "  ");
+    emit_op_list(e, p.post_ops, "  ", "0", {p.post_result}, "q", "acc0");
+    e("  return q%d;\n}\n", p.post_result);
+  }
+  const int64_t MT = (M + 15) / 16;
+  e("extern \"C\" __global__ void __launch_bounds__(128) small_n_mma(%s) {\n", param_list(n_args, true, "dst").c_str());
+  e("  const int lane = threadIdx.x & 31, gid = lane >> 2, tig = lane & 3;\n");
+  e("  unsigned bh[%lld][%lld][2], bl[%lld][%lld][2];\n", (long long)KS, (long long)NT, (long long)KS, (long long)NT);
+  e("  #pragma unroll\n  for (int ks = 0; ks < %lld; ++ks)\n    #pragma unroll\n    for (int nt = 0; nt < %lld; ++nt)\n      #pragma unroll\n      for (int r = 0; r < 2; ++r) {\n",
+    (long long)KS, (long long)NT);
+  e("        float h, l;\n        cc_split_tf32(ld_b((%s)(nt * 8 + gid), (%s)(ks * 8 + 2 * tig + r)%s), h, l);\n", IDX, IDX, pass.c_str());
+  e("        bh[ks][nt][r] = __float_as_uint(h);\n        bl[ks][nt][r] = __float_as_uint(l);\n      }\n");
+  e("  for (%s tile = (%s)blockIdx.x * 4 + (threadIdx.x >> 5); tile < (%s)%lld; tile += (%s)gridDim.x * 4) {\n", IDX, IDX, IDX, (long long)MT, IDX);
+  e("    const %s m0 = tile * 16 + gid, m1 = m0 + 8;\n", IDX);
+  e("    float c[%lld][4];\n    #pragma unroll\n    for (int nt = 0; nt < %lld; ++nt) c[nt][0] = c[nt][1] = c[nt][2] = c[nt][3] = 0.f;\n", (long long)NT, (long long)NT);
+  e("    #pragma unroll\n    for (int ks = 0; ks < %lld; ++ks) {\n      const %s k0 = (%s)(ks * 8 + 2 * tig);\n", (long long)KS, IDX, IDX);
+  e("      const float a[4] = {ld_a(m0, k0%s), ld_a(m1, k0%s), ld_a(m0, k0 + 1%s), ld_a(m1, k0 + 1%s)};\n", pass.c_str(), pass.c_str(), pass.c_str(), pass.c_str());
+  e("      unsigned ah[4], al[4];\n      #pragma unroll\n      for (int i = 0; i < 4; ++i) {\n        float h, l;\n        cc_split_tf32(a[i], h, l);\n"
+    "        ah[i] = __float_as_uint(h);\n        al[i] = __float_as_uint(l);\n      }\n");
+  e("      #pragma unroll\n      for (int nt = 0; nt < %lld; ++nt) {\n        cc_mma_tf32_16x8x8(c[nt], al, bh[ks][nt]);\n        cc_mma_tf32_16x8x8(c[nt], ah, bl[ks][nt]);\n"
+    "        cc_mma_tf32_16x8x8(c[nt], ah, bh[ks][nt]);\n      }\n    }\n", (long long)NT);
+  e("    #pragma unroll\n    for (int nt = 0; nt < %lld; ++nt) {\n      const %s n0 = (%s)(nt * 8 + 2 * tig);\n      if (n0 >= (%s)%lld) continue;\n", (long long)NT, IDX, IDX, IDX,
+    (long long)N);
+  e("      #pragma unroll\n      for (int h = 0; h < 2; ++h) {\n        const %s m = h ? m1 : m0;\n        if (m >= (%s)%lld) continue;\n", IDX, IDX, (long long)M);
+  if (has_post)
+    e("        const float2 v = make_float2(post1(c[nt][2 * h], m, n0%s), post1(c[nt][2 * h + 1], m, n0 + 1%s));\n", pass.c_str(), pass.c_str());
+  else
+    e("        const float2 v = make_float2(c[nt][2 * h], c[nt][2 * h + 1]);\n");
+  e("        __stcs(reinterpret_cast<float2*>(dst + (long long)m * %lld + n0), v);\n      }\n    }\n  }\n}\n", (long long)N);
+  plan.source += e.s;
+  LaunchSpec ls;
+  ls.entry = "small_n_mma";
+  ls.grid[0] = (uint32_t)std::min<int64_t>((MT + 3) / 4, 148 * 8);
+  ls.block[0] = 128;
+  for (int i = 0; i < n_args; ++i) ls.args.push_back(i);
+  ls.args.push_back(ARG_OUT);
+  plan.launches.push_back(ls);
+  plan.kind = PLAN_AXIS_REDUCE;
+  plan.flops = 2ull * (uint64_t)M * (uint64_t)N * (uint64_t)K;
+  plan.note += strprintf("; small-N contraction %lldx%lldx%lld on warp-level 3xTF32 MMAs, B in registers%s", (long long)M, (long long)N, (long long)K,
+                         has_post ? ", epilogue in the same kernel" : "");
+  return true;
+}
+
 // Tries to lower the reduction program to gathered panels + the tcgen05 pipeline. Returns false if the shape of the term does not fit.
 bool try_general_contraction(Plan& plan, const Program& p, int n_args) {
   const int nd = (int)p.dims.size();
@@ -1908,6 +2160,7 @@ bool try_general_contraction(Plan& plan, const Program& p, int n_args) {
   for (int x = nb; x < s; ++x) M *= p.dims[x];
   for (int x = s; x < no; ++x) N *= p.dims[x];
   for (int x = no; x < nd; ++x) K *= p.dims[x];
+  if (nb == 0 && try_small_n_mma(plan, p, n_args, la, lb, s, M, N, K)) return true;
   int64_t min_macs = (int64_t)1 << 25;
   if (const char* ev = plan_knob("CC_TUNE_CONTRACTION_MIN_MACS")) min_macs = atoll(ev);
   // the gathered panels cost 8 bytes of HBM traffic per (row, k) each way, so this pays off when N (the reuse of an A row) is large
@@ -2314,7 +2567,9 @@ Plan make_plan(const Tree& t, const DeviceProps& dev) {
         // 16.7 us, 65536x32x32: 16.9 vs 29.1 us, 512^3: 20.9 vs 33.4 us).
         int64_t min_macs = (int64_t)1 << 25;
         if (const char* ev = plan_knob("CC_TUNE_CONTRACTION_MIN_MACS")) min_macs = atoll(ev);
-        const bool worth = M * N * K >= min_macs && N >= 32 && K >= 32;
+        // (few columns and a short K: B fits in a warp's registers -- one generated kernel on warp-level MMAs, no workspace: 65536x32x32
+        // 16.4 -> see profiles/r02_small_n_mma.md)
+        const bool worth = M * N * K >= min_macs && N >= 32 && K >= 32 && !small_n_mma_fits(M, N, K);
         if (a_arg >= 0 && a_arg != b_arg && worth && M < ((int64_t)1 << 31) && N < ((int64_t)1 << 31) && K < ((int64_t)1 << 31) - 32) {
           const int64_t Kp = (K + 31) / 32 * 32;  // gemm_padded_k
           plan.kind = PLAN_CONTRACTION;

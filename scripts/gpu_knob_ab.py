@@ -2,6 +2,8 @@
   python scripts/gpu_knob_ab.py fuse_col     CC_FUSE_COL_STAGE      split axis reductions: second stage inside reduce_cols
   python scripts/gpu_knob_ab.py batched      CC_BATCHED_CONTRACTION batched matmul on the tcgen05 pipeline (one launch per batch)
   python scripts/gpu_knob_ab.py pdl          CC_PDL (default on)    programmatic dependent launch
+  python scripts/gpu_knob_ab.py tile_owner   CC_REDUCE_TILE_OWNER   re-rolled reductions with a small trailing output dimension: a thread owns all of it
+  python scripts/gpu_knob_ab.py small_n      CC_SMALL_N_MMA         small-N contractions (the reference's convolution benchmark sizes) on warp-level MMAs
 Per workload: device time per step (CUDA events around the loop, best of 3), max |a - b| between the arms relative to max |a|.
 Writes gpurun_out/knob_<name>.json.  (scripts/gpu_pdl.py is the earlier, PDL-only version with host submission times.)"""
 import json
@@ -12,7 +14,10 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-KNOBS = {"fuse_col": ("CC_FUSE_COL_STAGE", "0", "1"), "batched": ("CC_BATCHED_CONTRACTION", "0", "1"), "pdl": ("CC_PDL", "0", "1")}
+KNOBS = {"fuse_col": ("CC_FUSE_COL_STAGE", "0", "1"), "batched": ("CC_BATCHED_CONTRACTION", "0", "1"), "pdl": ("CC_PDL", "0", "1"),
+         "tile_owner": ("CC_REDUCE_TILE_OWNER", "0", "1"),
+         # off = the generic re-rolled reduction as it stood before both small-N lowerings
+         "small_n": ("CC_SMALL_N_MMA", "0", "1", {"CC_REDUCE_TILE_OWNER": "0"})}
 
 
 def chain(parts):
@@ -38,19 +43,28 @@ def workloads(name, T):
                 return chain((A.broadcast([b, m, k, n]) * B.reshape([b, 1, k, n]).broadcast([b, m, k, n])).split(2))
             out.append((f"batched matmul {b}x{m}x{k}x{n}", build, 20))
         return out
-    if name.startswith("red_p"):
-        def conv(batch, size, depth, filters):  # benchmarks.scala:463-556
-            x, w, bias = T.random([batch, size, size, depth], seed=1).doCache(), T.random([3, 3, depth, filters], seed=2).doCache(), T.random([filters], seed=3).doCache()
+    if name.startswith("red_p") or name in ("tile_owner", "small_n"):
+        def conv(batch, size, depth, filters, ks=3):  # benchmarks.scala:463-556
+            x, w, bias = T.randomNormal([batch, size, size, depth], seed=1).doCache(), T.randomNormal([ks, ks, depth, filters], seed=2).doCache(), T.randomNormal([filters], seed=3).doCache()
             xs, bs = x.split(3), bias.split(0)
             ws = [[[wc.split(0) for wc in wx.split(0)] for wx in wy.split(0)] for wy in w.split(0)]
 
             def build():
                 outs = []
                 for f in range(filters):
-                    terms = [xs[c].translate([0, dy - 1, dx - 1]) * ws[dy][dx][c][f].broadcast([batch, size, size]) for dy in range(3) for dx in range(3) for c in range(depth)]
-                    outs.append(chain(terms) + bs[f].broadcast([batch, size, size]))
+                    terms = [xs[c].translate([0, dy - ks // 2, dx - ks // 2]) * ws[dy][dx][c][f].broadcast([batch, size, size]) for dy in range(ks) for dx in range(ks) for c in range(depth)]
+                    outs.append(bs[f].broadcast([batch, size, size]) + chain(terms))
                 return T.join(outs)
             return build
+    if name in ("tile_owner", "small_n"):
+        # the reference's own benchmark grid (benchmarks.scala:612-630: kernel 3 / 1, batch 128 / 32, 32 x 32 images, depth 8 / 3) and its skinny products
+        out = [(f"conv {ks}x{ks} batch {b} 32x32 depth {d}", conv(b, 32, d, d, ks), 500) for ks in (3, 1) for b in (128, 32) for d in (8, 3)]
+        out.append(("conv 3x3 batch 64 64x64 depth 16", conv(64, 64, 16, 16), 100))
+        for m, k, n in ((65536, 32, 32), (65536, 8, 8), (8192, 64, 16)):
+            A, B = T.randomNormal([m, k], seed=4).doCache(), T.randomNormal([k, n], seed=5).doCache()
+            out.append((f"matmul {m}x{k}x{n} (split / broadcast / sum)", lambda A=A, B=B, m=m, k=k, n=n: chain((A.broadcast([m, k, n]) * B.reshape([1, k, n]).broadcast([m, k, n])).split(1)), 500))
+        return out
+    if name.startswith("red_p"):
         A, B = T.random([512, 64], seed=4).doCache(), T.random([64, 512], seed=5).doCache()
         return [("conv 3x3 batch 128 32x32 depth 8", conv(128, 32, 8, 8), 500), ("conv 3x3 batch 32 32x32 depth 3", conv(32, 32, 3, 3), 1000),
                 ("conv 3x3 batch 64 64x64 depth 16", conv(64, 64, 16, 16), 100),
@@ -95,11 +109,12 @@ if __name__ == "__main__":
     import numpy as np
 
     name = sys.argv[1]
-    env_name, off, on = KNOBS[name]
+    env_name, off, on = KNOBS[name][:3]
+    off_extra = KNOBS[name][3] if len(KNOBS[name]) > 3 else {}
     res = {}
     for tag, v in (("off", off), ("on", on)):
-        r = subprocess.run([sys.executable, os.path.abspath(__file__), name, "arm"], env=dict(os.environ, ARM=tag, **{env_name: v}), capture_output=True, text=True,
-                           timeout=900)
+        r = subprocess.run([sys.executable, os.path.abspath(__file__), name, "arm"], env=dict(os.environ, ARM=tag, **{env_name: v}, **(off_extra if tag == "off" else {})),
+                           capture_output=True, text=True, timeout=900)
         res[tag] = json.loads(r.stdout.strip().splitlines()[-1]) if r.returncode == 0 else {"error": (r.stderr or r.stdout)[-1500:]}
     if all("error" not in v for v in res.values()):
         res["speedup"], res["max_rel_diff"] = {}, {}
@@ -107,6 +122,7 @@ if __name__ == "__main__":
             res["speedup"][label] = res["off"][label]["us_per_step"] / res["on"][label]["us_per_step"]
             a, b = (np.load(os.path.join(ROOT, "gpurun_out", f"_knob_{t}_{i}.npy")) for t in ("off", "on"))
             res["max_rel_diff"][label] = float(np.abs(a - b).max() / max(1e-30, float(np.abs(a).max())))
+            res.setdefault("bit_identical", {})[label] = bool(np.array_equal(a.view(np.uint32), b.view(np.uint32)))
     for f in os.listdir(os.path.join(ROOT, "gpurun_out")):
         if f.startswith("_knob_"):
             os.remove(os.path.join(ROOT, "gpurun_out", f))

@@ -310,7 +310,7 @@ def convolute(inp, weight, bias):
 
 def test_convolution_is_a_nested_reduction_with_an_epilogue():
     # 3 x 3 x depth terms per output channel, affine in (kernel row, kernel column, channel); `bias + chain` is the epilogue
-    k = convolute(rnd([16, 32, 32, 8], 1), rnd([3, 3, 8, 8], 2), rnd([8], 3)).compile()
+    k = convolute(rnd([2, 32, 32, 8], 1), rnd([3, 3, 8, 8], 2), rnd([8], 3)).compile()
     assert k.info.kind == 1 and k.info.n_args == 3
     src = k.source
     assert "Plus chain of 72 congruent terms re-rolled into a reduction over 3 x 3 x 8 with an elementwise epilogue" in src
@@ -318,6 +318,11 @@ def test_convolution_is_a_nested_reduction_with_an_epilogue():
     assert "cc_ldc4(p1" in src  # the weights are reused by every output pixel: L1-cached loads
     # padding tests survive only where the 3x3 window can leave the image (rows / columns), never on batch or channel
     assert "i0_1 >= 0 && i0_1 < 32 && i0_2 >= 0 && i0_2 < 32" in src and "i0_0" not in src and "i0_3" not in src
+    # many pixels, few filters, short K (the reference's own benchmark sizes, benchmarks.scala:612-630): one kernel on warp-level MMAs with the
+    # weights in registers; the bias epilogue is applied to the accumulator fragments
+    small = convolute(rnd([128, 32, 32, 8], 1), rnd([3, 3, 8, 8], 2), rnd([8], 3)).compile()
+    assert small.info.kind == 1 and small.info.n_launches == 1 and small.info.flops == 2 * 128 * 32 * 32 * 8 * 72
+    assert "small-N contraction 131072x8x72 on warp-level MMAs" in small.source and "cc_mma_tf32_16x8x8" in small.source and "post1(" in small.source
     # large enough (and enough filters to reuse each gathered row): an implicit GEMM over gathered operand panels
     big = convolute(rnd([64, 56, 56, 64], 1), rnd([3, 3, 64, 64], 2), rnd([64], 3)).compile()
     assert big.info.kind == 2 and big.info.n_launches == 4 and big.info.flops == 2 * 64 * 56 * 56 * 64 * 576

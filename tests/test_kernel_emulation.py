@@ -212,6 +212,49 @@ def test_fused_second_stage_of_a_split_axis_reduction(monkeypatch):
         cuda.kernel_cache_clear()
 
 
+def convolute(B, inp, weight, bias):
+    """benchmarks.scala:463-556"""
+    batch, height, width, depth = inp.shape
+    kh, kw, _, filters = weight.shape
+    input_seq = inp.split(3)
+    bias_seq = bias.split(0)
+    outs = []
+    for f, khkwd in enumerate(weight.split(3)):
+        summands = []
+        for oy, kwd in zip(range(-(kh // 2), kh // 2 + 1), khkwd.split(0)):
+            for ox, d in zip(range(-(kw // 2), kw // 2 + 1), kwd.split(0)):
+                for in_c, w_c in zip(input_seq, d.split(0)):
+                    summands.append(in_c.translate([0, oy, ox]) * w_c.broadcast([batch, height, width]))
+        outs.append(bias_seq[f].broadcast([batch, height, width]) + chain(summands))
+    return B.join(outs)
+
+
+def test_tile_owner_small_trailing_output_dimension(monkeypatch):
+    """the reference's own benchmark shapes (benchmarks.scala:612-630: 3 x 3 and 1 x 1 kernels, depth 8 / 3; :196-198 skinny products): a thread
+    owns every output along the small trailing dimension, lane-invariant loads are shared by all of them and fetched as one vector along the
+    innermost reduction digit where that is contiguous"""
+    monkeypatch.setenv("CC_REDUCE_TILE_OWNER", "2")  # (the shapes the emulator can afford are below the size from which it is the default)
+    cuda.kernel_cache_clear()
+    check(lambda B, leaf: convolute(B, leaf([3, 9, 10, 8], 1), leaf([3, 3, 8, 8], 2), leaf([8], 3)), "tile owner): out dims=[3,9,10,8] T=3x3x8 F=8 (2 vectors per thread) P=2 kvec=4", 1)
+    check(lambda B, leaf: convolute(B, leaf([3, 9, 10, 8], 1), leaf([1, 1, 8, 8], 2), leaf([8], 3)), "tile owner", 1)
+    check(lambda B, leaf: convolute(B, leaf([2, 5, 12, 8], 1), leaf([3, 3, 8, 8], 2), leaf([8], 3)), "P=4 kvec=4", 1)  # four positions per thread, window across the tile edge
+    check(lambda B, leaf: convolute(B, leaf([2, 5, 12, 4], 1), leaf([3, 5, 4, 4], 2), leaf([4], 3)), "P=4 kvec=4", 1)  # 3 x 5 window
+    # depth 3 (no vector along the channels), 12 filters = 3 vectors per thread
+    check(lambda B, leaf: convolute(B, leaf([2, 7, 9, 3], 1), leaf([3, 3, 3, 12], 2), leaf([12], 3)), "F=12 (3 vectors per thread) P=1 kvec=1", 1)
+    # depth 3, 3 filters: scalar lanes, the column owner as before
+    check(lambda B, leaf: convolute(B, leaf([2, 7, 9, 3], 1), leaf([3, 3, 3, 3], 2), leaf([3], 3)), "column owner", 1)
+
+    def skinny(B, leaf, m=300, k=16, n=8, fold=None):  # benchmarks.scala:188-191 on a tall A
+        a, b = leaf([m, k], 1), leaf([k, n], 2)
+        prod = a.broadcast([m, k, n]) * b.reshape([1, k, n]).broadcast([m, k, n])
+        return chain(prod.split(1), fold) if fold else chain(prod.split(1))
+    check(skinny, "tile owner", 1)
+    check(lambda B, leaf: skinny(B, leaf, k=10, n=32), "F=32 (8 vectors per thread) P=1 kvec=1", 1)
+    check(lambda B, leaf: skinny(B, leaf, fold=B.max), "fold=Max", 1)
+    monkeypatch.delenv("CC_REDUCE_TILE_OWNER")
+    cuda.kernel_cache_clear()
+
+
 def test_matmul1_join_of_folds_rerolled_twice():
     """benchmarks.scala:176-187: the result's columns are separate left folds over t of A[:, t] * B[t, c] (a scalar broadcast), joined:
     the join is re-rolled into the output dimension c and every fold into a reduction over t -- one kernel, one reduction"""

@@ -536,6 +536,46 @@ def test_convolution_nested_reduction(cuda, batch, size, depth, filters, ks):
         assert np.array_equal(got.reshape(-1).view(np.uint32), lit.view(np.uint32))
 
 
+@pytest.mark.parametrize("batch,size,depth,filters,ks", [(128, 32, 8, 8, 3), (32, 32, 8, 8, 3), (128, 32, 8, 8, 1), (17, 31, 8, 12, 3), (20, 32, 6, 6, 3),
+                                                         (9, 32, 16, 16, 1), (6, 40, 4, 32, 3)])
+def test_convolution_small_n_on_warp_mmas(cuda, batch, size, depth, filters, ks):
+    """the reference's own benchmark sizes (benchmarks.scala:612-630) and ragged relatives: many pixels, few filters, short K. One generated
+    kernel keeps the weights as TF32 hi / lo fragments in registers and streams the pixels through warp-level MMAs (3xTF32): exact on
+    exactly representable data (rows not a multiple of 16, filters not a multiple of 8, K padded to 8 included), <= 1e-5 of |in| |w| on
+    normal data (reductions and matmul), and the lo terms are really there (hi-only would be ~1e-3)"""
+    T = cuda.Tensor
+    rng = np.random.default_rng(batch + size + depth)
+    r = ks // 2
+
+    def direct(inp, w, b):
+        padded = np.zeros((batch, size + 2 * r, size + 2 * r, depth), np.float64)
+        padded[:, r : r + size, r : r + size, :] = inp
+        want = np.zeros((batch, size, size, filters), np.float64) + b
+        mag = np.zeros((batch, size, size, filters), np.float64) + np.abs(b)
+        for ky in range(ks):
+            for kx in range(ks):
+                oy, ox = ky - r, kx - r
+                window = padded[:, r - oy : r - oy + size, r - ox : r - ox + size, :]
+                want += np.einsum("bhwd,df->bhwf", window, w[ky, kx].astype(np.float64))
+                mag += np.einsum("bhwd,df->bhwf", np.abs(window), np.abs(w[ky, kx]).astype(np.float64))
+        return want, mag
+
+    inp = rng.integers(-3, 4, (batch, size, size, depth)).astype(np.float32)
+    w = rng.integers(-3, 4, (ks, ks, depth, filters)).astype(np.float32)
+    b = rng.integers(-8, 9, (filters,)).astype(np.float32) / np.float32(2.0)
+    e = _convolute(T, T(inp), T(w), T(b))
+    kern = e.compile()
+    assert kern.info.kind == 1 and "small-N contraction" in kern.source and "cc_mma_tf32_16x8x8" in kern.source, kern.source[:200]
+    got = e.flatArray().reshape(batch, size, size, filters)
+    assert np.array_equal(got.astype(np.float64), direct(inp, w, b)[0])
+    inp = rng.standard_normal((batch, size, size, depth)).astype(np.float32)
+    w = (rng.standard_normal((ks, ks, depth, filters)) * (1.0 + 2.0**-12)).astype(np.float32)
+    b = rng.standard_normal((filters,)).astype(np.float32)
+    got = _convolute(T, T(inp), T(w), T(b)).flatArray().reshape(batch, size, size, filters)
+    want, mag = direct(inp, w, b)
+    assert (np.abs(got - want) / mag).max() <= 2e-6  # (the bar is 1e-5; fp32 FMA chains of this length sit at ~1e-7)
+
+
 @pytest.mark.parametrize("rows", [64, 4096])  # one CTA covers all of T / partials + second stage (epilogue applied there)
 def test_epilogue_around_an_axis_sum(cuda, rows):
     T = cuda.Tensor
