@@ -2029,14 +2029,15 @@ void emit_post_kernel(Emit& e, const Program& p, int n_args) {
 // a_lo b_hi + a_hi b_lo + a_hi b_hi, as the large contraction does), so A is read once — straight through its affine map, bounds tests and
 // padding included: an implicit im2col — and B once per warp. K is permuted inside a k step (thread t holds k = 2t, 2t + 1 of both
 // operands) so a thread's two A elements of a row are adjacent in memory.
-// (B must fit in registers: k steps x n tiles x 4 registers; enough rows to fill the SMs with warps that each amortise loading it)
+// (B must fit in a warp's registers — k steps x n tiles x 4 registers <= 96 — or, as ready-made fragments, in 48 KB of shared memory; enough
+// rows to fill the SMs with warps that each amortise loading it)
 bool small_n_mma_fits(int64_t M, int64_t N, int64_t K) {
   if (const char* ev = plan_knob("CC_SMALL_N_MMA"))
     if (atoi(ev) == 0) return false;
   const int64_t KS = (K + 7) / 8, NT = (N + 7) / 8;
   // (odd N — the depth-3 convolutions, N = 3 and K = 27 — was timed too: 4.4 -> 7.9 us, the padded tiles and the runtime index divisions cost
   // more than the generic reduction's 27 multiply-adds per output)
-  return N >= 4 && N % 2 == 0 && N <= 32 && K >= 8 && KS * NT <= 24 && M >= 4096 && M * N * K >= ((int64_t)1 << 20) && M < ((int64_t)1 << 31) - 16;
+  return N >= 4 && N % 2 == 0 && N <= 32 && K >= 8 && K <= 256 && KS * NT <= 96 && M >= 4096 && M * N * K >= ((int64_t)1 << 20) && M < ((int64_t)1 << 31) - 16;
 }
 
 bool try_small_n_mma(Plan& plan, const Program& p, int n_args, int la, int lb, int s, int64_t M, int64_t N, int64_t K) {
@@ -2052,6 +2053,7 @@ bool try_small_n_mma(Plan& plan, const Program& p, int n_args, int la, int lb, i
   Emit e;
   e("// small-N contraction %lldx%lldx%lld on warp-level MMAs (m16n8k8 TF32, 3xTF32): B in registers (%lld k steps x %lld n tiles), rows of A streamed "
     "through their affine map; idx=%s epilogue=%d\n", (long long)M, (long long)N, (long long)K, (long long)KS, (long long)NT, IDX, (int)has_post);
+  // (from 25 fragments on B lives in shared memory instead, built once per CTA)
   auto decode = [&](const char* src, int first, int last, const char* indent) {  // flat index -> g{first..last-1} (row-major)
     e("%s%s r_%d = %s;\n", indent, IDX, first, src);
     for (int x = last - 1; x > first; --x)
@@ -2083,11 +2085,21 @@ bool try_small_n_mma(Plan& plan, const Program& p, int n_args, int la, int lb, i
   const int64_t MT = (M + 15) / 16;
   e("extern \"C\" __global__ void __launch_bounds__(128) small_n_mma(%s) {\n", param_list(n_args, true, "dst").c_str());
   e("  const int lane = threadIdx.x & 31, gid = lane >> 2, tig = lane & 3;\n");
-  e("  unsigned bh[%lld][%lld][2], bl[%lld][%lld][2];\n", (long long)KS, (long long)NT, (long long)KS, (long long)NT);
-  e("  #pragma unroll\n  for (int ks = 0; ks < %lld; ++ks)\n    #pragma unroll\n    for (int nt = 0; nt < %lld; ++nt)\n      #pragma unroll\n      for (int r = 0; r < 2; ++r) {\n",
-    (long long)KS, (long long)NT);
-  e("        float h, l;\n        cc_split_tf32(ld_b((%s)(nt * 8 + gid), (%s)(ks * 8 + 2 * tig + r)%s), h, l);\n", IDX, IDX, pass.c_str());
-  e("        bh[ks][nt][r] = __float_as_uint(h);\n        bl[ks][nt][r] = __float_as_uint(l);\n      }\n");
+  const bool b_shared = KS * NT > 24;
+  if (!b_shared) {
+    e("  unsigned bh[%lld][%lld][2], bl[%lld][%lld][2];\n", (long long)KS, (long long)NT, (long long)KS, (long long)NT);
+    e("  #pragma unroll\n  for (int ks = 0; ks < %lld; ++ks)\n    #pragma unroll\n    for (int nt = 0; nt < %lld; ++nt)\n      #pragma unroll\n      for (int r = 0; r < 2; ++r) {\n",
+      (long long)KS, (long long)NT);
+    e("        float h, l;\n        cc_split_tf32(ld_b((%s)(nt * 8 + gid), (%s)(ks * 8 + 2 * tig + r)%s), h, l);\n", IDX, IDX, pass.c_str());
+    e("        bh[ks][nt][r] = __float_as_uint(h);\n        bl[ks][nt][r] = __float_as_uint(l);\n      }\n");
+  } else {
+    // B too large for registers: the CTA builds every lane's fragments {hi0, hi1, lo0, lo1} once, in shared memory (conflict-free 128-bit reads)
+    e("  __shared__ uint4 bfrag[%lld][32];\n", (long long)(KS * NT));
+    e("  for (int i = threadIdx.x; i < %lld; i += 128) {\n    const int f = i >> 5, ln = i & 31, ks = f / %lld, nt = f %% %lld;\n    float h[2], l[2];\n", (long long)(KS * NT * 32),
+      (long long)NT, (long long)NT);
+    e("    #pragma unroll\n    for (int r = 0; r < 2; ++r) cc_split_tf32(ld_b((%s)(nt * 8 + (ln >> 2)), (%s)(ks * 8 + 2 * (ln & 3) + r)%s), h[r], l[r]);\n", IDX, IDX, pass.c_str());
+    e("    bfrag[f][ln] = make_uint4(__float_as_uint(h[0]), __float_as_uint(h[1]), __float_as_uint(l[0]), __float_as_uint(l[1]));\n  }\n  __syncthreads();\n");
+  }
   e("  for (%s tile = (%s)blockIdx.x * 4 + (threadIdx.x >> 5); tile < (%s)%lld; tile += (%s)gridDim.x * 4) {\n", IDX, IDX, IDX, (long long)MT, IDX);
   e("    const %s m0 = tile * 16 + gid, m1 = m0 + 8;\n", IDX);
   e("    float c[%lld][4];\n    #pragma unroll\n    for (int nt = 0; nt < %lld; ++nt) c[nt][0] = c[nt][1] = c[nt][2] = c[nt][3] = 0.f;\n", (long long)NT, (long long)NT);
@@ -2095,8 +2107,12 @@ bool try_small_n_mma(Plan& plan, const Program& p, int n_args, int la, int lb, i
   e("      const float a[4] = {ld_a(m0, k0%s), ld_a(m1, k0%s), ld_a(m0, k0 + 1%s), ld_a(m1, k0 + 1%s)};\n", pass.c_str(), pass.c_str(), pass.c_str(), pass.c_str());
   e("      unsigned ah[4], al[4];\n      #pragma unroll\n      for (int i = 0; i < 4; ++i) {\n        float h, l;\n        cc_split_tf32(a[i], h, l);\n"
     "        ah[i] = __float_as_uint(h);\n        al[i] = __float_as_uint(l);\n      }\n");
-  e("      #pragma unroll\n      for (int nt = 0; nt < %lld; ++nt) {\n        cc_mma_tf32_16x8x8(c[nt], al, bh[ks][nt]);\n        cc_mma_tf32_16x8x8(c[nt], ah, bl[ks][nt]);\n"
-    "        cc_mma_tf32_16x8x8(c[nt], ah, bh[ks][nt]);\n      }\n    }\n", (long long)NT);
+  if (!b_shared)
+    e("      #pragma unroll\n      for (int nt = 0; nt < %lld; ++nt) {\n        cc_mma_tf32_16x8x8(c[nt], al, bh[ks][nt]);\n        cc_mma_tf32_16x8x8(c[nt], ah, bl[ks][nt]);\n"
+      "        cc_mma_tf32_16x8x8(c[nt], ah, bh[ks][nt]);\n      }\n    }\n", (long long)NT);
+  else
+    e("      #pragma unroll\n      for (int nt = 0; nt < %lld; ++nt) {\n        const uint4 bf = bfrag[ks * %lld + nt][lane];\n        const unsigned bh[2] = {bf.x, bf.y}, bl[2] = {bf.z, bf.w};\n"
+      "        cc_mma_tf32_16x8x8(c[nt], al, bh);\n        cc_mma_tf32_16x8x8(c[nt], ah, bl);\n        cc_mma_tf32_16x8x8(c[nt], ah, bh);\n      }\n    }\n", (long long)NT, (long long)NT);
   e("    #pragma unroll\n    for (int nt = 0; nt < %lld; ++nt) {\n      const %s n0 = (%s)(nt * 8 + 2 * tig);\n      if (n0 >= (%s)%lld) continue;\n", (long long)NT, IDX, IDX, IDX,
     (long long)N);
   e("      #pragma unroll\n      for (int h = 0; h < 2; ++h) {\n        const %s m = h ? m1 : m0;\n        if (m >= (%s)%lld) continue;\n", IDX, IDX, (long long)M);
@@ -2115,8 +2131,8 @@ bool try_small_n_mma(Plan& plan, const Program& p, int n_args, int la, int lb, i
   plan.launches.push_back(ls);
   plan.kind = PLAN_AXIS_REDUCE;
   plan.flops = 2ull * (uint64_t)M * (uint64_t)N * (uint64_t)K;
-  plan.note += strprintf("; small-N contraction %lldx%lldx%lld on warp-level 3xTF32 MMAs, B in registers%s", (long long)M, (long long)N, (long long)K,
-                         has_post ? ", epilogue in the same kernel" : "");
+  plan.note += strprintf("; small-N contraction %lldx%lldx%lld on warp-level 3xTF32 MMAs, B in %s%s", (long long)M, (long long)N, (long long)K,
+                         b_shared ? "shared memory" : "registers", has_post ? ", epilogue in the same kernel" : "");
   return true;
 }
 

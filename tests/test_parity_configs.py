@@ -537,7 +537,7 @@ def test_convolution_nested_reduction(cuda, batch, size, depth, filters, ks):
 
 
 @pytest.mark.parametrize("batch,size,depth,filters,ks", [(128, 32, 8, 8, 3), (32, 32, 8, 8, 3), (128, 32, 8, 8, 1), (17, 31, 8, 12, 3), (20, 32, 6, 6, 3),
-                                                         (9, 32, 16, 16, 1), (6, 40, 4, 32, 3)])
+                                                         (9, 32, 16, 16, 1), (6, 40, 4, 32, 3), (8, 64, 16, 16, 3), (5, 40, 28, 24, 3)])
 def test_convolution_small_n_on_warp_mmas(cuda, batch, size, depth, filters, ks):
     """the reference's own benchmark sizes (benchmarks.scala:612-630) and ragged relatives: many pixels, few filters, short K. One generated
     kernel keeps the weights as TF32 hi / lo fragments in registers and streams the pixels through warp-level MMAs (3xTF32): exact on
