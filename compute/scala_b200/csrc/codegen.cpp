@@ -38,7 +38,7 @@ std::unordered_map<std::string, std::string> g_knobs;
 bool g_knobs_sampled = false;
 const char* const kKnobNames[] = {"CC_BATCHED_CONTRACTION", "CC_FUSE_COL_STAGE", "CC_NO_OP_LOOPS", "CC_NO_STENCIL_TILE", "CC_TUNE_CONTRACTION_MIN_MACS",
                                   "CC_TUNE_GRID_MULT", "CC_TUNE_MIN_BLOCKS", "CC_TUNE_MIN_REROLL_TERMS", "CC_TUNE_STENCIL_RT", "CC_TUNE_T_GRID_MULT",
-                                  "CC_TUNE_U", "CC_DISABLE_CONTRACTION", "CC_REDUCE_TILE_OWNER", "CC_TUNE_TILE_P", "CC_SMALL_N_MMA"};
+                                  "CC_TUNE_U", "CC_DISABLE_CONTRACTION", "CC_REDUCE_TILE_OWNER", "CC_TUNE_TILE_P", "CC_SMALL_N_MMA", "CC_TUNE_STENCIL_CTAS"};
 void sample_knobs_locked() {
   g_knobs.clear();
   for (const char* name : kKnobNames)
@@ -1402,9 +1402,11 @@ bool try_emit_stencil_tile(Plan& plan, const Program& p, int n_args, const Devic
   int RT = 4;
   if (const char* ev = plan_knob("CC_TUNE_STENCIL_RT")) RT = std::max(1, std::min(8, atoi(ev)));  // tuning knob
   const int TW = 128;
-  const int TH = 8 * RT;
   const int64_t HX0 = floor4(xmin), HX1 = -floor4(-xmax);  // halo columns rounded outwards to the 16-byte grid
-  const int SH = TH + (int)(ymax - ymin), SW = TW + (int)(HX1 - HX0);
+  const int SW = TW + (int)(HX1 - HX0);
+  while (RT > 1 && 2 * (8 * RT + (int)(ymax - ymin)) * SW * 4 > 48 * 1024) RT /= 2;  // two tile buffers within the static shared-memory limit
+  const int TH = 8 * RT;
+  const int SH = TH + (int)(ymax - ymin);
   const int64_t total = product(p.dims);
   const char* IDX = pick_idx_type(p, total);
   int64_t lead = 1;
@@ -1412,16 +1414,24 @@ bool try_emit_stencil_tile(Plan& plan, const Program& p, int n_args, const Devic
   const int64_t tilesY = (H + TH - 1) / TH, tilesX = (W + TW - 1) / TW;
   const int64_t ntiles = lead * tilesY * tilesX;
   const int64_t grid = std::max<int64_t>(1, std::min<int64_t>(ntiles, 0x7fffffff));
-  (void)dev;
-
   Emit e;
   e("// stencil tile: dims=[");
   for (int x = 0; x < nd; ++x) e("%s%lld", x ? "," : "", (long long)p.dims[x]);
   e("] %d window loads of p%d, dy=[%lld,%lld] dx=[%lld,%lld], tile %dx%d + halo -> shared %dx%d, %d other loads, idx=%s grid=%lld\n", nwin, wa, (long long)ymin,
-    (long long)ymax, (long long)xmin, (long long)xmax, TH, TW, SH, SW, nloads - nwin, IDX, (long long)grid);
-  e("extern \"C\" __global__ void __launch_bounds__(256) jit_kernel(%s) {\n", param_list(n_args, true).c_str());
-  e("  __shared__ __align__(16) float tile[%d][%d];\n", SH, SW);
-  e("  for (%s t_ = blockIdx.x; t_ < (%s)%lld; t_ += gridDim.x) {\n", IDX, IDX, (long long)ntiles);
+    (long long)ymax, (long long)xmin, (long long)xmax, TH, TW, SH, SW, nloads - nwin, IDX, (long long)std::min<int64_t>(ntiles, (int64_t)dev.sm_count * 2));
+  // Persistent CTAs, two tile buffers: while a tile is being computed the next one is already on its way into the other buffer
+  // (cp.async, 16 bytes each, L1 bypassed) — the copy engine-less equivalent of a TMA pipeline, with the halo's out-of-range vectors
+  // (whole vectors: the tile origin, the halo and W are multiples of 4) written as padding by ordinary stores. Before round 2 a CTA
+  // staged, synchronised, computed and exited: with 2 CTAs per SM (registers) the loads of one tile barely overlapped the arithmetic of
+  // another (3 x 3: 0.67 of HBM, 5 x 5: 0.46).
+  int ctas_per_sm = 2;
+  if (const char* ev = plan_knob("CC_TUNE_STENCIL_CTAS")) ctas_per_sm = std::max(1, std::min(4, atoi(ev)));  // tuning knob
+  const int64_t pgrid = std::max<int64_t>(1, std::min<int64_t>(ntiles, (int64_t)dev.sm_count * ctas_per_sm));
+  e("extern \"C\" __global__ void __launch_bounds__(256, %d) jit_kernel(%s) {\n", ctas_per_sm, param_list(n_args, true).c_str());
+  e("  __shared__ __align__(16) float tiles_[2][%d][%d];\n", SH, SW);
+  const std::string pad = flit(padding);
+  // stage(t, buffer): issue the copies of tile t
+  e("  auto stage = [&](const %s t_, float (*tile)[%d]) {\n", IDX, SW);
   e("    %s r_ = t_;\n    const %s c0 = (r_ %% (%s)%lld) * %d; r_ /= (%s)%lld;\n    const %s r0 = (r_ %% (%s)%lld) * %d; r_ /= (%s)%lld;\n", IDX, IDX, IDX,
     (long long)tilesX, TW, IDX, (long long)tilesX, IDX, IDX, (long long)tilesY, TH, IDX, (long long)tilesY);
   for (int x = nd - 3; x >= 0; --x)
@@ -1433,19 +1443,27 @@ bool try_emit_stencil_tile(Plan& plan, const Program& p, int n_args, const Devic
       lead_ok += strprintf(" && g%d + %lld >= 0 && g%d + %lld < %lld", x, (long long)lead_off[(size_t)x], x, (long long)lead_off[(size_t)x], (long long)p.dims[x]);
     lead_base += strprintf(" + (g%d + (%s)%lld) * (%s)%lld", x, IDX, (long long)lead_off[(size_t)x], IDX, (long long)stride[x]);
   }
-  const std::string pad = flit(padding);
   e("    const bool lead_ok = %s;\n    const %s lead_base = %s;\n", lead_ok.c_str(), IDX, lead_base.c_str());
-  // ---- staging: SH rows of SW/4 vectors
-  e("    for (int i_ = threadIdx.x; i_ < %d; i_ += 256) {\n", SH * (SW / 4));
-  e("      const int sy = i_ / %d, sx = (i_ %% %d) * 4;\n", SW / 4, SW / 4);
-  e("      const %s yy = r0 + sy + (%s)%lld;\n      const %s xx = c0 + sx + (%s)%lld;\n", IDX, IDX, (long long)ymin, IDX, IDX, (long long)HX0);
-  e("      float v4[4] = {%s, %s, %s, %s};\n", pad.c_str(), pad.c_str(), pad.c_str(), pad.c_str());
-  e("      if (lead_ok && yy >= 0 && yy < (%s)%lld) {\n", IDX, (long long)H);
-  e("        const float* src = p%d + lead_base + yy * (%s)%lld + xx;\n", wa, IDX, (long long)W);
-  e("        if (xx >= 0 && xx + 3 < (%s)%lld) {\n          cc_ldg4(src, v4);\n        } else {\n", IDX, (long long)W);
-  e("          #pragma unroll\n          for (int l = 0; l < 4; ++l)\n            if (xx + l >= 0 && xx + l < (%s)%lld) v4[l] = cc_ldg(src + l);\n        }\n      }\n", IDX,
-    (long long)W);
-  e("      *reinterpret_cast<float4*>(&tile[sy][sx]) = make_float4(v4[0], v4[1], v4[2], v4[3]);\n    }\n    __syncthreads();\n");
+  // a thread keeps its column vector and walks down the rows (RPP rows per pass): one bounds test and two pointer bumps per copy, no
+  // index division in the loop (the staging loop was a quarter of the 3 x 3 kernel's instructions)
+  const int VPR = SW / 4, RPP = 256 / VPR;
+  e("    const int sy0 = threadIdx.x / %d, sx = (threadIdx.x %% %d) * 4;\n", VPR, VPR);
+  e("    const %s xx = c0 + sx + (%s)%lld;\n    const bool col_ok = lead_ok && xx >= 0 && xx < (%s)%lld;\n", IDX, IDX, (long long)HX0, IDX, (long long)W);
+  e("    if (sy0 < %d) {\n      %s yy = r0 + sy0 + (%s)%lld;\n      const float* src = p%d + lead_base + yy * (%s)%lld + xx;\n      float* dst = &tile[sy0][sx];\n", RPP, IDX,
+    IDX, (long long)ymin, wa, IDX, (long long)W);
+  e("      #pragma unroll\n      for (int sy = sy0; sy < %d; sy += %d, yy += %d, src += (%s)%lld, dst += %d) {\n", SH, RPP, RPP, IDX, (long long)(RPP * W), RPP * SW);
+  e("        if (col_ok && yy >= 0 && yy < (%s)%lld)\n          cc_cp_async16(dst, src);\n        else\n          *reinterpret_cast<float4*>(dst) = make_float4(%s, %s, %s, %s);\n", IDX,
+    (long long)H, pad.c_str(), pad.c_str(), pad.c_str(), pad.c_str());
+  e("      }\n    }\n    cc_cp_async_commit();\n  };\n");
+  e("  int buf_ = 0;\n  if ((%s)blockIdx.x < (%s)%lld) stage((%s)blockIdx.x, tiles_[0]);\n", IDX, IDX, (long long)ntiles, IDX);
+  e("  for (%s t_ = blockIdx.x; t_ < (%s)%lld; t_ += gridDim.x, buf_ ^= 1) {\n", IDX, IDX, (long long)ntiles);
+  e("    float (*tile)[%d] = tiles_[buf_];\n", SW);
+  e("    if (t_ + (%s)gridDim.x < (%s)%lld) {\n      stage(t_ + (%s)gridDim.x, tiles_[buf_ ^ 1]);\n      cc_cp_async_wait<1>();\n    } else {\n      cc_cp_async_wait<0>();\n    }\n    __syncthreads();\n",
+    IDX, IDX, (long long)ntiles, IDX);
+  e("    %s r_ = t_;\n    const %s c0 = (r_ %% (%s)%lld) * %d; r_ /= (%s)%lld;\n    const %s r0 = (r_ %% (%s)%lld) * %d; r_ /= (%s)%lld;\n", IDX, IDX, IDX,
+    (long long)tilesX, TW, IDX, (long long)tilesX, IDX, IDX, (long long)tilesY, TH, IDX, (long long)tilesY);
+  for (int x = nd - 3; x >= 0; --x)
+    e("    const %s g%d = r_ %% (%s)%lld; r_ /= (%s)%lld;\n", IDX, x, IDX, (long long)p.dims[x], IDX, (long long)p.dims[x]);
   // ---- compute: a thread owns RT rows x 4 adjacent columns. It pulls the RT + (ymax - ymin) rows of covering aligned vectors out of
   // shared memory once (conflict-free 128-bit reads; a row is shared by the RT outputs above and below it, which is what takes the
   // shared-memory pipe off the critical path: ncu showed it 75 % busy with one row of outputs per thread) and every window position
@@ -1455,6 +1473,8 @@ bool try_emit_stencil_tile(Plan& plan, const Program& p, int n_args, const Devic
   e("    {\n      const int ly0 = (threadIdx.x / %d) * %d, lx = (threadIdx.x %% %d) * 4;\n", TW / 4, RT, TW / 4);
   e("      const %s g%d = c0 + lx;\n", IDX, nd - 1);
   e("      if (g%d < (%s)%lld && r0 + ly0 < (%s)%lld) {\n", nd - 1, IDX, (long long)W, IDX, (long long)H);
+  // (reading only the columns some window position picks — the outer vectors shrunk to 8 or 4 bytes — was timed and is slower: lanes are 16
+  // bytes apart, so a 4-byte read is a 4-way bank conflict and costs the same wavefronts as the whole vector: 3 x 3 0.92 -> 0.88 of HBM)
   for (int r = 0; r < RT + WY; ++r)
     e("        float R%d[%d];\n        #pragma unroll\n        for (int k = 0; k < %d; ++k) *reinterpret_cast<float4*>(&R%d[4 * k]) = *reinterpret_cast<const float4*>(&tile[ly0 + %d][lx + 4 * k]);\n",
       r, NC, NC / 4, r, r);
@@ -1482,12 +1502,12 @@ bool try_emit_stencil_tile(Plan& plan, const Program& p, int n_args, const Devic
   plan.source += e.s;
   LaunchSpec ls;
   ls.entry = "jit_kernel";
-  ls.grid[0] = (uint32_t)grid;
+  ls.grid[0] = (uint32_t)pgrid;
   ls.block[0] = 256;
   for (int i = 0; i < n_args; ++i) ls.args.push_back(i);
   ls.args.push_back(ARG_OUT);
   if (total > 0) plan.launches.push_back(ls);
-  plan.note += "; dense window staged through shared memory";
+  plan.note += "; dense window staged through shared memory (double-buffered cp.async)";
   return true;
 }
 

@@ -56,6 +56,23 @@ __device__ __forceinline__ void cc_pdl_entry() {
 }
 #endif
 
+// 16-byte asynchronous global -> shared copies (L1 bypassed), in commit groups: the staging pipeline of dense-window tiles
+#ifdef CC_HOST_EMULATION
+__device__ __forceinline__ void cc_cp_async16(float* smem_dst, const float* src) { smem_dst[0] = src[0], smem_dst[1] = src[1], smem_dst[2] = src[2], smem_dst[3] = src[3]; }
+__device__ __forceinline__ void cc_cp_async_commit() {}
+template <int N>
+__device__ __forceinline__ void cc_cp_async_wait() {}
+#else
+__device__ __forceinline__ void cc_cp_async16(float* smem_dst, const float* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cc_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cc_cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+#endif
+
 // cached flavours (allocate in L1) for data that is reused across the index space: broadcast operands, the operands of a
 // re-rolled reduction whose address does not depend on every output index (matmul / convolution patterns)
 #if defined(CC_COHERENT_LOADS) && !defined(CC_HOST_EMULATION)

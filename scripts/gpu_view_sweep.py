@@ -78,6 +78,11 @@ def chain_with(parts, f):
 case("3x3 box sum (9 translated views) 4096^2", lambda: window(XS, lambda a, b: a + b), 2 * 4 * 4096 * 4096)
 case("3x3 max pool, stride 1 (9 translated views) 4096^2", lambda: window(XS, T.max), 2 * 4 * 4096 * 4096)
 case("5x5 box sum (25 translated views) 4096^2", lambda: chain_with([XS.translate([dy, dx]) for dy in range(-2, 3) for dx in range(-2, 3)], lambda a, b: a + b), 2 * 4 * 4096 * 4096)
+# the same windows where fixed costs (launch, the first tile's latency, the tail) weigh less, and the plain copy at both sizes for scale
+case("identity copy 4096^2 (x + 0 literal)", lambda: XS + T.fill(0.0, S2), 2 * 4 * 4096 * 4096)
+case("3x3 box sum (9 translated views) 16384x8192", lambda: chain_with([XL.translate([dy, dx]) for dy in (-1, 0, 1) for dx in (-1, 0, 1)], lambda a, b: a + b), 2 * 4 * 16384 * 8192)
+case("5x5 box sum (25 translated views) 16384x8192", lambda: chain_with([XL.translate([dy, dx]) for dy in range(-2, 3) for dx in range(-2, 3)], lambda a, b: a + b), 2 * 4 * 16384 * 8192)
+case("identity copy 16384x8192 (x + 0 literal)", lambda: XL + T.fill(0.0, [16384, 8192]), 2 * 4 * 16384 * 8192)
 M3 = [256, 512, 1024]
 case("sum over middle axis 256x512x1024", lambda: chain_sum(XM.split(1)), 4 * n_of(M3) + 4 * 256 * 1024)
 case("sum over last axis 256x512x1024", lambda: chain_sum(XM.split(2)), 4 * n_of(M3) + 4 * 256 * 512)
@@ -96,6 +101,7 @@ XT2 = T.random([8192, 8191], seed=6).doCache()
 ROW = T.random([512], seed=7).doCache()
 XM = T.random(M3, seed=8).doCache()
 XS = T.random(S2, seed=13).doCache()
+XL = T.random([16384, 8192], seed=14).doCache()
 XA = T.random([16384, 4096], seed=9).doCache()
 XB = T.random([16384, 4096], seed=10).doCache()
 XC = T.random([1024, 1024, 3], seed=11).doCache()
