@@ -38,7 +38,7 @@ std::unordered_map<std::string, std::string> g_knobs;
 bool g_knobs_sampled = false;
 const char* const kKnobNames[] = {"CC_BATCHED_CONTRACTION", "CC_FUSE_COL_STAGE", "CC_NO_OP_LOOPS", "CC_NO_STENCIL_TILE", "CC_TUNE_CONTRACTION_MIN_MACS",
                                   "CC_TUNE_GRID_MULT", "CC_TUNE_MIN_BLOCKS", "CC_TUNE_MIN_REROLL_TERMS", "CC_TUNE_STENCIL_RT", "CC_TUNE_T_GRID_MULT",
-                                  "CC_TUNE_U", "CC_DISABLE_CONTRACTION", "CC_REDUCE_TILE_OWNER", "CC_TUNE_TILE_P", "CC_SMALL_N_MMA", "CC_TUNE_STENCIL_CTAS"};
+                                  "CC_TUNE_U", "CC_DISABLE_CONTRACTION", "CC_REDUCE_TILE_OWNER", "CC_TUNE_TILE_P", "CC_SMALL_N_MMA", "CC_TUNE_STENCIL_CTAS", "CC_TUNE_SMALL_N_PAIR"};
 void sample_knobs_locked() {
   g_knobs.clear();
   for (const char* name : kKnobNames)
@@ -877,6 +877,9 @@ struct LoadCtx {
   // bounds-tested vector loads are issued unconditionally from a clamped address and the padding is selected afterwards: in the
   // straight-line body of an unrolled reduction a branch around the load would pin it next to its use, exposing its whole latency
   bool unconditional = false;
+  // V == 1 only: fetch the element and its successor along the fastest source dimension as one 8-byte load into L[0], L[1] (the caller has
+  // checked that the offset is even and that both share their bounds tests)
+  bool pair = false;
 };
 
 // index expression of source row y for lane `lane` ("" = lane 0 / no lane term)
@@ -924,7 +927,7 @@ void emit_load(Emit& e, const Program& p, int j, const LoadCtx& c, const char* i
   // streaming (no L1 allocation) for data read once; cached for data reused across the index space (broadcasts, reductions)
   const char* LD1 = L.reuse ? "cc_ldc" : "cc_ldg";
   const char* LD4 = L.reuse ? "cc_ldc4" : "cc_ldg4";
-  e("%sfloat L%d[%d];\n", indent, j, V);
+  e("%sfloat L%d[%d];\n", indent, j, c.pair ? 2 : V);
   if (!L.integer) {
     // general path: per lane, per row index in the reference's arithmetic
     e("%s#pragma unroll\n%sfor (int l = 0; l < %d; ++l) {\n", indent, indent, V);
@@ -971,6 +974,12 @@ void emit_load(Emit& e, const Program& p, int j, const LoadCtx& c, const char* i
   if (aligned)
     for (int x = 0; x < nd; ++x)
       if (x != c.vdim && L.coef[x] % 4 != 0) aligned = false;
+  if (V == 1 && c.pair) {
+    e("%s{\n%s  const bool in_ = %s;\n%s  const float2 t_ = cc_ldc2(p%d + (in_ ? o%d : (%s)0));\n", indent, indent, ucond.empty() ? "true" : ucond.c_str(), indent, L.arg, j,
+      c.idx_type);
+    e("%s  L%d[0] = in_ ? t_.x : %s;\n%s  L%d[1] = in_ ? t_.y : %s;\n%s}\n", indent, j, pad.c_str(), indent, j, pad.c_str(), indent);
+    return;
+  }
   if (V == 1) {
     if (ucond.empty())
       e("%sL%d[0] = %s(p%d + o%d);\n", indent, j, LD1, L.arg, j);
@@ -2081,12 +2090,36 @@ bool try_small_n_mma(Plan& plan, const Program& p, int n_args, int la, int lb, i
     e("%sconst %s g%d = r_%d;\n", indent, IDX, first, first);
   };
   LoadCtx c1{1, -1, IDX};
-  e("__device__ __forceinline__ float ld_a(const %s m, const %s k%s) {\n  if (m >= (%s)%lld || k >= (%s)%lld) return 0.f;\n", IDX, IDX, params.c_str(), IDX,
-    (long long)M, IDX, (long long)K);
-  decode("m", 0, s, "  ");
-  decode("k", no, nd, "  ");
-  emit_load(e, p, la, c1, "  ");
-  e("  return L%d[0];\n}\n", la);
+  // a thread's two k of a step (2t, 2t + 1) are neighbours along the innermost reduction digit: one 8-byte load when A runs along it
+  // (with ONE n tile a k step is 3 MMAs, too few to cover a load: the kernel is latency-bound and four 4-byte loads in flight per step beat
+  // two 8-byte ones — 3 x 3 / depth 8: 6.7 vs 7.9 us; from two n tiles on it is instruction-bound and the pair wins — 64 x 64 x 64 depth 16:
+  // 45.9 -> 31.5 us, 65536 x 32 x 32: 7.3 -> 6.4)
+  bool a_pair = NT >= 2 && K % 2 == 0 && p.dims[nd - 1] % 2 == 0 && p.loads[la].coef[nd - 1] == 1 && p.loads[la].base % 2 == 0;
+  if (const char* ev = plan_knob("CC_TUNE_SMALL_N_PAIR")) a_pair = a_pair && atoi(ev) != 0;  // A/B knob
+  {
+    const Load& L = p.loads[la];
+    for (int x = 0; a_pair && x < nd - 1; ++x)
+      if (L.coef[x] % 2 != 0) a_pair = false;
+    for (int y = 0; a_pair && y < L.rows; ++y)
+      if ((L.need_lo[y] || L.need_hi[y]) && L.M[(size_t)y * (nd + 1) + (nd - 1)] != 0.0) a_pair = false;
+  }
+  if (a_pair) {
+    LoadCtx c2{1, -1, IDX};
+    c2.pair = true;
+    e("__device__ __forceinline__ float2 ld_a2(const %s m, const %s k%s) {\n  if (m >= (%s)%lld || k >= (%s)%lld) return make_float2(0.f, 0.f);\n", IDX, IDX, params.c_str(),
+      IDX, (long long)M, IDX, (long long)K);
+    decode("m", 0, s, "  ");
+    decode("k", no, nd, "  ");
+    emit_load(e, p, la, c2, "  ");
+    e("  return make_float2(L%d[0], L%d[1]);\n}\n", la, la);
+  } else {
+    e("__device__ __forceinline__ float ld_a(const %s m, const %s k%s) {\n  if (m >= (%s)%lld || k >= (%s)%lld) return 0.f;\n", IDX, IDX, params.c_str(), IDX,
+      (long long)M, IDX, (long long)K);
+    decode("m", 0, s, "  ");
+    decode("k", no, nd, "  ");
+    emit_load(e, p, la, c1, "  ");
+    e("  return L%d[0];\n}\n", la);
+  }
   e("__device__ __forceinline__ float ld_b(const %s n, const %s k%s) {\n  if (n >= (%s)%lld || k >= (%s)%lld) return 0.f;\n", IDX, IDX, params.c_str(), IDX,
     (long long)N, IDX, (long long)K);
   decode("n", s, no, "  ");
@@ -2123,16 +2156,33 @@ bool try_small_n_mma(Plan& plan, const Program& p, int n_args, int la, int lb, i
   e("  for (%s tile = (%s)blockIdx.x * 4 + (threadIdx.x >> 5); tile < (%s)%lld; tile += (%s)gridDim.x * 4) {\n", IDX, IDX, IDX, (long long)MT, IDX);
   e("    const %s m0 = tile * 16 + gid, m1 = m0 + 8;\n", IDX);
   e("    float c[%lld][4];\n    #pragma unroll\n    for (int nt = 0; nt < %lld; ++nt) c[nt][0] = c[nt][1] = c[nt][2] = c[nt][3] = 0.f;\n", (long long)NT, (long long)NT);
-  e("    #pragma unroll\n    for (int ks = 0; ks < %lld; ++ks) {\n      const %s k0 = (%s)(ks * 8 + 2 * tig);\n", (long long)KS, IDX, IDX);
-  e("      const float a[4] = {ld_a(m0, k0%s), ld_a(m1, k0%s), ld_a(m0, k0 + 1%s), ld_a(m1, k0 + 1%s)};\n", pass.c_str(), pass.c_str(), pass.c_str(), pass.c_str());
+  // A for up to 8 k steps is fetched before the first of them is used: the loads of a tile are then in flight together instead of
+  // two at a time in front of their MMAs (timed: 3 x 3 / depth 8 went 6.7 -> 7.9 us with pair loads issued just in time)
+  const int64_t KC = std::min<int64_t>(KS, 8);
+  e("    #pragma unroll\n    for (int kc = 0; kc < %lld; kc += %lld) {\n", (long long)KS, (long long)KC);
+  if (a_pair) {
+    e("      float2 x0[%lld], x1[%lld];\n      #pragma unroll\n      for (int j = 0; j < %lld; ++j) {\n        const %s k0 = (%s)((kc + j) * 8 + 2 * tig);\n", (long long)KC,
+      (long long)KC, (long long)KC, IDX, IDX);
+    e("        x0[j] = ld_a2(m0, k0%s);\n        x1[j] = ld_a2(m1, k0%s);\n      }\n", pass.c_str(), pass.c_str());
+  } else {
+    e("      float xa[%lld][4];\n      #pragma unroll\n      for (int j = 0; j < %lld; ++j) {\n        const %s k0 = (%s)((kc + j) * 8 + 2 * tig);\n", (long long)KC, (long long)KC,
+      IDX, IDX);
+    e("        xa[j][0] = ld_a(m0, k0%s);\n        xa[j][1] = ld_a(m1, k0%s);\n        xa[j][2] = ld_a(m0, k0 + 1%s);\n        xa[j][3] = ld_a(m1, k0 + 1%s);\n      }\n", pass.c_str(),
+      pass.c_str(), pass.c_str(), pass.c_str());
+  }
+  e("      #pragma unroll\n      for (int j = 0; j < %lld; ++j) {\n        const int ks = kc + j;\n        if (ks >= %lld) break;\n", (long long)KC, (long long)KS);
+  if (a_pair)
+    e("        const float a[4] = {x0[j].x, x1[j].x, x0[j].y, x1[j].y};\n");
+  else
+    e("        const float a[4] = {xa[j][0], xa[j][1], xa[j][2], xa[j][3]};\n");
   e("      unsigned ah[4], al[4];\n      #pragma unroll\n      for (int i = 0; i < 4; ++i) {\n        float h, l;\n        cc_split_tf32(a[i], h, l);\n"
     "        ah[i] = __float_as_uint(h);\n        al[i] = __float_as_uint(l);\n      }\n");
   if (!b_shared)
     e("      #pragma unroll\n      for (int nt = 0; nt < %lld; ++nt) {\n        cc_mma_tf32_16x8x8(c[nt], al, bh[ks][nt]);\n        cc_mma_tf32_16x8x8(c[nt], ah, bl[ks][nt]);\n"
-      "        cc_mma_tf32_16x8x8(c[nt], ah, bh[ks][nt]);\n      }\n    }\n", (long long)NT);
+      "        cc_mma_tf32_16x8x8(c[nt], ah, bh[ks][nt]);\n      }\n      }\n    }\n", (long long)NT);
   else
     e("      #pragma unroll\n      for (int nt = 0; nt < %lld; ++nt) {\n        const uint4 bf = bfrag[ks * %lld + nt][lane];\n        const unsigned bh[2] = {bf.x, bf.y}, bl[2] = {bf.z, bf.w};\n"
-      "        cc_mma_tf32_16x8x8(c[nt], al, bh);\n        cc_mma_tf32_16x8x8(c[nt], ah, bl);\n        cc_mma_tf32_16x8x8(c[nt], ah, bh);\n      }\n    }\n", (long long)NT, (long long)NT);
+      "        cc_mma_tf32_16x8x8(c[nt], al, bh);\n        cc_mma_tf32_16x8x8(c[nt], ah, bl);\n        cc_mma_tf32_16x8x8(c[nt], ah, bh);\n      }\n      }\n    }\n", (long long)NT, (long long)NT);
   e("    #pragma unroll\n    for (int nt = 0; nt < %lld; ++nt) {\n      const %s n0 = (%s)(nt * 8 + 2 * tig);\n      if (n0 >= (%s)%lld) continue;\n", (long long)NT, IDX, IDX, IDX,
     (long long)N);
   e("      #pragma unroll\n      for (int h = 0; h < 2; ++h) {\n        const %s m = h ? m1 : m0;\n        if (m >= (%s)%lld) continue;\n", IDX, IDX, (long long)M);

@@ -80,6 +80,27 @@ __device__ __forceinline__ float cc_ldc(const float* p) { return *p; }
 #else
 __device__ __forceinline__ float cc_ldc(const float* p) { return __ldg(p); }
 #endif
+// p must be 8-byte aligned. A volatile statement: it keeps its place among the other volatile statements of a kernel (the MMAs of the
+// small-N contraction), so a batch of these written ahead of the MMAs that consume them is ISSUED ahead of them — left to itself the compiler
+// sinks every load to just before its use and a warp has two loads in flight instead of sixteen.
+__device__ __forceinline__ float2 cc_ldc2(const float* p) {
+#if defined(CC_HOST_EMULATION)
+  return make_float2(p[0], p[1]);
+#else
+  float2 v;
+  asm volatile("ld.global" CC_LD_NC ".v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+  return v;
+#endif
+}
+__device__ __forceinline__ float cc_ldc1v(const float* p) {
+#if defined(CC_HOST_EMULATION)
+  return *p;
+#else
+  float v;
+  asm volatile("ld.global" CC_LD_NC ".f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+#endif
+}
 __device__ __forceinline__ void cc_ldc4(const float* p, float (&v)[4]) {
 #if defined(CC_COHERENT_LOADS) && !defined(CC_HOST_EMULATION)
   const float4 x = *reinterpret_cast<const float4*>(p);
