@@ -576,6 +576,33 @@ def test_convolution_small_n_on_warp_mmas(cuda, batch, size, depth, filters, ks)
     assert (np.abs(got - want) / mag).max() <= 2e-6  # (the bar is 1e-5; fp32 FMA chains of this length sit at ~1e-7)
 
 
+@pytest.mark.parametrize("m,k,n", [(4096, 20, 12), (5000, 33, 8), (65536, 32, 32), (4100, 256, 6), (8192, 64, 16), (4097, 9, 30)])
+def test_small_n_contraction_over_views(cuda, m, k, n):
+    """skinny products written as split / broadcast / sum (benchmarks.scala:188-191) whose operands are views: A stored transposed, B read
+    through a translation with a non-zero padding, an epilogue around the sum. Tall M, N <= 32, short K: the small-N kernel on warp-level
+    MMAs (K not a multiple of 8, rows not a multiple of 16, N not a multiple of 8 included), exact on exactly representable data"""
+    T = cuda.Tensor
+    rng = np.random.default_rng(m + k + n)
+    at = rng.integers(-4, 5, (k, m)).astype(np.float32)       # A^T in memory
+    b = rng.integers(-4, 5, (k, n)).astype(np.float32)
+    bias = rng.integers(-6, 7, (n,)).astype(np.float32) / np.float32(4.0)
+    A = T(at).permute([1, 0])                                  # [m, k] view
+    Bs = T(b, padding=2.5).translate([1, 0])                   # rows shifted down by one, first row = padding 2.5
+    prod = A.broadcast([m, k, n]) * Bs.nonInline().reshape([1, k, n]).broadcast([m, k, n])
+    acc = axis_sum(T, prod, 1) * T.fill(0.5, [m, n]) + T(bias).reshape([1, n]).broadcast([m, n])
+    kern = acc.compile()
+    assert kern.info.kind == 1 and "small-N contraction" in kern.source, kern.source[:300]
+    bs_host = np.full_like(b, 2.5)
+    bs_host[1:] = b[:-1]
+    want = ((at.T.astype(np.float64) @ bs_host.astype(np.float64)) * 0.5 + bias).astype(np.float32)
+    assert np.array_equal(acc.flatArray().reshape(m, n), want)
+    # the plain operands, the pattern as the reference writes it
+    a = np.ascontiguousarray(at.T)
+    plain = axis_sum(T, T(a).broadcast([m, k, n]) * T(b).reshape([1, k, n]).broadcast([m, k, n]), 1)
+    assert "small-N contraction" in plain.compile().source
+    assert np.array_equal(plain.flatArray().reshape(m, n), (a.astype(np.float64) @ b.astype(np.float64)).astype(np.float32))
+
+
 @pytest.mark.parametrize("rows", [64, 4096])  # one CTA covers all of T / partials + second stage (epilogue applied there)
 def test_epilogue_around_an_axis_sum(cuda, rows):
     T = cuda.Tensor
