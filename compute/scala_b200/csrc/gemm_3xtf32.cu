@@ -1088,6 +1088,13 @@ int gemm_config_for(const float* a, int64_t m, int64_t n, int64_t k, int sm_coun
   // a product of few tiles: the tensor-memory-A kernel with K split over the CTA pairs beats a narrow-tile configuration that fills the SMs
   // with inefficient tiles (1024^3: 16 tiles of 256 x 256, 4 splits -> 64 units for 74 pairs)
   if (config != 1024 && tmema_ok && tmema_default() && gemm_k_splits(m, n, k, sm_count) > 1) config = 1024;
+  // gather epilogue: every tile's stores leave when the tile is complete, and the receiving side takes ~450 GB/s (8 ranks: 224 MiB per GPU).
+  // With fewer than three waves of pair tiles the traffic comes in two bursts and the second one is all tail (8192^3 on 8 ranks: 0.477 ms
+  // un-gathered, 0.739 gathered); 128 x 128 tiles are slower per flop but finish continuously: 0.678 ms (profiles/r02_gather_n8_tile_configs.json)
+  if (gather_epilogue && config == 512) {
+    const int64_t pair_tiles = ((m + 255) / 256) * ((n + 255) / 256), small_tiles = ((m + 127) / 128) * ((n + 127) / 128);
+    if (pair_tiles * 2 < (int64_t)3 * sm_count && small_tiles >= (int64_t)3 * sm_count) config = 128;
+  }
   if (const char* force = getenv("CC_GEMM_FORCE_CONFIG")) {
     const int f = atoi(force);
     if (f == 256 || f == 128 || f == 64 || (f == 512 && m > BM) || (f == 1024 && tmema_ok)) config = f;

@@ -22,7 +22,7 @@ cuda.init(local, streams=1)
 comm = sharding.Communicator(cuda, dist)
 T = cuda.Tensor
 out = {"n_gpus": world, "route": "nvls multicast" if os.environ.get("CC_MULTICAST", "1") != "0" else "one TMA store per peer (CUDA IPC)"}
-for n5 in (8192, 4096):
+for n5 in [int(x) for x in os.environ.get("GATHER_SIZES", "8192,4096").split(",")]:
     m5 = n5 // world
 
     def e_tensor(shape, seed):
@@ -75,7 +75,7 @@ dist.all_reduce(t, op=dist.ReduceOp.MIN)
 out["verified on every rank"] = bool(t.item())
 if rank == 0:
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-    tag = "mc" if os.environ.get("CC_MULTICAST", "1") != "0" else "ipc"
+    tag = ("mc" if os.environ.get("CC_MULTICAST", "1") != "0" else "ipc") + os.environ.get("GATHER_TAG", "")
     json.dump(out, open(os.path.join(ROOT, "gpurun_out", f"gather_mc_n{world}_{tag}.json"), "w"), indent=1)
     print(json.dumps(out))
 cuda.synchronize()

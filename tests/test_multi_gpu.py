@@ -107,7 +107,7 @@ def _worker(rank, world, port, multicast):
                 assert not arena.is_multicast
             elif rank == 0:
                 print("symmetric arena has an NVLS multicast mapping:", arena.is_multicast)
-            for rep, config in enumerate((None, None, "512", "256", "64")):  # back to back: the entry barrier protects the arena
+            for rep, config in enumerate((None, None, "512", "256", "128", "64")):  # back to back: the entry barrier protects the arena
                 # every tile configuration of the gather epilogue: CTA pairs (cta_group::2) and single CTAs
                 if config:
                     os.environ["CC_GEMM_FORCE_CONFIG"] = config
