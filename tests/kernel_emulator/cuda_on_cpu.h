@@ -36,6 +36,10 @@ struct uint2 {
   unsigned x, y;
 };
 inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
+struct float2 {
+  float x, y;
+};
+inline float2 make_float2(float x, float y) { return float2{x, y}; }
 
 inline thread_local uint3_ threadIdx, blockIdx;
 inline uint3_ blockDim, gridDim;

@@ -378,3 +378,4 @@ def test_random_graphs_on_the_emulator(block):
 def test_larger_random_graphs_on_the_emulator(block):
     ran, kinds = _emulated_fuzz([310000 + 100 * block + case for case in range(10)], dims=DIMS_BIG, max_rank=3)
     assert ran >= 5, (ran, kinds)
+
