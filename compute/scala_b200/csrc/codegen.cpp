@@ -1785,8 +1785,13 @@ void emit_reduce(Plan& plan, const Program& p, int n_args, const DeviceProps& de
     const int64_t gridx = (NV + CW - 1) / CW;
     bool fused = Sy > 1 && gridx <= kColCounters;
     if (const char* ev = plan_knob("CC_FUSE_COL_STAGE")) fused = fused && atoi(ev) != 0;
-    e("extern \"C\" __global__ void __launch_bounds__(256) reduce_cols(%s%s) {\n", param_list(n_args, true, "dst").c_str(),
-      fused ? ", float* __restrict__ out, unsigned* __restrict__ counters" : "");
+    // A partial sum of a sharded tensor (`shard.split(0).reduce(_ + _)`) is all-reduced when it is evaluated: when this kernel also writes the
+    // final values (no separate second launch) the threads that hold them complete the all-reduce over the peer mailboxes themselves — the
+    // compute step and its collective are ONE launch (`mb_` is null on ordinary launches).
+    const bool coll = mono == K_PLUS && !has_post && V == 4 && NOUT <= 65536 && (Sy == 1 || fused);
+    const char* COLL_PARAMS = coll ? ", const cc_peer_mailboxes* __restrict__ mb_, const unsigned long long epoch_" : "";
+    e("extern \"C\" __global__ void __launch_bounds__(256) reduce_cols(%s%s%s) {\n", param_list(n_args, true, "dst").c_str(),
+      fused ? ", float* __restrict__ out, unsigned* __restrict__ counters" : "", COLL_PARAMS);
     if (S == 1) {
       e("  const %s v = (%s)blockIdx.x * 256 + threadIdx.x;\n  if (v >= %lld) return;\n", IDX, IDX, (long long)NV);
     } else {
@@ -1853,6 +1858,7 @@ void emit_reduce(Plan& plan, const Program& p, int n_args, const DeviceProps& de
         e("  float* d = out + v * %d;\n", V);
       }
     }
+    if (coll) e("  if (mb_) cc_ll_allreduce4(acc, (unsigned long long)v * 4, mb_, (unsigned)epoch_);\n");
     if (V == 4)
       e("  cc_stg4(d, acc);\n");
     else
@@ -1870,6 +1876,11 @@ void emit_reduce(Plan& plan, const Program& p, int n_args, const DeviceProps& de
       ls.args.push_back(ARG_COL_COUNTERS);
       plan.scratch_floats.push_back((uint64_t)(Sy * NOUT));
       plan.note += "; second stage fused into reduce_cols (last CTA per column block)";
+    }
+    if (coll) {
+      ls.args.push_back(ARG_PEER_MB);
+      ls.args.push_back(ARG_PEER_EPOCH);
+      plan.collective = 1;
     }
     plan.launches.push_back(ls);
     S = fused ? 1 : Sy;  // what the second-stage kernel folds
@@ -1930,7 +1941,11 @@ void emit_reduce(Plan& plan, const Program& p, int n_args, const DeviceProps& de
     else
       e("  return o[0];\n}\n");
     emit_post_fn(1, -1);
-    e("extern \"C\" __global__ void __launch_bounds__(256) reduce_rows(%s) {\n", param_list(n_args, true).c_str());
+    // the row sums of a sharded tensor stay a row block; when every rank wants all of them (`gather`) lane 0 of every output pushes its value
+    // into all ranks' mailboxes and collects the other ranks' — the kernel writes the gathered vector ([ranks x outputs]) itself
+    const bool collg = !has_post && NOUT <= 65536;
+    e("extern \"C\" __global__ void __launch_bounds__(256) reduce_rows(%s%s) {\n", param_list(n_args, true).c_str(),
+      collg ? ", const cc_peer_mailboxes* __restrict__ mb_, const unsigned long long epoch_" : "");
     e("  const int lane = threadIdx.x %% %d;\n", G);
     e("  const %s oidx = (%s)blockIdx.x * %d + threadIdx.x / %d;\n", IDX, IDX, OPB, G);
     e("  const bool live = oidx < %lld;\n  const %s oc = live ? oidx : 0;\n", (long long)NOUT, IDX);
@@ -1946,6 +1961,9 @@ void emit_reduce(Plan& plan, const Program& p, int n_args, const DeviceProps& de
     }
     if (has_post)
       e("  if (lane == 0 && live) {\n    float a1[1] = {acc};\n    post(a1%s%s);\n    out[oidx] = a1[0];\n  }\n}\n", gs.c_str(), pass.c_str());
+    else if (collg)
+      e("  if (lane == 0 && live) {\n    if (mb_) cc_ll_allgather1(acc, (unsigned long long)oidx, %lldull, out, mb_, (unsigned)epoch_);\n    else out[oidx] = acc;\n  }\n}\n",
+        (long long)NOUT);
     else
       e("  if (lane == 0 && live) out[oidx] = acc;\n}\n");
     LaunchSpec ls;
@@ -1954,6 +1972,11 @@ void emit_reduce(Plan& plan, const Program& p, int n_args, const DeviceProps& de
     ls.block[0] = 256;
     for (int i = 0; i < n_args; ++i) ls.args.push_back(i);
     ls.args.push_back(ARG_OUT);
+    if (collg) {
+      ls.args.push_back(ARG_PEER_MB);
+      ls.args.push_back(ARG_PEER_EPOCH);
+      plan.collective = 2;
+    }
     plan.launches.push_back(ls);
   }
   plan.source += e.s;

@@ -19,7 +19,11 @@ enum {
   ARG_REDUCE_PARTIALS = -100,
   ARG_REDUCE_COUNTER = -101,
   // fused second stage of a split axis reduction (opt-in): self-resetting per-stream block counters, one per blockIdx.x (<= kColCounters)
-  ARG_COL_COUNTERS = -102
+  ARG_COL_COUNTERS = -102,
+  // a reduction that can complete a collective itself (Plan::collective): pointer to the device copy of the peer mailboxes (null on ordinary
+  // launches) and the collective's epoch as a 64-bit value
+  ARG_PEER_MB = -103,
+  ARG_PEER_EPOCH = -104
 };
 constexpr int kColCounters = 4096;
 constexpr int kFullReduceThreads = 512;
@@ -47,6 +51,9 @@ struct Plan {
   // contraction whose K-major hi / lo operand panels are written by generated kernels (launches[0] = panel_a, [1] = panel_b,
   // optional [2] = post_kernel applied in place to the result) instead of the precompiled split kernels
   bool gathered_panels = false;
+  // 1: the plan's last launch can all-reduce (sum) its output over the peer mailboxes itself; 2: it can all-gather it (the output buffer is then
+  // the gathered one, [ranks x out_floats]). 0: neither.
+  int collective = 0;
   int64_t batch = 1;  // gathered panels only: leading output dims both operands depend on = that many independent M x N x K products
   std::string note;             // human-readable description of the choices made (kept in the kernel source header)
 };

@@ -172,6 +172,74 @@ __device__ __forceinline__ float cc_block_sum_256(float v) {
   return v;
 }
 
+// ---- collectives folded into a reduction's final stage (sharded tensors, one process per GPU) ---------------------------------------
+// The mailboxes of builtin_kernels.h (PeerMailboxes, same layout): every rank owns [2][world][65536] LL slots {float, epoch} in its HBM,
+// mapped into every peer. The thread that holds a final value pushes it into all ranks' mailboxes (NVLink stores) and then reads every
+// rank's slot out of its own mailbox — the payload carries its own ready flag. A generated reduction takes `mb_` = null on ordinary
+// launches; cc_shard_launch_allreduce / _allgather pass the mailboxes and a fresh epoch, and the kernel IS the collective (the sum of
+// the contributions is taken in rank order from 0.f, as the stand-alone all-reduce kernel takes it: same bits on every rank and route).
+struct cc_peer_mailboxes {
+  float* data[8];
+  unsigned* flags[8];
+  int world;
+  int rank;
+};
+#ifdef CC_HOST_EMULATION
+__device__ __forceinline__ void cc_ll_allreduce4(float (&)[4], unsigned long long, const cc_peer_mailboxes*, unsigned) {}
+__device__ __forceinline__ void cc_ll_allgather1(float, unsigned long long, unsigned long long, float*, const cc_peer_mailboxes*, unsigned) {}
+#else
+__device__ __forceinline__ void cc_ll_store2(uint2* p, float v0, float v1, unsigned e) {
+  asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(__float_as_uint(v0)), "r"(e), "r"(__float_as_uint(v1)), "r"(e) : "memory");
+}
+__device__ __forceinline__ void cc_ll_store1(uint2* p, float v, unsigned e) {
+  asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(__float_as_uint(v)), "r"(e) : "memory");
+}
+__device__ __forceinline__ void cc_ll_load2(const uint2* p, unsigned e, float& v0, float& v1) {
+  unsigned a, b, c, d, spins = 0;
+  do {
+    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "l"(p) : "memory");
+    if (++spins > (1u << 27)) __trap();  // a peer that never shows up must abort this launch, not hang the GPU
+  } while (b != e || d != e);
+  v0 = __uint_as_float(a);
+  v1 = __uint_as_float(c);
+}
+__device__ __forceinline__ float cc_ll_load1(const uint2* p, unsigned e) {
+  unsigned a, b, spins = 0;
+  do {
+    asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(a), "=r"(b) : "l"(p) : "memory");
+    if (++spins > (1u << 27)) __trap();
+  } while (b != e);
+  return __uint_as_float(a);
+}
+__device__ __forceinline__ uint2* cc_ll_slot(const cc_peer_mailboxes* mb, int owner, int parity, int src_rank, unsigned long long i) {
+  return reinterpret_cast<uint2*>(mb->data[owner]) + ((size_t)parity * mb->world + src_rank) * (size_t)65536 + i;
+}
+// acc[0..4) = sum over ranks of their acc[0..4) for elements [i, i + 4), i % 4 == 0, i + 4 <= 65536
+__device__ __forceinline__ void cc_ll_allreduce4(float (&acc)[4], unsigned long long i, const cc_peer_mailboxes* mb, unsigned epoch) {
+  const int parity = (int)(epoch & 1u), world = mb->world, rank = mb->rank;
+  for (int peer = 0; peer < world; ++peer) {
+    uint2* dst = cc_ll_slot(mb, peer, parity, rank, i);
+    cc_ll_store2(dst, acc[0], acc[1], epoch);
+    cc_ll_store2(dst + 2, acc[2], acc[3], epoch);
+  }
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  for (int r = 0; r < world; ++r) {
+    const uint2* src = cc_ll_slot(mb, rank, parity, r, i);
+    float x0, x1, x2, x3;
+    cc_ll_load2(src, epoch, x0, x1);
+    cc_ll_load2(src + 2, epoch, x2, x3);
+    s0 = __fadd_rn(s0, x0), s1 = __fadd_rn(s1, x1), s2 = __fadd_rn(s2, x2), s3 = __fadd_rn(s3, x3);
+  }
+  acc[0] = s0, acc[1] = s1, acc[2] = s2, acc[3] = s3;
+}
+// out[r * n + i] = rank r's v for every rank r (this rank's own included)
+__device__ __forceinline__ void cc_ll_allgather1(float v, unsigned long long i, unsigned long long n, float* out, const cc_peer_mailboxes* mb, unsigned epoch) {
+  const int parity = (int)(epoch & 1u), world = mb->world, rank = mb->rank;
+  for (int peer = 0; peer < world; ++peer) cc_ll_store1(cc_ll_slot(mb, peer, parity, rank, i), v, epoch);
+  for (int r = 0; r < world; ++r) out[(size_t)r * n + i] = cc_ll_load1(cc_ll_slot(mb, rank, parity, r, i), epoch);
+}
+#endif
+
 // ---- monoids (MonoidPrograms, Tensors.scala:308-311: append / zero) ------------------------------------------------------
 // ap() never contracts with the producer of its operands (__fadd_rn / __fmul_rn), so a reduction fused with an elementwise
 // closure folds exactly the values the unfused "materialise, then reduce" sequence of the reference would fold.

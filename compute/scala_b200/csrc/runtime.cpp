@@ -108,6 +108,7 @@ struct Nccl {
   CUdeviceptr mailbox = 0;
   CUdeviceptr peer_base[kPeerMaxRanks] = {0};
   PeerMailboxes mb{};
+  CUdeviceptr mb_dev = 0;  // device copy of `mb`: what a generated reduction that completes its collective itself is handed (ARG_PEER_MB)
   unsigned epoch = 0;
   std::vector<Buffer*> symmetric;  // cc_comm_symmetric_alloc results, freed when the communicator goes
   void load() {
@@ -777,6 +778,8 @@ void close_peers(Nccl& n) {
     if (r != n.rank && n.peer_base[r]) driver().cuIpcCloseMemHandle(n.peer_base[r]);
   if (n.mailbox) driver().cuMemFree(n.mailbox);
   n.mailbox = 0;
+  if (n.mb_dev) driver().cuMemFree(n.mb_dev);
+  n.mb_dev = 0;
   n.peer_enabled = false;
   n.peer_mapped = false;
 }
@@ -1586,13 +1589,20 @@ void label_kernel_op(Op& op, const Kernel& k) {
 }
 }  // namespace
 
-int cc_launch(cc_kernel h, const cc_buffer* args, int n_args, cc_buffer out, const cc_event* waits, int n_waits, cc_event* out_event) {
+namespace {
+// `collective`: the plan's last launch completes its all-reduce / all-gather over the peer mailboxes itself (Plan::collective; the caller has
+// checked that the route is open). Such a launch takes the next epoch and runs on stream 0, where every collective runs: epochs are consumed
+// in stream order on every rank.
+int launch_kernel(cc_kernel h, const cc_buffer* args, int n_args, cc_buffer out, const cc_event* waits, int n_waits, cc_event* out_event, bool collective) {
   return guarded([&] {
     Lock lock;
     require_init();
     Runtime& r = rt();
     Kernel* k = as_kernel(h);
     const Plan& p = k->plan;
+    CC_REQUIRE(!collective || (p.collective != 0 && r.nccl.comm && r.nccl.peer_enabled && r.nccl.mb_dev), CC_ERR_ILLEGAL_ARGUMENT,
+               "this kernel cannot complete a collective itself");
+    const unsigned coll_epoch = collective ? ++r.nccl.epoch : 0u;
     CC_REQUIRE(n_args == (int)p.arg_params.size(), CC_ERR_ILLEGAL_ARGUMENT, "kernel expects %zu buffers, got %d", p.arg_params.size(), n_args);
     Buffer* ob = as_buffer(out);
     CC_REQUIRE(ob->n_floats >= p.out_floats, CC_ERR_ILLEGAL_ARGUMENT, "output buffer has %llu floats, kernel writes %llu",
@@ -1622,6 +1632,10 @@ int cc_launch(cc_kernel h, const cc_buffer* args, int n_args, cc_buffer out, con
           ptrs.push_back(r.reduce_counter);
         else if (a == ARG_COL_COUNTERS)
           ptrs.push_back(col_counters_for(launch_stream));
+        else if (a == ARG_PEER_MB)
+          ptrs.push_back(collective ? r.nccl.mb_dev : (CUdeviceptr)0);
+        else if (a == ARG_PEER_EPOCH)
+          ptrs.push_back((CUdeviceptr)coll_epoch);
         else
           ptrs.push_back(scratch[ARG_SCRATCH0 - a]->ptr);
       }
@@ -1713,8 +1727,9 @@ int cc_launch(cc_kernel h, const cc_buffer* args, int n_args, cc_buffer out, con
     for (uint64_t n : p.scratch_floats) scratch.push_back(alloc_buffer(n));
     // whole-tensor folds share the runtime's partials buffer and block counter: serialised on stream 0 like cc_reduce_sum
     Buffer* shared_partials = p.kind == PLAN_FULL_REDUCE ? reduce_scratch() : nullptr;
-    Op op{shared_partials ? 0 : pick_stream_for(in, {ob}), in, {ob}};
+    Op op{(shared_partials || collective) ? 0 : pick_stream_for(in, {ob}), in, {ob}};
     label_kernel_op(op, *k);
+    if (collective && (r.profiling || r.nvtx)) op.label += p.collective == 1 ? " + all-reduce over NVLink (same kernel)" : " + all-gather over NVLink (same kernel)";
     for (Buffer* s : scratch) op.writes.push_back(s);
     if (shared_partials) op.writes.push_back(shared_partials);
     launch_stream = op.stream;
@@ -1734,6 +1749,11 @@ int cc_launch(cc_kernel h, const cc_buffer* args, int n_args, cc_buffer out, con
     }
     for (Buffer* s : scratch) release(s);
   });
+}
+}  // namespace
+
+int cc_launch(cc_kernel h, const cc_buffer* args, int n_args, cc_buffer out, const cc_event* waits, int n_waits, cc_event* out_event) {
+  return launch_kernel(h, args, n_args, out, waits, n_waits, out_event, false);
 }
 
 int cc_reduce_sum(cc_buffer in, uint64_t n_floats, cc_buffer out, const cc_event* waits, int n_waits, cc_event* out_event) {
@@ -2044,6 +2064,8 @@ int cc_comm_enable_peer(void) {
     driver().cuMemFree(token);
     rt().seq[0]++;
     n.epoch = 0;
+    if (!n.mb_dev) CC_CU(cuMemAlloc(&n.mb_dev, sizeof(PeerMailboxes)));
+    CC_CU(cuMemcpyHtoD(n.mb_dev, &n.mb, sizeof(PeerMailboxes)));
     n.peer_enabled = true;
     n.peer_mapped = true;
   });
@@ -2660,11 +2682,18 @@ int cc_shard_agree(uint64_t value, int* out_all_equal) {
 
 int cc_shard_launch_allreduce(cc_kernel h, const cc_buffer* args, int n_args, cc_buffer out, const cc_event* waits, int n_waits, cc_event* out_event) {
   uint64_t n = 0;
+  bool same_kernel = false;
   int st = guarded([&] {
     Lock lock;
-    n = as_kernel(h)->plan.out_floats;
+    require_init();
+    const Plan& p = as_kernel(h)->plan;
+    Nccl& nc = rt().nccl;
+    n = p.out_floats;
+    // a generated reduction that writes its final values itself completes the all-reduce over the peer mailboxes too: one launch
+    same_kernel = p.collective == 1 && nc.comm && nc.n_ranks > 1 && nc.peer_enabled && nc.mb_dev && n <= (uint64_t)kPeerCapFloats && !rt().capture;
   });
   if (st != CC_OK) return st;
+  if (same_kernel) return launch_kernel(h, args, n_args, out, waits, n_waits, out_event, true);
   st = cc_launch(h, args, n_args, out, waits, n_waits, nullptr);
   if (st != CC_OK) return st;
   // the hazard tracker orders the combine after the launch (it writes the buffer the launch wrote)
@@ -2673,7 +2702,7 @@ int cc_shard_launch_allreduce(cc_kernel h, const cc_buffer* args, int n_args, cc
 
 int cc_shard_launch_allgather(cc_kernel h, const cc_buffer* args, int n_args, cc_buffer gathered, const cc_event* waits, int n_waits, cc_event* out_event,
                               int* out_fused) {
-  bool fuse = false;
+  bool fuse = false, same_kernel = false;
   uint64_t n = 0;
   int64_t M = 0, N = 0, K = 0;
   int st = guarded([&] {
@@ -2689,10 +2718,13 @@ int cc_shard_launch_allgather(cc_kernel h, const cc_buffer* args, int n_args, cc
     M = p.M, N = p.N, K = p.K;
     fuse = p.kind == PLAN_CONTRACTION && !p.gathered_panels && n_args == 2 && nc.comm && nc.peer_mapped && nc.peer_enabled &&
            ((int)gb->peers.size() == nc.n_ranks || gb->mc_ptr) && N % 4 == 0;
+    // a row-owner reduction gathers its own outputs over the peer mailboxes (lane 0 of every output): one launch
+    same_kernel = p.collective == 2 && nc.comm && nc.n_ranks > 1 && nc.peer_enabled && nc.mb_dev && n <= (uint64_t)kPeerCapFloats && !rt().capture;
   });
   if (st != CC_OK) return st;
-  if (out_fused) *out_fused = fuse ? 1 : 0;
+  if (out_fused) *out_fused = (fuse || same_kernel) ? 1 : 0;
   if (fuse) return cc_matmul_3xtf32_allgather(args[0], args[1], gathered, M, N, K, waits, n_waits, out_event);
+  if (same_kernel) return launch_kernel(h, args, n_args, gathered, waits, n_waits, out_event, true);
   cc_buffer part = 0;
   st = cc_buffer_alloc(n, &part);
   if (st == CC_OK) st = cc_launch(h, args, n_args, part, waits, n_waits, nullptr);

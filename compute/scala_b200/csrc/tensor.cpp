@@ -205,7 +205,9 @@ struct InlineTensor : Counted {
         resolve_plan(plan, ctx, root, shape);
       }
     }
-    return enqueue_plan(s, plan, shape);
+    // a partial sum (the fold of a row block's split(0) views) is evaluated COMBINED: the library runs the kernel and the all-reduce, as ONE
+    // launch when the reduction can complete the exchange itself (cc_shard_launch_allreduce)
+    return enqueue_plan(s, plan, shape, 0, nullptr, dist == kPartialSum);
   }
   bool evaluate_into(Session& s, cc_buffer out, cc_event* out_event) const override {
     {
@@ -540,6 +542,19 @@ struct GatherTensor final : NonInlineTensor {
         }
         return {copy_of(arena, n * (uint64_t)world), 0};
       }
+      // any other kernel of the block's own: the library launches it and gathers — in ONE launch when the kernel can collect the other ranks'
+      // values itself (a row-owner reduction: `shard.split(1).reduce(_ + _).gather`), else kernel + one-shot all-gather
+      cc_buffer whole = 0;
+      check(cc_buffer_alloc(n * (uint64_t)world, &whole));
+      cc::SmallVec<cc_buffer, 16> args;
+      for (const Tensor* t : inl->plan.args) args.push_back(t->borrow_buffer(s));
+      const int st = cc_shard_launch_allgather(inl->plan.kernel, args.data(), (int)args.size(), whole, nullptr, 0, nullptr, nullptr);
+      if (st != CC_OK) {
+        const std::string m = cc_last_error();
+        cc_buffer_release(whole);
+        throw Error(st, m);
+      }
+      return {whole, 0};
     }
     PendingBuffer part = base->do_buffer(s);
     cc_buffer whole = 0;
@@ -612,8 +627,9 @@ cc_buffer Tensor::borrow_buffer(Session& s) const {
   PendingBuffer* p = s.find(this);
   if (!p) {
     PendingBuffer fresh = evaluate(s);
-    if (dist == kPartialSum) {
-      // a partial sum is only ever an inline expression (split(0) views folded with +), so `fresh` is this evaluation's own output
+    if (dist == kPartialSum && !is_inline()) {
+      // (a partial sum is an inline expression — split(0) views folded with + — and InlineTensor::evaluate has already combined it; this is
+      // the route for any other producer: `fresh` is this evaluation's own output)
       int st = cc_allreduce_sum(fresh.buffer, (uint64_t)size(), nullptr, 0, nullptr);
       if (st != CC_OK) {
         std::string m = cc_last_error();

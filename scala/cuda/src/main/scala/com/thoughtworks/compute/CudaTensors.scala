@@ -532,6 +532,25 @@ trait CudaTensors extends Cuda {
                 case inline: InlineTensor
                     if CudaNative.commPeerEnabled() && inline.plan.kind == 2 && inline.shape.length == 2 && inline.shape(1) % 4 == 0 =>
                   gatherFromEpilogue(inline, blockFloats * numberOfRanks, zeroCopy)
+                case inline: InlineTensor if CudaNative.commPeerEnabled() =>
+                  // any other kernel of the block's own (twin: GatherTensor::evaluate in tensor.cpp): the library launches it and gathers —
+                  // in ONE launch when the kernel can collect the other ranks' values itself (a row-owner reduction:
+                  // `shard.split(1).reduce(_ + _).gather`), else kernel + one-shot all-gather
+                  inline.plan.arguments
+                    .traverse[ParallelDo, PendingBuffer](tensor => Parallel(tensor.doBuffer))
+                    .unwrap
+                    .flatMap { arguments: List[PendingBuffer] =>
+                      allocateBuffer(blockFloats * numberOfRanks).flatMap { whole =>
+                        Do.monadicCloseable {
+                            val (event, _) = CudaNative.shardLaunchAllGather(inline.plan.handle,
+                                                                             arguments.map(_.buffer.handle).toArray,
+                                                                             whole.handle,
+                                                                             arguments.flatMap(_.eventOption.map(_.handle)).toArray)
+                            new Event(event)
+                          }
+                          .map(event => EventBuffer(whole, event): PendingBuffer)
+                      }
+                    }
                 case _ =>
                   thisTensor.doBuffer.flatMap { block =>
                     allocateBuffer(blockFloats * numberOfRanks).flatMap { whole =>

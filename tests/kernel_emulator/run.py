@@ -10,7 +10,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 _CACHE = os.path.join(tempfile.gettempdir(), "compute_cuda_kernel_emulator")
-ARG_OUT, ARG_SCRATCH0, ARG_PARTIALS, ARG_COUNTER, ARG_COL_COUNTERS = -1, -2, -100, -101, -102
+ARG_OUT, ARG_SCRATCH0, ARG_PARTIALS, ARG_COUNTER, ARG_COL_COUNTERS, ARG_PEER_MB, ARG_PEER_EPOCH = -1, -2, -100, -101, -102, -103, -104
 COL_COUNTERS = np.zeros(4096, np.uint32)  # persistent and self-resetting, like the runtime's
 FOLD_PARTIALS = 148 * 4 * 2
 
@@ -91,6 +91,8 @@ def _call(lib, i, li, args, out, scratch, partials, counter):
             ptrs[j] = counter.ctypes.data
         elif a == ARG_COL_COUNTERS:
             ptrs[j] = COL_COUNTERS.ctypes.data
+        elif a in (ARG_PEER_MB, ARG_PEER_EPOCH):
+            ptrs[j] = 0  # no communicator on the host: the reduction stores its own values (mb_ == nullptr)
         else:
             ptrs[j] = scratch[ARG_SCRATCH0 - a].ctypes.data
     fn = getattr(lib, f"emu_launch_{i}")

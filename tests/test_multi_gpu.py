@@ -153,6 +153,15 @@ def _api_level(cuda, comm, sharding, ref, rank, world):
         assert np.array_equal(row.flatArray(), i64[start : start + n].sum(axis=1).astype(np.float32))  # stays sharded: no exchange
         assert np.array_equal(row.gather().flatArray(), i64.sum(axis=1).astype(np.float32))
         assert np.array_equal((x * x - x).gather().flatArray().reshape(rows, cols), full * full - full)  # elementwise: no exchange until gathered
+        # compute step + collective = ONE kernel on the peer route (the reduction's final stage pushes / collects over the mailboxes itself),
+        # reduction + collective call on the NCCL route; same values either way (checked above), here the launch counts
+        counts = []
+        for build in (lambda: comm.fold(x.split(0)), lambda: comm.fold(x.split(1)).gather(), lambda: x.sum()):
+            s0 = cuda.stats()["device_kernels"]
+            build().flatArray()
+            counts.append(cuda.stats()["device_kernels"] - s0)
+        if route:
+            assert counts == [1, 1, 1], counts
     comm.route_peer(True)
     for (m, k, nn) in ((512, 256, 512), (2 * 200, 96, 132), (1024, 512, 1024)):
         a = (np.floor(ref.random_buffer(m * k, 9) * 9) - 4).astype(np.float32).reshape(m, k)
