@@ -2102,7 +2102,7 @@ int cc_reduce_sum_allreduce(cc_buffer in, uint64_t n_floats, cc_buffer out, cons
     op.label = "sum + all-reduce over NVLink (one kernel)";
     op.bytes = n_floats * 4 + 4;
     op_begin(op, waits, n_waits);
-    if (n.comm && n.peer_enabled) {
+    if (n.comm && n.peer_enabled && !rt().capture) {  // (an epoch captured into a graph would be replayed: NCCL inside captures)
       // ONE kernel: local reduction + all-reduce of its result over NVLink peer memory
       launch_reduce_sum_allreduce((const float*)ib->ptr, n_floats, (float*)ob->ptr, (float*)sc->ptr, (unsigned*)r.reduce_counter, r.info.sm_count,
                                   n.mb, ++n.epoch, (cudaStream_t)op.cu());
@@ -2372,6 +2372,7 @@ int cc_matmul_3xtf32_allgather(cc_buffer a, cc_buffer b, cc_buffer gathered, int
     Buffer* bb = as_buffer(b);
     Buffer* gb = as_buffer(gathered);
     CC_REQUIRE(nc.comm && nc.peer_mapped, CC_ERR_ILLEGAL_ARGUMENT, "cc_matmul_3xtf32_allgather needs cc_comm_enable_peer");
+    CC_REQUIRE(!r.capture, CC_ERR_UNSUPPORTED, "the fused all-gather's flag barriers carry an epoch: not inside a graph capture");
     CC_REQUIRE((int)gb->peers.size() == nc.n_ranks || gb->mc_ptr, CC_ERR_ILLEGAL_ARGUMENT, "`gathered` must come from cc_comm_symmetric_alloc");
     CC_REQUIRE(m_shard > 0 && n > 0 && k > 0 && n % 4 == 0, CC_ERR_UNSUPPORTED, "fused all-gather needs N %% 4 == 0 (got %lld x %lld x %lld)",
                (long long)m_shard, (long long)n, (long long)k);
@@ -2440,7 +2441,7 @@ int cc_allreduce_sum(cc_buffer buf, uint64_t n_floats, const cc_event* waits, in
     op.label = "all-reduce";
     op.bytes = n_floats * 4;
     op_begin(op, waits, n_waits);
-    if (n.comm && n.peer_enabled && n_floats <= (uint64_t)kPeerCapFloats) {
+    if (n.comm && n.peer_enabled && !rt().capture && n_floats <= (uint64_t)kPeerCapFloats) {  // (a captured epoch would be replayed)
       launch_peer_allreduce((float*)b->ptr, n_floats, n.mb, ++n.epoch, (cudaStream_t)op.cu());
       rt().stats.device_kernels++;
     } else if (n.comm) {
@@ -2462,7 +2463,7 @@ int cc_allgather(cc_buffer send, cc_buffer recv, uint64_t n_per_rank, const cc_e
     op.label = "all-gather";
     op.bytes = n_per_rank * 4 * (uint64_t)ranks;
     op_begin(op, waits, n_waits);
-    if (n.comm && n.peer_enabled && n_per_rank <= (uint64_t)kPeerCapFloats) {
+    if (n.comm && n.peer_enabled && !rt().capture && n_per_rank <= (uint64_t)kPeerCapFloats) {
       // small blocks (the row sums of a sharded tensor): one kernel over the NVLink mailboxes instead of an NCCL call
       launch_peer_allgather((const float*)s->ptr, (float*)d->ptr, n_per_rank, n.mb, ++n.epoch, (cudaStream_t)op.cu());
       rt().stats.device_kernels++;
@@ -2717,7 +2718,7 @@ int cc_shard_launch_allgather(cc_kernel h, const cc_buffer* args, int n_args, cc
                (unsigned long long)gb->n_floats, ranks, (unsigned long long)n);
     M = p.M, N = p.N, K = p.K;
     fuse = p.kind == PLAN_CONTRACTION && !p.gathered_panels && n_args == 2 && nc.comm && nc.peer_mapped && nc.peer_enabled &&
-           ((int)gb->peers.size() == nc.n_ranks || gb->mc_ptr) && N % 4 == 0;
+           ((int)gb->peers.size() == nc.n_ranks || gb->mc_ptr) && N % 4 == 0 && !rt().capture;
     // a row-owner reduction gathers its own outputs over the peer mailboxes (lane 0 of every output): one launch
     same_kernel = p.collective == 2 && nc.comm && nc.n_ranks > 1 && nc.peer_enabled && nc.mb_dev && n <= (uint64_t)kPeerCapFloats && !rt().capture;
   });
