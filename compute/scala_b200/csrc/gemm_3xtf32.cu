@@ -707,6 +707,12 @@ __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+// Programmatic dependent launch inside one product (split B -> contraction -> sum of the K splits): a kernel launched with the attribute
+// may become resident while its predecessor still runs; it announces its own dependents at once and waits for the predecessor's memory
+// before it touches any (CC_GEMM_PDL=0 launches plainly). Saves the launch gaps of small products; nothing at 8192^3.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 template <int BN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TA_THREADS, 1)
 gemm_3xtf32_tmema_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
@@ -772,6 +778,8 @@ gemm_3xtf32_tmema_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  pdl_launch_dependents();
+  pdl_wait();  // (barriers, tensor memory and the tensor maps are set up; from here on global memory is read and written)
 
   if (warp == 0) {
     // ===== TMA producer (both CTAs): own 128 rows of the original A, own half of the B^T hi / lo panels =====
@@ -966,6 +974,8 @@ __global__ void __launch_bounds__(256) split_transpose_b_kernel(const float* __r
                                                                 int N, int Kp) {
   __shared__ float th[32][33];
   __shared__ float tl[32][33];
+  pdl_launch_dependents();
+  pdl_wait();
   const int n0 = blockIdx.x * 32, k0 = blockIdx.y * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
 #pragma unroll
@@ -1162,6 +1172,8 @@ void launch_pair(const GemmWorkspace& ws, float* c, int64_t m, int64_t n, int64_
 
 // C = sum over s of partial[s] (fixed order: deterministic), 128-bit vectors; n is a multiple of 4 or the tail runs scalar
 __global__ void __launch_bounds__(256) sum_k_splits_kernel(const float* __restrict__ partials, float* __restrict__ c, size_t n, int splits, size_t stride) {
+  pdl_launch_dependents();
+  pdl_wait();
   const size_t nvec = n / 4;
   for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < nvec; i += (size_t)gridDim.x * 256) {
     float4 acc = __ldcs(reinterpret_cast<const float4*>(partials) + i);
@@ -1177,6 +1189,30 @@ __global__ void __launch_bounds__(256) sum_k_splits_kernel(const float* __restri
     for (int sp = 1; sp < splits; ++sp) acc += partials[(size_t)sp * stride + i];
     c[i] = acc;
   }
+}
+
+bool gemm_pdl() {
+  static const bool on = [] {
+    const char* e = getenv("CC_GEMM_PDL");
+    return e ? atoi(e) != 0 : true;
+  }();
+  return on;
+}
+// launch with programmatic stream serialisation allowed (the kernel must call pdl_wait() before it touches global memory)
+template <class... Params, class... Args>
+void launch_dependent(void (*kernel)(Params...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr{};
+  attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr.val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = &attr;
+  cfg.numAttrs = gemm_pdl() ? 1 : 0;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, static_cast<Params>(args)...);
+  if (e != cudaSuccess) fail(CC_ERR_CUDA, strprintf("cudaLaunchKernelEx: %s", cudaGetErrorString(e)));
 }
 
 // config 1024: CTA pairs, 256 x 256 tiles (one accumulator), A read as the original fp32 matrix and split inside the kernel (through tensor
@@ -1208,18 +1244,18 @@ int launch_tmema(const float* a, const GemmWorkspace& ws, float* c, int64_t m, i
     pairs = tiles_pm * tiles_n * splits;
     if (pairs > sm_count / 2) pairs = sm_count / 2;
     const size_t out_floats = (size_t)m * (size_t)n;
-    gemm_3xtf32_tmema_kernel<BN><<<2 * pairs, TA_THREADS, SMEM, stream>>>(ma, mb_hi, mb_lo, ws.k_split_partials, (int)m, (int)n, (int)(kbs * BK), tiles_pm, tiles_n,
-                                                                          (int)kb_begin, 0, splits, (long long)out_floats);
+    launch_dependent(gemm_3xtf32_tmema_kernel<BN>, dim3((unsigned)(2 * pairs)), dim3(TA_THREADS), SMEM, stream, ma, mb_hi, mb_lo, ws.k_split_partials, (int)m, (int)n,
+                     (int)(kbs * BK), tiles_pm, tiles_n, (int)kb_begin, 0, splits, (long long)out_floats);
     check_launch("gemm_3xtf32 (CTA pairs, A through tensor memory, split K)");
     size_t blocks = (out_floats / 4 + 255) / 256;
     if (blocks > (size_t)sm_count * 8) blocks = (size_t)sm_count * 8;
     if (blocks == 0) blocks = 1;
-    sum_k_splits_kernel<<<(unsigned)blocks, 256, 0, stream>>>(ws.k_split_partials, c, out_floats, splits, out_floats);
+    launch_dependent(sum_k_splits_kernel, dim3((unsigned)blocks), dim3(256), 0, stream, (const float*)ws.k_split_partials, c, out_floats, splits, out_floats);
     check_launch("sum_k_splits");
     return 2;
   }
-  gemm_3xtf32_tmema_kernel<BN><<<2 * pairs, TA_THREADS, SMEM, stream>>>(ma, mb_hi, mb_lo, c, (int)m, (int)n, (int)(kbs * BK), tiles_pm, tiles_n, (int)kb_begin,
-                                                                        kb_begin > 0 ? 1 : 0, 1, 0ll);
+  launch_dependent(gemm_3xtf32_tmema_kernel<BN>, dim3((unsigned)(2 * pairs)), dim3(TA_THREADS), SMEM, stream, ma, mb_hi, mb_lo, c, (int)m, (int)n, (int)(kbs * BK), tiles_pm,
+                   tiles_n, (int)kb_begin, kb_begin > 0 ? 1 : 0, 1, 0ll);
   check_launch("gemm_3xtf32 (CTA pairs, A through tensor memory)");
   return 1;
 }
@@ -1241,7 +1277,7 @@ int launch_pipeline(const float* a, const float* b, float* c, int64_t m, int64_t
     check_launch("split_a");
   }
   if (!b_panels_ready) {
-    split_transpose_b_kernel<<<dim3((unsigned)((n + 31) / 32), (unsigned)(kp / 32)), 256, 0, stream>>>(b, ws.bt_hi, ws.bt_lo, (int)k, (int)n, (int)kp);
+    launch_dependent(split_transpose_b_kernel, dim3((unsigned)((n + 31) / 32), (unsigned)(kp / 32)), dim3(256), 0, stream, b, ws.bt_hi, ws.bt_lo, (int)k, (int)n, (int)kp);
     check_launch("split_transpose_b");
   }
   // The tensor core accumulates the 3 * K / 8 partial products of an output in fp32 with TRUNCATION, so the error of one launch grows
