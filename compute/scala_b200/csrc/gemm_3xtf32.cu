@@ -171,6 +171,12 @@ struct GatherMaps {
   int rank;
 };
 
+// Programmatic dependent launch inside one product (split A -> split B -> contraction -> sum of the K splits): a kernel launched with the attribute
+// may become resident while its predecessor still runs; it announces its own dependents at once and waits for the predecessor's memory
+// before it touches any (CC_GEMM_PDL=0 launches plainly). Saves the launch gaps of small products; nothing at 8192^3.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 template <int BN, bool kGather>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
@@ -227,6 +233,8 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  pdl_launch_dependents();
+  pdl_wait();  // (set-up done; from here on global memory is read and written)
 
   if (warp == 0) {
     // ===== TMA producer =====
@@ -492,6 +500,8 @@ gemm_3xtf32_pair_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __gri
   cluster_sync_all();  // both CTAs' barriers are initialised before anybody signals across
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  pdl_launch_dependents();
+  pdl_wait();  // (set-up done; from here on global memory is read and written)
 
   if (warp == 0) {
     // ===== TMA producer (both CTAs): own 128 rows of A_hi / A_lo, own 128 columns of B_hi / B_lo =====
@@ -706,12 +716,6 @@ __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r
       : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-
-// Programmatic dependent launch inside one product (split B -> contraction -> sum of the K splits): a kernel launched with the attribute
-// may become resident while its predecessor still runs; it announces its own dependents at once and waits for the predecessor's memory
-// before it touches any (CC_GEMM_PDL=0 launches plainly). Saves the launch gaps of small products; nothing at 8192^3.
-__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
-__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 template <int BN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TA_THREADS, 1)
@@ -942,6 +946,8 @@ gemm_3xtf32_tmema_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
 
 // A [M,K] row-major -> A_hi / A_lo [M,Kp] (Kp % 32 == 0, columns >= K zero). One thread per 4 output floats.
 __global__ void __launch_bounds__(256) split_a_kernel(const float* __restrict__ a, float* __restrict__ hi, float* __restrict__ lo, int M, int K, int Kp) {
+  pdl_launch_dependents();
+  pdl_wait();
   const size_t vec_per_row = (size_t)Kp / 4;
   const size_t nvec = (size_t)M * vec_per_row;
   const size_t stride = (size_t)gridDim.x * 256;
@@ -1122,6 +1128,35 @@ bool tmema_default() {
   return on;
 }
 
+bool gemm_pdl() {
+  static const bool on = [] {
+    const char* e = getenv("CC_GEMM_PDL");
+    return e ? atoi(e) != 0 : true;
+  }();
+  return on;
+}
+// launch with programmatic stream serialisation allowed (the kernel must call pdl_wait() before it touches global memory)
+template <class... Params, class... Args>
+void launch_dependent_if(bool dependent, void (*kernel)(Params...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr{};
+  attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr.val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = &attr;
+  cfg.numAttrs = dependent && gemm_pdl() ? 1 : 0;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, static_cast<Params>(args)...);
+  if (e != cudaSuccess) fail(CC_ERR_CUDA, strprintf("cudaLaunchKernelEx: %s", cudaGetErrorString(e)));
+}
+
+template <class... Params, class... Args>
+void launch_dependent(void (*kernel)(Params...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  launch_dependent_if(true, kernel, grid, block, smem, stream, std::forward<Args>(args)...);
+}
+
 template <int BN, bool kGather>
 void launch_main(const GemmWorkspace& ws, float* c, int64_t m, int64_t n, int64_t kp, int sm_count, TensorMapEncodeFn encode, cudaStream_t stream,
                  const GatherMaps& gather, int64_t kb_begin = 0, int64_t kb_count = -1) {
@@ -1141,8 +1176,9 @@ void launch_main(const GemmWorkspace& ws, float* c, int64_t m, int64_t n, int64_
   int grid = tiles_m * tiles_n;
   if (grid > sm_count) grid = sm_count;
   const int64_t kbs = kb_count < 0 ? kp / BK : kb_count;
-  gemm_3xtf32_kernel<BN, kGather><<<grid, GEMM_THREADS, SMEM, stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, c, (int)m, (int)n, (int)(kbs * BK), tiles_m, tiles_n, gather,
-                                                                        (int)kb_begin, kb_begin > 0 ? 1 : 0);
+  // (the gather variant follows a cross-rank flag barrier: it is launched plainly)
+  launch_dependent_if(!kGather, gemm_3xtf32_kernel<BN, kGather>, dim3((unsigned)grid), dim3(GEMM_THREADS), SMEM, stream, ma_hi, ma_lo, mb_hi, mb_lo, c, (int)m, (int)n,
+                      (int)(kbs * BK), tiles_m, tiles_n, gather, (int)kb_begin, kb_begin > 0 ? 1 : 0);
   check_launch(kGather ? "gemm_3xtf32 (all-gather epilogue)" : "gemm_3xtf32");
 }
 
@@ -1165,8 +1201,8 @@ void launch_pair(const GemmWorkspace& ws, float* c, int64_t m, int64_t n, int64_
   int pairs = tiles_pm * tiles_n;
   if (pairs > sm_count / 2) pairs = sm_count / 2;
   const int64_t kbs = kb_count < 0 ? kp / BK : kb_count;
-  gemm_3xtf32_pair_kernel<kGather><<<2 * pairs, GEMM_THREADS, SMEM, stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, c, (int)m, (int)n, (int)(kbs * BK), tiles_pm, tiles_n,
-                                                                              gather, (int)kb_begin, kb_begin > 0 ? 1 : 0);
+  launch_dependent_if(!kGather, gemm_3xtf32_pair_kernel<kGather>, dim3((unsigned)(2 * pairs)), dim3(GEMM_THREADS), SMEM, stream, ma_hi, ma_lo, mb_hi, mb_lo, c, (int)m, (int)n,
+                      (int)(kbs * BK), tiles_pm, tiles_n, gather, (int)kb_begin, kb_begin > 0 ? 1 : 0);
   check_launch(kGather ? "gemm_3xtf32 (CTA pairs, all-gather epilogue)" : "gemm_3xtf32 (CTA pairs)");
 }
 
@@ -1189,30 +1225,6 @@ __global__ void __launch_bounds__(256) sum_k_splits_kernel(const float* __restri
     for (int sp = 1; sp < splits; ++sp) acc += partials[(size_t)sp * stride + i];
     c[i] = acc;
   }
-}
-
-bool gemm_pdl() {
-  static const bool on = [] {
-    const char* e = getenv("CC_GEMM_PDL");
-    return e ? atoi(e) != 0 : true;
-  }();
-  return on;
-}
-// launch with programmatic stream serialisation allowed (the kernel must call pdl_wait() before it touches global memory)
-template <class... Params, class... Args>
-void launch_dependent(void (*kernel)(Params...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = grid;
-  cfg.blockDim = block;
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = stream;
-  cudaLaunchAttribute attr{};
-  attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr.val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = &attr;
-  cfg.numAttrs = gemm_pdl() ? 1 : 0;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, static_cast<Params>(args)...);
-  if (e != cudaSuccess) fail(CC_ERR_CUDA, strprintf("cudaLaunchKernelEx: %s", cudaGetErrorString(e)));
 }
 
 // config 1024: CTA pairs, 256 x 256 tiles (one accumulator), A read as the original fp32 matrix and split inside the kernel (through tensor
@@ -1273,7 +1285,7 @@ int launch_pipeline(const float* a, const float* b, float* c, int64_t m, int64_t
   size_t blocks = (nvec + 255) / 256;
   if (blocks > (size_t)sm_count * 8) blocks = (size_t)sm_count * 8;
   if (split_a_needed) {
-    split_a_kernel<<<(unsigned)blocks, 256, 0, stream>>>(a, ws.a_hi, ws.a_lo, (int)m, (int)k, (int)kp);
+    launch_dependent(split_a_kernel, dim3((unsigned)blocks), dim3(256), 0, stream, a, ws.a_hi, ws.a_lo, (int)m, (int)k, (int)kp);
     check_launch("split_a");
   }
   if (!b_panels_ready) {
