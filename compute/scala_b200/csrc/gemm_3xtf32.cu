@@ -987,7 +987,9 @@ __global__ void __launch_bounds__(256) split_transpose_b_kernel(const float* __r
 #pragma unroll
   for (int r = 0; r < 32; r += 8) {
     const int k = k0 + ty + r, n = n0 + tx;
-    const float x = (k < K && n < N) ? b[(size_t)k * N + n] : 0.f;
+    // (a coherent streaming load, not the ld.global.nc a `const __restrict__` read may become: this grid can be resident — waiting in
+    // pdl_wait — while the producer of B is still writing it)
+    const float x = (k < K && n < N) ? __ldcs(b + (size_t)k * N + n) : 0.f;
     float h, l;
     split_tf32(x, h, l);
     th[ty + r][tx] = h;
@@ -1221,8 +1223,8 @@ __global__ void __launch_bounds__(256) sum_k_splits_kernel(const float* __restri
   }
   if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
     const size_t i = (n & ~(size_t)3) + threadIdx.x;
-    float acc = partials[i];
-    for (int sp = 1; sp < splits; ++sp) acc += partials[(size_t)sp * stride + i];
+    float acc = __ldcs(partials + i);
+    for (int sp = 1; sp < splits; ++sp) acc += __ldcs(partials + (size_t)sp * stride + i);
     c[i] = acc;
   }
 }
