@@ -242,6 +242,35 @@ def test_split_k_on_small_products_is_exact_and_deterministic(cuda, monkeypatch,
         assert np.array_equal(first.view(np.uint32), run_matmul(cuda, a, b).view(np.uint32))
 
 
+@pytest.mark.parametrize("size", [1024, 768, 320])
+def test_products_chained_through_their_outputs(cuda, size):
+    """X <- X · P twenty times with P a permutation matrix and X, P re-written between products: every kernel of a product (split A, split B,
+    contraction, sum of the K splits) is launched as a programmatic dependent of the one before it, so each may be resident while its input
+    is still being written by its predecessor — the chain must still see exactly the previous product (1024: split K on the
+    tensor-memory-A kernel; 768 / 320: operand panels + single-CTA tiles). Operand cache off: B is split again for every product."""
+    rng = np.random.default_rng(size)
+    x = rng.integers(-7, 8, (size, size)).astype(np.float32)
+    perms = [rng.permutation(size) for _ in range(4)]
+    cuda.set_operand_cache(False)
+    try:
+        X, Y = cuda.Buffer.from_host(x), cuda.Buffer.alloc(size * size)
+        Ps = []
+        for p in perms:
+            m = np.zeros((size, size), np.float32)
+            m[p, np.arange(size)] = 1.0  # (X · P)[:, j] = X[:, p[j]]
+            Ps.append(cuda.Buffer.from_host(m))
+        want = x
+        for step in range(20):
+            cuda.matmul_3xtf32(X, Ps[step % 4], Y, size, size, size)
+            X, Y = Y, X
+            want = want[:, perms[step % 4]]
+        assert np.array_equal(X.to_host(size * size).reshape(size, size), want)
+        for b in [X, Y] + Ps:
+            b.release()
+    finally:
+        cuda.set_operand_cache(True)
+
+
 def test_pattern_lowers_to_tcgen05(cuda):
     """matmul written the way benchmarks.scala:188-191 writes it runs on the tensor cores and never materialises i*j*k"""
     T = cuda.Tensor
