@@ -252,7 +252,7 @@ def side_configs(cuda, hbm_peak: float, tf_peak: float) -> dict:
     T = cuda.Tensor
     out = {}
 
-    def measure(name, build, alg_bytes, steps=10, flops=None, warmup=3):
+    def measure(name, build, alg_bytes, steps=10, flops=None, warmup=3, best_of=1):
         try:
             expr = build()
             k = expr.compile()
@@ -263,8 +263,15 @@ def side_configs(cuda, hbm_peak: float, tf_peak: float) -> dict:
                 expr.doBuffer().release()
 
             ms, launches, _, _ = time_steps(cuda, step, steps, warmup)
-            per = ms / steps
+            windows = [ms / steps]
+            for _ in range(best_of - 1):  # (a host-bound loop: other processes on the box show up as slow windows)
+                ms, launches, _, _ = time_steps(cuda, step, steps, 0)
+                windows.append(ms / steps)
+            per = min(windows)
             rec = {"ms": per, "kernels_per_step": launches / steps, "plan": kind}
+            if best_of > 1:
+                rec["windows_ms"] = windows
+                rec["note"] = f"best of {best_of} windows of {steps} steps (bound by the host's submission rate, not by the kernel)"
             if flops:
                 rec["tflops"] = flops / per / 1e9
                 rec["frac_of_3xtf32_peak"] = rec["tflops"] / tf_peak
@@ -280,7 +287,7 @@ def side_configs(cuda, hbm_peak: float, tf_peak: float) -> dict:
     # a 5 us step: enough warm-up and steps that the clock ramp after the idle CPU-baseline phase is not what gets timed
     # (--short-side: a handful of steps only, so that an ncu launch list of the whole run stays short)
     n_c1 = 5 if SHORT_SIDE else 2000
-    measure("C1 tanh(a*b+c) 1024^2", lambda: T.tanh(a1 * b1 + c1), 16 * n1 * n1, steps=n_c1, warmup=n_c1)
+    measure("C1 tanh(a*b+c) 1024^2", lambda: T.tanh(a1 * b1 + c1), 16 * n1 * n1, steps=n_c1, warmup=n_c1, best_of=1 if SHORT_SIDE else 3)
     # one call = one launch is bound by the host's submission rate (~3 us per step for a ~2 us kernel): the same loop captured ONCE into a
     # CUDA graph (cc_graph_begin / cc_graph_end) and replayed with one driver call per 50 evaluations shows the kernel itself
     try:
