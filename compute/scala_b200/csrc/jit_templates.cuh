@@ -130,7 +130,9 @@ __device__ __forceinline__ void cc_split_tf32(float x, float& hi, float& lo) {
 
 // D (16 x 8, fp32) += A (16 x 8, row) * B (8 x 8, col) on the warp-level tensor-core path. Fragments (g = lane / 4, t = lane % 4):
 // a = {A[g][t], A[g + 8][t], A[g][t + 4], A[g + 8][t + 4]}, b = {B[t][g], B[t + 4][g]}, c = {C[g][2t], C[g][2t + 1], C[g + 8][2t], C[g + 8][2t + 1]}
-#ifndef CC_HOST_EMULATION
+#ifdef CC_HOST_EMULATION
+__device__ __forceinline__ void cc_mma_tf32_16x8x8(float (&c)[4], const unsigned (&a)[4], const unsigned (&b)[2]) { cc_emu_mma_tf32_16x8x8(c, a, b); }
+#else
 __device__ __forceinline__ void cc_mma_tf32_16x8x8(float (&c)[4], const unsigned (&a)[4], const unsigned (&b)[2]) {
   asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
                : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])

@@ -40,6 +40,10 @@ struct float2 {
   float x, y;
 };
 inline float2 make_float2(float x, float y) { return float2{x, y}; }
+struct uint4 {
+  unsigned x, y, z, w;
+};
+inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) { return uint4{x, y, z, w}; }
 
 inline thread_local uint3_ threadIdx, blockIdx;
 inline uint3_ blockDim, gridDim;
@@ -86,6 +90,39 @@ inline float __shfl_xor_sync(unsigned, float v, int lane_mask) {
 }
 inline unsigned atomicAdd(unsigned* p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
 
+// mma.sync.m16n8k8 (row x col, fp32 accumulate) for the 32 host threads of a warp: every lane publishes its fragments, then computes its own
+// four accumulator elements from the whole tile. Fragment layout as in jit_templates.cuh (g = lane / 4, t = lane % 4):
+// a = {A[g][t], A[g+8][t], A[g][t+4], A[g+8][t+4]}, b = {B[t][g], B[t+4][g]}, c = {C[g][2t], C[g][2t+1], C[g+8][2t], C[g+8][2t+1]}.
+// Products in double, accumulated in k order and rounded once per call: exact on the exactly representable data the emulator tests use.
+namespace emu {
+inline unsigned mma_buf[1024][6];
+}
+inline void cc_emu_mma_tf32_16x8x8(float (&c)[4], const unsigned (&a)[4], const unsigned (&b)[2]) {
+  const int t_ = emu::linear_tid(), warp0 = t_ / 32 * 32, lane = t_ % 32, g = lane / 4, t = lane % 4;
+  for (int i = 0; i < 4; ++i) emu::mma_buf[t_][i] = a[i];
+  for (int i = 0; i < 2; ++i) emu::mma_buf[t_][4 + i] = b[i];
+  emu::warp_barriers[(size_t)(t_ / 32)]->arrive_and_wait();
+  auto A = [&](int row, int k) {  // row in [0, 16), k in [0, 8)
+    unsigned u = emu::mma_buf[warp0 + (row % 8) * 4 + (k % 4)][(row >= 8 ? 1 : 0) + (k >= 4 ? 2 : 0)];
+    float f;
+    memcpy(&f, &u, 4);
+    return (double)f;
+  };
+  auto B = [&](int k, int n) {  // k in [0, 8), n in [0, 8)
+    unsigned u = emu::mma_buf[warp0 + n * 4 + (k % 4)][4 + (k >= 4 ? 1 : 0)];
+    float f;
+    memcpy(&f, &u, 4);
+    return (double)f;
+  };
+  for (int i = 0; i < 4; ++i) {
+    const int row = g + (i >= 2 ? 8 : 0), col = 2 * t + (i & 1);
+    double acc = (double)c[i];
+    for (int k = 0; k < 8; ++k) acc += A(row, k) * B(k, col);
+    c[i] = (float)acc;
+  }
+  emu::warp_barriers[(size_t)(t_ / 32)]->arrive_and_wait();
+}
+
 inline float __uint_as_float(unsigned u) {
   float f;
   memcpy(&f, &u, 4);
@@ -113,5 +150,6 @@ inline T __ldcg(const T* p) { return *p; }
 template <class T>
 inline T __ldcv(const T* p) { return *p; }
 inline void __stcs(float* p, float v) { *p = v; }
+inline void __stcs(float2* p, float2 v) { *p = v; }
 using std::min;
 using std::max;

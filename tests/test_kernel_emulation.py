@@ -255,6 +255,23 @@ def test_tile_owner_small_trailing_output_dimension(monkeypatch):
     cuda.kernel_cache_clear()
 
 
+def test_small_n_contraction_on_emulated_warp_mmas():
+    """the small-N contraction kernel (warp-level m16n8k8 MMAs, B as TF32 hi / lo fragments in registers or shared memory, A gathered through
+    its affine map) with the MMA emulated for the 32 host threads of a warp: the implicit im2col (window offsets, padding at the image
+    border), K padded to a multiple of 8, rows not a multiple of 16, the bias epilogue on the accumulator fragments, both B placements and
+    both A load widths — exact on exactly representable data"""
+    check(lambda B, leaf: convolute(B, leaf([4, 32, 32, 8], 1), leaf([3, 3, 8, 8], 2), leaf([8], 3)), "small-N contraction 4096x8x72", 1)         # B in registers, scalar A loads
+    check(lambda B, leaf: convolute(B, leaf([1, 64, 65, 4], 1), leaf([3, 3, 4, 16], 2), leaf([16], 3)), "small-N contraction 4160x16x36", 1)      # K = 36 padded to 40, two n tiles: pair loads
+    check(lambda B, leaf: convolute(B, leaf([1, 65, 64, 16], 1), leaf([3, 3, 16, 16], 2), leaf([16], 3)), "B in shared memory", 1)               # 36 fragments
+
+    def skinny(B, leaf, m=4101, k=28, n=12):  # rows % 16 != 0, n % 8 != 0, k % 8 != 0; A stored transposed and shifted along k with a padding
+        at, b = leaf([k, m], 1, padding=2.5), leaf([k, n], 2)
+        a = at.permute([1, 0]).translate([0, 1])  # [m, k]: column 0 is the padding
+        prod = a.broadcast([m, k, n]) * b.reshape([1, k, n]).broadcast([m, k, n])
+        return chain(prod.split(1))
+    check(skinny, "small-N contraction 4101x12x28", 1)
+
+
 def test_matmul1_join_of_folds_rerolled_twice():
     """benchmarks.scala:176-187: the result's columns are separate left folds over t of A[:, t] * B[t, c] (a scalar broadcast), joined:
     the join is re-rolled into the output dimension c and every fold into a reduction over t -- one kernel, one reduction"""
