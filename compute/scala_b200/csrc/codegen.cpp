@@ -2179,8 +2179,9 @@ bool try_small_n_mma(Plan& plan, const Program& p, int n_args, int la, int lb, i
   e("  for (%s tile = (%s)blockIdx.x * 4 + (threadIdx.x >> 5); tile < (%s)%lld; tile += (%s)gridDim.x * 4) {\n", IDX, IDX, IDX, (long long)MT, IDX);
   e("    const %s m0 = tile * 16 + gid, m1 = m0 + 8;\n", IDX);
   e("    float c[%lld][4];\n    #pragma unroll\n    for (int nt = 0; nt < %lld; ++nt) c[nt][0] = c[nt][1] = c[nt][2] = c[nt][3] = 0.f;\n", (long long)NT, (long long)NT);
-  // A for up to 8 k steps is fetched before the first of them is used: the loads of a tile are then in flight together instead of
-  // two at a time in front of their MMAs (timed: 3 x 3 / depth 8 went 6.7 -> 7.9 us with pair loads issued just in time)
+  // A is written as "fetch up to 8 k steps, then use them"; ptxas sinks the loads to their uses regardless (two k steps stay in flight).
+  // Two tiles per warp at a time (twice the loads in flight, two MMA chains) was timed on the 3 x 3 / depth 8 convolution: 6.74 -> 6.88 us
+  // at 126 registers — not kept; what is left above the ~2.7 us launch floor is the legacy MMA rate and the scattered 32-byte pixel reads.
   const int64_t KC = std::min<int64_t>(KS, 8);
   e("    #pragma unroll\n    for (int kc = 0; kc < %lld; kc += %lld) {\n", (long long)KS, (long long)KC);
   if (a_pair) {
