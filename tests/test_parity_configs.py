@@ -603,6 +603,27 @@ def test_small_n_contraction_over_views(cuda, m, k, n):
     assert np.array_equal(plain.flatArray().reshape(m, n), (a.astype(np.float64) @ b.astype(np.float64)).astype(np.float32))
 
 
+@pytest.mark.parametrize("m,k,f,fold", [(20000, 16, 8, "sum"), (19000, 12, 16, "max"), (40000, 20, 4, "sum")])
+def test_tile_owner_reductions_that_are_not_products(cuda, m, k, f, fold):
+    """distances of many points to a few centres, written as broadcast / split / fold like the matmul pattern but with |x - c| (or its max)
+    instead of x * c: not a contraction, so the re-rolled reduction's tile owner runs — a thread owns all f outputs of a point, the point's
+    coordinates are fetched as vectors along the reduction and shared by the f centres. Exact on exactly representable data."""
+    T = cuda.Tensor
+    rng = np.random.default_rng(m + k + f)
+    x = rng.integers(-9, 10, (m, k)).astype(np.float32)
+    c = rng.integers(-9, 10, (k, f)).astype(np.float32)
+    d = T.abs(T(x).broadcast([m, k, f]) - T(c).reshape([1, k, f]).broadcast([m, k, f]))
+    parts = d.split(1)
+    acc = parts[0]
+    for p in parts[1:]:
+        acc = acc + p if fold == "sum" else T.max(acc, p)
+    kern = acc.compile()
+    assert kern.info.kind == 1 and "tile owner" in kern.source, kern.source[:300]
+    diff = np.abs(x[:, :, None].astype(np.float64) - c[None, :, :].astype(np.float64))
+    want = diff.sum(axis=1) if fold == "sum" else diff.max(axis=1)
+    assert np.array_equal(acc.flatArray().reshape(m, f).astype(np.float64), want)
+
+
 @pytest.mark.parametrize("rows", [64, 4096])  # one CTA covers all of T / partials + second stage (epilogue applied there)
 def test_epilogue_around_an_axis_sum(cuda, rows):
     T = cuda.Tensor
