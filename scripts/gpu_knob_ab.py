@@ -63,6 +63,10 @@ def workloads(name, T):
         for m, k, n in ((65536, 32, 32), (65536, 8, 8), (8192, 64, 16)):
             A, B = T.randomNormal([m, k], seed=4).doCache(), T.randomNormal([k, n], seed=5).doCache()
             out.append((f"matmul {m}x{k}x{n} (split / broadcast / sum)", lambda A=A, B=B, m=m, k=k, n=n: chain((A.broadcast([m, k, n]) * B.reshape([1, k, n]).broadcast([m, k, n])).split(1)), 500))
+        # not a product of two loads: the tile owner's own territory (distances of many points to a few centres)
+        for m, k, f in ((1 << 20, 16, 8), (1 << 18, 32, 16)):
+            X, Cn = T.randomNormal([m, k], seed=6).doCache(), T.randomNormal([k, f], seed=7).doCache()
+            out.append((f"L1 distances {m} points x {k} dims -> {f} centres", lambda X=X, Cn=Cn, m=m, k=k, f=f: chain(T.abs(X.broadcast([m, k, f]) - Cn.reshape([1, k, f]).broadcast([m, k, f])).split(1)), 200))
         return out
     if name.startswith("red_p"):
         A, B = T.random([512, 64], seed=4).doCache(), T.random([64, 512], seed=5).doCache()
